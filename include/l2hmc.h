@@ -1,0 +1,176 @@
+/*
+ * l2hmc.h -- C ABI of libl2hmc.so, the B200 (sm_100a) implementation of the L2HMC
+ * augmented-leapfrog sampling path.
+ *
+ * The reference (brain-research/l2hmc, TF1/Python) has no FFI of its own; its boundary for
+ * this path is the Python call surface Dynamics / propose / tf_accept / chain_operator and the
+ * distribution energy callbacks.  Every entry point below names the
+ * reference interface it sits under (file:line into /root/reference).  The Python package
+ * l2hmc_b200 binds these with ctypes and keeps the reference's names and signatures.
+ *
+ * Conventions
+ *  - All tensors are IEEE fp32, row-major [n, D] (chain-major) or [n]; direction / accept flags
+ *    are uint8 [n].  (Reference: TF_FLOAT = tf.float32, utils/dynamics.py:27.)
+ *  - Pointers in l2hmc_transition_args and the component calls are DEVICE pointers and are
+ *    BORROWED for the duration of the (stream-ordered) call; the caller (PyTorch) owns storage.
+ *    Pointers passed to the l2hmc_set_* calls are HOST pointers and are copied before return.
+ *    l2hmc_transition_host takes HOST pointers for everything and does the copies itself.
+ *  - Every call returns an l2hmc_status; the message for the last failure on a context is
+ *    l2hmc_last_error(ctx) (l2hmc_last_error(NULL) for failures of l2hmc_create).
+ *    No C++ exception crosses this boundary; CUDA errors are captured and translated.
+ *  - A context is bound to one device and is not thread-safe.  Calls are asynchronous on the
+ *    caller's stream (cudaStream_t passed as void*; NULL = legacy default stream).
+ *  - Randomness: when v / dir / u pointers are non-NULL they are used verbatim; when NULL the
+ *    kernel draws them from Philox4x32-10 keyed by (seed, counter, global chain id), so results
+ *    do not depend on how chains are sharded over GPUs.  l2hmc_b200/philox.py is the host twin.
+ */
+#ifndef L2HMC_H_
+#define L2HMC_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct l2hmc_ctx l2hmc_ctx;
+
+typedef enum {
+  L2HMC_OK = 0,
+  L2HMC_EINVAL = 1,        /* bad argument / state (message says which)            */
+  L2HMC_ECUDA = 2,         /* a CUDA runtime call failed                           */
+  L2HMC_EUNSUPPORTED = 3,  /* shape / energy kind outside what the kernels cover   */
+  L2HMC_ENOMEM = 4
+} l2hmc_status;
+
+/* utils/distributions.py energy closures that the kernels evaluate analytically. */
+typedef enum {
+  L2HMC_ENERGY_NONE = -1,
+  L2HMC_ENERGY_GAUSSIAN = 0,  /* Gaussian.get_energy_function       utils/distributions.py:50-57   */
+  L2HMC_ENERGY_GMM = 1,       /* GMM.get_energy_function            utils/distributions.py:125-134 */
+  L2HMC_ENERGY_ROUGHWELL = 2, /* RoughWell.get_energy_function      utils/distributions.py:90-97   */
+  L2HMC_ENERGY_FUNNEL = 3     /* GaussianFunnel.get_energy_function utils/distributions.py:161-180 */
+} l2hmc_energy_kind;
+
+typedef enum { L2HMC_XNET = 0, L2HMC_VNET = 1 } l2hmc_net_id; /* utils/dynamics.py:78-79 */
+
+typedef enum {
+  L2HMC_DIR_FORWARD = 0,   /* Dynamics.forward   utils/dynamics.py:246-272                       */
+  L2HMC_DIR_BACKWARD = 1,  /* Dynamics.backward  utils/dynamics.py:274-300                       */
+  L2HMC_DIR_PER_CHAIN = 2, /* propose: dir[n] given (1 = forward)  utils/sampler.py:34-44        */
+  L2HMC_DIR_RANDOM = 3     /* propose: direction bit drawn in-kernel (Philox)                    */
+} l2hmc_dir_mode;
+
+typedef enum {
+  L2HMC_KERNEL_AUTO = 0,
+  L2HMC_KERNEL_TILE = 1,   /* generic fp32-FMA tile kernel (any D <= 64, H <= 128)               */
+  L2HMC_KERNEL_SMALL = 2,  /* one chain per thread, nets in registers (D <= 4, H <= 16)          */
+  L2HMC_KERNEL_TC = 3      /* tcgen05 3xTF32 tensor-core kernel                                  */
+} l2hmc_kernel_kind;
+
+/* Dynamics.__init__(x_dim, energy_function, T, eps, hmc, net_factory, ...)  utils/dynamics.py:35-81 */
+typedef struct {
+  int32_t x_dim;   /* D                                                                          */
+  int32_t width;   /* H, hidden width of the S/T/Q nets (ignored when hmc != 0)                  */
+  int32_t T;       /* leapfrog steps per trajectory (reference default 25)                       */
+  int32_t hmc;     /* 1: both nets return zeros (utils/dynamics.py:73-76)                        */
+  int32_t device;  /* CUDA device ordinal                                                        */
+  int32_t kernel;  /* l2hmc_kernel_kind                                                          */
+  float eps;       /* step size; the reference holds alpha = log(eps), eps = exp(alpha) (:50-58) */
+} l2hmc_config;
+
+/* One S/T/Q net as built by net_factory (SCGExperiment.ipynb:51-77): variables
+ * {embed_1,embed_2,embed_3,linear_1,linear_s,linear_t,linear_f}/{W,b}, {scale_s,scale_f}/scale.
+ * W matrices are [in, out] row-major like utils/layers.py:33. HOST pointers. */
+typedef struct {
+  const float *W1, *b1; /* embed_1  [D,H], [H]                                                   */
+  const float *W2, *b2; /* embed_2  [D,H], [H]                                                   */
+  const float *W3, *b3; /* embed_3  [2,H], [H]                                                   */
+  const float *W4, *b4; /* linear_1 [H,H], [H]                                                   */
+  const float *Ws, *bs; /* linear_s [H,D], [D]                                                   */
+  const float *Wt, *bt; /* linear_t [H,D], [D]                                                   */
+  const float *Wq, *bq; /* linear_f [H,D], [D]                                                   */
+  const float *scale_s; /* scale_s/scale [D] (log-scale; the layer multiplies by exp(scale))     */
+  const float *scale_q; /* scale_f/scale [D]                                                     */
+} l2hmc_net_params;
+
+/* One transition = propose (+ optional tf_accept):  utils/sampler.py:28-55.
+ * For n_transitions > 1 the kernel iterates x <- x_next on-chip (the reference's host loop of
+ * sess.run, SCGExperiment.ipynb:291-298) and requires do_mh != 0 and Philox randomness. */
+typedef struct {
+  int64_t n;              /* chains in this call                                                 */
+  int64_t chain_offset;   /* global id of chain 0 (Philox keying when chains are sharded)        */
+  const float *x;         /* [n,D]                                                               */
+  const float *v;         /* [n,D] momentum to use, or NULL: draw N(0,I)                         */
+  const uint8_t *dir;     /* [n], dir_mode == L2HMC_DIR_PER_CHAIN                                */
+  const float *u;         /* [n] accept uniforms, or NULL: draw U[0,1) (only read if do_mh)      */
+  int32_t dir_mode;       /* l2hmc_dir_mode                                                      */
+  int32_t log_jac;        /* 1: px_out = accumulated log|J| ; 0: px_out = p_accept               */
+  int32_t do_mh;          /* 1: also write x_next = tf_accept(x, Lx, px)                         */
+  int32_t n_transitions;  /* >= 1                                                                */
+  uint64_t seed;          /* Philox key                                                          */
+  uint64_t counter;       /* Philox call counter (advance by n_transitions per call)             */
+  float *x_out;           /* Lx [n,D]                                                            */
+  float *v_out;           /* Lv [n,D] or NULL                                                    */
+  float *px_out;          /* [n]                                                                 */
+  float *x_next;          /* [n,D] or NULL (required when do_mh)                                 */
+  uint8_t *accepted;      /* [n] or NULL                                                         */
+  void *stream;           /* cudaStream_t                                                        */
+} l2hmc_transition_args;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out); /* Dynamics.__init__ utils/dynamics.py:35 */
+void l2hmc_destroy(l2hmc_ctx *ctx);
+const char *l2hmc_last_error(const l2hmc_ctx *ctx);
+const char *l2hmc_version(void);
+
+/* ---- parameters (host pointers, copied) ---------------------------------------------------- */
+int l2hmc_set_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p); /* XNet/VNet utils/dynamics.py:78-79 */
+int l2hmc_set_masks(l2hmc_ctx *ctx, const float *mask /* [T,D] of {0,1} */); /* Dynamics.mask utils/dynamics.py:84-97 */
+int l2hmc_set_eps(l2hmc_ctx *ctx, float eps);                 /* Dynamics.eps utils/dynamics.py:58 */
+int l2hmc_set_temperature(l2hmc_ctx *ctx, float temperature); /* Dynamics.temperature utils/dynamics.py:47,203-207 */
+/* Energy closure parameters (utils/distributions.py):
+ *  GAUSSIAN : mu [D], S [D,D] (= i_sigma as fp32), n_comp = 1
+ *  GMM      : mu [K,D], S [K,D,D], logc [K] (= log of the fp32 constants, :120-123), n_comp = K <= 8
+ *  ROUGHWELL: scalars[0] = eps, scalars[1] = the cosine's denominator: eps if easy else eps*eps
+ *             (evaluated in double, rounded once to fp32, as python-float * tensor does in TF)
+ *  FUNNEL   : scalars[0] = sigma (2.0), scalars[1] = clip (8.0) */
+int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const float *mu, const float *S,
+                     const float *logc, const float *scalars, int n_scalars);
+
+/* ---- the hot path -------------------------------------------------------------------------- */
+int l2hmc_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a); /* propose utils/sampler.py:28-51 */
+/* Same call with HOST buffers (pageable or pinned): H2D of inputs, kernel, D2H of outputs, stream
+ * synchronised before return.  This is what a reference-side sess.run replacement measures. */
+int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args *a);
+
+/* ---- components (Dynamics methods), device pointers ---------------------------------------- */
+int l2hmc_energy(l2hmc_ctx *ctx, int64_t n, const float *x, float *out, void *stream);       /* Dynamics.energy      utils/dynamics.py:203-212 */
+int l2hmc_grad_energy(l2hmc_ctx *ctx, int64_t n, const float *x, float *out, void *stream);  /* Dynamics.grad_energy utils/dynamics.py:217-218 */
+int l2hmc_kinetic(l2hmc_ctx *ctx, int64_t n, const float *v, float *out, void *stream);      /* Dynamics.kinetic     utils/dynamics.py:107-108 */
+int l2hmc_hamiltonian(l2hmc_ctx *ctx, int64_t n, const float *x, const float *v, float *out, void *stream); /* utils/dynamics.py:214-215 */
+int l2hmc_p_accept(l2hmc_ctx *ctx, int64_t n, const float *x0, const float *v0, const float *x1,
+                   const float *v1, const float *log_jac, float *out, void *stream);         /* Dynamics.p_accept    utils/dynamics.py:302-309 */
+/* net([a, b, t, aux]) -> [S, T, Q]; t is the scalar step index the reference feeds _format_time (utils/dynamics.py:99-105). */
+int l2hmc_net_apply(l2hmc_ctx *ctx, int net_id, int64_t n, const float *a, const float *b, float step,
+                    float *S, float *T, float *Q, void *stream);
+/* tf_accept(x, Lx, px): where(px - u >= 0, Lx, x)  utils/sampler.py:53-55. u NULL => Philox(seed, counter). */
+int l2hmc_accept(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset, const float *x, const float *Lx, const float *px,
+                 const float *u, uint64_t seed, uint64_t counter, float *out, uint8_t *accepted, void *stream);
+/* The in-kernel generator, exported so tests can compare it with the host twin and re-inject it:
+ * v [n,D] normals, dir [n] bits, u [n] uniforms (any may be NULL). */
+int l2hmc_philox_fill(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset, uint64_t seed, uint64_t counter,
+                      float *v, uint8_t *dir, float *u, void *stream);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+const char *l2hmc_kernel_name(const l2hmc_ctx *ctx); /* kernel the next l2hmc_transition will launch */
+int64_t l2hmc_launch_count(const l2hmc_ctx *ctx);    /* kernels launched by this context so far      */
+/* CUDA-event timing of the hot kernel on the launching stream: average ms over launches since reset. */
+int l2hmc_timing_enable(l2hmc_ctx *ctx, int on);
+int l2hmc_timing_read(l2hmc_ctx *ctx, double *avg_ms, int64_t *launches); /* synchronises */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* L2HMC_H_ */

@@ -1,0 +1,729 @@
+// C ABI of libl2hmc.so (see include/l2hmc.h).  Host side: context, parameter packing, launches.
+#include "../../include/l2hmc.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernel_tile.cuh"
+
+using namespace l2hmc;
+
+// ---------------------------------------------------------------------------------------------
+// Context
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  float *p = nullptr;
+  size_t n = 0;
+};
+
+struct l2hmc_ctx {
+  l2hmc_config cfg;
+  Shape sh;
+  int kernel = L2HMC_KERNEL_TILE;
+  std::string err;
+  // device copies
+  DevBuf net_packed[2];  // tile layout
+  DevBuf net_raw[2];     // reference layout
+  NetDev net_dev[2];
+  NetRaw net_rawv[2];
+  bool net_set[2] = {false, false};
+  // host copies of the raw nets (eps / T changes do not need them, kept for re-packing)
+  std::vector<float> net_host[2];
+  DevBuf mask;
+  bool mask_set = false;
+  DevBuf energy_buf;
+  EnergyDev en;
+  bool energy_set = false;
+  int64_t launches = 0;
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;  // pairs
+  size_t ev_used = 0;
+  // host-call staging
+  DevBuf hx, hv, hu, hxo, hvo, hpx, hxn;
+  uint8_t *hdir = nullptr, *hacc = nullptr;
+  size_t hdir_n = 0, hacc_n = 0;
+  cudaStream_t hstream = nullptr;
+};
+
+static thread_local std::string g_err;
+
+static int fail(l2hmc_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf; else g_err = buf;
+  return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t e_ = (expr);                                                                     \
+    if (e_ != cudaSuccess)                                                                       \
+      return fail(ctx, L2HMC_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+static int ensure(l2hmc_ctx *ctx, DevBuf &b, size_t n) {
+  if (b.n >= n && b.p) return L2HMC_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.n = 0;
+  CUDA_TRY(ctx, cudaMalloc(&b.p, n * sizeof(float)));
+  b.n = n;
+  return L2HMC_OK;
+}
+
+static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// ---------------------------------------------------------------------------------------------
+// Component kernels (Dynamics methods; not the hot path)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_energy(EnergyDev en, Shape sh, long long n, const float *x, float *out) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g < n) out[g] = energy_chain(en, sh, x + g * sh.D, 1);
+}
+__global__ void k_grad(EnergyDev en, Shape sh, long long n, const float *x, float *out) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g < n) grad_chain(en, sh, x + g * sh.D, 1, out + g * sh.D, 1);
+}
+__global__ void k_kinetic(int D, long long n, const float *v, float *out) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g < n) {
+    float s = 0.f;
+    for (int d = 0; d < D; ++d) s = fmaf(v[g * D + d], v[g * D + d], s);
+    out[g] = 0.5f * s;  // utils/dynamics.py:107-108
+  }
+}
+__global__ void k_hamiltonian(EnergyDev en, Shape sh, long long n, const float *x, const float *v, float *out) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g < n) {
+    float s = 0.f;
+    for (int d = 0; d < sh.D; ++d) s = fmaf(v[g * sh.D + d], v[g * sh.D + d], s);
+    out[g] = energy_chain(en, sh, x + g * sh.D, 1) + 0.5f * s;
+  }
+}
+__global__ void k_p_accept(EnergyDev en, Shape sh, long long n, const float *x0, const float *v0,
+                           const float *x1, const float *v1, const float *lj, float *out) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g < n) {
+    float k0 = 0.f, k1 = 0.f;
+    for (int d = 0; d < sh.D; ++d) {
+      k0 = fmaf(v0[g * sh.D + d], v0[g * sh.D + d], k0);
+      k1 = fmaf(v1[g * sh.D + d], v1[g * sh.D + d], k1);
+    }
+    const float e_new = energy_chain(en, sh, x1 + g * sh.D, 1) + 0.5f * k1;
+    const float e_old = energy_chain(en, sh, x0 + g * sh.D, 1) + 0.5f * k0;
+    out[g] = accept_prob(e_old, e_new, lj[g]);
+  }
+}
+
+constexpr int NET_MAXH = 256;
+__global__ void k_net_apply(NetRaw w, int D, int H, int T, int hmc, long long n, const float *a, const float *b,
+                            float step, float *S, float *Tt, float *Q) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  if (hmc) {
+    for (int d = 0; d < D; ++d) S[g * D + d] = Tt[g * D + d] = Q[g * D + d] = 0.f;
+    return;
+  }
+  float h1[NET_MAXH], h2[NET_MAXH];
+  const float arg = 6.2831855f * step / (float)T;  // utils/dynamics.py:99-105
+  const float ct = cosf(arg), st = sinf(arg);
+  for (int j = 0; j < H; ++j) {
+    float e1 = 0.f, e2 = 0.f;
+    for (int i = 0; i < D; ++i) {
+      e1 = fmaf(a[g * D + i], w.W1[i * H + j], e1);
+      e2 = fmaf(b[g * D + i], w.W2[i * H + j], e2);
+    }
+    float e3 = fmaf(st, w.W3[H + j], ct * w.W3[j]);
+    float s = (((0.f + (e1 + w.b1[j])) + (e2 + w.b2[j])) + (e3 + w.b3[j]));
+    h1[j] = fmaxf(s, 0.f);
+  }
+  for (int j = 0; j < H; ++j) {
+    float s = 0.f;
+    for (int i = 0; i < H; ++i) s = fmaf(h1[i], w.W4[i * H + j], s);
+    h2[j] = fmaxf(s + w.b4[j], 0.f);
+  }
+  for (int d = 0; d < D; ++d) {
+    float s = 0.f, t = 0.f, q = 0.f;
+    for (int i = 0; i < H; ++i) {
+      s = fmaf(h2[i], w.Ws[i * D + d], s);
+      t = fmaf(h2[i], w.Wt[i * D + d], t);
+      q = fmaf(h2[i], w.Wq[i * D + d], q);
+    }
+    S[g * D + d] = expf(w.ls[d]) * tanhf(s + w.bs[d]);
+    Tt[g * D + d] = t + w.bt[d];
+    Q[g * D + d] = expf(w.lq[d]) * tanhf(q + w.bq[d]);
+  }
+}
+
+__global__ void k_accept(int D, long long n, long long off, const float *x, const float *Lx, const float *px,
+                         const float *u, unsigned long long seed, unsigned long long counter, float *out,
+                         uint8_t *accepted) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n * D) return;
+  const long long g = i / D;
+  float uu;
+  if (u) uu = u[g];
+  else {
+    int dd;
+    philox_dir_u(seed, counter, off + g, dd, uu);
+  }
+  const bool acc = (px[g] - uu >= 0.f);
+  out[i] = acc ? Lx[i] : x[i];
+  if (accepted && (i - g * D) == 0) accepted[g] = acc ? 1 : 0;
+}
+
+__global__ void k_philox_fill(int D, long long n, long long off, unsigned long long seed,
+                              unsigned long long counter, float *v, uint8_t *dir, float *u) {
+  long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  if (v) {
+    for (int b = 0; b < (D + 3) / 4; ++b) {
+      float z[4];
+      philox_normals4(seed, counter, off + g, b, z);
+      for (int q = 0; q < 4; ++q)
+        if (4 * b + q < D) v[g * D + 4 * b + q] = z[q];
+    }
+  }
+  if (dir || u) {
+    int dbit;
+    float uu;
+    philox_dir_u(seed, counter, off + g, dbit, uu);
+    if (dir) dir[g] = (uint8_t)dbit;
+    if (u) u[g] = uu;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// lifetime
+// ---------------------------------------------------------------------------------------------
+extern "C" const char *l2hmc_version(void) { return "l2hmc_b200 0.1 (sm_100a)"; }
+
+extern "C" const char *l2hmc_last_error(const l2hmc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+static int pick_kernel(l2hmc_ctx *ctx) {
+  const Shape &sh = ctx->sh;
+  int k = ctx->cfg.kernel;
+  if (k == L2HMC_KERNEL_AUTO) k = L2HMC_KERNEL_TILE;
+  if (k == L2HMC_KERNEL_TILE) {
+    if (sh.DP > 64 || (!sh.hmc && sh.HP > 128))
+      return fail(ctx, L2HMC_EUNSUPPORTED, "tile kernel covers x_dim <= 64 and width <= 128 (got %d, %d)", sh.D, sh.H);
+  } else {
+    return fail(ctx, L2HMC_EUNSUPPORTED, "kernel kind %d not available in this build", k);
+  }
+  ctx->kernel = k;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
+  if (!cfg || !out) return fail(nullptr, L2HMC_EINVAL, "l2hmc_create: null argument");
+  if (cfg->x_dim < 1 || cfg->T < 1 || (!cfg->hmc && cfg->width < 1) || !(cfg->eps > 0.f))
+    return fail(nullptr, L2HMC_EINVAL, "l2hmc_create: need x_dim >= 1, T >= 1, width >= 1, eps > 0");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, L2HMC_ECUDA, "l2hmc_create: no CUDA device (%s)", cudaGetErrorString(e));
+  if (cfg->device < 0 || cfg->device >= ndev)
+    return fail(nullptr, L2HMC_EINVAL, "l2hmc_create: device %d out of range (%d devices)", cfg->device, ndev);
+  l2hmc_ctx *ctx = new (std::nothrow) l2hmc_ctx();
+  if (!ctx) return fail(nullptr, L2HMC_ENOMEM, "l2hmc_create: out of host memory");
+  ctx->cfg = *cfg;
+  Shape &sh = ctx->sh;
+  sh.D = cfg->x_dim;
+  sh.DP = round_up(cfg->x_dim, 4);
+  sh.H = cfg->hmc ? 4 : cfg->width;
+  sh.HP = round_up(sh.H, 4);
+  sh.T = cfg->T;
+  sh.LDE = 128;
+  sh.LDH = 192;
+  sh.LDS = 128;
+  sh.hmc = cfg->hmc ? 1 : 0;
+  sh.eps = cfg->eps;
+  ctx->en.kind = L2HMC_ENERGY_NONE;
+  ctx->en.temperature = 1.0f;
+  int rc = pick_kernel(ctx);
+  if (rc != L2HMC_OK) {
+    g_err = ctx->err;
+    delete ctx;
+    return rc;
+  }
+  if (cudaSetDevice(cfg->device) != cudaSuccess) {
+    delete ctx;
+    return fail(nullptr, L2HMC_ECUDA, "l2hmc_create: cudaSetDevice(%d) failed", cfg->device);
+  }
+  *out = ctx;
+  return L2HMC_OK;
+}
+
+extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  DevBuf *bufs[] = {&ctx->net_packed[0], &ctx->net_packed[1], &ctx->net_raw[0], &ctx->net_raw[1], &ctx->mask,
+                    &ctx->energy_buf, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn};
+  for (DevBuf *b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->hdir) cudaFree(ctx->hdir);
+  if (ctx->hacc) cudaFree(ctx->hacc);
+  for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
+  if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
+  delete ctx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// parameters
+// ---------------------------------------------------------------------------------------------
+extern "C" int l2hmc_set_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
+  if (!ctx || !p) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_net: null argument");
+  if (net_id != L2HMC_XNET && net_id != L2HMC_VNET) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_net: bad net id %d", net_id);
+  if (ctx->sh.hmc) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_net: context is hmc (nets are zero)");
+  const float *ptrs[] = {p->W1, p->b1, p->W2, p->b2, p->W3, p->b3, p->W4, p->b4, p->Ws, p->bs,
+                         p->Wt, p->bt, p->Wq, p->bq, p->scale_s, p->scale_q};
+  for (const float *q : ptrs)
+    if (!q) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_net: null weight pointer");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const Shape &sh = ctx->sh;
+  const int D = sh.D, H = sh.H, DP = sh.DP, HP = sh.HP, T = sh.T;
+
+  // ---- raw copy (reference layout) ------------------------------------------------------------
+  const size_t sizes[] = {(size_t)D * H, (size_t)H, (size_t)D * H, (size_t)H, (size_t)2 * H, (size_t)H,
+                          (size_t)H * H, (size_t)H, (size_t)H * D, (size_t)D, (size_t)H * D, (size_t)D,
+                          (size_t)H * D, (size_t)D, (size_t)D, (size_t)D};
+  size_t total = 0;
+  for (size_t s : sizes) total += round_up((int)s, 4);
+  std::vector<float> raw(total, 0.f);
+  size_t off[16], o = 0;
+  for (int i = 0; i < 16; ++i) {
+    off[i] = o;
+    memcpy(raw.data() + o, ptrs[i], sizes[i] * sizeof(float));
+    o += round_up((int)sizes[i], 4);
+  }
+  for (float f : raw)
+    if (!isfinite(f)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_net: non-finite weight");
+  int rc = ensure(ctx, ctx->net_raw[net_id], total);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(ctx->net_raw[net_id].p, raw.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    const float *b = ctx->net_raw[net_id].p;
+    NetRaw &r = ctx->net_rawv[net_id];
+    r.W1 = b + off[0]; r.b1 = b + off[1]; r.W2 = b + off[2]; r.b2 = b + off[3];
+    r.W3 = b + off[4]; r.b3 = b + off[5]; r.W4 = b + off[6]; r.b4 = b + off[7];
+    r.Ws = b + off[8]; r.bs = b + off[9]; r.Wt = b + off[10]; r.bt = b + off[11];
+    r.Wq = b + off[12]; r.bq = b + off[13]; r.ls = b + off[14]; r.lq = b + off[15];
+  }
+
+  // ---- packed copy (tile-kernel layout, see NetDev) ---------------------------------------------
+  const int LDE = sh.LDE, LDH = sh.LDH;
+  const size_t nWemb = (size_t)2 * DP * LDE, ntb = (size_t)T * LDE, nW4 = (size_t)HP * LDE, nb4 = LDE,
+               nWh = (size_t)HP * LDH, nbh = LDH, nes = DP, neq = DP;
+  const size_t ptotal = nWemb + ntb + nW4 + nb4 + nWh + nbh + nes + neq;
+  std::vector<float> pk(ptotal, 0.f);
+  float *Wemb = pk.data(), *tb = Wemb + nWemb, *W4 = tb + ntb, *b4 = W4 + nW4, *Wh = b4 + nb4, *bh = Wh + nWh,
+        *es = bh + nbh, *eq = es + nes;
+  for (int i = 0; i < D; ++i)
+    for (int j = 0; j < H; ++j) {
+      Wemb[(size_t)i * LDE + j] = p->W1[(size_t)i * H + j];
+      Wemb[(size_t)(DP + i) * LDE + j] = p->W2[(size_t)i * H + j];
+    }
+  for (int t = 0; t < T; ++t) {
+    const float arg = 6.2831855f * (float)t / (float)T;  // utils/dynamics.py:99-105 in fp32
+    const float ct = cosf(arg), st = sinf(arg);
+    for (int j = 0; j < H; ++j) {
+      const float e3 = fmaf(st, p->W3[H + j], ct * p->W3[j]) + p->b3[j];
+      tb[(size_t)t * LDE + j] = (p->b1[j] + p->b2[j]) + e3;
+    }
+  }
+  for (int i = 0; i < H; ++i)
+    for (int j = 0; j < H; ++j) W4[(size_t)i * LDE + j] = p->W4[(size_t)i * H + j];
+  for (int j = 0; j < H; ++j) b4[j] = p->b4[j];
+  for (int i = 0; i < H; ++i)
+    for (int d = 0; d < D; ++d) {
+      Wh[(size_t)i * LDH + 3 * d + 0] = p->Ws[(size_t)i * D + d];
+      Wh[(size_t)i * LDH + 3 * d + 1] = p->Wt[(size_t)i * D + d];
+      Wh[(size_t)i * LDH + 3 * d + 2] = p->Wq[(size_t)i * D + d];
+    }
+  for (int d = 0; d < DP; ++d) {
+    es[d] = eq[d] = 1.0f;
+    if (d < D) {
+      bh[3 * d + 0] = p->bs[d];
+      bh[3 * d + 1] = p->bt[d];
+      bh[3 * d + 2] = p->bq[d];
+      es[d] = expf(p->scale_s[d]);  // utils/layers.py:84
+      eq[d] = expf(p->scale_q[d]);
+    }
+  }
+  rc = ensure(ctx, ctx->net_packed[net_id], ptotal);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(ctx->net_packed[net_id].p, pk.data(), ptotal * sizeof(float), cudaMemcpyHostToDevice));
+  {
+    const float *b = ctx->net_packed[net_id].p;
+    NetDev &n = ctx->net_dev[net_id];
+    n.Wemb = b; n.tb = n.Wemb + nWemb; n.W4 = n.tb + ntb; n.b4 = n.W4 + nW4;
+    n.Wh = n.b4 + nb4; n.bh = n.Wh + nWh; n.es = n.bh + nbh; n.eq = n.es + nes;
+  }
+  ctx->net_set[net_id] = true;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_masks(l2hmc_ctx *ctx, const float *mask) {
+  if (!ctx || !mask) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_masks: null argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const Shape &sh = ctx->sh;
+  std::vector<float> m((size_t)sh.T * sh.DP, 0.f);
+  for (int t = 0; t < sh.T; ++t)
+    for (int d = 0; d < sh.D; ++d) {
+      const float v = mask[(size_t)t * sh.D + d];
+      if (v != 0.f && v != 1.f) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_masks: mask[%d,%d] = %g is not 0/1", t, d, v);
+      m[(size_t)t * sh.DP + d] = v;
+    }
+  int rc = ensure(ctx, ctx->mask, m.size());
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(ctx->mask.p, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->mask_set = true;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_eps(l2hmc_ctx *ctx, float eps) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_eps: null context");
+  if (!(eps > 0.f) || !isfinite(eps)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_eps: eps must be finite and > 0");
+  ctx->sh.eps = eps;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_temperature(l2hmc_ctx *ctx, float t) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_temperature: null context");
+  if (!(t > 0.f) || !isfinite(t)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_temperature: must be finite and > 0");
+  ctx->en.temperature = t;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const float *mu, const float *S,
+                                const float *logc, const float *scalars, int n_scalars) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: null context");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const Shape &sh = ctx->sh;
+  EnergyDev en = ctx->en;
+  en.kind = kind;
+  en.ncomp = 1;
+  en.mu = en.Ssym = en.logc = nullptr;
+  en.s0 = en.s1 = 0.f;
+  if (kind == L2HMC_ENERGY_GAUSSIAN || kind == L2HMC_ENERGY_GMM) {
+    if (kind == L2HMC_ENERGY_GAUSSIAN) n_comp = 1;
+    if (n_comp < 1 || n_comp > MAX_COMP) return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_energy: 1 <= n_comp <= %d", MAX_COMP);
+    if (!mu || !S || (kind == L2HMC_ENERGY_GMM && !logc)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: null parameter array");
+    const size_t nmu = (size_t)n_comp * sh.DP, nS = (size_t)n_comp * sh.DP * sh.LDS, nc = round_up(n_comp, 4);
+    std::vector<float> buf(nmu + nS + nc, 0.f);
+    for (int c = 0; c < n_comp; ++c) {
+      for (int i = 0; i < sh.D; ++i) buf[(size_t)c * sh.DP + i] = mu[(size_t)c * sh.D + i];
+      const float *Sc = S + (size_t)c * sh.D * sh.D;
+      for (int i = 0; i < sh.D; ++i)
+        for (int j = 0; j < sh.D; ++j)  // 0.5 * (d S^T) + 0.5 * (d S) == d (0.5 S^T + 0.5 S)
+          buf[nmu + ((size_t)c * sh.DP + i) * sh.LDS + j] = 0.5f * Sc[(size_t)i * sh.D + j] + 0.5f * Sc[(size_t)j * sh.D + i];
+      if (logc) buf[nmu + nS + c] = logc[c];
+    }
+    for (float f : buf)
+      if (!isfinite(f)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: non-finite parameter");
+    int rc = ensure(ctx, ctx->energy_buf, buf.size());
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpy(ctx->energy_buf.p, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    en.ncomp = n_comp;
+    en.mu = ctx->energy_buf.p;
+    en.Ssym = en.mu + nmu;
+    en.logc = en.Ssym + nS;
+  } else if (kind == L2HMC_ENERGY_ROUGHWELL || kind == L2HMC_ENERGY_FUNNEL) {
+    if (!scalars || n_scalars < 2) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: need 2 scalars");
+    en.s0 = scalars[0];
+    en.s1 = scalars[1];
+    if (kind == L2HMC_ENERGY_FUNNEL && sh.D < 2) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: funnel needs x_dim >= 2");
+  } else {
+    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_energy: unknown energy kind %d", kind);
+  }
+  ctx->en = en;
+  ctx->energy_set = true;
+  return L2HMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// hot path
+// ---------------------------------------------------------------------------------------------
+static int check_ready(l2hmc_ctx *ctx, const char *who) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "%s: null context", who);
+  if (!ctx->energy_set) return fail(ctx, L2HMC_EINVAL, "%s: energy not set (l2hmc_set_energy)", who);
+  return L2HMC_OK;
+}
+
+static int validate_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, bool host = false) {
+  int rc = check_ready(ctx, "l2hmc_transition");
+  if (rc) return rc;
+  if (!a) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: null args");
+  if (!ctx->mask_set) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: masks not set (l2hmc_set_masks)");
+  if (!ctx->sh.hmc && !(ctx->net_set[0] && ctx->net_set[1]))
+    return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: XNet/VNet not set (l2hmc_set_net)");
+  if (a->n < 0) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: n < 0");
+  if (a->n_transitions < 1) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: n_transitions must be >= 1");
+  if (a->n > 0 && (!a->x || (!host && (!a->x_out || !a->px_out))))
+    return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: x, x_out and px_out are required");
+  if (a->dir_mode < 0 || a->dir_mode > 3) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: bad dir_mode %d", a->dir_mode);
+  if (a->dir_mode == L2HMC_DIR_PER_CHAIN && !a->dir && a->n > 0) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: dir_mode PER_CHAIN needs dir");
+  if (a->do_mh && !a->x_next && a->n > 0 && !host) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: do_mh needs x_next");
+  if (a->n_transitions > 1 && !a->do_mh) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: n_transitions > 1 needs do_mh");
+  if (a->counter + (uint64_t)a->n_transitions >= (1ull << 30)) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: counter must stay below 2^30");
+  return L2HMC_OK;
+}
+
+static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cudaStream_t stream) {
+  if (a->n == 0) return L2HMC_OK;
+  KernelArgs K;
+  K.sh = ctx->sh;
+  K.xnet = ctx->net_dev[0];
+  K.vnet = ctx->net_dev[1];
+  K.en = ctx->en;
+  K.mask = ctx->mask.p;
+  TransitionIO &io = K.io;
+  io.n = a->n; io.chain_offset = a->chain_offset;
+  io.x = a->x; io.v = a->v; io.u = a->u; io.dir = a->dir;
+  io.dir_mode = a->dir_mode; io.log_jac = a->log_jac; io.do_mh = a->do_mh; io.n_transitions = a->n_transitions;
+  io.seed = a->seed; io.counter = a->counter;
+  io.x_out = a->x_out; io.v_out = a->v_out; io.px_out = a->px_out; io.x_next = a->x_next; io.accepted = a->accepted;
+
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->timing) {
+    if (ctx->ev_used + 2 > ctx->ev.size()) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEvent_t e;
+        CUDA_TRY(ctx, cudaEventCreate(&e));
+        ctx->ev.push_back(e);
+      }
+    }
+    e0 = ctx->ev[ctx->ev_used];
+    e1 = ctx->ev[ctx->ev_used + 1];
+    ctx->ev_used += 2;
+    CUDA_TRY(ctx, cudaEventRecord(e0, stream));
+  }
+  if (ctx->kernel == L2HMC_KERNEL_TILE) {
+    const size_t smem = tile::smem_bytes(ctx->sh.DP, ctx->sh.HP, ctx->sh.T);
+    static thread_local size_t configured = 0;
+    if (smem > configured) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tile::transition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    const long long blocks = (a->n + tile::M - 1) / tile::M;
+    tile::transition_kernel<<<(unsigned)blocks, tile::NT, smem, stream>>>(K);
+  } else {
+    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_transition: kernel kind %d not available", ctx->kernel);
+  }
+  CUDA_TRY(ctx, cudaGetLastError());
+  if (ctx->timing) CUDA_TRY(ctx, cudaEventRecord(e1, stream));
+  ctx->launches += 1;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
+  int rc = validate_transition(ctx, a);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  return launch_transition(ctx, a, (cudaStream_t)a->stream);
+}
+
+static int ensure_u8(l2hmc_ctx *ctx, uint8_t *&p, size_t &have, size_t n) {
+  if (have >= n && p) return L2HMC_OK;
+  if (p) cudaFree(p);
+  p = nullptr;
+  have = 0;
+  CUDA_TRY(ctx, cudaMalloc(&p, n));
+  have = n;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
+  int rc = validate_transition(ctx, a, true);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  if (a->n == 0) return L2HMC_OK;
+  if (!ctx->hstream) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->hstream, cudaStreamNonBlocking));
+  cudaStream_t s = ctx->hstream;
+  const size_t n = (size_t)a->n, D = (size_t)ctx->sh.D, K = (size_t)a->n_transitions;
+  l2hmc_transition_args d = *a;
+  d.stream = s;
+  if ((rc = ensure(ctx, ctx->hx, n * D))) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hx.p, a->x, n * D * sizeof(float), cudaMemcpyHostToDevice, s));
+  d.x = ctx->hx.p;
+  if (a->v) {
+    if ((rc = ensure(ctx, ctx->hv, K * n * D))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hv.p, a->v, K * n * D * sizeof(float), cudaMemcpyHostToDevice, s));
+    d.v = ctx->hv.p;
+  }
+  if (a->u) {
+    if ((rc = ensure(ctx, ctx->hu, K * n))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hu.p, a->u, K * n * sizeof(float), cudaMemcpyHostToDevice, s));
+    d.u = ctx->hu.p;
+  }
+  if (a->dir) {
+    if ((rc = ensure_u8(ctx, ctx->hdir, ctx->hdir_n, K * n))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hdir, a->dir, K * n, cudaMemcpyHostToDevice, s));
+    d.dir = ctx->hdir;
+  }
+  if ((rc = ensure(ctx, ctx->hxo, n * D))) return rc;
+  if ((rc = ensure(ctx, ctx->hpx, n))) return rc;
+  d.x_out = ctx->hxo.p;
+  d.px_out = ctx->hpx.p;
+  if (a->v_out) {
+    if ((rc = ensure(ctx, ctx->hvo, n * D))) return rc;
+    d.v_out = ctx->hvo.p;
+  }
+  if (a->x_next || a->do_mh) {
+    if ((rc = ensure(ctx, ctx->hxn, n * D))) return rc;
+    d.x_next = ctx->hxn.p;
+  }
+  if (a->accepted) {
+    if ((rc = ensure_u8(ctx, ctx->hacc, ctx->hacc_n, n))) return rc;
+    d.accepted = ctx->hacc;
+  }
+  if ((rc = launch_transition(ctx, &d, s))) return rc;
+  if (a->x_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->x_out, d.x_out, n * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (a->px_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->px_out, d.px_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (a->v_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->v_out, d.v_out, n * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (a->x_next) CUDA_TRY(ctx, cudaMemcpyAsync(a->x_next, d.x_next, n * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (a->accepted) CUDA_TRY(ctx, cudaMemcpyAsync(a->accepted, d.accepted, n, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  return L2HMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// components
+// ---------------------------------------------------------------------------------------------
+#define GRID(n) (unsigned)(((n) + 127) / 128), 128
+
+extern "C" int l2hmc_energy(l2hmc_ctx *ctx, int64_t n, const float *x, float *out, void *stream) {
+  int rc = check_ready(ctx, "l2hmc_energy");
+  if (rc) return rc;
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  k_energy<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_grad_energy(l2hmc_ctx *ctx, int64_t n, const float *x, float *out, void *stream) {
+  int rc = check_ready(ctx, "l2hmc_grad_energy");
+  if (rc) return rc;
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  k_grad<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_kinetic(l2hmc_ctx *ctx, int64_t n, const float *v, float *out, void *stream) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_kinetic: null context");
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  k_kinetic<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->sh.D, n, v, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_hamiltonian(l2hmc_ctx *ctx, int64_t n, const float *x, const float *v, float *out, void *stream) {
+  int rc = check_ready(ctx, "l2hmc_hamiltonian");
+  if (rc) return rc;
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  k_hamiltonian<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x, v, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_p_accept(l2hmc_ctx *ctx, int64_t n, const float *x0, const float *v0, const float *x1,
+                              const float *v1, const float *log_jac, float *out, void *stream) {
+  int rc = check_ready(ctx, "l2hmc_p_accept");
+  if (rc) return rc;
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  k_p_accept<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x0, v0, x1, v1, log_jac, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_net_apply(l2hmc_ctx *ctx, int net_id, int64_t n, const float *a, const float *b, float step,
+                               float *S, float *T, float *Q, void *stream) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_net_apply: null context");
+  if (net_id != 0 && net_id != 1) return fail(ctx, L2HMC_EINVAL, "l2hmc_net_apply: bad net id");
+  if (!ctx->sh.hmc && !ctx->net_set[net_id]) return fail(ctx, L2HMC_EINVAL, "l2hmc_net_apply: net not set");
+  if (ctx->sh.H > NET_MAXH) return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_net_apply: width > %d", NET_MAXH);
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  k_net_apply<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->net_rawv[net_id], ctx->sh.D, ctx->sh.H, ctx->sh.T, ctx->sh.hmc,
+                                                     n, a, b, step, S, T, Q);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_accept(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset, const float *x, const float *Lx,
+                            const float *px, const float *u, uint64_t seed, uint64_t counter, float *out,
+                            uint8_t *accepted, void *stream) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_accept: null context");
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const long long tot = n * ctx->sh.D;
+  k_accept<<<GRID(tot), 0, (cudaStream_t)stream>>>(ctx->sh.D, n, chain_offset, x, Lx, px, u, seed, counter, out, accepted);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_philox_fill(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset, uint64_t seed, uint64_t counter,
+                                 float *v, uint8_t *dir, float *u, void *stream) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_philox_fill: null context");
+  if (n <= 0) return L2HMC_OK;
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  k_philox_fill<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->sh.D, n, chain_offset, seed, counter, v, dir, u);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// introspection
+// ---------------------------------------------------------------------------------------------
+extern "C" const char *l2hmc_kernel_name(const l2hmc_ctx *ctx) {
+  if (!ctx) return "none";
+  switch (ctx->kernel) {
+    case L2HMC_KERNEL_TILE: return "tile_fma";
+    case L2HMC_KERNEL_SMALL: return "small_fma";
+    case L2HMC_KERNEL_TC: return "tc_3xtf32";
+    default: return "none";
+  }
+}
+extern "C" int64_t l2hmc_launch_count(const l2hmc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int l2hmc_timing_enable(l2hmc_ctx *ctx, int on) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_timing_enable: null context");
+  ctx->timing = on != 0;
+  ctx->ev_used = 0;
+  return L2HMC_OK;
+}
+extern "C" int l2hmc_timing_read(l2hmc_ctx *ctx, double *avg_ms, int64_t *launches) {
+  if (!ctx || !avg_ms || !launches) return fail(ctx, L2HMC_EINVAL, "l2hmc_timing_read: null argument");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  double tot = 0.0;
+  int64_t cnt = 0;
+  for (size_t i = 0; i + 1 < ctx->ev_used; i += 2) {
+    CUDA_TRY(ctx, cudaEventSynchronize(ctx->ev[i + 1]));
+    float ms = 0.f;
+    CUDA_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]));
+    tot += ms;
+    cnt++;
+  }
+  *avg_ms = cnt ? tot / cnt : 0.0;
+  *launches = cnt;
+  ctx->ev_used = 0;
+  return L2HMC_OK;
+}

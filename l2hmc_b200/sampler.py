@@ -1,0 +1,116 @@
+"""Sampling operators (mirror of the reference's utils/sampler.py).
+
+``propose`` (:28-51), ``tf_accept`` (:53-55) and ``chain_operator`` (:57-85) keep the reference's
+signatures and return values; keyword-only arguments after them are additions.
+
+What differs underneath: the reference runs BOTH directions for every chain and blends them with the
+direction bit (:35-44).  The fused kernel runs only the selected direction of each chain with one
+momentum draw -- the same transition kernel in distribution, half the work, and a non-finite value in
+the discarded direction can no longer leak into the result through ``mask * a + (1 - mask) * b``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .dynamics import Dynamics, TORCH_FLOAT
+
+
+def propose(x, dynamics, init_v=None, aux=None, do_mh_step=False, log_jac=False, *, rng=None, n_transitions=1):
+    """One L2HMC (or HMC) proposal; returns ``(Lx, Lv, px, outputs)`` like the reference.
+
+    rng: optional dict with explicit randomness -- 'direction' uint8 [N] (1 = forward), 'v' [N, D]
+    momentum for the selected direction, 'u' [N] accept uniforms.  Missing entries are drawn in-kernel
+    (Philox keyed by dynamics.seed and its call counter).
+    n_transitions > 1 iterates the MH chain on-chip (requires do_mh_step); outputs are the last ones.
+    """
+    rng = rng or {}
+    if dynamics.hmc:
+        # utils/sampler.py:29-31 -- forward only, init_v forwarded, MH output always appended
+        v = init_v if init_v is not None else rng.get("v")
+        o = dynamics._transition(x, v=v, dir_mode=_lib.DIR_FORWARD, u=rng.get("u"), do_mh=True,
+                                 n_transitions=n_transitions)
+        return o["Lx"], o["Lv"], o["px"], [o["x_next"]]
+    dynamics._no_aux(aux)
+    o = dynamics._transition(x, v=rng.get("v"), dir_mode=_lib.DIR_RANDOM, direction=rng.get("direction"),
+                             u=rng.get("u"), log_jac=log_jac, do_mh=do_mh_step, n_transitions=n_transitions)
+    Lv = o["Lv"] if init_v is not None else None  # utils/sampler.py:40-42
+    outputs = []
+    if do_mh_step:
+        outputs.append(o["x_next"])
+    return o["Lx"], Lv, o["px"], outputs
+
+
+_util_ctx = {}
+
+
+def _util(x_dim, device_index):
+    """A parameter-free context for the elementwise helper kernels."""
+    key = (int(x_dim), int(device_index))
+    ctx = _util_ctx.get(key)
+    if ctx is None:
+        lib = _lib.load()
+        cfg = _lib.Config(key[0], 1, 1, 1, key[1], _lib.KERNEL_AUTO, 0.1)
+        ctx = C.c_void_p()
+        rc = lib.l2hmc_create(C.byref(cfg), C.byref(ctx))
+        if rc != 0:
+            raise _lib.L2HMCError(rc, (lib.l2hmc_last_error(None) or b"?").decode())
+        _util_ctx[key] = ctx
+    return _lib.load(), ctx
+
+
+def tf_accept(x, Lx, px, *, u=None, seed=0, counter=0):
+    """where(px - u >= 0, Lx, x) row-wise (utils/sampler.py:53-55); u drawn in-kernel when None."""
+    if not (x.is_cuda and Lx.is_cuda and px.is_cuda):
+        raise TypeError("tf_accept works on CUDA tensors")
+    x = x.detach().to(TORCH_FLOAT).contiguous()
+    Lx = Lx.detach().to(TORCH_FLOAT).contiguous()
+    px = px.detach().to(TORCH_FLOAT).contiguous()
+    n, d = x.shape
+    lib, ctx = _util(d, x.device.index)
+    out = torch.empty_like(x)
+    up = None
+    if u is not None:
+        u = u.detach().to(device=x.device, dtype=TORCH_FLOAT).contiguous()
+        up = u.data_ptr()
+    stream = C.c_void_p(torch.cuda.current_stream(x.device.index).cuda_stream)
+    _lib.check(lib, ctx, lib.l2hmc_accept(ctx, n, 0, x.data_ptr(), Lx.data_ptr(), px.data_ptr(), up, int(seed),
+                                          int(counter), out.data_ptr(), None, stream))
+    return out
+
+
+def randn_like(x, *, seed=0, counter=0):
+    """N(0, I) with the library generator (tf.random_normal(tf.shape(x)) in the reference)."""
+    n, d = x.shape
+    lib, ctx = _util(d, x.device.index)
+    out = torch.empty((n, d), dtype=TORCH_FLOAT, device=x.device)
+    stream = C.c_void_p(torch.cuda.current_stream(x.device.index).cuda_stream)
+    _lib.check(lib, ctx, lib.l2hmc_philox_fill(ctx, n, 0, int(seed), int(counter), out.data_ptr(), None, None, stream))
+    return out
+
+
+def chain_operator(init_x, dynamics, nb_steps, aux=None, init_v=None, do_mh_step=False, *, rng=None):
+    """Compose nb_steps proposals, accumulate log|J|, one MH at the end (utils/sampler.py:57-85).
+
+    Kept quirk of the reference: sub-proposals draw fresh momentum (init_v only seeds the first
+    Hamiltonian and makes ``propose`` return Lv); the final p_accept pairs init_v with the last Lv.
+    rng: optional list (one dict per sub-proposal, see ``propose``) plus rng_final={'u': ...} as the
+    last element for the closing MH step.
+    """
+    dynamics._no_aux(aux)
+    if init_v is None:
+        init_v = randn_like(init_x, seed=dynamics.seed ^ 0x5EED, counter=dynamics.next_counter())
+    x, v = init_x, init_v
+    log_jac = torch.zeros((init_x.shape[0],), dtype=TORCH_FLOAT, device=init_x.device)
+    for t in range(int(nb_steps)):
+        r = rng[t] if rng is not None else None
+        x, v, px, _ = propose(x, dynamics, init_v=v, aux=aux, log_jac=True, do_mh_step=False, rng=r)
+        log_jac = log_jac + px
+    p_accept = dynamics.p_accept(init_x, init_v, x, v, log_jac, aux=aux)
+    outputs = []
+    if do_mh_step:
+        u = rng[int(nb_steps)].get("u") if rng is not None and len(rng) > int(nb_steps) else None
+        outputs.append(tf_accept(init_x, x, p_accept, u=u, seed=dynamics.seed, counter=dynamics.next_counter()))
+    return x, v, p_accept, outputs

@@ -1,0 +1,497 @@
+"""CPU oracle for the L2HMC augmented-leapfrog sampling path.  TEST INFRASTRUCTURE ONLY.
+
+This is an op-for-op CPU restatement (torch-CPU, fp32 twin and fp64 twin) of the
+reference's hot path.  It is the checker: only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl
+reference`` legs may import it.  Nothing under ``l2hmc_b200/`` imports it and the
+product path never falls back to it.
+
+PARITY UNPINNED: the reference (TF1 / Python 2, /root/reference) cannot run in
+this environment (no TensorFlow, no Python 2), holds no tests / golden vectors /
+fixtures and seeds none of its RNGs.  The oracle is
+therefore pinned only by (a) reading the reference line by line (citations
+below), (b) the algebraic properties the reference's code implies (exact
+inverse, log-det vs autograd Jacobian, HMC limit; tests/test_oracle.py) and (c)
+a second, independently written plain-C restatement (oracle/l2hmc_oracle.c)
+that must agree with it.
+
+All randomness is injected (the reference draws v, direction bits and accept
+uniforms from unseeded TF RNGs: utils/dynamics.py:248,276, utils/sampler.py:34,54).
+
+Reference citations are into /root/reference/.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+TWO_PI = 2 * np.pi  # utils/dynamics.py:101 -- python float, cast to the tensor dtype on use
+
+
+# --------------------------------------------------------------------------------------
+# S/T/Q net (SCGExperiment.ipynb:51-77, utils/layers.py:29-37,81-95)
+# --------------------------------------------------------------------------------------
+NET_KEYS = ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4",
+            "Ws", "bs", "Wt", "bt", "Wq", "bq", "ls", "lq")
+
+
+def net_cast(p: Dict[str, torch.Tensor], dtype) -> Dict[str, torch.Tensor]:
+    return {k: torch.as_tensor(np.asarray(v)).to(dtype) for k, v in p.items()}
+
+
+def net_apply(p, a, b, tau, aux_embed=None):
+    """net([a, b, t, aux]) -> [S, T, Q].
+
+    Zip of three Linear layers (+ the aux branch), python ``sum`` (order
+    (((0 + e1) + e2) + e3) + e_aux, SCGExperiment.ipynb:54-60), relu, Linear, relu,
+    Parallel[Linear+ScaleTanh, Linear, Linear+ScaleTanh] (SCGExperiment.ipynb:62-74).
+    Linear is ``tf.add(tf.matmul(x, W), b)`` (utils/layers.py:37); ScaleTanh is
+    ``exp(scale) * tanh(x)`` (utils/layers.py:83-86).  tau is [N, 2].
+    """
+    e1 = a @ p["W1"] + p["b1"]
+    e2 = b @ p["W2"] + p["b2"]
+    e3 = tau @ p["W3"] + p["b3"]
+    e4 = 0.0 if aux_embed is None else aux_embed  # `lambda _: 0.` in the notebook
+    h = (((0 + e1) + e2) + e3) + e4
+    h = torch.relu(h)
+    h = torch.relu(h @ p["W4"] + p["b4"])
+    S = torch.exp(p["ls"]) * torch.tanh(h @ p["Ws"] + p["bs"])
+    T = h @ p["Wt"] + p["bt"]
+    Q = torch.exp(p["lq"]) * torch.tanh(h @ p["Wq"] + p["bq"])
+    return S, T, Q
+
+
+def net_zero(p, a, b, tau, aux_embed=None):
+    """hmc=True nets: three zero tensors shaped like the first input (utils/dynamics.py:73-76)."""
+    z = torch.zeros_like(a)
+    return z, z, z
+
+
+# --------------------------------------------------------------------------------------
+# Energies (utils/distributions.py)
+# --------------------------------------------------------------------------------------
+class Energy:
+    """energy(x) -> [N]; grad(x) -> [N, D] (what tf.gradients(energy, x) yields)."""
+
+    def energy(self, x):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def grad(self, x):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def to(self, dtype):  # pragma: no cover - interface
+        raise NotImplementedError
+
+    def grad_autodiff(self, x):
+        """Mirror of Dynamics.grad_energy (utils/dynamics.py:217-218): reverse mode through energy()."""
+        xr = x.detach().clone().requires_grad_(True)
+        e = self.energy(xr)
+        (g,) = torch.autograd.grad(e.sum(), xr)
+        return g
+
+
+def _quad(x, mu, S):
+    """quadratic_gaussian (utils/distributions.py:31-32) without the N x N intermediate:
+    diag(0.5 * ((x-mu) S) (x-mu)^T) == 0.5 * rowsum(((x-mu) S) * (x-mu))."""
+    d = x - mu
+    return 0.5 * ((d @ S) * d).sum(1)
+
+
+class GaussianEnergy(Energy):
+    """Gaussian.get_energy_function (utils/distributions.py:50-57). S = inv(sigma) computed in
+    fp64 and cast to fp32 (utils/distributions.py:48,52)."""
+
+    def __init__(self, mu, S, dtype=torch.float32):
+        self.mu = torch.as_tensor(np.asarray(mu, dtype=np.float32)).to(dtype)
+        self.S = torch.as_tensor(np.asarray(S, dtype=np.float32)).to(dtype)
+
+    def to(self, dtype):
+        return GaussianEnergy(self.mu.numpy(), self.S.numpy(), dtype)
+
+    def energy(self, x):
+        return _quad(x, self.mu, self.S)
+
+    def grad(self, x):
+        # reverse mode of 0.5 * (dS) d^T: 0.5 * d S^T + 0.5 * d S
+        d = x - self.mu
+        return 0.5 * (d @ self.S.T) + 0.5 * (d @ self.S)
+
+
+class GMMEnergy(Energy):
+    """GMM.get_energy_function (utils/distributions.py:125-134): U = -logsumexp_i(-q_i(x) + log c_i),
+    c_i = pi_i / sqrt((2 pi)^k det Sigma_i) as fp32 (utils/distributions.py:120-123)."""
+
+    def __init__(self, mus, Ss, cs, dtype=torch.float32):
+        self.mus = [torch.as_tensor(np.asarray(m, dtype=np.float32)).to(dtype) for m in mus]
+        self.Ss = [torch.as_tensor(np.asarray(s, dtype=np.float32)).to(dtype) for s in Ss]
+        self.cs = [torch.as_tensor(np.float32(c)).to(dtype) for c in cs]
+        self.dtype = dtype
+
+    def to(self, dtype):
+        return GMMEnergy([m.numpy() for m in self.mus], [s.numpy() for s in self.Ss],
+                         [float(c) for c in self.cs], dtype)
+
+    def _V(self, x):
+        return torch.stack([-_quad(x, m, S) + torch.log(c)
+                            for m, S, c in zip(self.mus, self.Ss, self.cs)], dim=1)
+
+    def energy(self, x):
+        return -torch.logsumexp(self._V(x), dim=1)
+
+    def grad(self, x):
+        w = torch.softmax(self._V(x), dim=1)  # d(-logsumexp)/dV_i = -softmax_i ; dV_i/dx = -grad q_i
+        g = torch.zeros_like(x)
+        for i, (m, S) in enumerate(zip(self.mus, self.Ss)):
+            d = x - m
+            g = g + w[:, i:i + 1] * (0.5 * (d @ S.T) + 0.5 * (d @ S))
+        return g
+
+
+class RoughWellEnergy(Energy):
+    """RoughWell.get_energy_function (utils/distributions.py:90-97)."""
+
+    def __init__(self, eps, easy=False, dtype=torch.float32):
+        self.eps = float(eps)
+        self.easy = bool(easy)
+        self.dtype = dtype
+
+    def to(self, dtype):
+        return RoughWellEnergy(self.eps, self.easy, dtype)
+
+    def _scale(self, x):
+        # python floats meet fp32 tensors in the reference (utils/distributions.py:92-96): eps and
+        # eps*eps (evaluated in double) are each rounded to fp32 once; the fp64 twin keeps those values
+        e = torch.tensor(np.float32(self.eps)).to(x.dtype)
+        den = e if self.easy else torch.tensor(np.float32(self.eps * self.eps)).to(x.dtype)
+        return e, den
+
+    def energy(self, x):
+        e, den = self._scale(x)
+        n = (x * x).sum(1)
+        return 0.5 * n + e * torch.cos(x / den).sum(1)
+
+    def grad(self, x):
+        e, den = self._scale(x)
+        return x - e * torch.sin(x / den) / den
+
+
+class FunnelEnergy(Energy):
+    """GaussianFunnel.get_energy_function (utils/distributions.py:161-180); sigma=2, clip=4*sigma
+    (the ctor's clip argument is ignored, utils/distributions.py:156-159)."""
+
+    def __init__(self, sigma=2.0, clip=8.0, dtype=torch.float32):
+        self.sigma = float(sigma)
+        self.clip = float(clip)
+        self.dtype = dtype
+
+    def to(self, dtype):
+        return FunnelEnergy(self.sigma, self.clip, dtype)
+
+    def energy(self, x):
+        dt = x.dtype
+        v = x[:, 0]
+        log_p_v = (v / self.sigma) ** 2
+        s = torch.exp(v)
+        sum_sq = (x[:, 1:] ** 2).sum(1)
+        n = torch.tensor(float(x.shape[1] - 1), dtype=dt)
+        two_pi = torch.tensor(2.0 * np.pi, dtype=dt)
+        E = 0.5 * (log_p_v + sum_sq / s + n * torch.log(two_pi * s))
+        s_min = torch.exp(torch.tensor(-self.clip, dtype=dt))
+        s_max = torch.exp(torch.tensor(self.clip, dtype=dt))
+        E1 = 0.5 * (log_p_v + sum_sq / s_max + n * torch.log(two_pi * s_max))
+        E2 = 0.5 * (log_p_v + sum_sq / s_min + n * torch.log(two_pi * s_min))
+        E_ = torch.where(v > self.clip, E1, E)
+        E_ = torch.where(-self.clip > v, E2, E_)
+        return E_
+
+    def grad(self, x):
+        dt = x.dtype
+        v = x[:, 0]
+        s = torch.exp(v)
+        sum_sq = (x[:, 1:] ** 2).sum(1)
+        n = float(x.shape[1] - 1)
+        s_min = torch.exp(torch.tensor(-self.clip, dtype=dt))
+        s_max = torch.exp(torch.tensor(self.clip, dtype=dt))
+        hi = v > self.clip
+        lo = -self.clip > v
+        s_eff = torch.where(lo, s_min, torch.where(hi, s_max, s))
+        gv_in = v / (self.sigma ** 2) + 0.5 * (-sum_sq / s + n)
+        gv_out = v / (self.sigma ** 2)
+        gv = torch.where(hi | lo, gv_out, gv_in)
+        g = x / s_eff[:, None]
+        g = g.clone()
+        g[:, 0] = gv
+        return g
+
+
+# --------------------------------------------------------------------------------------
+# Dynamics (utils/dynamics.py)
+# --------------------------------------------------------------------------------------
+@dataclass
+class OracleDynamics:
+    """State of a reference ``Dynamics`` object (utils/dynamics.py:35-81)."""
+    x_dim: int
+    T: int
+    eps: float
+    energy_obj: Energy
+    mask: np.ndarray                       # [T, D] of {0,1}  (utils/dynamics.py:84-93)
+    xnet: Optional[Dict[str, torch.Tensor]] = None
+    vnet: Optional[Dict[str, torch.Tensor]] = None
+    hmc: bool = False
+    temperature: float = 1.0               # utils/dynamics.py:204-207 (1.0 unless use_temperature)
+    dtype: torch.dtype = torch.float32
+    _m: torch.Tensor = field(init=False, repr=False)
+
+    def __post_init__(self):
+        self._m = torch.as_tensor(np.asarray(self.mask, dtype=np.float32)).to(self.dtype)
+        self.energy_obj = self.energy_obj.to(self.dtype)
+        if self.xnet is not None:
+            self.xnet = net_cast(self.xnet, self.dtype)
+        if self.vnet is not None:
+            self.vnet = net_cast(self.vnet, self.dtype)
+        # eps = exp(alpha), alpha = log(eps) in fp32 (utils/dynamics.py:50-58)
+        e32 = torch.exp(torch.log(torch.tensor(self.eps, dtype=torch.float32)))
+        self._eps = e32.to(self.dtype)
+
+    # -- pieces -------------------------------------------------------------------------
+    def _XNet(self, a, b, tau, ae):
+        return net_zero(None, a, b, tau) if self.hmc else net_apply(self.xnet, a, b, tau, ae)
+
+    def _VNet(self, a, b, tau, ae):
+        return net_zero(None, a, b, tau) if self.hmc else net_apply(self.vnet, a, b, tau, ae)
+
+    def format_time(self, t: float, n: int):
+        """_format_time (utils/dynamics.py:99-105)."""
+        t_ = torch.tensor(float(t), dtype=self.dtype)
+        arg = torch.tensor(TWO_PI, dtype=self.dtype) * t_ / torch.tensor(float(self.T), dtype=self.dtype)
+        trig = torch.stack([torch.cos(arg), torch.sin(arg)])
+        return trig[None, :].repeat(n, 1)
+
+    def kinetic(self, v):
+        return 0.5 * (v * v).sum(1)  # utils/dynamics.py:107-108
+
+    def energy(self, x):
+        return self.energy_obj.energy(x) / torch.tensor(np.float32(self.temperature)).to(self.dtype)  # :203-212
+
+    def grad_energy(self, x):
+        return self.energy_obj.grad(x) / torch.tensor(np.float32(self.temperature)).to(self.dtype)  # :217-218
+
+    def hamiltonian(self, x, v):
+        return self.energy(x) + self.kinetic(v)  # :214-215
+
+    # -- steps --------------------------------------------------------------------------
+    def forward_step(self, x, v, step: int, ae_x=None, ae_v=None):
+        """_forward_step (utils/dynamics.py:115-157)."""
+        eps = self._eps
+        t = self.format_time(step, x.shape[0])
+        grad1 = self.grad_energy(x)
+        S1 = self._VNet(x, grad1, t, ae_v)
+        sv1 = 0.5 * eps * S1[0]
+        tv1 = S1[1]
+        fv1 = eps * S1[2]
+        v_h = v * torch.exp(sv1) + 0.5 * eps * (-(torch.exp(fv1) * grad1) + tv1)
+        m = self._m[int(step)]
+        mb = 1.0 - m
+        X1 = self._XNet(v_h, m * x, t, ae_x)
+        sx1 = eps * X1[0]
+        tx1 = X1[1]
+        fx1 = eps * X1[2]
+        y = m * x + mb * (x * torch.exp(sx1) + eps * (torch.exp(fx1) * v_h + tx1))
+        X2 = self._XNet(v_h, mb * y, t, ae_x)
+        sx2 = eps * X2[0]
+        tx2 = X2[1]
+        fx2 = eps * X2[2]
+        x_o = mb * y + m * (y * torch.exp(sx2) + eps * (torch.exp(fx2) * v_h + tx2))
+        grad2 = self.grad_energy(x_o)
+        S2 = self._VNet(x_o, grad2, t, ae_v)
+        sv2 = 0.5 * eps * S2[0]
+        tv2 = S2[1]
+        fv2 = eps * S2[2]
+        v_o = v_h * torch.exp(sv2) + 0.5 * eps * (-(torch.exp(fv2) * grad2) + tv2)
+        log_jac = (sv1 + sv2 + mb * sx1 + m * sx2).sum(1)
+        return x_o, v_o, log_jac
+
+    def backward_step(self, x_o, v_o, step: int, ae_x=None, ae_v=None):
+        """_backward_step (utils/dynamics.py:159-201)."""
+        eps = self._eps
+        t = self.format_time(step, x_o.shape[0])
+        grad1 = self.grad_energy(x_o)
+        S1 = self._VNet(x_o, grad1, t, ae_v)
+        sv2 = -0.5 * eps * S1[0]
+        tv2 = S1[1]
+        fv2 = eps * S1[2]
+        v_h = (v_o - 0.5 * eps * (-(torch.exp(fv2) * grad1) + tv2)) * torch.exp(sv2)
+        m = self._m[int(step)]
+        mb = 1.0 - m
+        X1 = self._XNet(v_h, mb * x_o, t, ae_x)
+        sx2 = -eps * X1[0]
+        tx2 = X1[1]
+        fx2 = eps * X1[2]
+        y = mb * x_o + m * (torch.exp(sx2) * (x_o - eps * (torch.exp(fx2) * v_h + tx2)))
+        X2 = self._XNet(v_h, m * y, t, ae_x)
+        sx1 = -eps * X2[0]
+        tx1 = X2[1]
+        fx1 = eps * X2[2]
+        x = m * y + mb * (torch.exp(sx1) * (y - eps * (torch.exp(fx1) * v_h + tx1)))
+        grad2 = self.grad_energy(x)
+        S2 = self._VNet(x, grad2, t, ae_v)
+        sv1 = -0.5 * eps * S2[0]
+        tv1 = S2[1]
+        fv1 = eps * S2[2]
+        v = torch.exp(sv1) * (v_h - 0.5 * eps * (-(torch.exp(fv1) * grad2) + tv1))
+        return x, v, (sv1 + sv2 + mb * sx1 + m * sx2).sum(1)
+
+    # -- T-step loops -------------------------------------------------------------------
+    def forward(self, x, v, log_jac=False, ae_x=None, ae_v=None):
+        """forward (utils/dynamics.py:246-272) with v injected (the reference draws it, :248)."""
+        x = x.to(self.dtype)
+        v = v.to(self.dtype)
+        X, V = x, v
+        j = torch.zeros(x.shape[0], dtype=self.dtype)
+        for t in range(self.T):
+            X, V, lj = self.forward_step(X, V, t, ae_x, ae_v)
+            j = j + lj
+        if log_jac:
+            return X, V, j
+        return X, V, self.p_accept(x, v, X, V, j)
+
+    def backward(self, x, v, log_jac=False, ae_x=None, ae_v=None):
+        """backward (utils/dynamics.py:274-300): steps T-1 ... 0 (:285)."""
+        x = x.to(self.dtype)
+        v = v.to(self.dtype)
+        X, V = x, v
+        j = torch.zeros(x.shape[0], dtype=self.dtype)
+        for t in range(self.T):
+            X, V, lj = self.backward_step(X, V, self.T - t - 1, ae_x, ae_v)
+            j = j + lj
+        if log_jac:
+            return X, V, j
+        return X, V, self.p_accept(x, v, X, V, j)
+
+    def p_accept(self, x0, v0, x1, v1, log_jac):
+        """p_accept (utils/dynamics.py:302-309)."""
+        e_new = self.hamiltonian(x1, v1)
+        e_old = self.hamiltonian(x0, v0)
+        v = e_old - e_new + log_jac
+        p = torch.exp(torch.minimum(v, torch.zeros_like(v)))
+        return torch.where(torch.isfinite(p), p, torch.zeros_like(p))
+
+
+# --------------------------------------------------------------------------------------
+# Sampler (utils/sampler.py)
+# --------------------------------------------------------------------------------------
+def tf_accept(x, Lx, px, u):
+    """tf_accept (utils/sampler.py:53-55) with the uniforms injected."""
+    mask = (px - u) >= 0.0
+    return torch.where(mask[:, None], Lx, x)
+
+
+def propose(x, dyn: OracleDynamics, *, direction=None, v_f=None, v_b=None, u=None,
+            init_v=None, do_mh_step=False, log_jac=False, ae_x=None, ae_v=None):
+    """propose (utils/sampler.py:28-51) with injected randomness.
+
+    Non-HMC: BOTH directions are run for every chain (each with its own fresh v) and blended by the
+    direction bit, exactly as the reference does (:34-44).  HMC: forward only with init_v (:29-31).
+    Returns (Lx, Lv, px, outputs) like the reference.
+    """
+    x = x.to(dyn.dtype)
+    if dyn.hmc:
+        v0 = init_v if init_v is not None else v_f
+        Lx, Lv, px = dyn.forward(x, v0.to(dyn.dtype), ae_x=ae_x, ae_v=ae_v)
+        return Lx, Lv, px, [tf_accept(x, Lx, px, u.to(dyn.dtype))]
+    mask = direction.to(dyn.dtype)[:, None]
+    Lx1, Lv1, px1 = dyn.forward(x, v_f, log_jac=log_jac, ae_x=ae_x, ae_v=ae_v)
+    Lx2, Lv2, px2 = dyn.backward(x, v_b, log_jac=log_jac, ae_x=ae_x, ae_v=ae_v)
+    Lx = mask * Lx1 + (1 - mask) * Lx2
+    Lv = None
+    if init_v is not None:
+        Lv = mask * Lv1 + (1 - mask) * Lv2
+    px = mask[:, 0] * px1 + (1 - mask)[:, 0] * px2
+    outputs = []
+    if do_mh_step:
+        outputs.append(tf_accept(x, Lx, px, u.to(dyn.dtype)))
+    return Lx, Lv, px, outputs
+
+
+def propose_selected(x, dyn: OracleDynamics, *, direction, v, log_jac=False):
+    """Same transition, but each chain runs only its selected direction with the single v it is given
+    (what a fused kernel does).  Equal to propose(...) with v_f = v_b = v wherever the unselected
+    direction stays finite.  Returns (Lx, Lv, px)."""
+    x = x.to(dyn.dtype)
+    d = direction.to(torch.bool)
+    Lx = torch.empty_like(x)
+    Lv = torch.empty_like(x)
+    px = torch.empty(x.shape[0], dtype=dyn.dtype)
+    if d.any():
+        a, b, c = dyn.forward(x[d], v[d].to(dyn.dtype), log_jac=log_jac)
+        Lx[d], Lv[d], px[d] = a, b, c
+    if (~d).any():
+        a, b, c = dyn.backward(x[~d], v[~d].to(dyn.dtype), log_jac=log_jac)
+        Lx[~d], Lv[~d], px[~d] = a, b, c
+    return Lx, Lv, px
+
+
+def chain_operator(init_x, dyn: OracleDynamics, nb_steps: int, *, init_v, directions, v_fs, v_bs, u=None,
+                   do_mh_step=False):
+    """chain_operator (utils/sampler.py:57-85): nb_steps proposals composed with accumulated log|J|, one
+    MH at the end.  Note the reference's quirk: sub-proposals ignore the carried v (fresh v per
+    direction, utils/sampler.py:35-36) but the final p_accept uses init_v and the last blended Lv."""
+    x = init_x.to(dyn.dtype)
+    v = init_v.to(dyn.dtype)
+    lj = torch.zeros(x.shape[0], dtype=dyn.dtype)
+    cx, cv = x, v
+    for s in range(nb_steps):
+        cx, cv, px, _ = propose(cx, dyn, direction=directions[s], v_f=v_fs[s].to(dyn.dtype),
+                                v_b=v_bs[s].to(dyn.dtype), init_v=cv, log_jac=True)
+        lj = lj + px
+    p = dyn.p_accept(x, v, cx, cv, lj)
+    outputs = []
+    if do_mh_step:
+        outputs.append(tf_accept(x, cx, p, u.to(dyn.dtype)))
+    return cx, cv, p, outputs
+
+
+# --------------------------------------------------------------------------------------
+# Synthetic problem builders shared by tests / bench
+# --------------------------------------------------------------------------------------
+def trunc_normal(rng: np.random.Generator, shape, std):
+    """variance_scaling_initializer(uniform=False) draws a truncated normal (+-2 sigma), utils/layers.py:32."""
+    out = rng.standard_normal(shape)
+    bad = np.abs(out) > 2.0
+    while bad.any():
+        out[bad] = rng.standard_normal(int(bad.sum()))
+        bad = np.abs(out) > 2.0
+    return (out * std).astype(np.float32)
+
+
+def make_net(rng, D, H, factor, regime="init"):
+    """Weights of one S/T/Q net.  regime 'init' follows SCGExperiment.ipynb:55-71 (embed factors 1/3,
+    factor/3, 1/3; hidden 1.0; heads 0.001; biases 0; log-scales 0).  'stress' (trained-like) uses head
+    factor 0.003, N(0, 0.05^2) biases and log-scales ~ U(-0.5, 0.5): S, Q are O(0.1), log|J| is O(1) and
+    accept probabilities spread over (0, 1) instead of sitting near the untrained value."""
+    def lin(i, o, f):
+        return trunc_normal(rng, (i, o), math.sqrt(1.3 * 2.0 * f / i))
+    hf = 0.001 if regime == "init" else 0.003
+    p = {
+        "W1": lin(D, H, 1.0 / 3), "W2": lin(D, H, factor / 3.0), "W3": lin(2, H, 1.0 / 3),
+        "W4": lin(H, H, 1.0), "Ws": lin(H, D, hf), "Wt": lin(H, D, hf), "Wq": lin(H, D, hf),
+    }
+    for k, n in (("b1", H), ("b2", H), ("b3", H), ("b4", H), ("bs", D), ("bt", D), ("bq", D)):
+        p[k] = (np.zeros(n, np.float32) if regime == "init"
+                else (0.05 * rng.standard_normal(n)).astype(np.float32))
+    for k in ("ls", "lq"):
+        p[k] = (np.zeros(D, np.float32) if regime == "init"
+                else rng.uniform(-0.5, 0.5, D).astype(np.float32))
+    return p
+
+
+def make_masks(rng, T, D):
+    """_init_mask (utils/dynamics.py:84-93): floor(D/2) ones at a random permutation's head, per step."""
+    m = np.zeros((T, D), np.float32)
+    for t in range(T):
+        m[t, rng.permutation(D)[: int(D / 2)]] = 1.0
+    return m

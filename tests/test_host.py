@@ -1,0 +1,143 @@
+"""CPU tests of the host side: Philox twin, layer descriptions, mask init, the C-ABI library's exports
+(no compute calls without a GPU), argument validation that happens before any CUDA call."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import util as U
+from l2hmc_b200 import _lib, layers, philox
+from l2hmc_b200.dynamics import Dynamics, init_mask
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    def kat(c, k):
+        c = [np.array([x], dtype=np.uint32) for x in c]
+        return [int(x[0]) for x in philox.philox4x32_10(*c, k[0], k[1])]
+    assert kat([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert kat([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert kat([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_philox_streams_statistics_and_sharding():
+    v = philox.normals(3, 5, 20000, 6)
+    assert abs(v.mean()) < 0.02 and abs(v.std() - 1) < 0.02
+    d, u = philox.direction_and_uniform(3, 5, 20000)
+    assert abs(d.mean() - 0.5) < 0.02 and 0 <= u.min() and u.max() < 1
+    # keyed by global chain id: a shard regenerates the same numbers
+    v2 = philox.normals(3, 5, 100, 6, chain_offset=700)
+    assert np.array_equal(v2, v[700:800])
+    d2, u2 = philox.direction_and_uniform(3, 5, 100, chain_offset=700)
+    assert np.array_equal(d2, d[700:800]) and np.array_equal(u2, u[700:800])
+    # different call counters decorrelate
+    assert not np.array_equal(philox.normals(3, 6, 100, 6), v[:100])
+
+
+def test_init_mask_follows_reference():
+    """floor(D/2) ones per step (utils/dynamics.py:84-93)."""
+    for D in (2, 50, 32, 5):
+        m = init_mask(D, 7, np.random.default_rng(0))
+        assert m.shape == (7, D) and m.dtype == np.float32
+        assert set(np.unique(m)) <= {0.0, 1.0}
+        assert (m.sum(1) == int(D / 2)).all()
+
+
+def test_linear_init_is_tf_variance_scaling():
+    """variance_scaling_initializer(factor=2f, FAN_IN, normal): truncated normal, std sqrt(1.3*2f/fan_in)."""
+    layers.manual_seed(0)
+    l = layers.Linear(400, 300, factor=0.5)
+    std = np.sqrt(1.3 * 2 * 0.5 / 400)
+    w = l.W.numpy()
+    assert np.abs(w).max() <= 2 * std + 1e-7
+    assert abs(w.std() - 0.88 * std) < 0.03 * std  # a +-2 sigma truncated normal has 0.88 of the std
+    assert float(l.b.abs().max()) == 0.0
+
+
+def test_compile_net_roundtrip_and_rejects_other_structures():
+    P = U.Problem(regime="stress", **U.CONFIGS["c1_scg2"])
+    net = P.net_factory()(2, "XNet", 2.0)
+    got = layers.compile_stq_net(net, 2)
+    for k, v in P.xnet.items():
+        assert np.array_equal(got[k], v), k
+    # the description is also callable, like the reference's layer objects
+    a = torch.randn(5, 2)
+    S, T, Q = net([a, a, torch.ones(5, 2), None])
+    So, To, Qo = U.O.net_apply(U.O.net_cast(P.xnet, torch.float32), a, a, torch.ones(5, 2))
+    assert torch.allclose(S, So, atol=1e-6) and torch.allclose(T, To, atol=1e-6) and torch.allclose(Q, Qo, atol=1e-6)
+    with pytest.raises(layers.NetStructureError):
+        layers.compile_stq_net(layers.Sequential([layers.Linear(2, 2)]), 2)
+    bad = P.net_factory()(2, "XNet", 2.0)
+    bad.layers[0].layers[3] = layers.Linear(784, 10)  # non-zero aux branch
+    with pytest.raises(layers.NetStructureError):
+        layers.compile_stq_net(bad, 2)
+
+
+def test_dynamics_host_state_and_loud_failure_without_gpu():
+    P = U.Problem(**U.CONFIGS["c1_scg2"])
+    d = Dynamics(2, P.dist.get_energy_function(), T=10, eps=0.1, net_factory=P.net_factory())
+    assert d.mask.shape == (10, 2) and d.width == 10 and abs(d.eps - 0.1) < 1e-7 and not d.hmc
+    d.mask = P.mask
+    with pytest.raises(ValueError):
+        d.mask = np.zeros((3, 2), np.float32)
+    with pytest.raises(TypeError):
+        Dynamics(2, lambda x: x.sum(1), T=10, eps=0.1, net_factory=P.net_factory())  # opaque callable
+    with pytest.raises(ValueError):
+        Dynamics(3, P.dist.get_energy_function(), T=10, eps=0.1, net_factory=P.net_factory())
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.L2HMCLibraryError):
+            d.forward(torch.zeros(4, 2))
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    """nvcc cross-compiles for sm_100a without a GPU; every function include/l2hmc.h declares must be
+    exported by libl2hmc.so and bound by the ctypes layer."""
+    _lib.build()
+    lib = _lib.load()
+    hdr = open(os.path.join(U.ROOT, "include", "l2hmc.h")).read()
+    declared = set(re.findall(r"\b(l2hmc_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"l2hmc_ctx"}
+    bound = {name for name, _, _ in _lib.EXPORTS}
+    assert declared == bound, (declared ^ bound)
+    for name in declared:
+        assert hasattr(lib, name)
+    assert b"sm_100a" in lib.l2hmc_version()
+
+
+def test_library_reports_errors_without_exceptions():
+    lib = _lib.load()
+    ctx = C.c_void_p()
+    cfg = _lib.Config(0, 10, 10, 0, 0, 0, 0.1)  # x_dim = 0
+    assert lib.l2hmc_create(C.byref(cfg), C.byref(ctx)) == 1  # L2HMC_EINVAL
+    assert b"x_dim" in lib.l2hmc_last_error(None)
+    if not torch.cuda.is_available():
+        cfg = _lib.Config(2, 10, 10, 0, 0, 0, 0.1)
+        assert lib.l2hmc_create(C.byref(cfg), C.byref(ctx)) == 2  # L2HMC_ECUDA: no device, no fallback
+        assert b"no CUDA device" in lib.l2hmc_last_error(None)
+
+
+def test_sass_is_sm100a_only():
+    """The shipped library holds sm_100a code and nothing else (no multi-arch fallback)."""
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([cuobjdump, "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    archs = set(re.findall(r"sm_(\d+a?)", out))
+    assert archs == {"100a"}, out
+
+
+def test_shard_bounds_partition():
+    from l2hmc_b200.sharding import shard_bounds
+    for n in (0, 1, 7, 64, 1 << 18, 1000003):
+        for w in (1, 2, 3, 8):
+            b = [shard_bounds(n, r, w) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            sizes = [h - l for l, h in b]
+            assert max(sizes) - min(sizes) <= 1
