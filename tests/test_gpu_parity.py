@@ -115,7 +115,9 @@ def test_components_match_oracle():
         e = dyn.energy(x).cpu().numpy()
         assert U.max_rel(e, o.energy(U.t64(d["x"])).numpy()) <= 1e-5, name
         g = dyn.grad_energy(x).cpu().numpy()
-        assert U.max_rel(g, o.grad_energy(U.t64(d["x"])).numpy()) <= 1e-5, name
+        # sin(x / 0.01): one fp32 ulp of the argument (|arg| ~ 300) is already 3e-5 in the sine
+        gtol = 5e-5 if name == "c4_rw32_hard" else 1e-5
+        assert U.max_rel(g, o.grad_energy(U.t64(d["x"])).numpy()) <= gtol, name
         k = dyn.kinetic(v).cpu().numpy()
         assert U.max_rel(k, o.kinetic(U.t64(d["v_f"])).numpy()) <= 1e-6, name
         h = dyn.hamiltonian(x, v).cpu().numpy()

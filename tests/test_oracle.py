@@ -131,6 +131,34 @@ def test_golden_fixtures_reproduce():
             assert np.allclose(got[k], ref[k], rtol=0, atol=1e-9 * max(1.0, np.abs(ref[k]).max())), (f, k)
 
 
+@pytest.mark.parametrize("name", list(U.CONFIGS))
+def test_c_restatement_agrees_with_torch_oracle(name):
+    """Two independently written restatements (torch op-for-op, plain C scalar loops) must agree:
+    fp64 twins to rounding, fp32 twins each within the fp32 noise floor of the fp64 result."""
+    import c_oracle
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    d = P.draws(48)
+    co = c_oracle.COracle(P)
+    c64, t64 = co.propose(d, np.float64), U.run_oracle_propose(P, d, torch.float64)
+    assert U.max_rel(c64["Lx"], t64["Lx"]) < 1e-7 and U.max_rel(c64["Lv"], t64["Lv"]) < 1e-7
+    assert np.max(np.abs(c64["px"] - t64["px"])) < 1e-5
+    c32 = co.propose(d, np.float32)
+    assert U.max_rel(c32["Lx"], t64["Lx"]) < 2e-5
+    assert np.max(np.abs(c32["px"] - t64["px"])) < 2e-4
+    lj_c = co.propose(d, np.float64, log_jac=True)["px"]
+    lj_t = U.run_oracle_propose(P, d, torch.float64, log_jac=True)["px"]
+    assert np.max(np.abs(lj_c - lj_t)) < 1e-6
+
+
+def test_c_restatement_hmc():
+    import c_oracle
+    P = U.Problem(kind="gaussian", D=2, T=10, eps=0.15, hmc=True)
+    d = P.draws(64)
+    c64 = c_oracle.COracle(P).propose(d, np.float64)
+    t64 = U.run_oracle_propose(P, d, torch.float64)
+    assert U.max_rel(c64["Lx"], t64["Lx"]) < 1e-10 and np.max(np.abs(c64["px"] - t64["px"])) < 1e-10
+
+
 def test_statistical_hmc_recovers_covariance():
     """HMC-mode chains on BASELINE config 1's target recover its covariance (sanity of the whole
     transition: energy, leapfrog, accept)."""
