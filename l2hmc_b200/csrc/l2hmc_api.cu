@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "kernel_tile.cuh"
+#include "kernel_tc.cuh"
 
 using namespace l2hmc;
 
@@ -48,6 +49,11 @@ struct l2hmc_ctx {
   size_t ev_used = 0;
   // host-call staging
   DevBuf hx, hv, hu, hxo, hvo, hpx, hxn;
+  // tensor-core kernel: pre-split weight streams
+  tc::TcDims td;
+  DevBuf tc_buf[2], tc_gbuf;
+  tc::TcNet tc_net[2];
+  bool tc_ok = false;  // shape / energy kind inside what kernel_tc covers
   uint8_t *hdir = nullptr, *hacc = nullptr;
   size_t hdir_n = 0, hacc_n = 0;
   cudaStream_t hstream = nullptr;
@@ -211,16 +217,146 @@ extern "C" const char *l2hmc_version(void) { return "l2hmc_b200 0.1 (sm_100a)"; 
 
 extern "C" const char *l2hmc_last_error(const l2hmc_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
 
-static int pick_kernel(l2hmc_ctx *ctx) {
+// ---- tensor-core kernel: host-side operand preparation ------------------------------------------------
+static inline float tf32_rna_host(float x) {  // cvt.rna.tf32.f32: round to nearest, ties away from zero
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  u = (u + 0x1000u) & 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+// Append the chunk stream of one B operand (B[n][k] = get(k, n), zero outside the real extent) to `out`:
+// for every K=8 step one chunk = {hi slab, lo slab}, each slab Npad x 8 floats in the canonical K-major
+// no-swizzle core-matrix order [k_core (2)][n_group (Npad/8)][row (8)][4 floats]  (LBO = Npad/8 * 128 B, SBO = 128 B).
+template <class Get>
+static void append_b_stream(std::vector<float> &out, int Kpad, int Npad, Get get) {
+  const int NG = Npad / 8;
+  for (int ks = 0; ks < Kpad / 8; ++ks) {
+    const size_t base = out.size();
+    out.resize(base + (size_t)16 * Npad, 0.f);
+    float *hi = out.data() + base, *lo = hi + (size_t)8 * Npad;
+    for (int n = 0; n < Npad; ++n)
+      for (int kk = 0; kk < 8; ++kk) {
+        const float w = get(8 * ks + kk, n);
+        const float h = tf32_rna_host(w);
+        const float l = tf32_rna_host(w - h);
+        const size_t idx = ((size_t)(kk >> 2) * NG + (n >> 3)) * 32 + (size_t)(n & 7) * 4 + (kk & 3);
+        hi[idx] = h;
+        lo[idx] = l;
+      }
+  }
+}
+
+static void tc_setup_dims(l2hmc_ctx *ctx) {
+  const Shape &sh = ctx->sh;
+  tc::TcDims &td = ctx->td;
+  td.K1 = 2 * sh.DP;
+  td.HK = round_up(sh.H, 8);
+  td.N1 = round_up(td.HK, 16);
+  td.N3 = round_up(3 * sh.DP, 16);
+  td.KG = round_up(sh.DP, 8);
+  td.NG = round_up(sh.DP, 16);
+  int nmax = td.N1 > td.N3 ? td.N1 : td.N3;
+  if (td.NG > nmax) nmax = td.NG;
+  td.slot_floats = 16 * nmax;
+  const long long state_bytes = (long long)tc::make_tclay(sh.DP, sh.T).ring * 4;
+  long long ns = (232448LL - 1024 - state_bytes) / ((long long)td.slot_floats * 4);
+  td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
+  ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
+}
+
+static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
+  const Shape &sh = ctx->sh;
+  const tc::TcDims &td = ctx->td;
+  const int D = sh.D, H = sh.H, DP = sh.DP, T = sh.T;
+  std::vector<float> img;
+  append_b_stream(img, td.K1, td.N1, [&](int k, int n) -> float {  // embed: rows [a | b]
+    if (n >= H) return 0.f;
+    if (k < DP) return k < D ? p->W1[(size_t)k * H + n] : 0.f;
+    const int d = k - DP;
+    return d < D ? p->W2[(size_t)d * H + n] : 0.f;
+  });
+  append_b_stream(img, td.HK, td.N1, [&](int k, int n) -> float { return (k < H && n < H) ? p->W4[(size_t)k * H + n] : 0.f; });
+  append_b_stream(img, td.HK, td.N3, [&](int k, int n) -> float {  // heads: columns S | T | Q blocks of DP
+    if (k >= H || n >= 3 * DP) return 0.f;
+    const int blk = n / DP, d = n - blk * DP;
+    if (d >= D) return 0.f;
+    const float *W = blk == 0 ? p->Ws : (blk == 1 ? p->Wt : p->Wq);
+    return W[(size_t)k * D + d];
+  });
+  const size_t nimg = img.size(), ntb = (size_t)T * td.N1, nb4 = td.N1, nbh = td.N3, nes = DP;
+  std::vector<float> buf(nimg + ntb + nb4 + nbh + 2 * nes, 0.f);
+  memcpy(buf.data(), img.data(), nimg * sizeof(float));
+  float *tb = buf.data() + nimg, *b4 = tb + ntb, *bh = b4 + nb4, *es = bh + nbh, *eq = es + nes;
+  for (int t = 0; t < T; ++t) {
+    const float arg = 6.2831855f * (float)t / (float)T;  // utils/dynamics.py:99-105 in fp32
+    const float ct = cosf(arg), st = sinf(arg);
+    for (int j = 0; j < H; ++j) tb[(size_t)t * td.N1 + j] = (p->b1[j] + p->b2[j]) + (fmaf(st, p->W3[H + j], ct * p->W3[j]) + p->b3[j]);
+  }
+  for (int j = 0; j < H; ++j) b4[j] = p->b4[j];
+  for (int d = 0; d < DP; ++d) {
+    es[d] = eq[d] = 1.f;
+    if (d < D) {
+      bh[d] = p->bs[d];
+      bh[DP + d] = p->bt[d];
+      bh[2 * DP + d] = p->bq[d];
+      es[d] = expf(p->scale_s[d]);
+      eq[d] = expf(p->scale_q[d]);
+    }
+  }
+  int rc = ensure(ctx, ctx->tc_buf[net_id], buf.size());
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(ctx->tc_buf[net_id].p, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
+  tc::TcNet &n = ctx->tc_net[net_id];
+  n.img = ctx->tc_buf[net_id].p;
+  n.tb = n.img + nimg;
+  n.b4 = n.tb + ntb;
+  n.bh = n.b4 + nb4;
+  n.es = n.bh + nbh;
+  n.eq = n.es + nes;
+  return L2HMC_OK;
+}
+
+static int tc_pack_gaussian(l2hmc_ctx *ctx, const float *Ssym_padded /* [DP][LDS] host */) {
+  const Shape &sh = ctx->sh;
+  const tc::TcDims &td = ctx->td;
+  std::vector<float> img;
+  append_b_stream(img, td.KG, td.NG, [&](int k, int n) -> float {  // g_n = sum_k d_k Ssym[k][n]
+    return (k < sh.D && n < sh.D) ? Ssym_padded[(size_t)k * sh.LDS + n] : 0.f;
+  });
+  int rc = ensure(ctx, ctx->tc_gbuf, img.size());
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(ctx->tc_gbuf.p, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return L2HMC_OK;
+}
+
+// Which kernel a transition launches: the explicit request, or for AUTO the generic tile kernel
+// (kernel_tc is opt-in until its parity is signed off on the GPU).
+static int resolve_kernel(l2hmc_ctx *ctx, int *out) {
   const Shape &sh = ctx->sh;
   int k = ctx->cfg.kernel;
   if (k == L2HMC_KERNEL_AUTO) k = L2HMC_KERNEL_TILE;
   if (k == L2HMC_KERNEL_TILE) {
     if (sh.DP > 64 || (!sh.hmc && sh.HP > 128))
       return fail(ctx, L2HMC_EUNSUPPORTED, "tile kernel covers x_dim <= 64 and width <= 128 (got %d, %d)", sh.D, sh.H);
+  } else if (k == L2HMC_KERNEL_TC) {
+    if (!ctx->tc_ok) return fail(ctx, L2HMC_EUNSUPPORTED, "tensor-core kernel does not cover this shape (x_dim %d, width %d, hmc %d)", sh.D, sh.H, sh.hmc);
+    if (ctx->energy_set && !((ctx->en.kind == L2HMC_ENERGY_GAUSSIAN && ctx->en.ncomp == 1) || ctx->en.kind == L2HMC_ENERGY_ROUGHWELL))
+      return fail(ctx, L2HMC_EUNSUPPORTED, "tensor-core kernel covers the Gaussian and RoughWell energies (kind %d given)", ctx->en.kind);
   } else {
     return fail(ctx, L2HMC_EUNSUPPORTED, "kernel kind %d not available in this build", k);
   }
+  *out = k;
+  return L2HMC_OK;
+}
+
+static int pick_kernel(l2hmc_ctx *ctx) {
+  tc_setup_dims(ctx);
+  int k = 0;
+  int rc = resolve_kernel(ctx, &k);
+  if (rc) return rc;
   ctx->kernel = k;
   return L2HMC_OK;
 }
@@ -269,7 +405,8 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   DevBuf *bufs[] = {&ctx->net_packed[0], &ctx->net_packed[1], &ctx->net_raw[0], &ctx->net_raw[1], &ctx->mask,
-                    &ctx->energy_buf, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn};
+                    &ctx->energy_buf, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn,
+                    &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   if (ctx->hdir) cudaFree(ctx->hdir);
@@ -370,6 +507,10 @@ extern "C" int l2hmc_set_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params 
     n.Wemb = b; n.tb = n.Wemb + nWemb; n.W4 = n.tb + ntb; n.b4 = n.W4 + nW4;
     n.Wh = n.b4 + nb4; n.bh = n.Wh + nWh; n.es = n.bh + nbh; n.eq = n.es + nes;
   }
+  if (ctx->tc_ok) {
+    rc = tc_pack_net(ctx, net_id, p);
+    if (rc) return rc;
+  }
   ctx->net_set[net_id] = true;
   return L2HMC_OK;
 }
@@ -435,6 +576,10 @@ extern "C" int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const floa
     int rc = ensure(ctx, ctx->energy_buf, buf.size());
     if (rc) return rc;
     CUDA_TRY(ctx, cudaMemcpy(ctx->energy_buf.p, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (ctx->tc_ok && kind == L2HMC_ENERGY_GAUSSIAN) {
+      rc = tc_pack_gaussian(ctx, buf.data() + nmu);
+      if (rc) return rc;
+    }
     en.ncomp = n_comp;
     en.mu = ctx->energy_buf.p;
     en.Ssym = en.mu + nmu;
@@ -509,7 +654,31 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     ctx->ev_used += 2;
     CUDA_TRY(ctx, cudaEventRecord(e0, stream));
   }
-  if (ctx->kernel == L2HMC_KERNEL_TILE) {
+  int kernel = 0;
+  {
+    int rc = resolve_kernel(ctx, &kernel);  // the energy kind may have been set after l2hmc_create
+    if (rc) return rc;
+    ctx->kernel = kernel;
+  }
+  if (kernel == L2HMC_KERNEL_TC) {
+    tc::TcArgs TA;
+    TA.sh = ctx->sh;
+    TA.td = ctx->td;
+    TA.xnet = ctx->tc_net[0];
+    TA.vnet = ctx->tc_net[1];
+    TA.gimg = ctx->tc_gbuf.p;
+    TA.en = ctx->en;
+    TA.mask = ctx->mask.p;
+    TA.io = K.io;
+    const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
+    static thread_local size_t tc_configured = 0;
+    if (smem > tc_configured) {
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      tc_configured = smem;
+    }
+    const long long blocks = (a->n + tc::MT - 1) / tc::MT;
+    tc::tc_transition_kernel<<<(unsigned)blocks, tc::NTHREADS, smem, stream>>>(TA);
+  } else if (kernel == L2HMC_KERNEL_TILE) {
     const size_t smem = tile::smem_bytes(ctx->sh.DP, ctx->sh.HP, ctx->sh.T);
     static thread_local size_t configured = 0;
     if (smem > configured) {

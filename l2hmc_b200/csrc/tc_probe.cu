@@ -140,7 +140,127 @@ static double run(int N, int K, int layout_mode, int terms, int swap, const std:
   return err;
 }
 
-int main() {
+// ---- micro-benchmark 1: tensor-pipe rate for back-to-back TS-mode tf32 MMAs of one tile shape ----------
+__global__ void __launch_bounds__(128, 1) mma_rate_kernel(int N, int nmma, long long *cycles_out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(8) uint64_t mbar;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  float *Bs = reinterpret_cast<float *>(smem_raw);
+  for (int i = tid; i < N * 8; i += 128) Bs[i] = 0.001f * (i % 17);
+  if (warp == 0) tmem_alloc(&tmem_base_slot, 512);
+  if (tid == 0) {
+    mbar_init(&mbar, 1);
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  {
+    float z[8] = {1.f, 0.5f, 0.25f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    tmem_st8(tmem + 256 + (((uint32_t)(warp * 32)) << 16), z);
+    tmem_wait_st();
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_tf32(128, N);
+    const uint64_t d = make_smem_desc(smem_u32(Bs), (N / 8) * 128, 128);
+    const long long t0 = clock64();
+    for (int i = 0; i < nmma; ++i) mma_tf32_ts(tmem, tmem + 256, d, idesc, i > 0);
+    tcgen05_commit(&mbar);
+    mbar_wait(&mbar, 0);
+    const long long t1 = clock64();
+    cycles_out[blockIdx.x] = t1 - t0;
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---- micro-benchmark 2: every CTA streams the same weight image from L2 into a shared-memory ring with
+// 1-D TMA bulk copies (the pattern kernel_tc uses for the B operands) -------------------------------------
+__global__ void __launch_bounds__(128, 1) stream_kernel(const uint8_t *img, int img_bytes, int chunk_bytes, int nslots,
+                                                        int reps, long long *cycles_out) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full[8];
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < nslots; ++s) mbar_init(&full[s], 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const int nchunks = img_bytes / chunk_bytes;
+    const long long total = (long long)nchunks * reps;
+    const long long t0 = clock64();
+    long long issued = 0, done = 0;
+    for (; issued < nslots && issued < total; ++issued) {
+      const int s = (int)(issued % nslots);
+      mbar_arrive_expect_tx(&full[s], chunk_bytes);
+      bulk_g2s(smem_raw + (size_t)s * chunk_bytes, img + (size_t)(issued % nchunks) * chunk_bytes, chunk_bytes, &full[s]);
+    }
+    for (; done < total; ++done) {
+      const int s = (int)(done % nslots);
+      mbar_wait(&full[s], (uint32_t)((done / nslots) & 1));
+      if (issued < total) {  // slot is free again (nobody consumes here): refill it
+        mbar_arrive_expect_tx(&full[s], chunk_bytes);
+        bulk_g2s(smem_raw + (size_t)s * chunk_bytes, img + (size_t)(issued % nchunks) * chunk_bytes, chunk_bytes, &full[s]);
+        ++issued;
+      }
+    }
+    cycles_out[blockIdx.x] = clock64() - t0;
+  }
+  __syncthreads();
+}
+
+static void micro() {
+  long long *dc;
+  cudaMalloc(&dc, 1024 * sizeof(long long));
+  std::vector<long long> hc(1024);
+  int clk_khz = 0;
+  cudaDeviceGetAttribute(&clk_khz, cudaDevAttrClockRate, 0);
+  for (int N : {64, 80, 112, 160, 256}) {
+    for (int grid : {1, 148}) {
+      const int nmma = 2000;
+      cudaFuncSetAttribute(mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      mma_rate_kernel<<<grid, 128, 64 * 1024>>>(N, nmma, dc);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("mma_rate CUDA error: %s\n", cudaGetErrorString(e)); exit(3); }
+      cudaMemcpy(hc.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long mx = 0;
+      for (int i = 0; i < grid; ++i) mx = hc[i] > mx ? hc[i] : mx;
+      printf("MMA_RATE N=%d grid=%d: %.1f cycles per 128xNx8 tf32 MMA (%.0f MAC/cycle/SM)\n", N, grid, (double)mx / nmma,
+             128.0 * N * 8 * nmma / mx);
+    }
+  }
+  const int img_bytes = 320 * 1024;
+  uint8_t *img;
+  cudaMalloc(&img, img_bytes);
+  cudaMemset(img, 1, img_bytes);
+  for (int chunk : {8192, 16384, 32768}) {
+    for (int grid : {1, 148, 296}) {
+      const int nslots = 4, reps = 40;
+      cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, nslots * chunk);
+      stream_kernel<<<grid, 128, nslots * chunk>>>(img, img_bytes, chunk, nslots, reps, dc);
+      cudaError_t e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) { printf("stream CUDA error: %s\n", cudaGetErrorString(e)); exit(4); }
+      cudaMemcpy(hc.data(), dc, grid * sizeof(long long), cudaMemcpyDeviceToHost);
+      long long mx = 0;
+      for (int i = 0; i < grid; ++i) mx = hc[i] > mx ? hc[i] : mx;
+      const double bytes = (double)img_bytes * reps;
+      printf("STREAM chunk=%d slots=%d grid=%d: %.1f B/cycle per CTA, %.0f B/cycle chip-wide (max over CTAs %lld cycles)\n", chunk,
+             nslots, grid, bytes / mx, bytes * grid / mx, mx);
+    }
+  }
+  cudaFree(img);
+  cudaFree(dc);
+}
+
+int main(int argc, char **argv) {
+  if (argc > 1 && argv[1][0] == 'm') { micro(); return 0; }
   const int shapes[3][2] = {{112, 104}, {160, 104}, {64, 56}};
   for (auto &s : shapes) {
     const int N = s[0], K = s[1];

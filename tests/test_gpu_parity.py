@@ -301,3 +301,39 @@ def test_full_size_properties_config2():
     o = P.oracle(torch.float64)
     _, _, po = o.forward(U.t64(x[idx].cpu().numpy()), U.t64(v[idx].cpu().numpy()))
     assert float(np.max(np.abs(p[idx].cpu().numpy() - po.numpy()))) <= 1e-4
+
+
+# ---- tensor-core kernel (tcgen05, 3xTF32) ---------------------------------------------------------------
+@pytest.mark.parametrize("name,n,regime", [
+    ("c2_scg50", 320, "init"),
+    ("c2_scg50", 320, "stress"),
+    ("c2_scg50", 129, "stress"),   # ragged: one full 128-chain tile + 1
+    ("c4_rw32", 320, "stress"),
+    ("c4_rw32_hard", 200, "stress"),
+])
+def test_tc_kernel_matches_oracle(name, n, regime):
+    P = U.Problem(regime=regime, **U.CONFIGS[name])
+    dyn = P.product(kernel="tc")
+    rep, _ = U.parity_report(P, n, dyn=dyn)
+    assert dyn.kernel_name == "tc_3xtf32"
+    _check(rep)
+
+
+def test_tc_kernel_multi_transition_and_philox():
+    """Fused transitions equal the host loop, and in-kernel Philox equals injected randomness (TC kernel)."""
+    P = U.Problem(regime="stress", **U.CONFIGS["c2_scg50"])
+    dyn = P.product(seed=5, kernel="tc")
+    x0 = torch.as_tensor(P.draws(300)["x"]).cuda()
+    K = 3
+    a = dyn._transition(x0, dir_mode=3, do_mh=True, n_transitions=K, counter=100)
+    x = x0
+    for t in range(K):
+        b = dyn._transition(x, dir_mode=3, do_mh=True, counter=100 + t)
+        x = b["x_next"]
+    assert torch.equal(a["x_next"], b["x_next"]) and torch.equal(a["px"], b["px"])
+    # same numbers as the tile kernel's generator -> same decisions up to rounding
+    tile = P.product(seed=5, kernel="tile")
+    c = tile._transition(x0, dir_mode=3, do_mh=True, counter=100)
+    d = dyn._transition(x0, dir_mode=3, do_mh=True, counter=100)
+    assert U.max_rel(d["Lx"].cpu().numpy(), c["Lx"].cpu().numpy()) <= 2e-5
+    assert float((d["px"] - c["px"]).abs().max()) <= 2e-4

@@ -27,6 +27,8 @@ def parity(quick, kernel):
     cases = [("c1_scg2", 200), ("c2_scg50", 192), ("c3_mog2", 256), ("c4_rw32", 192), ("c4_rw32_hard", 192), ("funnel3", 128)]
     if quick:
         cases = cases[:2]
+    if kernel == "tc":  # what the tensor-core kernel covers
+        cases = [("c2_scg50", 192), ("c2_scg50", 500), ("c4_rw32", 192), ("c4_rw32_hard", 192)]
     for name, n in cases:
         for regime in ("init", "stress"):
             try:
@@ -37,7 +39,7 @@ def parity(quick, kernel):
             except Exception:
                 print("PARITY %s %s FAILED" % (name, regime))
                 traceback.print_exc()
-    for kind, D in (("gaussian", 2), ("gaussian", 50), ("roughwell", 32)):
+    for kind, D in (() if kernel == "tc" else (("gaussian", 2), ("gaussian", 50), ("roughwell", 32))):
         try:
             P = U.Problem(kind=kind, D=D, T=10, eps=0.05, hmc=True)
             rep, _ = U.parity_report(P, 192, dyn=P.product(kernel=kernel))
@@ -49,7 +51,10 @@ def parity(quick, kernel):
 
 def timing(kernel):
     from l2hmc_b200 import _lib
-    for name, n in (("c2_scg50", 1 << 18), ("c4_rw32", 1 << 17), ("c1_scg2", 1 << 18), ("c3_mog2", 1 << 18)):
+    cfgs = (("c2_scg50", 1 << 18), ("c4_rw32", 1 << 17), ("c1_scg2", 1 << 18), ("c3_mog2", 1 << 18))
+    if kernel == "tc":
+        cfgs = cfgs[:2]
+    for name, n in cfgs:
         try:
             P = U.Problem(regime="stress", **U.CONFIGS[name])
             dyn = P.product(kernel=kernel)
