@@ -1,0 +1,277 @@
+// One-chain-per-thread transition kernel for the small nets of the reference's notebook
+// (SCGExperiment.ipynb: x_dim 2, width 10) and anything with x_dim <= 4, width <= 16.
+//
+// With D = 2 and H = 10 a net call is 200 MACs: there is nothing to tile.  Each thread keeps x, v, grad U and
+// both hidden layers of its chain in registers for the whole transition; the (zero-padded) weights of both
+// nets sit in shared memory and every lane reads the same word (broadcast), so a warp needs no shuffle, no
+// barrier and no divergence except the per-chain direction predicate, which is folded arithmetically.
+// Math follows utils/dynamics.py:115-201,246-309 and utils/sampler.py:28-55 exactly like kernel_tile.cuh.
+#pragma once
+#include "common.cuh"
+
+namespace l2hmc {
+namespace small {
+
+constexpr int NT = 128;
+
+// shared-memory image of one net, all extents padded to the template sizes (DM, HM)
+template <int DM, int HM>
+struct NetS {
+  float W1[DM][HM], W2[DM][HM], W4[HM][HM], b4[HM];
+  float Ws[HM][DM], Wt[HM][DM], Wq[HM][DM], bs[DM], bt[DM], bq[DM], es[DM], eq[DM];
+};
+
+struct SmallArgs {
+  Shape sh;
+  NetRaw xnet, vnet;   // reference-layout device copies
+  const float *tbx, *tbv;  // [T][LDE] folded time/bias tables (b1 + b2 + tau(t) W3 + b3), NetDev::tb
+  EnergyDev en;
+  const float *mask;   // [T][DP]
+  TransitionIO io;
+};
+
+template <int DM, int HM>
+__device__ __forceinline__ void load_net(NetS<DM, HM> &s, const NetRaw &w, int D, int H) {
+  for (int i = threadIdx.x; i < DM * HM; i += NT) {
+    const int d = i / HM, j = i - d * HM;
+    const bool ok = d < D && j < H;
+    s.W1[d][j] = ok ? w.W1[d * H + j] : 0.f;
+    s.W2[d][j] = ok ? w.W2[d * H + j] : 0.f;
+    const int jj = i / DM, dd = i - jj * DM;  // [HM][DM] view of the same index range
+    const bool ok2 = jj < H && dd < D;
+    s.Ws[jj][dd] = ok2 ? w.Ws[jj * D + dd] : 0.f;
+    s.Wt[jj][dd] = ok2 ? w.Wt[jj * D + dd] : 0.f;
+    s.Wq[jj][dd] = ok2 ? w.Wq[jj * D + dd] : 0.f;
+  }
+  for (int i = threadIdx.x; i < HM * HM; i += NT) {
+    const int a = i / HM, b = i - a * HM;
+    s.W4[a][b] = (a < H && b < H) ? w.W4[a * H + b] : 0.f;
+  }
+  for (int i = threadIdx.x; i < HM; i += NT) s.b4[i] = i < H ? w.b4[i] : 0.f;
+  for (int i = threadIdx.x; i < DM; i += NT) {
+    const bool ok = i < D;
+    s.bs[i] = ok ? w.bs[i] : 0.f;
+    s.bt[i] = ok ? w.bt[i] : 0.f;
+    s.bq[i] = ok ? w.bq[i] : 0.f;
+    s.es[i] = ok ? expf(w.ls[i]) : 1.f;
+    s.eq[i] = ok ? expf(w.lq[i]) : 1.f;
+  }
+}
+
+// [S, T, Q] = net([a, b, t]) with the time/bias row tb (already selected for this chain's direction)
+template <int DM, int HM>
+__device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb, const float (&a)[DM], const float (&b)[DM],
+                                         float (&S)[DM], float (&T)[DM], float (&Q)[DM]) {
+  float h1[HM], h2[HM];
+#pragma unroll
+  for (int j = 0; j < HM; ++j) h1[j] = tb[j];
+#pragma unroll
+  for (int d = 0; d < DM; ++d)
+#pragma unroll
+    for (int j = 0; j < HM; ++j) h1[j] = fmaf(b[d], n.W2[d][j], fmaf(a[d], n.W1[d][j], h1[j]));
+#pragma unroll
+  for (int j = 0; j < HM; ++j) {
+    h1[j] = fmaxf(h1[j], 0.f);
+    h2[j] = n.b4[j];
+  }
+#pragma unroll
+  for (int i = 0; i < HM; ++i)
+#pragma unroll
+    for (int j = 0; j < HM; ++j) h2[j] = fmaf(h1[i], n.W4[i][j], h2[j]);
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    S[d] = n.bs[d];
+    T[d] = n.bt[d];
+    Q[d] = n.bq[d];
+  }
+#pragma unroll
+  for (int i = 0; i < HM; ++i) {
+    const float h = fmaxf(h2[i], 0.f);
+#pragma unroll
+    for (int d = 0; d < DM; ++d) {
+      S[d] = fmaf(h, n.Ws[i][d], S[d]);
+      T[d] = fmaf(h, n.Wt[i][d], T[d]);
+      Q[d] = fmaf(h, n.Wq[i][d], Q[d]);
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DM; ++d) {
+    S[d] = n.es[d] * tanhf(S[d]);
+    Q[d] = n.eq[d] * tanhf(Q[d]);
+  }
+}
+
+template <int DM>
+__device__ __forceinline__ void grad_small(const EnergyDev &en, const Shape &sh, const float (&x)[DM], float (&g)[DM]) {
+  float xs[DM], gl[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) { xs[d] = x[d]; gl[d] = 0.f; }
+  grad_chain(en, sh, xs, 1, gl, 1);
+#pragma unroll
+  for (int d = 0; d < DM; ++d) g[d] = d < sh.D ? gl[d] : 0.f;
+}
+
+template <int DM, int HM>
+__global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_constant__ SmallArgs A) {
+  extern __shared__ __align__(16) float smem_small[];
+  const Shape &sh = A.sh;
+  const TransitionIO &io = A.io;
+  const int D = sh.D, H = sh.H, T = sh.T;
+  NetS<DM, HM> &NX = *reinterpret_cast<NetS<DM, HM> *>(smem_small);
+  NetS<DM, HM> &NV = *(&NX + 1);
+  float *tbx = reinterpret_cast<float *>(&NV + 1);  // [T][HM]
+  float *tbv = tbx + T * HM;
+  float *msk = tbv + T * HM;                         // [T][DM]
+  if (!sh.hmc) {
+    load_net(NX, A.xnet, D, H);
+    load_net(NV, A.vnet, D, H);
+    for (int i = threadIdx.x; i < T * HM; i += NT) {
+      const int t = i / HM, j = i - t * HM;
+      tbx[i] = j < H ? A.tbx[t * sh.LDE + j] : 0.f;  // rows of the tile-layout table (stride LDE)
+      tbv[i] = j < H ? A.tbv[t * sh.LDE + j] : 0.f;
+    }
+  }
+  for (int i = threadIdx.x; i < T * DM; i += NT) {
+    const int t = i / DM, d = i - t * DM;
+    msk[i] = d < D ? A.mask[t * sh.DP + d] : 0.f;
+  }
+  __syncthreads();
+
+  const long long g = (long long)blockIdx.x * NT + threadIdx.x;
+  if (g >= io.n) return;
+  const float eps = sh.eps;
+  float x[DM], v[DM], gr[DM], xin[DM];
+#pragma unroll
+  for (int d = 0; d < DM; ++d) x[d] = d < D ? io.x[g * D + d] : 0.f;
+
+  for (int tr = 0; tr < io.n_transitions; ++tr) {
+    const unsigned long long ctr = io.counter + (unsigned long long)tr;
+    float x0[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) x0[d] = x[d];
+    if (io.v != nullptr) {
+#pragma unroll
+      for (int d = 0; d < DM; ++d) v[d] = d < D ? io.v[((long long)tr * io.n + g) * D + d] : 0.f;
+    } else {
+      float z[4];
+      philox_normals4(io.seed, ctr, io.chain_offset + g, 0, z);
+#pragma unroll
+      for (int d = 0; d < DM; ++d) v[d] = d < D ? z[d] : 0.f;  // DM <= 4: one Philox block
+    }
+    int pd = 1;
+    float pu = 0.f;
+    if (io.dir_mode == 3 || (io.do_mh && io.u == nullptr)) philox_dir_u(io.seed, ctr, io.chain_offset + g, pd, pu);
+    bool fwd = true;
+    if (io.dir_mode == 1) fwd = false;
+    else if (io.dir_mode == 2) fwd = io.dir[(long long)tr * io.n + g] != 0;
+    else if (io.dir_mode == 3) fwd = pd != 0;
+    if (io.do_mh && io.u != nullptr) pu = io.u[(long long)tr * io.n + g];
+
+    grad_small<DM>(A.en, sh, x, gr);
+    float kin = 0.f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) kin = fmaf(v[d], v[d], kin);
+    float xs0[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) xs0[d] = x[d];
+    const float h_old = energy_chain(A.en, sh, xs0, 1) + 0.5f * kin;
+    float lj = 0.f;
+
+    for (int it = 0; it < T; ++it) {
+      const int t = fwd ? it : T - 1 - it;
+      float S[DM], Tt[DM], Q[DM];
+      // ---- v half step ----
+      if (sh.hmc) {
+#pragma unroll
+        for (int d = 0; d < DM; ++d) S[d] = Tt[d] = Q[d] = 0.f;
+      } else {
+        net_eval(NV, tbv + t * HM, x, gr, S, Tt, Q);
+      }
+#pragma unroll
+      for (int d = 0; d < DM; ++d) {
+        const float sv = fwd ? (0.5f * eps) * S[d] : (-0.5f * eps) * S[d];
+        const float cterm = (0.5f * eps) * (-(expf(eps * Q[d]) * gr[d]) + Tt[d]);
+        const float e = expf(sv);
+        v[d] = fwd ? (v[d] * e + cterm) : ((v[d] - cterm) * e);
+        lj += sv;
+      }
+      // ---- two masked x updates ----
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        float k[DM];
+#pragma unroll
+        for (int d = 0; d < DM; ++d) {
+          const float m = msk[t * DM + d];
+          k[d] = (fwd == (half == 0)) ? m : 1.f - m;
+          xin[d] = k[d] * x[d];
+        }
+        if (sh.hmc) {
+#pragma unroll
+          for (int d = 0; d < DM; ++d) S[d] = Tt[d] = Q[d] = 0.f;
+        } else {
+          net_eval(NX, tbx + t * HM, v, xin, S, Tt, Q);
+        }
+#pragma unroll
+        for (int d = 0; d < DM; ++d) {
+          const float uu = 1.f - k[d];
+          const float sx = fwd ? eps * S[d] : -eps * S[d];
+          const float inner = eps * (expf(eps * Q[d]) * v[d] + Tt[d]);
+          const float e = expf(sx);
+          const float nx = fwd ? (x[d] * e + inner) : (e * (x[d] - inner));
+          x[d] = k[d] * x[d] + uu * nx;
+          lj += uu * sx;
+        }
+      }
+      // ---- v half step at the new x ----
+      grad_small<DM>(A.en, sh, x, gr);
+      if (sh.hmc) {
+#pragma unroll
+        for (int d = 0; d < DM; ++d) S[d] = Tt[d] = Q[d] = 0.f;
+      } else {
+        net_eval(NV, tbv + t * HM, x, gr, S, Tt, Q);
+      }
+#pragma unroll
+      for (int d = 0; d < DM; ++d) {
+        const float sv = fwd ? (0.5f * eps) * S[d] : (-0.5f * eps) * S[d];
+        const float cterm = (0.5f * eps) * (-(expf(eps * Q[d]) * gr[d]) + Tt[d]);
+        const float e = expf(sv);
+        v[d] = fwd ? (v[d] * e + cterm) : ((v[d] - cterm) * e);
+        lj += sv;
+      }
+    }
+    if (sh.hmc) lj = 0.f;
+    kin = 0.f;
+#pragma unroll
+    for (int d = 0; d < DM; ++d) kin = fmaf(v[d], v[d], kin);
+    float xs1[DM];
+#pragma unroll
+    for (int d = 0; d < DM; ++d) xs1[d] = x[d];
+    const float h_new = energy_chain(A.en, sh, xs1, 1) + 0.5f * kin;
+    const float p = accept_prob(h_old, h_new, lj);
+    const float px = io.log_jac ? lj : p;
+    const bool acc = io.do_mh && (px - pu >= 0.f);
+    const bool last = tr == io.n_transitions - 1;
+    if (last) {
+      io.px_out[g] = px;
+      if (io.accepted) io.accepted[g] = acc ? 1 : 0;
+#pragma unroll
+      for (int d = 0; d < DM; ++d)
+        if (d < D) {
+          io.x_out[g * D + d] = x[d];
+          if (io.v_out) io.v_out[g * D + d] = v[d];
+          if (io.do_mh) io.x_next[g * D + d] = acc ? x[d] : x0[d];
+        }
+    } else {
+#pragma unroll
+      for (int d = 0; d < DM; ++d) x[d] = acc ? x[d] : x0[d];
+    }
+  }
+}
+
+template <int DM, int HM>
+inline size_t small_smem_bytes(int T) {
+  return 2 * sizeof(NetS<DM, HM>) + sizeof(float) * ((size_t)2 * T * HM + (size_t)T * DM);
+}
+
+}  // namespace small
+}  // namespace l2hmc

@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "kernel_tile.cuh"
 #include "kernel_tc.cuh"
+#include "kernel_small.cuh"
 
 using namespace l2hmc;
 
@@ -337,10 +338,13 @@ static int tc_pack_gaussian(l2hmc_ctx *ctx, const float *Ssym_padded /* [DP][LDS
 static int resolve_kernel(l2hmc_ctx *ctx, int *out) {
   const Shape &sh = ctx->sh;
   int k = ctx->cfg.kernel;
-  if (k == L2HMC_KERNEL_AUTO) k = L2HMC_KERNEL_TILE;
+  const bool small_ok = sh.D <= 4 && (sh.hmc || sh.H <= 16);
+  if (k == L2HMC_KERNEL_AUTO) k = small_ok ? L2HMC_KERNEL_SMALL : L2HMC_KERNEL_TILE;
   if (k == L2HMC_KERNEL_TILE) {
     if (sh.DP > 64 || (!sh.hmc && sh.HP > 128))
       return fail(ctx, L2HMC_EUNSUPPORTED, "tile kernel covers x_dim <= 64 and width <= 128 (got %d, %d)", sh.D, sh.H);
+  } else if (k == L2HMC_KERNEL_SMALL) {
+    if (!small_ok) return fail(ctx, L2HMC_EUNSUPPORTED, "small kernel covers x_dim <= 4 and width <= 16 (got %d, %d)", sh.D, sh.H);
   } else if (k == L2HMC_KERNEL_TC) {
     if (!ctx->tc_ok) return fail(ctx, L2HMC_EUNSUPPORTED, "tensor-core kernel does not cover this shape (x_dim %d, width %d, hmc %d)", sh.D, sh.H, sh.hmc);
     if (ctx->energy_set && !((ctx->en.kind == L2HMC_ENERGY_GAUSSIAN && ctx->en.ncomp == 1) || ctx->en.kind == L2HMC_ENERGY_ROUGHWELL))
@@ -678,6 +682,22 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     }
     const long long blocks = (a->n + tc::MT - 1) / tc::MT;
     tc::tc_transition_kernel<<<(unsigned)blocks, tc::NTHREADS, smem, stream>>>(TA);
+  } else if (kernel == L2HMC_KERNEL_SMALL) {
+    small::SmallArgs SA;
+    SA.sh = ctx->sh;
+    SA.xnet = ctx->net_rawv[0];
+    SA.vnet = ctx->net_rawv[1];
+    SA.tbx = ctx->net_dev[0].tb;
+    SA.tbv = ctx->net_dev[1].tb;
+    SA.en = ctx->en;
+    SA.mask = ctx->mask.p;
+    SA.io = K.io;
+    const unsigned blocks = (unsigned)((a->n + small::NT - 1) / small::NT);
+    if (ctx->sh.D <= 2 && (ctx->sh.hmc || ctx->sh.H <= 10)) {
+      small::small_transition_kernel<2, 10><<<blocks, small::NT, small::small_smem_bytes<2, 10>(ctx->sh.T), stream>>>(SA);
+    } else {
+      small::small_transition_kernel<4, 16><<<blocks, small::NT, small::small_smem_bytes<4, 16>(ctx->sh.T), stream>>>(SA);
+    }
   } else if (kernel == L2HMC_KERNEL_TILE) {
     const size_t smem = tile::smem_bytes(ctx->sh.DP, ctx->sh.HP, ctx->sh.T);
     static thread_local size_t configured = 0;

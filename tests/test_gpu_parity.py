@@ -337,3 +337,42 @@ def test_tc_kernel_multi_transition_and_philox():
     d = dyn._transition(x0, dir_mode=3, do_mh=True, counter=100)
     assert U.max_rel(d["Lx"].cpu().numpy(), c["Lx"].cpu().numpy()) <= 2e-5
     assert float((d["px"] - c["px"]).abs().max()) <= 2e-4
+
+
+# ---- kernel selection: every kernel that covers a configuration must pass on it -------------------------
+@pytest.mark.parametrize("name,n,kernel", [
+    ("c1_scg2", 200, "small"), ("c1_scg2", 200, "tile"),
+    ("c3_mog2", 300, "small"), ("c3_mog2", 300, "tile"),
+    ("funnel3", 200, "small"), ("funnel3", 200, "tile"),
+])
+def test_small_and_tile_kernels_on_small_nets(name, n, kernel):
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    dyn = P.product(kernel=kernel)
+    rep, _ = U.parity_report(P, n, dyn=dyn)
+    assert dyn.kernel_name == {"small": "small_fma", "tile": "tile_fma"}[kernel]
+    _check(rep)
+
+
+def test_auto_kernel_choice():
+    assert U.Problem(**U.CONFIGS["c1_scg2"]).product().kernel_name == "small_fma"
+    assert U.Problem(**U.CONFIGS["c2_scg50"]).product().kernel_name == "tile_fma"
+    assert U.Problem(kind="gaussian", D=2, T=5, eps=0.1, hmc=True).product().kernel_name == "small_fma"
+    assert U.Problem(kind="gaussian", D=50, T=5, eps=0.1, hmc=True).product().kernel_name == "tile_fma"
+
+
+def test_small_kernel_multi_transition_and_generic_size():
+    """Fused transitions on the thread-per-chain kernel; and the padded <4,16> instantiation (D=3, H=12)."""
+    P = U.Problem(regime="stress", **U.CONFIGS["c1_scg2"])
+    dyn = P.product(seed=5)
+    x0 = torch.as_tensor(P.draws(333)["x"]).cuda()
+    a = dyn._transition(x0, dir_mode=3, do_mh=True, n_transitions=4, counter=10)
+    x = x0
+    for t in range(4):
+        b = dyn._transition(x, dir_mode=3, do_mh=True, counter=10 + t)
+        x = b["x_next"]
+    assert torch.equal(a["x_next"], b["x_next"]) and torch.equal(a["px"], b["px"])
+    P2 = U.Problem(kind="gaussian", D=3, H=12, T=7, eps=0.1, regime="stress")
+    d2 = P2.product()
+    assert d2.kernel_name == "small_fma"
+    rep, _ = U.parity_report(P2, 150, dyn=d2)
+    _check(rep)
