@@ -1,21 +1,22 @@
 // Tensor-core transition kernel (sm_100a, tcgen05 / TMEM / TMA bulk copies).
 //
 // Same transition as kernel_tile.cuh (reference: utils/dynamics.py:115-201,246-309; utils/sampler.py:28-55;
-// net SCGExperiment.ipynb:51-77) with the four GEMMs of every net call and the Gaussian grad-U on the 5th-gen
+// net SCGExperiment.ipynb:51-77) with the three GEMMs of every net call and the Gaussian grad-U on the 5th-gen
 // tensor cores.  fp32 parity is kept with the 3xTF32 split: a = a_hi + a_lo (both tf32),
 //   acc += a_lo * b_hi ;  acc += a_hi * b_lo ;  acc += a_hi * b_hi      (fp32 accumulate in TMEM)
 // whose dropped term a_lo * b_lo is 2^-22 relative.
 //
 // One CTA = 128 chains = the 128 TMEM lanes (chain c <-> lane c, MMA M = 128), for the WHOLE transition.
-//   warps 0-7 (256 compute threads): thread (c = 32*(w&3) + lane, half = w>>2) owns chain c and every second
-//       4-dim / 8-column chunk.  It builds the A operand rows directly in TMEM (tcgen05.st), reads the fp32
-//       accumulators back (tcgen05.ld) and does the relu / split / tanh / exp / leapfrog epilogue; x, v, grad U
-//       live in shared memory feature-major, every (chain, dim) element is only ever touched by its owner.
-//   warp 8 lane 0: MMA issuer  (tcgen05.mma kind::tf32, A from TMEM, B from the shared-memory ring)
-//   warp 9 lane 0: TMA producer (cp.async.bulk global -> shared ring, mbarrier complete_tx)
+//   warps 0-15 (512 compute threads): thread (c = 32*(w&3) + lane, quarter = w>>2) owns chain c and every
+//       fourth 4-dim / 8-column chunk.  It builds the A operand rows directly in TMEM (tcgen05.st), reads the
+//       fp32 accumulators back (tcgen05.ld) and does the relu / split / tanh / exp / leapfrog epilogue; x, v,
+//       grad U live in shared memory feature-major and every (chain, dim) element is only touched by its owner.
+//   warp 16 lane 0: MMA issuer  (tcgen05.mma kind::tf32, A from TMEM, B from the shared-memory ring)
+//   warp 17 lane 0: TMA producer (cp.async.bulk global -> shared ring, mbarrier complete_tx)
 // B operands (weights, pre-split hi/lo on the host, canonical K-major no-swizzle core-matrix layout) do not fit
-// in shared memory for both nets (640 KB for config 2), so they stream from L2 through an 8-slot ring in
-// consumption order; one slot = one K=8 step of one GEMM = {B_hi slab, B_lo slab}.
+// in shared memory for both nets (640 KB for config 2), so they stream from L2 through a ring in consumption
+// order; one slot = one K=8 step of one GEMM = {B_hi slab, B_lo slab}.  A bulk copy has ~2.3k cycles of latency
+// (profiles/r01_tc_probe.txt), so the ring is as deep as shared memory allows (14 slots for config 2).
 //
 // TMEM columns: [0,192) accumulator, [192,320) A_hi, [320,448) A_lo.
 #pragma once
@@ -26,9 +27,12 @@ namespace l2hmc {
 namespace tc {
 
 constexpr int MT = 128;               // chains per CTA
-constexpr int NCT = 256;              // compute threads
-constexpr int NTHREADS = 320;         // + MMA-issuer warp + producer warp
+constexpr int NQ = 4;                 // compute threads per chain
+constexpr int NCT = MT * NQ;          // 512 compute threads
+constexpr int NTHREADS = NCT + 64;    // + MMA-issuer warp + producer warp
+constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
 constexpr int MAX_SLOT = 16;          // ring slots (the host sizes the ring to what shared memory allows)
+constexpr int MAXC = 4;               // max chunks per thread: ceil(16 / NQ) -> K, 4*dims <= 128
 constexpr uint32_t T_ACC = 0, T_AHI = 192, T_ALO = 320;
 
 struct TcDims {
@@ -40,6 +44,7 @@ struct TcDims {
   int NG;   // DP rounded to 16: grad GEMM width
   int nslot;        // ring slots (<= MAX_SLOT)
   int slot_floats;  // 16 * max(N1, N3): one K=8 step of the widest GEMM, hi + lo slabs
+  int fast_math;    // 1: ex2/rcp based exp and tanh in the epilogue (abs error ~1e-7)
 };
 
 struct TcNet {
@@ -73,8 +78,8 @@ __host__ __device__ inline TcLay make_tclay(int DP, int T) {
   l.su = l.h0 + MT;
   l.sdir = l.su + MT;
   l.sacc = l.sdir + MT;
-  l.part = l.sacc + MT;          // [3][2][MT] partial U, K, log|J| of the two column halves
-  l.ring = (l.part + 6 * MT + 31) & ~31;  // 128-byte aligned
+  l.part = l.sacc + MT;                          // [2][NQ][MT]: partial Hamiltonian, partial log|J|
+  l.ring = (l.part + 2 * NQ * MT + 31) & ~31;    // 128-byte aligned
   return l;
 }
 __host__ __device__ inline size_t tc_smem_bytes(int DP, int T, int nslot, int slot_floats) {
@@ -92,7 +97,7 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                : "memory");
 }
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 // split 4 values into tf32 hi / lo and store them at column `col` of this thread's TMEM lane
 __device__ __forceinline__ void put_a4(uint32_t lane_base, int col, const float (&a)[4]) {
@@ -104,6 +109,16 @@ __device__ __forceinline__ void put_a4(uint32_t lane_base, int col, const float 
   }
   tmem_st4(T_AHI + lane_base + col, hi);
   tmem_st4(T_ALO + lane_base + col, lo);
+}
+
+// exp / tanh of the epilogue.  FAST: ex2.approx + rcp.approx (abs error ~1e-7 for the O(1) arguments here).
+__device__ __forceinline__ float ep_exp(float x, bool fast) {
+  return fast ? exp2f(x * 1.4426950408889634f) : expf(x);
+}
+__device__ __forceinline__ float ep_tanh(float x, bool fast) {
+  if (!fast) return tanhf(x);
+  const float t = exp2f(x * 2.8853900817779268f);  // e^{2x}
+  return 1.f - __fdividef(2.f, t + 1.f);
 }
 
 struct Sync {
@@ -148,6 +163,7 @@ __device__ __forceinline__ GemmDesc gemm_desc(const TcArgs &A, int kind, int net
   return g;
 }
 
+template <bool FAST>
 __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid_constant__ TcArgs A) {
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_SLOT + 2];
@@ -172,13 +188,13 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
     mbar_init(S.acc_ready, 1);
     fence_mbar_init();
   }
-  if (warp == 8) tmem_alloc(&tmem_slot, 512);
+  if (warp == W_MMA) tmem_alloc(&tmem_slot, 512);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_slot;
 
-  if (warp == 9) {
+  if (warp == W_TMA) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       uint32_t n = 0;
@@ -193,7 +209,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
         }
       });
     }
-  } else if (warp == 8) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t n = 0, gi = 0;
@@ -223,15 +239,17 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
   } else {
     // ===================== compute warps =====================
     const int c = 32 * (warp & 3) + lane;  // chain within the tile == TMEM lane
-    const int half = warp >> 2;
+    const int qd = warp >> 2;              // which quarter of the chunks this thread owns
     const uint32_t lb = tmem + (((uint32_t)(32 * (warp & 3))) << 16);
     const long long gch = base + c;
     const bool gauss = A.en.kind == 0;
+    constexpr bool fast = FAST;
     float *xs = smem + L.xs, *vs = smem + L.vs, *gs = smem + L.gs;
     int *sdir = reinterpret_cast<int *>(smem + L.sdir), *sacc = reinterpret_cast<int *>(smem + L.sacc);
     uint32_t gi = 0;  // GEMM counter (parity of a_ready / acc_ready)
     const float eps = sh.eps, Tm = A.en.temperature;
-    const int nq = DP / 4;  // 4-dim chunks; this thread owns q with (q & 1) == half
+    const int nq = DP / 4;      // 4-dim chunks; this thread owns q with (q & 3) == qd
+    const int nh = td.HK / 8;   // 8-column chunks of the hidden layers
 
     for (int i = tid; i < sh.T * DP; i += NCT) smem[L.smask + i] = A.mask[i];
     for (int i = tid; i < MT * DP; i += NCT) {
@@ -243,7 +261,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
 
     for (int tr = 0; tr < io.n_transitions; ++tr) {
       const unsigned long long ctr = io.counter + (unsigned long long)tr;
-      // ---- setup: x0, momentum, direction, uniform --------------------------------------------------
+      // ---- setup: momentum, direction, uniform -------------------------------------------------------
       if (io.v != nullptr) {
         for (int i = tid; i < MT * DP; i += NCT) {
           const int ch = i / DP, d = i - ch * DP;
@@ -251,14 +269,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
           vs[d * MT + ch] = (g < io.n && d < D) ? io.v[((long long)tr * io.n + g) * D + d] : 0.f;
         }
       } else {
-        for (int q = half; q < nq; q += 2) {
+        for (int q = qd; q < nq; q += NQ) {
           float z[4];
           philox_normals4(io.seed, ctr, io.chain_offset + gch, q, z);
 #pragma unroll
           for (int j = 0; j < 4; ++j) vs[(4 * q + j) * MT + c] = (gch < io.n && 4 * q + j < D) ? z[j] : 0.f;
         }
       }
-      if (half == 0) {
+      if (qd == 0) {
         int pd = 1;
         float pu = 0.f;
         if (io.dir_mode == 3 || (io.do_mh && io.u == nullptr)) philox_dir_u(io.seed, ctr, io.chain_offset + gch, pd, pu);
@@ -277,7 +295,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
       // ---- grad U at the current x -> gs (own dims); Gaussian: tensor-core GEMM with Ssym ----------------
       auto grad_phase = [&]() {
         if (gauss) {
-          for (int q = half; q < td.KG / 4; q += 2) {
+          for (int q = qd; q < td.KG / 4; q += NQ) {
             float a[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -292,7 +310,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
           mbar_wait(S.acc_ready, gi & 1u);
           ++gi;
           tcgen05_fence_after();
-          for (int q = half; q < nq; q += 2) {
+#pragma unroll 1
+          for (int q = qd; q < nq; q += NQ) {
             float g4[4];
             tmem_ld4(lb + T_ACC + 4 * q, g4);
             tmem_wait_ld();
@@ -302,7 +321,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
           tcgen05_fence_before();
         } else {  // RoughWell (utils/distributions.py:90-97)
           const float e = A.en.s0, den = A.en.s1;
-          for (int q = half; q < nq; q += 2)
+          for (int q = qd; q < nq; q += NQ)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int d = 4 * q + j;
@@ -312,9 +331,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
         }
       };
       // partial Hamiltonian over this thread's dims (needs gs = grad U(x) for the Gaussian kind)
-      auto ham_partial = [&](float &U, float &K) {
-        U = 0.f; K = 0.f;
-        for (int q = half; q < nq; q += 2)
+      auto ham_partial = [&]() -> float {
+        float U = 0.f, K = 0.f;
+        for (int q = qd; q < nq; q += NQ)
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int d = 4 * q + j;
@@ -326,15 +345,43 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
             }
           }
         if (gauss) U *= 0.5f;
-        K *= 0.5f;
+        return U + 0.5f * K;
+      };
+      // relu(acc + bias) of this thread's 8-column chunks -> next A operand (bias may differ per direction)
+      auto hidden_epilogue = [&](const float *bias) {
+        mbar_wait(S.acc_ready, gi & 1u);
+        ++gi;
+        tcgen05_fence_after();
+        // software pipeline: the load of the next chunk is in flight while this one is processed
+        float h[8], hn[8];
+        if (qd < nh) tmem_ld8(lb + T_ACC + 8 * qd, h);
+#pragma unroll 1
+        for (int q = qd; q < nh; q += NQ) {
+          tmem_wait_ld();
+          if (q + NQ < nh) tmem_ld8(lb + T_ACC + 8 * (q + NQ), hn);
+          float a0[4], a1[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a0[j] = fmaxf(h[j] + bias[8 * q + j], 0.f);
+            a1[j] = fmaxf(h[4 + j] + bias[8 * q + 4 + j], 0.f);
+          }
+          put_a4(lb, 8 * q, a0);
+          put_a4(lb, 8 * q + 4, a1);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) h[j] = hn[j];
+        }
+        tmem_wait_st();
+        tcgen05_fence_before();
+        mbar_arrive(S.a_ready);
       };
 
       // one S/T/Q net call + fused update.  net: 0 X / 1 V ; mode: 0 momentum, 1 position (xhalf 0/1)
       auto net_call = [&](int net, int it, int mode, int xhalf) {
         const TcNet &N = net ? A.vnet : A.xnet;
         const int tF = it, tB = sh.T - 1 - it;
+        const float *mrow = smem + L.smask + (fwd ? tF : tB) * DP;
         // ---- A = [a | b] ----
-        for (int q = half; q < nq; q += 2) {
+        for (int q = qd; q < nq; q += NQ) {
           float a[4], b[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -343,7 +390,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
               a[j] = xs[d * MT + c];
               b[j] = gs[d * MT + c];
             } else {
-              const float m = fwd ? smem[L.smask + tF * DP + d] : smem[L.smask + tB * DP + d];
+              const float m = mrow[d];
               const float k = (fwd == (xhalf == 0)) ? m : 1.f - m;
               a[j] = vs[d * MT + c];
               b[j] = k * xs[d * MT + c];
@@ -355,98 +402,76 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
         tmem_wait_st();
         tcgen05_fence_before();
         mbar_arrive(S.a_ready);
-        // ---- embed epilogue: h1 = relu(acc + tb[t_chain]) -> A ----
-        mbar_wait(S.acc_ready, gi & 1u);
-        ++gi;
-        tcgen05_fence_after();
-        const float *tbp = N.tb + (size_t)(fwd ? tF : tB) * td.N1;
-        for (int q = half; q < td.HK / 8; q += 2) {
-          float h[8];
-          tmem_ld8(lb + T_ACC + 8 * q, h);
-          tmem_wait_ld();
-          float a0[4], a1[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            a0[j] = fmaxf(h[j] + tbp[8 * q + j], 0.f);
-            a1[j] = fmaxf(h[4 + j] + tbp[8 * q + 4 + j], 0.f);
-          }
-          put_a4(lb, 8 * q, a0);
-          put_a4(lb, 8 * q + 4, a1);
-        }
-        tmem_wait_st();
-        tcgen05_fence_before();
-        mbar_arrive(S.a_ready);
-        // ---- hidden epilogue: h2 = relu(acc + b4) -> A ----
-        mbar_wait(S.acc_ready, gi & 1u);
-        ++gi;
-        tcgen05_fence_after();
-        for (int q = half; q < td.HK / 8; q += 2) {
-          float h[8];
-          tmem_ld8(lb + T_ACC + 8 * q, h);
-          tmem_wait_ld();
-          float a0[4], a1[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            a0[j] = fmaxf(h[j] + N.b4[8 * q + j], 0.f);
-            a1[j] = fmaxf(h[4 + j] + N.b4[8 * q + 4 + j], 0.f);
-          }
-          put_a4(lb, 8 * q, a0);
-          put_a4(lb, 8 * q + 4, a1);
-        }
-        tmem_wait_st();
-        tcgen05_fence_before();
-        mbar_arrive(S.a_ready);
+        hidden_epilogue(N.tb + (size_t)(fwd ? tF : tB) * td.N1);  // h1 = relu(acc + tb[t_chain])
+        hidden_epilogue(N.b4);                                    // h2 = relu(acc + b4)
         // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) ----
         mbar_wait(S.acc_ready, gi & 1u);
         ++gi;
         tcgen05_fence_after();
-        for (int q = half; q < nq; q += 2) {
-          float s4[4], t4[4], q4[4];
-          tmem_ld4(lb + T_ACC + 4 * q, s4);
-          tmem_ld4(lb + T_ACC + DP + 4 * q, t4);
-          tmem_ld4(lb + T_ACC + 2 * DP + 4 * q, q4);
+        float s4[4], t4[4], q4[4], sn[4], tn[4], qn[4];
+        if (qd < nq) {
+          tmem_ld4(lb + T_ACC + 4 * qd, s4);
+          tmem_ld4(lb + T_ACC + DP + 4 * qd, t4);
+          tmem_ld4(lb + T_ACC + 2 * DP + 4 * qd, q4);
+        }
+#pragma unroll 1
+        for (int q = qd; q < nq; q += NQ) {
           tmem_wait_ld();
+          if (q + NQ < nq) {  // next chunk's accumulators travel while this chunk is processed
+            tmem_ld4(lb + T_ACC + 4 * (q + NQ), sn);
+            tmem_ld4(lb + T_ACC + DP + 4 * (q + NQ), tn);
+            tmem_ld4(lb + T_ACC + 2 * DP + 4 * (q + NQ), qn);
+          }
+          {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int d = 4 * q + j;
+              const float Sx = N.es[d] * ep_tanh(s4[j] + N.bh[d], fast);
+              const float Tt = t4[j] + N.bh[DP + d];
+              const float Qx = N.eq[d] * ep_tanh(q4[j] + N.bh[2 * DP + d], fast);
+              if (mode == 0) {
+                float v = vs[d * MT + c];
+                const float g = gs[d * MT + c];
+                const float sv = fwd ? (0.5f * eps) * Sx : (-0.5f * eps) * Sx;
+                const float cterm = (0.5f * eps) * (-(ep_exp(eps * Qx, fast) * g) + Tt);
+                const float e = ep_exp(sv, fast);
+                v = fwd ? (v * e + cterm) : ((v - cterm) * e);
+                vs[d * MT + c] = v;
+                lj += sv;
+              } else {
+                const float m = mrow[d];
+                const float k = (fwd == (xhalf == 0)) ? m : 1.f - m;
+                const float uu = 1.f - k;
+                float x = xs[d * MT + c];
+                const float v = vs[d * MT + c];
+                const float sx = fwd ? eps * Sx : -eps * Sx;
+                const float inner = eps * (ep_exp(eps * Qx, fast) * v + Tt);
+                const float e = ep_exp(sx, fast);
+                const float nx = fwd ? (x * e + inner) : (e * (x - inner));
+                xs[d * MT + c] = k * x + uu * nx;
+                lj += uu * sx;
+              }
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const int d = 4 * q + j;
-            const float Sx = N.es[d] * tanhf(s4[j] + N.bh[d]);
-            const float Tt = t4[j] + N.bh[DP + d];
-            const float Qx = N.eq[d] * tanhf(q4[j] + N.bh[2 * DP + d]);
-            if (mode == 0) {
-              float v = vs[d * MT + c];
-              const float g = gs[d * MT + c];
-              const float sv = fwd ? (0.5f * eps) * Sx : (-0.5f * eps) * Sx;
-              const float cterm = (0.5f * eps) * (-(expf(eps * Qx) * g) + Tt);
-              const float e = expf(sv);
-              v = fwd ? (v * e + cterm) : ((v - cterm) * e);
-              vs[d * MT + c] = v;
-              lj += sv;
-            } else {
-              const float m = fwd ? smem[L.smask + tF * DP + d] : smem[L.smask + tB * DP + d];
-              const float k = (fwd == (xhalf == 0)) ? m : 1.f - m;
-              const float uu = 1.f - k;
-              float x = xs[d * MT + c];
-              const float v = vs[d * MT + c];
-              const float sx = fwd ? eps * Sx : -eps * Sx;
-              const float inner = eps * (expf(eps * Qx) * v + Tt);
-              const float e = expf(sx);
-              const float nx = fwd ? (x * e + inner) : (e * (x - inner));
-              xs[d * MT + c] = k * x + uu * nx;
-              lj += uu * sx;
-            }
+            s4[j] = sn[j];
+            t4[j] = tn[j];
+            q4[j] = qn[j];
           }
         }
         tcgen05_fence_before();
       };
 
       grad_phase();
-      {
-        float U, K;
-        ham_partial(U, K);
-        smem[L.part + half * MT + c] = U + K;
-      }
+      smem[L.part + qd * MT + c] = ham_partial();
       compute_bar();
-      if (half == 0) smem[L.h0 + c] = smem[L.part + c] + smem[L.part + MT + c];
+      if (qd == 0) {
+        float h = 0.f;
+#pragma unroll
+        for (int r = 0; r < NQ; ++r) h += smem[L.part + r * MT + c];
+        smem[L.h0 + c] = h;
+      }
 
       for (int it = 0; it < sh.T; ++it) {
         net_call(1, it, 0, 0);
@@ -457,17 +482,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
       }
 
       // ---- log|J|, Hamiltonian, accept ---------------------------------------------------------------
-      {
-        float U, K;
-        ham_partial(U, K);
-        smem[L.part + half * MT + c] = U + K;
-        smem[L.part + (2 + half) * MT + c] = lj;
-      }
+      compute_bar();  // h0 readers are done with `part`
+      smem[L.part + qd * MT + c] = ham_partial();
+      smem[L.part + (NQ + qd) * MT + c] = lj;
       compute_bar();
       const bool last = (tr == io.n_transitions - 1);
-      if (half == 0) {
-        const float h1 = smem[L.part + c] + smem[L.part + MT + c];
-        const float logj = smem[L.part + 2 * MT + c] + smem[L.part + 3 * MT + c];
+      if (qd == 0) {
+        float h1 = 0.f, logj = 0.f;
+#pragma unroll
+        for (int r = 0; r < NQ; ++r) {
+          h1 += smem[L.part + r * MT + c];
+          logj += smem[L.part + (NQ + r) * MT + c];
+        }
         const float p = accept_prob(smem[L.h0 + c], h1, logj);
         const float px = io.log_jac ? logj : p;
         int acc = 0;
@@ -509,7 +535,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == W_MMA) {
     __syncwarp();
     tmem_dealloc(tmem, 512);
   }

@@ -5,6 +5,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -265,6 +266,8 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   const long long state_bytes = (long long)tc::make_tclay(sh.DP, sh.T).ring * 4;
   long long ns = (232448LL - 1024 - state_bytes) / ((long long)td.slot_floats * 4);
   td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
+  const char *fm = getenv("L2HMC_TC_FAST_MATH");  // ex2/rcp-based exp and tanh in the epilogue; default off
+  td.fast_math = (fm && fm[0] == '1') ? 1 : 0;
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
 }
 
@@ -677,11 +680,13 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
     static thread_local size_t tc_configured = 0;
     if (smem > tc_configured) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc_configured = smem;
     }
     const long long blocks = (a->n + tc::MT - 1) / tc::MT;
-    tc::tc_transition_kernel<<<(unsigned)blocks, tc::NTHREADS, smem, stream>>>(TA);
+    if (ctx->td.fast_math) tc::tc_transition_kernel<true><<<(unsigned)blocks, tc::NTHREADS, smem, stream>>>(TA);
+    else tc::tc_transition_kernel<false><<<(unsigned)blocks, tc::NTHREADS, smem, stream>>>(TA);
   } else if (kernel == L2HMC_KERNEL_SMALL) {
     small::SmallArgs SA;
     SA.sh = ctx->sh;

@@ -235,8 +235,9 @@ class Dynamics(object):
         return c
 
     def _transition(self, x, *, v=None, dir_mode=_lib.DIR_FORWARD, direction=None, u=None, log_jac=False,
-                    do_mh=False, n_transitions=1, want_v=True, counter=None, chain_offset=0, seed=None):
-        """One l2hmc_transition call. Returns dict(Lx, Lv, px, x_next, accepted)."""
+                    do_mh=False, n_transitions=1, want_v=True, counter=None, chain_offset=0, seed=None, out=None):
+        """One l2hmc_transition call. Returns dict(Lx, Lv, px, x_next, accepted).  `out` may hold preallocated
+        tensors of the right shapes under the same keys (steady-state loops then allocate nothing)."""
         self._ensure_ctx()
         self._sync_temperature()
         x = self._prep(x, "x", self.x_dim)
@@ -268,7 +269,7 @@ class Dynamics(object):
         a.dir_mode, a.log_jac, a.do_mh, a.n_transitions = int(dir_mode), int(bool(log_jac)), int(bool(do_mh)), int(n_transitions)
         a.seed = self.seed if seed is None else int(seed)
         a.counter = self.next_counter(n_transitions) if counter is None else int(counter)
-        out = {
+        out = out if out is not None else {
             "Lx": torch.empty((n, self.x_dim), dtype=TORCH_FLOAT, device=dev),
             "Lv": torch.empty((n, self.x_dim), dtype=TORCH_FLOAT, device=dev) if want_v else None,
             "px": torch.empty((n,), dtype=TORCH_FLOAT, device=dev),
