@@ -27,12 +27,9 @@ namespace l2hmc {
 namespace tc {
 
 constexpr int MT = 128;               // chains per CTA
-constexpr int NQ = 4;                 // compute threads per chain
-constexpr int NCT = MT * NQ;          // 512 compute threads
-constexpr int NTHREADS = NCT + 64;    // + MMA-issuer warp + producer warp
-constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
+constexpr int NQMAX = 4;              // compute threads per chain: template parameter NQ in {2, 4}
 constexpr int MAX_SLOT = 16;          // ring slots (the host sizes the ring to what shared memory allows)
-constexpr int MAXC = 4;               // max chunks per thread: ceil(16 / NQ) -> K, 4*dims <= 128
+constexpr int KSLOT = 2;              // K=8 steps per ring slot (halves the mbarrier traffic of the MMA issuer)
 constexpr uint32_t T_ACC = 0, T_AHI = 192, T_ALO = 320;
 
 struct TcDims {
@@ -43,8 +40,9 @@ struct TcDims {
   int KG;   // DP rounded to 8: grad GEMM depth
   int NG;   // DP rounded to 16: grad GEMM width
   int nslot;        // ring slots (<= MAX_SLOT)
-  int slot_floats;  // 16 * max(N1, N3): one K=8 step of the widest GEMM, hi + lo slabs
+  int slot_floats;  // KSLOT * 16 * max(N1, N3): KSLOT K=8 steps of the widest GEMM, hi + lo slabs each
   int fast_math;    // 1: ex2/rcp based exp and tanh in the epilogue (abs error ~1e-7)
+  int nq;           // compute threads per chain (2 or 4) -> which instantiation the host launches
 };
 
 struct TcNet {
@@ -78,8 +76,8 @@ __host__ __device__ inline TcLay make_tclay(int DP, int T) {
   l.su = l.h0 + MT;
   l.sdir = l.su + MT;
   l.sacc = l.sdir + MT;
-  l.part = l.sacc + MT;                          // [2][NQ][MT]: partial Hamiltonian, partial log|J|
-  l.ring = (l.part + 2 * NQ * MT + 31) & ~31;    // 128-byte aligned
+  l.part = l.sacc + MT;                          // [2][NQMAX][MT]: partial Hamiltonian, partial log|J|
+  l.ring = (l.part + 2 * NQMAX * MT + 31) & ~31; // 128-byte aligned
   return l;
 }
 __host__ __device__ inline size_t tc_smem_bytes(int DP, int T, int nslot, int slot_floats) {
@@ -97,7 +95,26 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const float (&v)[4]) {
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3]))
                : "memory");
 }
-__device__ __forceinline__ void compute_bar() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+template <int NCT>
+__device__ __forceinline__ void compute_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
+// waits that last thousands of cycles (compute warps waiting for a GEMM): back off so the spinning warps do not
+// take issue slots from the single MMA-issuer / producer threads
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (done) break;
+    __nanosleep(64);
+  }
+}
 
 // split 4 values into tf32 hi / lo and store them at column `col` of this thread's TMEM lane
 __device__ __forceinline__ void put_a4(uint32_t lane_base, int col, const float (&a)[4]) {
@@ -163,8 +180,11 @@ __device__ __forceinline__ GemmDesc gemm_desc(const TcArgs &A, int kind, int net
   return g;
 }
 
-template <bool FAST>
-__global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid_constant__ TcArgs A) {
+template <int NQ, bool FAST>
+__global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __grid_constant__ TcArgs A) {
+  constexpr int NCT = MT * NQ;                       // compute threads
+  constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1; // + MMA-issuer warp + producer warp
+  auto compute_bar = []() { compute_bar_n<NCT>(); };
   extern __shared__ __align__(128) float smem[];
   __shared__ __align__(8) uint64_t bars[2 * MAX_SLOT + 2];
   __shared__ uint32_t tmem_slot;
@@ -196,13 +216,14 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
 
   if (warp == W_TMA) {
     // ===================== TMA producer =====================
+    // one ring slot = up to KSLOT consecutive K=8 steps of one GEMM (contiguous in the weight stream)
     if (lane == 0) {
       uint32_t n = 0;
       walk_schedule(A, [&](int kind, int net) {
         const GemmDesc g = gemm_desc(A, kind, net);
-        const uint32_t bytes = (uint32_t)g.chunk_floats * 4u;
-        for (int ks = 0; ks < g.nsteps; ++ks, ++n) {
+        for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++n) {
           const uint32_t s = n % NSLOT;
+          const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
           mbar_wait(&S.empty[s], ((n / NSLOT) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&S.full[s], bytes);
           bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
@@ -213,23 +234,30 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t n = 0, gi = 0;
+      const uint32_t ring_u32 = smem_u32(ring);
       walk_schedule(A, [&](int kind, int net) {
         const GemmDesc g = gemm_desc(A, kind, net);
         const uint32_t idesc = make_idesc_tf32(128, g.n);
-        const uint32_t lbo = (uint32_t)(g.n / 8) * 128u, sbo = 128u;
+        // descriptor of a slab at shared address 0; the start-address field (bits 0-13, 16-byte units) is added per slab
+        const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
+        const uint32_t slab16 = (uint32_t)g.n * 2u;  // one slab (n x 8 floats) in 16-byte units
         mbar_wait(S.a_ready, gi & 1u);
         tcgen05_fence_after();
-        for (int ks = 0; ks < g.nsteps; ++ks, ++n) {
+        for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++n) {
           const uint32_t s = n % NSLOT;
           mbar_wait(&S.full[s], (n / NSLOT) & 1u);
-          tcgen05_fence_after();
-          const uint32_t bhi = smem_u32(ring + (size_t)s * SLOT_FLOATS);
-          const uint32_t blo = bhi + (uint32_t)g.n * 32u;  // hi slab = n x 8 floats
-          const uint64_t dhi = make_smem_desc(bhi, lbo, sbo), dlo = make_smem_desc(blo, lbo, sbo);
-          const uint32_t ahi = tmem + T_AHI + 8u * ks, alo = tmem + T_ALO + 8u * ks;
-          mma_tf32_ts(tmem + T_ACC, alo, dhi, idesc, ks > 0);
-          mma_tf32_ts(tmem + T_ACC, ahi, dlo, idesc, true);
-          mma_tf32_ts(tmem + T_ACC, ahi, dhi, idesc, true);
+          const uint32_t b16 = (ring_u32 + s * SLOT_FLOATS * 4u) >> 4;
+#pragma unroll
+          for (int kk = 0; kk < KSLOT; ++kk) {
+            if (ks + kk < g.nsteps) {
+              const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
+              const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
+              const uint32_t ahi = tmem + T_AHI + 8u * (ks + kk), alo = tmem + T_ALO + 8u * (ks + kk);
+              mma_tf32_ts(tmem + T_ACC, alo, dhi, idesc, (ks + kk) > 0);
+              mma_tf32_ts(tmem + T_ACC, ahi, dlo, idesc, true);
+              mma_tf32_ts(tmem + T_ACC, ahi, dhi, idesc, true);
+            }
+          }
           tcgen05_commit(&S.empty[s]);
         }
         tcgen05_commit(S.acc_ready);
@@ -239,7 +267,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
   } else {
     // ===================== compute warps =====================
     const int c = 32 * (warp & 3) + lane;  // chain within the tile == TMEM lane
-    const int qd = warp >> 2;              // which quarter of the chunks this thread owns
+    const int qd = warp >> 2;              // which 1/NQ of the chunks this thread owns
     const uint32_t lb = tmem + (((uint32_t)(32 * (warp & 3))) << 16);
     const long long gch = base + c;
     const bool gauss = A.en.kind == 0;
@@ -307,7 +335,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
           tmem_wait_st();
           tcgen05_fence_before();
           mbar_arrive(S.a_ready);
-          mbar_wait(S.acc_ready, gi & 1u);
+          mbar_wait_sleep(S.acc_ready, gi & 1u);
           ++gi;
           tcgen05_fence_after();
 #pragma unroll 1
@@ -349,7 +377,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
       };
       // relu(acc + bias) of this thread's 8-column chunks -> next A operand (bias may differ per direction)
       auto hidden_epilogue = [&](const float *bias) {
-        mbar_wait(S.acc_ready, gi & 1u);
+        mbar_wait_sleep(S.acc_ready, gi & 1u);
         ++gi;
         tcgen05_fence_after();
         // software pipeline: the load of the next chunk is in flight while this one is processed
@@ -359,12 +387,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
         for (int q = qd; q < nh; q += NQ) {
           tmem_wait_ld();
           if (q + NQ < nh) tmem_ld8(lb + T_ACC + 8 * (q + NQ), hn);
-          float a0[4], a1[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            a0[j] = fmaxf(h[j] + bias[8 * q + j], 0.f);
-            a1[j] = fmaxf(h[4 + j] + bias[8 * q + 4 + j], 0.f);
-          }
+          const float4 b0 = __ldg(reinterpret_cast<const float4 *>(bias + 8 * q));
+          const float4 b1 = __ldg(reinterpret_cast<const float4 *>(bias + 8 * q + 4));
+          const float a0[4] = {fmaxf(h[0] + b0.x, 0.f), fmaxf(h[1] + b0.y, 0.f), fmaxf(h[2] + b0.z, 0.f), fmaxf(h[3] + b0.w, 0.f)};
+          const float a1[4] = {fmaxf(h[4] + b1.x, 0.f), fmaxf(h[5] + b1.y, 0.f), fmaxf(h[6] + b1.z, 0.f), fmaxf(h[7] + b1.w, 0.f)};
           put_a4(lb, 8 * q, a0);
           put_a4(lb, 8 * q + 4, a1);
 #pragma unroll
@@ -405,7 +431,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
         hidden_epilogue(N.tb + (size_t)(fwd ? tF : tB) * td.N1);  // h1 = relu(acc + tb[t_chain])
         hidden_epilogue(N.b4);                                    // h2 = relu(acc + b4)
         // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) ----
-        mbar_wait(S.acc_ready, gi & 1u);
+        mbar_wait_sleep(S.acc_ready, gi & 1u);
         ++gi;
         tcgen05_fence_after();
         float s4[4], t4[4], q4[4], sn[4], tn[4], qn[4];
@@ -423,12 +449,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) tc_transition_kernel(const __grid
             tmem_ld4(lb + T_ACC + 2 * DP + 4 * (q + NQ), qn);
           }
           {
+            // per-dimension constants of this 4-dim chunk: one 16-byte load each (warp-uniform addresses)
+            const float4 c_es = __ldg(reinterpret_cast<const float4 *>(N.es + 4 * q));
+            const float4 c_eq = __ldg(reinterpret_cast<const float4 *>(N.eq + 4 * q));
+            const float4 c_bs = __ldg(reinterpret_cast<const float4 *>(N.bh + 4 * q));
+            const float4 c_bt = __ldg(reinterpret_cast<const float4 *>(N.bh + DP + 4 * q));
+            const float4 c_bq = __ldg(reinterpret_cast<const float4 *>(N.bh + 2 * DP + 4 * q));
+            const float es4[4] = {c_es.x, c_es.y, c_es.z, c_es.w}, eq4[4] = {c_eq.x, c_eq.y, c_eq.z, c_eq.w};
+            const float bs4[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bt4[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};
+            const float bq4[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int d = 4 * q + j;
-              const float Sx = N.es[d] * ep_tanh(s4[j] + N.bh[d], fast);
-              const float Tt = t4[j] + N.bh[DP + d];
-              const float Qx = N.eq[d] * ep_tanh(q4[j] + N.bh[2 * DP + d], fast);
+              const float Sx = es4[j] * ep_tanh(s4[j] + bs4[j], fast);
+              const float Tt = t4[j] + bt4[j];
+              const float Qx = eq4[j] * ep_tanh(q4[j] + bq4[j], fast);
               if (mode == 0) {
                 float v = vs[d * MT + c];
                 const float g = gs[d * MT + c];

@@ -262,12 +262,14 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   td.NG = round_up(sh.DP, 16);
   int nmax = td.N1 > td.N3 ? td.N1 : td.N3;
   if (td.NG > nmax) nmax = td.NG;
-  td.slot_floats = 16 * nmax;
+  td.slot_floats = tc::KSLOT * 16 * nmax;
   const long long state_bytes = (long long)tc::make_tclay(sh.DP, sh.T).ring * 4;
   long long ns = (232448LL - 1024 - state_bytes) / ((long long)td.slot_floats * 4);
   td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
   const char *fm = getenv("L2HMC_TC_FAST_MATH");  // ex2/rcp-based exp and tanh in the epilogue; default off
   td.fast_math = (fm && fm[0] == '1') ? 1 : 0;
+  const char *nqe = getenv("L2HMC_TC_NQ");  // compute threads per chain: 2 or 4
+  td.nq = (nqe && nqe[0] >= '2' && nqe[0] <= '4') ? (nqe[0] - '0') : 4;
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
 }
 
@@ -680,13 +682,26 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
     static thread_local size_t tc_configured = 0;
     if (smem > tc_configured) {
-      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<4, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc_configured = smem;
     }
-    const long long blocks = (a->n + tc::MT - 1) / tc::MT;
-    if (ctx->td.fast_math) tc::tc_transition_kernel<true><<<(unsigned)blocks, tc::NTHREADS, smem, stream>>>(TA);
-    else tc::tc_transition_kernel<false><<<(unsigned)blocks, tc::NTHREADS, smem, stream>>>(TA);
+    const unsigned blocks = (unsigned)((a->n + tc::MT - 1) / tc::MT);
+    const unsigned nthreads = (unsigned)(tc::MT * ctx->td.nq + 64);
+    if (ctx->td.nq == 2) {
+      if (ctx->td.fast_math) tc::tc_transition_kernel<2, true><<<blocks, nthreads, smem, stream>>>(TA);
+      else tc::tc_transition_kernel<2, false><<<blocks, nthreads, smem, stream>>>(TA);
+    } else if (ctx->td.nq == 3) {
+      if (ctx->td.fast_math) tc::tc_transition_kernel<3, true><<<blocks, nthreads, smem, stream>>>(TA);
+      else tc::tc_transition_kernel<3, false><<<blocks, nthreads, smem, stream>>>(TA);
+    } else {
+      if (ctx->td.fast_math) tc::tc_transition_kernel<4, true><<<blocks, nthreads, smem, stream>>>(TA);
+      else tc::tc_transition_kernel<4, false><<<blocks, nthreads, smem, stream>>>(TA);
+    }
   } else if (kernel == L2HMC_KERNEL_SMALL) {
     small::SmallArgs SA;
     SA.sh = ctx->sh;
