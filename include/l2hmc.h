@@ -169,6 +169,10 @@ int64_t l2hmc_launch_count(const l2hmc_ctx *ctx);    /* kernels launched by this
 /* CUDA-event timing of the hot kernel on the launching stream: average ms over launches since reset. */
 int l2hmc_timing_enable(l2hmc_ctx *ctx, int on);
 int l2hmc_timing_read(l2hmc_ctx *ctx, double *avg_ms, int64_t *launches); /* synchronises */
+/* Phase accounting of the tensor-core kernel's CTA 0 in SM clock cycles (synchronises the device):
+ * out[0] MMA issuer waiting for A operands, [1] waiting for TMA weight slabs, [2] issuer total,
+ * [3] compute thread 0 waiting for accumulators, [4] compute thread 0 total, [5] GEMMs issued. n <= 8. */
+int l2hmc_debug_counters(l2hmc_ctx *ctx, int64_t *out, int n);
 
 #ifdef __cplusplus
 }

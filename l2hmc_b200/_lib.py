@@ -119,6 +119,7 @@ EXPORTS = [
     ("l2hmc_launch_count", _i64, [_vp]),
     ("l2hmc_timing_enable", C.c_int, [_vp, C.c_int]),
     ("l2hmc_timing_read", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
+    ("l2hmc_debug_counters", C.c_int, [_vp, C.POINTER(_i64), C.c_int]),
 ]
 
 _lib: Optional[C.CDLL] = None

@@ -142,6 +142,11 @@ struct Sync {
   uint64_t *full, *empty, *a_ready, *acc_ready;
 };
 
+// Phase accounting of CTA 0 (clock64 cycles), read back through l2hmc_debug_counters():
+// [0] issuer: waiting for A operands (tensor pipe idle, compute warps busy)   [1] issuer: waiting for TMA data
+// [2] issuer: total   [3] compute thread 0: waiting for accumulators   [4] compute thread 0: total   [5] GEMMs issued
+__device__ long long g_tc_dbg[8];
+
 // ---- the GEMM schedule, walked identically by the producer, the MMA issuer and (structurally) the compute warps
 // kind: 0 = grad (Gaussian), 1 = embed, 2 = hidden, 3 = heads ; net: 0 = X, 1 = V
 template <class F>
@@ -232,37 +237,57 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // The whole warp walks the schedule (warp-uniform control flow and addresses, so the operands of
+    // tcgen05.mma live in uniform registers); only the elected lane issues the MMAs and commits.
+    {
+      const bool leader = (lane == 0);
       uint32_t n = 0, gi = 0;
-      const uint32_t ring_u32 = smem_u32(ring);
+      const uint32_t ring_u32 = __shfl_sync(0xffffffffu, smem_u32(ring), 0);
+      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      long long w_a = 0, w_f = 0;
+      const long long t_begin = clock64();
       walk_schedule(A, [&](int kind, int net) {
         const GemmDesc g = gemm_desc(A, kind, net);
         const uint32_t idesc = make_idesc_tf32(128, g.n);
         // descriptor of a slab at shared address 0; the start-address field (bits 0-13, 16-byte units) is added per slab
         const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
         const uint32_t slab16 = (uint32_t)g.n * 2u;  // one slab (n x 8 floats) in 16-byte units
+        long long t0 = clock64();
         mbar_wait(S.a_ready, gi & 1u);
+        w_a += clock64() - t0;
         tcgen05_fence_after();
         for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++n) {
           const uint32_t s = n % NSLOT;
+          t0 = clock64();
           mbar_wait(&S.full[s], (n / NSLOT) & 1u);
+          w_f += clock64() - t0;
           const uint32_t b16 = (ring_u32 + s * SLOT_FLOATS * 4u) >> 4;
+          if (leader) {
 #pragma unroll
-          for (int kk = 0; kk < KSLOT; ++kk) {
-            if (ks + kk < g.nsteps) {
-              const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
-              const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
-              const uint32_t ahi = tmem + T_AHI + 8u * (ks + kk), alo = tmem + T_ALO + 8u * (ks + kk);
-              mma_tf32_ts(tmem + T_ACC, alo, dhi, idesc, (ks + kk) > 0);
-              mma_tf32_ts(tmem + T_ACC, ahi, dlo, idesc, true);
-              mma_tf32_ts(tmem + T_ACC, ahi, dhi, idesc, true);
+            for (int kk = 0; kk < KSLOT; ++kk) {
+              if (ks + kk < g.nsteps) {
+                const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
+                const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
+                const uint32_t ahi = tmem_u + T_AHI + 8u * (ks + kk), alo = tmem_u + T_ALO + 8u * (ks + kk);
+                mma_tf32_ts(tmem_u + T_ACC, alo, dhi, idesc, (ks + kk) > 0);
+                mma_tf32_ts(tmem_u + T_ACC, ahi, dlo, idesc, true);
+                mma_tf32_ts(tmem_u + T_ACC, ahi, dhi, idesc, true);
+              }
             }
+            tcgen05_commit(&S.empty[s]);
           }
-          tcgen05_commit(&S.empty[s]);
+          __syncwarp();
         }
-        tcgen05_commit(S.acc_ready);
+        if (leader) tcgen05_commit(S.acc_ready);
+        __syncwarp();
         ++gi;
       });
+      if (blockIdx.x == 0 && leader) {
+        g_tc_dbg[0] = w_a;
+        g_tc_dbg[1] = w_f;
+        g_tc_dbg[2] = clock64() - t_begin;
+        g_tc_dbg[5] = gi;
+      }
     }
   } else {
     // ===================== compute warps =====================
@@ -275,6 +300,14 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
     float *xs = smem + L.xs, *vs = smem + L.vs, *gs = smem + L.gs;
     int *sdir = reinterpret_cast<int *>(smem + L.sdir), *sacc = reinterpret_cast<int *>(smem + L.sacc);
     uint32_t gi = 0;  // GEMM counter (parity of a_ready / acc_ready)
+    long long w_acc = 0;
+    const long long t_begin = clock64();
+    auto wait_acc = [&]() {
+      const long long t0 = clock64();
+      mbar_wait_sleep(S.acc_ready, gi & 1u);
+      w_acc += clock64() - t0;
+      ++gi;
+    };
     const float eps = sh.eps, Tm = A.en.temperature;
     const int nq = DP / 4;      // 4-dim chunks; this thread owns q with (q & 3) == qd
     const int nh = td.HK / 8;   // 8-column chunks of the hidden layers
@@ -335,8 +368,7 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
           tmem_wait_st();
           tcgen05_fence_before();
           mbar_arrive(S.a_ready);
-          mbar_wait_sleep(S.acc_ready, gi & 1u);
-          ++gi;
+          wait_acc();
           tcgen05_fence_after();
 #pragma unroll 1
           for (int q = qd; q < nq; q += NQ) {
@@ -377,8 +409,7 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
       };
       // relu(acc + bias) of this thread's 8-column chunks -> next A operand (bias may differ per direction)
       auto hidden_epilogue = [&](const float *bias) {
-        mbar_wait_sleep(S.acc_ready, gi & 1u);
-        ++gi;
+        wait_acc();
         tcgen05_fence_after();
         // software pipeline: the load of the next chunk is in flight while this one is processed
         float h[8], hn[8];
@@ -431,8 +462,7 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
         hidden_epilogue(N.tb + (size_t)(fwd ? tF : tB) * td.N1);  // h1 = relu(acc + tb[t_chain])
         hidden_epilogue(N.b4);                                    // h2 = relu(acc + b4)
         // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) ----
-        mbar_wait_sleep(S.acc_ready, gi & 1u);
-        ++gi;
+        wait_acc();
         tcgen05_fence_after();
         float s4[4], t4[4], q4[4], sn[4], tn[4], qn[4];
         if (qd < nq) {
@@ -566,6 +596,10 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
         }
         compute_bar();
       }
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+      g_tc_dbg[3] = w_acc;
+      g_tc_dbg[4] = clock64() - t_begin;
     }
   }
   tcgen05_fence_before();

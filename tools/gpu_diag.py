@@ -72,6 +72,16 @@ def timing(kernel):
             ms = e0.elapsed_time(e1) / reps
             print("TIMING %-10s n=%d T=%d kernel=%s ms=%.3f steps/s=%.4g mean_p=%.3f" %
                   (name, n, P.T, dyn.kernel_name, ms, n * P.T / (ms * 1e-3), float(o["px"].mean())), flush=True)
+            if dyn.kernel_name.startswith("tc"):
+                import ctypes as C
+                buf = (C.c_int64 * 8)()
+                dyn._chk(dyn._lib.l2hmc_debug_counters(dyn._ctx, buf, 8))
+                c = list(buf)
+                if c[2] > 0 and c[4] > 0:
+                    print("TCPHASE %-10s CTA0 cycles: issuer total=%d wait_A=%.1f%% wait_TMA=%.1f%% issue/MMA=%.1f%% | compute total=%d "
+                          "wait_acc=%.1f%% | gemms=%d cycles/gemm=%.0f" %
+                          (name, c[2], 100.0 * c[0] / c[2], 100.0 * c[1] / c[2], 100.0 * (c[2] - c[0] - c[1]) / c[2], c[4],
+                           100.0 * c[3] / c[4], c[5], c[2] / max(c[5], 1)), flush=True)
         except Exception:
             print("TIMING %s FAILED" % name)
             traceback.print_exc()
