@@ -266,10 +266,12 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   const long long state_bytes = (long long)tc::make_tclay(sh.DP, sh.T).ring * 4;
   long long ns = (232448LL - 1024 - state_bytes) / ((long long)td.slot_floats * 4);
   td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
-  const char *fm = getenv("L2HMC_TC_FAST_MATH");  // ex2/rcp-based exp and tanh in the epilogue; default off
-  td.fast_math = (fm && fm[0] == '1') ? 1 : 0;
-  const char *nqe = getenv("L2HMC_TC_NQ");  // compute threads per chain: 2 or 4
-  td.nq = (nqe && nqe[0] >= '2' && nqe[0] <= '4') ? (nqe[0] - '0') : 4;
+  // Tunables measured on B200 (profiles/r01_tc_*): 2 compute threads per chain beat 3 and 4 (10.6 / 11.1 / 12.1 ms
+  // on config 2), and the ex2/rcp-based exp and tanh keep parity at the fp32 noise floor while saving 4%.
+  const char *fm = getenv("L2HMC_TC_FAST_MATH");
+  td.fast_math = (fm && fm[0] == '0') ? 0 : 1;
+  const char *nqe = getenv("L2HMC_TC_NQ");
+  td.nq = (nqe && nqe[0] >= '2' && nqe[0] <= '4') ? (nqe[0] - '0') : 2;
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
 }
 
@@ -338,13 +340,17 @@ static int tc_pack_gaussian(l2hmc_ctx *ctx, const float *Ssym_padded /* [DP][LDS
   return L2HMC_OK;
 }
 
-// Which kernel a transition launches: the explicit request, or for AUTO the generic tile kernel
-// (kernel_tc is opt-in until its parity is signed off on the GPU).
+// Which kernel a transition launches: the explicit request, or for AUTO
+//   thread-per-chain kernel for tiny nets, tensor-core kernel for nets wide enough to fill 128x(>=32)x(>=16) MMAs on
+//   the energies it covers, the generic FMA tile kernel otherwise.
 static int resolve_kernel(l2hmc_ctx *ctx, int *out) {
   const Shape &sh = ctx->sh;
   int k = ctx->cfg.kernel;
   const bool small_ok = sh.D <= 4 && (sh.hmc || sh.H <= 16);
-  if (k == L2HMC_KERNEL_AUTO) k = small_ok ? L2HMC_KERNEL_SMALL : L2HMC_KERNEL_TILE;
+  const bool tc_energy = ctx->energy_set && ((ctx->en.kind == L2HMC_ENERGY_GAUSSIAN && ctx->en.ncomp == 1) ||
+                                             ctx->en.kind == L2HMC_ENERGY_ROUGHWELL);
+  const bool tc_auto = ctx->tc_ok && tc_energy && sh.D >= 8 && sh.H >= 32;
+  if (k == L2HMC_KERNEL_AUTO) k = small_ok ? L2HMC_KERNEL_SMALL : (tc_auto ? L2HMC_KERNEL_TC : L2HMC_KERNEL_TILE);
   if (k == L2HMC_KERNEL_TILE) {
     if (sh.DP > 64 || (!sh.hmc && sh.HP > 128))
       return fail(ctx, L2HMC_EUNSUPPORTED, "tile kernel covers x_dim <= 64 and width <= 128 (got %d, %d)", sh.D, sh.H);
@@ -603,6 +609,10 @@ extern "C" int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const floa
   }
   ctx->en = en;
   ctx->energy_set = true;
+  {
+    int k = ctx->kernel;
+    if (resolve_kernel(ctx, &k) == L2HMC_OK) ctx->kernel = k;  // AUTO may now pick the tensor-core kernel
+  }
   return L2HMC_OK;
 }
 

@@ -353,9 +353,22 @@ def test_small_and_tile_kernels_on_small_nets(name, n, kernel):
     _check(rep)
 
 
+@pytest.mark.parametrize("name,n", [("c2_scg50", 200), ("c2_scg50", 65), ("c4_rw32", 200), ("c4_rw32_hard", 130)])
+def test_tile_kernel_on_large_nets(name, n):
+    """AUTO picks the tensor-core kernel for these shapes; the generic FMA kernel must stay correct on them."""
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    dyn = P.product(kernel="tile")
+    rep, _ = U.parity_report(P, n, dyn=dyn)
+    assert dyn.kernel_name == "tile_fma"
+    _check(rep)
+
+
 def test_auto_kernel_choice():
     assert U.Problem(**U.CONFIGS["c1_scg2"]).product().kernel_name == "small_fma"
-    assert U.Problem(**U.CONFIGS["c2_scg50"]).product().kernel_name == "tile_fma"
+    assert U.Problem(**U.CONFIGS["c2_scg50"]).product().kernel_name == "tc_3xtf32"
+    assert U.Problem(**U.CONFIGS["c4_rw32"]).product().kernel_name == "tc_3xtf32"
+    assert U.Problem(**U.CONFIGS["c3_mog2"]).product().kernel_name == "small_fma"
+    assert U.Problem(kind="gmm", D=8, H=32, T=5, eps=0.1).product().kernel_name == "tile_fma"  # GMM: not on the TC path
     assert U.Problem(kind="gaussian", D=2, T=5, eps=0.1, hmc=True).product().kernel_name == "small_fma"
     assert U.Problem(kind="gaussian", D=50, T=5, eps=0.1, hmc=True).product().kernel_name == "tile_fma"
 
