@@ -102,7 +102,7 @@ def test_forward_backward_methods(name):
     # p_accept from forward() equals the component call on its own outputs
     _, _, p = dyn.forward(x, init_v=v)
     p2 = dyn.p_accept(x, v, X, V, lj)
-    assert float((p - p2).abs().max()) <= 1e-5
+    assert float((p - p2).abs().max()) <= P_TOL  # two fp32 orders of the same cancellation-prone Hamiltonian difference
 
 
 def test_components_match_oracle():
