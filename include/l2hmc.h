@@ -50,7 +50,8 @@ typedef enum {
   L2HMC_ENERGY_GAUSSIAN = 0,  /* Gaussian.get_energy_function       utils/distributions.py:50-57   */
   L2HMC_ENERGY_GMM = 1,       /* GMM.get_energy_function            utils/distributions.py:125-134 */
   L2HMC_ENERGY_ROUGHWELL = 2, /* RoughWell.get_energy_function      utils/distributions.py:90-97   */
-  L2HMC_ENERGY_FUNNEL = 3     /* GaussianFunnel.get_energy_function utils/distributions.py:161-180 */
+  L2HMC_ENERGY_FUNNEL = 3,    /* GaussianFunnel.get_energy_function utils/distributions.py:161-180 */
+  L2HMC_ENERGY_DECODER = 4    /* energy(z, aux) of the VAE posterior target   mnist_vae.py:104-126 (l2hmc_set_energy_decoder) */
 } l2hmc_energy_kind;
 
 typedef enum { L2HMC_XNET = 0, L2HMC_VNET = 1 } l2hmc_net_id; /* utils/dynamics.py:78-79 */
@@ -66,7 +67,9 @@ typedef enum {
   L2HMC_KERNEL_AUTO = 0,
   L2HMC_KERNEL_TILE = 1,   /* generic fp32-FMA tile kernel (any D <= 64, H <= 128)               */
   L2HMC_KERNEL_SMALL = 2,  /* one chain per thread, nets in registers (D <= 4, H <= 16)          */
-  L2HMC_KERNEL_TC = 3      /* tcgen05 3xTF32 tensor-core kernel                                  */
+  L2HMC_KERNEL_TC = 3,     /* tcgen05 3xTF32 tensor-core kernel                                  */
+  L2HMC_KERNEL_LAYERED = 4 /* batched GEMM + elementwise launches over all chains: any x_dim / width,
+                              the decoder energy and aux-conditioned nets (state in HBM between launches) */
 } l2hmc_kernel_kind;
 
 /* Dynamics.__init__(x_dim, energy_function, T, eps, hmc, net_factory, ...)  utils/dynamics.py:35-81 */
@@ -117,6 +120,8 @@ typedef struct {
   float *x_next;          /* [n,D] or NULL (required when do_mh)                                 */
   uint8_t *accepted;      /* [n] or NULL                                                         */
   void *stream;           /* cudaStream_t                                                        */
+  const float *aux;       /* [n,aux_dim] conditioning rows (propose(..., aux=) utils/sampler.py:28; the
+                             image batch `inp` of mnist_vae.py:196,204), or NULL when the target takes none */
 } l2hmc_transition_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -138,6 +143,21 @@ int l2hmc_set_temperature(l2hmc_ctx *ctx, float temperature); /* Dynamics.temper
  *  FUNNEL   : scalars[0] = sigma (2.0), scalars[1] = clip (8.0) */
 int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const float *mu, const float *S,
                      const float *logc, const float *scalars, int n_scalars);
+
+/* energy(z, aux) = sum_pix sigmoid_cross_entropy_with_logits(labels=aux, logits=decoder(z)) + 0.5 |z|^2
+ * (mnist_vae.py:122-126) with decoder = Linear, softplus, ..., Linear (mnist_vae.py:104-111).
+ * widths [n_layers+1] = {x_dim, ..., aux_dim}; W[i] is [widths[i], widths[i+1]] row-major, b[i] [widths[i+1]].
+ * Runs on the layered engine; every transition / component call then needs aux rows. */
+int l2hmc_set_energy_decoder(l2hmc_ctx *ctx, int n_layers, const int32_t *widths, const float *const *W,
+                             const float *const *b);
+/* The aux branch of the S/T/Q nets' first stage: h1 = relu(embed_1(a) + embed_2(b) + embed_3(t) + enc(aux)),
+ * enc = Linear, softplus, ..., Linear shared by XNet and VNet (encoder_sampler, mnist_vae.py:134-149).
+ * widths [n_layers+1] = {aux_dim, ..., width}.  n_layers = 0 removes it (`lambda _: 0.`, SCGExperiment.ipynb:58). */
+int l2hmc_set_aux_encoder(l2hmc_ctx *ctx, int n_layers, const int32_t *widths, const float *const *W,
+                          const float *const *b);
+/* aux rows (DEVICE pointer [n,aux_dim], borrowed until rebound) used by the component calls below
+ * (Dynamics.energy(x, aux=aux) etc., utils/dynamics.py:203-218,302); NULL unbinds. */
+int l2hmc_bind_aux(l2hmc_ctx *ctx, int64_t n, const float *aux);
 
 /* ---- the hot path -------------------------------------------------------------------------- */
 int l2hmc_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a); /* propose utils/sampler.py:28-51 */

@@ -16,7 +16,8 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libl2hmc.so")
 SOURCES = ["l2hmc_api.cu"]
-HEADERS = ["common.cuh", "kernel_tile.cuh", os.path.join("..", "..", "include", "l2hmc.h")]
+HEADERS = ["common.cuh", "kernel_tile.cuh", "kernel_tc.cuh", "kernel_small.cuh", "layered.cuh", "layered_host.cuh",
+           os.path.join("..", "..", "include", "l2hmc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
@@ -85,13 +86,13 @@ class TransitionArgs(C.Structure):
                 ("dir_mode", C.c_int32), ("log_jac", C.c_int32), ("do_mh", C.c_int32), ("n_transitions", C.c_int32),
                 ("seed", C.c_uint64), ("counter", C.c_uint64),
                 ("x_out", C.c_void_p), ("v_out", C.c_void_p), ("px_out", C.c_void_p), ("x_next", C.c_void_p),
-                ("accepted", C.c_void_p), ("stream", C.c_void_p)]
+                ("accepted", C.c_void_p), ("stream", C.c_void_p), ("aux", C.c_void_p)]
 
 
-ENERGY_GAUSSIAN, ENERGY_GMM, ENERGY_ROUGHWELL, ENERGY_FUNNEL = 0, 1, 2, 3
+ENERGY_GAUSSIAN, ENERGY_GMM, ENERGY_ROUGHWELL, ENERGY_FUNNEL, ENERGY_DECODER = 0, 1, 2, 3, 4
 XNET, VNET = 0, 1
 DIR_FORWARD, DIR_BACKWARD, DIR_PER_CHAIN, DIR_RANDOM = 0, 1, 2, 3
-KERNEL_AUTO, KERNEL_TILE, KERNEL_SMALL, KERNEL_TC = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_TILE, KERNEL_SMALL, KERNEL_TC, KERNEL_LAYERED = 0, 1, 2, 3, 4
 
 # every symbol include/l2hmc.h declares: (name, restype, argtypes)
 _vp, _i64, _u64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_float
@@ -105,6 +106,9 @@ EXPORTS = [
     ("l2hmc_set_eps", C.c_int, [_vp, _f32]),
     ("l2hmc_set_temperature", C.c_int, [_vp, _f32]),
     ("l2hmc_set_energy", C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int]),
+    ("l2hmc_set_energy_decoder", C.c_int, [_vp, C.c_int, C.POINTER(_i32), C.POINTER(_fp), C.POINTER(_fp)]),
+    ("l2hmc_set_aux_encoder", C.c_int, [_vp, C.c_int, C.POINTER(_i32), C.POINTER(_fp), C.POINTER(_fp)]),
+    ("l2hmc_bind_aux", C.c_int, [_vp, _i64, _vp]),
     ("l2hmc_transition", C.c_int, [_vp, C.POINTER(TransitionArgs)]),
     ("l2hmc_transition_host", C.c_int, [_vp, C.POINTER(TransitionArgs)]),
     ("l2hmc_energy", C.c_int, [_vp, _i64, _vp, _vp, _vp]),

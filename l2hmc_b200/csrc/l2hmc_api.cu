@@ -15,6 +15,7 @@
 #include "kernel_tile.cuh"
 #include "kernel_tc.cuh"
 #include "kernel_small.cuh"
+#include "layered.cuh"
 
 using namespace l2hmc;
 
@@ -24,6 +25,31 @@ using namespace l2hmc;
 struct DevBuf {
   float *p = nullptr;
   size_t n = 0;
+};
+
+// layered engine (layered.cuh / layered_host.cuh)
+struct LayNetView {
+  const float *Wemb = nullptr, *tb = nullptr, *W4 = nullptr, *b4 = nullptr, *Wh = nullptr, *bh = nullptr,
+              *es = nullptr, *eq = nullptr;
+};
+struct LayMlp {  // Linear / softplus stack (decoder of the energy, aux encoder of the nets)
+  int n_layers = 0;
+  std::vector<int> w, wp;  // widths and widths rounded up to 8
+  DevBuf buf;
+  std::vector<const float *> W, Wt, b;
+};
+struct LayeredCtx {
+  layered::LayDims dm;
+  DevBuf net_buf[2];
+  LayNetView net[2];
+  LayMlp dec, enc;
+  DevBuf x, v, x0, ab, hd, hA, hB, vec, eaux, auxp, tbias;
+  std::vector<DevBuf> dact, eact;
+  long long ws_n = 0;
+  cudaEvent_t ws_event = nullptr;  // recorded when a call's last workspace user is enqueued
+  bool ws_recorded = false;
+  const float *aux = nullptr;  // bound by l2hmc_bind_aux for the component calls
+  long long aux_n = 0;
 };
 
 struct l2hmc_ctx {
@@ -59,6 +85,8 @@ struct l2hmc_ctx {
   uint8_t *hdir = nullptr, *hacc = nullptr;
   size_t hdir_n = 0, hacc_n = 0;
   cudaStream_t hstream = nullptr;
+  LayeredCtx lay;
+  DevBuf haux;
 };
 
 static thread_local std::string g_err;
@@ -91,6 +119,8 @@ static int ensure(l2hmc_ctx *ctx, DevBuf &b, size_t n) {
 }
 
 static inline int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+#include "layered_host.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // Component kernels (Dynamics methods; not the hot path)
@@ -136,7 +166,7 @@ __global__ void k_p_accept(EnergyDev en, Shape sh, long long n, const float *x0,
 
 constexpr int NET_MAXH = 256;
 __global__ void k_net_apply(NetRaw w, int D, int H, int T, int hmc, long long n, const float *a, const float *b,
-                            float step, float *S, float *Tt, float *Q) {
+                            float step, float *S, float *Tt, float *Q, const float *eaux, int lde) {
   long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (g >= n) return;
   if (hmc) {
@@ -154,6 +184,7 @@ __global__ void k_net_apply(NetRaw w, int D, int H, int T, int hmc, long long n,
     }
     float e3 = fmaf(st, w.W3[H + j], ct * w.W3[j]);
     float s = (((0.f + (e1 + w.b1[j])) + (e2 + w.b2[j])) + (e3 + w.b3[j]));
+    if (eaux) s += eaux[g * lde + j];  // 4th Zip entry: encoder_sampler(aux), mnist_vae.py:149
     h1[j] = fmaxf(s, 0.f);
   }
   for (int j = 0; j < H; ++j) {
@@ -350,8 +381,17 @@ static int resolve_kernel(l2hmc_ctx *ctx, int *out) {
   const bool tc_energy = ctx->energy_set && ((ctx->en.kind == L2HMC_ENERGY_GAUSSIAN && ctx->en.ncomp == 1) ||
                                              ctx->en.kind == L2HMC_ENERGY_ROUGHWELL);
   const bool tc_auto = ctx->tc_ok && tc_energy && sh.D >= 8 && sh.H >= 32;
-  if (k == L2HMC_KERNEL_AUTO) k = small_ok ? L2HMC_KERNEL_SMALL : (tc_auto ? L2HMC_KERNEL_TC : L2HMC_KERNEL_TILE);
-  if (k == L2HMC_KERNEL_TILE) {
+  // what only the layered engine covers: the decoder energy, aux-conditioned nets, shapes beyond one SM's tile
+  const bool needs_layered = (ctx->energy_set && ctx->en.kind == L2HMC_ENERGY_DECODER) || ctx->lay.enc.n_layers > 0 ||
+                             sh.DP > 64 || (!sh.hmc && sh.HP > 128);
+  if (k == L2HMC_KERNEL_AUTO)
+    k = needs_layered ? L2HMC_KERNEL_LAYERED
+                      : (small_ok ? L2HMC_KERNEL_SMALL : (tc_auto ? L2HMC_KERNEL_TC : L2HMC_KERNEL_TILE));
+  if (k != L2HMC_KERNEL_LAYERED && ((ctx->energy_set && ctx->en.kind == L2HMC_ENERGY_DECODER) || ctx->lay.enc.n_layers > 0))
+    return fail(ctx, L2HMC_EUNSUPPORTED, "the decoder energy and aux-conditioned nets run on the layered engine only");
+  if (k == L2HMC_KERNEL_LAYERED) {
+    if (!sh.hmc && sh.H > 65536) return fail(ctx, L2HMC_EUNSUPPORTED, "layered engine: width too large");
+  } else if (k == L2HMC_KERNEL_TILE) {
     if (sh.DP > 64 || (!sh.hmc && sh.HP > 128))
       return fail(ctx, L2HMC_EUNSUPPORTED, "tile kernel covers x_dim <= 64 and width <= 128 (got %d, %d)", sh.D, sh.H);
   } else if (k == L2HMC_KERNEL_SMALL) {
@@ -397,11 +437,12 @@ extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
   sh.T = cfg->T;
   sh.LDE = 128;
   sh.LDH = 192;
-  sh.LDS = 128;
+  sh.LDS = round_up(sh.DP, 128);
   sh.hmc = cfg->hmc ? 1 : 0;
   sh.eps = cfg->eps;
   ctx->en.kind = L2HMC_ENERGY_NONE;
   ctx->en.temperature = 1.0f;
+  lay_setup_dims(ctx);
   int rc = pick_kernel(ctx);
   if (rc != L2HMC_OK) {
     g_err = ctx->err;
@@ -424,6 +465,18 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
                     &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
+  {
+    LayeredCtx &L = ctx->lay;
+    DevBuf *lb[] = {&L.net_buf[0], &L.net_buf[1], &L.dec.buf, &L.enc.buf, &L.x, &L.v, &L.x0, &L.ab, &L.hd, &L.hA, &L.hB,
+                    &L.vec, &L.eaux, &L.auxp, &L.tbias, &ctx->haux};
+    for (DevBuf *b : lb)
+      if (b->p) cudaFree(b->p);
+    for (DevBuf &b : L.dact)
+      if (b.p) cudaFree(b.p);
+    for (DevBuf &b : L.eact)
+      if (b.p) cudaFree(b.p);
+    if (L.ws_event) cudaEventDestroy(L.ws_event);
+  }
   if (ctx->hdir) cudaFree(ctx->hdir);
   if (ctx->hacc) cudaFree(ctx->hacc);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
@@ -471,6 +524,14 @@ extern "C" int l2hmc_set_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params 
     r.W3 = b + off[4]; r.b3 = b + off[5]; r.W4 = b + off[6]; r.b4 = b + off[7];
     r.Ws = b + off[8]; r.bs = b + off[9]; r.Wt = b + off[10]; r.bt = b + off[11];
     r.Wq = b + off[12]; r.bq = b + off[13]; r.ls = b + off[14]; r.lq = b + off[15];
+  }
+
+  // ---- layered-engine layout (any shape) ----------------------------------------------------------
+  rc = lay_pack_net(ctx, net_id, p);
+  if (rc) return rc;
+  if (sh.HP > sh.LDE || 3 * sh.DP > sh.LDH) {  // beyond the fused kernels' layouts: layered engine only
+    ctx->net_set[net_id] = true;
+    return L2HMC_OK;
   }
 
   // ---- packed copy (tile-kernel layout, see NetDev) ---------------------------------------------
@@ -616,6 +677,75 @@ extern "C" int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const floa
   return L2HMC_OK;
 }
 
+static int set_aux_dim(l2hmc_ctx *ctx, int aux_dim, const char *who) {
+  layered::LayDims &dm = ctx->lay.dm;
+  const bool other_uses = (std::string(who) == "l2hmc_set_energy_decoder") ? ctx->lay.enc.n_layers > 0
+                                                                            : (ctx->energy_set && ctx->en.kind == L2HMC_ENERGY_DECODER);
+  if (other_uses && dm.aux != aux_dim)
+    return fail(ctx, L2HMC_EINVAL, "%s: aux_dim %d differs from the one already configured (%d)", who, aux_dim, dm.aux);
+  dm.aux = aux_dim;
+  dm.auxp = round_up(aux_dim, 8);
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_energy_decoder(l2hmc_ctx *ctx, int n_layers, const int32_t *widths, const float *const *W,
+                                        const float *const *b) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy_decoder: null context");
+  if (ctx->cfg.kernel != L2HMC_KERNEL_AUTO && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED)
+    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_energy_decoder: the decoder energy runs on the layered engine only");
+  if (!widths || n_layers < 1) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy_decoder: bad argument");
+  if (widths[0] != ctx->sh.D)
+    return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy_decoder: first width %d is not x_dim %d", widths[0], ctx->sh.D);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  int rc = set_aux_dim(ctx, widths[n_layers], "l2hmc_set_energy_decoder");
+  if (rc) return rc;
+  if ((rc = lay_pack_mlp(ctx, ctx->lay.dec, n_layers, widths, W, b, "l2hmc_set_energy_decoder"))) return rc;
+  EnergyDev en = ctx->en;
+  en.kind = L2HMC_ENERGY_DECODER;
+  en.ncomp = 1;
+  en.mu = en.Ssym = en.logc = nullptr;
+  en.s0 = en.s1 = 0.f;
+  ctx->en = en;
+  ctx->energy_set = true;
+  int k = ctx->kernel;
+  if ((rc = resolve_kernel(ctx, &k))) return rc;
+  ctx->kernel = k;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_aux_encoder(l2hmc_ctx *ctx, int n_layers, const int32_t *widths, const float *const *W,
+                                     const float *const *b) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_aux_encoder: null context");
+  if (n_layers == 0) {
+    ctx->lay.enc.n_layers = 0;
+    int k = ctx->kernel;
+    if (resolve_kernel(ctx, &k) == L2HMC_OK) ctx->kernel = k;
+    return L2HMC_OK;
+  }
+  if (ctx->sh.hmc) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_aux_encoder: context is hmc (nets are zero)");
+  if (ctx->cfg.kernel != L2HMC_KERNEL_AUTO && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED)
+    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_aux_encoder: aux-conditioned nets run on the layered engine only");
+  if (!widths || n_layers < 1) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_aux_encoder: bad argument");
+  if (widths[n_layers] != ctx->sh.H)
+    return fail(ctx, L2HMC_EINVAL, "l2hmc_set_aux_encoder: last width %d is not the net width %d", widths[n_layers], ctx->sh.H);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  int rc = set_aux_dim(ctx, widths[0], "l2hmc_set_aux_encoder");
+  if (rc) return rc;
+  if ((rc = lay_pack_mlp(ctx, ctx->lay.enc, n_layers, widths, W, b, "l2hmc_set_aux_encoder"))) return rc;
+  int k = ctx->kernel;
+  if ((rc = resolve_kernel(ctx, &k))) return rc;
+  ctx->kernel = k;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_bind_aux(l2hmc_ctx *ctx, int64_t n, const float *aux) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_bind_aux: null context");
+  if (aux && n < 0) return fail(ctx, L2HMC_EINVAL, "l2hmc_bind_aux: n < 0");
+  ctx->lay.aux = aux;
+  ctx->lay.aux_n = aux ? n : 0;
+  return L2HMC_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // hot path
 // ---------------------------------------------------------------------------------------------
@@ -737,6 +867,10 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     }
     const long long blocks = (a->n + tile::M - 1) / tile::M;
     tile::transition_kernel<<<(unsigned)blocks, tile::NT, smem, stream>>>(K);
+  } else if (kernel == L2HMC_KERNEL_LAYERED) {
+    int rc = launch_layered(ctx, a, K.io, stream);  // counts its own launches
+    if (rc) return rc;
+    ctx->launches -= 1;
   } else {
     return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_transition: kernel kind %d not available", ctx->kernel);
   }
@@ -791,6 +925,12 @@ extern "C" int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hdir, a->dir, K * n, cudaMemcpyHostToDevice, s));
     d.dir = ctx->hdir;
   }
+  if (a->aux && ctx->lay.dm.aux > 0) {
+    const size_t na = n * (size_t)ctx->lay.dm.aux;
+    if ((rc = ensure(ctx, ctx->haux, na))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->haux.p, a->aux, na * sizeof(float), cudaMemcpyHostToDevice, s));
+    d.aux = ctx->haux.p;
+  }
   if ((rc = ensure(ctx, ctx->hxo, n * D))) return rc;
   if ((rc = ensure(ctx, ctx->hpx, n))) return rc;
   d.x_out = ctx->hxo.p;
@@ -822,11 +962,31 @@ extern "C" int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args
 // ---------------------------------------------------------------------------------------------
 #define GRID(n) (unsigned)(((n) + 127) / 128), 128
 
+// Decoder target: U(x) -> workspace U (and grad U(x) -> ab[:, D:2D]) for caller rows x [n, D] and the bound aux rows.
+static int lay_component_energy(l2hmc_ctx *ctx, cudaStream_t s, int64_t n, const float *x, int want_grad, const char *who) {
+  if (!ctx->lay.aux || ctx->lay.aux_n != n)
+    return fail(ctx, L2HMC_EINVAL, "%s: bind aux rows for these %lld chains first (l2hmc_bind_aux)", who, (long long)n);
+  int rc = lay_ensure_ws(ctx, n, s);
+  if (rc) return rc;
+  ctx->lay.ws_n = n;
+  const layered::LayDims &dm = ctx->lay.dm;
+  const long long tot = n * dm.D;
+  layered::k_lay_copy_rows<<<(unsigned)((tot + 255) / 256), 256, 0, s>>>(x, dm.D, ctx->lay.x.p, dm.Dp, dm.D, n);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return lay_energy_grad(ctx, s, n, ctx->lay.aux, want_grad);
+}
+
 extern "C" int l2hmc_energy(l2hmc_ctx *ctx, int64_t n, const float *x, float *out, void *stream) {
   int rc = check_ready(ctx, "l2hmc_energy");
   if (rc) return rc;
   if (n <= 0) return L2HMC_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  if (ctx->en.kind == L2HMC_ENERGY_DECODER) {
+    if ((rc = lay_component_energy(ctx, (cudaStream_t)stream, n, x, 0, "l2hmc_energy"))) return rc;
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, lay_state(ctx, n).U, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return lay_release(ctx, (cudaStream_t)stream);
+  }
   k_energy<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x, out);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
@@ -837,6 +997,15 @@ extern "C" int l2hmc_grad_energy(l2hmc_ctx *ctx, int64_t n, const float *x, floa
   if (rc) return rc;
   if (n <= 0) return L2HMC_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  if (ctx->en.kind == L2HMC_ENERGY_DECODER) {
+    if ((rc = lay_component_energy(ctx, (cudaStream_t)stream, n, x, 1, "l2hmc_grad_energy"))) return rc;
+    const layered::LayDims &dm = ctx->lay.dm;
+    const long long tot = n * dm.D;
+    layered::k_lay_copy_rows<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(ctx->lay.ab.p + dm.D, dm.K1p, out, dm.D, dm.D, n);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return lay_release(ctx, (cudaStream_t)stream);
+  }
   k_grad<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x, out);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
@@ -856,6 +1025,13 @@ extern "C" int l2hmc_hamiltonian(l2hmc_ctx *ctx, int64_t n, const float *x, cons
   if (rc) return rc;
   if (n <= 0) return L2HMC_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  if (ctx->en.kind == L2HMC_ENERGY_DECODER) {
+    if ((rc = lay_component_energy(ctx, (cudaStream_t)stream, n, x, 0, "l2hmc_hamiltonian"))) return rc;
+    layered::k_lay_hamiltonian<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->sh.D, n, lay_state(ctx, n).U, v, out);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return lay_release(ctx, (cudaStream_t)stream);
+  }
   k_hamiltonian<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x, v, out);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
@@ -867,6 +1043,17 @@ extern "C" int l2hmc_p_accept(l2hmc_ctx *ctx, int64_t n, const float *x0, const 
   if (rc) return rc;
   if (n <= 0) return L2HMC_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  if (ctx->en.kind == L2HMC_ENERGY_DECODER) {
+    cudaStream_t s = (cudaStream_t)stream;
+    if ((rc = lay_component_energy(ctx, s, n, x0, 0, "l2hmc_p_accept"))) return rc;
+    float *U = lay_state(ctx, n).U, *U0 = ctx->lay.vec.p + 6 * n;
+    CUDA_TRY(ctx, cudaMemcpyAsync(U0, U, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if ((rc = lay_component_energy(ctx, s, n, x1, 0, "l2hmc_p_accept"))) return rc;
+    layered::k_lay_p_accept<<<GRID(n), 0, s>>>(ctx->sh.D, n, U0, U, v0, v1, log_jac, out);
+    CUDA_TRY(ctx, cudaGetLastError());
+    ctx->launches++;
+    return lay_release(ctx, s);
+  }
   k_p_accept<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->en, ctx->sh, n, x0, v0, x1, v1, log_jac, out);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
@@ -880,10 +1067,21 @@ extern "C" int l2hmc_net_apply(l2hmc_ctx *ctx, int net_id, int64_t n, const floa
   if (ctx->sh.H > NET_MAXH) return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_net_apply: width > %d", NET_MAXH);
   if (n <= 0) return L2HMC_OK;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const float *eaux = nullptr;
+  if (!ctx->sh.hmc && ctx->lay.enc.n_layers > 0) {
+    if (!ctx->lay.aux || ctx->lay.aux_n != n)
+      return fail(ctx, L2HMC_EINVAL, "l2hmc_net_apply: bind aux rows for these chains first (l2hmc_bind_aux)");
+    int rc = lay_ensure_ws(ctx, n, (cudaStream_t)stream);
+    if (rc) return rc;
+    ctx->lay.ws_n = n;
+    if ((rc = lay_encode_aux(ctx, (cudaStream_t)stream, n, ctx->lay.aux))) return rc;
+    eaux = ctx->lay.eaux.p;
+  }
   k_net_apply<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->net_rawv[net_id], ctx->sh.D, ctx->sh.H, ctx->sh.T, ctx->sh.hmc,
-                                                     n, a, b, step, S, T, Q);
+                                                     n, a, b, step, S, T, Q, eaux, ctx->lay.dm.Hp);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
+  if (eaux) return lay_release(ctx, (cudaStream_t)stream);
   return L2HMC_OK;
 }
 extern "C" int l2hmc_accept(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset, const float *x, const float *Lx,
@@ -918,6 +1116,7 @@ extern "C" const char *l2hmc_kernel_name(const l2hmc_ctx *ctx) {
     case L2HMC_KERNEL_TILE: return "tile_fma";
     case L2HMC_KERNEL_SMALL: return "small_fma";
     case L2HMC_KERNEL_TC: return "tc_3xtf32";
+    case L2HMC_KERNEL_LAYERED: return "layered_fma";
     default: return "none";
   }
 }

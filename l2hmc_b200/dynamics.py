@@ -10,8 +10,11 @@ Differences a reference user should know (all additive or forced by eager execut
   * randomness is Philox keyed by ``seed`` and a per-object call counter (the reference is unseeded);
     explicit momentum via ``init_v`` exactly as in the reference, explicit direction bits / accept
     uniforms through the keyword-only ``rng`` argument of ``propose``;
-  * ``energy_function`` must come from ``l2hmc_b200.distributions`` (closed-form descriptor); an
-    arbitrary Python callable cannot be fused into the kernel and is rejected loudly.
+  * ``energy_function`` must come from ``l2hmc_b200.distributions`` (closed-form descriptor) or be a
+    ``l2hmc_b200.vae.DecoderEnergy`` (the ``energy(z, aux)`` closure of mnist_vae.py:122-126); an
+    arbitrary Python callable cannot be fused into the kernels and is rejected loudly;
+  * ``aux`` (mnist_vae.py:196,204 pass the image batch) is a CUDA fp32 [N, aux_dim] tensor; it is required
+    exactly when the energy or the nets consume it.
 """
 from __future__ import annotations
 
@@ -23,12 +26,13 @@ import numpy as np
 import torch
 
 from . import _lib
-from .layers import compile_stq_net
+from .layers import compile_softplus_mlp, compile_stq_net
 
 TORCH_FLOAT = torch.float32
 NP_FLOAT = np.float32
 
-_KERNELS = {"auto": _lib.KERNEL_AUTO, "tile": _lib.KERNEL_TILE, "small": _lib.KERNEL_SMALL, "tc": _lib.KERNEL_TC}
+_KERNELS = {"auto": _lib.KERNEL_AUTO, "tile": _lib.KERNEL_TILE, "small": _lib.KERNEL_SMALL, "tc": _lib.KERNEL_TC,
+            "layered": _lib.KERNEL_LAYERED}
 
 
 def _fptr(a: np.ndarray):
@@ -106,6 +110,7 @@ class Dynamics(object):
             self.width = int(self._net_params[0]["W4"].shape[0])
             if self._net_params[1]["W4"].shape[0] != self.width:
                 raise ValueError("XNet and VNet must have the same width")
+        self._compile_aux_encoder()
 
         if torch.cuda.is_available():
             self._ensure_ctx()
@@ -129,6 +134,45 @@ class Dynamics(object):
         if not self.hmc:
             self._push_nets()
 
+    def _compile_aux_encoder(self):
+        """The 4th Zip entry of both nets: `lambda _: 0.` or ONE softplus MLP of aux shared by XNet and VNet
+        (encoder_sampler, mnist_vae.py:134-149)."""
+        self._aux_encoder = None
+        if self.hmc or self._net_params is None:
+            return
+        ex, ev = (p.get("aux_encoder") for p in self._net_params)
+        if ex is None and ev is None:
+            return
+        if ex is None or ev is None:
+            raise ValueError("XNet and VNet must both take the aux encoding or neither")
+        wx, Wx, bx = compile_softplus_mlp(ex, "aux encoder")
+        if ev is not ex:
+            wv, Wv, bv = compile_softplus_mlp(ev, "aux encoder")
+            same = wx == wv and all(np.array_equal(a, b) for a, b in zip(Wx + bx, Wv + bv))
+            if not same:
+                raise ValueError("XNet and VNet must share one aux encoder (mnist_vae.py:134-149 builds a single "
+                                 "encoder_sampler); two different encoders are not supported")
+        if wx[-1] != self.width:
+            raise ValueError("aux encoder ends in %d units but the nets are %d wide" % (wx[-1], self.width))
+        self._aux_encoder = (wx, Wx, bx)
+
+    @property
+    def aux_dim(self):
+        """Columns of the aux rows this Dynamics consumes (0: none)."""
+        if getattr(self._fn, "kind", None) == _lib.ENERGY_DECODER:
+            return int(self._fn.aux_dim)
+        if self._aux_encoder is not None:
+            return int(self._aux_encoder[0][0])
+        return 0
+
+    @staticmethod
+    def _mlp_args(widths, Ws, bs):
+        n = len(Ws)
+        w = (C.c_int32 * (n + 1))(*[int(v) for v in widths])
+        Wp = (C.POINTER(C.c_float) * n)(*[_fptr(a) for a in Ws])
+        bp = (C.POINTER(C.c_float) * n)(*[_fptr(a) for a in bs])
+        return n, w, Wp, bp
+
     def __del__(self):
         try:
             if self._ctx is not None and self._lib is not None:
@@ -142,6 +186,10 @@ class Dynamics(object):
 
     def _push_energy(self):
         e = self._fn
+        if e.kind == _lib.ENERGY_DECODER:
+            n, w, Wp, bp = self._mlp_args(e.widths, e.Ws, e.bs)
+            self._chk(self._lib.l2hmc_set_energy_decoder(self._ctx, n, w, Wp, bp))
+            return
         null = C.POINTER(C.c_float)()
         mu = _fptr(e.mu) if e.mu is not None else null
         S = _fptr(e.S) if e.S is not None else null
@@ -160,11 +208,15 @@ class Dynamics(object):
                                                              "Ws", "bs", "Wt", "bt", "Wq", "bq")},
                                 scale_s=_fptr(p["ls"]), scale_q=_fptr(p["lq"]))
             self._chk(self._lib.l2hmc_set_net(self._ctx, net_id, C.byref(st)))
+        if self._aux_encoder is not None:
+            n, w, Wp, bp = self._mlp_args(*self._aux_encoder)
+            self._chk(self._lib.l2hmc_set_aux_encoder(self._ctx, n, w, Wp, bp))
 
     def refresh(self):
         """Re-read XNet/VNet weights from the layer objects (after loading a checkpoint into them)."""
         if not self.hmc:
             self._net_params = [compile_stq_net(self.XNet, self.x_dim), compile_stq_net(self.VNet, self.x_dim)]
+            self._compile_aux_encoder()
             if self._ctx is not None:
                 self._push_nets()
 
@@ -225,9 +277,23 @@ class Dynamics(object):
         t = float(self.temperature) if self.use_temperature else 1.0
         self._chk(self._lib.l2hmc_set_temperature(self._ctx, t))
 
-    def _no_aux(self, aux):
-        if aux is not None:
-            raise NotImplementedError("aux-conditioned energies / nets (the MNIST-VAE target) are not in this build")
+    def _aux(self, aux, n):
+        """Validated aux rows for n chains, or None when this Dynamics consumes none (then aux is ignored exactly
+        as the reference's `aux=aux` pass-through to nets that drop it, SCGExperiment.ipynb:58)."""
+        ad = self.aux_dim
+        if ad == 0:
+            return None
+        if aux is None:
+            raise ValueError("this target / these nets are conditioned on aux: pass aux=[N, %d]" % ad)
+        aux = self._prep(aux, "aux", ad)
+        if aux.shape[0] != n:
+            raise ValueError("aux has %d rows for %d chains" % (aux.shape[0], n))
+        return aux
+
+    def _bind_aux(self, aux, n):
+        aux = self._aux(aux, n)
+        self._chk(self._lib.l2hmc_bind_aux(self._ctx, n, aux.data_ptr() if aux is not None else None))
+        return aux
 
     def next_counter(self, n=1):
         c = self._counter
@@ -235,7 +301,8 @@ class Dynamics(object):
         return c
 
     def _transition(self, x, *, v=None, dir_mode=_lib.DIR_FORWARD, direction=None, u=None, log_jac=False,
-                    do_mh=False, n_transitions=1, want_v=True, counter=None, chain_offset=0, seed=None, out=None):
+                    do_mh=False, n_transitions=1, want_v=True, counter=None, chain_offset=0, seed=None, out=None,
+                    aux=None):
         """One l2hmc_transition call. Returns dict(Lx, Lv, px, x_next, accepted).  `out` may hold preallocated
         tensors of the right shapes under the same keys (steady-state loops then allocate nothing)."""
         self._ensure_ctx()
@@ -247,6 +314,10 @@ class Dynamics(object):
         a.n, a.chain_offset = n, int(chain_offset)
         a.x = x.data_ptr()
         keep = [x]
+        aux = self._aux(aux, n)
+        if aux is not None:
+            keep.append(aux)
+            a.aux = aux.data_ptr()
         if v is not None:
             v = self._prep(v, "init_v")
             if v.numel() != n_transitions * n * self.x_dim:
@@ -286,7 +357,7 @@ class Dynamics(object):
         return out
 
     def transition_host(self, x, *, v=None, direction=None, u=None, dir_mode=_lib.DIR_RANDOM, log_jac=False,
-                        do_mh=True, n_transitions=1, counter=None, chain_offset=0, seed=None, out=None):
+                        do_mh=True, n_transitions=1, counter=None, chain_offset=0, seed=None, out=None, aux=None):
         """The same transition through l2hmc_transition_host: numpy in, numpy out, H2D/D2H inside."""
         self._ensure_ctx()
         self._sync_temperature()
@@ -296,6 +367,14 @@ class Dynamics(object):
         a.n, a.chain_offset = n, int(chain_offset)
         a.x = x.ctypes.data
         keep = [x]
+        if self.aux_dim:
+            if aux is None:
+                raise ValueError("this target / these nets are conditioned on aux: pass aux=[N, %d]" % self.aux_dim)
+            aux = np.ascontiguousarray(aux, dtype=NP_FLOAT)
+            if aux.shape != (n, self.aux_dim):
+                raise ValueError("aux must be [%d, %d]" % (n, self.aux_dim))
+            keep.append(aux)
+            a.aux = aux.ctypes.data
         if v is not None:
             v = np.ascontiguousarray(v, dtype=NP_FLOAT)
             keep.append(v)
@@ -344,38 +423,39 @@ class Dynamics(object):
         return out
 
     def energy(self, x, aux=None):
-        self._no_aux(aux)
         self._ensure_ctx()
         self._sync_temperature()
         x = self._prep(x, "x", self.x_dim)
+        aux = self._bind_aux(aux, x.shape[0])
         out = torch.empty((x.shape[0],), dtype=TORCH_FLOAT, device=x.device)
         self._chk(self._lib.l2hmc_energy(self._ctx, x.shape[0], x.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
     def hamiltonian(self, x, v, aux=None):
-        self._no_aux(aux)
         self._ensure_ctx()
         self._sync_temperature()
         x = self._prep(x, "x", self.x_dim)
+        aux = self._bind_aux(aux, x.shape[0])
         v = self._prep(v, "v", self.x_dim)
         out = torch.empty((x.shape[0],), dtype=TORCH_FLOAT, device=x.device)
         self._chk(self._lib.l2hmc_hamiltonian(self._ctx, x.shape[0], x.data_ptr(), v.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
     def grad_energy(self, x, aux=None):
-        self._no_aux(aux)
         self._ensure_ctx()
         self._sync_temperature()
         x = self._prep(x, "x", self.x_dim)
+        aux = self._bind_aux(aux, x.shape[0])
         out = torch.empty_like(x)
         self._chk(self._lib.l2hmc_grad_energy(self._ctx, x.shape[0], x.data_ptr(), out.data_ptr(), self._stream()))
         return out
 
-    def net_apply(self, which, a, b, step):
-        """[S, T, Q] = {X,V}Net([a, b, _format_time(step), None]) on the GPU (diagnostic entry point)."""
+    def net_apply(self, which, a, b, step, aux=None):
+        """[S, T, Q] = {X,V}Net([a, b, _format_time(step), aux]) on the GPU (diagnostic entry point)."""
         self._ensure_ctx()
         a = self._prep(a, "a", self.x_dim)
         b = self._prep(b, "b", self.x_dim)
+        aux = self._bind_aux(aux, a.shape[0]) if self._aux_encoder is not None else None
         S, T, Q = (torch.empty_like(a) for _ in range(3))
         net_id = _lib.XNET if which in ("XNet", "x", 0) else _lib.VNET
         self._chk(self._lib.l2hmc_net_apply(self._ctx, net_id, a.shape[0], a.data_ptr(), b.data_ptr(), float(step),
@@ -383,20 +463,18 @@ class Dynamics(object):
         return [S, T, Q]
 
     def forward(self, x, init_v=None, aux=None, log_path=False, log_jac=False):
-        self._no_aux(aux)
-        o = self._transition(x, v=init_v, dir_mode=_lib.DIR_FORWARD, log_jac=log_jac)
+        o = self._transition(x, v=init_v, dir_mode=_lib.DIR_FORWARD, log_jac=log_jac, aux=aux)
         return o["Lx"], o["Lv"], o["px"]
 
     def backward(self, x, init_v=None, aux=None, log_jac=False):
-        self._no_aux(aux)
-        o = self._transition(x, v=init_v, dir_mode=_lib.DIR_BACKWARD, log_jac=log_jac)
+        o = self._transition(x, v=init_v, dir_mode=_lib.DIR_BACKWARD, log_jac=log_jac, aux=aux)
         return o["Lx"], o["Lv"], o["px"]
 
     def p_accept(self, x0, v0, x1, v1, log_jac, aux=None):
-        self._no_aux(aux)
         self._ensure_ctx()
         self._sync_temperature()
         x0, v0, x1, v1 = (self._prep(t, n, self.x_dim) for t, n in ((x0, "x0"), (v0, "v0"), (x1, "x1"), (v1, "v1")))
+        aux = self._bind_aux(aux, x0.shape[0])
         lj = self._prep(log_jac, "log_jac")
         out = torch.empty((x0.shape[0],), dtype=TORCH_FLOAT, device=x0.device)
         self._chk(self._lib.l2hmc_p_accept(self._ctx, x0.shape[0], x0.data_ptr(), v0.data_ptr(), x1.data_ptr(),

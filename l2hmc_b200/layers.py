@@ -148,11 +148,37 @@ def _zero_aux(f) -> bool:
     return isinstance(r, (int, float)) and r == 0
 
 
+def _is_softplus(f) -> bool:
+    return (f is softplus or f is torch.nn.functional.softplus or getattr(f, "__name__", "") == "softplus")
+
+
+def compile_softplus_mlp(seq, what="softplus MLP"):
+    """Weights of Sequential([Linear, softplus, Linear, ..., Linear]) (the decoder, mnist_vae.py:104-111, and the
+    nets' aux encoder, mnist_vae.py:134-140) as (widths, [W...], [b...]) fp32 arrays."""
+    if not isinstance(seq, Sequential) or len(seq.layers) < 1 or len(seq.layers) % 2 != 1:
+        raise NetStructureError("%s must be Sequential([Linear, softplus, ..., Linear])" % what)
+    Ws, bs, widths = [], [], []
+    for i, l in enumerate(seq.layers):
+        if i % 2 == 0:
+            if not isinstance(l, Linear):
+                raise NetStructureError("%s: stage %d must be Linear" % (what, i))
+            if widths and widths[-1] != l.in_:
+                raise NetStructureError("%s: Linear %s takes %d inputs after a layer of %d" % (what, l.scope, l.in_, widths[-1]))
+            if not widths:
+                widths.append(l.in_)
+            widths.append(l.out_)
+            Ws.append(np.ascontiguousarray(l.W.detach().cpu().numpy().astype(np.float32)))
+            bs.append(np.ascontiguousarray(l.b.detach().cpu().numpy().astype(np.float32)))
+        elif not _is_softplus(l):
+            raise NetStructureError("%s: stage %d must be softplus" % (what, i))
+    return widths, Ws, bs
+
+
 def compile_stq_net(net, x_dim: int) -> Dict[str, np.ndarray]:
     """Extract the weights of a canonical S/T/Q net as fp32 arrays keyed like the C ABI struct
     (include/l2hmc.h: l2hmc_net_params).  Accepted structure (SCGExperiment.ipynb:51-77):
 
-        Sequential([Zip([Linear(D,H), Linear(D,H), Linear(2,H), <zero aux>]), sum, relu,
+        Sequential([Zip([Linear(D,H), Linear(D,H), Linear(2,H), <zero aux | softplus-MLP encoder of aux>]), sum, relu,
                     Linear(H,H), relu,
                     Parallel([Sequential([Linear(H,D), ScaleTanh(D)]), Linear(H,D),
                               Sequential([Linear(H,D), ScaleTanh(D)])])])
@@ -168,8 +194,12 @@ def compile_stq_net(net, x_dim: int) -> Dict[str, np.ndarray]:
     e1, e2, e3 = z.layers[:3]
     if not all(isinstance(e, Linear) for e in (e1, e2, e3)):
         bad("Zip entries 0-2 must be Linear")
+    aux_enc = None
     if len(z.layers) == 4 and not _zero_aux(z.layers[3]):
-        bad("a non-zero aux branch (4th Zip entry) is not supported by this build")
+        # encoder_sampler of mnist_vae.py:134-149: a Linear/softplus stack of aux, shared by XNet and VNet
+        if not isinstance(z.layers[3], Sequential):
+            bad("the aux branch (4th Zip entry) must be `lambda _: 0.` or Sequential([Linear, softplus, ..., Linear])")
+        aux_enc = z.layers[3]
     if not _is_sum(s) or not _is_relu(r1) or not _is_relu(r2):
         bad("stages 1,2,4 must be sum, relu, relu")
     if not isinstance(lin, Linear):
@@ -203,6 +233,7 @@ def compile_stq_net(net, x_dim: int) -> Dict[str, np.ndarray]:
         "W4": f(lin.W), "b4": f(lin.b), "Ws": f(ls_.W), "bs": f(ls_.b), "Wt": f(ht.W), "bt": f(ht.b),
         "Wq": f(lq_.W), "bq": f(lq_.b),
         "ls": f(ss_.log_scale).reshape(-1), "lq": f(sq_.log_scale).reshape(-1),
+        "aux_encoder": aux_enc,
     }
 
 

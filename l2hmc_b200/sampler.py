@@ -31,11 +31,10 @@ def propose(x, dynamics, init_v=None, aux=None, do_mh_step=False, log_jac=False,
         # utils/sampler.py:29-31 -- forward only, init_v forwarded, MH output always appended
         v = init_v if init_v is not None else rng.get("v")
         o = dynamics._transition(x, v=v, dir_mode=_lib.DIR_FORWARD, u=rng.get("u"), do_mh=True,
-                                 n_transitions=n_transitions)
+                                 n_transitions=n_transitions, aux=aux)
         return o["Lx"], o["Lv"], o["px"], [o["x_next"]]
-    dynamics._no_aux(aux)
     o = dynamics._transition(x, v=rng.get("v"), dir_mode=_lib.DIR_RANDOM, direction=rng.get("direction"),
-                             u=rng.get("u"), log_jac=log_jac, do_mh=do_mh_step, n_transitions=n_transitions)
+                             u=rng.get("u"), log_jac=log_jac, do_mh=do_mh_step, n_transitions=n_transitions, aux=aux)
     Lv = o["Lv"] if init_v is not None else None  # utils/sampler.py:40-42
     outputs = []
     if do_mh_step:
@@ -99,7 +98,6 @@ def chain_operator(init_x, dynamics, nb_steps, aux=None, init_v=None, do_mh_step
     rng: optional list (one dict per sub-proposal, see ``propose``) plus rng_final={'u': ...} as the
     last element for the closing MH step.
     """
-    dynamics._no_aux(aux)
     if init_v is None:
         init_v = randn_like(init_x, seed=dynamics.seed ^ 0x5EED, counter=dynamics.next_counter())
     x, v = init_x, init_v

@@ -40,9 +40,10 @@ def init_distributed(backend: Optional[str] = None) -> Tuple[int, int, int]:
     return rank, world, local
 
 
-def all_gather_chains(local: torch.Tensor, n_total: int, group=None) -> torch.Tensor:
+def all_gather_chains(local: torch.Tensor, n_total: int, group=None, out=None) -> torch.Tensor:
     """Reassemble a chain-sharded tensor ([n_local, ...] per rank, shard_bounds layout) into
-    [n_total, ...] on every rank with ONE all_gather (uneven shards are padded to the largest)."""
+    [n_total, ...] on every rank with ONE all_gather (uneven shards are padded to the largest).
+    ``out``: optional preallocated [n_total, ...] result (used when the shards are even)."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         if local.shape[0] != n_total:
             raise ValueError("single-rank gather: local has %d chains, expected %d" % (local.shape[0], n_total))
@@ -58,7 +59,8 @@ def all_gather_chains(local: torch.Tensor, n_total: int, group=None) -> torch.Te
     if local.shape[0] != pad:
         buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
         buf[: local.shape[0]] = local
-    out = torch.empty((world * pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    if out is None or tuple(out.shape) != (world * pad,) + tuple(local.shape[1:]):
+        out = torch.empty((world * pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
     dist.all_gather_into_tensor(out, buf.contiguous(), group=group)
     if n_total == world * pad:
         return out

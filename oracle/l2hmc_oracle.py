@@ -229,6 +229,74 @@ class FunnelEnergy(Energy):
 
 
 # --------------------------------------------------------------------------------------
+# VAE posterior target and aux-conditioned nets (mnist_vae.py)
+# --------------------------------------------------------------------------------------
+def softplus_mlp(Ws, bs, x):
+    """Sequential([Linear, softplus, ..., Linear]) (mnist_vae.py:104-111, 134-140): softplus between
+    layers, none after the last.  tf.nn.softplus(x) = log(1 + exp(x)), evaluated overflow-free."""
+    h = x
+    for i, (W, b) in enumerate(zip(Ws, bs)):
+        h = h @ W + b
+        if i + 1 < len(Ws):
+            h = torch.clamp(h, min=0) + torch.log1p(torch.exp(-torch.abs(h)))
+    return h
+
+
+class DecoderBernoulliEnergy(Energy):
+    """energy(z, aux) of mnist_vae.py:122-126: sum_pix sigmoid_cross_entropy_with_logits(labels=aux,
+    logits=decoder(z)) + 0.5 |z|^2, decoder = Linear/softplus/Linear/softplus/Linear (:104-111).
+    TF's sigmoid_cross_entropy_with_logits is max(l, 0) - l*z + log(1 + exp(-|l|)).
+    The per-chain aux rows are held by the object (Dynamics passes aux= through, utils/dynamics.py:209-212)."""
+
+    def __init__(self, Ws, bs, aux, dtype=torch.float32):
+        self.Ws = [torch.as_tensor(np.asarray(W)).to(dtype) for W in Ws]
+        self.bs = [torch.as_tensor(np.asarray(b)).to(dtype) for b in bs]
+        self.aux = torch.as_tensor(np.asarray(aux)).to(dtype)
+        self.dtype = dtype
+
+    def to(self, dtype):
+        return DecoderBernoulliEnergy(self.Ws, self.bs, self.aux, dtype)
+
+    def select(self, idx):
+        e = DecoderBernoulliEnergy(self.Ws, self.bs, self.aux[idx], self.dtype)
+        return e
+
+    def energy(self, z):
+        l = softplus_mlp(self.Ws, self.bs, z)
+        bce = torch.clamp(l, min=0) - l * self.aux + torch.log1p(torch.exp(-torch.abs(l)))
+        return bce.sum(1) + 0.5 * (z * z).sum(1)
+
+    def grad(self, z):
+        """Reverse mode written out: dU/dl = sigmoid(l) - aux; softplus' = sigmoid(pre)."""
+        pres, hs = [], [z]
+        h = z
+        for i, (W, b) in enumerate(zip(self.Ws, self.bs)):
+            pre = h @ W + b
+            pres.append(pre)
+            if i + 1 < len(self.Ws):
+                h = torch.clamp(pre, min=0) + torch.log1p(torch.exp(-torch.abs(pre)))
+                hs.append(h)
+        d = torch.sigmoid(pres[-1]) - self.aux
+        for i in range(len(self.Ws) - 1, -1, -1):
+            d = d @ self.Ws[i].T
+            if i > 0:
+                d = d * torch.sigmoid(pres[i - 1])
+        return d + z
+
+
+def make_softplus_mlp(rng, widths, last_factor=1.0):
+    """Weights of a Linear/softplus stack with the reference initialiser (utils/layers.py:29-37,
+    factor 1.0; the decoder's last layer uses factor 0.01, mnist_vae.py:110); small biases so the
+    synthetic problem exercises them."""
+    Ws, bs = [], []
+    for i in range(len(widths) - 1):
+        f = last_factor if i == len(widths) - 2 else 1.0
+        Ws.append(trunc_normal(rng, (widths[i], widths[i + 1]), math.sqrt(1.3 * 2.0 * f / widths[i])))
+        bs.append((0.05 * rng.standard_normal(widths[i + 1])).astype(np.float32))
+    return Ws, bs
+
+
+# --------------------------------------------------------------------------------------
 # Dynamics (utils/dynamics.py)
 # --------------------------------------------------------------------------------------
 @dataclass
@@ -417,21 +485,28 @@ def propose(x, dyn: OracleDynamics, *, direction=None, v_f=None, v_b=None, u=Non
     return Lx, Lv, px, outputs
 
 
-def propose_selected(x, dyn: OracleDynamics, *, direction, v, log_jac=False):
+def propose_selected(x, dyn: OracleDynamics, *, direction, v, log_jac=False, ae_x=None, ae_v=None):
     """Same transition, but each chain runs only its selected direction with the single v it is given
     (what a fused kernel does).  Equal to propose(...) with v_f = v_b = v wherever the unselected
-    direction stays finite.  Returns (Lx, Lv, px)."""
+    direction stays finite.  Returns (Lx, Lv, px).  Energies that hold per-chain rows (aux) provide
+    ``select(idx)``; ae_x / ae_v are the per-chain aux embeddings of the two nets."""
+    import copy
     x = x.to(dyn.dtype)
     d = direction.to(torch.bool)
     Lx = torch.empty_like(x)
     Lv = torch.empty_like(x)
     px = torch.empty(x.shape[0], dtype=dyn.dtype)
-    if d.any():
-        a, b, c = dyn.forward(x[d], v[d].to(dyn.dtype), log_jac=log_jac)
-        Lx[d], Lv[d], px[d] = a, b, c
-    if (~d).any():
-        a, b, c = dyn.backward(x[~d], v[~d].to(dyn.dtype), log_jac=log_jac)
-        Lx[~d], Lv[~d], px[~d] = a, b, c
+    for sel, fn in ((d, "forward"), (~d, "backward")):
+        if not sel.any():
+            continue
+        sub = dyn
+        if hasattr(dyn.energy_obj, "select"):
+            sub = copy.copy(dyn)
+            sub.energy_obj = dyn.energy_obj.select(sel)
+        a, b, c = getattr(sub, fn)(x[sel], v[sel].to(dyn.dtype), log_jac=log_jac,
+                                   ae_x=None if ae_x is None else ae_x[sel],
+                                   ae_v=None if ae_v is None else ae_v[sel])
+        Lx[sel], Lv[sel], px[sel] = a, b, c
     return Lx, Lv, px
 
 

@@ -33,3 +33,7 @@ if __name__ == "__main__":
     path = os.path.join(HERE, "hmc_scg2_n200.npz")
     golden_io.save(path, "hmc_scg2_n200", hmc, 200, 16, "init")
     print(path, os.path.getsize(path))
+    # BASELINE config 5 in miniature: decoder-Bernoulli target + aux-conditioned nets (mnist_vae.py:104-178)
+    path = os.path.join(HERE, "c5_vae_mini_n96.npz")
+    golden_io.save_vae(path, "c5_vae_mini_n96", U.VAE_CONFIGS["c5_vae_mini"], 96, 17)
+    print(path, os.path.getsize(path))

@@ -1,0 +1,168 @@
+"""GPU parity of the layered engine (csrc/layered.cuh) against the CPU oracle, through the Python mirror -> C ABI.
+
+Covers BASELINE config 5 (the MNIST-VAE posterior target: decoder energy + aux-conditioned width-200 nets,
+mnist_vae.py:104-178) at the reference's layer sizes and in miniature / ragged shapes, and the same engine on the
+closed-form targets (where it must agree with the fused kernels' oracle too).
+
+Tolerances: as tests/test_gpu_parity.py -- samples within 2e-5 relative (or 4x the fp32 oracle's own error),
+accept probabilities within 5e-5 per chain (or 4x the fp32 oracle's own error: at the full layer sizes the energy is
+a sum over 784 pixels of O(500), so fp32 Hamiltonian differences carry ~1e-4 of noise in either implementation),
+their mean within 1e-5 (or 2x the fp32 oracle's).
+"""
+import numpy as np
+import pytest
+import torch
+
+import util as U
+
+pytestmark = pytest.mark.gpu
+
+SAMPLE_TOL = 2e-5
+P_TOL = 5e-5
+P_MEAN_TOL = 1e-5
+
+
+def _check(rep):
+    assert rep["Lx_kernel"] <= max(SAMPLE_TOL, 4 * rep["Lx_o32"]), rep
+    assert rep["Lv_kernel"] <= max(SAMPLE_TOL, 4 * rep["Lv_o32"]), rep
+    assert rep["px_kernel"] <= max(P_TOL, 4 * rep["px_o32"]), rep
+    assert rep["px_mean_kernel"] <= max(P_MEAN_TOL, 2 * rep["px_mean_o32"]), rep
+    assert rep["accept_flips_outside_noise"] == 0, rep
+
+
+@pytest.mark.parametrize("name,n", [
+    ("c5_vae_mini", 300),
+    ("c5_vae_ragged", 131),     # no dimension a multiple of 8, chains not a multiple of the 128-row tile
+    ("c5_vae_noenc", 200),      # decoder energy with the notebook's zero aux branch in the nets
+    ("c5_vae_full", 96),        # mnist_vae.py layer sizes: 50 / 1024-1024-784 / 512-512-200 / width 200 / Lf=15
+])
+def test_vae_target_matches_oracle(name, n):
+    P = U.VaeProblem(**U.VAE_CONFIGS[name])
+    dyn = P.product()
+    assert dyn.kernel_name == "layered_fma"
+    rep, _ = U.parity_report(P, n, dyn=dyn)
+    _check(rep)
+
+
+def test_vae_log_jac_mode():
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
+    rep, _ = U.parity_report(P, 192, log_jac=True)
+    assert rep["Lx_kernel"] <= max(SAMPLE_TOL, 4 * rep["Lx_o32"]), rep
+    assert rep["px_kernel"] <= max(2e-4, 4 * rep["px_o32"]), rep  # px is log|J| here
+
+
+def test_vae_components_match_oracle():
+    """Dynamics.energy / grad_energy / hamiltonian / p_accept / net call with aux= (utils/dynamics.py:203-218,302)."""
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
+    dyn = P.product()
+    n = 77
+    d = P.draws(n, seed=3)
+    o64, ae = P.oracle_for(d, torch.float64)
+    g = lambda a: torch.as_tensor(np.asarray(a)).cuda()  # noqa: E731
+    x, v, aux = g(d["x"]), g(d["v_f"]), g(d["aux"])
+    x64, v64 = U.t64(d["x"]), U.t64(d["v_f"])
+    e_ref = o64.energy(x64).numpy()
+    assert U.max_rel(dyn.energy(x, aux=aux).cpu().numpy(), e_ref) <= 2e-6
+    assert U.max_rel(dyn.grad_energy(x, aux=aux).cpu().numpy(), o64.grad_energy(x64).numpy()) <= 5e-6
+    assert U.max_rel(dyn.hamiltonian(x, v, aux=aux).cpu().numpy(), o64.hamiltonian(x64, v64).numpy()) <= 2e-6
+    x1, v1 = g(d["x"] * 0.9 + 0.05), g(d["v_b"])
+    lj = g(0.01 * d["u"])
+    p_ref = o64.p_accept(x64, v64, U.t64(d["x"] * 0.9 + 0.05), U.t64(d["v_b"]), U.t64(0.01 * d["u"])).numpy()
+    assert np.max(np.abs(dyn.p_accept(x, v, x1, v1, lj, aux=aux).cpu().numpy() - p_ref)) <= P_TOL
+    # the energy descriptor is callable like the reference's closure: energy(z, aux=aux)
+    assert U.max_rel(dyn._fn(x, aux=aux).cpu().numpy(), e_ref) <= 2e-6
+    # net call with the aux branch
+    S, T, Q = dyn.net_apply("XNet", v, x, 2.0, aux=aux)
+    tau = o64.format_time(2.0, n)
+    Sr, Tr, Qr = U.O.net_apply(o64.xnet, v64, x64, tau, ae)
+    for a, b in ((S, Sr), (T, Tr), (Q, Qr)):
+        assert U.max_rel(a.cpu().numpy(), b.numpy()) <= 5e-6
+    # aux is mandatory for this target
+    with pytest.raises(ValueError):
+        dyn.energy(x)
+    with pytest.raises(ValueError):
+        dyn.forward(x)
+
+
+def test_vae_forward_backward_roundtrip_and_host_path():
+    """backward(forward(x)) returns to x with log|J| cancelling (the reference's exact inverse), through aux-conditioned
+    nets; and l2hmc_transition_host (host buffers incl. aux) equals the device path."""
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
+    dyn = P.product()
+    d = P.draws(150, seed=5)
+    g = lambda a: torch.as_tensor(np.asarray(a)).cuda()  # noqa: E731
+    x, v, aux = g(d["x"]), g(d["v_f"]), g(d["aux"])
+    X, V, j1 = dyn.forward(x, init_v=v, aux=aux, log_jac=True)
+    x2, v2, j2 = dyn.backward(X, init_v=V, aux=aux, log_jac=True)
+    assert U.max_rel(x2.cpu().numpy(), d["x"]) <= 2e-5
+    assert U.max_rel(v2.cpu().numpy(), d["v_f"]) <= 2e-5
+    assert float((j1 + j2).abs().max()) <= 2e-4
+    o = dyn._transition(x, v=v, direction=g(d["dir"]), u=g(d["u"]), do_mh=True, aux=aux, counter=0)
+    h = dyn.transition_host(d["x"], v=d["v_f"], direction=d["dir"], u=d["u"], do_mh=True, aux=d["aux"], counter=0)
+    for k in ("Lx", "Lv", "px", "x_next"):
+        np.testing.assert_array_equal(o[k].cpu().numpy(), h[k])
+
+
+def test_vae_multi_transition_and_philox_sharding():
+    """n_transitions > 1 on the layered engine equals the host loop; Philox keyed by global chain id makes a
+    sharded run equal the unsharded one."""
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
+    dyn = P.product(seed=11)
+    d = P.draws(130, seed=7)
+    g = lambda a: torch.as_tensor(np.asarray(a)).cuda()  # noqa: E731
+    x, aux = g(d["x"]), g(d["aux"])
+    o3 = dyn._transition(x, dir_mode=3, do_mh=True, n_transitions=3, counter=5, aux=aux)
+    cur = x
+    for k in range(3):
+        o1 = dyn._transition(cur, dir_mode=3, do_mh=True, counter=5 + k, aux=aux)
+        cur = o1["x_next"]
+    np.testing.assert_array_equal(o3["x_next"].cpu().numpy(), cur.cpu().numpy())
+    np.testing.assert_array_equal(o3["px"].cpu().numpy(), o1["px"].cpu().numpy())
+    lo = dyn._transition(x[:50], dir_mode=3, do_mh=True, counter=9, aux=aux[:50], chain_offset=0)
+    hi = dyn._transition(x[50:], dir_mode=3, do_mh=True, counter=9, aux=aux[50:], chain_offset=50)
+    al = dyn._transition(x, dir_mode=3, do_mh=True, counter=9, aux=aux)
+    np.testing.assert_array_equal(torch.cat([lo["x_next"], hi["x_next"]]).cpu().numpy(), al["x_next"].cpu().numpy())
+
+
+@pytest.mark.parametrize("name,n,regime", [
+    ("c2_scg50", 200, "stress"),
+    ("c3_mog2", 130, "stress"),
+    ("c4_rw32_hard", 129, "stress"),
+    ("funnel3", 100, "stress"),
+])
+def test_layered_engine_on_closed_form_targets(name, n, regime):
+    """kernel='layered' forces the batched engine on shapes the fused kernels also cover."""
+    P = U.Problem(regime=regime, **U.CONFIGS[name])
+    dyn = P.product(kernel="layered")
+    assert dyn.kernel_name == "layered_fma"
+    rep, _ = U.parity_report(P, n, dyn=dyn)
+    _check(rep)
+
+
+def test_layered_hmc_mode():
+    P = U.Problem(kind="gaussian", D=50, T=10, eps=0.05, hmc=True)
+    rep, _ = U.parity_report(P, 200, dyn=P.product(kernel="layered"))
+    _check(rep)
+
+
+@pytest.mark.parametrize("D,H", [(80, 100), (50, 200), (130, 40)])
+def test_shapes_beyond_the_fused_kernels(D, H):
+    """x_dim > 64 or width > 128: AUTO must route to the layered engine (the fused kernels reject these)."""
+    P = U.Problem(kind="gaussian", D=D, H=H, T=5, eps=0.05, regime="stress")
+    dyn = P.product()
+    assert dyn.kernel_name == "layered_fma"
+    rep, _ = U.parity_report(P, 150, dyn=dyn)
+    _check(rep)
+    with pytest.raises(Exception):
+        P.product(kernel="tile")
+
+
+def test_vae_golden_fixture():
+    """Committed fp64-oracle vectors for the miniature config-5 problem (tests/golden/make_golden.py)."""
+    import os
+    import golden_io
+    P, d, gold = golden_io.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c5_vae_mini_n96.npz"))
+    rk = U.run_kernel_propose(P, d)
+    assert U.max_rel(rk["Lx"], gold["Lx"]) <= 4e-5
+    assert U.max_rel(rk["Lv"], gold["Lv"]) <= 4e-5
+    assert np.max(np.abs(rk["px"] - gold["px"])) <= P_TOL

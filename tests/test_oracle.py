@@ -193,3 +193,47 @@ def test_untrained_accept_rate_near_notebook():
         d["x"] = np.random.default_rng(s).standard_normal((200, 2)).astype(np.float32)  # notebook :257
         vals.append(float(U.run_oracle_propose(P, d, torch.float32)["px"].mean()))
     assert 0.75 < np.mean(vals) <= 1.0, vals
+
+
+# ---- BASELINE config 5: decoder-Bernoulli target + aux-conditioned nets (mnist_vae.py:104-178) ------------
+@pytest.mark.parametrize("name", ["c5_vae_mini", "c5_vae_ragged"])
+def test_vae_energy_gradient_is_reverse_mode_of_energy(name):
+    """Dynamics.grad_energy is tf.gradients(energy(x, aux), x) (utils/dynamics.py:217-218): the written-out reverse
+    pass of the decoder energy must equal autograd through energy()."""
+    P = U.VaeProblem(**U.VAE_CONFIGS[name])
+    d = P.draws(33)
+    dyn, _ = P.oracle_for(d, torch.float64)
+    x = U.t64(d["x"])
+    g = dyn.energy_obj.grad(x)
+    assert torch.allclose(g, dyn.energy_obj.grad_autodiff(x), rtol=0, atol=1e-12)
+    # sigmoid_cross_entropy_with_logits(labels=z, logits=l) == -(z log s(l) + (1-z) log(1-s(l)))
+    l = U.O.softplus_mlp(dyn.energy_obj.Ws, dyn.energy_obj.bs, x)
+    a = dyn.energy_obj.aux
+    bce = -(a * torch.nn.functional.logsigmoid(l) + (1 - a) * torch.nn.functional.logsigmoid(-l)).sum(1)
+    assert torch.allclose(dyn.energy(x), bce + 0.5 * (x * x).sum(1), rtol=0, atol=1e-10)
+
+
+def test_vae_backward_inverts_forward_with_aux_branch():
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
+    d = P.draws(40)
+    dyn, ae = P.oracle_for(d, torch.float64)
+    assert ae is not None and ae.shape == (40, P.H)
+    x, v = U.t64(d["x"]), U.t64(d["v_f"])
+    X, V, j1 = dyn.forward(x, v, log_jac=True, ae_x=ae, ae_v=ae)
+    x2, v2, j2 = dyn.backward(X, V, log_jac=True, ae_x=ae, ae_v=ae)
+    assert float((x2 - x).abs().max()) < 1e-9 and float((v2 - v).abs().max()) < 1e-9
+    assert float((j1 + j2).abs().max()) < 1e-9
+    # the aux branch matters: dropping it changes the proposal
+    X0, _, _ = dyn.forward(x, v, log_jac=True)
+    assert float((X0 - X).abs().max()) > 1e-4
+
+
+def test_vae_selected_direction_equals_blend():
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
+    d = P.draws(50)
+    dyn, ae = P.oracle_for(d, torch.float64)
+    ref = U.run_oracle_propose(P, d, torch.float64)
+    v_sel = np.where(d["dir"][:, None] != 0, d["v_f"], d["v_b"])
+    Lx, Lv, px = U.O.propose_selected(U.t64(d["x"]), dyn, direction=torch.as_tensor(d["dir"]), v=U.t64(v_sel),
+                                      ae_x=ae, ae_v=ae)
+    assert np.allclose(Lx.numpy(), ref["Lx"], atol=1e-12) and np.allclose(px.numpy(), ref["px"], atol=1e-12)

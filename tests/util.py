@@ -129,6 +129,107 @@ class Problem:
         }
 
 
+class VaeProblem:
+    """BASELINE config 5 in miniature or at full layer sizes: the decoder-Bernoulli posterior target of
+    mnist_vae.py:104-126 with S/T/Q nets that add a shared softplus-MLP encoding of aux to their first stage
+    (mnist_vae.py:134-167).  Random weights, Bernoulli(0.5) aux rows (no dataset here)."""
+    hmc = False
+
+    def __init__(self, D=8, H=24, T=4, eps=0.1, dec=(64, 64), aux_dim=40, enc=(32, 32), regime="stress", seed=0,
+                 use_encoder=True):
+        self.kind, self.D, self.H, self.T, self.eps = "decoder", D, H, T, eps
+        rng = np.random.default_rng(seed)
+        self.aux_dim = aux_dim
+        self.dec_w = [D] + list(dec) + [aux_dim]
+        self.dec_W, self.dec_b = O.make_softplus_mlp(rng, self.dec_w, last_factor=0.01)
+        self.use_encoder = use_encoder
+        if use_encoder:
+            self.enc_w = [aux_dim] + list(enc) + [H]
+            self.enc_W, self.enc_b = O.make_softplus_mlp(rng, self.enc_w)
+        self.mask = O.make_masks(rng, T, D)
+        self.xnet = O.make_net(rng, D, H, 2.0, regime)
+        self.vnet = O.make_net(rng, D, H, 1.0, regime)
+
+    def oracle_for(self, d, dtype=torch.float64, temperature=1.0):
+        en = O.DecoderBernoulliEnergy(self.dec_W, self.dec_b, d["aux"], dtype)
+        dyn = O.OracleDynamics(self.D, self.T, self.eps, en, self.mask, self.xnet, self.vnet, hmc=False,
+                               temperature=temperature, dtype=dtype)
+        ae = None
+        if self.use_encoder:
+            tt = lambda a: torch.as_tensor(np.asarray(a)).to(dtype)  # noqa: E731
+            ae = O.softplus_mlp([tt(W) for W in self.enc_W], [tt(b) for b in self.enc_b], tt(d["aux"]))
+        return dyn, ae
+
+    @staticmethod
+    def _mlp(widths, Ws, bs, scope):
+        from l2hmc_b200.layers import Linear, Sequential, softplus
+        layers = []
+        for i in range(len(Ws)):
+            l = Linear(widths[i], widths[i + 1], scope="%s_%d" % (scope, i + 1))
+            l.W = torch.as_tensor(Ws[i]).clone()
+            l.b = torch.as_tensor(bs[i]).clone()
+            layers.append(l)
+            if i + 1 < len(Ws):
+                layers.append(softplus)
+        return Sequential(layers)
+
+    def net_factory(self):
+        from l2hmc_b200.layers import Linear, Sequential, Zip, Parallel, ScaleTanh, relu, load_stq_net
+        H = self.H
+        params = {"XNet": self.xnet, "VNet": self.vnet}
+        encoder_sampler = self._mlp(self.enc_w, self.enc_W, self.enc_b, "encoder") if self.use_encoder else (lambda _: 0.)
+
+        def net_factory(x_dim, scope, factor):  # mnist_vae.py:142-167
+            net = Sequential([
+                Zip([
+                    Linear(x_dim, H, scope='embed_1', factor=0.33),
+                    Linear(x_dim, H, scope='embed_2', factor=factor * 0.33),
+                    Linear(2, H, scope='embed_3', factor=0.33),
+                    encoder_sampler,
+                ]),
+                sum,
+                relu,
+                Linear(H, H, scope='linear_1'),
+                relu,
+                Parallel([
+                    Sequential([Linear(H, x_dim, scope='linear_s', factor=0.01), ScaleTanh(x_dim, scope='scale_s')]),
+                    Linear(H, x_dim, scope='linear_t', factor=0.01),
+                    Sequential([Linear(H, x_dim, scope='linear_f', factor=0.01), ScaleTanh(x_dim, scope='scale_f')]),
+                ])
+            ])
+            load_stq_net(net, params[scope])
+            return net
+        return net_factory
+
+    def product(self, **kw):
+        from l2hmc_b200 import Dynamics
+        from l2hmc_b200.vae import DecoderEnergy
+        energy = DecoderEnergy(self._mlp(self.dec_w, self.dec_W, self.dec_b, "decoder"))
+        d = Dynamics(self.D, energy, T=self.T, eps=self.eps, net_factory=self.net_factory(), **kw)
+        d.mask = self.mask
+        return d
+
+    def draws(self, n, seed=1):
+        rng = np.random.default_rng(seed)
+        return {
+            "x": rng.standard_normal((n, self.D)).astype(np.float32),  # latent prior, like init_x = latent_q
+            "aux": (rng.random((n, self.aux_dim)) < 0.5).astype(np.float32),
+            "v_f": rng.standard_normal((n, self.D)).astype(np.float32),
+            "v_b": rng.standard_normal((n, self.D)).astype(np.float32),
+            "dir": rng.integers(0, 2, n).astype(np.uint8),
+            "u": rng.random(n).astype(np.float32),
+        }
+
+
+VAE_CONFIGS = {
+    "c5_vae_mini": dict(D=8, H=24, T=4, dec=(64, 64), aux_dim=40, enc=(32, 32)),
+    "c5_vae_ragged": dict(D=7, H=21, T=3, dec=(33,), aux_dim=19, enc=(10,)),   # nothing a multiple of 8
+    "c5_vae_noenc": dict(D=8, H=24, T=4, dec=(64, 64), aux_dim=40, use_encoder=False),
+    # the layer sizes of mnist_vae.py: latent 50, decoder 1024-1024-784, encoder 512-512-200, nets 200 wide, Lf=15
+    "c5_vae_full": dict(D=50, H=200, T=15, dec=(1024, 1024), aux_dim=784, enc=(512, 512)),
+}
+
+
 def t64(a):
     return torch.as_tensor(np.asarray(a)).to(torch.float64)
 
@@ -157,14 +258,14 @@ CONFIGS = {
 # ---- parity measurement (GPU) ------------------------------------------------------------------------
 def run_oracle_propose(P, d, dtype, log_jac=False):
     """Reference-style propose (both directions computed, blended) on the CPU oracle."""
-    dyn = P.oracle(dtype)
+    dyn, ae = P.oracle_for(d, dtype) if hasattr(P, "oracle_for") else (P.oracle(dtype), None)
     tt = lambda a: torch.as_tensor(np.asarray(a)).to(dtype)
     if P.hmc:
         Lx, Lv, px, outs = O.propose(tt(d["x"]), dyn, init_v=tt(d["v_f"]), u=tt(d["u"]), do_mh_step=True)
     else:
         Lx, Lv, px, outs = O.propose(tt(d["x"]), dyn, direction=torch.as_tensor(d["dir"].astype(np.float32)),
                                      v_f=tt(d["v_f"]), v_b=tt(d["v_b"]), u=tt(d["u"]), init_v=tt(d["v_f"]),
-                                     do_mh_step=True, log_jac=log_jac)
+                                     do_mh_step=True, log_jac=log_jac, ae_x=ae, ae_v=ae)
     return {"Lx": Lx.numpy(), "Lv": Lv.numpy(), "px": px.numpy(), "x_next": outs[0].numpy()}
 
 
@@ -174,11 +275,12 @@ def run_kernel_propose(P, d, dyn=None, log_jac=False, device="cuda"):
     dyn = dyn or P.product()
     g = lambda a: torch.as_tensor(np.asarray(a)).to(device)
     x = g(d["x"])
+    aux = g(d["aux"]) if "aux" in d else None
     if P.hmc:
-        Lx, Lv, px, outs = propose(x, dyn, init_v=g(d["v_f"]), do_mh_step=True, rng={"u": g(d["u"])})
+        Lx, Lv, px, outs = propose(x, dyn, init_v=g(d["v_f"]), aux=aux, do_mh_step=True, rng={"u": g(d["u"])})
     else:
         v_sel = np.where(d["dir"][:, None] != 0, d["v_f"], d["v_b"]).astype(np.float32)
-        Lx, Lv, px, outs = propose(x, dyn, init_v=g(v_sel), do_mh_step=True, log_jac=log_jac,
+        Lx, Lv, px, outs = propose(x, dyn, init_v=g(v_sel), aux=aux, do_mh_step=True, log_jac=log_jac,
                                    rng={"direction": g(d["dir"]), "v": g(v_sel), "u": g(d["u"])})
     torch.cuda.synchronize()
     return {"Lx": Lx.cpu().numpy(), "Lv": Lv.cpu().numpy(), "px": px.cpu().numpy(), "x_next": outs[0].cpu().numpy()}
