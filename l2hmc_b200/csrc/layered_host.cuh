@@ -192,6 +192,8 @@ int lay_gemm(l2hmc_ctx *ctx, cudaStream_t s, GemmArgs g) {
   g.vec = ((g.ldc % 4) == 0 && (g.N % 4) == 0 && (reinterpret_cast<uintptr_t>(g.C) % 16) == 0) ? 1 : 0;
   const int bn8 = round_up(g.N, 128), bn4 = round_up(g.N, 64);
   const unsigned my = (unsigned)((g.M + 127) / 128);
+  // Measured on B200 (profiles/r01_vae_launches.txt): both tile widths run at 46-50% of the FMA peak per padded
+  // column, so the one that pads N less wins (ties -> the wide tile).
   if (bn8 <= bn4) l2hmc::layered::sgemm_kernel<8><<<dim3(bn8 / 128, my), 256, 0, s>>>(g);
   else l2hmc::layered::sgemm_kernel<4><<<dim3(bn4 / 64, my), 256, 0, s>>>(g);
   CUDA_TRY(ctx, cudaGetLastError());
