@@ -68,8 +68,10 @@ typedef enum {
   L2HMC_KERNEL_TILE = 1,   /* generic fp32-FMA tile kernel (any D <= 64, H <= 128)               */
   L2HMC_KERNEL_SMALL = 2,  /* one chain per thread, nets in registers (D <= 4, H <= 16)          */
   L2HMC_KERNEL_TC = 3,     /* tcgen05 3xTF32 tensor-core kernel                                  */
-  L2HMC_KERNEL_LAYERED = 4 /* batched GEMM + elementwise launches over all chains: any x_dim / width,
-                              the decoder energy and aux-conditioned nets (state in HBM between launches) */
+  L2HMC_KERNEL_LAYERED = 4, /* batched GEMM + elementwise launches over all chains: any x_dim / width,
+                               the decoder energy and aux-conditioned nets (state in HBM between launches);
+                               GEMMs on tcgen05 (3xTF32, fp32-level accuracy)                              */
+  L2HMC_KERNEL_LAYERED_FMA = 5 /* the same engine with fp32-FMA GEMMs                                     */
 } l2hmc_kernel_kind;
 
 /* Dynamics.__init__(x_dim, energy_function, T, eps, hmc, net_factory, ...)  utils/dynamics.py:35-81 */

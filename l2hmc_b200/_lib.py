@@ -16,7 +16,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libl2hmc.so")
 SOURCES = ["l2hmc_api.cu"]
-HEADERS = ["common.cuh", "kernel_tile.cuh", "kernel_tc.cuh", "kernel_small.cuh", "layered.cuh", "layered_host.cuh",
+HEADERS = ["common.cuh", "kernel_tile.cuh", "kernel_tc.cuh", "kernel_small.cuh", "layered.cuh", "layered_host.cuh", "tc_gemm.cuh",
            os.path.join("..", "..", "include", "l2hmc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -92,7 +92,7 @@ class TransitionArgs(C.Structure):
 ENERGY_GAUSSIAN, ENERGY_GMM, ENERGY_ROUGHWELL, ENERGY_FUNNEL, ENERGY_DECODER = 0, 1, 2, 3, 4
 XNET, VNET = 0, 1
 DIR_FORWARD, DIR_BACKWARD, DIR_PER_CHAIN, DIR_RANDOM = 0, 1, 2, 3
-KERNEL_AUTO, KERNEL_TILE, KERNEL_SMALL, KERNEL_TC, KERNEL_LAYERED = 0, 1, 2, 3, 4
+KERNEL_AUTO, KERNEL_TILE, KERNEL_SMALL, KERNEL_TC, KERNEL_LAYERED, KERNEL_LAYERED_FMA = 0, 1, 2, 3, 4, 5
 
 # every symbol include/l2hmc.h declares: (name, restype, argtypes)
 _vp, _i64, _u64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_uint64, C.c_int32, C.c_float

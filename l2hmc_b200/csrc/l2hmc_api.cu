@@ -16,6 +16,9 @@
 #include "kernel_tc.cuh"
 #include "kernel_small.cuh"
 #include "layered.cuh"
+#include "tc_gemm.cuh"
+
+#include <map>
 
 using namespace l2hmc;
 
@@ -38,8 +41,15 @@ struct LayMlp {  // Linear / softplus stack (decoder of the energy, aux encoder 
   DevBuf buf;
   std::vector<const float *> W, Wt, b;
 };
+struct LayTcWeight {  // one weight matrix pre-split / pre-tiled for tc_gemm_kernel
+  tcg::TcGemmB d;
+  DevBuf buf;
+};
 struct LayeredCtx {
   layered::LayDims dm;
+  bool gemm_tc = true;                             // tcgen05 3xTF32 GEMMs (false: fp32 FMA sgemm_kernel)
+  std::map<const float *, LayTcWeight> tcw;        // keyed by the device pointer of the row-major weight
+  int sms = 0;
   DevBuf net_buf[2];
   LayNetView net[2];
   LayMlp dec, enc;
@@ -377,6 +387,10 @@ static int tc_pack_gaussian(l2hmc_ctx *ctx, const float *Ssym_padded /* [DP][LDS
 static int resolve_kernel(l2hmc_ctx *ctx, int *out) {
   const Shape &sh = ctx->sh;
   int k = ctx->cfg.kernel;
+  if (k == L2HMC_KERNEL_LAYERED_FMA) {  // the layered engine with fp32-FMA GEMMs
+    ctx->lay.gemm_tc = false;
+    k = L2HMC_KERNEL_LAYERED;
+  }
   const bool small_ok = sh.D <= 4 && (sh.hmc || sh.H <= 16);
   const bool tc_energy = ctx->energy_set && ((ctx->en.kind == L2HMC_ENERGY_GAUSSIAN && ctx->en.ncomp == 1) ||
                                              ctx->en.kind == L2HMC_ENERGY_ROUGHWELL);
@@ -443,6 +457,11 @@ extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
   ctx->en.kind = L2HMC_ENERGY_NONE;
   ctx->en.temperature = 1.0f;
   lay_setup_dims(ctx);
+  {
+    const char *gm = getenv("L2HMC_LAYERED_GEMM");  // "fma" forces the fp32 FMA GEMMs
+    if (gm && gm[0] == 'f') ctx->lay.gemm_tc = false;
+    cudaDeviceGetAttribute(&ctx->lay.sms, cudaDevAttrMultiProcessorCount, cfg->device);
+  }
   int rc = pick_kernel(ctx);
   if (rc != L2HMC_OK) {
     g_err = ctx->err;
@@ -475,6 +494,8 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
       if (b.p) cudaFree(b.p);
     for (DevBuf &b : L.eact)
       if (b.p) cudaFree(b.p);
+    for (auto &kv : L.tcw)
+      if (kv.second.buf.p) cudaFree(kv.second.buf.p);
     if (L.ws_event) cudaEventDestroy(L.ws_event);
   }
   if (ctx->hdir) cudaFree(ctx->hdir);
@@ -691,7 +712,7 @@ static int set_aux_dim(l2hmc_ctx *ctx, int aux_dim, const char *who) {
 extern "C" int l2hmc_set_energy_decoder(l2hmc_ctx *ctx, int n_layers, const int32_t *widths, const float *const *W,
                                         const float *const *b) {
   if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy_decoder: null context");
-  if (ctx->cfg.kernel != L2HMC_KERNEL_AUTO && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED)
+  if (ctx->cfg.kernel != L2HMC_KERNEL_AUTO && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED_FMA)
     return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_energy_decoder: the decoder energy runs on the layered engine only");
   if (!widths || n_layers < 1) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy_decoder: bad argument");
   if (widths[0] != ctx->sh.D)
@@ -723,7 +744,7 @@ extern "C" int l2hmc_set_aux_encoder(l2hmc_ctx *ctx, int n_layers, const int32_t
     return L2HMC_OK;
   }
   if (ctx->sh.hmc) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_aux_encoder: context is hmc (nets are zero)");
-  if (ctx->cfg.kernel != L2HMC_KERNEL_AUTO && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED)
+  if (ctx->cfg.kernel != L2HMC_KERNEL_AUTO && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED && ctx->cfg.kernel != L2HMC_KERNEL_LAYERED_FMA)
     return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_aux_encoder: aux-conditioned nets run on the layered engine only");
   if (!widths || n_layers < 1) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_aux_encoder: bad argument");
   if (widths[n_layers] != ctx->sh.H)
@@ -1116,7 +1137,7 @@ extern "C" const char *l2hmc_kernel_name(const l2hmc_ctx *ctx) {
     case L2HMC_KERNEL_TILE: return "tile_fma";
     case L2HMC_KERNEL_SMALL: return "small_fma";
     case L2HMC_KERNEL_TC: return "tc_3xtf32";
-    case L2HMC_KERNEL_LAYERED: return "layered_fma";
+    case L2HMC_KERNEL_LAYERED: return ctx->lay.gemm_tc ? "layered_tc3xtf32" : "layered_fma";
     default: return "none";
   }
 }

@@ -24,6 +24,19 @@ inline void lay_setup_dims(l2hmc_ctx *ctx) {
 
 // One S/T/Q net in the layered layout: Wemb [K1p][Hp] (rows 0..D-1 embed_1/W, D..2D-1 embed_2/W), tb [T][Hp] the
 // folded time-embedding bias, W4 [Hp][Hp], b4 [Hp], Wh [Hp][N3p] with columns [S | T | Q], bh [N3p], es/eq [Dp].
+// Pre-split (tf32 hi / lo) and pre-tile a row-major weight [K][ldb] for tc_gemm_kernel; keyed by its device pointer.
+int lay_tc_register(l2hmc_ctx *ctx, const float *dev_B, const float *host_B, int ldb, int K, int N) {
+  LayeredCtx &L = ctx->lay;
+  std::vector<float> pk;
+  LayTcWeight &w = L.tcw[dev_B];
+  l2hmc::tcg::pack_b(host_B, ldb, K, N, pk, &w.d);
+  int rc = ensure(ctx, w.buf, pk.size());
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(w.buf.p, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
+  w.d.pk = w.buf.p;
+  return L2HMC_OK;
+}
+
 int lay_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
   const LayDims &dm = ctx->lay.dm;
   const int D = dm.D, H = dm.H, Hp = dm.Hp, T = dm.T;
@@ -71,6 +84,9 @@ int lay_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
   v.bh = v.Wh + nWh;
   v.es = v.bh + nbh;
   v.eq = v.es + nes;
+  if ((rc = lay_tc_register(ctx, v.Wemb, Wemb, Hp, dm.K1p, Hp))) return rc;
+  if ((rc = lay_tc_register(ctx, v.W4, W4, Hp, Hp, Hp))) return rc;
+  if ((rc = lay_tc_register(ctx, v.Wh, Wh, dm.N3p, Hp, dm.N3p))) return rc;
   return L2HMC_OK;
 }
 
@@ -120,6 +136,8 @@ int lay_pack_mlp(l2hmc_ctx *ctx, LayMlp &m, int n_layers, const int32_t *widths,
     m.W[i] = m.buf.p + oW[i];
     m.Wt[i] = m.buf.p + oT[i];
     m.b[i] = m.buf.p + ob[i];
+    if ((rc = lay_tc_register(ctx, m.W[i], pk.data() + oW[i], m.wp[i + 1], m.wp[i], m.wp[i + 1]))) return rc;
+    if ((rc = lay_tc_register(ctx, m.Wt[i], pk.data() + oT[i], m.wp[i], m.wp[i + 1], m.wp[i]))) return rc;
   }
   m.n_layers = n_layers;
   return L2HMC_OK;
@@ -190,6 +208,17 @@ int lay_gemm(l2hmc_ctx *ctx, cudaStream_t s, GemmArgs g) {
   if (g.M <= 0 || g.N <= 0) return L2HMC_OK;
   if ((g.M + 127) / 128 > 65535) return fail(ctx, L2HMC_EUNSUPPORTED, "layered engine: more than 8.3M chains per call");
   g.vec = ((g.ldc % 4) == 0 && (g.N % 4) == 0 && (reinterpret_cast<uintptr_t>(g.C) % 16) == 0) ? 1 : 0;
+  if (ctx->lay.gemm_tc) {
+    // tensor-core path: the weight must have been registered, bias / C rows 16-byte aligned
+    auto it = ctx->lay.tcw.find(g.B);
+    const bool aligned = (reinterpret_cast<uintptr_t>(g.bias) % 16) == 0 && (reinterpret_cast<uintptr_t>(g.bias_b) % 16) == 0 &&
+                         (reinterpret_cast<uintptr_t>(g.A) % 16) == 0 && (g.lda % 4) == 0;
+    if (it != ctx->lay.tcw.end() && aligned) {
+      CUDA_TRY(ctx, l2hmc::tcg::launch_tc_gemm(g, it->second.d, ctx->lay.sms, s));
+      ctx->launches++;
+      return L2HMC_OK;
+    }
+  }
   const int bn8 = round_up(g.N, 128), bn4 = round_up(g.N, 64);
   const unsigned my = (unsigned)((g.M + 127) / 128);
   // Measured on B200 (profiles/r01_vae_launches.txt): both tile widths run at 46-50% of the FMA peak per padded

@@ -1,0 +1,408 @@
+// Tensor-core GEMM of the layered engine: C = epi(A B + bias [+ R]) with fp32 inputs / outputs and fp32-level
+// accuracy from three tf32 tcgen05 MMAs per product (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation in TMEM),
+// the same split the fused kernel (kernel_tc.cuh) uses.  Same GemmArgs / epilogues as layered::sgemm_kernel.
+//
+//   Persistent CTAs (one per SM) walk 128 x BN output tiles (BN <= 256, multiple of 16), 14 warps:
+//     warps 0-3  A path: LDG fp32 rows (three k-blocks in flight in registers) -> split into tf32 hi / lo ->
+//                STS into the UMMA K-major core-matrix layout.
+//     warps 4-11 epilogue: tcgen05.ld of their 32 TMEM lanes (= 32 output rows; two warps per lane group split the
+//                columns), fused tail, stores; the accumulator is double-buffered in TMEM (2 x 256 columns) so tile
+//                i's epilogue overlaps tile i+1's MMAs.
+//     warp 12    B path: one cp.async.bulk (TMA) per k-block of the host-packed, pre-split weight image.
+//     warp 13    one thread issues the tcgen05.mma's (SS form: A and B from shared memory) and commits the stage
+//                back to the producers; owns the TMEM allocation.
+//   4-stage ring, k-block = 16 (two K=8 MMA steps x 3 products); mbarriers full_a / full_b / empty per stage and
+//   acc_full / acc_empty per accumulator buffer.
+//
+// Shared-memory operand layout (no swizzle, K-major): core matrix = 8 rows x 16 B (4 tf32) stored as 128 contiguous
+// bytes; [k-chunk][row-group][8][16 B], so LBO (K-adjacent core matrices) = rows/8 * 128 B and SBO (adjacent 8-row
+// groups) = 128 B -- the encoding verified by tools/tc_probe (profiles/r01_tc_probe.txt).
+#pragma once
+#include "layered.cuh"
+#include "tc_common.cuh"
+
+namespace l2hmc {
+namespace tcg {
+
+constexpr int GM = 128;   // rows per CTA tile
+constexpr int GBK = 16;   // k-block per pipeline stage
+constexpr int GNS = 4;    // stages
+constexpr int G_THREADS = 448;  // warps 0-3 A path, 4-11 epilogue, 12 TMA (B), 13 MMA
+constexpr int W_TMA = 12, W_MMA = 13;
+
+// Host-packed B: for n-block nb and k-block kb, a contiguous image [hi|lo][GBK/4][BN/8][8 rows][4 floats].
+struct TcGemmB {
+  const float *pk;
+  int BN;    // columns per n-block (multiple of 16, <= 256)
+  int nblk;  // n-blocks
+  int nkb;   // k-blocks (K padded to a multiple of 16 with zero rows)
+};
+
+__host__ __device__ inline size_t b_block_floats(int BN) { return (size_t)2 * GBK * BN; }
+__host__ __device__ inline size_t stage_bytes(int BN) { return (size_t)2 * GM * GBK * 4 + b_block_floats(BN) * 4; }
+__host__ __device__ inline size_t tc_gemm_smem(int BN) { return GNS * stage_bytes(BN) + 1024 + 256; }
+
+// D[tmem] (+)= A[smem] * B[smem]^T, one K=8 slice; issued by ONE thread.
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ void wait_spin(uint64_t *bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = tc::smem_u32(bar);
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+
+// log(1 + e) for e in [0, 1]: e * p9(e), Chebyshev fit of log1p(e)/e (max relative error 1.8e-7 in fp32 Horner form)
+__device__ __forceinline__ float log1p_unit(float e) {
+  float p = -3.176057013e-03f;
+  p = fmaf(p, e, 1.954252645e-02f);
+  p = fmaf(p, e, -5.637361109e-02f);
+  p = fmaf(p, e, 1.054362357e-01f);
+  p = fmaf(p, e, -1.526966691e-01f);
+  p = fmaf(p, e, 1.966327429e-01f);
+  p = fmaf(p, e, -2.495161593e-01f);
+  p = fmaf(p, e, 3.332971036e-01f);
+  p = fmaf(p, e, -4.999989271e-01f);
+  p = fmaf(p, e, 1.0f);
+  return p * e;
+}
+
+// The fused layer tails (same meaning as in layered::sgemm_kernel); v already carries the bias.
+template <int EPI>
+__device__ __forceinline__ float epi_apply(float v, float aux, float scale) {
+  if (EPI == layered::EPI_RELU) return fmaxf(v + aux, 0.f);                              // aux: + enc(aux) row term
+  if (EPI == layered::EPI_SOFTPLUS) return fmaxf(v, 0.f) + log1p_unit(expf(-fabsf(v)));   // tf.nn.softplus
+  if (EPI == layered::EPI_DSOFTPLUS) return v * (1.f - expf(-aux));                       // aux: stored softplus output
+  if (EPI == layered::EPI_ADD_SCALE) return (v + aux) * scale;                            // aux: z
+  return v;
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::GemmArgs g, const TcGemmB tb) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte aligned base (descriptors address in 16-byte units; keep stages well aligned)
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = tb.BN;
+  const size_t SB = stage_bytes(BN);
+  const uint32_t A_HALF = GM * GBK * 4;        // bytes of one A image (hi or lo)
+  const uint32_t B_HALF = (uint32_t)BN * GBK * 4;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GNS * SB);
+  uint64_t *full_a = bars, *full_b = bars + GNS, *empty = bars + 2 * GNS, *acc_full = bars + 3 * GNS,
+           *acc_empty = bars + 3 * GNS + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * GNS + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = tb.nkb, nblk = tb.nblk;
+  const long long mblocks = (g.M + GM - 1) / GM;
+  const long long tiles = mblocks * nblk;
+  // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; n-block fastest so neighbouring CTAs share A rows in L2
+  const long long my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < GNS; ++s) {
+      tc::mbar_init(&full_a[s], 4);
+      tc::mbar_init(&full_b[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], 8);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == W_MMA) tc::tmem_alloc(tmem_slot, 512);  // two 256-column accumulators
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- A path: LDG (3 k-blocks in flight) -> tf32 hi / lo -> UMMA layout ----------------
+    // element i of this thread: idx = i*128 + tid -> r8 = idx & 7, kc = (idx >> 3) & 3, mg = idx >> 5
+    int mrow[4], kofs[4];
+    uint32_t sofs[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int idx = i * 128 + tid;
+      const int r8 = idx & 7, kc = (idx >> 3) & 3, mg = idx >> 5;
+      mrow[i] = mg * 8 + r8;
+      kofs[i] = kc * 4;
+      sofs[i] = (uint32_t)((kc * (GM / 8) + mg) * 128 + r8 * 16);
+    }
+    const long long total = my_tiles * nkb;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    auto load_blk = [&](long long flat, float4(&dst)[4]) {
+      if (flat >= total) return;
+      const long long ti = flat / nkb;
+      const int kb = (int)(flat - ti * nkb);
+      const long long mb = (blockIdx.x + ti * gridDim.x) / nblk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const long long m = mb * GM + mrow[i];
+        const int k = kb * GBK + kofs[i];
+        dst[i] = (m < g.M && k < g.K) ? __ldg(reinterpret_cast<const float4 *>(g.A + m * (long long)g.lda + k)) : z4;
+      }
+    };
+    auto put_blk = [&](long long flat, const float4(&src)[4]) {
+      const int s = (int)(flat % GNS);
+      const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
+      wait_spin(&empty[s], ph ^ 1u);
+      uint8_t *st = smem + s * SB;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 hi, lo;
+        hi.x = tc::tf32_rna(src[i].x); lo.x = tc::tf32_rna(src[i].x - hi.x);
+        hi.y = tc::tf32_rna(src[i].y); lo.y = tc::tf32_rna(src[i].y - hi.y);
+        hi.z = tc::tf32_rna(src[i].z); lo.z = tc::tf32_rna(src[i].z - hi.z);
+        hi.w = tc::tf32_rna(src[i].w); lo.w = tc::tf32_rna(src[i].w - hi.w);
+        *reinterpret_cast<float4 *>(st + sofs[i]) = hi;
+        *reinterpret_cast<float4 *>(st + A_HALF + sofs[i]) = lo;
+      }
+      tc::fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&full_a[s]);
+    };
+    float4 b0[4], b1[4], b2[4];
+    load_blk(0, b0);
+    load_blk(1, b1);
+    load_blk(2, b2);
+    for (long long flat = 0; flat < total; flat += 3) {
+      put_blk(flat, b0);
+      load_blk(flat + 3, b0);
+      if (flat + 1 < total) {
+        put_blk(flat + 1, b1);
+        load_blk(flat + 4, b1);
+      }
+      if (flat + 2 < total) {
+        put_blk(flat + 2, b2);
+        load_blk(flat + 5, b2);
+      }
+    }
+  } else if (warp < 12) {
+    // ---------------- epilogue warps: thread = output row; two warps per TMEM lane group split the columns ----------
+    const int ew = (warp - 4) & 3;   // TMEM lane group = warp % 4
+    const int half = (warp - 4) >> 2;
+    const int chunks = BN / 16, c_lo = half ? (chunks + 1) / 2 : 0, c_hi = half ? chunks : (chunks + 1) / 2;
+    for (long long ti = 0; ti < my_tiles; ++ti) {
+      const long long tile = blockIdx.x + ti * gridDim.x;
+      const long long mb = tile / nblk;
+      const int nb = (int)(tile - mb * nblk);
+      const int n0 = nb * BN;
+      const int buf = (int)(ti & 1);
+      wait_spin(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+      tc::tcgen05_fence_after();
+      const long long m = mb * GM + ew * 32 + lane;
+      const bool mok = m < g.M;
+      const float *bias = (EPI == layered::EPI_RELU && g.dir != nullptr && mok && g.dir[m] == 0) ? g.bias_b : g.bias;
+      const uint32_t trow = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(32 * ew) << 16);
+      for (int ch = c_lo; ch < c_hi; ++ch) {
+        const int c = ch * 16;
+        float acc[16];
+        tc::tmem_ld16(trow + (uint32_t)c, acc);
+        tc::tmem_wait_ld();
+        const int nbase = n0 + c;
+        if (!mok || nbase >= g.N) continue;
+        float *Cp = g.C + m * (long long)g.ldc + nbase;
+        const bool full = nbase + 15 < g.N;
+        if (full && g.vec) {
+          // fast path: whole 16-column chunk inside N, 16-byte aligned rows
+          float aux[16];
+          if (EPI == layered::EPI_DSOFTPLUS) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = *reinterpret_cast<const float4 *>(Cp + 4 * q);
+              aux[4 * q] = t.x; aux[4 * q + 1] = t.y; aux[4 * q + 2] = t.z; aux[4 * q + 3] = t.w;
+            }
+          } else if (EPI == layered::EPI_ADD_SCALE || (EPI == layered::EPI_RELU && g.R != nullptr)) {
+            const float *Rp = g.R + m * (long long)g.ldr + nbase;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) aux[j] = Rp[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) aux[j] = 0.f;
+          }
+          if (EPI != layered::EPI_DSOFTPLUS && EPI != layered::EPI_ADD_SCALE && bias != nullptr) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + nbase + 4 * q));
+              acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[j] = epi_apply<EPI>(acc[j], aux[j], g.scale);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<float4 *>(Cp + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int nn = nbase + j;
+            if (nn < g.N) {
+              float v = acc[j], a = 0.f;
+              if (EPI == layered::EPI_DSOFTPLUS) a = Cp[j];
+              else if (EPI == layered::EPI_ADD_SCALE || (EPI == layered::EPI_RELU && g.R != nullptr)) a = g.R[m * (long long)g.ldr + nn];
+              if (EPI != layered::EPI_DSOFTPLUS && EPI != layered::EPI_ADD_SCALE && bias != nullptr) v += bias[nn];
+              Cp[j] = epi_apply<EPI>(v, a, g.scale);
+            }
+          }
+        }
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+    }
+  } else if (warp == W_TMA) {
+    // ---------------- B path (TMA bulk copies of the packed weight image) ----------------
+    if (lane == 0) {
+      const uint32_t bytes = 2 * B_HALF;
+      long long flat = 0;
+      for (long long ti = 0; ti < my_tiles; ++ti) {
+        const long long tile = blockIdx.x + ti * gridDim.x;
+        const int nb = (int)(tile % nblk);
+        const float *src = tb.pk + ((size_t)nb * nkb) * b_block_floats(BN);
+        for (int kb = 0; kb < nkb; ++kb, ++flat) {
+          const int s = (int)(flat % GNS);
+          const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
+          wait_spin(&empty[s], ph ^ 1u);
+          tc::mbar_arrive_expect_tx(&full_b[s], bytes);
+          tc::bulk_g2s(smem + s * SB + 2 * A_HALF, src + (size_t)kb * b_block_floats(BN), bytes, &full_b[s]);
+        }
+      }
+    }
+  } else {
+    // ---------------- MMA issuer ----------------
+    if (lane == 0) {
+      const uint32_t idesc = tc::make_idesc_tf32(GM, BN);
+      const uint32_t lbo_a = (GM / 8) * 128, lbo_b = (uint32_t)(BN / 8) * 128;
+      long long flat = 0;
+      for (long long ti = 0; ti < my_tiles; ++ti) {
+        const int buf = (int)(ti & 1);
+        wait_spin(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+        tc::tcgen05_fence_after();
+        const uint32_t dacc = tmem_base + (uint32_t)(buf * 256);
+        for (int kb = 0; kb < nkb; ++kb, ++flat) {
+          const int s = (int)(flat % GNS);
+          const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
+          wait_spin(&full_a[s], ph);
+          wait_spin(&full_b[s], ph);
+          tc::tcgen05_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + s * SB), sb = sa + 2 * A_HALF;
+#pragma unroll
+          for (int ks = 0; ks < GBK / 8; ++ks) {
+            const uint64_t a_hi = tc::make_smem_desc(sa + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t a_lo = tc::make_smem_desc(sa + A_HALF + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t b_hi = tc::make_smem_desc(sb + ks * 2 * lbo_b, lbo_b, 128);
+            const uint64_t b_lo = tc::make_smem_desc(sb + B_HALF + ks * 2 * lbo_b, lbo_b, 128);
+            mma_tf32_ss(dacc, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first
+            mma_tf32_ss(dacc, a_hi, b_lo, idesc, true);
+            mma_tf32_ss(dacc, a_hi, b_hi, idesc, true);
+          }
+          tc::tcgen05_commit(&empty[s]);
+        }
+        tc::tcgen05_commit(&acc_full[buf]);
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc::tcgen05_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// Launch helper: picks the epilogue instantiation; grid = min(tiles, SMs).
+inline cudaError_t launch_tc_gemm(const layered::GemmArgs &g, const TcGemmB &tb, int sms, cudaStream_t s) {
+  const size_t smem = tc_gemm_smem(tb.BN);
+  const long long tiles = (long long)tb.nblk * ((g.M + GM - 1) / GM);
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  cudaError_t e = cudaSuccess;
+#define L2HMC_TCG_LAUNCH(E)                                                                                              \
+  case E: {                                                                                                              \
+    static thread_local size_t configured = 0;                                                                           \
+    if (smem > configured) {                                                                                             \
+      e = cudaFuncSetAttribute(tc_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+      if (e != cudaSuccess) return e;                                                                                    \
+      configured = smem;                                                                                                 \
+    }                                                                                                                    \
+    tc_gemm_kernel<E><<<grid, G_THREADS, smem, s>>>(g, tb);                                                              \
+  } break;
+  switch (g.epi) {
+    L2HMC_TCG_LAUNCH(layered::EPI_BIAS)
+    L2HMC_TCG_LAUNCH(layered::EPI_RELU)
+    L2HMC_TCG_LAUNCH(layered::EPI_SOFTPLUS)
+    L2HMC_TCG_LAUNCH(layered::EPI_DSOFTPLUS)
+    L2HMC_TCG_LAUNCH(layered::EPI_ADD_SCALE)
+    default: return cudaErrorInvalidValue;
+  }
+#undef L2HMC_TCG_LAUNCH
+  return cudaGetLastError();
+}
+
+// ---- host side: pre-split, pre-tiled weight image ---------------------------------------------------------------
+inline float tf32_rna_h(float x) {  // cvt.rna.tf32.f32: round to nearest, ties away from zero
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7F800000u) == 0x7F800000u) return x;
+  u += 0x1000u;
+  u &= 0xFFFFE000u;
+  float r;
+  memcpy(&r, &u, 4);
+  return r;
+}
+
+inline void choose_bn(int N, int *BN, int *nblk) {
+  int nb = (N + 255) / 256;
+  int bn = ((N + nb - 1) / nb + 15) / 16 * 16;
+  *BN = bn;
+  *nblk = nb;
+}
+
+// B [K][ldb] row-major (columns [0, N)) -> packed image; returns floats written. K rows beyond `K` are zero.
+inline size_t pack_b(const float *B, int ldb, int K, int N, std::vector<float> &out, TcGemmB *desc) {
+  int BN, nblk;
+  choose_bn(N, &BN, &nblk);
+  const int nkb = (K + GBK - 1) / GBK;
+  const size_t blk = b_block_floats(BN);
+  const size_t base = out.size();
+  out.resize(base + (size_t)nblk * nkb * blk, 0.f);
+  float *o = out.data() + base;
+  for (int nb = 0; nb < nblk; ++nb)
+    for (int kb = 0; kb < nkb; ++kb) {
+      float *hi = o + ((size_t)nb * nkb + kb) * blk, *lo = hi + (size_t)GBK * BN;
+      for (int kc = 0; kc < GBK / 4; ++kc)
+        for (int ng = 0; ng < BN / 8; ++ng)
+          for (int r = 0; r < 8; ++r)
+            for (int e = 0; e < 4; ++e) {
+              const int n = nb * BN + ng * 8 + r, k = kb * GBK + kc * 4 + e;
+              const float w = (n < N && k < K) ? B[(size_t)k * ldb + n] : 0.f;
+              const float h = tf32_rna_h(w);
+              const size_t idx = ((size_t)(kc * (BN / 8) + ng) * 8 + r) * 4 + e;
+              hi[idx] = h;
+              lo[idx] = tf32_rna_h(w - h);
+            }
+    }
+  desc->pk = nullptr;  // caller sets the device pointer
+  desc->BN = BN;
+  desc->nblk = nblk;
+  desc->nkb = nkb;
+  return out.size() - base;
+}
+
+}  // namespace tcg
+}  // namespace l2hmc

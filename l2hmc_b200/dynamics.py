@@ -32,7 +32,7 @@ TORCH_FLOAT = torch.float32
 NP_FLOAT = np.float32
 
 _KERNELS = {"auto": _lib.KERNEL_AUTO, "tile": _lib.KERNEL_TILE, "small": _lib.KERNEL_SMALL, "tc": _lib.KERNEL_TC,
-            "layered": _lib.KERNEL_LAYERED}
+            "layered": _lib.KERNEL_LAYERED, "layered_fma": _lib.KERNEL_LAYERED_FMA}
 
 
 def _fptr(a: np.ndarray):

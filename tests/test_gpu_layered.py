@@ -39,9 +39,24 @@ def _check(rep):
 def test_vae_target_matches_oracle(name, n):
     P = U.VaeProblem(**U.VAE_CONFIGS[name])
     dyn = P.product()
+    assert dyn.kernel_name.startswith("layered")
+    rep, _ = U.parity_report(P, n, dyn=dyn)
+    _check(rep)
+
+
+@pytest.mark.parametrize("name,n", [("c5_vae_mini", 200), ("c5_vae_ragged", 131), ("c5_vae_full", 64)])
+def test_vae_target_on_fma_gemms(name, n):
+    """kernel='layered_fma': the same engine with the fp32-FMA GEMMs instead of the tcgen05 3xTF32 ones."""
+    P = U.VaeProblem(**U.VAE_CONFIGS[name])
+    dyn = P.product(kernel="layered_fma")
     assert dyn.kernel_name == "layered_fma"
     rep, _ = U.parity_report(P, n, dyn=dyn)
     _check(rep)
+
+
+def test_default_layered_gemms_are_tensor_core():
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
+    assert P.product().kernel_name == "layered_tc3xtf32"
 
 
 def test_vae_log_jac_mode():
@@ -134,7 +149,7 @@ def test_layered_engine_on_closed_form_targets(name, n, regime):
     """kernel='layered' forces the batched engine on shapes the fused kernels also cover."""
     P = U.Problem(regime=regime, **U.CONFIGS[name])
     dyn = P.product(kernel="layered")
-    assert dyn.kernel_name == "layered_fma"
+    assert dyn.kernel_name.startswith("layered")
     rep, _ = U.parity_report(P, n, dyn=dyn)
     _check(rep)
 
@@ -150,7 +165,7 @@ def test_shapes_beyond_the_fused_kernels(D, H):
     """x_dim > 64 or width > 128: AUTO must route to the layered engine (the fused kernels reject these)."""
     P = U.Problem(kind="gaussian", D=D, H=H, T=5, eps=0.05, regime="stress")
     dyn = P.product()
-    assert dyn.kernel_name == "layered_fma"
+    assert dyn.kernel_name.startswith("layered")
     rep, _ = U.parity_report(P, 150, dyn=dyn)
     _check(rep)
     with pytest.raises(Exception):
