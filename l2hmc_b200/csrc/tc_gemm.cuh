@@ -67,6 +67,8 @@ __device__ __forceinline__ void wait_spin(uint64_t *bar, uint32_t parity) {
   }
 }
 
+__device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
 // log(1 + e) for e in [0, 1]: e * p9(e), Chebyshev fit of log1p(e)/e (max relative error 1.8e-7 in fp32 Horner form)
 __device__ __forceinline__ float log1p_unit(float e) {
   float p = -3.176057013e-03f;
@@ -166,10 +168,13 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         float4 hi, lo;
-        hi.x = tc::tf32_rna(src[i].x); lo.x = tc::tf32_rna(src[i].x - hi.x);
-        hi.y = tc::tf32_rna(src[i].y); lo.y = tc::tf32_rna(src[i].y - hi.y);
-        hi.z = tc::tf32_rna(src[i].z); lo.z = tc::tf32_rna(src[i].z - hi.z);
-        hi.w = tc::tf32_rna(src[i].w); lo.w = tc::tf32_rna(src[i].w - hi.w);
+        // hi = a with the 13 low mantissa bits cleared (what the tf32 datapath keeps), lo = a - hi exactly; the MMA
+        // reads lo's top 19 bits.  Two instructions per element: cvt.rna.tf32 lowers to ~7 (ncu: the A path, not the
+        // tensor pipe, bounded the first version), and the dropped terms stay <= 2^-20 |a b|.
+        hi.x = trunc_tf32(src[i].x); lo.x = src[i].x - hi.x;
+        hi.y = trunc_tf32(src[i].y); lo.y = src[i].y - hi.y;
+        hi.z = trunc_tf32(src[i].z); lo.z = src[i].z - hi.z;
+        hi.w = trunc_tf32(src[i].w); lo.w = src[i].w - hi.w;
         *reinterpret_cast<float4 *>(st + sofs[i]) = hi;
         *reinterpret_cast<float4 *>(st + A_HALF + sofs[i]) = lo;
       }
