@@ -2,33 +2,37 @@
 // accuracy from three tf32 tcgen05 MMAs per product (a_lo b_hi + a_hi b_lo + a_hi b_hi, fp32 accumulation in TMEM),
 // the same split the fused kernel (kernel_tc.cuh) uses.  Same GemmArgs / epilogues as layered::sgemm_kernel.
 //
-//   Persistent CTAs (one per SM) walk 128 x BN output tiles (BN <= 256, multiple of 16), 14 warps:
-//     warps 0-3  A path: LDG fp32 rows (three k-blocks in flight in registers) -> split into tf32 hi / lo ->
-//                STS into the UMMA K-major core-matrix layout.
-//     warps 4-11 epilogue: tcgen05.ld of their 32 TMEM lanes (= 32 output rows; two warps per lane group split the
-//                columns), fused tail, stores; the accumulator is double-buffered in TMEM (2 x 256 columns) so tile
-//                i's epilogue overlaps tile i+1's MMAs.
-//     warp 12    B path: one cp.async.bulk (TMA) per k-block of the host-packed, pre-split weight image.
-//     warp 13    one thread issues the tcgen05.mma's (SS form: A and B from shared memory) and commits the stage
-//                back to the producers; owns the TMEM allocation.
-//   4-stage ring, k-block = 16 (two K=8 MMA steps x 3 products); mbarriers full_a / full_b / empty per stage and
-//   acc_full / acc_empty per accumulator buffer.
+//   Persistent CTAs (one per SM) walk 256 x BN output tiles (BN <= 256, multiple of 16) as two 128-row halves that
+//   share every B stage, so the weight stream per flop -- the first version's limit: 40 KB of L2->SM traffic per 768
+//   tensor cycles -- is halved.  18 warps:
+//     warps 0-7   A path: LDG fp32 rows (three k-blocks in flight in registers) -> tf32 hi / lo -> STS into the UMMA
+//                 K-major core-matrix layout.
+//     warps 8-15  epilogue: warp e reads the 32 TMEM lanes (e % 4) of accumulator (e / 4) = 32 output rows, applies
+//                 the fused layer tail and stores.
+//     warp 16     B path: one cp.async.bulk (TMA) per k-block of the host-packed, pre-split weight image.
+//     warp 17     one thread issues the tcgen05.mma's (SS form: A and B from shared memory) and commits each stage back
+//                 to the producers; owns the TMEM allocation (2 accumulators x 256 columns).
+//   3-stage ring of 64 KB, k-block = 16 (two K=8 MMA steps x 3 products x 2 row halves); mbarriers full_a / full_b /
+//   empty per stage and acc_full / acc_empty for the accumulators.
 //
 // Shared-memory operand layout (no swizzle, K-major): core matrix = 8 rows x 16 B (4 tf32) stored as 128 contiguous
 // bytes; [k-chunk][row-group][8][16 B], so LBO (K-adjacent core matrices) = rows/8 * 128 B and SBO (adjacent 8-row
 // groups) = 128 B -- the encoding verified by tools/tc_probe (profiles/r01_tc_probe.txt).
 #pragma once
+#include <vector>
+
 #include "layered.cuh"
 #include "tc_common.cuh"
 
 namespace l2hmc {
 namespace tcg {
 
-constexpr int GM = 128;   // rows per CTA tile
-constexpr int GBK = 16;   // k-block per pipeline stage
-constexpr int GNS = 4;    // stages
-constexpr int G_THREADS = 448;  // warps 0-3 A path, 4-11 epilogue, 12 TMA (B), 13 MMA
-constexpr int W_TMA = 12, W_MMA = 13;
+constexpr int GM = 128;        // rows per MMA (one accumulator)
+constexpr int GROWS = 2 * GM;  // rows per CTA tile
+constexpr int GBK = 16;        // k-block per pipeline stage
+constexpr int GNS = 3;         // stages
+constexpr int G_THREADS = 576; // warps 0-7 A path, 8-15 epilogue, 16 TMA (B), 17 MMA
+constexpr int W_TMA = 16, W_MMA = 17;
 
 // Host-packed B: for n-block nb and k-block kb, a contiguous image [hi|lo][GBK/4][BN/8][8 rows][4 floats].
 struct TcGemmB {
@@ -39,7 +43,7 @@ struct TcGemmB {
 };
 
 __host__ __device__ inline size_t b_block_floats(int BN) { return (size_t)2 * GBK * BN; }
-__host__ __device__ inline size_t stage_bytes(int BN) { return (size_t)2 * GM * GBK * 4 + b_block_floats(BN) * 4; }
+__host__ __device__ inline size_t stage_bytes(int BN) { return (size_t)2 * GROWS * GBK * 4 + b_block_floats(BN) * 4; }
 __host__ __device__ inline size_t tc_gemm_smem(int BN) { return GNS * stage_bytes(BN) + 1024 + 256; }
 
 // D[tmem] (+)= A[smem] * B[smem]^T, one K=8 slice; issued by ONE thread.
@@ -101,50 +105,49 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const int BN = tb.BN;
   const size_t SB = stage_bytes(BN);
-  const uint32_t A_HALF = GM * GBK * 4;        // bytes of one A image (hi or lo)
+  const uint32_t A_IMG = GM * GBK * 4;   // bytes of one A image (128 rows, hi or lo); stage: [A0hi|A0lo|A1hi|A1lo|Bhi|Blo]
+  const uint32_t A_ALL = 4 * A_IMG;
   const uint32_t B_HALF = (uint32_t)BN * GBK * 4;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + GNS * SB);
   uint64_t *full_a = bars, *full_b = bars + GNS, *empty = bars + 2 * GNS, *acc_full = bars + 3 * GNS,
-           *acc_empty = bars + 3 * GNS + 2;
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * GNS + 4);
+           *acc_empty = bars + 3 * GNS + 1;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * GNS + 2);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nkb = tb.nkb, nblk = tb.nblk;
-  const long long mblocks = (g.M + GM - 1) / GM;
+  const long long mblocks = (g.M + GROWS - 1) / GROWS;
   const long long tiles = mblocks * nblk;
   // persistent CTA: tiles blockIdx.x, blockIdx.x + gridDim.x, ... ; n-block fastest so neighbouring CTAs share A rows in L2
   const long long my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
   if (tid == 0) {
     for (int s = 0; s < GNS; ++s) {
-      tc::mbar_init(&full_a[s], 4);
+      tc::mbar_init(&full_a[s], 8);
       tc::mbar_init(&full_b[s], 1);
       tc::mbar_init(&empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      tc::mbar_init(&acc_full[b], 1);
-      tc::mbar_init(&acc_empty[b], 8);
-    }
+    tc::mbar_init(acc_full, 1);
+    tc::mbar_init(acc_empty, 8);
     tc::fence_mbar_init();
   }
-  if (warp == W_MMA) tc::tmem_alloc(tmem_slot, 512);  // two 256-column accumulators
+  if (warp == W_MMA) tc::tmem_alloc(tmem_slot, 512);  // two 256-column accumulators (row halves of the tile)
   tc::tcgen05_fence_before();
   __syncthreads();
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ---------------- A path: LDG (3 k-blocks in flight) -> tf32 hi / lo -> UMMA layout ----------------
-    // element i of this thread: idx = i*128 + tid -> r8 = idx & 7, kc = (idx >> 3) & 3, mg = idx >> 5
+    // element i of this thread: idx = i*256 + tid -> r8 = idx & 7, kc = (idx >> 3) & 3, mg = idx >> 5 (0..31)
     int mrow[4], kofs[4];
     uint32_t sofs[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const int idx = i * 128 + tid;
+      const int idx = i * 256 + tid;
       const int r8 = idx & 7, kc = (idx >> 3) & 3, mg = idx >> 5;
       mrow[i] = mg * 8 + r8;
       kofs[i] = kc * 4;
-      sofs[i] = (uint32_t)((kc * (GM / 8) + mg) * 128 + r8 * 16);
+      sofs[i] = (uint32_t)((mg >> 4) * 2 * A_IMG + (kc * (GM / 8) + (mg & 15)) * 128 + r8 * 16);
     }
     const long long total = my_tiles * nkb;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -155,7 +158,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
       const long long mb = (blockIdx.x + ti * gridDim.x) / nblk;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const long long m = mb * GM + mrow[i];
+        const long long m = mb * GROWS + mrow[i];
         const int k = kb * GBK + kofs[i];
         dst[i] = (m < g.M && k < g.K) ? __ldg(reinterpret_cast<const float4 *>(g.A + m * (long long)g.lda + k)) : z4;
       }
@@ -167,16 +170,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
       uint8_t *st = smem + s * SB;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        float4 hi, lo;
         // hi = a with the 13 low mantissa bits cleared (what the tf32 datapath keeps), lo = a - hi exactly; the MMA
         // reads lo's top 19 bits.  Two instructions per element: cvt.rna.tf32 lowers to ~7 (ncu: the A path, not the
         // tensor pipe, bounded the first version), and the dropped terms stay <= 2^-20 |a b|.
+        float4 hi, lo;
         hi.x = trunc_tf32(src[i].x); lo.x = src[i].x - hi.x;
         hi.y = trunc_tf32(src[i].y); lo.y = src[i].y - hi.y;
         hi.z = trunc_tf32(src[i].z); lo.z = src[i].z - hi.z;
         hi.w = trunc_tf32(src[i].w); lo.w = src[i].w - hi.w;
         *reinterpret_cast<float4 *>(st + sofs[i]) = hi;
-        *reinterpret_cast<float4 *>(st + A_HALF + sofs[i]) = lo;
+        *reinterpret_cast<float4 *>(st + A_IMG + sofs[i]) = lo;
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
@@ -198,25 +201,22 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
         load_blk(flat + 5, b2);
       }
     }
-  } else if (warp < 12) {
-    // ---------------- epilogue warps: thread = output row; two warps per TMEM lane group split the columns ----------
-    const int ew = (warp - 4) & 3;   // TMEM lane group = warp % 4
-    const int half = (warp - 4) >> 2;
-    const int chunks = BN / 16, c_lo = half ? (chunks + 1) / 2 : 0, c_hi = half ? chunks : (chunks + 1) / 2;
+  } else if (warp < 16) {
+    // ---------------- epilogue warps: thread = output row of accumulator (e / 4), TMEM lane group (e % 4) ----------
+    const int e = warp - 8;
+    const int lg = e & 3, half = e >> 2;
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long tile = blockIdx.x + ti * gridDim.x;
       const long long mb = tile / nblk;
       const int nb = (int)(tile - mb * nblk);
       const int n0 = nb * BN;
-      const int buf = (int)(ti & 1);
-      wait_spin(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+      wait_spin(acc_full, (uint32_t)ti & 1u);
       tc::tcgen05_fence_after();
-      const long long m = mb * GM + ew * 32 + lane;
+      const long long m = mb * GROWS + half * GM + lg * 32 + lane;
       const bool mok = m < g.M;
       const float *bias = (EPI == layered::EPI_RELU && g.dir != nullptr && mok && g.dir[m] == 0) ? g.bias_b : g.bias;
-      const uint32_t trow = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(32 * ew) << 16);
-      for (int ch = c_lo; ch < c_hi; ++ch) {
-        const int c = ch * 16;
+      const uint32_t trow = tmem_base + (uint32_t)(half * 256) + ((uint32_t)(32 * lg) << 16);
+      for (int c = 0; c < BN; c += 16) {
         float acc[16];
         tc::tmem_ld16(trow + (uint32_t)c, acc);
         tc::tmem_wait_ld();
@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
       }
       tc::tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+      if (lane == 0) tc::mbar_arrive(acc_empty);
     }
   } else if (warp == W_TMA) {
     // ---------------- B path (TMA bulk copies of the packed weight image) ----------------
@@ -285,7 +285,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
           const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
           wait_spin(&empty[s], ph ^ 1u);
           tc::mbar_arrive_expect_tx(&full_b[s], bytes);
-          tc::bulk_g2s(smem + s * SB + 2 * A_HALF, src + (size_t)kb * b_block_floats(BN), bytes, &full_b[s]);
+          tc::bulk_g2s(smem + s * SB + A_ALL, src + (size_t)kb * b_block_floats(BN), bytes, &full_b[s]);
         }
       }
     }
@@ -296,30 +296,33 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
       const uint32_t lbo_a = (GM / 8) * 128, lbo_b = (uint32_t)(BN / 8) * 128;
       long long flat = 0;
       for (long long ti = 0; ti < my_tiles; ++ti) {
-        const int buf = (int)(ti & 1);
-        wait_spin(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+        wait_spin(acc_empty, ((uint32_t)ti & 1u) ^ 1u);
         tc::tcgen05_fence_after();
-        const uint32_t dacc = tmem_base + (uint32_t)(buf * 256);
         for (int kb = 0; kb < nkb; ++kb, ++flat) {
           const int s = (int)(flat % GNS);
           const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
           wait_spin(&full_a[s], ph);
           wait_spin(&full_b[s], ph);
           tc::tcgen05_fence_after();
-          const uint32_t sa = tc::smem_u32(smem + s * SB), sb = sa + 2 * A_HALF;
+          const uint32_t sa = tc::smem_u32(smem + s * SB), sb = sa + A_ALL;
 #pragma unroll
-          for (int ks = 0; ks < GBK / 8; ++ks) {
-            const uint64_t a_hi = tc::make_smem_desc(sa + ks * 2 * lbo_a, lbo_a, 128);
-            const uint64_t a_lo = tc::make_smem_desc(sa + A_HALF + ks * 2 * lbo_a, lbo_a, 128);
-            const uint64_t b_hi = tc::make_smem_desc(sb + ks * 2 * lbo_b, lbo_b, 128);
-            const uint64_t b_lo = tc::make_smem_desc(sb + B_HALF + ks * 2 * lbo_b, lbo_b, 128);
-            mma_tf32_ss(dacc, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first
-            mma_tf32_ss(dacc, a_hi, b_lo, idesc, true);
-            mma_tf32_ss(dacc, a_hi, b_hi, idesc, true);
+          for (int h = 0; h < 2; ++h) {
+            const uint32_t dacc = tmem_base + (uint32_t)(h * 256);
+            const uint32_t sah = sa + h * 2 * A_IMG;
+#pragma unroll
+            for (int ks = 0; ks < GBK / 8; ++ks) {
+              const uint64_t a_hi = tc::make_smem_desc(sah + ks * 2 * lbo_a, lbo_a, 128);
+              const uint64_t a_lo = tc::make_smem_desc(sah + A_IMG + ks * 2 * lbo_a, lbo_a, 128);
+              const uint64_t b_hi = tc::make_smem_desc(sb + ks * 2 * lbo_b, lbo_b, 128);
+              const uint64_t b_lo = tc::make_smem_desc(sb + B_HALF + ks * 2 * lbo_b, lbo_b, 128);
+              mma_tf32_ss(dacc, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first
+              mma_tf32_ss(dacc, a_hi, b_lo, idesc, true);
+              mma_tf32_ss(dacc, a_hi, b_hi, idesc, true);
+            }
           }
           tc::tcgen05_commit(&empty[s]);
         }
-        tc::tcgen05_commit(&acc_full[buf]);
+        tc::tcgen05_commit(acc_full);
       }
     }
   }
@@ -334,7 +337,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
 // Launch helper: picks the epilogue instantiation; grid = min(tiles, SMs).
 inline cudaError_t launch_tc_gemm(const layered::GemmArgs &g, const TcGemmB &tb, int sms, cudaStream_t s) {
   const size_t smem = tc_gemm_smem(tb.BN);
-  const long long tiles = (long long)tb.nblk * ((g.M + GM - 1) / GM);
+  const long long tiles = (long long)tb.nblk * ((g.M + GROWS - 1) / GROWS);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
   cudaError_t e = cudaSuccess;
 #define L2HMC_TCG_LAUNCH(E)                                                                                              \
