@@ -215,9 +215,6 @@ def main():
         gathered = torch.empty((n_total, D), dtype=torch.float32, device=dev)
         for _ in range(2):
             all_gather_chains(x, n_total, out=gathered)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -225,6 +222,11 @@ def main():
     dyn.timing_enable(True)
     launches0 = dyn.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # all ranks enter the timed region together (rank 0 alone starts the clock sampler above: without this barrier
+    # the other ranks' timed all-gather would sit waiting for it)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     t_wall0 = time.time()
     e0.record()
