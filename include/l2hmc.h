@@ -185,6 +185,15 @@ int l2hmc_accept(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset, const float *x
 int l2hmc_philox_fill(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset, uint64_t seed, uint64_t counter,
                       float *v, uint8_t *dir, float *u, void *stream);
 
+/* ---- diagnostics on a device-resident sample trace -----------------------------------------
+ * acl_spectrum(X, scale) = [autocovariance(X / scale, tau) for tau in range(n_lags)]  (utils/func_utils.py:45-54,
+ * 114-116; the notebook calls it with n_lags = n_steps - 1, SCGExperiment.ipynb:331-334), where
+ * autocovariance(X, tau) = mean_t( sum_{chain, dim} X[t] * X[t + tau] / n ).  trace: DEVICE fp32 [n_steps, n, x_dim]
+ * (the samples of consecutive transitions, never copied to the host); out: DEVICE fp64 [n_lags]; products and sums
+ * are fp64 here (the reference's numpy keeps float32 products and per-step sums; the two agree to fp32 rounding).  ESS (utils/func_utils.py:118-120) is a 2-line reduction of `out`. */
+int l2hmc_acl_spectrum(l2hmc_ctx *ctx, int64_t n_steps, int64_t n, const float *trace, double scale, int64_t n_lags,
+                       double *out, void *stream);
+
 /* ---- introspection ------------------------------------------------------------------------- */
 const char *l2hmc_kernel_name(const l2hmc_ctx *ctx); /* kernel the next l2hmc_transition will launch */
 int64_t l2hmc_launch_count(const l2hmc_ctx *ctx);    /* kernels launched by this context so far      */

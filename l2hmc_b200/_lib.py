@@ -119,6 +119,7 @@ EXPORTS = [
     ("l2hmc_net_apply", C.c_int, [_vp, C.c_int, _i64, _vp, _vp, _f32, _vp, _vp, _vp, _vp]),
     ("l2hmc_accept", C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     ("l2hmc_philox_fill", C.c_int, [_vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
+    ("l2hmc_acl_spectrum", C.c_int, [_vp, _i64, _i64, _vp, C.c_double, _i64, _vp, _vp]),
     ("l2hmc_kernel_name", C.c_char_p, [_vp]),
     ("l2hmc_launch_count", _i64, [_vp]),
     ("l2hmc_timing_enable", C.c_int, [_vp, C.c_int]),

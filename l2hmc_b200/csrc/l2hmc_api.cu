@@ -96,7 +96,7 @@ struct l2hmc_ctx {
   size_t hdir_n = 0, hacc_n = 0;
   cudaStream_t hstream = nullptr;
   LayeredCtx lay;
-  DevBuf haux;
+  DevBuf haux, diag;
 };
 
 static thread_local std::string g_err;
@@ -487,7 +487,7 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   {
     LayeredCtx &L = ctx->lay;
     DevBuf *lb[] = {&L.net_buf[0], &L.net_buf[1], &L.dec.buf, &L.enc.buf, &L.x, &L.v, &L.x0, &L.ab, &L.hd, &L.hA, &L.hB,
-                    &L.vec, &L.eaux, &L.auxp, &L.tbias, &ctx->haux};
+                    &L.vec, &L.eaux, &L.auxp, &L.tbias, &ctx->haux, &ctx->diag};
     for (DevBuf *b : lb)
       if (b->p) cudaFree(b->p);
     for (DevBuf &b : L.dact)
@@ -1125,6 +1125,67 @@ extern "C" int l2hmc_philox_fill(l2hmc_ctx *ctx, int64_t n, int64_t chain_offset
   k_philox_fill<<<GRID(n), 0, (cudaStream_t)stream>>>(ctx->sh.D, n, chain_offset, seed, counter, v, dir, u);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
+  return L2HMC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// diagnostics on the device-resident sample trace (utils/func_utils.py:45-54,114-120)
+// ---------------------------------------------------------------------------------------------
+// part[tau][c] = sum_{t < S - tau} sum_{e in chunk c} X[t, e] * X[t + tau, e], products and sums in fp64 (the
+// reference's numpy keeps float32 products and per-step sums; the results agree to fp32 rounding).  Fixed reduction order: deterministic.
+__global__ void k_autocov_partial(const float *X, long long S, long long E, long long chunk, int nchunks, double *part) {
+  const long long tau = blockIdx.x;
+  const int c = blockIdx.y;
+  const long long e0 = c * chunk, e1 = (e0 + chunk < E) ? e0 + chunk : E;
+  double s = 0.0;
+  for (long long t = 0; t + tau < S; ++t) {
+    const float *a = X + t * E, *b = X + (t + tau) * E;
+    for (long long e = e0 + threadIdx.x; e < e1; e += blockDim.x) s += (double)a[e] * (double)b[e];
+  }
+  __shared__ double sh[256];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) part[tau * nchunks + c] = sh[0];
+}
+// out[tau] = autocovariance(X / scale, tau) = (sum / n) / (S - tau) / scale^2
+__global__ void k_autocov_final(const double *part, int nchunks, long long S, long long n, double scale, long long L, double *out) {
+  const long long tau = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (tau >= L) return;
+  double s = 0.0;
+  for (int c = 0; c < nchunks; ++c) s += part[tau * nchunks + c];
+  out[tau] = s / (double)n / (double)(S - tau) / (scale * scale);
+}
+
+extern "C" int l2hmc_acl_spectrum(l2hmc_ctx *ctx, int64_t n_steps, int64_t n, const float *trace, double scale,
+                                  int64_t n_lags, double *out, void *stream) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_acl_spectrum: null context");
+  if (n_steps < 1 || n < 1 || !trace || !out) return fail(ctx, L2HMC_EINVAL, "l2hmc_acl_spectrum: bad argument");
+  if (n_lags < 1 || n_lags > n_steps) return fail(ctx, L2HMC_EINVAL, "l2hmc_acl_spectrum: need 1 <= n_lags <= n_steps");
+  if (!(scale > 0.0)) return fail(ctx, L2HMC_EINVAL, "l2hmc_acl_spectrum: scale must be > 0");
+  if (n_lags > 2147483647LL) return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_acl_spectrum: too many lags");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  const long long E = n * (long long)ctx->sh.D;
+  // enough chunks to fill the GPU when there are few lags, at least 4096 elements per chunk
+  long long nch = (148LL * 8 + n_lags - 1) / n_lags;
+  const long long max_ch = (E + 4095) / 4096;
+  if (nch > max_ch) nch = max_ch;
+  if (nch < 1) nch = 1;
+  if (nch > 65535) nch = 65535;
+  const long long chunk = (E + nch - 1) / nch;
+  const size_t need = (size_t)n_lags * (size_t)nch * 2;  // doubles held in a float buffer
+  int rc = ensure(ctx, ctx->diag, need);
+  if (rc) return rc;
+  double *part = reinterpret_cast<double *>(ctx->diag.p);
+  cudaStream_t s = (cudaStream_t)stream;
+  k_autocov_partial<<<dim3((unsigned)n_lags, (unsigned)nch), 256, 0, s>>>(trace, n_steps, E, chunk, (int)nch, part);
+  CUDA_TRY(ctx, cudaGetLastError());
+  k_autocov_final<<<(unsigned)((n_lags + 127) / 128), 128, 0, s>>>(part, (int)nch, n_steps, n, scale, n_lags, out);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches += 2;
   return L2HMC_OK;
 }
 

@@ -570,3 +570,31 @@ def make_masks(rng, T, D):
     for t in range(T):
         m[t, rng.permutation(D)[: int(D / 2)]] = 1.0
     return m
+
+
+# --------------------------------------------------------------------------------------
+# Diagnostics (utils/func_utils.py:45-54,114-120), numpy like the reference
+# --------------------------------------------------------------------------------------
+def autocovariance(X, tau=0):
+    """utils/func_utils.py:45-54: mean over t of sum(X[t] * X[t+tau]) / N."""
+    dT, dN, dX = np.shape(X)
+    s = 0.
+    for t in range(dT - tau):
+        s += np.sum(X[t, :, :] * X[t + tau, :, :]) / dN
+    return s / (dT - tau)
+
+
+def acl_spectrum(X, scale):
+    """utils/func_utils.py:114-116.  The samples are float32 (sess.run output) and the scale a float64 scalar; under the
+    numpy of the reference's time a scalar does not upcast an array, so X / scale -- and every product and per-step sum
+    in autocovariance -- is float32 (only the running total over t is a python float).  Written out explicitly here
+    because NumPy >= 2 would promote to float64."""
+    n = X.shape[0]
+    Xs = (np.asarray(X, dtype=np.float32) / np.float32(scale)).astype(np.float32)
+    return np.array([autocovariance(Xs, tau=t) for t in range(n - 1)])
+
+
+def ESS(A):
+    """utils/func_utils.py:118-120."""
+    A = A * (A > 0.05)
+    return 1. / (1. + 2 * np.sum(A[1:]))

@@ -181,3 +181,45 @@ def test_vae_golden_fixture():
     assert U.max_rel(rk["Lx"], gold["Lx"]) <= 4e-5
     assert U.max_rel(rk["Lv"], gold["Lv"]) <= 4e-5
     assert np.max(np.abs(rk["px"] - gold["px"])) <= P_TOL
+
+
+# ---- device-side diagnostics (utils/func_utils.py:45-54,114-120) ------------------------------------------------
+def test_acl_spectrum_and_ess_match_the_numpy_reference():
+    from l2hmc_b200 import diagnostics as G
+    rng = np.random.default_rng(3)
+    for S, N, Dd in ((50, 37, 2), (33, 300, 50), (8, 5000, 7)):
+        X = rng.standard_normal((S, N, Dd)).astype(np.float32).cumsum(0).astype(np.float32) * 0.1
+        scale = float(np.sqrt(Dd) * 1.7)
+        ref = U.O.acl_spectrum(X, scale)
+        got = G.acl_spectrum(torch.as_tensor(X).cuda(), scale).cpu().numpy()
+        assert got.shape == ref.shape
+        # the reference's numpy keeps float32 products / per-step sums; the device sums in fp64
+        assert np.max(np.abs(got - ref)) <= 2e-6 * max(1.0, np.abs(ref).max())
+        assert abs(G.ESS(got) - U.O.ESS(ref)) <= 1e-5
+        assert abs(G.autocovariance(torch.as_tensor(X).cuda(), 3) - U.O.autocovariance(X, 3)) <= 2e-6 * abs(U.O.autocovariance(X, 3))
+    part = G.acl_spectrum(torch.as_tensor(X).cuda(), scale, n_lags=3).cpu().numpy()
+    assert np.allclose(part, ref[:3], rtol=0, atol=2e-6)
+
+
+def test_sample_trace_is_the_notebook_loop_on_device():
+    """sample_trace == repeated propose(do_mh_step=True) (SCGExperiment.ipynb:291-298), and the L2HMC / HMC ESS comparison
+    of the notebook (:331-334,388) runs end to end on the device."""
+    from l2hmc_b200 import diagnostics as G, propose
+    P = U.Problem(regime="init", **U.CONFIGS["c1_scg2"])
+    dyn = P.product(seed=5)
+    x0 = torch.as_tensor(P.x0(200, np.random.default_rng(1))).cuda()
+    c0 = dyn._counter
+    tr = G.sample_trace(x0, dyn, 6)
+    dyn._counter = c0
+    cur = x0
+    for t in range(6):
+        _, _, _, out = propose(cur, dyn, do_mh_step=True)
+        cur = out[0]
+        np.testing.assert_array_equal(tr[t].cpu().numpy(), cur.cpu().numpy())
+    # the notebook's evaluation, shortened: spectra normalised by sqrt(trace(cov)), ESS of both samplers
+    scale = float(np.sqrt(np.trace(U.scg2_cov())))
+    A = G.acl_spectrum(G.sample_trace(x0, dyn, 300), scale)
+    H = U.Problem(kind="gaussian", D=2, T=10, eps=0.15, hmc=True).product(seed=6)
+    B = G.acl_spectrum(G.sample_trace(x0, H, 300), scale)
+    assert A.shape == (299,) and 0.5 < float(A[0]) < 2.0 and 0.5 < float(B[0]) < 2.0
+    assert 0.0 < G.ESS(A) <= 1.0 and 0.0 < G.ESS(B) <= 1.0

@@ -237,3 +237,22 @@ def test_vae_selected_direction_equals_blend():
     Lx, Lv, px = U.O.propose_selected(U.t64(d["x"]), dyn, direction=torch.as_tensor(d["dir"]), v=U.t64(v_sel),
                                       ae_x=ae, ae_v=ae)
     assert np.allclose(Lx.numpy(), ref["Lx"], atol=1e-12) and np.allclose(px.numpy(), ref["px"], atol=1e-12)
+
+
+# ---- diagnostics (utils/func_utils.py:45-54,114-120) ---------------------------------------------------------
+def test_diagnostics_on_a_known_process():
+    """AR(1) chains x_t = a x_{t-1} + sqrt(1-a^2) n_t have autocovariance d * a^tau per chain; ESS follows."""
+    rng = np.random.default_rng(0)
+    S, N, Dd, a = 400, 3000, 2, 0.8
+    X = np.empty((S, N, Dd))
+    X[0] = rng.standard_normal((N, Dd))
+    for t in range(1, S):
+        X[t] = a * X[t - 1] + np.sqrt(1 - a * a) * rng.standard_normal((N, Dd))
+    X = X.astype(np.float32)
+    assert abs(U.O.autocovariance(X, 0) - Dd) < 0.02 and abs(U.O.autocovariance(X, 3) - Dd * a ** 3) < 0.02
+    A = U.O.acl_spectrum(X, np.sqrt(Dd))
+    assert A.shape == (S - 1,) and abs(A[0] - 1.0) < 0.01 and abs(A[5] - a ** 5) < 0.01
+    ess = U.O.ESS(A)
+    lags = np.arange(1, 60)
+    expect = 1.0 / (1.0 + 2.0 * np.sum((a ** lags)[a ** lags > 0.05]))
+    assert abs(ess - expect) / expect < 0.05
