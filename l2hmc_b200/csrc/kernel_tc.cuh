@@ -121,8 +121,11 @@ __device__ __forceinline__ void put_a4(uint32_t lane_base, int col, const float 
   float hi[4], lo[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    hi[j] = tf32_rna(a[j]);
-    lo[j] = tf32_rna(a[j] - hi[j]);
+    // hi = a with the 13 low mantissa bits cleared (what the tf32 datapath reads anyway), lo = a - hi exactly; the MMA
+    // keeps lo's top 19 bits.  2 instructions per element instead of 7 (cvt.rna.tf32 is FSETP + IADD + LOP3 in SASS);
+    // the dropped terms stay <= 2^-20 |a b| (the weights keep round-to-nearest hi / lo from the host).
+    hi[j] = __uint_as_float(__float_as_uint(a[j]) & 0xFFFFE000u);
+    lo[j] = a[j] - hi[j];
   }
   tmem_st4(T_AHI + lane_base + col, hi);
   tmem_st4(T_ALO + lane_base + col, lo);
