@@ -95,6 +95,7 @@ struct l2hmc_ctx {
   uint8_t *hdir = nullptr, *hacc = nullptr;
   size_t hdir_n = 0, hacc_n = 0;
   cudaStream_t hstream = nullptr;
+  cudaStream_t hstreams[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of l2hmc_transition_host
   LayeredCtx lay;
   DevBuf haux, diag;
 };
@@ -502,6 +503,8 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   if (ctx->hacc) cudaFree(ctx->hacc);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
+  for (cudaStream_t hs : ctx->hstreams)
+    if (hs) cudaStreamDestroy(hs);
   delete ctx;
 }
 
@@ -918,6 +921,63 @@ static int ensure_u8(l2hmc_ctx *ctx, uint8_t *&p, size_t &have, size_t n) {
   return L2HMC_OK;
 }
 
+// l2hmc_transition_host for one transition of a large batch: 4 chunks pipelined over 3 streams.
+static int transition_host_chunked(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
+  const size_t n = (size_t)a->n, D = (size_t)ctx->sh.D;
+  int rc;
+  for (int i = 0; i < 3; ++i)
+    if (!ctx->hstreams[i]) CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->hstreams[i], cudaStreamNonBlocking));
+  if ((rc = ensure(ctx, ctx->hx, n * D))) return rc;
+  if (a->v && (rc = ensure(ctx, ctx->hv, n * D))) return rc;
+  if (a->u && (rc = ensure(ctx, ctx->hu, n))) return rc;
+  if (a->dir && (rc = ensure_u8(ctx, ctx->hdir, ctx->hdir_n, n))) return rc;
+  if ((rc = ensure(ctx, ctx->hxo, n * D))) return rc;
+  if ((rc = ensure(ctx, ctx->hpx, n))) return rc;
+  if (a->v_out && (rc = ensure(ctx, ctx->hvo, n * D))) return rc;
+  const bool want_next = a->x_next || a->do_mh;
+  if (want_next && (rc = ensure(ctx, ctx->hxn, n * D))) return rc;
+  if (a->accepted && (rc = ensure_u8(ctx, ctx->hacc, ctx->hacc_n, n))) return rc;
+  const int NCH = 4;
+  const size_t per = ((n + NCH - 1) / NCH + 127) / 128 * 128;  // whole 128-chain tiles per chunk
+  for (int c = 0; c < NCH; ++c) {
+    const size_t lo = (size_t)c * per;
+    if (lo >= n) break;
+    const size_t m = (lo + per <= n) ? per : n - lo;
+    cudaStream_t s = ctx->hstreams[c % 3];
+    l2hmc_transition_args d = *a;
+    d.stream = s;
+    d.n = (int64_t)m;
+    d.chain_offset = a->chain_offset + (int64_t)lo;
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hx.p + lo * D, a->x + lo * D, m * D * sizeof(float), cudaMemcpyHostToDevice, s));
+    d.x = ctx->hx.p + lo * D;
+    if (a->v) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hv.p + lo * D, a->v + lo * D, m * D * sizeof(float), cudaMemcpyHostToDevice, s));
+      d.v = ctx->hv.p + lo * D;
+    }
+    if (a->u) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hu.p + lo, a->u + lo, m * sizeof(float), cudaMemcpyHostToDevice, s));
+      d.u = ctx->hu.p + lo;
+    }
+    if (a->dir) {
+      CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hdir + lo, a->dir + lo, m, cudaMemcpyHostToDevice, s));
+      d.dir = ctx->hdir + lo;
+    }
+    d.x_out = ctx->hxo.p + lo * D;
+    d.px_out = ctx->hpx.p + lo;
+    d.v_out = a->v_out ? ctx->hvo.p + lo * D : nullptr;
+    d.x_next = want_next ? ctx->hxn.p + lo * D : nullptr;
+    d.accepted = a->accepted ? ctx->hacc + lo : nullptr;
+    if ((rc = launch_transition(ctx, &d, s))) return rc;
+    if (a->x_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->x_out + lo * D, d.x_out, m * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (a->px_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->px_out + lo, d.px_out, m * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (a->v_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->v_out + lo * D, d.v_out, m * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (a->x_next) CUDA_TRY(ctx, cudaMemcpyAsync(a->x_next + lo * D, d.x_next, m * D * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (a->accepted) CUDA_TRY(ctx, cudaMemcpyAsync(a->accepted + lo, d.accepted, m, cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 3; ++i) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->hstreams[i]));
+  return L2HMC_OK;
+}
+
 extern "C" int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
   int rc = validate_transition(ctx, a, true);
   if (rc) return rc;
@@ -928,6 +988,15 @@ extern "C" int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args
   const size_t n = (size_t)a->n, D = (size_t)ctx->sh.D, K = (size_t)a->n_transitions;
   l2hmc_transition_args d = *a;
   d.stream = s;
+  {
+    // Chains are independent and Philox is keyed by the global chain id, so a large batch can be cut into chunks whose
+    // H2D copy, kernel and D2H copy run on separate streams: the copies of one chunk hide under the kernel of another.
+    // (Fused kernels only: the layered engine's workspace belongs to the context.  Single transition only: the
+    // multi-transition inputs are laid out [K][n].)
+    int kernel = 0;
+    if ((rc = resolve_kernel(ctx, &kernel))) return rc;
+    if (kernel != L2HMC_KERNEL_LAYERED && K == 1 && n >= 32768) return transition_host_chunked(ctx, a);
+  }
   if ((rc = ensure(ctx, ctx->hx, n * D))) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hx.p, a->x, n * D * sizeof(float), cudaMemcpyHostToDevice, s));
   d.x = ctx->hx.p;

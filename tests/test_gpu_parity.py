@@ -239,6 +239,27 @@ def test_transition_host_equals_device_path():
     assert np.array_equal(host["accepted"], dev["accepted"].cpu().numpy())
 
 
+@pytest.mark.parametrize("name,n", [("c2_scg50", 40000), ("c1_scg2", 33001)])
+def test_transition_host_chunk_pipeline_equals_device_path(name, n):
+    """From 32768 chains on, l2hmc_transition_host cuts the batch into chunks pipelined over streams (H2D / kernel / D2H
+    of different chunks overlap); chains are independent and Philox is keyed by the global chain id, so the result
+    must be bit-identical to one device-resident launch -- with in-kernel and with injected randomness."""
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    dyn = P.product(seed=13)
+    d = P.draws(n, seed=4)
+    x = torch.as_tensor(d["x"]).cuda()
+    dev = dyn._transition(x, dir_mode=3, do_mh=True, counter=7, chain_offset=1000)
+    host = dyn.transition_host(d["x"], counter=7, chain_offset=1000)
+    for k in ("Lx", "Lv", "px", "x_next", "accepted"):
+        assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+    v_sel = np.where(d["dir"][:, None] != 0, d["v_f"], d["v_b"]).astype(np.float32)
+    g = lambda a: torch.as_tensor(a).cuda()  # noqa: E731
+    dev = dyn._transition(x, v=g(v_sel), direction=g(d["dir"]), u=g(d["u"]), do_mh=True, counter=8)
+    host = dyn.transition_host(d["x"], v=v_sel, direction=d["dir"], u=d["u"], counter=8)
+    for k in ("Lx", "Lv", "px", "x_next", "accepted"):
+        assert np.array_equal(host[k], dev[k].cpu().numpy()), k
+
+
 def test_chain_operator_matches_oracle():
     from l2hmc_b200 import chain_operator
     P = U.Problem(regime="stress", **U.CONFIGS["c1_scg2"])
