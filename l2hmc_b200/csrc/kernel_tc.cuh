@@ -101,6 +101,7 @@ __device__ __forceinline__ void compute_bar_n() { asm volatile("bar.sync 1, %0;"
 // take issue slots from the single MMA-issuer / producer threads
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
+  const uint32_t bar_u32 = smem_u32(bar);
   while (true) {
     asm volatile(
         "{\n\t"
@@ -109,7 +110,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) 
         "selp.u32 %0, 1, 0, p;\n\t"
         "}\n"
         : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar_u32), "r"(parity)
         : "memory");
     if (done) break;
     __nanosleep(64);
@@ -132,12 +133,17 @@ __device__ __forceinline__ void put_a4(uint32_t lane_base, int col, const float 
 }
 
 // exp / tanh of the epilogue.  FAST: ex2.approx + rcp.approx (abs error ~1e-7 for the O(1) arguments here).
+__device__ __forceinline__ float ex2_approx(float x) {  // one MUFU.EX2 (exp2f adds a range check and two scalings)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float ep_exp(float x, bool fast) {
-  return fast ? exp2f(x * 1.4426950408889634f) : expf(x);
+  return fast ? ex2_approx(x * 1.4426950408889634f) : expf(x);
 }
 __device__ __forceinline__ float ep_tanh(float x, bool fast) {
   if (!fast) return tanhf(x);
-  const float t = exp2f(x * 2.8853900817779268f);  // e^{2x}
+  const float t = ex2_approx(x * 2.8853900817779268f);  // e^{2x}
   return 1.f - __fdividef(2.f, t + 1.f);
 }
 
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
         for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++n) {
           const uint32_t s = n % NSLOT;
           const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
-          mbar_wait(&S.empty[s], ((n / NSLOT) & 1u) ^ 1u);
+          mbar_wait_sleep(&S.empty[s], ((n / NSLOT) & 1u) ^ 1u);  // the producer waits 97 % of the time: do not spin on issue slots
           mbar_arrive_expect_tx(&S.full[s], bytes);
           bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
         }
