@@ -73,26 +73,11 @@ __device__ __forceinline__ void wait_spin(uint64_t *bar, uint32_t parity) {
 
 __device__ __forceinline__ float trunc_tf32(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 
-// log(1 + e) for e in [0, 1]: e * p9(e), Chebyshev fit of log1p(e)/e (max relative error 1.8e-7 in fp32 Horner form)
-__device__ __forceinline__ float log1p_unit(float e) {
-  float p = -3.176057013e-03f;
-  p = fmaf(p, e, 1.954252645e-02f);
-  p = fmaf(p, e, -5.637361109e-02f);
-  p = fmaf(p, e, 1.054362357e-01f);
-  p = fmaf(p, e, -1.526966691e-01f);
-  p = fmaf(p, e, 1.966327429e-01f);
-  p = fmaf(p, e, -2.495161593e-01f);
-  p = fmaf(p, e, 3.332971036e-01f);
-  p = fmaf(p, e, -4.999989271e-01f);
-  p = fmaf(p, e, 1.0f);
-  return p * e;
-}
-
 // The fused layer tails (same meaning as in layered::sgemm_kernel); v already carries the bias.
 template <int EPI>
 __device__ __forceinline__ float epi_apply(float v, float aux, float scale) {
   if (EPI == layered::EPI_RELU) return fmaxf(v + aux, 0.f);                              // aux: + enc(aux) row term
-  if (EPI == layered::EPI_SOFTPLUS) return fmaxf(v, 0.f) + log1p_unit(expf(-fabsf(v)));   // tf.nn.softplus
+  if (EPI == layered::EPI_SOFTPLUS) return fmaxf(v, 0.f) + layered::log1p_unit(expf(-fabsf(v)));   // tf.nn.softplus
   if (EPI == layered::EPI_DSOFTPLUS) return v * (1.f - expf(-aux));                       // aux: stored softplus output
   if (EPI == layered::EPI_ADD_SCALE) return (v + aux) * scale;                            // aux: z
   return v;
