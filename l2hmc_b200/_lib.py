@@ -14,13 +14,14 @@ from typing import Optional
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO_DIR = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
-LIB_PATH = os.path.join(PKG_DIR, "libl2hmc.so")
+# L2HMC_LIB: development override (kernel variants built side by side); the product library is in-tree
+LIB_PATH = os.environ.get("L2HMC_LIB") or os.path.join(PKG_DIR, "libl2hmc.so")
 SOURCES = ["l2hmc_api.cu"]
 HEADERS = ["common.cuh", "kernel_tile.cuh", "kernel_tc.cuh", "kernel_small.cuh", "layered.cuh", "layered_host.cuh", "tc_gemm.cuh",
            os.path.join("..", "..", "include", "l2hmc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"]
+              "-shared", "-Xcompiler", "-fPIC"] + os.environ.get("L2HMC_NVCC_EXTRA", "").split()
 
 
 class L2HMCLibraryError(RuntimeError):
@@ -33,18 +34,22 @@ class L2HMCError(RuntimeError):
         self.code = code
 
 
+def _src_hash() -> str:
+    """Content hash of everything the library is compiled from (mtimes do not survive a copy of the tree)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    names = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
+    for p in [os.path.join(CSRC, f) for f in names] + [os.path.join(REPO_DIR, "include", "l2hmc.h")]:
+        with open(p, "rb") as fh:
+            h.update(p.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(LIB_PATH + ".srchash"):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    for f in SOURCES + HEADERS:
-        p = os.path.join(CSRC, f)
-        if os.path.exists(p) and os.path.getmtime(p) > t:
-            return True
-    for f in os.listdir(CSRC):
-        if f.endswith((".cu", ".cuh")) and os.path.getmtime(os.path.join(CSRC, f)) > t:
-            return True
-    return False
+    with open(LIB_PATH + ".srchash") as fh:
+        return fh.read().strip() != _src_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -63,6 +68,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise L2HMCLibraryError("nvcc failed:\n%s\n%s" % (" ".join(cmd), r.stderr[-4000:]))
     if verbose:
         print(r.stderr)
+    with open(LIB_PATH + ".srchash", "w") as fh:
+        fh.write(_src_hash())
     return LIB_PATH
 
 

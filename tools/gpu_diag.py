@@ -91,9 +91,11 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--no-timing", action="store_true")
+    ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--kernel", default="auto")
     a = ap.parse_args()
     print("device:", torch.cuda.get_device_name(0), flush=True)
-    parity(a.quick, a.kernel)
+    if not a.no_parity:
+        parity(a.quick, a.kernel)
     if not a.no_timing and not a.quick:
         timing(a.kernel)
