@@ -21,7 +21,7 @@ HEADERS = ["common.cuh", "kernel_tile.cuh", "kernel_tc.cuh", "kernel_small.cuh",
            os.path.join("..", "..", "include", "l2hmc.h")]
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC"] + os.environ.get("L2HMC_NVCC_EXTRA", "").split()
+              "-shared", "-Xcompiler", "-fPIC"]
 
 
 class L2HMCLibraryError(RuntimeError):
@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise L2HMCLibraryError("nvcc not found; cannot build %s" % LIB_PATH)
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    # L2HMC_NVCC_EXTRA: development builds of kernel variants (e.g. -DL2HMC_TC_PHASE_ACCOUNTING); not part of the hash
+    cmd = [nvcc] + NVCC_FLAGS + os.environ.get("L2HMC_NVCC_EXTRA", "").split() + ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -206,7 +206,8 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
   const TcDims &td = A.td;
   const TransitionIO &io = A.io;
   const TcLay L = make_tclay(sh.DP, sh.T);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch stays on the uniform datapath)
   const int D = sh.D, DP = sh.DP;
   const long long base = (long long)blockIdx.x * MT;
   Sync S{bars, bars + MAX_SLOT, bars + 2 * MAX_SLOT, bars + 2 * MAX_SLOT + 1};
@@ -227,76 +228,95 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = tmem_slot;
+  if (tmem != 0u) __trap();  // this CTA owns all 512 columns: the issuer uses column / lane 0 as a constant
 
   if (warp == W_TMA) {
     // ===================== TMA producer =====================
-    // one ring slot = up to KSLOT consecutive K=8 steps of one GEMM (contiguous in the weight stream)
-    if (lane == 0) {
-      uint32_t n = 0;
-      walk_schedule(A, [&](int kind, int net) {
-        const GemmDesc g = gemm_desc(A, kind, net);
-        for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++n) {
-          const uint32_t s = n % NSLOT;
-          const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
-          mbar_wait_sleep(&S.empty[s], ((n / NSLOT) & 1u) ^ 1u);  // the producer waits 97 % of the time: do not spin on issue slots
+    // one ring slot = up to KSLOT consecutive K=8 steps of one GEMM (contiguous in the weight stream).
+    // The whole warp walks the schedule with warp-uniform values (kernel parameters and loop counters only), so
+    // ptxas keeps the addresses in uniform registers; elect.sync picks the lane that issues the copy.
+    uint32_t s = 0, ph = 1;  // slot and the parity of the `empty` phase to wait for
+    walk_schedule(A, [&](int kind, int net) {
+      const GemmDesc g = gemm_desc(A, kind, net);
+      for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
+        const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
+        mbar_wait_sleep(&S.empty[s], ph);  // the producer waits 97 % of the time: do not spin on issue slots
+        if (elect_one()) {
           mbar_arrive_expect_tx(&S.full[s], bytes);
           bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
         }
-      });
-    }
+        __syncwarp();
+        if (++s == NSLOT) { s = 0; ph ^= 1u; }
+      }
+    });
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
-    // The whole warp walks the schedule (warp-uniform control flow and addresses, so the operands of
-    // tcgen05.mma live in uniform registers); only the elected lane issues the MMAs and commits.
+    // The whole warp walks the schedule; every operand of tcgen05.mma is computed from kernel parameters and loop
+    // counters (never from the thread index or a shared-memory load), so the descriptors stay in uniform registers
+    // and the MMAs of a slot issue back to back (SASS: UTCHMMA x6, UTCBAR) -- with a `lane == 0` leader ptxas
+    // wrapped every MMA in an ELECT loop fed by R2UR moves and the issue, not the tensor pipe, set the pace
+    // (113 cycles per 128x112x8 MMA against 56 of tensor work, profiles/r02_tc_issue.txt).
+    // The TMEM base of a 512-column allocation is column 0 / lane 0 (checked below), so it is a constant here.
     {
-      const bool leader = (lane == 0);
-      uint32_t n = 0, gi = 0;
-      const uint32_t ring_u32 = __shfl_sync(0xffffffffu, smem_u32(ring), 0);
-      const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+      uint32_t s = 0, ph = 0, gi = 0;
+      const uint32_t ring_u32 = smem_u32(ring);
+      const uint32_t slot_bytes = SLOT_FLOATS * 4u;
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
       long long w_a = 0, w_f = 0;
       const long long t_begin = clock64();
+#endif
       walk_schedule(A, [&](int kind, int net) {
         const GemmDesc g = gemm_desc(A, kind, net);
         const uint32_t idesc = make_idesc_tf32(128, g.n);
         // descriptor of a slab at shared address 0; the start-address field (bits 0-13, 16-byte units) is added per slab
         const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
         const uint32_t slab16 = (uint32_t)g.n * 2u;  // one slab (n x 8 floats) in 16-byte units
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
         long long t0 = clock64();
+#endif
         mbar_wait(S.a_ready, gi & 1u);
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
         w_a += clock64() - t0;
+#endif
         tcgen05_fence_after();
-        for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++n) {
-          const uint32_t s = n % NSLOT;
+        for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
           t0 = clock64();
-          mbar_wait(&S.full[s], (n / NSLOT) & 1u);
+#endif
+          mbar_wait(&S.full[s], ph);
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
           w_f += clock64() - t0;
-          const uint32_t b16 = (ring_u32 + s * SLOT_FLOATS * 4u) >> 4;
-          if (leader) {
+#endif
+          const uint32_t b16 = (ring_u32 + s * slot_bytes) >> 4;
+          if (elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < KSLOT; ++kk) {
               if (ks + kk < g.nsteps) {
                 const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
                 const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
-                const uint32_t ahi = tmem_u + T_AHI + 8u * (ks + kk), alo = tmem_u + T_ALO + 8u * (ks + kk);
-                mma_tf32_ts(tmem_u + T_ACC, alo, dhi, idesc, (ks + kk) > 0);
-                mma_tf32_ts(tmem_u + T_ACC, ahi, dlo, idesc, true);
-                mma_tf32_ts(tmem_u + T_ACC, ahi, dhi, idesc, true);
+                const uint32_t ahi = T_AHI + 8u * (ks + kk), alo = T_ALO + 8u * (ks + kk);
+                mma_tf32_ts(T_ACC, alo, dhi, idesc, (ks + kk) > 0);
+                mma_tf32_ts(T_ACC, ahi, dlo, idesc, true);
+                mma_tf32_ts(T_ACC, ahi, dhi, idesc, true);
               }
             }
             tcgen05_commit(&S.empty[s]);
           }
           __syncwarp();
+          if (++s == NSLOT) { s = 0; ph ^= 1u; }
         }
-        if (leader) tcgen05_commit(S.acc_ready);
+        if (elect_one()) tcgen05_commit(S.acc_ready);
         __syncwarp();
         ++gi;
       });
-      if (blockIdx.x == 0 && leader) {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      if (blockIdx.x == 0 && lane == 0) {
         g_tc_dbg[0] = w_a;
         g_tc_dbg[1] = w_f;
         g_tc_dbg[2] = clock64() - t_begin;
         g_tc_dbg[5] = gi;
       }
+#endif
     }
   } else {
     // ===================== compute warps =====================
@@ -309,12 +329,18 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
     float *xs = smem + L.xs, *vs = smem + L.vs, *gs = smem + L.gs;
     int *sdir = reinterpret_cast<int *>(smem + L.sdir), *sacc = reinterpret_cast<int *>(smem + L.sacc);
     uint32_t gi = 0;  // GEMM counter (parity of a_ready / acc_ready)
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
     long long w_acc = 0;
     const long long t_begin = clock64();
+#endif
     auto wait_acc = [&]() {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
       const long long t0 = clock64();
       mbar_wait_sleep(S.acc_ready, gi & 1u);
       w_acc += clock64() - t0;
+#else
+      mbar_wait_sleep(S.acc_ready, gi & 1u);
+#endif
       ++gi;
     };
     const float eps = sh.eps, Tm = A.en.temperature;
@@ -606,10 +632,12 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
         compute_bar();
       }
     }
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
     if (blockIdx.x == 0 && tid == 0) {
       g_tc_dbg[3] = w_acc;
       g_tc_dbg[4] = clock64() - t_begin;
     }
+#endif
   }
   tcgen05_fence_before();
   __syncthreads();

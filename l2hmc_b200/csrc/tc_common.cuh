@@ -18,6 +18,19 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(r);
 }
 
+// one lane of a converged warp (elect.sync): ptxas keeps code under this predicate on the uniform datapath
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMEM ---------------------------------------------------------------------------------------------
 // Warp-collective. ncols: power of two in [32, 512]. The base address lands in *slot (shared memory).
 __device__ __forceinline__ void tmem_alloc(uint32_t *slot, uint32_t ncols) {
