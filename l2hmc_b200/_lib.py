@@ -41,7 +41,7 @@ def _src_hash() -> str:
     names = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")))
     for p in [os.path.join(CSRC, f) for f in names] + [os.path.join(REPO_DIR, "include", "l2hmc.h")]:
         with open(p, "rb") as fh:
-            h.update(p.encode() + b"\0" + fh.read())
+            h.update(os.path.basename(p).encode() + b"\0" + fh.read())  # names, not paths: the tree is copied to the GPU box
     return h.hexdigest()
 
 

@@ -22,6 +22,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
+#include <type_traits>
 
 namespace l2hmc {
 namespace tc {
@@ -51,6 +52,7 @@ struct TcNet {
   const float *b4;   // [N1]
   const float *bh;   // [N3]  (S | T | Q blocks)
   const float *es, *eq;  // [DP]
+  const float *hc;       // [DP/4][28]: pre-multiplied heads constants of the specialised kernel (kernel_tc_s.cuh)
 };
 
 struct TcArgs {
@@ -194,6 +196,98 @@ __device__ __forceinline__ GemmDesc gemm_desc(const TcArgs &A, int kind, int net
   return g;
 }
 
+// ===================== TMA producer (one warp) =====================
+// one ring slot = up to KSLOT consecutive K=8 steps of one GEMM (contiguous in the weight stream).
+// The whole warp walks the schedule with warp-uniform values (kernel parameters and loop counters only), so
+// ptxas keeps the addresses in uniform registers; elect.sync picks the lane that issues the copy.
+__device__ __forceinline__ void producer_loop(const TcArgs &A, const Sync &S, float *ring, uint32_t NSLOT, uint32_t SLOT_FLOATS) {
+  uint32_t s = 0, ph = 1;  // slot and the parity of the `empty` phase to wait for
+  walk_schedule(A, [&](int kind, int net) {
+    const GemmDesc g = gemm_desc(A, kind, net);
+    for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
+      const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
+      mbar_wait_sleep(&S.empty[s], ph);  // the producer waits 97 % of the time: do not spin on issue slots
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&S.full[s], bytes);
+        bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
+      }
+      __syncwarp();
+      if (++s == NSLOT) { s = 0; ph ^= 1u; }
+    }
+  });
+}
+
+// ===================== MMA issuer (one warp) =====================
+// The whole warp walks the schedule; every operand of tcgen05.mma is computed from kernel parameters and loop
+// counters (never from the thread index or a shared-memory load), so the descriptors stay in uniform registers
+// and the MMAs of a slot issue back to back (SASS: UTCHMMA x6, UTCBAR) -- with a `lane == 0` leader ptxas
+// wrapped every MMA in an ELECT loop fed by R2UR moves and the issue, not the tensor pipe, set the pace
+// (113 cycles per 128x112x8 MMA against 56 of tensor work, profiles/r02_tc_issue.txt).
+// The TMEM base of a 512-column allocation is column 0 / lane 0 (checked below), so it is a constant here.
+__device__ __forceinline__ void issuer_loop(const TcArgs &A, const Sync &S, float *ring, uint32_t NSLOT, uint32_t SLOT_FLOATS, int lane) {
+  {
+    uint32_t s = 0, ph = 0, gi = 0;
+    const uint32_t ring_u32 = smem_u32(ring);
+    const uint32_t slot_bytes = SLOT_FLOATS * 4u;
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+    long long w_a = 0, w_f = 0;
+    const long long t_begin = clock64();
+#endif
+    walk_schedule(A, [&](int kind, int net) {
+      const GemmDesc g = gemm_desc(A, kind, net);
+      const uint32_t idesc = make_idesc_tf32(128, g.n);
+      // descriptor of a slab at shared address 0; the start-address field (bits 0-13, 16-byte units) is added per slab
+      const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
+      const uint32_t slab16 = (uint32_t)g.n * 2u;  // one slab (n x 8 floats) in 16-byte units
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      long long t0 = clock64();
+#endif
+      mbar_wait(S.a_ready, gi & 1u);
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      w_a += clock64() - t0;
+#endif
+      tcgen05_fence_after();
+      for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+        t0 = clock64();
+#endif
+        mbar_wait(&S.full[s], ph);
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+        w_f += clock64() - t0;
+#endif
+        const uint32_t b16 = (ring_u32 + s * slot_bytes) >> 4;
+        if (elect_one()) {
+#pragma unroll
+          for (int kk = 0; kk < KSLOT; ++kk) {
+            if (ks + kk < g.nsteps) {
+              const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
+              const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
+              const uint32_t ahi = T_AHI + 8u * (ks + kk), alo = T_ALO + 8u * (ks + kk);
+              mma_tf32_ts(T_ACC, alo, dhi, idesc, (ks + kk) > 0);
+              mma_tf32_ts(T_ACC, ahi, dlo, idesc, true);
+              mma_tf32_ts(T_ACC, ahi, dhi, idesc, true);
+            }
+          }
+          tcgen05_commit(&S.empty[s]);
+        }
+        __syncwarp();
+        if (++s == NSLOT) { s = 0; ph ^= 1u; }
+      }
+      if (elect_one()) tcgen05_commit(S.acc_ready);
+      __syncwarp();
+      ++gi;
+    });
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+    if (blockIdx.x == 0 && lane == 0) {
+      g_tc_dbg[0] = w_a;
+      g_tc_dbg[1] = w_f;
+      g_tc_dbg[2] = clock64() - t_begin;
+      g_tc_dbg[5] = gi;
+    }
+#endif
+  }
+}
+
 template <int NQ, bool FAST>
 __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __grid_constant__ TcArgs A) {
   constexpr int NCT = MT * NQ;                       // compute threads
@@ -231,93 +325,9 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
   if (tmem != 0u) __trap();  // this CTA owns all 512 columns: the issuer uses column / lane 0 as a constant
 
   if (warp == W_TMA) {
-    // ===================== TMA producer =====================
-    // one ring slot = up to KSLOT consecutive K=8 steps of one GEMM (contiguous in the weight stream).
-    // The whole warp walks the schedule with warp-uniform values (kernel parameters and loop counters only), so
-    // ptxas keeps the addresses in uniform registers; elect.sync picks the lane that issues the copy.
-    uint32_t s = 0, ph = 1;  // slot and the parity of the `empty` phase to wait for
-    walk_schedule(A, [&](int kind, int net) {
-      const GemmDesc g = gemm_desc(A, kind, net);
-      for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
-        const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
-        mbar_wait_sleep(&S.empty[s], ph);  // the producer waits 97 % of the time: do not spin on issue slots
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&S.full[s], bytes);
-          bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
-        }
-        __syncwarp();
-        if (++s == NSLOT) { s = 0; ph ^= 1u; }
-      }
-    });
+    producer_loop(A, S, ring, NSLOT, SLOT_FLOATS);
   } else if (warp == W_MMA) {
-    // ===================== MMA issuer =====================
-    // The whole warp walks the schedule; every operand of tcgen05.mma is computed from kernel parameters and loop
-    // counters (never from the thread index or a shared-memory load), so the descriptors stay in uniform registers
-    // and the MMAs of a slot issue back to back (SASS: UTCHMMA x6, UTCBAR) -- with a `lane == 0` leader ptxas
-    // wrapped every MMA in an ELECT loop fed by R2UR moves and the issue, not the tensor pipe, set the pace
-    // (113 cycles per 128x112x8 MMA against 56 of tensor work, profiles/r02_tc_issue.txt).
-    // The TMEM base of a 512-column allocation is column 0 / lane 0 (checked below), so it is a constant here.
-    {
-      uint32_t s = 0, ph = 0, gi = 0;
-      const uint32_t ring_u32 = smem_u32(ring);
-      const uint32_t slot_bytes = SLOT_FLOATS * 4u;
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-      long long w_a = 0, w_f = 0;
-      const long long t_begin = clock64();
-#endif
-      walk_schedule(A, [&](int kind, int net) {
-        const GemmDesc g = gemm_desc(A, kind, net);
-        const uint32_t idesc = make_idesc_tf32(128, g.n);
-        // descriptor of a slab at shared address 0; the start-address field (bits 0-13, 16-byte units) is added per slab
-        const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
-        const uint32_t slab16 = (uint32_t)g.n * 2u;  // one slab (n x 8 floats) in 16-byte units
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-        long long t0 = clock64();
-#endif
-        mbar_wait(S.a_ready, gi & 1u);
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-        w_a += clock64() - t0;
-#endif
-        tcgen05_fence_after();
-        for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-          t0 = clock64();
-#endif
-          mbar_wait(&S.full[s], ph);
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-          w_f += clock64() - t0;
-#endif
-          const uint32_t b16 = (ring_u32 + s * slot_bytes) >> 4;
-          if (elect_one()) {
-#pragma unroll
-            for (int kk = 0; kk < KSLOT; ++kk) {
-              if (ks + kk < g.nsteps) {
-                const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
-                const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
-                const uint32_t ahi = T_AHI + 8u * (ks + kk), alo = T_ALO + 8u * (ks + kk);
-                mma_tf32_ts(T_ACC, alo, dhi, idesc, (ks + kk) > 0);
-                mma_tf32_ts(T_ACC, ahi, dlo, idesc, true);
-                mma_tf32_ts(T_ACC, ahi, dhi, idesc, true);
-              }
-            }
-            tcgen05_commit(&S.empty[s]);
-          }
-          __syncwarp();
-          if (++s == NSLOT) { s = 0; ph ^= 1u; }
-        }
-        if (elect_one()) tcgen05_commit(S.acc_ready);
-        __syncwarp();
-        ++gi;
-      });
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-      if (blockIdx.x == 0 && lane == 0) {
-        g_tc_dbg[0] = w_a;
-        g_tc_dbg[1] = w_f;
-        g_tc_dbg[2] = clock64() - t_begin;
-        g_tc_dbg[5] = gi;
-      }
-#endif
-    }
+    issuer_loop(A, S, ring, NSLOT, SLOT_FLOATS, lane);
   } else {
     // ===================== compute warps =====================
     const int c = 32 * (warp & 3) + lane;  // chain within the tile == TMEM lane

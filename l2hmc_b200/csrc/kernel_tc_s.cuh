@@ -1,0 +1,546 @@
+// Tensor-core transition kernel, shape-specialised compute path (sm_100a).
+//
+// Same launch shape, operand images, ring, producer and MMA issuer as kernel_tc.cuh (reference: utils/dynamics.py:115-201,
+// 246-309; utils/sampler.py:28-55; net SCGExperiment.ipynb:51-77); what differs is the code of the 8 compute warps, which
+// the ncu source page showed to be instruction-bound once the MMA issue had been fixed (profiles/r02_*):
+//   * chunk counts are template parameters (NQC = DP/4 dimension chunks, NHC = HK/8 hidden chunks), every loop over
+//     chunks is unrolled, so TMEM / shared / global addresses are `uniform base + immediate` (the generic kernel spent
+//     more instructions on addresses, R2UR moves and register rotation than on arithmetic);
+//   * x, v, grad U live in shared memory chain-major (row stride RS floats, conflict-free 128-bit accesses): one
+//     LDS.128 per 4 dimensions instead of 4 LDS.32;
+//   * the per-dimension constants of the heads epilogue are pre-multiplied on the host (TcNet::hc): tanh / exp of
+//     the S and Q heads run in log2 units with one reciprocal for both tanh (5 MUFU per dimension instead of 6 --
+//     MUFU is the floor of this epilogue: 16 lanes per clock per SM);
+//   * the A operand of the NEXT GEMM (net input [a | b], or x - mu for the Gaussian grad) is produced inside the
+//     heads / grad epilogue from values still in registers: no separate pass over the state;
+//   * one mbarrier arrival per warp (count 8) instead of one per thread (count 256) for a_ready.
+// Shapes without an instantiation run the generic kernel of kernel_tc.cuh.
+#pragma once
+#include "kernel_tc.cuh"
+
+namespace l2hmc {
+namespace tc {
+
+constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
+
+template <int NQC>
+struct SDims {
+  static constexpr int DP = 4 * NQC;
+  static constexpr int RS = (NQC & 1) ? DP : DP + 4;  // row stride with RS/4 odd: 8 lanes x 16 B hit 32 distinct banks
+};
+
+struct TcLayS {
+  int xs, vs, gs, smask, h0, su, sdir, sacc, part, ring;
+};
+__host__ __device__ inline TcLayS make_tclay_s(int RS, int DP, int T) {
+  TcLayS l;
+  l.xs = 0;
+  l.vs = l.xs + RS * MT;
+  l.gs = l.vs + RS * MT;
+  l.smask = l.gs + RS * MT;
+  l.h0 = l.smask + ((T * DP + 3) & ~3);
+  l.su = l.h0 + MT;
+  l.sdir = l.su + MT;
+  l.sacc = l.sdir + MT;
+  l.part = l.sacc + MT;                      // [2][2][MT]: partial Hamiltonian, partial log|J|
+  l.ring = (l.part + 2 * 2 * MT + 31) & ~31;  // 128-byte aligned
+  return l;
+}
+__host__ __device__ inline int tc_s_row_stride(int DP) { return ((DP / 4) & 1) ? DP : DP + 4; }
+__host__ __device__ inline size_t tc_s_smem_bytes(int DP, int T, int nslot, int slot_floats) {
+  return sizeof(float) * ((size_t)make_tclay_s(tc_s_row_stride(DP), DP, T).ring + (size_t)nslot * slot_floats);
+}
+
+__device__ __forceinline__ float4 lds4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+__device__ __forceinline__ void sts4(float *p, const float (&a)[4]) {
+  *reinterpret_cast<float4 *>(p) = make_float4(a[0], a[1], a[2], a[3]);
+}
+__device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// split 8 values into tf32 hi / lo (see put_a4) and store them at column `col` of this warp's TMEM lanes
+__device__ __forceinline__ void put_a8(uint32_t lane_base, int col, const float (&a)[8]) {
+  float hi[8], lo[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    hi[j] = __uint_as_float(__float_as_uint(a[j]) & 0xFFFFE000u);
+    lo[j] = a[j] - hi[j];
+  }
+  tmem_st8(T_AHI + lane_base + col, hi);
+  tmem_st8(T_ALO + lane_base + col, lo);
+}
+
+// what the heads epilogue prepares for the GEMM that follows it
+enum { NEXT_NONE = 0, NEXT_X1 = 1, NEXT_X2 = 2, NEXT_G = 3, NEXT_V = 4 };
+
+template <int NQC, int NHC, bool FAST>
+__global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const __grid_constant__ TcArgs A) {
+  constexpr int NCT = MT * 2;  // compute threads: 2 per chain
+  constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
+  constexpr int DP = SDims<NQC>::DP, RS = SDims<NQC>::RS;
+  constexpr int Q0 = (NQC + 1) / 2, H0 = (NHC + 1) / 2;  // chunks owned by the first thread of a chain
+  constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+  auto compute_bar = []() { compute_bar_n<NCT>(); };
+  extern __shared__ __align__(128) float smem[];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_SLOT + 2];
+  __shared__ uint32_t tmem_slot;
+  const Shape &sh = A.sh;
+  const TcDims &td = A.td;
+  const TransitionIO &io = A.io;
+  const TcLayS L = make_tclay_s(RS, DP, sh.T);
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler
+  const int D = sh.D;
+  const long long base = (long long)blockIdx.x * MT;
+  Sync S{bars, bars + MAX_SLOT, bars + 2 * MAX_SLOT, bars + 2 * MAX_SLOT + 1};
+  float *ring = smem + L.ring;
+  const uint32_t NSLOT = (uint32_t)td.nslot, SLOT_FLOATS = (uint32_t)td.slot_floats;
+
+  if (tid == 0) {
+    for (int s = 0; s < MAX_SLOT; ++s) {
+      mbar_init(&S.full[s], 1);
+      mbar_init(&S.empty[s], 1);
+    }
+    mbar_init(S.a_ready, NCT / 32);  // one arrival per compute warp
+    mbar_init(S.acc_ready, 1);
+    fence_mbar_init();
+  }
+  if (warp == W_MMA) tmem_alloc(&tmem_slot, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem = tmem_slot;
+  if (tmem != 0u) __trap();  // this CTA owns all 512 columns: column / lane 0 is a constant in the issuer and below
+
+  if (warp == W_TMA) {
+    producer_loop(A, S, ring, NSLOT, SLOT_FLOATS);
+  } else if (warp == W_MMA) {
+    issuer_loop(A, S, ring, NSLOT, SLOT_FLOATS, lane);
+  } else {
+    // ===================== compute warps =====================
+    const int c = 32 * (warp & 3) + lane;  // chain within the tile == TMEM lane
+    const int qd = warp >> 2;              // 0 / 1: which part of the chunks this thread owns (warp-uniform)
+    const uint32_t lb = ((uint32_t)(32 * (warp & 3))) << 16;
+    const int qb = qd ? Q0 : 0, qn = qd ? NQC - Q0 : Q0;  // 4-dim chunks [qb, qb + qn)
+    const int hb = qd ? H0 : 0, hn = qd ? NHC - H0 : H0;  // 8-column hidden chunks [hb, hb + hn)
+    const long long gch = base + c;
+    const bool gauss = A.en.kind == 0;
+    float *xr = smem + L.xs + c * RS, *vr = smem + L.vs + c * RS, *gr = smem + L.gs + c * RS;
+    int *sdir = reinterpret_cast<int *>(smem + L.sdir), *sacc = reinterpret_cast<int *>(smem + L.sacc);
+    uint32_t gi = 0;  // GEMM counter (parity of acc_ready)
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+    long long w_acc = 0;
+    const long long t_begin = clock64();
+#endif
+    auto wait_acc = [&]() {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      const long long t0 = clock64();
+      mbar_wait_sleep(S.acc_ready, gi & 1u);
+      w_acc += clock64() - t0;
+#else
+      mbar_wait_sleep(S.acc_ready, gi & 1u);
+#endif
+      ++gi;
+      tcgen05_fence_after();
+    };
+    // A operand complete: every thread's tcgen05.st has landed, one arrival per warp
+    auto a_done = [&]() {
+      tmem_wait_st();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(S.a_ready);
+    };
+    const float eps = sh.eps, Tm = A.en.temperature, rTm = 1.f / A.en.temperature;
+
+    for (int i = tid; i < sh.T * DP; i += NCT) smem[L.smask + i] = A.mask[i];
+    for (int i = tid; i < MT * DP; i += NCT) {
+      const int ch = i / DP, d = i - ch * DP;
+      const long long g = base + ch;
+      smem[L.xs + ch * RS + d] = (g < io.n && d < D) ? io.x[g * D + d] : 0.f;
+    }
+    compute_bar();
+
+    for (int tr = 0; tr < io.n_transitions; ++tr) {
+      const unsigned long long ctr = io.counter + (unsigned long long)tr;
+      // ---- setup: momentum, direction, uniform -------------------------------------------------------
+      if (io.v != nullptr) {
+        for (int i = tid; i < MT * DP; i += NCT) {
+          const int ch = i / DP, d = i - ch * DP;
+          const long long g = base + ch;
+          smem[L.vs + ch * RS + d] = (g < io.n && d < D) ? io.v[((long long)tr * io.n + g) * D + d] : 0.f;
+        }
+      } else {
+#pragma unroll 1
+        for (int i = 0; i < qn; ++i) {
+          const int q = qb + i;
+          float z[4];
+          philox_normals4(io.seed, ctr, io.chain_offset + gch, q, z);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) z[j] = (gch < io.n && 4 * q + j < D) ? z[j] : 0.f;
+          sts4(vr + 4 * q, z);
+        }
+      }
+      if (qd == 0) {
+        int pd = 1;
+        float pu = 0.f;
+        if (io.dir_mode == 3 || (io.do_mh && io.u == nullptr)) philox_dir_u(io.seed, ctr, io.chain_offset + gch, pd, pu);
+        int dbit = 1;
+        if (io.dir_mode == 1) dbit = 0;
+        else if (io.dir_mode == 2) dbit = (gch < io.n) ? (io.dir[(long long)tr * io.n + gch] != 0) : 1;
+        else if (io.dir_mode == 3) dbit = pd;
+        sdir[c] = dbit;
+        if (io.do_mh && io.u != nullptr) pu = (gch < io.n) ? io.u[(long long)tr * io.n + gch] : 0.f;
+        smem[L.su + c] = pu;
+      }
+      compute_bar();
+      const bool fwd = sdir[c] != 0;
+      const float sg = fwd ? 1.f : -1.f;
+      float ljl = 0.f;  // log|J| of this thread's dimensions, in log2 units
+
+      // ---- A operands ------------------------------------------------------------------------------------
+      // net input [a | b] of one 4-dim chunk -> columns 4q (a) and DP + 4q (b)
+      auto put_ab = [&](int q, const float (&a)[4], const float (&b)[4]) {
+        put_a4(lb, 4 * q, a);
+        put_a4(lb, DP + 4 * q, b);
+      };
+      // Gaussian grad GEMM input x - mu of one chunk (the K tail beyond DP is zeroed once per GEMM by zero_gtail)
+      auto put_xmu = [&](int q, const float (&x)[4]) {
+        const float4 mu = ldg4(A.en.mu + 4 * q);
+        const float a[4] = {x[0] - mu.x, x[1] - mu.y, x[2] - mu.z, x[3] - mu.w};
+        put_a4(lb, 4 * q, a);
+      };
+      auto zero_gtail = [&]() {  // KG = DP rounded to 8: one more 4-column chunk of zeros when NQC is odd
+        if ((NQC & 1) && qd == 1) {
+          const float z[4] = {0.f, 0.f, 0.f, 0.f};
+          put_a4(lb, DP, z);
+        }
+      };
+      // RoughWell grad U of one chunk (utils/distributions.py:90-97)
+      auto roughwell_grad = [&](int q, const float (&x)[4], float (&g)[4]) {
+        const float e = A.en.s0, den = A.en.s1;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) g[j] = (4 * q + j < D) ? (x[j] - e * sinf(x[j] / den) / den) * rTm : 0.f;
+      };
+
+      // ---- grad U at the current x (start of a transition): fills gs, prepares the V-net input ------------------
+      // partial Hamiltonian over this thread's dims, accumulated where x, v, g are in registers anyway
+      auto ham_chunk = [&](const float (&x)[4], const float (&v)[4], const float (&g)[4], int q, float &U, float &K) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          K = fmaf(v[j], v[j], K);
+          if (gauss) {
+            U = fmaf(x[j] - __ldg(A.en.mu + 4 * q + j), g[j], U);  // g carries 1/temperature
+          } else if (4 * q + j < D) {
+            U += (0.5f * x[j] * x[j] + A.en.s0 * cosf(x[j] / A.en.s1)) * rTm;
+          }
+        }
+      };
+      // Gaussian: epilogue of the grad GEMM -> gs, V-net input [x | g]; optional Hamiltonian partial
+      auto grad_epilogue = [&](bool want_h, float &Hpart) {
+        wait_acc();
+        float U = 0.f, K = 0.f;
+#pragma unroll
+        for (int i = 0; i < Q0; ++i) {
+          if (i < qn) {
+            const int q = qb + i;
+            float g4[4];
+            tmem_ld4(lb + T_ACC + 4 * q, g4);
+            const float4 xv = lds4(xr + 4 * q);
+            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) g4[j] *= rTm;
+            sts4(gr + 4 * q, g4);
+            if (want_h) {
+              const float4 vv = lds4(vr + 4 * q);
+              const float v4[4] = {vv.x, vv.y, vv.z, vv.w};
+              ham_chunk(x4, v4, g4, q, U, K);
+            }
+            put_ab(q, x4, g4);
+          }
+        }
+        a_done();
+        Hpart = (gauss ? 0.5f * U : U) + 0.5f * K;
+      };
+      // start of a transition: grad U(x), H(x, v) partial, first V-net input
+      auto first_grad = [&](float &Hpart) {
+        if (gauss) {
+#pragma unroll
+          for (int i = 0; i < Q0; ++i) {
+            if (i < qn) {
+              const int q = qb + i;
+              const float4 xv = lds4(xr + 4 * q);
+              const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+              put_xmu(q, x4);
+            }
+          }
+          zero_gtail();
+          a_done();
+          grad_epilogue(true, Hpart);
+        } else {
+          float U = 0.f, K = 0.f;
+#pragma unroll 1
+          for (int i = 0; i < qn; ++i) {
+            const int q = qb + i;
+            const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q);
+            const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
+            float g4[4];
+            roughwell_grad(q, x4, g4);
+            sts4(gr + 4 * q, g4);
+            ham_chunk(x4, v4, g4, q, U, K);
+            put_ab(q, x4, g4);
+          }
+          a_done();
+          Hpart = U + 0.5f * K;
+        }
+      };
+      // end of a transition: H(x', v') partial (g = grad U(x') is in gs: the last V-net call did not move x)
+      auto final_ham = [&]() -> float {
+        float U = 0.f, K = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < qn; ++i) {
+          const int q = qb + i;
+          const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), gv = lds4(gr + 4 * q);
+          const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w}, g4[4] = {gv.x, gv.y, gv.z, gv.w};
+          ham_chunk(x4, v4, g4, q, U, K);
+        }
+        return (gauss ? 0.5f * U : U) + 0.5f * K;
+      };
+
+      // ---- relu(acc + bias) of this thread's 8-column chunks -> next A operand (bias row may differ per lane) ----
+      auto hidden_epilogue = [&](const float *__restrict__ bias) {
+        wait_acc();
+        float h[2][8];
+        tmem_ld8(lb + T_ACC + 8 * hb, h[0]);
+#pragma unroll
+        for (int i = 0; i < H0; ++i) {
+          if (i < hn) {
+            const int q = hb + i;
+            const float4 b0 = ldg4(bias + 8 * q), b1 = ldg4(bias + 8 * q + 4);
+            tmem_wait_ld();
+            if (i + 1 < hn) tmem_ld8(lb + T_ACC + 8 * (q + 1), h[(i + 1) & 1]);
+            const float(&hh)[8] = h[i & 1];
+            const float a[8] = {fmaxf(hh[0] + b0.x, 0.f), fmaxf(hh[1] + b0.y, 0.f), fmaxf(hh[2] + b0.z, 0.f), fmaxf(hh[3] + b0.w, 0.f),
+                                fmaxf(hh[4] + b1.x, 0.f), fmaxf(hh[5] + b1.y, 0.f), fmaxf(hh[6] + b1.z, 0.f), fmaxf(hh[7] + b1.w, 0.f)};
+            put_a8(lb, 8 * q, a);
+          }
+        }
+        a_done();
+      };
+
+      // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) + next A operand --------------
+      // MODE 0: momentum half step (V net, scale 1/2 eps); MODE 1: position half step XH in {0, 1} (X net, scale eps).
+      // In log2 units: svl = cS * tanh(s + bs), fql = cQ * tanh(q + bq), with cS = e^{scale_s} * h * log2(e),
+      // cQ = e^{scale_q} * eps * log2(e), h = 1/2 eps or eps; exp(+-sv) = 2^{+-svl}; log|J| += +-svl * ln 2.
+      auto heads_epilogue = [&](auto mode_c, auto xh_c, auto next_c, const TcNet &N, const float *mrow) {
+        constexpr int MODE = decltype(mode_c)::value, XH = decltype(xh_c)::value, NEXT = decltype(next_c)::value;
+        const float hc = MODE == 0 ? 0.5f * eps : eps;
+        wait_acc();
+        float s4[2][4], t4[2][4], q4[2][4];
+        tmem_ld4(lb + T_ACC + 4 * qb, s4[0]);
+        tmem_ld4(lb + T_ACC + DP + 4 * qb, t4[0]);
+        tmem_ld4(lb + T_ACC + 2 * DP + 4 * qb, q4[0]);
+#pragma unroll
+        for (int i = 0; i < Q0; ++i) {
+          if (i < qn) {
+            const int q = qb + i;
+            const float *hcq = N.hc + HC_PER_CHUNK * q;
+            const float4 c_bs = ldg4(hcq), c_bq = ldg4(hcq + 4), c_ns = ldg4(hcq + 8), c_cs = ldg4(hcq + 12);
+            const float4 c_nq = ldg4(hcq + 16), c_cq = ldg4(hcq + 20), c_bt = ldg4(hcq + 24);
+            const float bs2[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bq2[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
+            const float n2cS[4] = {c_ns.x, c_ns.y, c_ns.z, c_ns.w}, cS[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w};
+            const float n2cQ[4] = {c_nq.x, c_nq.y, c_nq.z, c_nq.w}, cQ[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
+            const float bth[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};
+            const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q);
+            float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
+            float g4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {0.f, 0.f, 0.f, 0.f};
+            if (MODE == 0) {
+              const float4 gv = lds4(gr + 4 * q);
+              g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
+            }
+            if (MODE == 1 || NEXT == NEXT_X1) {
+              const float4 mv = lds4(mrow + 4 * q);
+              m4[0] = mv.x; m4[1] = mv.y; m4[2] = mv.z; m4[3] = mv.w;
+            }
+            tmem_wait_ld();
+            if (i + 1 < qn) {  // next chunk's accumulators travel while this chunk is processed
+              tmem_ld4(lb + T_ACC + 4 * (q + 1), s4[(i + 1) & 1]);
+              tmem_ld4(lb + T_ACC + DP + 4 * (q + 1), t4[(i + 1) & 1]);
+              tmem_ld4(lb + T_ACC + 2 * DP + 4 * (q + 1), q4[(i + 1) & 1]);
+            }
+            float uu4[4];  // MODE 1: 1 - k, the dimensions this half step moves
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float svl, fql;
+              if (FAST) {
+                // tanh(z) = 1 - 2 / (e^{2z} + 1); one reciprocal serves both heads (arguments clamped so that the
+                // product of the two denominators stays finite: tanh(19.7) == 1 in fp32)
+                const float eS = ex2_approx(fminf(fmaf(s4[i & 1][j], 2.f * L2E, bs2[j]), 57.f));
+                const float eQ = ex2_approx(fminf(fmaf(q4[i & 1][j], 2.f * L2E, bq2[j]), 57.f));
+                const float dS = eS + 1.f, dQ = eQ + 1.f;
+                const float r = rcp_approx(dS * dQ);
+                svl = fmaf(r * dQ, n2cS[j], cS[j]);
+                fql = fmaf(r * dS, n2cQ[j], cQ[j]);
+              } else {
+                svl = cS[j] * tanhf((s4[i & 1][j] * (2.f * L2E) + bs2[j]) * (0.5f * LN2));
+                fql = cQ[j] * tanhf((q4[i & 1][j] * (2.f * L2E) + bq2[j]) * (0.5f * LN2));
+              }
+              const float Tt = fmaf(t4[i & 1][j], hc, bth[j]);  // h * (t + bt)
+              const float eQx = FAST ? ex2_approx(fql) : exp2f(fql);
+              const float svs = svl * sg;                         // +- (scale * S) * log2(e)
+              const float e = FAST ? ex2_approx(svs) : exp2f(svs);
+              if (MODE == 0) {
+                // fwd: v e + h (T - e^{fq} g) ; bwd: (v - h (T - e^{fq} g)) e
+                const float tmp = fmaf(-eQx, hc * g4[j], Tt);
+                const float w = fwd ? 1.f : -e;
+                v4[j] = fmaf(v4[j], e, tmp * w);
+                ljl += svs;
+              } else {
+                const float m = m4[j];
+                const float k = (fwd == (XH == 0)) ? m : 1.f - m;
+                const float uu = 1.f - k;
+                uu4[j] = uu;
+                // fwd: x e + h (e^{fq} v + T) ; bwd: e (x - h (e^{fq} v + T))
+                const float inner = fmaf(eQx, hc * v4[j], Tt);
+                const float w = fwd ? 1.f : -e;
+                const float nx = fmaf(x4[j], e, inner * w);
+                x4[j] = k * x4[j] + uu * nx;
+                ljl = fmaf(uu, svs, ljl);
+              }
+            }
+            if (MODE == 0) sts4(vr + 4 * q, v4);
+            else sts4(xr + 4 * q, x4);
+            // ---- the A operand of the GEMM that follows ----
+            if (NEXT == NEXT_X1) {  // X net, first half: [v | k x], k = m (fwd) or 1 - m (bwd)
+              float b[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) b[j] = (fwd ? m4[j] : 1.f - m4[j]) * x4[j];
+              put_ab(q, v4, b);
+            } else if (NEXT == NEXT_X2) {  // X net, second half: its k is this half's 1 - k
+              float b[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) b[j] = uu4[j] * x4[j];
+              put_ab(q, v4, b);
+            } else if (NEXT == NEXT_G) {  // grad U at the new x
+              if (gauss) {
+                put_xmu(q, x4);
+              } else {
+                float g[4];
+                roughwell_grad(q, x4, g);
+                sts4(gr + 4 * q, g);
+                put_ab(q, x4, g);
+              }
+            } else if (NEXT == NEXT_V) {  // V net at the same x, g (first call of the next leapfrog step)
+              put_ab(q, x4, g4);
+            }
+          }
+        }
+        if (NEXT == NEXT_G && gauss) zero_gtail();
+        if (NEXT != NEXT_NONE) a_done();
+        else tcgen05_fence_before();
+      };
+
+      float hpart0 = 0.f;
+      first_grad(hpart0);
+      smem[L.part + qd * MT + c] = hpart0;
+      compute_bar();
+      if (qd == 0) smem[L.h0 + c] = smem[L.part + c] + smem[L.part + MT + c];
+
+      using I0 = std::integral_constant<int, 0>;
+      using I1 = std::integral_constant<int, 1>;
+#pragma unroll 1
+      for (int it = 0; it < sh.T; ++it) {
+        const int trow = fwd ? it : sh.T - 1 - it;  // the step index this chain is at (utils/dynamics.py:285)
+        const float *mrow = smem + L.smask + trow * DP;
+        const float *tbv = A.vnet.tb + (size_t)trow * td.N1, *tbx = A.xnet.tb + (size_t)trow * td.N1;
+        // V net, first momentum half step
+        hidden_epilogue(tbv);
+        hidden_epilogue(A.vnet.b4);
+        heads_epilogue(I0{}, I0{}, std::integral_constant<int, NEXT_X1>{}, A.vnet, mrow);
+        // X net, position half steps
+        hidden_epilogue(tbx);
+        hidden_epilogue(A.xnet.b4);
+        heads_epilogue(I1{}, I0{}, std::integral_constant<int, NEXT_X2>{}, A.xnet, mrow);
+        hidden_epilogue(tbx);
+        hidden_epilogue(A.xnet.b4);
+        heads_epilogue(I1{}, I1{}, std::integral_constant<int, NEXT_G>{}, A.xnet, mrow);
+        if (gauss) {
+          float dummy;
+          grad_epilogue(false, dummy);
+        }
+        // V net, second momentum half step
+        hidden_epilogue(tbv);
+        hidden_epilogue(A.vnet.b4);
+        if (it + 1 < sh.T) heads_epilogue(I0{}, I0{}, std::integral_constant<int, NEXT_V>{}, A.vnet, mrow);
+        else heads_epilogue(I0{}, I0{}, std::integral_constant<int, NEXT_NONE>{}, A.vnet, mrow);
+      }
+
+      // ---- log|J|, Hamiltonian, accept ---------------------------------------------------------------
+      compute_bar();  // h0 readers are done with `part`
+      smem[L.part + qd * MT + c] = final_ham();
+      smem[L.part + (2 + qd) * MT + c] = ljl * LN2;
+      compute_bar();
+      const bool last = (tr == io.n_transitions - 1);
+      if (qd == 0) {
+        const float h1 = smem[L.part + c] + smem[L.part + MT + c];
+        const float logj = smem[L.part + 2 * MT + c] + smem[L.part + 3 * MT + c];
+        const float p = accept_prob(smem[L.h0 + c], h1, logj);
+        const float px = io.log_jac ? logj : p;
+        int acc = 0;
+        if (io.do_mh) acc = (px - smem[L.su + c] >= 0.f) ? 1 : 0;
+        sacc[c] = acc;
+        if (gch < io.n && last) {
+          io.px_out[gch] = px;
+          if (io.accepted) io.accepted[gch] = (uint8_t)acc;
+        }
+      }
+      compute_bar();
+      if (last) {
+        for (int i = tid; i < MT * D; i += NCT) {
+          const int ch = i / D, d = i - ch * D;
+          const long long g = base + ch;
+          if (g < io.n) {
+            const float lx = smem[L.xs + ch * RS + d];
+            io.x_out[g * D + d] = lx;
+            if (io.v_out) io.v_out[g * D + d] = smem[L.vs + ch * RS + d];
+            // the state this transition started from: the caller's x, or the x_next written one transition ago
+            if (io.do_mh) io.x_next[g * D + d] = sacc[ch] ? lx : (tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d]);
+          }
+        }
+      } else {
+        // keep x_next in global memory between fused transitions (L2-resident, 2 x 4 D bytes per chain)
+        for (int i = tid; i < MT * D; i += NCT) {
+          const int ch = i / D, d = i - ch * D;
+          const long long g = base + ch;
+          if (g < io.n) {
+            const float prev = tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d];
+            const float nx = sacc[ch] ? smem[L.xs + ch * RS + d] : prev;
+            io.x_next[g * D + d] = nx;
+            smem[L.xs + ch * RS + d] = nx;
+          }
+        }
+        compute_bar();
+      }
+    }
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+    if (blockIdx.x == 0 && tid == 0) {
+      g_tc_dbg[3] = w_acc;
+      g_tc_dbg[4] = clock64() - t_begin;
+    }
+#endif
+    (void)Tm;
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    __syncwarp();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace tc
+}  // namespace l2hmc

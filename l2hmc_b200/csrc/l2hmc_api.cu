@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "kernel_tile.cuh"
 #include "kernel_tc.cuh"
+#include "kernel_tc_s.cuh"
 #include "kernel_small.cuh"
 #include "layered.cuh"
 #include "tc_gemm.cuh"
@@ -89,8 +90,9 @@ struct l2hmc_ctx {
   DevBuf hx, hv, hu, hxo, hvo, hpx, hxn;
   // tensor-core kernel: pre-split weight streams
   tc::TcDims td;
-  DevBuf tc_buf[2], tc_gbuf;
-  tc::TcNet tc_net[2];
+  DevBuf tc_buf[2], tc_gbuf, tc_hc[2];
+  std::vector<float> tc_head_raw[2];  // per net: bs | bt | bq | e^{scale_s} | e^{scale_q}, DP each (host copy for tc_pack_hc)
+  tc::TcNet tc_net[2] = {};
   bool tc_ok = false;  // shape / energy kind inside what kernel_tc covers
   uint8_t *hdir = nullptr, *hacc = nullptr;
   size_t hdir_n = 0, hacc_n = 0;
@@ -317,6 +319,8 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
 }
 
+static int tc_pack_hc(l2hmc_ctx *ctx, int net_id);
+
 static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
   const Shape &sh = ctx->sh;
   const tc::TcDims &td = ctx->td;
@@ -366,6 +370,44 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
   n.bh = n.b4 + nb4;
   n.es = n.bh + nbh;
   n.eq = n.es + nes;
+  std::vector<float> &raw = ctx->tc_head_raw[net_id];
+  raw.assign((size_t)5 * DP, 0.f);
+  for (int d = 0; d < D; ++d) {
+    raw[d] = p->bs[d];
+    raw[DP + d] = p->bt[d];
+    raw[2 * DP + d] = p->bq[d];
+    raw[3 * DP + d] = es[d];
+    raw[4 * DP + d] = eq[d];
+  }
+  return tc_pack_hc(ctx, net_id);
+}
+
+// Per-dimension constants of the specialised kernel's heads epilogue (kernel_tc_s.cuh), pre-multiplied so that tanh and
+// exp run in log2 units: per 4-dim chunk {bs2, bq2, n2cS, cS, n2cQ, cQ, bth} x 4 floats.  h = eps/2 for the V net
+// (momentum half steps, utils/dynamics.py:121-125) and eps for the X net (:133-145); depends on eps -> repacked by l2hmc_set_eps.
+static int tc_pack_hc(l2hmc_ctx *ctx, int net_id) {
+  const int DP = ctx->sh.DP;
+  const std::vector<float> &raw = ctx->tc_head_raw[net_id];
+  if (raw.size() != (size_t)5 * DP) return L2HMC_OK;  // net not set yet
+  const double L2E = 1.4426950408889634, eps = (double)ctx->sh.eps;
+  const double h = net_id == L2HMC_VNET ? 0.5 * eps : eps;
+  std::vector<float> hc((size_t)(DP / 4) * tc::HC_PER_CHUNK, 0.f);
+  for (int d = 0; d < ctx->sh.D; ++d) {
+    float *c = hc.data() + (size_t)(d / 4) * tc::HC_PER_CHUNK + (d & 3);
+    const double bs = raw[d], bt = raw[DP + d], bq = raw[2 * DP + d], es = raw[3 * DP + d], eq = raw[4 * DP + d];
+    const double cS = es * h * L2E, cQ = eq * eps * L2E;
+    c[0] = (float)(bs * 2.0 * L2E);
+    c[4] = (float)(bq * 2.0 * L2E);
+    c[8] = (float)(-2.0 * cS);
+    c[12] = (float)cS;
+    c[16] = (float)(-2.0 * cQ);
+    c[20] = (float)cQ;
+    c[24] = (float)(bt * h);
+  }
+  int rc = ensure(ctx, ctx->tc_hc[net_id], hc.size());
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpy(ctx->tc_hc[net_id].p, hc.data(), hc.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->tc_net[net_id].hc = ctx->tc_hc[net_id].p;
   return L2HMC_OK;
 }
 
@@ -482,7 +524,7 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   DevBuf *bufs[] = {&ctx->net_packed[0], &ctx->net_packed[1], &ctx->net_raw[0], &ctx->net_raw[1], &ctx->mask,
                     &ctx->energy_buf, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn,
-                    &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf};
+                    &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf, &ctx->tc_hc[0], &ctx->tc_hc[1]};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   {
@@ -637,6 +679,10 @@ extern "C" int l2hmc_set_eps(l2hmc_ctx *ctx, float eps) {
   if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_eps: null context");
   if (!(eps > 0.f) || !isfinite(eps)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_eps: eps must be finite and > 0");
   ctx->sh.eps = eps;
+  for (int net_id = 0; net_id < 2; ++net_id) {
+    int rc = tc_pack_hc(ctx, net_id);
+    if (rc) return rc;
+  }
   return L2HMC_OK;
 }
 
@@ -843,6 +889,35 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     TA.en = ctx->en;
     TA.mask = ctx->mask.p;
     TA.io = K.io;
+    // shape-specialised compute path (kernel_tc_s.cuh) where an instantiation exists; L2HMC_TC_GENERIC=1 forces the generic one
+    const int nqc = ctx->sh.DP / 4, nhc = ctx->td.HK / 8;
+    const char *ge = getenv("L2HMC_TC_GENERIC");
+    const bool spec = !(ge && ge[0] == '1') && ctx->td.nq == 2 && ctx->tc_net[0].hc && ctx->tc_net[1].hc &&
+                      ((nqc == 13 && nhc == 13) || (nqc == 8 && nhc == 13));
+    const unsigned blocks = (unsigned)((a->n + tc::MT - 1) / tc::MT);
+    if (spec) {
+      const long long state_bytes = (long long)tc::make_tclay_s(tc::tc_s_row_stride(ctx->sh.DP), ctx->sh.DP, ctx->sh.T).ring * 4;
+      long long ns = (232448LL - 1024 - state_bytes) / ((long long)ctx->td.slot_floats * 4);
+      TA.td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
+      if (TA.td.nslot < 4) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: shared-memory ring too small for this shape");
+      const size_t smem = tc::tc_s_smem_bytes(ctx->sh.DP, ctx->sh.T, TA.td.nslot, TA.td.slot_floats);
+      static thread_local size_t tc_s_configured = 0;
+      if (smem > tc_s_configured) {
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        tc_s_configured = smem;
+      }
+      const unsigned nthreads = (unsigned)(tc::MT * 2 + 64);
+      if (nqc == 13) {
+        if (ctx->td.fast_math) tc::tc_transition_kernel_s<13, 13, true><<<blocks, nthreads, smem, stream>>>(TA);
+        else tc::tc_transition_kernel_s<13, 13, false><<<blocks, nthreads, smem, stream>>>(TA);
+      } else {
+        if (ctx->td.fast_math) tc::tc_transition_kernel_s<8, 13, true><<<blocks, nthreads, smem, stream>>>(TA);
+        else tc::tc_transition_kernel_s<8, 13, false><<<blocks, nthreads, smem, stream>>>(TA);
+      }
+    } else {
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
     static thread_local size_t tc_configured = 0;
     if (smem > tc_configured) {
@@ -854,7 +929,6 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       tc_configured = smem;
     }
-    const unsigned blocks = (unsigned)((a->n + tc::MT - 1) / tc::MT);
     const unsigned nthreads = (unsigned)(tc::MT * ctx->td.nq + 64);
     if (ctx->td.nq == 2) {
       if (ctx->td.fast_math) tc::tc_transition_kernel<2, true><<<blocks, nthreads, smem, stream>>>(TA);
@@ -865,6 +939,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     } else {
       if (ctx->td.fast_math) tc::tc_transition_kernel<4, true><<<blocks, nthreads, smem, stream>>>(TA);
       else tc::tc_transition_kernel<4, false><<<blocks, nthreads, smem, stream>>>(TA);
+    }
     }
   } else if (kernel == L2HMC_KERNEL_SMALL) {
     small::SmallArgs SA;
