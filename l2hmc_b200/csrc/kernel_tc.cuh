@@ -166,11 +166,17 @@ __device__ __forceinline__ void walk_schedule(const TcArgs &A, F &&f) {
   for (int tr = 0; tr < A.io.n_transitions; ++tr) {
     if (gauss) f(0, 0);
     for (int it = 0; it < A.sh.T; ++it) {
-      f(1, 1); f(2, 1); f(3, 1);
-      f(1, 0); f(2, 0); f(3, 0);
-      f(1, 0); f(2, 0); f(3, 0);
-      if (gauss) f(0, 0);
-      f(1, 1); f(2, 1); f(3, 1);
+      // 13 slots per leapfrog step: V (embed, hidden, heads), X, X, grad (Gaussian only), V.  One rolled loop so that
+      // the body of f exists once: the issuer / producer code shares the instruction cache with the compute warps.
+#pragma unroll 1
+      for (int j = 0; j < 13; ++j) {
+        if (j == 9) {
+          if (gauss) f(0, 0);
+          continue;
+        }
+        const int jj = j > 9 ? j - 1 : j;  // 0..11
+        f(jj % 3 + 1, (jj < 3 || jj >= 9) ? 1 : 0);
+      }
     }
   }
 }
@@ -204,6 +210,7 @@ __device__ __forceinline__ void producer_loop(const TcArgs &A, const Sync &S, fl
   uint32_t s = 0, ph = 1;  // slot and the parity of the `empty` phase to wait for
   walk_schedule(A, [&](int kind, int net) {
     const GemmDesc g = gemm_desc(A, kind, net);
+#pragma unroll 1
     for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
       const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
       mbar_wait_sleep(&S.empty[s], ph);  // the producer waits 97 % of the time: do not spin on issue slots
@@ -247,6 +254,7 @@ __device__ __forceinline__ void issuer_loop(const TcArgs &A, const Sync &S, floa
       w_a += clock64() - t0;
 #endif
       tcgen05_fence_after();
+#pragma unroll 1
       for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
         t0 = clock64();

@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   constexpr int NCT = MT * 2;  // compute threads: 2 per chain
   constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
   constexpr int DP = SDims<NQC>::DP, RS = SDims<NQC>::RS;
-  constexpr int Q0 = (NQC + 1) / 2, H0 = (NHC + 1) / 2;  // chunks owned by the first thread of a chain
+  constexpr int Q0 = (NQC + 1) / 2, H0 = (NHC + 1) / 2;  // chunks owned by the first thread of a chain (the second owns the rest)
   constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   auto compute_bar = []() { compute_bar_n<NCT>(); };
   extern __shared__ __align__(128) float smem[];
@@ -122,6 +122,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
     issuer_loop(A, S, ring, NSLOT, SLOT_FLOATS, lane);
   } else {
     // ===================== compute warps =====================
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
     const int c = 32 * (warp & 3) + lane;  // chain within the tile == TMEM lane
     const int qd = warp >> 2;              // 0 / 1: which part of the chunks this thread owns (warp-uniform)
     const uint32_t lb = ((uint32_t)(32 * (warp & 3))) << 16;
@@ -243,9 +245,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       auto grad_epilogue = [&](bool want_h, float &Hpart) {
         wait_acc();
         float U = 0.f, K = 0.f;
-#pragma unroll
-        for (int i = 0; i < Q0; ++i) {
-          if (i < qn) {
+#pragma unroll 1
+        for (int i = 0; i < qn; ++i) {
+          {
             const int q = qb + i;
             float g4[4];
             tmem_ld4(lb + T_ACC + 4 * q, g4);
@@ -269,14 +271,12 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       // start of a transition: grad U(x), H(x, v) partial, first V-net input
       auto first_grad = [&](float &Hpart) {
         if (gauss) {
-#pragma unroll
-          for (int i = 0; i < Q0; ++i) {
-            if (i < qn) {
-              const int q = qb + i;
-              const float4 xv = lds4(xr + 4 * q);
-              const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
-              put_xmu(q, x4);
-            }
+#pragma unroll 1
+          for (int i = 0; i < qn; ++i) {
+            const int q = qb + i;
+            const float4 xv = lds4(xr + 4 * q);
+            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+            put_xmu(q, x4);
           }
           zero_gtail();
           a_done();
@@ -316,18 +316,23 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         wait_acc();
         float h[2][8];
         tmem_ld8(lb + T_ACC + 8 * hb, h[0]);
-#pragma unroll
-        for (int i = 0; i < H0; ++i) {
-          if (i < hn) {
-            const int q = hb + i;
-            const float4 b0 = ldg4(bias + 8 * q), b1 = ldg4(bias + 8 * q + 4);
-            tmem_wait_ld();
-            if (i + 1 < hn) tmem_ld8(lb + T_ACC + 8 * (q + 1), h[(i + 1) & 1]);
-            const float(&hh)[8] = h[i & 1];
-            const float a[8] = {fmaxf(hh[0] + b0.x, 0.f), fmaxf(hh[1] + b0.y, 0.f), fmaxf(hh[2] + b0.z, 0.f), fmaxf(hh[3] + b0.w, 0.f),
-                                fmaxf(hh[4] + b1.x, 0.f), fmaxf(hh[5] + b1.y, 0.f), fmaxf(hh[6] + b1.z, 0.f), fmaxf(hh[7] + b1.w, 0.f)};
-            put_a8(lb, 8 * q, a);
-          }
+        auto chunk = [&](int i, auto buf_c) {
+          constexpr int B = decltype(buf_c)::value;
+          const int q = hb + i;
+          const float4 b0 = ldg4(bias + 8 * q), b1 = ldg4(bias + 8 * q + 4);
+          tmem_wait_ld();
+          if (i + 1 < hn) tmem_ld8(lb + T_ACC + 8 * (q + 1), h[B ^ 1]);
+          const float(&hh)[8] = h[B];
+          const float a[8] = {fmaxf(hh[0] + b0.x, 0.f), fmaxf(hh[1] + b0.y, 0.f), fmaxf(hh[2] + b0.z, 0.f), fmaxf(hh[3] + b0.w, 0.f),
+                              fmaxf(hh[4] + b1.x, 0.f), fmaxf(hh[5] + b1.y, 0.f), fmaxf(hh[6] + b1.z, 0.f), fmaxf(hh[7] + b1.w, 0.f)};
+          put_a8(lb, 8 * q, a);
+        };
+        // two chunks per iteration (the register double buffer needs static names); rolled: the fully unrolled
+        // version of this kernel had a 178 KB loop body and spent 40 % of the epilogue time on instruction fetch
+#pragma unroll 1
+        for (int i = 0; i < hn; i += 2) {
+          chunk(i, I0{});
+          if (i + 1 < hn) chunk(i + 1, I1{});
         }
         a_done();
       };
@@ -336,111 +341,115 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       // MODE 0: momentum half step (V net, scale 1/2 eps); MODE 1: position half step XH in {0, 1} (X net, scale eps).
       // In log2 units: svl = cS * tanh(s + bs), fql = cQ * tanh(q + bq), with cS = e^{scale_s} * h * log2(e),
       // cQ = e^{scale_q} * eps * log2(e), h = 1/2 eps or eps; exp(+-sv) = 2^{+-svl}; log|J| += +-svl * ln 2.
-      auto heads_epilogue = [&](auto mode_c, auto xh_c, auto next_c, const TcNet &N, const float *mrow) {
-        constexpr int MODE = decltype(mode_c)::value, XH = decltype(xh_c)::value, NEXT = decltype(next_c)::value;
+      auto heads_epilogue = [&](auto mode_c, const int xh, const int next, const TcNet &N, const float *mrow) {
+        constexpr int MODE = decltype(mode_c)::value;
         const float hc = MODE == 0 ? 0.5f * eps : eps;
+        const bool flip = (fwd != (xh == 0));  // MODE 1: k = m, or 1 - m when flipped
         wait_acc();
         float s4[2][4], t4[2][4], q4[2][4];
         tmem_ld4(lb + T_ACC + 4 * qb, s4[0]);
         tmem_ld4(lb + T_ACC + DP + 4 * qb, t4[0]);
         tmem_ld4(lb + T_ACC + 2 * DP + 4 * qb, q4[0]);
+        auto chunk = [&](int i, auto buf_c) {
+          constexpr int B = decltype(buf_c)::value;
+          const int q = qb + i;
+          const float *hcq = N.hc + HC_PER_CHUNK * q;
+          const float4 c_bs = ldg4(hcq), c_bq = ldg4(hcq + 4), c_ns = ldg4(hcq + 8), c_cs = ldg4(hcq + 12);
+          const float4 c_nq = ldg4(hcq + 16), c_cq = ldg4(hcq + 20), c_bt = ldg4(hcq + 24);
+          const float bs2[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bq2[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
+          const float n2cS[4] = {c_ns.x, c_ns.y, c_ns.z, c_ns.w}, cS[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w};
+          const float n2cQ[4] = {c_nq.x, c_nq.y, c_nq.z, c_nq.w}, cQ[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
+          const float bth[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};
+          const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), mv = lds4(mrow + 4 * q);
+          float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
+          const float m4[4] = {mv.x, mv.y, mv.z, mv.w};
+          float g4[4] = {0.f, 0.f, 0.f, 0.f};
+          if (MODE == 0) {
+            const float4 gv = lds4(gr + 4 * q);
+            g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
+          }
+          tmem_wait_ld();
+          if (i + 1 < qn) {  // next chunk's accumulators travel while this chunk is processed
+            tmem_ld4(lb + T_ACC + 4 * (q + 1), s4[B ^ 1]);
+            tmem_ld4(lb + T_ACC + DP + 4 * (q + 1), t4[B ^ 1]);
+            tmem_ld4(lb + T_ACC + 2 * DP + 4 * (q + 1), q4[B ^ 1]);
+          }
+          float uu4[4];  // MODE 1: 1 - k, the dimensions this half step moves
 #pragma unroll
-        for (int i = 0; i < Q0; ++i) {
-          if (i < qn) {
-            const int q = qb + i;
-            const float *hcq = N.hc + HC_PER_CHUNK * q;
-            const float4 c_bs = ldg4(hcq), c_bq = ldg4(hcq + 4), c_ns = ldg4(hcq + 8), c_cs = ldg4(hcq + 12);
-            const float4 c_nq = ldg4(hcq + 16), c_cq = ldg4(hcq + 20), c_bt = ldg4(hcq + 24);
-            const float bs2[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bq2[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
-            const float n2cS[4] = {c_ns.x, c_ns.y, c_ns.z, c_ns.w}, cS[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w};
-            const float n2cQ[4] = {c_nq.x, c_nq.y, c_nq.z, c_nq.w}, cQ[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
-            const float bth[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};
-            const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q);
-            float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
-            float g4[4] = {0.f, 0.f, 0.f, 0.f}, m4[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int j = 0; j < 4; ++j) {
+            float svl, fql;
+            if (FAST) {
+              // tanh(z) = 1 - 2 / (e^{2z} + 1); one reciprocal serves both heads (arguments clamped so that the
+              // product of the two denominators stays finite: tanh(19.7) == 1 in fp32)
+              const float eS = ex2_approx(fminf(fmaf(s4[B][j], 2.f * L2E, bs2[j]), 57.f));
+              const float eQ = ex2_approx(fminf(fmaf(q4[B][j], 2.f * L2E, bq2[j]), 57.f));
+              const float dS = eS + 1.f, dQ = eQ + 1.f;
+              const float r = rcp_approx(dS * dQ);
+              svl = fmaf(r * dQ, n2cS[j], cS[j]);
+              fql = fmaf(r * dS, n2cQ[j], cQ[j]);
+            } else {
+              svl = cS[j] * tanhf((s4[B][j] * (2.f * L2E) + bs2[j]) * (0.5f * LN2));
+              fql = cQ[j] * tanhf((q4[B][j] * (2.f * L2E) + bq2[j]) * (0.5f * LN2));
+            }
+            const float Tt = fmaf(t4[B][j], hc, bth[j]);  // h * (t + bt)
+            const float eQx = FAST ? ex2_approx(fql) : exp2f(fql);
+            const float svs = svl * sg;                     // +- (scale * S) * log2(e)
+            const float e = FAST ? ex2_approx(svs) : exp2f(svs);
+            const float w = fwd ? 1.f : -e;
             if (MODE == 0) {
-              const float4 gv = lds4(gr + 4 * q);
-              g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
+              // fwd: v e + h (T - e^{fq} g) ; bwd: (v - h (T - e^{fq} g)) e
+              const float tmp = fmaf(-eQx, hc * g4[j], Tt);
+              v4[j] = fmaf(v4[j], e, tmp * w);
+              ljl += svs;
+            } else {
+              const float k = flip ? 1.f - m4[j] : m4[j];
+              const float uu = 1.f - k;
+              uu4[j] = uu;
+              // fwd: x e + h (e^{fq} v + T) ; bwd: e (x - h (e^{fq} v + T))
+              const float inner = fmaf(eQx, hc * v4[j], Tt);
+              const float nx = fmaf(x4[j], e, inner * w);
+              x4[j] = k * x4[j] + uu * nx;
+              ljl = fmaf(uu, svs, ljl);
             }
-            if (MODE == 1 || NEXT == NEXT_X1) {
-              const float4 mv = lds4(mrow + 4 * q);
-              m4[0] = mv.x; m4[1] = mv.y; m4[2] = mv.z; m4[3] = mv.w;
-            }
-            tmem_wait_ld();
-            if (i + 1 < qn) {  // next chunk's accumulators travel while this chunk is processed
-              tmem_ld4(lb + T_ACC + 4 * (q + 1), s4[(i + 1) & 1]);
-              tmem_ld4(lb + T_ACC + DP + 4 * (q + 1), t4[(i + 1) & 1]);
-              tmem_ld4(lb + T_ACC + 2 * DP + 4 * (q + 1), q4[(i + 1) & 1]);
-            }
-            float uu4[4];  // MODE 1: 1 - k, the dimensions this half step moves
+          }
+          // ---- the new state and the A operand of the GEMM that follows ----
+          if (MODE == 0) {
+            sts4(vr + 4 * q, v4);
+            if (next != NEXT_NONE) {
+              // NEXT_X1: X net, first half: [v | k x], k = m (fwd) or 1 - m (bwd); NEXT_V: V net again at the same [x | g]
+              const bool nx1 = next == NEXT_X1;
+              float a[4], b[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float svl, fql;
-              if (FAST) {
-                // tanh(z) = 1 - 2 / (e^{2z} + 1); one reciprocal serves both heads (arguments clamped so that the
-                // product of the two denominators stays finite: tanh(19.7) == 1 in fp32)
-                const float eS = ex2_approx(fminf(fmaf(s4[i & 1][j], 2.f * L2E, bs2[j]), 57.f));
-                const float eQ = ex2_approx(fminf(fmaf(q4[i & 1][j], 2.f * L2E, bq2[j]), 57.f));
-                const float dS = eS + 1.f, dQ = eQ + 1.f;
-                const float r = rcp_approx(dS * dQ);
-                svl = fmaf(r * dQ, n2cS[j], cS[j]);
-                fql = fmaf(r * dS, n2cQ[j], cQ[j]);
-              } else {
-                svl = cS[j] * tanhf((s4[i & 1][j] * (2.f * L2E) + bs2[j]) * (0.5f * LN2));
-                fql = cQ[j] * tanhf((q4[i & 1][j] * (2.f * L2E) + bq2[j]) * (0.5f * LN2));
+              for (int j = 0; j < 4; ++j) {
+                a[j] = nx1 ? v4[j] : x4[j];
+                b[j] = nx1 ? (fwd ? m4[j] : 1.f - m4[j]) * x4[j] : g4[j];
               }
-              const float Tt = fmaf(t4[i & 1][j], hc, bth[j]);  // h * (t + bt)
-              const float eQx = FAST ? ex2_approx(fql) : exp2f(fql);
-              const float svs = svl * sg;                         // +- (scale * S) * log2(e)
-              const float e = FAST ? ex2_approx(svs) : exp2f(svs);
-              if (MODE == 0) {
-                // fwd: v e + h (T - e^{fq} g) ; bwd: (v - h (T - e^{fq} g)) e
-                const float tmp = fmaf(-eQx, hc * g4[j], Tt);
-                const float w = fwd ? 1.f : -e;
-                v4[j] = fmaf(v4[j], e, tmp * w);
-                ljl += svs;
-              } else {
-                const float m = m4[j];
-                const float k = (fwd == (XH == 0)) ? m : 1.f - m;
-                const float uu = 1.f - k;
-                uu4[j] = uu;
-                // fwd: x e + h (e^{fq} v + T) ; bwd: e (x - h (e^{fq} v + T))
-                const float inner = fmaf(eQx, hc * v4[j], Tt);
-                const float w = fwd ? 1.f : -e;
-                const float nx = fmaf(x4[j], e, inner * w);
-                x4[j] = k * x4[j] + uu * nx;
-                ljl = fmaf(uu, svs, ljl);
-              }
+              put_ab(q, a, b);
             }
-            if (MODE == 0) sts4(vr + 4 * q, v4);
-            else sts4(xr + 4 * q, x4);
-            // ---- the A operand of the GEMM that follows ----
-            if (NEXT == NEXT_X1) {  // X net, first half: [v | k x], k = m (fwd) or 1 - m (bwd)
-              float b[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) b[j] = (fwd ? m4[j] : 1.f - m4[j]) * x4[j];
-              put_ab(q, v4, b);
-            } else if (NEXT == NEXT_X2) {  // X net, second half: its k is this half's 1 - k
+          } else {
+            sts4(xr + 4 * q, x4);
+            if (next == NEXT_X2) {  // X net, second half: its k is this half's 1 - k
               float b[4];
 #pragma unroll
               for (int j = 0; j < 4; ++j) b[j] = uu4[j] * x4[j];
               put_ab(q, v4, b);
-            } else if (NEXT == NEXT_G) {  // grad U at the new x
-              if (gauss) {
-                put_xmu(q, x4);
-              } else {
-                float g[4];
-                roughwell_grad(q, x4, g);
-                sts4(gr + 4 * q, g);
-                put_ab(q, x4, g);
-              }
-            } else if (NEXT == NEXT_V) {  // V net at the same x, g (first call of the next leapfrog step)
-              put_ab(q, x4, g4);
+            } else if (gauss) {  // NEXT_G: grad U at the new x
+              put_xmu(q, x4);
+            } else {
+              float g[4];
+              roughwell_grad(q, x4, g);
+              sts4(gr + 4 * q, g);
+              put_ab(q, x4, g);
             }
           }
+        };
+#pragma unroll 1
+        for (int i = 0; i < qn; i += 2) {
+          chunk(i, I0{});
+          if (i + 1 < qn) chunk(i + 1, I1{});
         }
-        if (NEXT == NEXT_G && gauss) zero_gtail();
-        if (NEXT != NEXT_NONE) a_done();
+        if (MODE == 1 && next == NEXT_G && gauss) zero_gtail();
+        if (next != NEXT_NONE) a_done();
         else tcgen05_fence_before();
       };
 
@@ -450,33 +459,28 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       compute_bar();
       if (qd == 0) smem[L.h0 + c] = smem[L.part + c] + smem[L.part + MT + c];
 
-      using I0 = std::integral_constant<int, 0>;
-      using I1 = std::integral_constant<int, 1>;
 #pragma unroll 1
       for (int it = 0; it < sh.T; ++it) {
         const int trow = fwd ? it : sh.T - 1 - it;  // the step index this chain is at (utils/dynamics.py:285)
         const float *mrow = smem + L.smask + trow * DP;
-        const float *tbv = A.vnet.tb + (size_t)trow * td.N1, *tbx = A.xnet.tb + (size_t)trow * td.N1;
-        // V net, first momentum half step
-        hidden_epilogue(tbv);
-        hidden_epilogue(A.vnet.b4);
-        heads_epilogue(I0{}, I0{}, std::integral_constant<int, NEXT_X1>{}, A.vnet, mrow);
-        // X net, position half steps
-        hidden_epilogue(tbx);
-        hidden_epilogue(A.xnet.b4);
-        heads_epilogue(I1{}, I0{}, std::integral_constant<int, NEXT_X2>{}, A.xnet, mrow);
-        hidden_epilogue(tbx);
-        hidden_epilogue(A.xnet.b4);
-        heads_epilogue(I1{}, I1{}, std::integral_constant<int, NEXT_G>{}, A.xnet, mrow);
-        if (gauss) {
-          float dummy;
-          grad_epilogue(false, dummy);
+        // four net calls per leapfrog step: V (momentum half step), X, X (position half steps), V
+#pragma unroll 1
+        for (int ni = 0; ni < 4; ++ni) {
+          const bool isv = (ni == 0 || ni == 3);
+          const TcNet &N = isv ? A.vnet : A.xnet;
+          const float *tb = N.tb + (size_t)trow * td.N1;
+#pragma unroll 1
+          for (int l = 0; l < 2; ++l) hidden_epilogue(l == 0 ? tb : N.b4);
+          if (isv) {
+            heads_epilogue(I0{}, 0, ni == 0 ? NEXT_X1 : (it + 1 < sh.T ? NEXT_V : NEXT_NONE), N, mrow);
+          } else {
+            heads_epilogue(I1{}, ni - 1, ni == 1 ? NEXT_X2 : NEXT_G, N, mrow);
+            if (ni == 2 && gauss) {
+              float dummy;
+              grad_epilogue(false, dummy);
+            }
+          }
         }
-        // V net, second momentum half step
-        hidden_epilogue(tbv);
-        hidden_epilogue(A.vnet.b4);
-        if (it + 1 < sh.T) heads_epilogue(I0{}, I0{}, std::integral_constant<int, NEXT_V>{}, A.vnet, mrow);
-        else heads_epilogue(I0{}, I0{}, std::integral_constant<int, NEXT_NONE>{}, A.vnet, mrow);
       }
 
       // ---- log|J|, Hamiltonian, accept ---------------------------------------------------------------
