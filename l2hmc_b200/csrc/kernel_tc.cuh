@@ -52,6 +52,7 @@ struct TcNet {
   const float *b4;   // [N1]
   const float *bh;   // [N3]  (S | T | Q blocks)
   const float *es, *eq;  // [DP]
+  const float *img_s;    // the same chunk stream with the embed rows interleaved per 4-dim chunk (kernel_tc_s.cuh)
   const float *hc;       // [DP/4][28]: pre-multiplied heads constants of the specialised kernel (kernel_tc_s.cuh)
 };
 

@@ -13,7 +13,14 @@
 //     MUFU is the floor of this epilogue: 16 lanes per clock per SM);
 //   * the A operand of the NEXT GEMM (net input [a | b], or x - mu for the Gaussian grad) is produced inside the
 //     heads / grad epilogue from values still in registers: no separate pass over the state;
-//   * one mbarrier arrival per warp (count 8) instead of one per thread (count 256) for a_ready.
+//   * one mbarrier arrival per warp (count 8) instead of one per thread (count 256) for a_ready;
+//   * the epilogue of GEMM k and the MMAs of GEMM k+1 overlap: two accumulator regions in TMEM (P: 160 columns, the
+//     only one wide enough for the heads; Q: 144), the A operand handed over in K slots of 16 columns (= one ring slot of
+//     the B stream) through sub-barriers a_sub[0..NSUB), chunks owned round-robin by the two threads of a chain so
+//     that they complete in K order, and the net input interleaved per chunk ([a0..3 | b0..3] = one K step; the
+//     embed weight image is permuted to match on the host).  512 TMEM columns are 16 short of two heads-sized
+//     accumulators, so per net call one GEMM (the hidden layer, whose accumulator shares Q with the embed) waits for
+//     the whole epilogue before it (s_slot() below); after a Gaussian grad GEMM the V net runs fully overlapped.
 // Shapes without an instantiation run the generic kernel of kernel_tc.cuh.
 #pragma once
 #include "kernel_tc.cuh"
@@ -21,6 +28,9 @@
 namespace l2hmc {
 namespace tc {
 
+// TMEM columns of this kernel: accumulators P [0,160) and Q [160,304), A_hi [304,408), A_lo [408,512)
+constexpr uint32_t S_ACC_P = 0, S_ACC_Q = 160, S_AHI = 304, S_ALO = 408;
+constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
 
 template <int NQC>
@@ -70,8 +80,136 @@ __device__ __forceinline__ void put_a8(uint32_t lane_base, int col, const float 
     hi[j] = __uint_as_float(__float_as_uint(a[j]) & 0xFFFFE000u);
     lo[j] = a[j] - hi[j];
   }
-  tmem_st8(T_AHI + lane_base + col, hi);
-  tmem_st8(T_ALO + lane_base + col, lo);
+  tmem_st8(S_AHI + lane_base + col, hi);
+  tmem_st8(S_ALO + lane_base + col, lo);
+}
+__device__ __forceinline__ void put_a4s(uint32_t lane_base, int col, const float (&a)[4]) {
+  float hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    hi[j] = __uint_as_float(__float_as_uint(a[j]) & 0xFFFFE000u);
+    lo[j] = a[j] - hi[j];
+  }
+  tmem_st4(S_AHI + lane_base + col, hi);
+  tmem_st4(S_ALO + lane_base + col, lo);
+}
+
+// The 13 GEMM slots of a leapfrog step (V: embed, hidden, heads; X; X; Gaussian grad; V), as walk_schedule orders them:
+// which accumulator region a GEMM writes and whether it must wait for the complete A operand (serial) or may follow
+// the epilogue before it slot by slot.  Heads need P; consecutive GEMMs need different regions to overlap.
+struct SlotInfo {
+  int kind, net;
+  uint32_t acc;
+  bool serial;
+};
+__device__ __forceinline__ SlotInfo s_slot(int j, bool gauss) {
+  SlotInfo s;
+  if (j == 9) {  // grad U: its A operand (x - mu, 4 columns per chunk) is not handed over in K order
+    s.kind = 0; s.net = 0; s.acc = S_ACC_Q; s.serial = true;
+    return s;
+  }
+  const int jj = j > 9 ? j - 1 : j;
+  const int nc = jj / 3, l = jj - 3 * nc;  // net call 0..3, layer 0 embed / 1 hidden / 2 heads
+  s.kind = l + 1;
+  s.net = (nc == 0 || nc == 3) ? 1 : 0;
+  if (nc == 3 && gauss) {  // after the grad GEMM (Q): embed P, hidden Q, heads P -- all overlapped
+    s.acc = (l == 1) ? S_ACC_Q : S_ACC_P;
+    s.serial = false;
+  } else {                 // embed Q, hidden Q (after the embed epilogue), heads P
+    s.acc = (l == 2) ? S_ACC_P : S_ACC_Q;
+    s.serial = (l == 1);
+  }
+  return s;
+}
+
+// ===================== MMA issuer of the overlapped schedule (one warp) =====================
+// As issuer_loop (uniform datapath, elect.sync), plus: the accumulator region per GEMM and the A operand awaited per
+// K slot (a_sub[si]) -- or, for a serial GEMM, awaited whole (a_sub[nsub-1], on which every warp arrives last).
+__device__ __forceinline__ void issuer_loop_p(const TcArgs &A, const Sync &S, uint64_t *a_sub, int nsub, float *ring, uint32_t NSLOT,
+                                              uint32_t SLOT_FLOATS, int lane) {
+  uint32_t s = 0, ph = 0, gi = 0;
+  const uint32_t ring_u32 = smem_u32(ring);
+  const uint32_t slot_bytes = SLOT_FLOATS * 4u;
+  const bool gauss = A.en.kind == 0;
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+  long long w_a = 0, w_f = 0;
+  const long long t_begin = clock64();
+#endif
+  auto gemm = [&](int kind, int net, uint32_t acc, bool serial) {
+    const GemmDesc g = gemm_desc(A, kind, net);
+    const uint32_t idesc = make_idesc_tf32(128, g.n);
+    const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
+    const uint32_t slab16 = (uint32_t)g.n * 2u;
+    const uint32_t par = gi & 1u;
+    if (serial) {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      const long long t0 = clock64();
+#endif
+      mbar_wait(&a_sub[nsub - 1], par);
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      w_a += clock64() - t0;
+#endif
+      tcgen05_fence_after();
+    }
+    int si = 0;
+#pragma unroll 1
+    for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++si) {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      long long t0 = clock64();
+#endif
+      mbar_wait(&S.full[s], ph);
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      w_f += clock64() - t0;
+      t0 = clock64();
+#endif
+      if (!serial) {
+        mbar_wait(&a_sub[si], par);
+        tcgen05_fence_after();
+      }
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+      w_a += clock64() - t0;
+#endif
+      const uint32_t b16 = (ring_u32 + s * slot_bytes) >> 4;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < KSLOT; ++kk) {
+          if (ks + kk < g.nsteps) {
+            const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
+            const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
+            const uint32_t ahi = S_AHI + 8u * (ks + kk), alo = S_ALO + 8u * (ks + kk);
+            mma_tf32_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
+            mma_tf32_ts(acc, ahi, dlo, idesc, true);
+            mma_tf32_ts(acc, ahi, dhi, idesc, true);
+          }
+        }
+        tcgen05_commit(&S.empty[s]);
+      }
+      __syncwarp();
+      if (++s == NSLOT) { s = 0; ph ^= 1u; }
+    }
+    if (elect_one()) tcgen05_commit(S.acc_ready);
+    __syncwarp();
+    ++gi;
+  };
+  for (int tr = 0; tr < A.io.n_transitions; ++tr) {
+    if (gauss) gemm(0, 0, S_ACC_P, true);  // grad U at the start of a transition (region P: the first embed takes Q)
+    for (int it = 0; it < A.sh.T; ++it) {
+#pragma unroll 1
+      for (int j = 0; j < 13; ++j) {
+        if (j == 9 && !gauss) continue;
+        const SlotInfo si = s_slot(j, gauss);
+        gemm(si.kind, si.net, si.acc, si.serial);
+      }
+    }
+  }
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+  if (blockIdx.x == 0 && lane == 0) {
+    g_tc_dbg[0] = w_a;
+    g_tc_dbg[1] = w_f;
+    g_tc_dbg[2] = clock64() - t_begin;
+    g_tc_dbg[5] = gi;
+  }
+#endif
 }
 
 // what the heads epilogue prepares for the GEMM that follows it
@@ -82,11 +220,13 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   constexpr int NCT = MT * 2;  // compute threads: 2 per chain
   constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
   constexpr int DP = SDims<NQC>::DP, RS = SDims<NQC>::RS;
-  constexpr int Q0 = (NQC + 1) / 2, H0 = (NHC + 1) / 2;  // chunks owned by the first thread of a chain (the second owns the rest)
+  constexpr int NSUB = ((NQC > NHC ? NQC : NHC) + 1) / 2;  // K slots (2 K steps) of the deepest GEMM = sub-barriers
+  static_assert(NSUB <= NSUB_MAX, "too many K slots");
+  static_assert(8 * NQC <= 104 && 8 * NHC <= 104 && 12 * NQC <= 160, "TMEM map of kernel_tc_s.cuh");
   constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   auto compute_bar = []() { compute_bar_n<NCT>(); };
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[2 * MAX_SLOT + 2];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_SLOT + 2 + NSUB_MAX];
   __shared__ uint32_t tmem_slot;
   const Shape &sh = A.sh;
   const TcDims &td = A.td;
@@ -97,6 +237,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   const int D = sh.D;
   const long long base = (long long)blockIdx.x * MT;
   Sync S{bars, bars + MAX_SLOT, bars + 2 * MAX_SLOT, bars + 2 * MAX_SLOT + 1};
+  uint64_t *a_sub = bars + 2 * MAX_SLOT + 2;
   float *ring = smem + L.ring;
   const uint32_t NSLOT = (uint32_t)td.nslot, SLOT_FLOATS = (uint32_t)td.slot_floats;
 
@@ -105,7 +246,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       mbar_init(&S.full[s], 1);
       mbar_init(&S.empty[s], 1);
     }
-    mbar_init(S.a_ready, NCT / 32);  // one arrival per compute warp
+    mbar_init(S.a_ready, 1);  // unused here (a_sub instead)
+    for (int p = 0; p < NSUB_MAX; ++p) mbar_init(&a_sub[p], NCT / 32);  // one arrival per compute warp
     mbar_init(S.acc_ready, 1);
     fence_mbar_init();
   }
@@ -119,16 +261,16 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   if (warp == W_TMA) {
     producer_loop(A, S, ring, NSLOT, SLOT_FLOATS);
   } else if (warp == W_MMA) {
-    issuer_loop(A, S, ring, NSLOT, SLOT_FLOATS, lane);
+    issuer_loop_p(A, S, a_sub, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
   } else {
     // ===================== compute warps =====================
     using I0 = std::integral_constant<int, 0>;
     using I1 = std::integral_constant<int, 1>;
     const int c = 32 * (warp & 3) + lane;  // chain within the tile == TMEM lane
-    const int qd = warp >> 2;              // 0 / 1: which part of the chunks this thread owns (warp-uniform)
+    const int qd = warp >> 2;              // 0 / 1: this thread owns the chunks q = qd, qd + 2, ... (warp-uniform)
     const uint32_t lb = ((uint32_t)(32 * (warp & 3))) << 16;
-    const int qb = qd ? Q0 : 0, qn = qd ? NQC - Q0 : Q0;  // 4-dim chunks [qb, qb + qn)
-    const int hb = qd ? H0 : 0, hn = qd ? NHC - H0 : H0;  // 8-column hidden chunks [hb, hb + hn)
+    const int qn = (NQC - qd + 1) / 2;     // its 4-dim chunks: q = qd + 2 i, i < qn
+    const int hn = (NHC - qd + 1) / 2;     // its 8-column hidden chunks: q = qd + 2 i, i < hn
     const long long gch = base + c;
     const bool gauss = A.en.kind == 0;
     float *xr = smem + L.xs + c * RS, *vr = smem + L.vs + c * RS, *gr = smem + L.gs + c * RS;
@@ -149,12 +291,21 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       ++gi;
       tcgen05_fence_after();
     };
-    // A operand complete: every thread's tcgen05.st has landed, one arrival per warp
-    auto a_done = [&]() {
+    // K slot p of the next A operand is complete for this warp's chains: every thread's tcgen05.st has landed, one
+    // arrival per warp
+    auto slot_done = [&](int p) {
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(S.a_ready);
+      if (lane == 0) mbar_arrive(&a_sub[p]);
+    };
+    // ... and every K slot from `from` on (chunks this warp does not own, or an operand that is handed over whole)
+    auto a_done = [&](int from) {
+      tmem_wait_st();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0)
+        for (int p = from; p < NSUB; ++p) mbar_arrive(&a_sub[p]);
     };
     const float eps = sh.eps, Tm = A.en.temperature, rTm = 1.f / A.en.temperature;
 
@@ -178,7 +329,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       } else {
 #pragma unroll 1
         for (int i = 0; i < qn; ++i) {
-          const int q = qb + i;
+          const int q = qd + 2 * i;
           float z[4];
           philox_normals4(io.seed, ctr, io.chain_offset + gch, q, z);
 #pragma unroll
@@ -204,21 +355,21 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       float ljl = 0.f;  // log|J| of this thread's dimensions, in log2 units
 
       // ---- A operands ------------------------------------------------------------------------------------
-      // net input [a | b] of one 4-dim chunk -> columns 4q (a) and DP + 4q (b)
+      // net input of one 4-dim chunk: [a0..3 | b0..3] = K step q of the embed GEMM (weight rows permuted to match)
       auto put_ab = [&](int q, const float (&a)[4], const float (&b)[4]) {
-        put_a4(lb, 4 * q, a);
-        put_a4(lb, DP + 4 * q, b);
+        const float ab[8] = {a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]};
+        put_a8(lb, 8 * q, ab);
       };
       // Gaussian grad GEMM input x - mu of one chunk (the K tail beyond DP is zeroed once per GEMM by zero_gtail)
       auto put_xmu = [&](int q, const float (&x)[4]) {
         const float4 mu = ldg4(A.en.mu + 4 * q);
         const float a[4] = {x[0] - mu.x, x[1] - mu.y, x[2] - mu.z, x[3] - mu.w};
-        put_a4(lb, 4 * q, a);
+        put_a4s(lb, 4 * q, a);
       };
       auto zero_gtail = [&]() {  // KG = DP rounded to 8: one more 4-column chunk of zeros when NQC is odd
         if ((NQC & 1) && qd == 1) {
           const float z[4] = {0.f, 0.f, 0.f, 0.f};
-          put_a4(lb, DP, z);
+          put_a4s(lb, DP, z);
         }
       };
       // RoughWell grad U of one chunk (utils/distributions.py:90-97)
@@ -241,31 +392,31 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           }
         }
       };
-      // Gaussian: epilogue of the grad GEMM -> gs, V-net input [x | g]; optional Hamiltonian partial
-      auto grad_epilogue = [&](bool want_h, float &Hpart) {
+      // Gaussian: epilogue of the grad GEMM (accumulator at column `acc`) -> gs, V-net input [x | g] handed over per
+      // K slot; optional Hamiltonian partial
+      auto grad_epilogue = [&](uint32_t acc, bool want_h, float &Hpart) {
         wait_acc();
         float U = 0.f, K = 0.f;
 #pragma unroll 1
         for (int i = 0; i < qn; ++i) {
-          {
-            const int q = qb + i;
-            float g4[4];
-            tmem_ld4(lb + T_ACC + 4 * q, g4);
-            const float4 xv = lds4(xr + 4 * q);
-            const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
-            tmem_wait_ld();
+          const int q = qd + 2 * i;
+          float g4[4];
+          tmem_ld4(lb + acc + 4 * q, g4);
+          const float4 xv = lds4(xr + 4 * q);
+          const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
+          tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 4; ++j) g4[j] *= rTm;
-            sts4(gr + 4 * q, g4);
-            if (want_h) {
-              const float4 vv = lds4(vr + 4 * q);
-              const float v4[4] = {vv.x, vv.y, vv.z, vv.w};
-              ham_chunk(x4, v4, g4, q, U, K);
-            }
-            put_ab(q, x4, g4);
+          for (int j = 0; j < 4; ++j) g4[j] *= rTm;
+          sts4(gr + 4 * q, g4);
+          if (want_h) {
+            const float4 vv = lds4(vr + 4 * q);
+            const float v4[4] = {vv.x, vv.y, vv.z, vv.w};
+            ham_chunk(x4, v4, g4, q, U, K);
           }
+          put_ab(q, x4, g4);
+          slot_done(i);
         }
-        a_done();
+        a_done(qn);
         Hpart = (gauss ? 0.5f * U : U) + 0.5f * K;
       };
       // start of a transition: grad U(x), H(x, v) partial, first V-net input
@@ -273,19 +424,19 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         if (gauss) {
 #pragma unroll 1
           for (int i = 0; i < qn; ++i) {
-            const int q = qb + i;
+            const int q = qd + 2 * i;
             const float4 xv = lds4(xr + 4 * q);
             const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
             put_xmu(q, x4);
           }
           zero_gtail();
-          a_done();
-          grad_epilogue(true, Hpart);
+          a_done(0);
+          grad_epilogue(S_ACC_P, true, Hpart);
         } else {
           float U = 0.f, K = 0.f;
 #pragma unroll 1
           for (int i = 0; i < qn; ++i) {
-            const int q = qb + i;
+            const int q = qd + 2 * i;
             const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q);
             const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
             float g4[4];
@@ -293,8 +444,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             sts4(gr + 4 * q, g4);
             ham_chunk(x4, v4, g4, q, U, K);
             put_ab(q, x4, g4);
+            slot_done(i);
           }
-          a_done();
+          a_done(qn);
           Hpart = U + 0.5f * K;
         }
       };
@@ -303,7 +455,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         float U = 0.f, K = 0.f;
 #pragma unroll 1
         for (int i = 0; i < qn; ++i) {
-          const int q = qb + i;
+          const int q = qd + 2 * i;
           const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), gv = lds4(gr + 4 * q);
           const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w}, g4[4] = {gv.x, gv.y, gv.z, gv.w};
           ham_chunk(x4, v4, g4, q, U, K);
@@ -311,21 +463,24 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         return (gauss ? 0.5f * U : U) + 0.5f * K;
       };
 
-      // ---- relu(acc + bias) of this thread's 8-column chunks -> next A operand (bias row may differ per lane) ----
-      auto hidden_epilogue = [&](const float *__restrict__ bias) {
+      // ---- relu(acc + bias) of this thread's 8-column chunks -> K steps of the next A operand (bias row may differ per
+      // lane).  `acc`: accumulator column of this GEMM; `handover`: arrive per K slot (the next GEMM follows slot by
+      // slot) or once at the end (the next GEMM is serial).
+      auto hidden_epilogue = [&](uint32_t acc, const float *__restrict__ bias, bool handover) {
         wait_acc();
         float h[2][8];
-        tmem_ld8(lb + T_ACC + 8 * hb, h[0]);
+        tmem_ld8(lb + acc + 8 * qd, h[0]);
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
-          const int q = hb + i;
+          const int q = qd + 2 * i;
           const float4 b0 = ldg4(bias + 8 * q), b1 = ldg4(bias + 8 * q + 4);
           tmem_wait_ld();
-          if (i + 1 < hn) tmem_ld8(lb + T_ACC + 8 * (q + 1), h[B ^ 1]);
+          if (i + 1 < hn) tmem_ld8(lb + acc + 8 * (q + 2), h[B ^ 1]);
           const float(&hh)[8] = h[B];
           const float a[8] = {fmaxf(hh[0] + b0.x, 0.f), fmaxf(hh[1] + b0.y, 0.f), fmaxf(hh[2] + b0.z, 0.f), fmaxf(hh[3] + b0.w, 0.f),
                               fmaxf(hh[4] + b1.x, 0.f), fmaxf(hh[5] + b1.y, 0.f), fmaxf(hh[6] + b1.z, 0.f), fmaxf(hh[7] + b1.w, 0.f)};
           put_a8(lb, 8 * q, a);
+          if (handover) slot_done(i);
         };
         // two chunks per iteration (the register double buffer needs static names); rolled: the fully unrolled
         // version of this kernel had a 178 KB loop body and spent 40 % of the epilogue time on instruction fetch
@@ -334,25 +489,28 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           chunk(i, I0{});
           if (i + 1 < hn) chunk(i + 1, I1{});
         }
-        a_done();
+        a_done(handover ? hn : 0);
       };
 
       // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) + next A operand --------------
-      // MODE 0: momentum half step (V net, scale 1/2 eps); MODE 1: position half step XH in {0, 1} (X net, scale eps).
+      // MODE 0: momentum half step (V net, scale 1/2 eps); MODE 1: position half step xh in {0, 1} (X net, scale eps).
       // In log2 units: svl = cS * tanh(s + bs), fql = cQ * tanh(q + bq), with cS = e^{scale_s} * h * log2(e),
       // cQ = e^{scale_q} * eps * log2(e), h = 1/2 eps or eps; exp(+-sv) = 2^{+-svl}; log|J| += +-svl * ln 2.
+      // The heads accumulator is always region P.
       auto heads_epilogue = [&](auto mode_c, const int xh, const int next, const TcNet &N, const float *mrow) {
         constexpr int MODE = decltype(mode_c)::value;
+        constexpr uint32_t acc = S_ACC_P;
         const float hc = MODE == 0 ? 0.5f * eps : eps;
         const bool flip = (fwd != (xh == 0));  // MODE 1: k = m, or 1 - m when flipped
+        const bool handover = !(MODE == 1 && next == NEXT_G && gauss);  // x - mu for the grad GEMM goes over whole
         wait_acc();
         float s4[2][4], t4[2][4], q4[2][4];
-        tmem_ld4(lb + T_ACC + 4 * qb, s4[0]);
-        tmem_ld4(lb + T_ACC + DP + 4 * qb, t4[0]);
-        tmem_ld4(lb + T_ACC + 2 * DP + 4 * qb, q4[0]);
+        tmem_ld4(lb + acc + 4 * qd, s4[0]);
+        tmem_ld4(lb + acc + DP + 4 * qd, t4[0]);
+        tmem_ld4(lb + acc + 2 * DP + 4 * qd, q4[0]);
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
-          const int q = qb + i;
+          const int q = qd + 2 * i;
           const float *hcq = N.hc + HC_PER_CHUNK * q;
           const float4 c_bs = ldg4(hcq), c_bq = ldg4(hcq + 4), c_ns = ldg4(hcq + 8), c_cs = ldg4(hcq + 12);
           const float4 c_nq = ldg4(hcq + 16), c_cq = ldg4(hcq + 20), c_bt = ldg4(hcq + 24);
@@ -370,9 +528,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           }
           tmem_wait_ld();
           if (i + 1 < qn) {  // next chunk's accumulators travel while this chunk is processed
-            tmem_ld4(lb + T_ACC + 4 * (q + 1), s4[B ^ 1]);
-            tmem_ld4(lb + T_ACC + DP + 4 * (q + 1), t4[B ^ 1]);
-            tmem_ld4(lb + T_ACC + 2 * DP + 4 * (q + 1), q4[B ^ 1]);
+            tmem_ld4(lb + acc + 4 * (q + 2), s4[B ^ 1]);
+            tmem_ld4(lb + acc + DP + 4 * (q + 2), t4[B ^ 1]);
+            tmem_ld4(lb + acc + 2 * DP + 4 * (q + 2), q4[B ^ 1]);
           }
           float uu4[4];  // MODE 1: 1 - k, the dimensions this half step moves
 #pragma unroll
@@ -425,6 +583,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
                 b[j] = nx1 ? (fwd ? m4[j] : 1.f - m4[j]) * x4[j] : g4[j];
               }
               put_ab(q, a, b);
+              slot_done(i);
             }
           } else {
             sts4(xr + 4 * q, x4);
@@ -433,6 +592,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
 #pragma unroll
               for (int j = 0; j < 4; ++j) b[j] = uu4[j] * x4[j];
               put_ab(q, v4, b);
+              slot_done(i);
             } else if (gauss) {  // NEXT_G: grad U at the new x
               put_xmu(q, x4);
             } else {
@@ -440,6 +600,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
               roughwell_grad(q, x4, g);
               sts4(gr + 4 * q, g);
               put_ab(q, x4, g);
+              slot_done(i);
             }
           }
         };
@@ -448,8 +609,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           chunk(i, I0{});
           if (i + 1 < qn) chunk(i + 1, I1{});
         }
-        if (MODE == 1 && next == NEXT_G && gauss) zero_gtail();
-        if (next != NEXT_NONE) a_done();
+        if (!handover) zero_gtail();
+        if (next != NEXT_NONE) a_done(handover ? qn : 0);
         else tcgen05_fence_before();
       };
 
@@ -463,21 +624,24 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       for (int it = 0; it < sh.T; ++it) {
         const int trow = fwd ? it : sh.T - 1 - it;  // the step index this chain is at (utils/dynamics.py:285)
         const float *mrow = smem + L.smask + trow * DP;
-        // four net calls per leapfrog step: V (momentum half step), X, X (position half steps), V
+        // four net calls per leapfrog step: V (momentum half step), X, X (position half steps), V.  Accumulator
+        // regions and which GEMMs follow their A operand slot by slot: s_slot().
 #pragma unroll 1
         for (int ni = 0; ni < 4; ++ni) {
           const bool isv = (ni == 0 || ni == 3);
+          const bool overlapped = (ni == 3 && gauss);  // after the grad GEMM: embed P, hidden Q, heads P
           const TcNet &N = isv ? A.vnet : A.xnet;
           const float *tb = N.tb + (size_t)trow * td.N1;
-#pragma unroll 1
-          for (int l = 0; l < 2; ++l) hidden_epilogue(l == 0 ? tb : N.b4);
+          // embed epilogue -> hidden GEMM (serial unless `overlapped`); hidden epilogue -> heads GEMM (always overlapped)
+          hidden_epilogue(overlapped ? S_ACC_P : S_ACC_Q, tb, overlapped);
+          hidden_epilogue(S_ACC_Q, N.b4, true);
           if (isv) {
             heads_epilogue(I0{}, 0, ni == 0 ? NEXT_X1 : (it + 1 < sh.T ? NEXT_V : NEXT_NONE), N, mrow);
           } else {
             heads_epilogue(I1{}, ni - 1, ni == 1 ? NEXT_X2 : NEXT_G, N, mrow);
             if (ni == 2 && gauss) {
               float dummy;
-              grad_epilogue(false, dummy);
+              grad_epilogue(S_ACC_Q, false, dummy);
             }
           }
         }
