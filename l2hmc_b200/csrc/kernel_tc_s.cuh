@@ -14,13 +14,15 @@
 //   * the A operand of the NEXT GEMM (net input [a | b], or x - mu for the Gaussian grad) is produced inside the
 //     heads / grad epilogue from values still in registers: no separate pass over the state;
 //   * one mbarrier arrival per warp (count 8) instead of one per thread (count 256) for a_ready;
-//   * the epilogue of GEMM k and the MMAs of GEMM k+1 overlap: two accumulator regions in TMEM (P: 160 columns, the
-//     only one wide enough for the heads; Q: 144), the A operand handed over in K slots of 16 columns (= one ring slot of
-//     the B stream) through sub-barriers a_sub[0..NSUB), chunks owned round-robin by the two threads of a chain so
-//     that they complete in K order, and the net input interleaved per chunk ([a0..3 | b0..3] = one K step; the
-//     embed weight image is permuted to match on the host).  512 TMEM columns are 16 short of two heads-sized
-//     accumulators, so per net call one GEMM (the hidden layer, whose accumulator shares Q with the embed) waits for
-//     the whole epilogue before it (s_slot() below); after a Gaussian grad GEMM the V net runs fully overlapped.
+//   * the epilogue of GEMM k and the MMAs of GEMM k+1 overlap: three accumulator regions in TMEM, the A operand
+//     handed over in K slots of 16 columns (= one ring slot of the B stream) through sub-barriers a_sub[0..NSUB),
+//     chunks owned round-robin by the two threads of a chain so that they complete in K order, and the net input
+//     interleaved per chunk ([a0..3 | b0..3] = one K step; the embed weight image is permuted to match on the host);
+//   * the heads GEMM is split by dimensions into two GEMMs (first ceil(NQC/2) chunks | the rest, each with its S | T | Q
+//     column blocks): two heads-sized accumulators do not fit beside the A operand in 512 TMEM columns, the halves do
+//     (embed / heads_a: R1, hidden / grad: R2, heads_b: R3), and the state update of the first half runs while the
+//     tensor pipe works on the second.  The A operand of the next GEMM is written during the second half's
+//     epilogue only (for all chunks), so nothing overwrites A while heads_b still reads it.
 // Shapes without an instantiation run the generic kernel of kernel_tc.cuh.
 #pragma once
 #include "kernel_tc.cuh"
@@ -28,8 +30,8 @@
 namespace l2hmc {
 namespace tc {
 
-// TMEM columns of this kernel: accumulators P [0,160) and Q [160,304), A_hi [304,408), A_lo [408,512)
-constexpr uint32_t S_ACC_P = 0, S_ACC_Q = 160, S_AHI = 304, S_ALO = 408;
+// TMEM columns of this kernel: A_hi [0,104), A_lo [104,208), accumulators R1 [208,320), R2 [320,432), R3 [432,512)
+constexpr uint32_t S_AHI = 0, S_ALO = 104, S_R1 = 208, S_R2 = 320, S_R3 = 432;
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
 
@@ -94,54 +96,101 @@ __device__ __forceinline__ void put_a4s(uint32_t lane_base, int col, const float
   tmem_st4(S_ALO + lane_base + col, lo);
 }
 
-// The 13 GEMM slots of a leapfrog step (V: embed, hidden, heads; X; X; Gaussian grad; V), as walk_schedule orders them:
-// which accumulator region a GEMM writes and whether it must wait for the complete A operand (serial) or may follow
-// the epilogue before it slot by slot.  Heads need P; consecutive GEMMs need different regions to overlap.
-struct SlotInfo {
-  int kind, net;
-  uint32_t acc;
-  bool serial;
-};
-__device__ __forceinline__ SlotInfo s_slot(int j, bool gauss) {
-  SlotInfo s;
-  if (j == 9) {  // grad U: its A operand (x - mu, 4 columns per chunk) is not handed over in K order
-    s.kind = 0; s.net = 0; s.acc = S_ACC_Q; s.serial = true;
-    return s;
+// GEMM kinds of this kernel: 0 grad (Gaussian), 1 embed, 2 hidden, 3 heads_a (first CA dimension chunks), 4 heads_b.
+// Where each accumulates and what it needs before its first MMA:
+//   embed -> R1, hidden -> R2, heads_a -> R1, heads_b -> R3, grad -> R2.  Consecutive GEMMs never share a region, the
+//   region a GEMM writes was last read by an epilogue that has finished, so every GEMM except grad (whose A operand
+//   x - mu is handed over whole) follows the epilogue before it K slot by K slot; heads_b reads the A operand heads_a
+//   has already waited for.
+__device__ __forceinline__ uint32_t s_region(int kind) {
+  return (kind == 1 || kind == 3) ? S_R1 : (kind == 4 ? S_R3 : S_R2);
+}
+// 17 slots per leapfrog step: V (embed, hidden, heads_a, heads_b), X, X, grad (Gaussian only), V
+template <class F>
+__device__ __forceinline__ void walk_schedule_s(const TcArgs &A, F &&f) {
+  const bool gauss = A.en.kind == 0;
+  for (int tr = 0; tr < A.io.n_transitions; ++tr) {
+    if (gauss) f(0, 0);
+    for (int it = 0; it < A.sh.T; ++it) {
+#pragma unroll 1
+      for (int j = 0; j < 17; ++j) {
+        if (j == 12) {
+          if (gauss) f(0, 0);
+          continue;
+        }
+        const int jj = j > 12 ? j - 1 : j;  // 0..15
+        f((jj & 3) + 1, (jj < 4 || jj >= 12) ? 1 : 0);
+      }
+    }
   }
-  const int jj = j > 9 ? j - 1 : j;
-  const int nc = jj / 3, l = jj - 3 * nc;  // net call 0..3, layer 0 embed / 1 hidden / 2 heads
-  s.kind = l + 1;
-  s.net = (nc == 0 || nc == 3) ? 1 : 0;
-  if (nc == 3 && gauss) {  // after the grad GEMM (Q): embed P, hidden Q, heads P -- all overlapped
-    s.acc = (l == 1) ? S_ACC_Q : S_ACC_P;
-    s.serial = false;
-  } else {                 // embed Q, hidden Q (after the embed epilogue), heads P
-    s.acc = (l == 2) ? S_ACC_P : S_ACC_Q;
-    s.serial = (l == 1);
+}
+// chunk stream of a GEMM in the specialised image [embed (interleaved rows) | hidden | heads_a | heads_b]
+template <int NQC>
+__device__ __forceinline__ GemmDesc gemm_desc_s(const TcArgs &A, int kind, int net) {
+  constexpr int CA = (NQC + 1) / 2, CB = NQC - CA;
+  constexpr int N3A = (12 * CA + 15) / 16 * 16, N3B = (12 * CB + 15) / 16 * 16;
+  const TcDims &td = A.td;
+  const TcNet &N = net ? A.vnet : A.xnet;
+  GemmDesc g;
+  const size_t o_hid = (size_t)(td.K1 / 8) * 16 * td.N1, o_ha = o_hid + (size_t)(td.HK / 8) * 16 * td.N1;
+  if (kind == 0) {
+    g.src = A.gimg; g.nsteps = td.KG / 8; g.n = td.NG;
+  } else if (kind == 1) {
+    g.src = N.img_s; g.nsteps = td.K1 / 8; g.n = td.N1;
+  } else if (kind == 2) {
+    g.src = N.img_s + o_hid; g.nsteps = td.HK / 8; g.n = td.N1;
+  } else if (kind == 3) {
+    g.src = N.img_s + o_ha; g.nsteps = td.HK / 8; g.n = N3A;
+  } else {
+    g.src = N.img_s + o_ha + (size_t)(td.HK / 8) * 16 * N3A; g.nsteps = td.HK / 8; g.n = N3B;
   }
-  return s;
+  g.chunk_floats = 16 * g.n;
+  return g;
+}
+
+// ===================== TMA producer of this schedule (one warp) =====================
+template <int NQC>
+__device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, float *ring, uint32_t NSLOT, uint32_t SLOT_FLOATS) {
+  uint32_t s = 0, ph = 1;
+  walk_schedule_s(A, [&](int kind, int net) {
+    const GemmDesc g = gemm_desc_s<NQC>(A, kind, net);
+#pragma unroll 1
+    for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
+      const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
+      mbar_wait_sleep(&S.empty[s], ph);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&S.full[s], bytes);
+        bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
+      }
+      __syncwarp();
+      if (++s == NSLOT) { s = 0; ph ^= 1u; }
+    }
+  });
 }
 
 // ===================== MMA issuer of the overlapped schedule (one warp) =====================
-// As issuer_loop (uniform datapath, elect.sync), plus: the accumulator region per GEMM and the A operand awaited per
-// K slot (a_sub[si]) -- or, for a serial GEMM, awaited whole (a_sub[nsub-1], on which every warp arrives last).
-__device__ __forceinline__ void issuer_loop_p(const TcArgs &A, const Sync &S, uint64_t *a_sub, int nsub, float *ring, uint32_t NSLOT,
-                                              uint32_t SLOT_FLOATS, int lane) {
-  uint32_t s = 0, ph = 0, gi = 0;
+// As issuer_loop (uniform datapath, elect.sync), plus: the accumulator region per GEMM, the A operand awaited per K slot
+// (a_sub[si]; grad: whole, i.e. a_sub[nsub-1], on which every warp arrives last; heads_b: not at all), and two
+// accumulator-ready barriers used alternately (heads_a and heads_b complete without an epilogue in between).
+template <int NQC>
+__device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, uint64_t *a_sub, uint64_t *acc_rdy, int nsub, float *ring,
+                                              uint32_t NSLOT, uint32_t SLOT_FLOATS, int lane) {
+  uint32_t s = 0, ph = 0, gi = 0, ai = 0;  // ring slot / phase, GEMM counter, A-operand generation counter
   const uint32_t ring_u32 = smem_u32(ring);
   const uint32_t slot_bytes = SLOT_FLOATS * 4u;
-  const bool gauss = A.en.kind == 0;
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
   long long w_a = 0, w_f = 0;
   const long long t_begin = clock64();
 #endif
-  auto gemm = [&](int kind, int net, uint32_t acc, bool serial) {
-    const GemmDesc g = gemm_desc(A, kind, net);
+  walk_schedule_s(A, [&](int kind, int net) {
+    const GemmDesc g = gemm_desc_s<NQC>(A, kind, net);
+    const uint32_t acc = s_region(kind);
     const uint32_t idesc = make_idesc_tf32(128, g.n);
     const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
     const uint32_t slab16 = (uint32_t)g.n * 2u;
-    const uint32_t par = gi & 1u;
-    if (serial) {
+    const uint32_t par = ai & 1u;
+    const bool whole = kind == 0, nowait = kind == 4;
+    if (whole) {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
       const long long t0 = clock64();
 #endif
@@ -162,7 +211,7 @@ __device__ __forceinline__ void issuer_loop_p(const TcArgs &A, const Sync &S, ui
       w_f += clock64() - t0;
       t0 = clock64();
 #endif
-      if (!serial) {
+      if (!whole && !nowait) {
         mbar_wait(&a_sub[si], par);
         tcgen05_fence_after();
       }
@@ -187,21 +236,11 @@ __device__ __forceinline__ void issuer_loop_p(const TcArgs &A, const Sync &S, ui
       __syncwarp();
       if (++s == NSLOT) { s = 0; ph ^= 1u; }
     }
-    if (elect_one()) tcgen05_commit(S.acc_ready);
+    if (elect_one()) tcgen05_commit(&acc_rdy[gi & 1u]);
     __syncwarp();
     ++gi;
-  };
-  for (int tr = 0; tr < A.io.n_transitions; ++tr) {
-    if (gauss) gemm(0, 0, S_ACC_P, true);  // grad U at the start of a transition (region P: the first embed takes Q)
-    for (int it = 0; it < A.sh.T; ++it) {
-#pragma unroll 1
-      for (int j = 0; j < 13; ++j) {
-        if (j == 9 && !gauss) continue;
-        const SlotInfo si = s_slot(j, gauss);
-        gemm(si.kind, si.net, si.acc, si.serial);
-      }
-    }
-  }
+    if (!nowait) ++ai;
+  });
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
   if (blockIdx.x == 0 && lane == 0) {
     g_tc_dbg[0] = w_a;
@@ -222,11 +261,12 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   constexpr int DP = SDims<NQC>::DP, RS = SDims<NQC>::RS;
   constexpr int NSUB = ((NQC > NHC ? NQC : NHC) + 1) / 2;  // K slots (2 K steps) of the deepest GEMM = sub-barriers
   static_assert(NSUB <= NSUB_MAX, "too many K slots");
-  static_assert(8 * NQC <= 104 && 8 * NHC <= 104 && 12 * NQC <= 160, "TMEM map of kernel_tc_s.cuh");
+  constexpr int CA = (NQC + 1) / 2, CB = NQC - CA;  // dimension chunks of heads_a / heads_b
+  static_assert(8 * NQC <= 104 && 8 * NHC <= 104 && 12 * CA <= 112 && 12 * CB <= 80 && (8 * NHC + 15) / 16 * 16 <= 112, "TMEM map of kernel_tc_s.cuh");
   constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   auto compute_bar = []() { compute_bar_n<NCT>(); };
   extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t bars[2 * MAX_SLOT + 2 + NSUB_MAX];
+  __shared__ __align__(8) uint64_t bars[2 * MAX_SLOT + 2 + NSUB_MAX + 2];
   __shared__ uint32_t tmem_slot;
   const Shape &sh = A.sh;
   const TcDims &td = A.td;
@@ -238,6 +278,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   const long long base = (long long)blockIdx.x * MT;
   Sync S{bars, bars + MAX_SLOT, bars + 2 * MAX_SLOT, bars + 2 * MAX_SLOT + 1};
   uint64_t *a_sub = bars + 2 * MAX_SLOT + 2;
+  uint64_t *acc_rdy = a_sub + NSUB_MAX;  // two accumulator-ready barriers, GEMM g commits to acc_rdy[g & 1]
   float *ring = smem + L.ring;
   const uint32_t NSLOT = (uint32_t)td.nslot, SLOT_FLOATS = (uint32_t)td.slot_floats;
 
@@ -248,7 +289,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
     }
     mbar_init(S.a_ready, 1);  // unused here (a_sub instead)
     for (int p = 0; p < NSUB_MAX; ++p) mbar_init(&a_sub[p], NCT / 32);  // one arrival per compute warp
-    mbar_init(S.acc_ready, 1);
+    mbar_init(S.acc_ready, 1);  // unused here (acc_rdy instead)
+    mbar_init(&acc_rdy[0], 1);
+    mbar_init(&acc_rdy[1], 1);
     fence_mbar_init();
   }
   if (warp == W_MMA) tmem_alloc(&tmem_slot, 512);
@@ -259,9 +302,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   if (tmem != 0u) __trap();  // this CTA owns all 512 columns: column / lane 0 is a constant in the issuer and below
 
   if (warp == W_TMA) {
-    producer_loop(A, S, ring, NSLOT, SLOT_FLOATS);
+    producer_loop_s<NQC>(A, S, ring, NSLOT, SLOT_FLOATS);
   } else if (warp == W_MMA) {
-    issuer_loop_p(A, S, a_sub, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
+    issuer_loop_s<NQC>(A, S, a_sub, acc_rdy, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
   } else {
     // ===================== compute warps =====================
     using I0 = std::integral_constant<int, 0>;
@@ -283,10 +326,10 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
     auto wait_acc = [&]() {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
       const long long t0 = clock64();
-      mbar_wait_sleep(S.acc_ready, gi & 1u);
+      mbar_wait_sleep(&acc_rdy[gi & 1u], (gi >> 1) & 1u);
       w_acc += clock64() - t0;
 #else
-      mbar_wait_sleep(S.acc_ready, gi & 1u);
+      mbar_wait_sleep(&acc_rdy[gi & 1u], (gi >> 1) & 1u);
 #endif
       ++gi;
       tcgen05_fence_after();
@@ -431,7 +474,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           }
           zero_gtail();
           a_done(0);
-          grad_epilogue(S_ACC_P, true, Hpart);
+          grad_epilogue(S_R2, true, Hpart);
         } else {
           float U = 0.f, K = 0.f;
 #pragma unroll 1
@@ -496,18 +539,72 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       // MODE 0: momentum half step (V net, scale 1/2 eps); MODE 1: position half step xh in {0, 1} (X net, scale eps).
       // In log2 units: svl = cS * tanh(s + bs), fql = cQ * tanh(q + bq), with cS = e^{scale_s} * h * log2(e),
       // cQ = e^{scale_q} * eps * log2(e), h = 1/2 eps or eps; exp(+-sv) = 2^{+-svl}; log|J| += +-svl * ln 2.
-      // The heads accumulator is always region P.
-      auto heads_epilogue = [&](auto mode_c, const int xh, const int next, const TcNet &N, const float *mrow) {
+      // The A operand of the GEMM that follows, for one chunk whose NEW state is in x4 / v4 (+ g4, mask row m4):
+      auto prep = [&](auto mode_c, const int xh, const int next, int q, int i, const float (&x4)[4], const float (&v4)[4],
+                      const float (&g4)[4], const float (&m4)[4]) {
         constexpr int MODE = decltype(mode_c)::value;
-        constexpr uint32_t acc = S_ACC_P;
+        if (MODE == 0) {
+          if (next != NEXT_NONE) {
+            // NEXT_X1: X net, first half: [v | k x], k = m (fwd) or 1 - m (bwd); NEXT_V: V net again at the same [x | g]
+            const bool nx1 = next == NEXT_X1;
+            float a[4], b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              a[j] = nx1 ? v4[j] : x4[j];
+              b[j] = nx1 ? (fwd ? m4[j] : 1.f - m4[j]) * x4[j] : g4[j];
+            }
+            put_ab(q, a, b);
+            slot_done(i);
+          }
+        } else {
+          if (next == NEXT_X2) {  // X net, second half: its k is this half's 1 - k
+            const bool flip = (fwd != (xh == 0));
+            float b[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = (flip ? m4[j] : 1.f - m4[j]) * x4[j];
+            put_ab(q, v4, b);
+            slot_done(i);
+          } else if (gauss) {  // NEXT_G: grad U at the new x, handed over whole
+            put_xmu(q, x4);
+          } else {
+            float g[4];
+            roughwell_grad(q, x4, g);
+            sts4(gr + 4 * q, g);
+            put_ab(q, x4, g);
+            slot_done(i);
+          }
+        }
+      };
+      // part 0: chunks q < CA (accumulator of heads_a in R1), state update only; part 1: chunks q >= CA (heads_b in R3),
+      // preceded by the A operand of the part-0 chunks (their new state is read back from shared memory) -- A is not
+      // written while heads_b still reads it, and the tensor pipe works on heads_b during part 0.
+      auto heads_epilogue = [&](auto mode_c, auto part_c, const int xh, const int next, const TcNet &N, const float *mrow) {
+        constexpr int MODE = decltype(mode_c)::value, PART = decltype(part_c)::value;
+        constexpr int CP = PART == 0 ? CA : CB;                                   // chunks of this part
+        constexpr uint32_t cS = PART == 0 ? S_R1 : S_R3 - 4 * CA;                 // S column of chunk q: cS + 4 q
+        constexpr uint32_t cT = cS + 4 * CP, cQ = cS + 8 * CP;
         const float hc = MODE == 0 ? 0.5f * eps : eps;
         const bool flip = (fwd != (xh == 0));  // MODE 1: k = m, or 1 - m when flipped
-        const bool handover = !(MODE == 1 && next == NEXT_G && gauss);  // x - mu for the grad GEMM goes over whole
+        const int na = (CA - qd + 1) / 2;      // this thread's chunks in part 0: i < na
+        const int ib = PART == 0 ? 0 : na, ie = PART == 0 ? na : qn;
         wait_acc();
         float s4[2][4], t4[2][4], q4[2][4];
-        tmem_ld4(lb + acc + 4 * qd, s4[0]);
-        tmem_ld4(lb + acc + DP + 4 * qd, t4[0]);
-        tmem_ld4(lb + acc + 2 * DP + 4 * qd, q4[0]);
+        if (ib < ie) {
+          const int q = qd + 2 * ib;
+          tmem_ld4(lb + cS + 4 * q, s4[0]);
+          tmem_ld4(lb + cT + 4 * q, t4[0]);
+          tmem_ld4(lb + cQ + 4 * q, q4[0]);
+        }
+        if (PART == 1 && next != NEXT_NONE) {
+#pragma unroll 1
+          for (int i = 0; i < na; ++i) {  // deferred A operand of the part-0 chunks
+            const int q = qd + 2 * i;
+            const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), mv = lds4(mrow + 4 * q), gv = lds4(gr + 4 * q);
+            const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
+            const float m4[4] = {mv.x, mv.y, mv.z, mv.w}, g4[4] = {gv.x, gv.y, gv.z, gv.w};
+            prep(mode_c, xh, next, q, i, x4, v4, g4, m4);
+          }
+        }
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
           const int q = qd + 2 * i;
@@ -515,8 +612,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           const float4 c_bs = ldg4(hcq), c_bq = ldg4(hcq + 4), c_ns = ldg4(hcq + 8), c_cs = ldg4(hcq + 12);
           const float4 c_nq = ldg4(hcq + 16), c_cq = ldg4(hcq + 20), c_bt = ldg4(hcq + 24);
           const float bs2[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bq2[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
-          const float n2cS[4] = {c_ns.x, c_ns.y, c_ns.z, c_ns.w}, cS[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w};
-          const float n2cQ[4] = {c_nq.x, c_nq.y, c_nq.z, c_nq.w}, cQ[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
+          const float n2cS[4] = {c_ns.x, c_ns.y, c_ns.z, c_ns.w}, cSc[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w};
+          const float n2cQ[4] = {c_nq.x, c_nq.y, c_nq.z, c_nq.w}, cQc[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
           const float bth[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};
           const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), mv = lds4(mrow + 4 * q);
           float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
@@ -527,12 +624,11 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
           }
           tmem_wait_ld();
-          if (i + 1 < qn) {  // next chunk's accumulators travel while this chunk is processed
-            tmem_ld4(lb + acc + 4 * (q + 2), s4[B ^ 1]);
-            tmem_ld4(lb + acc + DP + 4 * (q + 2), t4[B ^ 1]);
-            tmem_ld4(lb + acc + 2 * DP + 4 * (q + 2), q4[B ^ 1]);
+          if (i + 1 < ie) {  // next chunk's accumulators travel while this chunk is processed
+            tmem_ld4(lb + cS + 4 * (q + 2), s4[B ^ 1]);
+            tmem_ld4(lb + cT + 4 * (q + 2), t4[B ^ 1]);
+            tmem_ld4(lb + cQ + 4 * (q + 2), q4[B ^ 1]);
           }
-          float uu4[4];  // MODE 1: 1 - k, the dimensions this half step moves
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float svl, fql;
@@ -543,11 +639,11 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
               const float eQ = ex2_approx(fminf(fmaf(q4[B][j], 2.f * L2E, bq2[j]), 57.f));
               const float dS = eS + 1.f, dQ = eQ + 1.f;
               const float r = rcp_approx(dS * dQ);
-              svl = fmaf(r * dQ, n2cS[j], cS[j]);
-              fql = fmaf(r * dS, n2cQ[j], cQ[j]);
+              svl = fmaf(r * dQ, n2cS[j], cSc[j]);
+              fql = fmaf(r * dS, n2cQ[j], cQc[j]);
             } else {
-              svl = cS[j] * tanhf((s4[B][j] * (2.f * L2E) + bs2[j]) * (0.5f * LN2));
-              fql = cQ[j] * tanhf((q4[B][j] * (2.f * L2E) + bq2[j]) * (0.5f * LN2));
+              svl = cSc[j] * tanhf((s4[B][j] * (2.f * L2E) + bs2[j]) * (0.5f * LN2));
+              fql = cQc[j] * tanhf((q4[B][j] * (2.f * L2E) + bq2[j]) * (0.5f * LN2));
             }
             const float Tt = fmaf(t4[B][j], hc, bth[j]);  // h * (t + bt)
             const float eQx = FAST ? ex2_approx(fql) : exp2f(fql);
@@ -562,7 +658,6 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             } else {
               const float k = flip ? 1.f - m4[j] : m4[j];
               const float uu = 1.f - k;
-              uu4[j] = uu;
               // fwd: x e + h (e^{fq} v + T) ; bwd: e (x - h (e^{fq} v + T))
               const float inner = fmaf(eQx, hc * v4[j], Tt);
               const float nx = fmaf(x4[j], e, inner * w);
@@ -570,48 +665,23 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
               ljl = fmaf(uu, svs, ljl);
             }
           }
-          // ---- the new state and the A operand of the GEMM that follows ----
-          if (MODE == 0) {
-            sts4(vr + 4 * q, v4);
-            if (next != NEXT_NONE) {
-              // NEXT_X1: X net, first half: [v | k x], k = m (fwd) or 1 - m (bwd); NEXT_V: V net again at the same [x | g]
-              const bool nx1 = next == NEXT_X1;
-              float a[4], b[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                a[j] = nx1 ? v4[j] : x4[j];
-                b[j] = nx1 ? (fwd ? m4[j] : 1.f - m4[j]) * x4[j] : g4[j];
-              }
-              put_ab(q, a, b);
-              slot_done(i);
-            }
-          } else {
-            sts4(xr + 4 * q, x4);
-            if (next == NEXT_X2) {  // X net, second half: its k is this half's 1 - k
-              float b[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) b[j] = uu4[j] * x4[j];
-              put_ab(q, v4, b);
-              slot_done(i);
-            } else if (gauss) {  // NEXT_G: grad U at the new x
-              put_xmu(q, x4);
-            } else {
-              float g[4];
-              roughwell_grad(q, x4, g);
-              sts4(gr + 4 * q, g);
-              put_ab(q, x4, g);
-              slot_done(i);
-            }
-          }
+          if (MODE == 0) sts4(vr + 4 * q, v4);
+          else sts4(xr + 4 * q, x4);
+          if (PART == 1) prep(mode_c, xh, next, q, i, x4, v4, g4, m4);
         };
 #pragma unroll 1
-        for (int i = 0; i < qn; i += 2) {
+        for (int i = ib; i < ie; i += 2) {
           chunk(i, I0{});
-          if (i + 1 < qn) chunk(i + 1, I1{});
+          if (i + 1 < ie) chunk(i + 1, I1{});
         }
-        if (!handover) zero_gtail();
-        if (next != NEXT_NONE) a_done(handover ? qn : 0);
-        else tcgen05_fence_before();
+        if (PART == 1) {
+          const bool handover = !(MODE == 1 && next == NEXT_G && gauss);  // x - mu for the grad GEMM goes over whole
+          if (!handover) zero_gtail();
+          if (next != NEXT_NONE) a_done(handover ? qn : 0);
+          else tcgen05_fence_before();
+        } else {
+          tcgen05_fence_before();
+        }
       };
 
       float hpart0 = 0.f;
@@ -624,24 +694,25 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       for (int it = 0; it < sh.T; ++it) {
         const int trow = fwd ? it : sh.T - 1 - it;  // the step index this chain is at (utils/dynamics.py:285)
         const float *mrow = smem + L.smask + trow * DP;
-        // four net calls per leapfrog step: V (momentum half step), X, X (position half steps), V.  Accumulator
-        // regions and which GEMMs follow their A operand slot by slot: s_slot().
+        // four net calls per leapfrog step: V (momentum half step), X, X (position half steps), V
 #pragma unroll 1
         for (int ni = 0; ni < 4; ++ni) {
           const bool isv = (ni == 0 || ni == 3);
-          const bool overlapped = (ni == 3 && gauss);  // after the grad GEMM: embed P, hidden Q, heads P
           const TcNet &N = isv ? A.vnet : A.xnet;
           const float *tb = N.tb + (size_t)trow * td.N1;
-          // embed epilogue -> hidden GEMM (serial unless `overlapped`); hidden epilogue -> heads GEMM (always overlapped)
-          hidden_epilogue(overlapped ? S_ACC_P : S_ACC_Q, tb, overlapped);
-          hidden_epilogue(S_ACC_Q, N.b4, true);
+          hidden_epilogue(S_R1, tb, true);    // embed accumulator -> A of the hidden GEMM
+          hidden_epilogue(S_R2, N.b4, true);  // hidden accumulator -> A of heads_a / heads_b
           if (isv) {
-            heads_epilogue(I0{}, 0, ni == 0 ? NEXT_X1 : (it + 1 < sh.T ? NEXT_V : NEXT_NONE), N, mrow);
+            const int next = ni == 0 ? NEXT_X1 : (it + 1 < sh.T ? NEXT_V : NEXT_NONE);
+            heads_epilogue(I0{}, I0{}, 0, next, N, mrow);
+            heads_epilogue(I0{}, I1{}, 0, next, N, mrow);
           } else {
-            heads_epilogue(I1{}, ni - 1, ni == 1 ? NEXT_X2 : NEXT_G, N, mrow);
+            const int next = ni == 1 ? NEXT_X2 : NEXT_G;
+            heads_epilogue(I1{}, I0{}, ni - 1, next, N, mrow);
+            heads_epilogue(I1{}, I1{}, ni - 1, next, N, mrow);
             if (ni == 2 && gauss) {
               float dummy;
-              grad_epilogue(S_ACC_Q, false, dummy);
+              grad_epilogue(S_R2, false, dummy);
             }
           }
         }

@@ -340,7 +340,8 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
     const float *W = blk == 0 ? p->Ws : (blk == 1 ? p->Wt : p->Wq);
     return W[(size_t)k * D + d];
   });
-  // the specialised kernel (kernel_tc_s.cuh) interleaves the net input per 4-dim chunk: K step q = [a_{4q..4q+3} | b_{4q..4q+3}]
+  // the specialised kernel (kernel_tc_s.cuh): net input interleaved per 4-dim chunk (K step q = [a_{4q..4q+3} | b_{4q..4q+3}]),
+  // heads split by dimensions into heads_a (first CA chunks) and heads_b (the rest), each with S | T | Q column blocks
   std::vector<float> img_s;
   append_b_stream(img_s, td.K1, td.N1, [&](int k, int n) -> float {
     if (n >= H) return 0.f;
@@ -348,12 +349,26 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
     if (d >= D) return 0.f;
     return ((k & 7) < 4 ? p->W1 : p->W2)[(size_t)d * H + n];
   });
-  const size_t nemb = img_s.size();
-  img_s.insert(img_s.end(), img.begin() + nemb, img.end());  // hidden and heads streams are shared
+  append_b_stream(img_s, td.HK, td.N1, [&](int k, int n) -> float { return (k < H && n < H) ? p->W4[(size_t)k * H + n] : 0.f; });
+  {
+    const int nqc = DP / 4, ca = (nqc + 1) / 2, cb = nqc - ca;
+    for (int part = 0; part < 2; ++part) {
+      const int cp = part == 0 ? ca : cb, d0 = part == 0 ? 0 : 4 * ca, np = round_up(12 * cp, 16);
+      if (cp == 0) continue;
+      append_b_stream(img_s, td.HK, np, [&](int k, int n) -> float {
+        if (k >= H || n >= 12 * cp) return 0.f;
+        const int blk = n / (4 * cp), d = d0 + n - blk * 4 * cp;
+        if (d >= D) return 0.f;
+        const float *W = blk == 0 ? p->Ws : (blk == 1 ? p->Wt : p->Wq);
+        return W[(size_t)k * D + d];
+      });
+    }
+  }
+  const size_t nimg_s = img_s.size();
   const size_t nimg = img.size(), ntb = (size_t)T * td.N1, nb4 = td.N1, nbh = td.N3, nes = DP;
-  std::vector<float> buf(nimg + ntb + nb4 + nbh + 2 * nes + nimg, 0.f);
+  std::vector<float> buf(nimg + ntb + nb4 + nbh + 2 * nes + nimg_s, 0.f);
   memcpy(buf.data(), img.data(), nimg * sizeof(float));
-  memcpy(buf.data() + nimg + ntb + nb4 + nbh + 2 * nes, img_s.data(), nimg * sizeof(float));
+  memcpy(buf.data() + nimg + ntb + nb4 + nbh + 2 * nes, img_s.data(), nimg_s * sizeof(float));
   float *tb = buf.data() + nimg, *b4 = tb + ntb, *bh = b4 + nb4, *es = bh + nbh, *eq = es + nes;
   for (int t = 0; t < T; ++t) {
     const float arg = 6.2831855f * (float)t / (float)T;  // utils/dynamics.py:99-105 in fp32
@@ -909,10 +924,14 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     const unsigned blocks = (unsigned)((a->n + tc::MT - 1) / tc::MT);
     if (spec) {
       const long long state_bytes = (long long)tc::make_tclay_s(tc::tc_s_row_stride(ctx->sh.DP), ctx->sh.DP, ctx->sh.T).ring * 4;
-      long long ns = (232448LL - 1024 - state_bytes) / ((long long)ctx->td.slot_floats * 4);
+      {  // ring slot = KSLOT K steps of the widest GEMM of this kernel's schedule (the heads are split in two)
+        const int ca = (nqc + 1) / 2, n3a = round_up(12 * ca, 16);
+        int nmax = ctx->td.N1 > n3a ? ctx->td.N1 : n3a;
+        if (ctx->td.NG > nmax) nmax = ctx->td.NG;
+        TA.td.slot_floats = tc::KSLOT * 16 * nmax;
+      }
+      long long ns = (232448LL - 1024 - state_bytes) / ((long long)TA.td.slot_floats * 4);
       TA.td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
-      TA.xnet.img = TA.xnet.img_s;  // embed rows in the interleaved [a | b] chunk order
-      TA.vnet.img = TA.vnet.img_s;
       if (TA.td.nslot < 4) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: shared-memory ring too small for this shape");
       const size_t smem = tc::tc_s_smem_bytes(ctx->sh.DP, ctx->sh.T, TA.td.nslot, TA.td.slot_floats);
       static thread_local size_t tc_s_configured = 0;
