@@ -32,6 +32,14 @@ namespace tc {
 
 // TMEM columns of this kernel: A_hi [0,104), A_lo [104,208), accumulators R1 [208,320), R2 [320,432), R3 [432,512)
 constexpr uint32_t S_AHI = 0, S_ALO = 104, S_R1 = 208, S_R2 = 320, S_R3 = 432;
+#ifndef L2HMC_TC_KSLOT_S
+#define L2HMC_TC_KSLOT_S 4
+#endif
+// K steps per ring slot (= per bulk copy) of this kernel.  A bulk copy takes ~590 cycles whatever its size up to 32 KB
+// (profiles/r01_tc_probe.txt: 14 / 28 / 56 B/cycle for 8 / 16 / 32 KB), so the B stream (33 B/cycle per SM once every
+// GEMM overlaps an epilogue) wants few large copies; the A operand is still handed over per 2 K steps.
+constexpr int KSLOT_S = L2HMC_TC_KSLOT_S;
+static_assert(KSLOT_S % 2 == 0, "ring slot = whole A hand-over slots");
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
 
@@ -155,8 +163,8 @@ __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, 
   walk_schedule_s(A, [&](int kind, int net) {
     const GemmDesc g = gemm_desc_s<NQC>(A, kind, net);
 #pragma unroll 1
-    for (int ks = 0; ks < g.nsteps; ks += KSLOT) {
-      const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT, g.nsteps - ks);
+    for (int ks = 0; ks < g.nsteps; ks += KSLOT_S) {
+      const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT_S, g.nsteps - ks);
       mbar_wait_sleep(&S.empty[s], ph);
       if (elect_one()) {
         mbar_arrive_expect_tx(&S.full[s], bytes);
@@ -200,39 +208,46 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 #endif
       tcgen05_fence_after();
     }
-    int si = 0;
 #pragma unroll 1
-    for (int ks = 0; ks < g.nsteps; ks += KSLOT, ++si) {
+    for (int ks = 0; ks < g.nsteps; ks += KSLOT_S) {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
       long long t0 = clock64();
 #endif
       mbar_wait(&S.full[s], ph);
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
       w_f += clock64() - t0;
-      t0 = clock64();
-#endif
-      if (!whole && !nowait) {
-        mbar_wait(&a_sub[si], par);
-        tcgen05_fence_after();
-      }
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-      w_a += clock64() - t0;
 #endif
       const uint32_t b16 = (ring_u32 + s * slot_bytes) >> 4;
-      if (elect_one()) {
 #pragma unroll
-        for (int kk = 0; kk < KSLOT; ++kk) {
-          if (ks + kk < g.nsteps) {
-            const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
-            const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
-            const uint32_t ahi = S_AHI + 8u * (ks + kk), alo = S_ALO + 8u * (ks + kk);
-            mma_tf32_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
-            mma_tf32_ts(acc, ahi, dlo, idesc, true);
-            mma_tf32_ts(acc, ahi, dhi, idesc, true);
+      for (int k2 = 0; k2 < KSLOT_S; k2 += 2) {  // one A hand-over slot = 2 K steps
+        if (ks + k2 < g.nsteps) {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+          t0 = clock64();
+#endif
+          if (!whole && !nowait) {
+            mbar_wait(&a_sub[(ks + k2) >> 1], par);
+            tcgen05_fence_after();
           }
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+          w_a += clock64() - t0;
+#endif
+          if (elect_one()) {
+#pragma unroll
+            for (int kk = k2; kk < k2 + 2; ++kk) {
+              if (ks + kk < g.nsteps) {
+                const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
+                const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
+                const uint32_t ahi = S_AHI + 8u * (ks + kk), alo = S_ALO + 8u * (ks + kk);
+                mma_tf32_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
+                mma_tf32_ts(acc, ahi, dlo, idesc, true);
+                mma_tf32_ts(acc, ahi, dhi, idesc, true);
+              }
+            }
+          }
+          __syncwarp();
         }
-        tcgen05_commit(&S.empty[s]);
       }
+      if (elect_one()) tcgen05_commit(&S.empty[s]);
       __syncwarp();
       if (++s == NSLOT) { s = 0; ph ^= 1u; }
     }

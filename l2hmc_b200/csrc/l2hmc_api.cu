@@ -928,7 +928,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
         const int ca = (nqc + 1) / 2, n3a = round_up(12 * ca, 16);
         int nmax = ctx->td.N1 > n3a ? ctx->td.N1 : n3a;
         if (ctx->td.NG > nmax) nmax = ctx->td.NG;
-        TA.td.slot_floats = tc::KSLOT * 16 * nmax;
+        TA.td.slot_floats = tc::KSLOT_S * 16 * nmax;
       }
       long long ns = (232448LL - 1024 - state_bytes) / ((long long)TA.td.slot_floats * 4);
       TA.td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
