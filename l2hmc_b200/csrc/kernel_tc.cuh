@@ -102,6 +102,9 @@ template <int NCT>
 __device__ __forceinline__ void compute_bar_n() { asm volatile("bar.sync 1, %0;" ::"n"(NCT) : "memory"); }
 // waits that last thousands of cycles (compute warps waiting for a GEMM): back off so the spinning warps do not
 // take issue slots from the single MMA-issuer / producer threads
+#ifndef L2HMC_TC_SLEEP_NS
+#define L2HMC_TC_SLEEP_NS 64
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
   const uint32_t bar_u32 = smem_u32(bar);
@@ -116,7 +119,9 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) 
         : "r"(bar_u32), "r"(parity)
         : "memory");
     if (done) break;
-    __nanosleep(64);
+#if L2HMC_TC_SLEEP_NS > 0
+    __nanosleep(L2HMC_TC_SLEEP_NS);
+#endif
   }
 }
 

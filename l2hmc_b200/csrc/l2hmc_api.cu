@@ -1029,7 +1029,7 @@ static int ensure_u8(l2hmc_ctx *ctx, uint8_t *&p, size_t &have, size_t n) {
   return L2HMC_OK;
 }
 
-// l2hmc_transition_host for one transition of a large batch: 4 chunks pipelined over 3 streams.
+// l2hmc_transition_host for one transition of a large batch: chunks pipelined over 3 streams.
 static int transition_host_chunked(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
   const size_t n = (size_t)a->n, D = (size_t)ctx->sh.D;
   int rc;
@@ -1045,8 +1045,12 @@ static int transition_host_chunked(l2hmc_ctx *ctx, const l2hmc_transition_args *
   const bool want_next = a->x_next || a->do_mh;
   if (want_next && (rc = ensure(ctx, ctx->hxn, n * D))) return rc;
   if (a->accepted && (rc = ensure_u8(ctx, ctx->hacc, ctx->hacc_n, n))) return rc;
-  const int NCH = 4;
-  const size_t per = ((n + NCH - 1) / NCH + 127) / 128 * 128;  // whole 128-chain tiles per chunk
+  // chunk = two waves of 128-chain tiles (one tile per SM and wave), at least 4 chunks: the first copy in and the last
+  // copy out are the only ones that do not hide under a kernel
+  const size_t sms = ctx->lay.sms > 0 ? (size_t)ctx->lay.sms : 148;
+  size_t per = 2 * sms * 128;
+  if (per * 4 > n) per = ((n + 3) / 4 + 127) / 128 * 128;
+  const int NCH = (int)((n + per - 1) / per);
   for (int c = 0; c < NCH; ++c) {
     const size_t lo = (size_t)c * per;
     if (lo >= n) break;
