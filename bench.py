@@ -308,6 +308,12 @@ def main():
                 "frac_of_measured_tf32_tensor": (achieved / (float(peaks["bf16_tflops_sustained"]) / 2)) if achieved else None}
     if clocks.get("sm_mhz"):
         roofline["frac_at_clock_under_load"] = achieved / (148 * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12) if achieved else None
+    # DRAM bytes of one launch of the dominant kernel from the committed `ncu --set full` capture of this same workload
+    # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_tc_s_ncu.txt); below the algorithmic bytes because the
+    # 126 MB L2 still holds part of the written lines when the launch ends
+    if dyn.kernel_name.startswith("tc") and n == CHAINS_PER_GPU:
+        roofline["traffic"] = 53.356544e6 + 54.853120e6
+        roofline["traffic_source"] = "profiles/r01_tc_s_ncu.txt"
     if dyn.kernel_name.startswith("tc") and achieved:
         # the GEMMs run on the tensor pipe as 3xTF32 (three tf32 MMAs per fp32-accurate product, plus padding of
         # 100 -> 104/112 and 150 -> 160 columns): the honest denominator is the dense TF32 rate, = half the measured
@@ -319,6 +325,13 @@ def main():
                                         "counted once although each product costs three tf32 MMAs (3xTF32 split for 1e-5 parity), "
                                         "so frac <= ~0.29 by construction" % src,
                          "tensor_mma_per_product": 3})
+        # what the tensor pipe executes: 3 tf32 MMAs per product over the padded shapes (K 100 -> 104, N 100 -> 112,
+        # heads 150 -> 96 + 80 columns, grad 50 -> 56 x 64), per leapfrog step and 128-chain tile
+        mac_tile_step = 3 * (4 * 128 * 104 * (112 + 112 + 96 + 80) + 128 * 56 * 64)
+        executed = 2.0 * mac_tile_step * LF * (n / 128.0) / (kern_ms * 1e-3) / 1e12
+        roofline["executed_tf32_tflops"] = executed
+        roofline["executed_frac_of_measured_tf32"] = executed / tf32_peak
+        roofline["executed_frac_of_tf32_at_sm_max_clock"] = executed / (148 * 2048 * 2 * sm_max * 1e6 / 1e12)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
