@@ -360,6 +360,61 @@ def test_tc_kernel_multi_transition_and_philox():
     assert float((d["px"] - c["px"]).abs().max()) <= 2e-4
 
 
+def _fixed_inputs(P, n):
+    d = P.draws(n)
+    return (torch.as_tensor(d["x"]).cuda(), torch.as_tensor(d["v_f"]).cuda(), torch.as_tensor(d["dir"]).cuda(),
+            torch.as_tensor(d["u"]).cuda())
+
+
+@pytest.mark.parametrize("name,n", [("c2_scg50", 700), ("c4_rw32", 300)])
+def test_tc_specialised_and_generic_kernels_agree(name, n, monkeypatch):
+    """The shape-specialised compute path (kernel_tc_s.cuh: split heads GEMM, overlapped epilogues, interleaved net
+    input) and the generic tensor-core kernel run the same transition: same injected randomness -> same samples and
+    accept probabilities up to fp32 reordering, same Metropolis decisions outside that noise."""
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    dyn = P.product(kernel="tc")
+    x, v, dr, u = _fixed_inputs(P, n)
+    kw = dict(v=v, direction=dr, u=u, do_mh=True)
+    monkeypatch.delenv("L2HMC_TC_GENERIC", raising=False)
+    a = dyn._transition(x, **kw)
+    monkeypatch.setenv("L2HMC_TC_GENERIC", "1")
+    b = dyn._transition(x, **kw)
+    monkeypatch.delenv("L2HMC_TC_GENERIC", raising=False)
+    assert not torch.equal(a["Lx"], b["Lx"]) or name != "c2_scg50"  # two different code paths really ran
+    assert U.max_rel(a["Lx"].cpu().numpy(), b["Lx"].cpu().numpy()) <= SAMPLE_TOL
+    assert U.max_rel(a["Lv"].cpu().numpy(), b["Lv"].cpu().numpy()) <= SAMPLE_TOL
+    dp = (a["px"] - b["px"]).abs().cpu().numpy()
+    assert float(dp.max()) <= 2 * P_TOL
+    flips = (a["accepted"] != b["accepted"]).cpu().numpy()
+    margin = np.abs(a["px"].cpu().numpy() - u.cpu().numpy())
+    assert not np.any(flips & (margin > 1e-4))
+
+
+def test_tc_specialised_kernel_follows_eps_and_temperature():
+    """The specialised kernel's pre-multiplied head constants depend on eps: l2hmc_set_eps must repack them; the
+    temperature enters through grad U and the Hamiltonian (utils/dynamics.py:203-212)."""
+    P = U.Problem(regime="stress", **U.CONFIGS["c2_scg50"])
+    from l2hmc_b200 import Dynamics
+    dyn = Dynamics(P.D, P.dist.get_energy_function(), T=P.T, eps=0.3, net_factory=P.net_factory(), use_temperature=True,
+                   kernel="tc")
+    dyn.mask = P.mask
+    dyn.eps = P.eps          # changed after the nets were packed
+    dyn.temperature = 1.7
+    d = P.draws(256)
+    o = P.oracle(torch.float64, temperature=1.7)
+    x, v = torch.as_tensor(d["x"]).cuda(), torch.as_tensor(d["v_f"]).cuda()
+    X, V, p = dyn.forward(x, init_v=v)
+    assert dyn.kernel_name == "tc_3xtf32"
+    Xo, Vo, po = o.forward(U.t64(d["x"]), U.t64(d["v_f"]))
+    assert U.max_rel(X.cpu().numpy(), Xo.numpy()) <= SAMPLE_TOL
+    assert U.max_rel(V.cpu().numpy(), Vo.numpy()) <= SAMPLE_TOL
+    assert float(np.max(np.abs(p.cpu().numpy() - po.numpy()))) <= P_TOL
+    Xb, Vb, pb = dyn.backward(x, init_v=v)
+    Xob, Vob, pob = o.backward(U.t64(d["x"]), U.t64(d["v_f"]))
+    assert U.max_rel(Xb.cpu().numpy(), Xob.numpy()) <= SAMPLE_TOL
+    assert float(np.max(np.abs(pb.cpu().numpy() - pob.numpy()))) <= P_TOL
+
+
 # ---- kernel selection: every kernel that covers a configuration must pass on it -------------------------
 @pytest.mark.parametrize("name,n,kernel", [
     ("c1_scg2", 200, "small"), ("c1_scg2", 200, "tile"),
