@@ -49,8 +49,9 @@ struct SDims {
   static constexpr int RS = (NQC & 1) ? DP : DP + 4;  // row stride with RS/4 odd: 8 lanes x 16 B hit 32 distinct banks
 };
 
+constexpr int HCS_PER_CHUNK = 20;  // shared-memory copy of the head constants: bs2, bq2, cS, cQ, bth (4 floats each)
 struct TcLayS {
-  int xs, vs, gs, smask, h0, su, sdir, sacc, part, ring;
+  int xs, vs, gs, smask, h0, su, sdir, sacc, part, hcs, ring;
 };
 __host__ __device__ inline TcLayS make_tclay_s(int RS, int DP, int T) {
   TcLayS l;
@@ -62,8 +63,9 @@ __host__ __device__ inline TcLayS make_tclay_s(int RS, int DP, int T) {
   l.su = l.h0 + MT;
   l.sdir = l.su + MT;
   l.sacc = l.sdir + MT;
-  l.part = l.sacc + MT;                      // [2][2][MT]: partial Hamiltonian, partial log|J|
-  l.ring = (l.part + 2 * 2 * MT + 31) & ~31;  // 128-byte aligned
+  l.part = l.sacc + MT;                      // [2][MT]: partial Hamiltonian, then partial log|J| (one after the other)
+  l.hcs = l.part + 2 * MT;                    // [2 nets][DP/4][HCS_PER_CHUNK]
+  l.ring = (l.hcs + 2 * (DP / 4) * HCS_PER_CHUNK + 31) & ~31;  // 128-byte aligned
   return l;
 }
 __host__ __device__ inline int tc_s_row_stride(int DP) { return ((DP / 4) & 1) ? DP : DP + 4; }
@@ -187,10 +189,13 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
   const uint32_t ring_u32 = smem_u32(ring);
   const uint32_t slot_bytes = SLOT_FLOATS * 4u;
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
-  long long w_a = 0, w_f = 0;
+  long long w_a = 0, w_f = 0, k_a[5] = {0, 0, 0, 0, 0}, k_f[5] = {0, 0, 0, 0, 0}, k_n[5] = {0, 0, 0, 0, 0};
   const long long t_begin = clock64();
 #endif
   walk_schedule_s(A, [&](int kind, int net) {
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+    const long long w_a0 = w_a, w_f0 = w_f;
+#endif
     const GemmDesc g = gemm_desc_s<NQC>(A, kind, net);
     const uint32_t acc = s_region(kind);
     const uint32_t idesc = make_idesc_tf32(128, g.n);
@@ -255,6 +260,15 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
     __syncwarp();
     ++gi;
     if (!nowait) ++ai;
+#ifdef L2HMC_TC_PHASE_ACCOUNTING
+#pragma unroll
+    for (int k = 0; k < 5; ++k)
+      if (k == kind) {
+        k_a[k] += w_a - w_a0;
+        k_f[k] += w_f - w_f0;
+        k_n[k] += 1;
+      }
+#endif
   });
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
   if (blockIdx.x == 0 && lane == 0) {
@@ -262,6 +276,11 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
     g_tc_dbg[1] = w_f;
     g_tc_dbg[2] = clock64() - t_begin;
     g_tc_dbg[5] = gi;
+    for (int k = 0; k < 5; ++k) {
+      g_tc_dbg[8 + k] = k_a[k];
+      g_tc_dbg[13 + k] = k_f[k];
+      g_tc_dbg[18 + k] = k_n[k];
+    }
   }
 #endif
 }
@@ -368,6 +387,14 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
     const float eps = sh.eps, Tm = A.en.temperature, rTm = 1.f / A.en.temperature;
 
     for (int i = tid; i < sh.T * DP; i += NCT) smem[L.smask + i] = A.mask[i];
+    // head constants of both nets into shared memory (X net first): as global loads their latency was ~18 % of the
+    // heads epilogue (first use right after the load, 2 warps per scheduler)
+    for (int i = tid; i < 2 * NQC * HCS_PER_CHUNK; i += NCT) {
+      const int net = i / (NQC * HCS_PER_CHUNK), r = i - net * NQC * HCS_PER_CHUNK;
+      const int q = r / HCS_PER_CHUNK, e = r - q * HCS_PER_CHUNK;  // e: 0-3 bs2, 4-7 bq2, 8-11 cS, 12-15 cQ, 16-19 bth
+      const int src = e < 8 ? e : (e < 12 ? e + 4 : (e < 16 ? e + 8 : e + 8));
+      smem[L.hcs + i] = (net ? A.vnet.hc : A.xnet.hc)[HC_PER_CHUNK * q + src];
+    }
     for (int i = tid; i < MT * DP; i += NCT) {
       const int ch = i / DP, d = i - ch * DP;
       const long long g = base + ch;
@@ -599,6 +626,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         constexpr uint32_t cS = PART == 0 ? S_R1 : S_R3 - 4 * CA;                 // S column of chunk q: cS + 4 q
         constexpr uint32_t cT = cS + 4 * CP, cQ = cS + 8 * CP;
         const float hc = MODE == 0 ? 0.5f * eps : eps;
+        const float *hcs_net = smem + L.hcs + (MODE == 0 ? NQC * HCS_PER_CHUNK : 0);  // V net (MODE 0) second
         const bool flip = (fwd != (xh == 0));  // MODE 1: k = m, or 1 - m when flipped
         const int na = (CA - qd + 1) / 2;      // this thread's chunks in part 0: i < na
         const int ib = PART == 0 ? 0 : na, ie = PART == 0 ? na : qn;
@@ -623,12 +651,10 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
           const int q = qd + 2 * i;
-          const float *hcq = N.hc + HC_PER_CHUNK * q;
-          const float4 c_bs = ldg4(hcq), c_bq = ldg4(hcq + 4), c_ns = ldg4(hcq + 8), c_cs = ldg4(hcq + 12);
-          const float4 c_nq = ldg4(hcq + 16), c_cq = ldg4(hcq + 20), c_bt = ldg4(hcq + 24);
+          const float *hcq = hcs_net + HCS_PER_CHUNK * q;
+          const float4 c_bs = lds4(hcq), c_bq = lds4(hcq + 4), c_cs = lds4(hcq + 8), c_cq = lds4(hcq + 12), c_bt = lds4(hcq + 16);
           const float bs2[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bq2[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
-          const float n2cS[4] = {c_ns.x, c_ns.y, c_ns.z, c_ns.w}, cSc[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w};
-          const float n2cQ[4] = {c_nq.x, c_nq.y, c_nq.z, c_nq.w}, cQc[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
+          const float cSc[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w}, cQc[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
           const float bth[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};
           const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), mv = lds4(mrow + 4 * q);
           float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
@@ -654,8 +680,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
               const float eQ = ex2_approx(fminf(fmaf(q4[B][j], 2.f * L2E, bq2[j]), 57.f));
               const float dS = eS + 1.f, dQ = eQ + 1.f;
               const float r = rcp_approx(dS * dQ);
-              svl = fmaf(r * dQ, n2cS[j], cSc[j]);
-              fql = fmaf(r * dS, n2cQ[j], cQc[j]);
+              svl = cSc[j] * fmaf(r * dQ, -2.f, 1.f);  // cS * tanh
+              fql = cQc[j] * fmaf(r * dS, -2.f, 1.f);
             } else {
               svl = cSc[j] * tanhf((s4[B][j] * (2.f * L2E) + bs2[j]) * (0.5f * LN2));
               fql = cQc[j] * tanhf((q4[B][j] * (2.f * L2E) + bq2[j]) * (0.5f * LN2));
@@ -736,12 +762,14 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       // ---- log|J|, Hamiltonian, accept ---------------------------------------------------------------
       compute_bar();  // h0 readers are done with `part`
       smem[L.part + qd * MT + c] = final_ham();
-      smem[L.part + (2 + qd) * MT + c] = ljl * LN2;
+      compute_bar();
+      const float h1 = smem[L.part + c] + smem[L.part + MT + c];
+      compute_bar();
+      smem[L.part + qd * MT + c] = ljl * LN2;
       compute_bar();
       const bool last = (tr == io.n_transitions - 1);
       if (qd == 0) {
-        const float h1 = smem[L.part + c] + smem[L.part + MT + c];
-        const float logj = smem[L.part + 2 * MT + c] + smem[L.part + 3 * MT + c];
+        const float logj = smem[L.part + c] + smem[L.part + MT + c];
         const float p = accept_prob(smem[L.h0 + c], h1, logj);
         const float px = io.log_jac ? logj : p;
         int acc = 0;

@@ -74,14 +74,19 @@ def timing(kernel):
                   (name, n, P.T, dyn.kernel_name, ms, n * P.T / (ms * 1e-3), float(o["px"].mean())), flush=True)
             if dyn.kernel_name.startswith("tc"):
                 import ctypes as C
-                buf = (C.c_int64 * 8)()
-                dyn._chk(dyn._lib.l2hmc_debug_counters(dyn._ctx, buf, 8))
+                buf = (C.c_int64 * 24)()
+                dyn._chk(dyn._lib.l2hmc_debug_counters(dyn._ctx, buf, 24))
                 c = list(buf)
                 if c[2] > 0 and c[4] > 0:
                     print("TCPHASE %-10s CTA0 cycles: issuer total=%d wait_A=%.1f%% wait_TMA=%.1f%% issue/MMA=%.1f%% | compute total=%d "
                           "wait_acc=%.1f%% | gemms=%d cycles/gemm=%.0f" %
                           (name, c[2], 100.0 * c[0] / c[2], 100.0 * c[1] / c[2], 100.0 * (c[2] - c[0] - c[1]) / c[2], c[4],
                            100.0 * c[3] / c[4], c[5], c[2] / max(c[5], 1)), flush=True)
+                    if sum(c[18:23]) > 0:
+                        names = ("grad", "embed", "hidden", "heads_a", "heads_b")
+                        print("TCKIND  %-10s per GEMM (cycles): " % name + "  ".join(
+                            "%s: wait_A=%.0f wait_TMA=%.0f (x%d)" % (names[k], c[8 + k] / max(c[18 + k], 1), c[13 + k] / max(c[18 + k], 1), c[18 + k])
+                            for k in range(5)), flush=True)
         except Exception:
             print("TIMING %s FAILED" % name)
             traceback.print_exc()
