@@ -109,9 +109,9 @@ __device__ __forceinline__ void put_a4s(uint32_t lane_base, int col, const float
 // GEMM kinds of this kernel: 0 grad (Gaussian), 1 embed, 2 hidden, 3 heads_a (first CA dimension chunks), 4 heads_b.
 // Where each accumulates and what it needs before its first MMA:
 //   embed -> R1, hidden -> R2, heads_a -> R1, heads_b -> R3, grad -> R2.  Consecutive GEMMs never share a region, the
-//   region a GEMM writes was last read by an epilogue that has finished, so every GEMM except grad (whose A operand
-//   x - mu is handed over whole) follows the epilogue before it K slot by K slot; heads_b reads the A operand heads_a
-//   has already waited for.
+//   region a GEMM writes was last read by an epilogue that has finished, so every GEMM follows the epilogue before it
+//   K slot by K slot (grad: K step by K step, x - mu has 4 columns per chunk); heads_b reads the A operand heads_a has
+//   already waited for.
 __device__ __forceinline__ uint32_t s_region(int kind) {
   return (kind == 1 || kind == 3) ? S_R1 : (kind == 4 ? S_R3 : S_R2);
 }
@@ -180,7 +180,7 @@ __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, 
 
 // ===================== MMA issuer of the overlapped schedule (one warp) =====================
 // As issuer_loop (uniform datapath, elect.sync), plus: the accumulator region per GEMM, the A operand awaited per K slot
-// (a_sub[si]; grad: whole, i.e. a_sub[nsub-1], on which every warp arrives last; heads_b: not at all), and two
+// (a_sub[K step / 2]; grad: a_sub[K step], its A operand has 4 columns per chunk; heads_b: not at all), and two
 // accumulator-ready barriers used alternately (heads_a and heads_b complete without an epilogue in between).
 template <int NQC>
 __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, uint64_t *a_sub, uint64_t *acc_rdy, int nsub, float *ring,
@@ -202,17 +202,7 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
     const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
     const uint32_t slab16 = (uint32_t)g.n * 2u;
     const uint32_t par = ai & 1u;
-    const bool whole = kind == 0, nowait = kind == 4;
-    if (whole) {
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-      const long long t0 = clock64();
-#endif
-      mbar_wait(&a_sub[nsub - 1], par);
-#ifdef L2HMC_TC_PHASE_ACCOUNTING
-      w_a += clock64() - t0;
-#endif
-      tcgen05_fence_after();
-    }
+    const bool grad = kind == 0, nowait = kind == 4;
 #pragma unroll 1
     for (int ks = 0; ks < g.nsteps; ks += KSLOT_S) {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
@@ -224,30 +214,26 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 #endif
       const uint32_t b16 = (ring_u32 + s * slot_bytes) >> 4;
 #pragma unroll
-      for (int k2 = 0; k2 < KSLOT_S; k2 += 2) {  // one A hand-over slot = 2 K steps
-        if (ks + k2 < g.nsteps) {
+      for (int kk = 0; kk < KSLOT_S; ++kk) {
+        if (ks + kk < g.nsteps) {
+          // A hand-over slot: 2 K steps (8 columns per chunk); grad: 1 K step (x - mu has 4 columns per chunk)
+          if (!nowait && (grad || (kk & 1) == 0)) {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
-          t0 = clock64();
+            t0 = clock64();
 #endif
-          if (!whole && !nowait) {
-            mbar_wait(&a_sub[(ks + k2) >> 1], par);
+            mbar_wait(&a_sub[grad ? ks + kk : (ks + kk) >> 1], par);
             tcgen05_fence_after();
-          }
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
-          w_a += clock64() - t0;
+            w_a += clock64() - t0;
 #endif
+          }
           if (elect_one()) {
-#pragma unroll
-            for (int kk = k2; kk < k2 + 2; ++kk) {
-              if (ks + kk < g.nsteps) {
-                const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
-                const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
-                const uint32_t ahi = S_AHI + 8u * (ks + kk), alo = S_ALO + 8u * (ks + kk);
-                mma_tf32_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
-                mma_tf32_ts(acc, ahi, dlo, idesc, true);
-                mma_tf32_ts(acc, ahi, dhi, idesc, true);
-              }
-            }
+            const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
+            const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
+            const uint32_t ahi = S_AHI + 8u * (ks + kk), alo = S_ALO + 8u * (ks + kk);
+            mma_tf32_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
+            mma_tf32_ts(acc, ahi, dlo, idesc, true);
+            mma_tf32_ts(acc, ahi, dhi, idesc, true);
           }
           __syncwarp();
         }
@@ -513,9 +499,10 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             const float4 xv = lds4(xr + 4 * q);
             const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
             put_xmu(q, x4);
+            slot_done(i);
           }
           zero_gtail();
-          a_done(0);
+          a_done(qn);
           grad_epilogue(S_R2, true, Hpart);
         } else {
           float U = 0.f, K = 0.f;
@@ -606,8 +593,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             for (int j = 0; j < 4; ++j) b[j] = (flip ? m4[j] : 1.f - m4[j]) * x4[j];
             put_ab(q, v4, b);
             slot_done(i);
-          } else if (gauss) {  // NEXT_G: grad U at the new x, handed over whole
+          } else if (gauss) {  // NEXT_G: grad U at the new x (K step i of the grad GEMM = the chunks i of both threads)
             put_xmu(q, x4);
+            slot_done(i);
           } else {
             float g[4];
             roughwell_grad(q, x4, g);
@@ -716,9 +704,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           if (i + 1 < ie) chunk(i + 1, I1{});
         }
         if (PART == 1) {
-          const bool handover = !(MODE == 1 && next == NEXT_G && gauss);  // x - mu for the grad GEMM goes over whole
-          if (!handover) zero_gtail();
-          if (next != NEXT_NONE) a_done(handover ? qn : 0);
+          if (MODE == 1 && next == NEXT_G && gauss) zero_gtail();  // before this warp's arrival on the last K step
+          if (next != NEXT_NONE) a_done(qn);
           else tcgen05_fence_before();
         } else {
           tcgen05_fence_before();

@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
-T=${TAG:-r16}
+T=${TAG:-r17}
 timeout -s KILL 240 python tools/gpu_diag.py --kernel tc > gpurun_out/${T}_diag.txt 2>&1; echo "rc=$?" >> gpurun_out/${T}_diag.txt
-L2HMC_LIB=$PWD/l2hmc_b200/libl2hmc_acct.so timeout -s KILL 120 python tools/gpu_diag.py --kernel tc --no-parity > gpurun_out/${T}_diag_acct.txt 2>&1
+timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tc or golden or full_size" > gpurun_out/${T}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.txt
