@@ -44,6 +44,7 @@ struct TcDims {
   int slot_floats;  // KSLOT * 16 * max(N1, N3): KSLOT K=8 steps of the widest GEMM, hi + lo slabs each
   int fast_math;    // 1: ex2/rcp based exp and tanh in the epilogue (abs error ~1e-7)
   int nq;           // compute threads per chain (2 or 4) -> which instantiation the host launches
+  int biasg;        // kernel_tc_s: biases ride in the GEMMs (weight rows that meet constant-1 / one-hot A columns)
 };
 
 struct TcNet {
@@ -53,6 +54,7 @@ struct TcNet {
   const float *bh;   // [N3]  (S | T | Q blocks)
   const float *es, *eq;  // [DP]
   const float *img_s;    // the same chunk stream with the embed rows interleaved per 4-dim chunk (kernel_tc_s.cuh)
+  const float *emb_last; // [T] chunks: last embed K step with the time-embedding bias rows of each leapfrog step (biasg)
   const float *hc;       // [DP/4][28]: pre-multiplied heads constants of the specialised kernel (kernel_tc_s.cuh)
 };
 

@@ -120,16 +120,16 @@ template <class F>
 __device__ __forceinline__ void walk_schedule_s(const TcArgs &A, F &&f) {
   const bool gauss = A.en.kind == 0;
   for (int tr = 0; tr < A.io.n_transitions; ++tr) {
-    if (gauss) f(0, 0);
+    if (gauss) f(0, 0, 0);
     for (int it = 0; it < A.sh.T; ++it) {
 #pragma unroll 1
       for (int j = 0; j < 17; ++j) {
         if (j == 12) {
-          if (gauss) f(0, 0);
+          if (gauss) f(0, 0, it);
           continue;
         }
         const int jj = j > 12 ? j - 1 : j;  // 0..15
-        f((jj & 3) + 1, (jj < 4 || jj >= 12) ? 1 : 0);
+        f((jj & 3) + 1, (jj < 4 || jj >= 12) ? 1 : 0, it);
       }
     }
   }
@@ -162,7 +162,7 @@ __device__ __forceinline__ GemmDesc gemm_desc_s(const TcArgs &A, int kind, int n
 template <int NQC>
 __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, float *ring, uint32_t NSLOT, uint32_t SLOT_FLOATS) {
   uint32_t s = 0, ph = 1;
-  walk_schedule_s(A, [&](int kind, int net) {
+  walk_schedule_s(A, [&](int kind, int net, int it) {
     const GemmDesc g = gemm_desc_s<NQC>(A, kind, net);
 #pragma unroll 1
     for (int ks = 0; ks < g.nsteps; ks += KSLOT_S) {
@@ -170,7 +170,17 @@ __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, 
       mbar_wait_sleep(&S.empty[s], ph);
       if (elect_one()) {
         mbar_arrive_expect_tx(&S.full[s], bytes);
-        bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
+        const int nk = min(KSLOT_S, g.nsteps - ks);
+        if (A.td.biasg && kind == 1 && ks + nk == g.nsteps) {
+          // the last K step of the embed carries the time-embedding bias rows of leapfrog step `it` (forward and
+          // backward chains): it comes from the per-step image, the K steps before it from the common stream
+          const uint32_t cb = (uint32_t)g.chunk_floats * 4u;
+          if (nk > 1) bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, cb * (uint32_t)(nk - 1), &S.full[s]);
+          bulk_g2s(ring + (size_t)s * SLOT_FLOATS + (size_t)(nk - 1) * g.chunk_floats,
+                   (net ? A.vnet : A.xnet).emb_last + (size_t)it * g.chunk_floats, cb, &S.full[s]);
+        } else {
+          bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
+        }
       }
       __syncwarp();
       if (++s == NSLOT) { s = 0; ph ^= 1u; }
@@ -192,7 +202,7 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
   long long w_a = 0, w_f = 0, k_a[5] = {0, 0, 0, 0, 0}, k_f[5] = {0, 0, 0, 0, 0}, k_n[5] = {0, 0, 0, 0, 0};
   const long long t_begin = clock64();
 #endif
-  walk_schedule_s(A, [&](int kind, int net) {
+  walk_schedule_s(A, [&](int kind, int net, int) {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
     const long long w_a0 = w_a, w_f0 = w_f;
 #endif
@@ -274,7 +284,7 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 // what the heads epilogue prepares for the GEMM that follows it
 enum { NEXT_NONE = 0, NEXT_X1 = 1, NEXT_X2 = 2, NEXT_G = 3, NEXT_V = 4 };
 
-template <int NQC, int NHC, bool FAST>
+template <int NQC, int NHC, bool FAST, bool BIASG>
 __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const __grid_constant__ TcArgs A) {
   constexpr int NCT = MT * 2;  // compute threads: 2 per chain
   constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
@@ -427,8 +437,14 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
 
       // ---- A operands ------------------------------------------------------------------------------------
       // net input of one 4-dim chunk: [a0..3 | b0..3] = K step q of the embed GEMM (weight rows permuted to match)
+      // BIASG: the two pad dimensions of the last chunk's a-part select the time-embedding bias row of this chain's
+      // direction in the embed weights ([1, 0] forward, [0, 1] backward), see tc_pack_net
       auto put_ab = [&](int q, const float (&a)[4], const float (&b)[4]) {
-        const float ab[8] = {a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]};
+        float ab[8] = {a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]};
+        if (BIASG && q == NQC - 1) {
+          ab[2] = fwd ? 1.f : 0.f;
+          ab[3] = fwd ? 0.f : 1.f;
+        }
         put_a8(lb, 8 * q, ab);
       };
       // Gaussian grad GEMM input x - mu of one chunk (the K tail beyond DP is zeroed once per GEMM by zero_gtail)
@@ -545,7 +561,11 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
           const int q = qd + 2 * i;
-          const float4 b0 = ldg4(bias + 8 * q), b1 = ldg4(bias + 8 * q + 4);
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (!BIASG) {  // BIASG: the bias is a weight row that meets a constant-1 column of the A operand
+            b0 = ldg4(bias + 8 * q);
+            b1 = ldg4(bias + 8 * q + 4);
+          }
           tmem_wait_ld();
           if (i + 1 < hn) tmem_ld8(lb + acc + 8 * (q + 2), h[B ^ 1]);
           const float(&hh)[8] = h[B];
@@ -640,7 +660,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           constexpr int B = decltype(buf_c)::value;
           const int q = qd + 2 * i;
           const float *hcq = hcs_net + HCS_PER_CHUNK * q;
-          const float4 c_bs = lds4(hcq), c_bq = lds4(hcq + 4), c_cs = lds4(hcq + 8), c_cq = lds4(hcq + 12), c_bt = lds4(hcq + 16);
+          const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 c_bs = BIASG ? z4 : lds4(hcq), c_bq = BIASG ? z4 : lds4(hcq + 4), c_cs = lds4(hcq + 8), c_cq = lds4(hcq + 12);
+          const float4 c_bt = BIASG ? z4 : lds4(hcq + 16);
           const float bs2[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bq2[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
           const float cSc[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w}, cQc[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
           const float bth[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};

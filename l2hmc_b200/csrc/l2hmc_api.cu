@@ -316,6 +316,9 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   td.fast_math = (fm && fm[0] == '0') ? 0 : 1;
   const char *nqe = getenv("L2HMC_TC_NQ");
   td.nq = (nqe && nqe[0] >= '2' && nqe[0] <= '4') ? (nqe[0] - '0') : 2;
+  // kernel_tc_s: biases as weight rows (needs two pad dimensions in the last 4-dim chunk and a pad hidden unit)
+  const char *bg = getenv("L2HMC_TC_BIASG");
+  td.biasg = (!(bg && bg[0] == '0') && sh.D <= sh.DP - 2 && sh.H <= td.HK - 1) ? 1 : 0;
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
 }
 
@@ -341,27 +344,56 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
     return W[(size_t)k * D + d];
   });
   // the specialised kernel (kernel_tc_s.cuh): net input interleaved per 4-dim chunk (K step q = [a_{4q..4q+3} | b_{4q..4q+3}]),
-  // heads split by dimensions into heads_a (first CA chunks) and heads_b (the rest), each with S | T | Q column blocks
-  std::vector<float> img_s;
-  append_b_stream(img_s, td.K1, td.N1, [&](int k, int n) -> float {
+  // heads split by dimensions into heads_a (first CA chunks) and heads_b (the rest), each with S | T | Q column blocks.
+  // biasg: the biases ride in the GEMMs.  Hidden unit H (a pad column) is the constant 1: the embed produces it from the
+  // direction one-hot the kernel puts into the pad dimensions DP-2 / DP-1 of the a-part (rows kf / kb of the last K
+  // step, which also carry the time-embedding bias row of the chain's step: tb[it] forward, tb[T-1-it] backward -> one
+  // image of that K step per leapfrog step, `emb_last`), the hidden layer passes it on and adds b4, the heads add bs/bt/bq.
+  const bool biasg = td.biasg != 0;
+  const int kf = td.K1 - 6, kb = td.K1 - 5;  // K rows of the a-part pad dimensions DP-2, DP-1 in the interleaved order
+  auto embed_w = [&](int k, int n) -> float {
     if (n >= H) return 0.f;
     const int d = 4 * (k / 8) + (k & 3);
     if (d >= D) return 0.f;
     return ((k & 7) < 4 ? p->W1 : p->W2)[(size_t)d * H + n];
+  };
+  auto tb_at = [&](int t, int j) -> float {
+    const float arg = 6.2831855f * (float)t / (float)T;  // utils/dynamics.py:99-105 in fp32
+    const float ct = cosf(arg), st = sinf(arg);
+    return (p->b1[j] + p->b2[j]) + (fmaf(st, p->W3[H + j], ct * p->W3[j]) + p->b3[j]);
+  };
+  std::vector<float> img_s;
+  append_b_stream(img_s, td.K1, td.N1, embed_w);
+  append_b_stream(img_s, td.HK, td.N1, [&](int k, int n) -> float {
+    if (biasg && k == H) return n < H ? p->b4[n] : (n == H ? 1.f : 0.f);
+    return (k < H && n < H) ? p->W4[(size_t)k * H + n] : 0.f;
   });
-  append_b_stream(img_s, td.HK, td.N1, [&](int k, int n) -> float { return (k < H && n < H) ? p->W4[(size_t)k * H + n] : 0.f; });
   {
     const int nqc = DP / 4, ca = (nqc + 1) / 2, cb = nqc - ca;
     for (int part = 0; part < 2; ++part) {
       const int cp = part == 0 ? ca : cb, d0 = part == 0 ? 0 : 4 * ca, np = round_up(12 * cp, 16);
       if (cp == 0) continue;
       append_b_stream(img_s, td.HK, np, [&](int k, int n) -> float {
-        if (k >= H || n >= 12 * cp) return 0.f;
+        if (k > H || (k == H && !biasg) || n >= 12 * cp) return 0.f;
         const int blk = n / (4 * cp), d = d0 + n - blk * 4 * cp;
         if (d >= D) return 0.f;
+        if (k == H) return (blk == 0 ? p->bs : (blk == 1 ? p->bt : p->bq))[d];
         const float *W = blk == 0 ? p->Ws : (blk == 1 ? p->Wt : p->Wq);
         return W[(size_t)k * D + d];
       });
+    }
+  }
+  const size_t nstream_s = img_s.size();
+  if (biasg) {  // per leapfrog step: the last K step of the embed with the bias rows
+    for (int t = 0; t < T; ++t) {
+      std::vector<float> one;
+      append_b_stream(one, 8, td.N1, [&](int kk, int n) -> float {
+        const int k = td.K1 - 8 + kk;
+        if (k == kf) return n < H ? tb_at(t, n) : (n == H ? 1.f : 0.f);
+        if (k == kb) return n < H ? tb_at(T - 1 - t, n) : (n == H ? 1.f : 0.f);
+        return embed_w(k, n);
+      });
+      img_s.insert(img_s.end(), one.begin(), one.end());
     }
   }
   const size_t nimg_s = img_s.size();
@@ -397,6 +429,7 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
   n.es = n.bh + nbh;
   n.eq = n.es + nes;
   n.img_s = n.eq + nes;
+  n.emb_last = biasg ? n.img_s + nstream_s : nullptr;
   std::vector<float> &raw = ctx->tc_head_raw[net_id];
   raw.assign((size_t)5 * DP, 0.f);
   for (int d = 0; d < D; ++d) {
@@ -423,7 +456,7 @@ static int tc_pack_hc(l2hmc_ctx *ctx, int net_id) {
     float *c = hc.data() + (size_t)(d / 4) * tc::HC_PER_CHUNK + (d & 3);
     const double bs = raw[d], bt = raw[DP + d], bq = raw[2 * DP + d], es = raw[3 * DP + d], eq = raw[4 * DP + d];
     const double cS = es * h * L2E, cQ = eq * eps * L2E;
-    c[0] = (float)(bs * 2.0 * L2E);
+    c[0] = (float)(bs * 2.0 * L2E);  // (the bias entries are unused when the biases ride in the GEMMs, td.biasg)
     c[4] = (float)(bq * 2.0 * L2E);
     c[8] = (float)(-2.0 * cS);
     c[12] = (float)cS;
@@ -936,19 +969,28 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       const size_t smem = tc::tc_s_smem_bytes(ctx->sh.DP, ctx->sh.T, TA.td.nslot, TA.td.slot_floats);
       static thread_local size_t tc_s_configured = 0;
       if (smem > tc_s_configured) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         tc_s_configured = smem;
       }
       const unsigned nthreads = (unsigned)(tc::MT * 2 + 64);
+      const bool fm = ctx->td.fast_math != 0, bg = ctx->td.biasg != 0;
       if (nqc == 13) {
-        if (ctx->td.fast_math) tc::tc_transition_kernel_s<13, 13, true><<<blocks, nthreads, smem, stream>>>(TA);
-        else tc::tc_transition_kernel_s<13, 13, false><<<blocks, nthreads, smem, stream>>>(TA);
+        if (bg) {
+          if (fm) tc::tc_transition_kernel_s<13, 13, true, true><<<blocks, nthreads, smem, stream>>>(TA);
+          else tc::tc_transition_kernel_s<13, 13, false, true><<<blocks, nthreads, smem, stream>>>(TA);
+        } else {
+          if (fm) tc::tc_transition_kernel_s<13, 13, true, false><<<blocks, nthreads, smem, stream>>>(TA);
+          else tc::tc_transition_kernel_s<13, 13, false, false><<<blocks, nthreads, smem, stream>>>(TA);
+        }
       } else {
-        if (ctx->td.fast_math) tc::tc_transition_kernel_s<8, 13, true><<<blocks, nthreads, smem, stream>>>(TA);
-        else tc::tc_transition_kernel_s<8, 13, false><<<blocks, nthreads, smem, stream>>>(TA);
+        if (bg) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: no bias-in-GEMM instantiation for this shape");
+        if (fm) tc::tc_transition_kernel_s<8, 13, true, false><<<blocks, nthreads, smem, stream>>>(TA);
+        else tc::tc_transition_kernel_s<8, 13, false, false><<<blocks, nthreads, smem, stream>>>(TA);
       }
     } else {
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
