@@ -1,5 +1,12 @@
+# Round evidence: GPU tests, smoke, bench (both arms), ncu launch list and one full capture of the dominant kernel.
 mkdir -p gpurun_out
-T=${TAG:-r18}
-timeout -s KILL 240 python tools/gpu_diag.py --kernel tc > gpurun_out/${T}_diag.txt 2>&1; echo "rc=$?" >> gpurun_out/${T}_diag.txt
-L2HMC_TC_BIASG=0 timeout -s KILL 240 python tools/gpu_diag.py --kernel tc --no-parity > gpurun_out/${T}_diag_nobg.txt 2>&1
-timeout -s KILL 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "tc or golden or full_size" > gpurun_out/${T}_pytest.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.txt
+T=${TAG:-final}
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.txt
+timeout -s KILL 600 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest_gpu.txt 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest_gpu.txt
+timeout -s KILL 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.txt 2>&1; echo "smoke rc=$?" >> gpurun_out/${T}_smoke.txt
+timeout -s KILL 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${T}_bench_reference.json 2> gpurun_out/${T}_bench_reference.err
+timeout -s KILL 300 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_launches.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tc_transition -s 3 -c 1 -f -o gpurun_out/${T}_prof python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu.log 2>&1
+L2HMC_LIB=$PWD/l2hmc_b200/libl2hmc_acct.so timeout -s KILL 120 python tools/gpu_diag.py --kernel tc --no-parity > gpurun_out/${T}_phase_accounting.txt 2>&1
+timeout -s KILL 300 python tools/gpu_diag.py > gpurun_out/${T}_parity_timing.txt 2>&1
