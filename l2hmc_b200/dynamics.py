@@ -212,6 +212,15 @@ class Dynamics(object):
             n, w, Wp, bp = self._mlp_args(*self._aux_encoder)
             self._chk(self._lib.l2hmc_set_aux_encoder(self._ctx, n, w, Wp, bp))
 
+    def set_energy_function(self, energy_function):
+        """Replace the target of an existing Dynamics (same kind of descriptor, same dimension): the annealed energy of
+        utils/ais.py:44-58 changes at every step while the leapfrog operator stays."""
+        if not hasattr(energy_function, "kind") or energy_function.dim != self.x_dim:
+            raise TypeError("set_energy_function needs a closed-form %d-d energy" % self.x_dim)
+        self._fn = energy_function
+        if self._ctx is not None:
+            self._push_energy()
+
     def refresh(self):
         """Re-read XNet/VNet weights from the layer objects (after loading a checkpoint into them)."""
         if not self.hmc:

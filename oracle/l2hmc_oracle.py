@@ -598,3 +598,53 @@ def ESS(A):
     """utils/func_utils.py:118-120."""
     A = A * (A > 0.05)
     return 1. / (1. + 2 * np.sum(A[1:]))
+
+
+# --------------------------------------------------------------------------------------
+# Annealed importance sampling (utils/ais.py:30-82), HMC-mode Dynamics inside a scan over beta
+# --------------------------------------------------------------------------------------
+class MixedEnergy(Energy):
+    """curr_energy of utils/ais.py:44-45: (1 - beta) * init_energy(z) + beta * final_energy(z)."""
+
+    def __init__(self, e0: Energy, e1: Energy, beta: float):
+        self.e0, self.e1, self.beta = e0, e1, float(beta)
+
+    def to(self, dtype):
+        return MixedEnergy(self.e0.to(dtype), self.e1.to(dtype), self.beta)
+
+    def energy(self, x):
+        return (1.0 - self.beta) * self.e0.energy(x) + self.beta * self.e1.energy(x)
+
+    def grad(self, x):
+        return (1.0 - self.beta) * self.e0.grad(x) + self.beta * self.e1.grad(x)
+
+
+def ais_estimate(e0: Energy, e1: Energy, anneal_steps: int, initial_x, *, step_size, leapfrogs, v0, v_refresh, u,
+                 num_splits=1, refresh=False, refreshment=0.1, dtype=torch.float64):
+    """ais_estimate (utils/ais.py:30-82) with all randomness injected: v0 [N, D] (the scan's initial momentum, used
+    only when refresh=True), v_refresh [steps, N, D] normals, u [steps, N] uniforms.
+    Returns (log-mean-exp of the weights per split summed, mean accept probability, final x, final w)."""
+    x = torch.as_tensor(np.asarray(initial_x)).to(dtype)
+    n, D = x.shape
+    w = torch.zeros((n,), dtype=dtype)
+    v = torch.as_tensor(np.asarray(v0)).to(dtype)
+    e0, e1 = e0.to(dtype), e1.to(dtype)
+    # beta = linspace(0, 1, steps + 1)[1:], beta_diff = beta[1] - beta[0] in fp32 like tf.linspace (utils/ais.py:43-44)
+    beta = np.linspace(0.0, 1.0, anneal_steps + 1, dtype=np.float32)[1:]
+    beta_diff = float(beta[1] - beta[0]) if anneal_steps > 1 else float(beta[0])
+    alphas = []
+    for s in range(anneal_steps):
+        z = torch.as_tensor(np.asarray(v_refresh[s])).to(dtype)
+        rv = v * math.sqrt(1.0 - refreshment) + z * math.sqrt(refreshment) if refresh else z
+        w = w + beta_diff * (-e1.energy(x) + e0.energy(x))
+        dyn = OracleDynamics(D, leapfrogs, step_size, MixedEnergy(e0, e1, float(beta[s])), np.zeros((leapfrogs, D), np.float32),
+                             hmc=True, dtype=dtype)
+        Lx, Lv, px = dyn.forward(x, rv)
+        mask = (px - torch.as_tensor(np.asarray(u[s])).to(dtype)) >= 0.0
+        x = torch.where(mask[:, None], Lx, x)
+        v = torch.where(mask[:, None], Lv, -Lv)
+        alphas.append(px)
+    lme = lambda zz: torch.logsumexp(zz, 0) - math.log(zz.shape[0])  # noqa: E731
+    parts = torch.chunk(w, num_splits, dim=0)
+    est = sum(lme(p) for p in parts)
+    return est, torch.stack(alphas).mean(), x, w

@@ -465,3 +465,38 @@ def test_small_kernel_multi_transition_and_generic_size():
     assert d2.kernel_name == "small_fma"
     rep, _ = U.parity_report(P2, 150, dyn=d2)
     _check(rep)
+
+
+# ---- annealed importance sampling (utils/ais.py) on the HMC-mode kernels --------------------------------
+@pytest.mark.parametrize("D,refresh", [(3, False), (6, True)])
+def test_ais_estimate_matches_oracle(D, refresh):
+    """ais_estimate (Gaussian -> Gaussian) against the fp64 restatement with the same injected randomness: weights,
+    final particles, estimate and mean accept probability; D=3 runs the chain-per-thread kernel, D=6 the tile kernel."""
+    from l2hmc_b200.ais import ais_estimate
+    from l2hmc_b200.distributions import Gaussian
+    n, steps, L, eps = 384, 12, 5, 0.25
+    rng = np.random.default_rng(3)
+    A = rng.standard_normal((D, D))
+    cov1 = A @ A.T / D + 0.3 * np.eye(D)
+    mu1 = rng.standard_normal(D) * 0.5
+    g0, g1 = Gaussian(np.zeros(D), np.eye(D)), Gaussian(mu1, cov1)
+    e0 = U.O.GaussianEnergy(np.zeros(D), g0.i_sigma)
+    e1 = U.O.GaussianEnergy(mu1, g1.i_sigma)
+    r = {"v0": rng.standard_normal((n, D)).astype(np.float32), "v": rng.standard_normal((steps, n, D)).astype(np.float32),
+         "u": rng.random((steps, n)).astype(np.float32)}
+    x0 = rng.standard_normal((n, D)).astype(np.float32)
+    est_o, alpha_o, x_o, w_o = U.O.ais_estimate(e0, e1, steps, x0, step_size=eps, leapfrogs=L, v0=r["v0"], v_refresh=r["v"],
+                                                u=r["u"], refresh=refresh, num_splits=4)
+    est, alpha, x, w = ais_estimate(g0.get_energy_function(), g1.get_energy_function(), steps, torch.as_tensor(x0).cuda(),
+                                    step_size=eps, leapfrogs=L, x_dim=D, num_splits=4, refresh=refresh, rng=r, return_state=True)
+    # a Metropolis decision may flip where |p - u| is inside fp32 noise: compare the chains that agree on every decision
+    same = np.abs(x.cpu().numpy() - x_o.numpy()).max(1) < 1e-3
+    assert same.mean() > 0.99
+    assert U.max_rel(x.cpu().numpy()[same], x_o.numpy()[same]) <= 5e-5
+    assert float(np.abs(w.cpu().numpy()[same] - w_o.numpy()[same]).max()) <= 2e-4
+    assert abs(alpha - float(alpha_o)) <= 1e-4
+    if same.all():
+        assert abs(est - float(est_o)) <= 1e-3
+    with pytest.raises(NotImplementedError):
+        from l2hmc_b200.distributions import RoughWell
+        ais_estimate(g0.get_energy_function(), RoughWell(D, 0.1).get_energy_function(), 2, torch.as_tensor(x0).cuda(), x_dim=D)

@@ -256,3 +256,30 @@ def test_diagnostics_on_a_known_process():
     lags = np.arange(1, 60)
     expect = 1.0 / (1.0 + 2.0 * np.sum((a ** lags)[a ** lags > 0.05]))
     assert abs(ess - expect) / expect < 0.05
+
+
+def _ais_problem(D=3, seed=0):
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((D, D))
+    cov1 = A @ A.T / D + 0.3 * np.eye(D)
+    mu1 = rng.standard_normal(D) * 0.5
+    S0 = np.eye(D)
+    S1 = np.linalg.inv(cov1)
+    e0 = U.O.GaussianEnergy(np.zeros(D), S0)
+    e1 = U.O.GaussianEnergy(mu1, S1)
+    log_ratio = -0.5 * (np.linalg.slogdet(S1)[1] - np.linalg.slogdet(S0)[1])  # log Z1 / Z0 of exp(-U)
+    return e0, e1, mu1, cov1, log_ratio
+
+
+def test_ais_oracle_recovers_the_normaliser_ratio():
+    """utils/ais.py:30-82 restated: annealing N(0, I) -> N(mu1, cov1) estimates log Z1/Z0 = 0.5 log det(cov1)."""
+    D, n, steps, L = 3, 4000, 40, 5
+    e0, e1, mu1, cov1, log_ratio = _ais_problem(D)
+    rng = np.random.default_rng(1)
+    x0 = rng.standard_normal((n, D))
+    est, alpha, x, w = U.O.ais_estimate(e0, e1, steps, x0, step_size=0.3, leapfrogs=L, v0=rng.standard_normal((n, D)),
+                                        v_refresh=rng.standard_normal((steps, n, D)), u=rng.random((steps, n)))
+    assert abs(float(est) - log_ratio) < 0.1, (float(est), log_ratio)
+    assert 0.5 < float(alpha) <= 1.0
+    # the final particles target N(mu1, cov1) (weights aside: close already, the annealing is slow)
+    assert np.abs(x.numpy().mean(0) - mu1).max() < 0.15
