@@ -44,6 +44,7 @@ struct TcDims {
   int slot_floats;  // KSLOT * 16 * max(N1, N3): KSLOT K=8 steps of the widest GEMM, hi + lo slabs each
   int fast_math;    // 1: ex2/rcp based exp and tanh in the epilogue (abs error ~1e-7)
   int nq;           // compute threads per chain (2 or 4) -> which instantiation the host launches
+  int f16;          // kernel_tc_s: fp16 split instead of tf32 (all operands inside the fp16 range)
   int biasg;        // kernel_tc_s: biases ride in the GEMMs (weight rows that meet constant-1 / one-hot A columns)
 };
 
@@ -54,6 +55,7 @@ struct TcNet {
   const float *bh;   // [N3]  (S | T | Q blocks)
   const float *es, *eq;  // [DP]
   const float *img_s;    // the same chunk stream with the embed rows interleaved per 4-dim chunk (kernel_tc_s.cuh)
+  const float *img_h, *emb_last_h;  // fp16 twins of img_s / emb_last (kernel_tc_s, F16)
   const float *emb_last; // [T] chunks: last embed K step with the time-embedding bias rows of each leapfrog step (biasg)
   const float *hc;       // [DP/4][28]: pre-multiplied heads constants of the specialised kernel (kernel_tc_s.cuh)
 };
@@ -63,6 +65,7 @@ struct TcArgs {
   TcDims td;
   TcNet xnet, vnet;
   const float *gimg;  // Gaussian: Ssym chunk stream (KG/8 chunks of 2*NG*8 floats)
+  const float *gimg_h;  // its fp16 twin (K steps of 16)
   EnergyDev en;
   const float *mask;  // [T][DP]
   TransitionIO io;
@@ -164,7 +167,7 @@ struct Sync {
 // Phase accounting of CTA 0 (clock64 cycles), read back through l2hmc_debug_counters():
 // [0] issuer: waiting for A operands (tensor pipe idle, compute warps busy)   [1] issuer: waiting for TMA data
 // [2] issuer: total   [3] compute thread 0: waiting for accumulators   [4] compute thread 0: total   [5] GEMMs issued
-__device__ long long g_tc_dbg[24];  // [8..12] wait-for-A per GEMM kind, [13..17] wait-for-TMA per kind, [18..22] GEMMs per kind (kernel_tc_s)
+__device__ long long g_tc_dbg[24];  // [8..12] wait-for-A per GEMM kind, [13..17] wait-for-TMA per kind, [18..22] GEMMs per kind (kernel_tc_s), [23] fp16 range flag
 
 // ---- the GEMM schedule, walked identically by the producer, the MMA issuer and (structurally) the compute warps
 // kind: 0 = grad (Gaussian), 1 = embed, 2 = hidden, 3 = heads ; net: 0 = X, 1 = V

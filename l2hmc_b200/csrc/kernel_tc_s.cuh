@@ -23,8 +23,14 @@
 //     (embed / heads_a: R1, hidden / grad: R2, heads_b: R3), and the state update of the first half runs while the
 //     tensor pipe works on the second.  The A operand of the next GEMM is written during the second half's
 //     epilogue only (for all chunks), so nothing overwrites A while heads_b still reads it.
+//   * F16 = true: the same split with fp16 pairs instead of tf32 (a = a_hi + a_lo, b = b_hi + b_lo as fp16; three
+//     kind::f16 MMAs per product, each covering K = 16 in the cycles a tf32 MMA needs for K = 8: half the tensor time;
+//     measured error 5.9e-7 relative, profiles/r01_f16_probe.txt).  Two fp16 share a 32-bit TMEM column (low half = lower
+//     k), the B images hold fp16.  fp16 stops at 65504: the host keeps tf32 when a weight is out of range, the kernel
+//     records operand magnitudes and raises a sticky flag (l2hmc_debug_counters[23]) when an activation was.
 // Shapes without an instantiation run the generic kernel of kernel_tc.cuh.
 #pragma once
+#include <cuda_fp16.h>
 #include "kernel_tc.cuh"
 
 namespace l2hmc {
@@ -84,26 +90,71 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
-// split 8 values into tf32 hi / lo (see put_a4) and store them at column `col` of this warp's TMEM lanes
-__device__ __forceinline__ void put_a8(uint32_t lane_base, int col, const float (&a)[8]) {
-  float hi[8], lo[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    hi[j] = __uint_as_float(__float_as_uint(a[j]) & 0xFFFFE000u);
-    lo[j] = a[j] - hi[j];
-  }
-  tmem_st8(S_AHI + lane_base + col, hi);
-  tmem_st8(S_ALO + lane_base + col, lo);
+__device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
-__device__ __forceinline__ void put_a4s(uint32_t lane_base, int col, const float (&a)[4]) {
-  float hi[4], lo[4];
+__device__ __forceinline__ void tmem_st2u(uint32_t taddr, const uint32_t (&v)[2]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1,%2};" ::"r"(taddr), "r"(v[0]), "r"(v[1]) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float k_even, float k_odd) {  // low half = lower k (profiles/r01_f16_probe.txt)
+  const __half2 h = __floats2half2_rn(k_even, k_odd);
+  return *reinterpret_cast<const uint32_t *>(&h);
+}
+// tcgen05.mma kind::f16 (fp16 inputs, fp32 accumulate): D[tmem] (+)= A[tmem] * B[smem]^T, one K = 16 slice
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);  // A / B format 0 = f16, D format 1 = f32
+}
+__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+
+// split N values a[k0 .. k0+N) of the A operand into hi / lo and store them in this warp's TMEM lanes.
+//   tf32: hi = a with the 13 low mantissa bits cleared, lo = a - hi (see put_a4); one 32-bit column per k.
+//   fp16: the same hi (11 significant bits: exactly an fp16 inside its normal range) and lo, rounded to fp16 and packed
+//         two per column (column k / 2); amax tracks |a| for the range check (fp16 overflows at 65504).
+template <bool F16, int N>
+__device__ __forceinline__ void put_a(uint32_t lane_base, int k0, const float (&a)[N], float &amax) {
+  static_assert(N == 4 || N == 8, "4 or 8 values");
+  float hi[N], lo[N];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
+  for (int j = 0; j < N; ++j) {
     hi[j] = __uint_as_float(__float_as_uint(a[j]) & 0xFFFFE000u);
     lo[j] = a[j] - hi[j];
   }
-  tmem_st4(S_AHI + lane_base + col, hi);
-  tmem_st4(S_ALO + lane_base + col, lo);
+  if (F16) {
+    uint32_t h2[N / 2], l2[N / 2];
+#pragma unroll
+    for (int j = 0; j < N / 2; ++j) {
+      h2[j] = pack_h2(hi[2 * j], hi[2 * j + 1]);
+      l2[j] = pack_h2(lo[2 * j], lo[2 * j + 1]);
+      amax = fmaxf(amax, fmaxf(fabsf(a[2 * j]), fabsf(a[2 * j + 1])));
+    }
+    if (N == 8) {
+      const uint32_t h4[4] = {h2[0], h2[1], h2[2], h2[3]}, l4[4] = {l2[0], l2[1], l2[2], l2[3]};
+      tmem_st4u(S_AHI + lane_base + k0 / 2, h4);
+      tmem_st4u(S_ALO + lane_base + k0 / 2, l4);
+    } else {
+      const uint32_t hh[2] = {h2[0], h2[1]}, ll[2] = {l2[0], l2[1]};
+      tmem_st2u(S_AHI + lane_base + k0 / 2, hh);
+      tmem_st2u(S_ALO + lane_base + k0 / 2, ll);
+    }
+  } else {
+    if (N == 8) {
+      const float h8[8] = {hi[0], hi[1], hi[2], hi[3], hi[4], hi[5], hi[6], hi[7]}, l8[8] = {lo[0], lo[1], lo[2], lo[3], lo[4], lo[5], lo[6], lo[7]};
+      tmem_st8(S_AHI + lane_base + k0, h8);
+      tmem_st8(S_ALO + lane_base + k0, l8);
+    } else {
+      const float h4[4] = {hi[0], hi[1], hi[2], hi[3]}, l4[4] = {lo[0], lo[1], lo[2], lo[3]};
+      tmem_st4(S_AHI + lane_base + k0, h4);
+      tmem_st4(S_ALO + lane_base + k0, l4);
+    }
+  }
 }
 
 // GEMM kinds of this kernel: 0 grad (Gaussian), 1 embed, 2 hidden, 3 heads_a (first CA dimension chunks), 4 heads_b.
@@ -134,36 +185,40 @@ __device__ __forceinline__ void walk_schedule_s(const TcArgs &A, F &&f) {
     }
   }
 }
-// chunk stream of a GEMM in the specialised image [embed (interleaved rows) | hidden | heads_a | heads_b]
-template <int NQC>
+// chunk stream of a GEMM in the specialised image [embed (interleaved rows) | hidden | heads_a | heads_b]; one chunk =
+// one MMA K step (8 k in tf32, 16 k in fp16) = {hi slab, lo slab} = 16 * n 32-bit words either way
+template <int NQC, bool F16>
 __device__ __forceinline__ GemmDesc gemm_desc_s(const TcArgs &A, int kind, int net) {
   constexpr int CA = (NQC + 1) / 2, CB = NQC - CA;
   constexpr int N3A = (12 * CA + 15) / 16 * 16, N3B = (12 * CB + 15) / 16 * 16;
+  constexpr int KS = F16 ? 16 : 8;
   const TcDims &td = A.td;
   const TcNet &N = net ? A.vnet : A.xnet;
+  const float *img = F16 ? N.img_h : N.img_s;
+  const int ne = (td.K1 + KS - 1) / KS, nh = (td.HK + KS - 1) / KS, ng = (td.KG + KS - 1) / KS;
   GemmDesc g;
-  const size_t o_hid = (size_t)(td.K1 / 8) * 16 * td.N1, o_ha = o_hid + (size_t)(td.HK / 8) * 16 * td.N1;
+  const size_t o_hid = (size_t)ne * 16 * td.N1, o_ha = o_hid + (size_t)nh * 16 * td.N1;
   if (kind == 0) {
-    g.src = A.gimg; g.nsteps = td.KG / 8; g.n = td.NG;
+    g.src = F16 ? A.gimg_h : A.gimg; g.nsteps = ng; g.n = td.NG;
   } else if (kind == 1) {
-    g.src = N.img_s; g.nsteps = td.K1 / 8; g.n = td.N1;
+    g.src = img; g.nsteps = ne; g.n = td.N1;
   } else if (kind == 2) {
-    g.src = N.img_s + o_hid; g.nsteps = td.HK / 8; g.n = td.N1;
+    g.src = img + o_hid; g.nsteps = nh; g.n = td.N1;
   } else if (kind == 3) {
-    g.src = N.img_s + o_ha; g.nsteps = td.HK / 8; g.n = N3A;
+    g.src = img + o_ha; g.nsteps = nh; g.n = N3A;
   } else {
-    g.src = N.img_s + o_ha + (size_t)(td.HK / 8) * 16 * N3A; g.nsteps = td.HK / 8; g.n = N3B;
+    g.src = img + o_ha + (size_t)nh * 16 * N3A; g.nsteps = nh; g.n = N3B;
   }
   g.chunk_floats = 16 * g.n;
   return g;
 }
 
 // ===================== TMA producer of this schedule (one warp) =====================
-template <int NQC>
+template <int NQC, bool F16>
 __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, float *ring, uint32_t NSLOT, uint32_t SLOT_FLOATS) {
   uint32_t s = 0, ph = 1;
   walk_schedule_s(A, [&](int kind, int net, int it) {
-    const GemmDesc g = gemm_desc_s<NQC>(A, kind, net);
+    const GemmDesc g = gemm_desc_s<NQC, F16>(A, kind, net);
 #pragma unroll 1
     for (int ks = 0; ks < g.nsteps; ks += KSLOT_S) {
       const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT_S, g.nsteps - ks);
@@ -177,7 +232,8 @@ __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, 
           const uint32_t cb = (uint32_t)g.chunk_floats * 4u;
           if (nk > 1) bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, cb * (uint32_t)(nk - 1), &S.full[s]);
           bulk_g2s(ring + (size_t)s * SLOT_FLOATS + (size_t)(nk - 1) * g.chunk_floats,
-                   (net ? A.vnet : A.xnet).emb_last + (size_t)it * g.chunk_floats, cb, &S.full[s]);
+                   (F16 ? (net ? A.vnet : A.xnet).emb_last_h : (net ? A.vnet : A.xnet).emb_last) + (size_t)it * g.chunk_floats, cb,
+                   &S.full[s]);
         } else {
           bulk_g2s(ring + (size_t)s * SLOT_FLOATS, g.src + (size_t)ks * g.chunk_floats, bytes, &S.full[s]);
         }
@@ -192,7 +248,7 @@ __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, 
 // As issuer_loop (uniform datapath, elect.sync), plus: the accumulator region per GEMM, the A operand awaited per K slot
 // (a_sub[K step / 2]; grad: a_sub[K step], its A operand has 4 columns per chunk; heads_b: not at all), and two
 // accumulator-ready barriers used alternately (heads_a and heads_b complete without an epilogue in between).
-template <int NQC>
+template <int NQC, bool F16>
 __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, uint64_t *a_sub, uint64_t *acc_rdy, int nsub, float *ring,
                                               uint32_t NSLOT, uint32_t SLOT_FLOATS, int lane) {
   uint32_t s = 0, ph = 0, gi = 0, ai = 0;  // ring slot / phase, GEMM counter, A-operand generation counter
@@ -206,9 +262,9 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
     const long long w_a0 = w_a, w_f0 = w_f;
 #endif
-    const GemmDesc g = gemm_desc_s<NQC>(A, kind, net);
+    const GemmDesc g = gemm_desc_s<NQC, F16>(A, kind, net);
     const uint32_t acc = s_region(kind);
-    const uint32_t idesc = make_idesc_tf32(128, g.n);
+    const uint32_t idesc = F16 ? make_idesc_f16(128, g.n) : make_idesc_tf32(128, g.n);
     const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
     const uint32_t slab16 = (uint32_t)g.n * 2u;
     const uint32_t par = ai & 1u;
@@ -226,12 +282,22 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 #pragma unroll
       for (int kk = 0; kk < KSLOT_S; ++kk) {
         if (ks + kk < g.nsteps) {
-          // A hand-over slot: 2 K steps (8 columns per chunk); grad: 1 K step (x - mu has 4 columns per chunk)
-          if (!nowait && (grad || (kk & 1) == 0)) {
+          // A hand-over slot i = the chunks i of both threads of a chain = 16 k (grad: 8 k, x - mu has 4 per chunk).
+          // tf32 (K step = 8 k): slot = 2 K steps, grad 1.  fp16 (K step = 16 k): slot = 1 K step, grad: 2 slots.
+          bool need;
+          int sub;
+          if (F16) {
+            need = true;
+            sub = grad ? min(2 * (ks + kk) + 1, nsub - 1) : ks + kk;
+          } else {
+            need = grad || (kk & 1) == 0;
+            sub = grad ? ks + kk : (ks + kk) >> 1;
+          }
+          if (!nowait && need) {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
             t0 = clock64();
 #endif
-            mbar_wait(&a_sub[grad ? ks + kk : (ks + kk) >> 1], par);
+            mbar_wait(&a_sub[sub], par);
             tcgen05_fence_after();
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
             w_a += clock64() - t0;
@@ -241,9 +307,15 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
             const uint64_t dhi = desc0 + (uint64_t)(b16 + (2u * kk) * slab16);
             const uint64_t dlo = desc0 + (uint64_t)(b16 + (2u * kk + 1u) * slab16);
             const uint32_t ahi = S_AHI + 8u * (ks + kk), alo = S_ALO + 8u * (ks + kk);
-            mma_tf32_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
-            mma_tf32_ts(acc, ahi, dlo, idesc, true);
-            mma_tf32_ts(acc, ahi, dhi, idesc, true);
+            if (F16) {
+              mma_f16_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
+              mma_f16_ts(acc, ahi, dlo, idesc, true);
+              mma_f16_ts(acc, ahi, dhi, idesc, true);
+            } else {
+              mma_tf32_ts(acc, alo, dhi, idesc, (ks + kk) > 0);
+              mma_tf32_ts(acc, ahi, dlo, idesc, true);
+              mma_tf32_ts(acc, ahi, dhi, idesc, true);
+            }
           }
           __syncwarp();
         }
@@ -284,7 +356,7 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 // what the heads epilogue prepares for the GEMM that follows it
 enum { NEXT_NONE = 0, NEXT_X1 = 1, NEXT_X2 = 2, NEXT_G = 3, NEXT_V = 4 };
 
-template <int NQC, int NHC, bool FAST, bool BIASG>
+template <int NQC, int NHC, bool FAST, bool BIASG, bool F16>
 __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const __grid_constant__ TcArgs A) {
   constexpr int NCT = MT * 2;  // compute threads: 2 per chain
   constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
@@ -332,9 +404,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   if (tmem != 0u) __trap();  // this CTA owns all 512 columns: column / lane 0 is a constant in the issuer and below
 
   if (warp == W_TMA) {
-    producer_loop_s<NQC>(A, S, ring, NSLOT, SLOT_FLOATS);
+    producer_loop_s<NQC, F16>(A, S, ring, NSLOT, SLOT_FLOATS);
   } else if (warp == W_MMA) {
-    issuer_loop_s<NQC>(A, S, a_sub, acc_rdy, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
+    issuer_loop_s<NQC, F16>(A, S, a_sub, acc_rdy, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
   } else {
     // ===================== compute warps =====================
     using I0 = std::integral_constant<int, 0>;
@@ -381,6 +453,17 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         for (int p = from; p < NSUB; ++p) mbar_arrive(&a_sub[p]);
     };
     const float eps = sh.eps, Tm = A.en.temperature, rTm = 1.f / A.en.temperature;
+    float amax = 0.f;  // F16: largest |value| this thread put into an A operand
+    if (F16) {
+      // TMEM is not cleared by the allocation: K tails of the A operand that no epilogue writes (k >= 8 NHC of the
+      // embed / hidden operands, the grad GEMM's tail before the first net call) must not hold NaN / Inf patterns
+      const uint32_t z4[4] = {0u, 0u, 0u, 0u};
+      for (int cq = qd; cq < 14; cq += 2) {
+        tmem_st4u(S_AHI + lb + 4 * cq, z4);
+        tmem_st4u(S_ALO + lb + 4 * cq, z4);
+      }
+      tmem_wait_st();
+    }
 
     for (int i = tid; i < sh.T * DP; i += NCT) smem[L.smask + i] = A.mask[i];
     // head constants of both nets into shared memory (X net first): as global loads their latency was ~18 % of the
@@ -445,18 +528,18 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           ab[2] = fwd ? 1.f : 0.f;
           ab[3] = fwd ? 0.f : 1.f;
         }
-        put_a8(lb, 8 * q, ab);
+        put_a<F16, 8>(lb, 8 * q, ab, amax);
       };
       // Gaussian grad GEMM input x - mu of one chunk (the K tail beyond DP is zeroed once per GEMM by zero_gtail)
       auto put_xmu = [&](int q, const float (&x)[4]) {
         const float4 mu = ldg4(A.en.mu + 4 * q);
         const float a[4] = {x[0] - mu.x, x[1] - mu.y, x[2] - mu.z, x[3] - mu.w};
-        put_a4s(lb, 4 * q, a);
+        put_a<F16, 4>(lb, 4 * q, a, amax);
       };
       auto zero_gtail = [&]() {  // KG = DP rounded to 8: one more 4-column chunk of zeros when NQC is odd
-        if ((NQC & 1) && qd == 1) {
+        if (!F16 && (NQC & 1) && qd == 1) {  // fp16: the K tail holds finite values of earlier operands, its B rows are 0
           const float z[4] = {0.f, 0.f, 0.f, 0.f};
-          put_a4s(lb, DP, z);
+          put_a<F16, 4>(lb, DP, z, amax);
         }
       };
       // RoughWell grad U of one chunk (utils/distributions.py:90-97)
@@ -571,7 +654,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           const float(&hh)[8] = h[B];
           const float a[8] = {fmaxf(hh[0] + b0.x, 0.f), fmaxf(hh[1] + b0.y, 0.f), fmaxf(hh[2] + b0.z, 0.f), fmaxf(hh[3] + b0.w, 0.f),
                               fmaxf(hh[4] + b1.x, 0.f), fmaxf(hh[5] + b1.y, 0.f), fmaxf(hh[6] + b1.z, 0.f), fmaxf(hh[7] + b1.w, 0.f)};
-          put_a8(lb, 8 * q, a);
+          put_a<F16, 8>(lb, 8 * q, a, amax);
           if (handover) slot_done(i);
         };
         // two chunks per iteration (the register double buffer needs static names); rolled: the fully unrolled
@@ -823,6 +906,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       g_tc_dbg[4] = clock64() - t_begin;
     }
 #endif
+    if (F16 && !(amax < 60000.f)) g_tc_dbg[23] = 1;  // sticky: an A operand left the fp16 range (or was not finite)
     (void)Tm;
   }
   tcgen05_fence_before();

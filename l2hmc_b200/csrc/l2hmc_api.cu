@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "kernel_tile.cuh"
+#include <cuda_fp16.h>
 #include "kernel_tc.cuh"
 #include "kernel_tc_s.cuh"
 #include "kernel_small.cuh"
@@ -91,6 +92,8 @@ struct l2hmc_ctx {
   // tensor-core kernel: pre-split weight streams
   tc::TcDims td;
   DevBuf tc_buf[2], tc_gbuf, tc_hc[2];
+  size_t tc_g_h_off = 0;  // offset of the fp16 twin inside tc_gbuf
+  float tc_wmax[3] = {0.f, 0.f, 0.f};  // largest |value| packed for the X net, the V net, the Gaussian grad (fp16 range check)
   std::vector<float> tc_head_raw[2];  // per net: bs | bt | bq | e^{scale_s} | e^{scale_q}, DP each (host copy for tc_pack_hc)
   tc::TcNet tc_net[2] = {};
   bool tc_ok = false;  // shape / energy kind inside what kernel_tc covers
@@ -295,6 +298,32 @@ static void append_b_stream(std::vector<float> &out, int Kpad, int Npad, Get get
   }
 }
 
+// fp16 twin of append_b_stream for the kind::f16 MMAs (K step = 16): per K step one chunk = {hi slab, lo slab}, each
+// slab Npad x 16 halfs in the K-major no-swizzle core-matrix order [k_core (2)][n_group (Npad/8)][row (8)][8 halfs] --
+// 16 * Npad 32-bit words per chunk, like one tf32 K step.  Returns the largest |value| (fp16 range check).
+template <class Get>
+static float append_b_stream_f16(std::vector<float> &out, int K, int Npad, Get get) {
+  const int NG = Npad / 8, nsteps = (K + 15) / 16;
+  float amax = 0.f;
+  for (int ks = 0; ks < nsteps; ++ks) {
+    const size_t base = out.size();
+    out.resize(base + (size_t)16 * Npad, 0.f);
+    uint16_t *hi = reinterpret_cast<uint16_t *>(out.data() + base), *lo = hi + (size_t)16 * Npad;
+    for (int n = 0; n < Npad; ++n)
+      for (int kk = 0; kk < 16; ++kk) {
+        const int k = 16 * ks + kk;
+        const float w = k < K ? get(k, n) : 0.f;
+        amax = fmaxf(amax, fabsf(w));
+        const __half h = __float2half_rn(w);
+        const __half l = __float2half_rn(w - __half2float(h));
+        const size_t idx = ((size_t)(kk >> 3) * NG + (n >> 3)) * 64 + (size_t)(n & 7) * 8 + (kk & 7);
+        memcpy(&hi[idx], &h, 2);
+        memcpy(&lo[idx], &l, 2);
+      }
+  }
+  return amax;
+}
+
 static void tc_setup_dims(l2hmc_ctx *ctx) {
   const Shape &sh = ctx->sh;
   tc::TcDims &td = ctx->td;
@@ -319,6 +348,8 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   // kernel_tc_s: biases as weight rows (needs two pad dimensions in the last 4-dim chunk and a pad hidden unit)
   const char *bg = getenv("L2HMC_TC_BIASG");
   td.biasg = (!(bg && bg[0] == '0') && sh.D <= sh.DP - 2 && sh.H <= td.HK - 1) ? 1 : 0;
+  const char *fe = getenv("L2HMC_TC_F16");
+  td.f16 = (fe && fe[0] == '0') ? 0 : 1;  // fp16 split when every packed value is inside the fp16 range (checked at pack time)
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
 }
 
@@ -397,10 +428,49 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
     }
   }
   const size_t nimg_s = img_s.size();
+  // fp16 twins (K steps of 16; the embed's last K step covers k = K1-8 .. K1+7)
+  std::vector<float> img_h;
+  size_t nstream_h = 0;
+  float wmax = 0.f;
+  {
+    wmax = fmaxf(wmax, append_b_stream_f16(img_h, td.K1, td.N1, embed_w));
+    wmax = fmaxf(wmax, append_b_stream_f16(img_h, td.HK, td.N1, [&](int k, int n) -> float {
+      if (biasg && k == H) return n < H ? p->b4[n] : (n == H ? 1.f : 0.f);
+      return (k < H && n < H) ? p->W4[(size_t)k * H + n] : 0.f;
+    }));
+    const int nqc = DP / 4, ca = (nqc + 1) / 2, cb = nqc - ca;
+    for (int part = 0; part < 2; ++part) {
+      const int cp = part == 0 ? ca : cb, d0 = part == 0 ? 0 : 4 * ca, np = round_up(12 * cp, 16);
+      if (cp == 0) continue;
+      wmax = fmaxf(wmax, append_b_stream_f16(img_h, td.HK, np, [&](int k, int n) -> float {
+        if (k > H || (k == H && !biasg) || n >= 12 * cp) return 0.f;
+        const int blk = n / (4 * cp), d = d0 + n - blk * 4 * cp;
+        if (d >= D) return 0.f;
+        if (k == H) return (blk == 0 ? p->bs : (blk == 1 ? p->bt : p->bq))[d];
+        const float *W = blk == 0 ? p->Ws : (blk == 1 ? p->Wt : p->Wq);
+        return W[(size_t)k * D + d];
+      }));
+    }
+    nstream_h = img_h.size();
+    if (biasg) {
+      const int k0 = (td.K1 - 1) / 16 * 16;  // first k of the embed's last K = 16 step
+      for (int t = 0; t < T; ++t)
+        wmax = fmaxf(wmax, append_b_stream_f16(img_h, 16, td.N1, [&](int kk, int n) -> float {
+          const int k = k0 + kk;
+          if (k >= td.K1) return 0.f;
+          if (k == kf) return n < H ? tb_at(t, n) : (n == H ? 1.f : 0.f);
+          if (k == kb) return n < H ? tb_at(T - 1 - t, n) : (n == H ? 1.f : 0.f);
+          return embed_w(k, n);
+        }));
+    }
+  }
+  ctx->tc_wmax[net_id] = wmax;
+  const size_t nimg_h = img_h.size();
   const size_t nimg = img.size(), ntb = (size_t)T * td.N1, nb4 = td.N1, nbh = td.N3, nes = DP;
-  std::vector<float> buf(nimg + ntb + nb4 + nbh + 2 * nes + nimg_s, 0.f);
+  std::vector<float> buf(nimg + ntb + nb4 + nbh + 2 * nes + nimg_s + nimg_h, 0.f);
   memcpy(buf.data(), img.data(), nimg * sizeof(float));
   memcpy(buf.data() + nimg + ntb + nb4 + nbh + 2 * nes, img_s.data(), nimg_s * sizeof(float));
+  memcpy(buf.data() + nimg + ntb + nb4 + nbh + 2 * nes + nimg_s, img_h.data(), nimg_h * sizeof(float));
   float *tb = buf.data() + nimg, *b4 = tb + ntb, *bh = b4 + nb4, *es = bh + nbh, *eq = es + nes;
   for (int t = 0; t < T; ++t) {
     const float arg = 6.2831855f * (float)t / (float)T;  // utils/dynamics.py:99-105 in fp32
@@ -430,6 +500,8 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
   n.eq = n.es + nes;
   n.img_s = n.eq + nes;
   n.emb_last = biasg ? n.img_s + nstream_s : nullptr;
+  n.img_h = n.img_s + nimg_s;
+  n.emb_last_h = biasg ? n.img_h + nstream_h : nullptr;
   std::vector<float> &raw = ctx->tc_head_raw[net_id];
   raw.assign((size_t)5 * DP, 0.f);
   for (int d = 0; d < D; ++d) {
@@ -478,9 +550,14 @@ static int tc_pack_gaussian(l2hmc_ctx *ctx, const float *Ssym_padded /* [DP][LDS
   append_b_stream(img, td.KG, td.NG, [&](int k, int n) -> float {  // g_n = sum_k d_k Ssym[k][n]
     return (k < sh.D && n < sh.D) ? Ssym_padded[(size_t)k * sh.LDS + n] : 0.f;
   });
+  const size_t ng32 = img.size();
+  ctx->tc_wmax[2] = append_b_stream_f16(img, td.KG, td.NG, [&](int k, int n) -> float {
+    return (k < sh.D && n < sh.D) ? Ssym_padded[(size_t)k * sh.LDS + n] : 0.f;
+  });
   int rc = ensure(ctx, ctx->tc_gbuf, img.size());
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpy(ctx->tc_gbuf.p, img.data(), img.size() * sizeof(float), cudaMemcpyHostToDevice));
+  ctx->tc_g_h_off = ng32;
   return L2HMC_OK;
 }
 
@@ -946,6 +1023,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     TA.xnet = ctx->tc_net[0];
     TA.vnet = ctx->tc_net[1];
     TA.gimg = ctx->tc_gbuf.p;
+    TA.gimg_h = ctx->tc_gbuf.p ? ctx->tc_gbuf.p + ctx->tc_g_h_off : nullptr;
     TA.en = ctx->en;
     TA.mask = ctx->mask.p;
     TA.io = K.io;
@@ -969,29 +1047,39 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       const size_t smem = tc::tc_s_smem_bytes(ctx->sh.DP, ctx->sh.T, TA.td.nslot, TA.td.slot_floats);
       static thread_local size_t tc_s_configured = 0;
       if (smem > tc_s_configured) {
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<13, 13, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<8, 13, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+#define L2HMC_TC_S_ATTR(Q, HH, F, B, X) \
+  CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<Q, HH, F, B, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
+        L2HMC_TC_S_ATTR(13, 13, true, true, true); L2HMC_TC_S_ATTR(13, 13, true, true, false);
+        L2HMC_TC_S_ATTR(13, 13, false, true, true); L2HMC_TC_S_ATTR(13, 13, false, true, false);
+        L2HMC_TC_S_ATTR(13, 13, true, false, true); L2HMC_TC_S_ATTR(13, 13, true, false, false);
+        L2HMC_TC_S_ATTR(13, 13, false, false, true); L2HMC_TC_S_ATTR(13, 13, false, false, false);
+        L2HMC_TC_S_ATTR(8, 13, true, false, true); L2HMC_TC_S_ATTR(8, 13, true, false, false);
+        L2HMC_TC_S_ATTR(8, 13, false, false, true); L2HMC_TC_S_ATTR(8, 13, false, false, false);
+#undef L2HMC_TC_S_ATTR
         tc_s_configured = smem;
       }
       const unsigned nthreads = (unsigned)(tc::MT * 2 + 64);
       const bool fm = ctx->td.fast_math != 0, bg = ctx->td.biasg != 0;
+      // fp16 split only when everything packed (weights, biases, time-embedding rows, precision matrix) is well inside
+      // the fp16 range; activations are checked by the kernel (sticky flag, l2hmc_debug_counters[23])
+      const float wmax = fmaxf(fmaxf(ctx->tc_wmax[0], ctx->tc_wmax[1]), ctx->en.kind == L2HMC_ENERGY_GAUSSIAN ? ctx->tc_wmax[2] : 0.f);
+      const bool h16 = ctx->td.f16 != 0 && wmax < 3.0e4f;
+      TA.td.f16 = h16 ? 1 : 0;
+#define L2HMC_TC_S_LAUNCH(Q, HH, F, B, X) tc::tc_transition_kernel_s<Q, HH, F, B, X><<<blocks, nthreads, smem, stream>>>(TA)
       if (nqc == 13) {
         if (bg) {
-          if (fm) tc::tc_transition_kernel_s<13, 13, true, true><<<blocks, nthreads, smem, stream>>>(TA);
-          else tc::tc_transition_kernel_s<13, 13, false, true><<<blocks, nthreads, smem, stream>>>(TA);
+          if (fm) { if (h16) L2HMC_TC_S_LAUNCH(13, 13, true, true, true); else L2HMC_TC_S_LAUNCH(13, 13, true, true, false); }
+          else { if (h16) L2HMC_TC_S_LAUNCH(13, 13, false, true, true); else L2HMC_TC_S_LAUNCH(13, 13, false, true, false); }
         } else {
-          if (fm) tc::tc_transition_kernel_s<13, 13, true, false><<<blocks, nthreads, smem, stream>>>(TA);
-          else tc::tc_transition_kernel_s<13, 13, false, false><<<blocks, nthreads, smem, stream>>>(TA);
+          if (fm) { if (h16) L2HMC_TC_S_LAUNCH(13, 13, true, false, true); else L2HMC_TC_S_LAUNCH(13, 13, true, false, false); }
+          else { if (h16) L2HMC_TC_S_LAUNCH(13, 13, false, false, true); else L2HMC_TC_S_LAUNCH(13, 13, false, false, false); }
         }
       } else {
         if (bg) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: no bias-in-GEMM instantiation for this shape");
-        if (fm) tc::tc_transition_kernel_s<8, 13, true, false><<<blocks, nthreads, smem, stream>>>(TA);
-        else tc::tc_transition_kernel_s<8, 13, false, false><<<blocks, nthreads, smem, stream>>>(TA);
+        if (fm) { if (h16) L2HMC_TC_S_LAUNCH(8, 13, true, false, true); else L2HMC_TC_S_LAUNCH(8, 13, true, false, false); }
+        else { if (h16) L2HMC_TC_S_LAUNCH(8, 13, false, false, true); else L2HMC_TC_S_LAUNCH(8, 13, false, false, false); }
       }
+#undef L2HMC_TC_S_LAUNCH
     } else {
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
     static thread_local size_t tc_configured = 0;

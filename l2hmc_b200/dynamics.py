@@ -212,6 +212,15 @@ class Dynamics(object):
             n, w, Wp, bp = self._mlp_args(*self._aux_encoder)
             self._chk(self._lib.l2hmc_set_aux_encoder(self._ctx, n, w, Wp, bp))
 
+    def fp16_range_exceeded(self):
+        """True when the tensor-core kernel's fp16 operand split met a value outside the fp16 range (|a| >= 6e4 or not
+        finite) since the library was loaded: results of the affected chains are not valid -- rerun with
+        L2HMC_TC_F16=0 (tf32 split, fp32 range).  Synchronises the device."""
+        self._ensure_ctx()
+        buf = (C.c_int64 * 24)()
+        self._chk(self._lib.l2hmc_debug_counters(self._ctx, buf, 24))
+        return bool(buf[23])
+
     def set_energy_function(self, energy_function):
         """Replace the target of an existing Dynamics (same kind of descriptor, same dimension): the annealed energy of
         utils/ais.py:44-58 changes at every step while the leapfrog operator stays."""

@@ -338,6 +338,7 @@ def test_tc_kernel_matches_oracle(name, n, regime):
     rep, _ = U.parity_report(P, n, dyn=dyn)
     assert dyn.kernel_name == "tc_3xtf32"
     _check(rep)
+    assert not dyn.fp16_range_exceeded()
 
 
 def test_tc_kernel_multi_transition_and_philox():
@@ -413,6 +414,29 @@ def test_tc_specialised_kernel_follows_eps_and_temperature():
     Xob, Vob, pob = o.backward(U.t64(d["x"]), U.t64(d["v_f"]))
     assert U.max_rel(Xb.cpu().numpy(), Xob.numpy()) <= SAMPLE_TOL
     assert float(np.max(np.abs(pb.cpu().numpy() - pob.numpy()))) <= P_TOL
+
+
+def test_tc_fp16_and_tf32_splits_agree_and_range_flag(monkeypatch):
+    """The specialised kernel's fp16 operand split (three kind::f16 MMAs per product) against its tf32 split on the same
+    inputs; and the sticky range flag when an operand leaves the fp16 range."""
+    P = U.Problem(regime="stress", **U.CONFIGS["c2_scg50"])
+    x, v, dr, u = _fixed_inputs(P, 600)
+    kw = dict(v=v, direction=dr, u=u, do_mh=True)
+    monkeypatch.delenv("L2HMC_TC_F16", raising=False)
+    a = P.product(kernel="tc")._transition(x, **kw)
+    monkeypatch.setenv("L2HMC_TC_F16", "0")       # read when the context is created
+    b = P.product(kernel="tc")._transition(x, **kw)
+    monkeypatch.delenv("L2HMC_TC_F16", raising=False)
+    assert not torch.equal(a["Lx"], b["Lx"])
+    assert U.max_rel(a["Lx"].cpu().numpy(), b["Lx"].cpu().numpy()) <= SAMPLE_TOL
+    assert U.max_rel(a["Lv"].cpu().numpy(), b["Lv"].cpu().numpy()) <= SAMPLE_TOL
+    assert float((a["px"] - b["px"]).abs().max()) <= 2 * P_TOL
+    dyn = P.product(kernel="tc")
+    assert not dyn.fp16_range_exceeded()
+    big = x.clone()
+    big[0, 0] = 1.0e5                              # outside the fp16 range
+    dyn._transition(big, **kw)
+    assert dyn.fp16_range_exceeded()
 
 
 # ---- kernel selection: every kernel that covers a configuration must pass on it -------------------------
