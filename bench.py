@@ -312,28 +312,30 @@ def main():
     # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_tc_final_ncu.txt); below the algorithmic bytes because the
     # 126 MB L2 still holds part of the written lines when the launch ends
     if dyn.kernel_name.startswith("tc") and n == CHAINS_PER_GPU:
-        roofline["traffic"] = 53.430272e6 + 56.727296e6
+        roofline["traffic"] = 53.337600e6 + 53.924352e6
         roofline["traffic_source"] = "profiles/r01_tc_final_ncu.txt"
     if dyn.kernel_name.startswith("tc") and achieved:
-        # the GEMMs run on the tensor pipe as 3xTF32 (three tf32 MMAs per fp32-accurate product, plus padding of
-        # 100 -> 104/112 and 150 -> 160 columns): the honest denominator is the dense TF32 rate, = half the measured
-        # bf16 rate (sustained figure: the kernel is timed inside a long step).
-        tf32_peak = float(peaks["bf16_tflops_sustained"]) / 2.0
-        roofline.update({"bound": "tensor", "peak": tf32_peak, "frac": achieved / tf32_peak,
+        # the GEMMs run on the tensor pipe with an error-compensated split: three MMAs per fp32-accurate product, tf32
+        # (K = 8 per MMA) or fp16 pairs (K = 16 per MMA, twice the rate) -- l2hmc_kernel_name says which the launch used.
+        # Denominator: the measured sustained dense rate of that input type (bf16 figure for fp16, half of it for tf32).
+        f16 = dyn.kernel_name == "tc_3xf16"
+        t_peak = float(peaks["bf16_tflops_sustained"]) / (1.0 if f16 else 2.0)
+        roofline.update({"bound": "tensor", "peak": t_peak, "frac": achieved / t_peak,
                          "frac_of_fma_roofline": achieved / fma_peak_tflops,
-                         "peak_source": "dense TF32 = MEASURED_PEAKS.json bf16_tflops_sustained / 2 (%s); algorithmic fp32 FLOP "
-                                        "counted once although each product costs three tf32 MMAs over padded shapes (3xTF32 split for 1e-5 "
-                                        "parity): see executed_tf32_tflops for what the tensor pipe really does; the kernel holds "
-                                        "the maximum SM clock while the bf16 GEMM behind the measured peak runs power-capped, so "
-                                        "executed/measured can exceed 1" % src,
-                         "tensor_mma_per_product": 3})
-        # what the tensor pipe executes: 3 tf32 MMAs per product over the padded shapes (K 100 -> 104, N 100 -> 112,
-        # heads 150 -> 96 + 80 columns, grad 50 -> 56 x 64), per leapfrog step and 128-chain tile
-        mac_tile_step = 3 * (4 * 128 * 104 * (112 + 112 + 96 + 80) + 128 * 56 * 64)
+                         "peak_source": "dense %s = MEASURED_PEAKS.json bf16_tflops_sustained%s (%s); algorithmic fp32 FLOP counted "
+                                        "once although each product costs three MMAs over padded shapes (error-compensated split for "
+                                        "1e-5 parity): see executed_tensor_tflops for what the tensor pipe really does; the kernel "
+                                        "holds the maximum SM clock while the GEMM behind the measured peak runs power-capped"
+                                        % ("fp16" if f16 else "TF32", "" if f16 else " / 2", src),
+                         "tensor_mma_per_product": 3, "operand_split": "fp16 x3" if f16 else "tf32 x3"})
+        # what the tensor pipe executes per leapfrog step and 128-chain tile: 3 MMAs per product over the padded shapes
+        # (K 100 -> 104 (tf32) / 112 (fp16), N 100 -> 112, heads 150 -> 96 + 80 columns, grad 50 -> K 56 / 64 x N 64)
+        kp, kg = (112, 64) if f16 else (104, 56)
+        mac_tile_step = 3 * (4 * 128 * kp * (112 + 112 + 96 + 80) + 128 * kg * 64)
         executed = 2.0 * mac_tile_step * LF * (n / 128.0) / (kern_ms * 1e-3) / 1e12
-        roofline["executed_tf32_tflops"] = executed
-        roofline["executed_frac_of_measured_tf32"] = executed / tf32_peak
-        roofline["executed_frac_of_tf32_at_sm_max_clock"] = executed / (148 * 2048 * 2 * sm_max * 1e6 / 1e12)
+        roofline["executed_tensor_tflops"] = executed
+        roofline["executed_frac_of_measured_peak"] = executed / t_peak
+        roofline["executed_frac_at_sm_max_clock"] = executed / (148 * (4096 if f16 else 2048) * 2 * sm_max * 1e6 / 1e12)
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -92,6 +92,7 @@ struct l2hmc_ctx {
   // tensor-core kernel: pre-split weight streams
   tc::TcDims td;
   DevBuf tc_buf[2], tc_gbuf, tc_hc[2];
+  bool tc_used_f16 = false;  // the last tensor-core launch used the fp16 operand split
   size_t tc_g_h_off = 0;  // offset of the fp16 twin inside tc_gbuf
   float tc_wmax[3] = {0.f, 0.f, 0.f};  // largest |value| packed for the X net, the V net, the Gaussian grad (fp16 range check)
   std::vector<float> tc_head_raw[2];  // per net: bs | bt | bq | e^{scale_s} | e^{scale_q}, DP each (host copy for tc_pack_hc)
@@ -1065,6 +1066,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       const float wmax = fmaxf(fmaxf(ctx->tc_wmax[0], ctx->tc_wmax[1]), ctx->en.kind == L2HMC_ENERGY_GAUSSIAN ? ctx->tc_wmax[2] : 0.f);
       const bool h16 = ctx->td.f16 != 0 && wmax < 3.0e4f;
       TA.td.f16 = h16 ? 1 : 0;
+      ctx->tc_used_f16 = h16;
 #define L2HMC_TC_S_LAUNCH(Q, HH, F, B, X) tc::tc_transition_kernel_s<Q, HH, F, B, X><<<blocks, nthreads, smem, stream>>>(TA)
       if (nqc == 13) {
         if (bg) {
@@ -1081,6 +1083,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       }
 #undef L2HMC_TC_S_LAUNCH
     } else {
+    ctx->tc_used_f16 = false;
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
     static thread_local size_t tc_configured = 0;
     if (smem > tc_configured) {
@@ -1508,7 +1511,7 @@ extern "C" const char *l2hmc_kernel_name(const l2hmc_ctx *ctx) {
   switch (ctx->kernel) {
     case L2HMC_KERNEL_TILE: return "tile_fma";
     case L2HMC_KERNEL_SMALL: return "small_fma";
-    case L2HMC_KERNEL_TC: return "tc_3xtf32";
+    case L2HMC_KERNEL_TC: return ctx->tc_used_f16 ? "tc_3xf16" : "tc_3xtf32";  // operand split of the last launch
     case L2HMC_KERNEL_LAYERED: return ctx->lay.gemm_tc ? "layered_tc3xtf32" : "layered_fma";
     default: return "none";
   }

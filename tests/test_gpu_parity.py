@@ -336,7 +336,7 @@ def test_tc_kernel_matches_oracle(name, n, regime):
     P = U.Problem(regime=regime, **U.CONFIGS[name])
     dyn = P.product(kernel="tc")
     rep, _ = U.parity_report(P, n, dyn=dyn)
-    assert dyn.kernel_name == "tc_3xtf32"
+    assert dyn.kernel_name in ("tc_3xf16", "tc_3xtf32")
     _check(rep)
     assert not dyn.fp16_range_exceeded()
 
@@ -405,7 +405,7 @@ def test_tc_specialised_kernel_follows_eps_and_temperature():
     o = P.oracle(torch.float64, temperature=1.7)
     x, v = torch.as_tensor(d["x"]).cuda(), torch.as_tensor(d["v_f"]).cuda()
     X, V, p = dyn.forward(x, init_v=v)
-    assert dyn.kernel_name == "tc_3xtf32"
+    assert dyn.kernel_name in ("tc_3xf16", "tc_3xtf32")
     Xo, Vo, po = o.forward(U.t64(d["x"]), U.t64(d["v_f"]))
     assert U.max_rel(X.cpu().numpy(), Xo.numpy()) <= SAMPLE_TOL
     assert U.max_rel(V.cpu().numpy(), Vo.numpy()) <= SAMPLE_TOL
@@ -465,8 +465,8 @@ def test_tile_kernel_on_large_nets(name, n):
 
 def test_auto_kernel_choice():
     assert U.Problem(**U.CONFIGS["c1_scg2"]).product().kernel_name == "small_fma"
-    assert U.Problem(**U.CONFIGS["c2_scg50"]).product().kernel_name == "tc_3xtf32"
-    assert U.Problem(**U.CONFIGS["c4_rw32"]).product().kernel_name == "tc_3xtf32"
+    assert U.Problem(**U.CONFIGS["c2_scg50"]).product().kernel_name.startswith("tc_3x")
+    assert U.Problem(**U.CONFIGS["c4_rw32"]).product().kernel_name.startswith("tc_3x")
     assert U.Problem(**U.CONFIGS["c3_mog2"]).product().kernel_name == "small_fma"
     assert U.Problem(kind="gmm", D=8, H=32, T=5, eps=0.1).product().kernel_name == "tile_fma"  # GMM: not on the TC path
     assert U.Problem(kind="gaussian", D=2, T=5, eps=0.1, hmc=True).product().kernel_name == "small_fma"
