@@ -61,7 +61,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("L2HMC_BENCH_SMI_MS", "50")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append((time.time(), line.strip()))
@@ -141,7 +141,7 @@ def cpu_reference_run(steps, warmup, sample_chains):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
@@ -215,7 +215,8 @@ def main():
         gathered = torch.empty((n_total, D), dtype=torch.float32, device=dev)
         for _ in range(2):
             all_gather_chains(x, n_total, out=gathered)
-    sampler = ClockSampler(local) if rank == 0 else None
+    # L2HMC_BENCH_NO_SMI=1: development switch to measure what the nvidia-smi polling itself costs (it does perturb the GPU)
+    sampler = ClockSampler(local) if rank == 0 and os.environ.get("L2HMC_BENCH_NO_SMI") != "1" else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
@@ -292,7 +293,7 @@ def main():
             dist.destroy_process_group()
         return
 
-    clocks = sampler.summary(t_wall0, t_wall1)
+    clocks = sampler.summary(t_wall0, t_wall1) if sampler else {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
     peaks, src = measured_peaks()
     sm_max = float(peaks.get("sm_max_mhz", 1965.0))
     fma_peak_tflops = 148 * 128 * 2 * sm_max * 1e6 / 1e12  # fp32 FMA pipe at the max SM clock

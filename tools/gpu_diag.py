@@ -63,7 +63,7 @@ def timing(kernel):
                 o = dyn._transition(x, dir_mode=_lib.DIR_RANDOM, do_mh=True, want_v=False)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 5
+            reps = int(os.environ.get("L2HMC_DIAG_REPS", "5"))
             e0.record()
             for _ in range(reps):
                 o = dyn._transition(o["x_next"], dir_mode=_lib.DIR_RANDOM, do_mh=True, want_v=False)
