@@ -313,7 +313,7 @@ def main():
     # (dram__bytes_read.sum + dram__bytes_write.sum, profiles/r01_tc_final_ncu.txt); below the algorithmic bytes because the
     # 126 MB L2 still holds part of the written lines when the launch ends
     if dyn.kernel_name.startswith("tc") and n == CHAINS_PER_GPU:
-        roofline["traffic"] = 53.337600e6 + 53.924352e6
+        roofline["traffic"] = 53.189120e6 + 51.559936e6
         roofline["traffic_source"] = "profiles/r01_tc_final_ncu.txt"
     if dyn.kernel_name.startswith("tc") and achieved:
         # the GEMMs run on the tensor pipe with an error-compensated split: three MMAs per fp32-accurate product, tf32
