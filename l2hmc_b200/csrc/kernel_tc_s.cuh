@@ -452,17 +452,6 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       if (lane == 0)
         for (int p = from; p < NSUB; ++p) mbar_arrive(&a_sub[p]);
     };
-#ifdef L2HMC_TC_LATE_ARRIVE
-    // arrive for slot i-1 just before the stores of chunk i (tcgen05.wait::st then covers stores that landed during the
-    // math of chunk i); the last slot is announced by a_done
-    auto before_put = [&](int i) { if (i > 0) slot_done(i - 1); };
-    auto after_put = [&](int) {};
-    constexpr int LATE = 1;
-#else
-    auto before_put = [&](int) {};
-    auto after_put = [&](int i) { slot_done(i); };
-    constexpr int LATE = 0;
-#endif
     const float eps = sh.eps, Tm = A.en.temperature, rTm = 1.f / A.en.temperature;
     float amax = 0.f;  // F16: largest |value| this thread put into an A operand
     if (F16) {
@@ -594,11 +583,10 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             const float v4[4] = {vv.x, vv.y, vv.z, vv.w};
             ham_chunk(x4, v4, g4, q, U, K);
           }
-          before_put(i);
           put_ab(q, x4, g4);
-          after_put(i);
+          slot_done(i);
         }
-        a_done(qn - LATE);
+        a_done(qn);
         Hpart = (gauss ? 0.5f * U : U) + 0.5f * K;
       };
       // start of a transition: grad U(x), H(x, v) partial, first V-net input
@@ -609,12 +597,11 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             const int q = qd + 2 * i;
             const float4 xv = lds4(xr + 4 * q);
             const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
-            before_put(i);
             put_xmu(q, x4);
-            after_put(i);
+            slot_done(i);
           }
           zero_gtail();
-          a_done(qn - LATE);
+          a_done(qn);
           grad_epilogue(S_R2, true, Hpart);
         } else {
           float U = 0.f, K = 0.f;
@@ -627,11 +614,10 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             roughwell_grad(q, x4, g4);
             sts4(gr + 4 * q, g4);
             ham_chunk(x4, v4, g4, q, U, K);
-            before_put(i);
             put_ab(q, x4, g4);
-            after_put(i);
+            slot_done(i);
           }
-          a_done(qn - LATE);
+          a_done(qn);
           Hpart = U + 0.5f * K;
         }
       };
@@ -668,9 +654,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           const float(&hh)[8] = h[B];
           const float a[8] = {fmaxf(hh[0] + b0.x, 0.f), fmaxf(hh[1] + b0.y, 0.f), fmaxf(hh[2] + b0.z, 0.f), fmaxf(hh[3] + b0.w, 0.f),
                               fmaxf(hh[4] + b1.x, 0.f), fmaxf(hh[5] + b1.y, 0.f), fmaxf(hh[6] + b1.z, 0.f), fmaxf(hh[7] + b1.w, 0.f)};
-          if (handover) before_put(i);
           put_a<F16, 8>(lb, 8 * q, a, amax);
-          if (handover) after_put(i);
+          if (handover) slot_done(i);
         };
         // two chunks per iteration (the register double buffer needs static names); rolled: the fully unrolled
         // version of this kernel had a 178 KB loop body and spent 40 % of the epilogue time on instruction fetch
@@ -679,7 +664,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           chunk(i, I0{});
           if (i + 1 < hn) chunk(i + 1, I1{});
         }
-        a_done(handover ? hn - LATE : 0);
+        a_done(handover ? hn : 0);
       };
 
       // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) + next A operand --------------
@@ -700,9 +685,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
               a[j] = nx1 ? v4[j] : x4[j];
               b[j] = nx1 ? (fwd ? m4[j] : 1.f - m4[j]) * x4[j] : g4[j];
             }
-            before_put(i);
             put_ab(q, a, b);
-            after_put(i);
+            slot_done(i);
           }
         } else {
           if (next == NEXT_X2) {  // X net, second half: its k is this half's 1 - k
@@ -710,20 +694,17 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             float b[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = (flip ? m4[j] : 1.f - m4[j]) * x4[j];
-            before_put(i);
             put_ab(q, v4, b);
-            after_put(i);
+            slot_done(i);
           } else if (gauss) {  // NEXT_G: grad U at the new x (K step i of the grad GEMM = the chunks i of both threads)
-            before_put(i);
             put_xmu(q, x4);
-            after_put(i);
+            slot_done(i);
           } else {
             float g[4];
             roughwell_grad(q, x4, g);
             sts4(gr + 4 * q, g);
-            before_put(i);
             put_ab(q, x4, g);
-            after_put(i);
+            slot_done(i);
           }
         }
       };
@@ -829,7 +810,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         }
         if (PART == 1) {
           if (MODE == 1 && next == NEXT_G && gauss) zero_gtail();  // before this warp's arrival on the last K step
-          if (next != NEXT_NONE) a_done(qn - LATE);
+          if (next != NEXT_NONE) a_done(qn);
           else tcgen05_fence_before();
         } else {
           tcgen05_fence_before();
