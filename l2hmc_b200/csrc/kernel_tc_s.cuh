@@ -1,21 +1,25 @@
 // Tensor-core transition kernel, shape-specialised compute path (sm_100a).
 //
-// Same launch shape, operand images, ring, producer and MMA issuer as kernel_tc.cuh (reference: utils/dynamics.py:115-201,
-// 246-309; utils/sampler.py:28-55; net SCGExperiment.ipynb:51-77); what differs is the code of the 8 compute warps, which
-// the ncu source page showed to be instruction-bound once the MMA issue had been fixed (profiles/r02_*):
-//   * chunk counts are template parameters (NQC = DP/4 dimension chunks, NHC = HK/8 hidden chunks), every loop over
-//     chunks is unrolled, so TMEM / shared / global addresses are `uniform base + immediate` (the generic kernel spent
-//     more instructions on addresses, R2UR moves and register rotation than on arithmetic);
+// Same launch shape and roles as kernel_tc.cuh (reference: utils/dynamics.py:115-201, 246-309; utils/sampler.py:28-55; net
+// SCGExperiment.ipynb:51-77): one CTA = 128 chains for the whole transition, 8 compute warps, one MMA-issuer warp, one
+// TMA-producer warp.  What differs is everything the ncu source page and the phase counters pointed at, one measured
+// step at a time (profiles/r01_tc_s_history.txt):
+//   * chunk counts are template parameters (NQC = DP/4 dimension chunks, NHC = HK/8 hidden chunks); the chunk loops stay
+//     rolled, two chunks per iteration for the register double buffer (fully unrolled, the loop body was 178 KB and
+//     instruction fetch took 40 % of the epilogue time);
 //   * x, v, grad U live in shared memory chain-major (row stride RS floats, conflict-free 128-bit accesses): one
 //     LDS.128 per 4 dimensions instead of 4 LDS.32;
-//   * the per-dimension constants of the heads epilogue are pre-multiplied on the host (TcNet::hc): tanh / exp of
+//   * the per-dimension constants of the heads epilogue are pre-multiplied on the host (TcNet::hc) and copied to shared
+//     memory once per CTA (as global loads their latency was ~18 % of the heads epilogue): tanh / exp of
 //     the S and Q heads run in log2 units with one reciprocal for both tanh (5 MUFU per dimension instead of 6 --
 //     MUFU is the floor of this epilogue: 16 lanes per clock per SM);
 //   * the A operand of the NEXT GEMM (net input [a | b], or x - mu for the Gaussian grad) is produced inside the
 //     heads / grad epilogue from values still in registers: no separate pass over the state;
-//   * one mbarrier arrival per warp (count 8) instead of one per thread (count 256) for a_ready;
+//   * one mbarrier arrival per warp (count 8) instead of one per thread (count 256);
+//   * biases ride in the GEMMs where the shape has pad rows (BIASG): a constant-1 hidden unit, and a direction one-hot in
+//     the net input that selects the time-embedding bias row of the chain's leapfrog step;
 //   * the epilogue of GEMM k and the MMAs of GEMM k+1 overlap: three accumulator regions in TMEM, the A operand
-//     handed over in K slots of 16 columns (= one ring slot of the B stream) through sub-barriers a_sub[0..NSUB),
+//     handed over in slots of 16 k (the chunks i of both threads of a chain) through sub-barriers a_sub[0..NSUB),
 //     chunks owned round-robin by the two threads of a chain so that they complete in K order, and the net input
 //     interleaved per chunk ([a0..3 | b0..3] = one K step; the embed weight image is permuted to match on the host);
 //   * the heads GEMM is split by dimensions into two GEMMs (first ceil(NQC/2) chunks | the rest, each with its S | T | Q
@@ -43,7 +47,7 @@ constexpr uint32_t S_AHI = 0, S_ALO = 104, S_R1 = 208, S_R2 = 320, S_R3 = 432;
 #endif
 // K steps per ring slot (= per bulk copy) of this kernel.  A bulk copy takes ~590 cycles whatever its size up to 32 KB
 // (profiles/r01_tc_probe.txt: 14 / 28 / 56 B/cycle for 8 / 16 / 32 KB), so the B stream (33 B/cycle per SM once every
-// GEMM overlaps an epilogue) wants few large copies; the A operand is still handed over per 2 K steps.
+// GEMM overlaps an epilogue) wants few large copies; the A operand is still handed over per slot of 16 k.
 constexpr int KSLOT_S = L2HMC_TC_KSLOT_S;
 static_assert(KSLOT_S % 2 == 0, "ring slot = whole A hand-over slots");
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
