@@ -348,7 +348,7 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   td.nq = (nqe && nqe[0] >= '2' && nqe[0] <= '4') ? (nqe[0] - '0') : 2;
   // kernel_tc_s: biases as weight rows (needs two pad dimensions in the last 4-dim chunk and a pad hidden unit)
   const char *bg = getenv("L2HMC_TC_BIASG");
-  td.biasg = (!(bg && bg[0] == '0') && sh.D <= sh.DP - 2 && sh.H <= td.HK - 1) ? 1 : 0;
+  td.biasg = (!(bg && bg[0] == '0') && sh.D <= sh.DP - 2 && sh.H <= td.HK - 1 && sh.DP == 52) ? 1 : 0;  // instantiated for DP = 52 only
   const char *fe = getenv("L2HMC_TC_F16");
   td.f16 = (fe && fe[0] == '0') ? 0 : 1;  // fp16 split when every packed value is inside the fp16 range (checked at pack time)
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;

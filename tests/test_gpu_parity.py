@@ -416,6 +416,25 @@ def test_tc_specialised_kernel_follows_eps_and_temperature():
     assert float(np.max(np.abs(pb.cpu().numpy() - pob.numpy()))) <= P_TOL
 
 
+@pytest.mark.parametrize("kind,D,H,T,mu_shift", [
+    ("gaussian", 52, 104, 6, 0.7),   # no pad dimension / hidden unit: explicit biases in the specialised kernel
+    ("gaussian", 49, 97, 7, -0.4),   # three pad dimensions, seven pad hidden units, odd Lf, non-zero mean
+    ("gaussian", 51, 103, 5, 0.0),   # one pad dimension only: no room for the direction one-hot -> explicit biases
+    ("roughwell", 30, 100, 4, 0.0),  # the 8 x 13 instantiation with pad dimensions
+    ("gaussian", 29, 98, 5, 0.3),    # Gaussian grad GEMM on the 8 x 13 instantiation
+])
+def test_tc_specialised_kernel_edge_shapes(kind, D, H, T, mu_shift):
+    """Every (x_dim, width) that maps to a specialised instantiation (x_dim padded to 52 or 32, width padded to 104), with
+    and without room for the biases in the GEMMs, against the oracle."""
+    kw = dict(mu=np.full(D, mu_shift)) if kind == "gaussian" else dict(easy=True)
+    P = U.Problem(kind=kind, D=D, H=H, T=T, eps=0.1, regime="stress", **kw)
+    dyn = P.product(kernel="tc")
+    rep, _ = U.parity_report(P, 200, dyn=dyn)
+    assert dyn.kernel_name in ("tc_3xf16", "tc_3xtf32")
+    _check(rep)
+    assert not dyn.fp16_range_exceeded()
+
+
 def test_tc_fp16_and_tf32_splits_agree_and_range_flag(monkeypatch):
     """The specialised kernel's fp16 operand split (three kind::f16 MMAs per product) against its tf32 split on the same
     inputs; and the sticky range flag when an operand leaves the fp16 range."""
