@@ -137,6 +137,9 @@ int l2hmc_set_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p); /* XNe
 int l2hmc_set_masks(l2hmc_ctx *ctx, const float *mask /* [T,D] of {0,1} */); /* Dynamics.mask utils/dynamics.py:84-97 */
 int l2hmc_set_eps(l2hmc_ctx *ctx, float eps);                 /* Dynamics.eps utils/dynamics.py:58 */
 int l2hmc_set_temperature(l2hmc_ctx *ctx, float temperature); /* Dynamics.temperature utils/dynamics.py:47,203-207 */
+/* Decoder energy only: U = beta * sum_pixels BCE + 0.5 |z|^2 -- the annealed energy (1-beta) prior + beta posterior of
+ * utils/ais.py:44-45 / eval_vae.py:52-62 (beta = 1: the sampler's energy, mnist_vae.py:122-126). */
+int l2hmc_set_likelihood_scale(l2hmc_ctx *ctx, float beta);
 /* Energy closure parameters (utils/distributions.py):
  *  GAUSSIAN : mu [D], S [D,D] (= i_sigma as fp32), n_comp = 1
  *  GMM      : mu [K,D], S [K,D,D], logc [K] (= log of the fp32 constants, :120-123), n_comp = K <= 8

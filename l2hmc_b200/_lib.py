@@ -113,6 +113,7 @@ EXPORTS = [
     ("l2hmc_set_masks", C.c_int, [_vp, _fp]),
     ("l2hmc_set_eps", C.c_int, [_vp, _f32]),
     ("l2hmc_set_temperature", C.c_int, [_vp, _f32]),
+    ("l2hmc_set_likelihood_scale", C.c_int, [_vp, _f32]),
     ("l2hmc_set_energy", C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int]),
     ("l2hmc_set_energy_decoder", C.c_int, [_vp, C.c_int, C.POINTER(_i32), C.POINTER(_fp), C.POINTER(_fp)]),
     ("l2hmc_set_aux_encoder", C.c_int, [_vp, C.c_int, C.POINTER(_i32), C.POINTER(_fp), C.POINTER(_fp)]),

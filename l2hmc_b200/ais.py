@@ -4,11 +4,14 @@
 arguments.  Each annealing step runs on the GPU through the same library as the sampler: the energies, the
 HMC-mode leapfrog transition (``Dynamics(hmc=True).forward``) and the Metropolis select (``tf_accept``).
 
-What is covered: both energies closed-form single Gaussians (``distributions.Gaussian``), for which
-``(1 - beta) U0 + beta U1`` is again a Gaussian energy (precision ``(1-beta) S0 + beta S1``) up to an additive
-constant that cancels in every Hamiltonian difference -- one HMC context whose energy parameters are re-sent per
-beta.  The reference's own use (eval_vae.py:52-65: prior -> decoder posterior) needs the annealed *decoder* energy in
-HMC mode on the layered engine, which this package does not have yet: that case raises NotImplementedError.
+What is covered:
+  * both energies closed-form single Gaussians (``distributions.Gaussian``), for which ``(1 - beta) U0 + beta U1`` is again
+    a Gaussian energy (precision ``(1-beta) S0 + beta S1``) up to an additive constant that cancels in every Hamiltonian
+    difference -- one HMC context whose energy parameters are re-sent per beta;
+  * the reference's own use (eval_vae.py:52-65): init_energy = standard normal prior, final_energy = the decoder posterior
+    ``vae.DecoderEnergy`` with ``aux`` = the images.  ``(1-beta) 0.5|z|^2 + beta (BCE + 0.5|z|^2) = beta BCE + 0.5|z|^2``: the
+    decoder energy with a likelihood weight (``l2hmc_set_likelihood_scale``), HMC mode on the layered engine.
+Other pairs raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -40,15 +43,26 @@ def ais_estimate(init_energy, final_energy, anneal_steps, initial_x, aux=None, s
     """utils/ais.py:30-82.  rng: optional explicit randomness {'v0' [N,D], 'v' [steps,N,D], 'u' [steps,N]} (parity
     tests); otherwise the library generator (Philox keyed by seed and step).  Returns (estimate, mean accept prob)
     like the reference, plus (x, w) when return_state."""
-    for e in (init_energy, final_energy):
-        if not isinstance(e, EnergyFunction):
-            raise TypeError("ais_estimate needs closed-form energies from l2hmc_b200.distributions (got %r)" % (e,))
-    if not (init_energy.kind == _lib.ENERGY_GAUSSIAN and final_energy.kind == _lib.ENERGY_GAUSSIAN and
-            init_energy.n_comp == 1 and final_energy.n_comp == 1):
-        raise NotImplementedError("ais_estimate covers Gaussian -> Gaussian annealing; the annealed decoder energy of "
-                                  "eval_vae.py needs HMC mode on the layered engine (not built yet)")
-    if aux is not None:
-        raise NotImplementedError("aux-conditioned final energies (eval_vae.py) are not covered yet")
+    decoder = getattr(final_energy, "kind", None) == _lib.ENERGY_DECODER
+    if decoder:
+        e0 = init_energy
+        std = (isinstance(e0, EnergyFunction) and e0.kind == _lib.ENERGY_GAUSSIAN and e0.n_comp == 1 and
+               np.allclose(e0.mu, 0.0) and np.allclose(e0.S[0], np.eye(e0.dim)))
+        if not std:
+            raise NotImplementedError("with a decoder final energy the initial energy must be the standard normal prior "
+                                      "(eval_vae.py:49-50)")
+        if aux is None:
+            raise TypeError("the decoder posterior needs aux (the images)")
+    else:
+        for e in (init_energy, final_energy):
+            if not isinstance(e, EnergyFunction):
+                raise TypeError("ais_estimate needs closed-form energies from l2hmc_b200.distributions (got %r)" % (e,))
+        if not (init_energy.kind == _lib.ENERGY_GAUSSIAN and final_energy.kind == _lib.ENERGY_GAUSSIAN and
+                init_energy.n_comp == 1 and final_energy.n_comp == 1):
+            raise NotImplementedError("ais_estimate covers Gaussian -> Gaussian annealing and standard normal -> decoder "
+                                      "posterior (eval_vae.py)")
+        if aux is not None:
+            raise NotImplementedError("aux is only consumed by the decoder posterior")
     x = initial_x.detach().to(TORCH_FLOAT).contiguous()
     if not x.is_cuda:
         raise TypeError("ais_estimate works on CUDA tensors")
@@ -72,13 +86,20 @@ def ais_estimate(init_energy, final_energy, anneal_steps, initial_x, aux=None, s
         else:
             z = randn_like(x, seed=seed, counter=2 * s + 1)
         rv = v * math.sqrt(1.0 - refreshment) + z * math.sqrt(refreshment) if refresh else z
-        w = w + beta_diff * (-final_energy(x) + init_energy(x))
-        mixed = _mixed_gaussian(init_energy, final_energy, float(beta[s]))
-        if dyn is None:
-            dyn = Dynamics(int(x_dim), mixed, T=int(leapfrogs), eps=float(step_size), hmc=True, device=dev.index)
+        if decoder:
+            w = w + beta_diff * (-final_energy(x, aux=aux) + init_energy(x))
+            if dyn is None:
+                dyn = Dynamics(int(x_dim), final_energy, T=int(leapfrogs), eps=float(step_size), hmc=True, device=dev.index)
+            dyn.set_likelihood_scale(float(beta[s]))   # curr_energy = beta * BCE + 0.5 |z|^2
+            Lx, Lv, px = dyn.forward(x, init_v=rv, aux=aux)
         else:
-            dyn.set_energy_function(mixed)
-        Lx, Lv, px = dyn.forward(x, init_v=rv)
+            w = w + beta_diff * (-final_energy(x) + init_energy(x))
+            mixed = _mixed_gaussian(init_energy, final_energy, float(beta[s]))
+            if dyn is None:
+                dyn = Dynamics(int(x_dim), mixed, T=int(leapfrogs), eps=float(step_size), hmc=True, device=dev.index)
+            else:
+                dyn.set_energy_function(mixed)
+            Lx, Lv, px = dyn.forward(x, init_v=rv)
         if rng is not None and "u" in rng:
             u = torch.as_tensor(np.asarray(rng["u"][s], dtype=np.float32)).to(dev)
         else:

@@ -60,6 +60,7 @@ struct LayeredCtx {
   long long ws_n = 0;
   cudaEvent_t ws_event = nullptr;  // recorded when a call's last workspace user is enqueued
   bool ws_recorded = false;
+  float like_scale = 1.0f;     // weight of the Bernoulli log-likelihood in the decoder energy (AIS: beta)
   const float *aux = nullptr;  // bound by l2hmc_bind_aux for the component calls
   long long aux_n = 0;
 };
@@ -821,6 +822,13 @@ extern "C" int l2hmc_set_eps(l2hmc_ctx *ctx, float eps) {
     int rc = tc_pack_hc(ctx, net_id);
     if (rc) return rc;
   }
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_likelihood_scale(l2hmc_ctx *ctx, float beta) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_likelihood_scale: null context");
+  if (!(beta >= 0.f) || !isfinite(beta)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_likelihood_scale: must be finite and >= 0");
+  ctx->lay.like_scale = beta;
   return L2HMC_OK;
 }
 

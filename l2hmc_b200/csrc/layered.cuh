@@ -251,8 +251,9 @@ __global__ void k_lay_grad_generic(LayDims dm, LayState st, EnergyDev en, Shape 
 }
 
 // Bernoulli decoder target (mnist_vae.py:122-126) given logits l = decoder(z):
-//   U = sum_j [max(l,0) - l a + log(1 + exp(-|l|))] + 0.5 |z|^2, all / temperature;  l <- dU/dl = sigmoid(l) - a.
-__global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const float *aux, float inv_temp,
+//   U = like * sum_j [max(l,0) - l a + log(1 + exp(-|l|))] + 0.5 |z|^2, all / temperature;  l <- dU/dl = like * (sigmoid(l) - a).
+// like = 1 for the sampler; the annealed energy of utils/ais.py:44-45 between the prior and this posterior is like = beta.
+__global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const float *aux, float inv_temp, float like,
                           long long n_chains) {
   const long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -265,7 +266,7 @@ __global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const
     const float e = expf(-fabsf(lj));
     s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
     const float r = __fdividef(1.f, 1.f + e);  // 1 + e in [1, 2]
-    l[j] = ((lj >= 0.f) ? r : e * r) - aj;
+    l[j] = like * (((lj >= 0.f) ? r : e * r) - aj);
   }
   float q = 0.f;
   for (int d = lane; d < dm.D; d += 32) {
@@ -274,7 +275,7 @@ __global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const
   }
   s = warp_sum(s);
   q = warp_sum(q);
-  if (lane == 0) st.U[n] = (s + 0.5f * q) * inv_temp;
+  if (lane == 0) st.U[n] = (like * s + 0.5f * q) * inv_temp;
 }
 
 __global__ void k_lay_add_h0(LayState st, long long n_chains) {

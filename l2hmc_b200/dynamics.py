@@ -221,6 +221,14 @@ class Dynamics(object):
         self._chk(self._lib.l2hmc_debug_counters(self._ctx, buf, 24))
         return bool(buf[23])
 
+    def set_likelihood_scale(self, beta):
+        """Decoder energy only: U = beta * sum BCE + 0.5 |z|^2, the annealed energy between the prior and the posterior
+        (utils/ais.py:44-45 with init_energy = standard normal, eval_vae.py:52-62)."""
+        if getattr(self._fn, "kind", None) != _lib.ENERGY_DECODER:
+            raise TypeError("set_likelihood_scale applies to the decoder energy")
+        self._ensure_ctx()
+        self._chk(self._lib.l2hmc_set_likelihood_scale(self._ctx, float(beta)))
+
     def set_energy_function(self, energy_function):
         """Replace the target of an existing Dynamics (same kind of descriptor, same dimension): the annealed energy of
         utils/ais.py:44-58 changes at every step while the leapfrog operator stays."""

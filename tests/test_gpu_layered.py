@@ -223,3 +223,32 @@ def test_sample_trace_is_the_notebook_loop_on_device():
     B = G.acl_spectrum(G.sample_trace(x0, H, 300), scale)
     assert A.shape == (299,) and 0.5 < float(A[0]) < 2.0 and 0.5 < float(B[0]) < 2.0
     assert 0.0 < G.ESS(A) <= 1.0 and 0.0 < G.ESS(B) <= 1.0
+
+
+def test_ais_on_the_vae_posterior_matches_oracle():
+    """eval_vae.py:49-65: annealing from the standard normal prior to the decoder posterior with HMC-mode Dynamics; the
+    annealed energy is the decoder energy with the likelihood weighted by beta (l2hmc_set_likelihood_scale)."""
+    from l2hmc_b200.ais import ais_estimate
+    from l2hmc_b200.distributions import Gaussian
+    P = U.VaeProblem(regime="stress", **U.VAE_CONFIGS["c5_vae_noenc"])
+    n, steps, L, eps = 192, 6, 4, 0.08
+    d = P.draws(n)
+    rng = np.random.default_rng(7)
+    r = {"v0": rng.standard_normal((n, P.D)).astype(np.float32), "v": rng.standard_normal((steps, n, P.D)).astype(np.float32),
+         "u": rng.random((steps, n)).astype(np.float32)}
+    e1 = U.O.DecoderBernoulliEnergy(P.dec_W, P.dec_b, d["aux"], torch.float64)
+    e0 = U.O.GaussianEnergy(np.zeros(P.D), np.eye(P.D))
+    est_o, alpha_o, x_o, w_o = U.O.ais_estimate(e0, e1, steps, d["x"], step_size=eps, leapfrogs=L, v0=r["v0"], v_refresh=r["v"],
+                                                u=r["u"], num_splits=3)
+    dyn = P.product()                                  # only to get the DecoderEnergy descriptor of this problem
+    final_energy = dyn._fn
+    prior = Gaussian(np.zeros(P.D), np.eye(P.D)).get_energy_function()
+    est, alpha, x, w = ais_estimate(prior, final_energy, steps, torch.as_tensor(d["x"]).cuda(), aux=torch.as_tensor(d["aux"]).cuda(),
+                                    step_size=eps, leapfrogs=L, x_dim=P.D, num_splits=3, rng=r, return_state=True)
+    same = np.abs(x.cpu().numpy() - x_o.numpy()).max(1) < 1e-3
+    assert same.mean() > 0.98
+    assert U.max_rel(x.cpu().numpy()[same], x_o.numpy()[same]) <= 5e-5
+    assert float(np.abs(w.cpu().numpy()[same] - w_o.numpy()[same]).max()) <= 5e-4 * max(1.0, float(np.abs(w_o.numpy()).max()))
+    assert abs(alpha - float(alpha_o)) <= 2e-4
+    # the weight changes what the sampler's energy calls return: put it back
+    dyn.set_likelihood_scale(1.0)
