@@ -1186,16 +1186,33 @@ static int transition_host_chunked(l2hmc_ctx *ctx, const l2hmc_transition_args *
   const bool want_next = a->x_next || a->do_mh;
   if (want_next && (rc = ensure(ctx, ctx->hxn, n * D))) return rc;
   if (a->accepted && (rc = ensure_u8(ctx, ctx->hacc, ctx->hacc_n, n))) return rc;
-  // chunk = two waves of 128-chain tiles (one tile per SM and wave), at least 4 chunks: the first copy in and the last
-  // copy out are the only ones that do not hide under a kernel
+  // chunks of two waves of 128-chain tiles (one tile per SM and wave), at least 4 chunks; the first and the last chunk are
+  // one wave only: their copy in / copy out are the ones that do not hide under a kernel
   const size_t sms = ctx->lay.sms > 0 ? (size_t)ctx->lay.sms : 148;
-  size_t per = 2 * sms * 128;
-  if (per * 4 > n) per = ((n + 3) / 4 + 127) / 128 * 128;
-  const int NCH = (int)((n + per - 1) / per);
+  const size_t wave = sms * 128;
+  std::vector<size_t> bounds;  // chunk c covers chains [bounds[c], bounds[c+1])
+  bounds.push_back(0);
+  if (n >= 8 * wave) {
+    size_t lo = wave;
+    bounds.push_back(lo);
+    while (n - lo > 3 * wave) {
+      lo += 2 * wave;
+      bounds.push_back(lo);
+    }
+    if (n - lo > wave) {  // what is left: one more middle chunk, then a last chunk of at most one wave
+      lo = n - wave;
+      bounds.push_back(lo);
+    }
+    bounds.push_back(n);
+  } else {
+    const size_t per = ((n + 3) / 4 + 127) / 128 * 128;
+    for (size_t lo = per; lo < n; lo += per) bounds.push_back(lo);
+    bounds.push_back(n);
+  }
+  const int NCH = (int)bounds.size() - 1;
   for (int c = 0; c < NCH; ++c) {
-    const size_t lo = (size_t)c * per;
-    if (lo >= n) break;
-    const size_t m = (lo + per <= n) ? per : n - lo;
+    const size_t lo = bounds[c];
+    const size_t m = bounds[c + 1] - lo;
     cudaStream_t s = ctx->hstreams[c % 3];
     l2hmc_transition_args d = *a;
     d.stream = s;
