@@ -1248,7 +1248,24 @@ static int transition_host_chunked(l2hmc_ctx *ctx, const l2hmc_transition_args *
   return L2HMC_OK;
 }
 
+static int transition_host_once(l2hmc_ctx *ctx, const l2hmc_transition_args *a);
+
+// The host-buffer entry point is synchronous, so it can afford to look at the fp16 range flag of the tensor-core
+// kernel: if an operand left the fp16 range the call is repeated with the tf32 split (fp32 range) and the context
+// stays on tf32.  Device-resident callers (l2hmc_transition) check l2hmc_debug_counters[23] themselves.
 extern "C" int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
+  int rc = transition_host_once(ctx, a);
+  if (rc != L2HMC_OK || !ctx || ctx->kernel != L2HMC_KERNEL_TC || !ctx->tc_used_f16) return rc;
+  long long flag = 0;
+  CUDA_TRY(ctx, cudaMemcpyFromSymbol(&flag, tc::g_tc_dbg, sizeof(flag), 23 * sizeof(long long)));
+  if (!flag) return L2HMC_OK;
+  flag = 0;
+  CUDA_TRY(ctx, cudaMemcpyToSymbol(tc::g_tc_dbg, &flag, sizeof(flag), 23 * sizeof(long long)));
+  ctx->td.f16 = 0;
+  return transition_host_once(ctx, a);
+}
+
+static int transition_host_once(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
   int rc = validate_transition(ctx, a, true);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));

@@ -456,6 +456,15 @@ def test_tc_fp16_and_tf32_splits_agree_and_range_flag(monkeypatch):
     big[0, 0] = 1.0e5                              # outside the fp16 range
     dyn._transition(big, **kw)
     assert dyn.fp16_range_exceeded()
+    # the synchronous host-buffer entry point notices, repeats the call with the tf32 split and stays on it
+    ref = P.product(kernel="tc")
+    monkeypatch.setenv("L2HMC_TC_F16", "0")
+    ref32 = P.product(kernel="tc")
+    r32 = ref32._transition(big, **kw)
+    monkeypatch.delenv("L2HMC_TC_F16", raising=False)
+    host = ref.transition_host(big.cpu().numpy(), v=v.cpu().numpy(), direction=dr.cpu().numpy(), u=u.cpu().numpy(), do_mh=True)
+    assert ref.kernel_name == "tc_3xtf32"
+    assert np.array_equal(host["x_next"], r32["x_next"].cpu().numpy())
 
 
 # ---- kernel selection: every kernel that covers a configuration must pass on it -------------------------
