@@ -49,7 +49,8 @@ struct LayTcWeight {  // one weight matrix pre-split / pre-tiled for tc_gemm_ker
 };
 struct LayeredCtx {
   layered::LayDims dm;
-  bool gemm_tc = true;                             // tcgen05 3xTF32 GEMMs (false: fp32 FMA sgemm_kernel)
+  bool gemm_tc = true;                             // tcgen05 split GEMMs (false: fp32 FMA sgemm_kernel)
+  bool gemm_f16 = false;                           // fp16 x3 operand split instead of tf32 x3 (L2HMC_LAYERED_GEMM=f16)
   std::map<const float *, LayTcWeight> tcw;        // keyed by the device pointer of the row-major weight
   int sms = 0;
   DevBuf net_buf[2];
@@ -641,7 +642,8 @@ extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
   lay_setup_dims(ctx);
   {
     const char *gm = getenv("L2HMC_LAYERED_GEMM");  // "fma" forces the fp32 FMA GEMMs
-    if (gm && gm[0] == 'f') ctx->lay.gemm_tc = false;
+    if (gm && gm[0] == 'f' && gm[1] == '1') ctx->lay.gemm_f16 = true;  // "f16"
+    else if (gm && gm[0] == 'f') ctx->lay.gemm_tc = false;             // "fma"
     cudaDeviceGetAttribute(&ctx->lay.sms, cudaDevAttrMultiProcessorCount, cfg->device);
   }
   int rc = pick_kernel(ctx);
@@ -1554,7 +1556,7 @@ extern "C" const char *l2hmc_kernel_name(const l2hmc_ctx *ctx) {
     case L2HMC_KERNEL_TILE: return "tile_fma";
     case L2HMC_KERNEL_SMALL: return "small_fma";
     case L2HMC_KERNEL_TC: return ctx->tc_used_f16 ? "tc_3xf16" : "tc_3xtf32";  // operand split of the last launch
-    case L2HMC_KERNEL_LAYERED: return ctx->lay.gemm_tc ? "layered_tc3xtf32" : "layered_fma";
+    case L2HMC_KERNEL_LAYERED: return ctx->lay.gemm_tc ? (ctx->lay.gemm_f16 ? "layered_tc3xf16" : "layered_tc3xtf32") : "layered_fma";
     default: return "none";
   }
 }

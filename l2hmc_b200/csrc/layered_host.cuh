@@ -29,7 +29,7 @@ int lay_tc_register(l2hmc_ctx *ctx, const float *dev_B, const float *host_B, int
   LayeredCtx &L = ctx->lay;
   std::vector<float> pk;
   LayTcWeight &w = L.tcw[dev_B];
-  l2hmc::tcg::pack_b(host_B, ldb, K, N, pk, &w.d);
+  l2hmc::tcg::pack_b(host_B, ldb, K, N, pk, &w.d, L.gemm_f16);
   int rc = ensure(ctx, w.buf, pk.size());
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpy(w.buf.p, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));

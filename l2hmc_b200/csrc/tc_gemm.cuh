@@ -15,10 +15,16 @@
 //   3-stage ring of 64 KB, k-block = 16 (two K=8 MMA steps x 3 products x 2 row halves); mbarriers full_a / full_b /
 //   empty per stage and acc_full / acc_empty for the accumulators.
 //
+// F16 = true (L2HMC_LAYERED_GEMM=f16): the same split with fp16 pairs and kind::f16 MMAs (K = 16 per MMA at the rate of a
+// K = 8 tf32 MMA): a stage of the same 64 KB then holds a k-block of 32 instead of 16 -- half the tensor time AND half the
+// shared-memory operand traffic per flop, which is what bounds the tf32 version (SS form).  fp16 range: |values| < 65504.
+//
 // Shared-memory operand layout (no swizzle, K-major): core matrix = 8 rows x 16 B (4 tf32) stored as 128 contiguous
 // bytes; [k-chunk][row-group][8][16 B], so LBO (K-adjacent core matrices) = rows/8 * 128 B and SBO (adjacent 8-row
 // groups) = 128 B -- the encoding verified by tools/tc_probe (profiles/r01_tc_probe.txt).
 #pragma once
+#include <cuda_fp16.h>
+
 #include <vector>
 
 #include "layered.cuh"
@@ -39,7 +45,8 @@ struct TcGemmB {
   const float *pk;
   int BN;    // columns per n-block (multiple of 16, <= 256)
   int nblk;  // n-blocks
-  int nkb;   // k-blocks (K padded to a multiple of 16 with zero rows)
+  int nkb;   // k-blocks (K padded to a multiple of the k-block with zero rows)
+  int f16;   // image holds fp16 hi / lo, k-block = 32 (else tf32, k-block = 16)
 };
 
 __host__ __device__ inline size_t b_block_floats(int BN) { return (size_t)2 * GBK * BN; }
@@ -55,6 +62,23 @@ __device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
       "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
       : "memory");
+}
+
+__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+      : "memory");
+}
+__host__ __device__ __forceinline__ uint32_t make_idesc_f16g(int M, int N) {  // kind::f16: A / B format 0 = f16, D format 1 = f32
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t pack_h2g(float k_even, float k_odd) {  // low half = lower k
+  const __half2 h = __floats2half2_rn(k_even, k_odd);
+  return *reinterpret_cast<const uint32_t *>(&h);
 }
 
 __device__ __forceinline__ void wait_spin(uint64_t *bar, uint32_t parity) {
@@ -83,8 +107,9 @@ __device__ __forceinline__ float epi_apply(float v, float aux, float scale) {
   return v;
 }
 
-template <int EPI>
+template <int EPI, bool F16>
 __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::GemmArgs g, const TcGemmB tb) {
+  constexpr int KB = F16 ? 2 * GBK : GBK;  // K elements per k-block (the stage bytes are the same)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned base (descriptors address in 16-byte units; keep stages well aligned)
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -136,7 +161,8 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
     }
     const long long total = my_tiles * nkb;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    auto load_blk = [&](long long flat, float4(&dst)[4]) {
+    constexpr int NV = F16 ? 2 : 1;  // float4 per 16-byte piece of the operand image (8 halfs or 4 tf32)
+    auto load_blk = [&](long long flat, float4(&dst)[4 * NV]) {
       if (flat >= total) return;
       const long long ti = flat / nkb;
       const int kb = (int)(flat - ti * nkb);
@@ -144,46 +170,75 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const long long m = mb * GROWS + mrow[i];
-        const int k = kb * GBK + kofs[i];
-        dst[i] = (m < g.M && k < g.K) ? __ldg(reinterpret_cast<const float4 *>(g.A + m * (long long)g.lda + k)) : z4;
+        const int k = kb * KB + kofs[i] * NV;
+#pragma unroll
+        for (int h = 0; h < NV; ++h)
+          dst[NV * i + h] = (m < g.M && k + 4 * h < g.K) ? __ldg(reinterpret_cast<const float4 *>(g.A + m * (long long)g.lda + k + 4 * h)) : z4;
       }
     };
-    auto put_blk = [&](long long flat, const float4(&src)[4]) {
+    auto put_blk = [&](long long flat, const float4(&src)[4 * NV]) {
       const int s = (int)(flat % GNS);
       const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
       wait_spin(&empty[s], ph ^ 1u);
       uint8_t *st = smem + s * SB;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        // hi = a with the 13 low mantissa bits cleared (what the tf32 datapath keeps), lo = a - hi exactly; the MMA
-        // reads lo's top 19 bits.  Two instructions per element: cvt.rna.tf32 lowers to ~7 (ncu: the A path, not the
+        // hi = a with the 13 low mantissa bits cleared (what the tf32 datapath keeps; exactly an fp16 inside its normal
+        // range), lo = a - hi exactly.  Two instructions per element: cvt.rna.tf32 lowers to ~7 (ncu: the A path, not the
         // tensor pipe, bounded the first version), and the dropped terms stay <= 2^-20 |a b|.
-        float4 hi, lo;
-        hi.x = trunc_tf32(src[i].x); lo.x = src[i].x - hi.x;
-        hi.y = trunc_tf32(src[i].y); lo.y = src[i].y - hi.y;
-        hi.z = trunc_tf32(src[i].z); lo.z = src[i].z - hi.z;
-        hi.w = trunc_tf32(src[i].w); lo.w = src[i].w - hi.w;
-        *reinterpret_cast<float4 *>(st + sofs[i]) = hi;
-        *reinterpret_cast<float4 *>(st + A_IMG + sofs[i]) = lo;
+        if (F16) {
+          const float a[8] = {src[2 * i].x, src[2 * i].y, src[2 * i].z, src[2 * i].w, src[2 * i + 1].x, src[2 * i + 1].y, src[2 * i + 1].z, src[2 * i + 1].w};
+          uint32_t hp[4], lp[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float h0 = trunc_tf32(a[2 * j]), h1 = trunc_tf32(a[2 * j + 1]);
+            hp[j] = pack_h2g(h0, h1);
+            lp[j] = pack_h2g(a[2 * j] - h0, a[2 * j + 1] - h1);
+          }
+          *reinterpret_cast<uint4 *>(st + sofs[i]) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+          *reinterpret_cast<uint4 *>(st + A_IMG + sofs[i]) = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+        } else {
+          float4 hi, lo;
+          hi.x = trunc_tf32(src[i].x); lo.x = src[i].x - hi.x;
+          hi.y = trunc_tf32(src[i].y); lo.y = src[i].y - hi.y;
+          hi.z = trunc_tf32(src[i].z); lo.z = src[i].z - hi.z;
+          hi.w = trunc_tf32(src[i].w); lo.w = src[i].w - hi.w;
+          *reinterpret_cast<float4 *>(st + sofs[i]) = hi;
+          *reinterpret_cast<float4 *>(st + A_IMG + sofs[i]) = lo;
+        }
       }
       tc::fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&full_a[s]);
     };
-    float4 b0[4], b1[4], b2[4];
-    load_blk(0, b0);
-    load_blk(1, b1);
-    load_blk(2, b2);
-    for (long long flat = 0; flat < total; flat += 3) {
-      put_blk(flat, b0);
-      load_blk(flat + 3, b0);
-      if (flat + 1 < total) {
-        put_blk(flat + 1, b1);
-        load_blk(flat + 4, b1);
+    if (F16) {  // two k-blocks in flight (a k-block is 32 floats per thread here)
+      float4 b0[4 * NV], b1[4 * NV];
+      load_blk(0, b0);
+      load_blk(1, b1);
+      for (long long flat = 0; flat < total; flat += 2) {
+        put_blk(flat, b0);
+        load_blk(flat + 2, b0);
+        if (flat + 1 < total) {
+          put_blk(flat + 1, b1);
+          load_blk(flat + 3, b1);
+        }
       }
-      if (flat + 2 < total) {
-        put_blk(flat + 2, b2);
-        load_blk(flat + 5, b2);
+    } else {
+      float4 b0[4 * NV], b1[4 * NV], b2[4 * NV];
+      load_blk(0, b0);
+      load_blk(1, b1);
+      load_blk(2, b2);
+      for (long long flat = 0; flat < total; flat += 3) {
+        put_blk(flat, b0);
+        load_blk(flat + 3, b0);
+        if (flat + 1 < total) {
+          put_blk(flat + 1, b1);
+          load_blk(flat + 4, b1);
+        }
+        if (flat + 2 < total) {
+          put_blk(flat + 2, b2);
+          load_blk(flat + 5, b2);
+        }
       }
     }
   } else if (warp < 16) {
@@ -277,7 +332,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
   } else {
     // ---------------- MMA issuer ----------------
     if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_tf32(GM, BN);
+      const uint32_t idesc = F16 ? make_idesc_f16g(GM, BN) : tc::make_idesc_tf32(GM, BN);
       const uint32_t lbo_a = (GM / 8) * 128, lbo_b = (uint32_t)(BN / 8) * 128;
       long long flat = 0;
       for (long long ti = 0; ti < my_tiles; ++ti) {
@@ -300,9 +355,15 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
               const uint64_t a_lo = tc::make_smem_desc(sah + A_IMG + ks * 2 * lbo_a, lbo_a, 128);
               const uint64_t b_hi = tc::make_smem_desc(sb + ks * 2 * lbo_b, lbo_b, 128);
               const uint64_t b_lo = tc::make_smem_desc(sb + B_HALF + ks * 2 * lbo_b, lbo_b, 128);
-              mma_tf32_ss(dacc, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first
-              mma_tf32_ss(dacc, a_hi, b_lo, idesc, true);
-              mma_tf32_ss(dacc, a_hi, b_hi, idesc, true);
+              if (F16) {
+                mma_f16_ss(dacc, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first
+                mma_f16_ss(dacc, a_hi, b_lo, idesc, true);
+                mma_f16_ss(dacc, a_hi, b_hi, idesc, true);
+              } else {
+                mma_tf32_ss(dacc, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first
+                mma_tf32_ss(dacc, a_hi, b_lo, idesc, true);
+                mma_tf32_ss(dacc, a_hi, b_hi, idesc, true);
+              }
             }
           }
           tc::tcgen05_commit(&empty[s]);
@@ -329,11 +390,14 @@ inline cudaError_t launch_tc_gemm(const layered::GemmArgs &g, const TcGemmB &tb,
   case E: {                                                                                                              \
     static thread_local size_t configured = 0;                                                                           \
     if (smem > configured) {                                                                                             \
-      e = cudaFuncSetAttribute(tc_gemm_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);               \
+      e = cudaFuncSetAttribute(tc_gemm_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
+      if (e != cudaSuccess) return e;                                                                                    \
+      e = cudaFuncSetAttribute(tc_gemm_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
       if (e != cudaSuccess) return e;                                                                                    \
       configured = smem;                                                                                                 \
     }                                                                                                                    \
-    tc_gemm_kernel<E><<<grid, G_THREADS, smem, s>>>(g, tb);                                                              \
+    if (tb.f16) tc_gemm_kernel<E, true><<<grid, G_THREADS, smem, s>>>(g, tb);                                            \
+    else tc_gemm_kernel<E, false><<<grid, G_THREADS, smem, s>>>(g, tb);                                                  \
   } break;
   switch (g.epi) {
     L2HMC_TCG_LAUNCH(layered::EPI_BIAS)
@@ -367,10 +431,12 @@ inline void choose_bn(int N, int *BN, int *nblk) {
 }
 
 // B [K][ldb] row-major (columns [0, N)) -> packed image; returns floats written. K rows beyond `K` are zero.
-inline size_t pack_b(const float *B, int ldb, int K, int N, std::vector<float> &out, TcGemmB *desc) {
+// f16: fp16 hi / lo, k-block = 32, core-matrix rows of 8 halfs (the image of a k-block has the same size in bytes).
+inline size_t pack_b(const float *B, int ldb, int K, int N, std::vector<float> &out, TcGemmB *desc, bool f16 = false) {
   int BN, nblk;
   choose_bn(N, &BN, &nblk);
-  const int nkb = (K + GBK - 1) / GBK;
+  const int kbe = f16 ? 2 * GBK : GBK;
+  const int nkb = (K + kbe - 1) / kbe;
   const size_t blk = b_block_floats(BN);
   const size_t base = out.size();
   out.resize(base + (size_t)nblk * nkb * blk, 0.f);
@@ -378,6 +444,22 @@ inline size_t pack_b(const float *B, int ldb, int K, int N, std::vector<float> &
   for (int nb = 0; nb < nblk; ++nb)
     for (int kb = 0; kb < nkb; ++kb) {
       float *hi = o + ((size_t)nb * nkb + kb) * blk, *lo = hi + (size_t)GBK * BN;
+      if (f16) {
+        uint16_t *hh = reinterpret_cast<uint16_t *>(hi), *lh = reinterpret_cast<uint16_t *>(lo);
+        for (int kc = 0; kc < 4; ++kc)
+          for (int ng = 0; ng < BN / 8; ++ng)
+            for (int r = 0; r < 8; ++r)
+              for (int e = 0; e < 8; ++e) {
+                const int n = nb * BN + ng * 8 + r, k = kb * kbe + kc * 8 + e;
+                const float w = (n < N && k < K) ? B[(size_t)k * ldb + n] : 0.f;
+                const __half h = __float2half_rn(w);
+                const __half l = __float2half_rn(w - __half2float(h));
+                const size_t idx = ((size_t)(kc * (BN / 8) + ng) * 8 + r) * 8 + e;
+                memcpy(&hh[idx], &h, 2);
+                memcpy(&lh[idx], &l, 2);
+              }
+        continue;
+      }
       for (int kc = 0; kc < GBK / 4; ++kc)
         for (int ng = 0; ng < BN / 8; ++ng)
           for (int r = 0; r < 8; ++r)
@@ -394,6 +476,7 @@ inline size_t pack_b(const float *B, int ldb, int K, int N, std::vector<float> &
   desc->BN = BN;
   desc->nblk = nblk;
   desc->nkb = nkb;
+  desc->f16 = f16 ? 1 : 0;
   return out.size() - base;
 }
 

@@ -56,7 +56,7 @@ def test_vae_target_on_fma_gemms(name, n):
 
 def test_default_layered_gemms_are_tensor_core():
     P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
-    assert P.product().kernel_name == "layered_tc3xtf32"
+    assert P.product().kernel_name in ("layered_tc3xtf32", "layered_tc3xf16")
 
 
 def test_vae_log_jac_mode():
