@@ -141,3 +141,27 @@ def test_shard_bounds_partition():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [h - l for l, h in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_ais_mixed_gaussian_is_the_annealed_energy_up_to_a_constant():
+    """ais._mixed_gaussian: (1 - beta) U0 + beta U1 of two Gaussian energies is one Gaussian energy plus a constant
+    (utils/ais.py:44-45); checked against the oracle's MixedEnergy on random points (energy differences and gradients)."""
+    import torch
+    import util as U
+    from l2hmc_b200.ais import _mixed_gaussian
+    from l2hmc_b200.distributions import Gaussian
+    rng = np.random.default_rng(0)
+    D = 5
+    A = rng.standard_normal((D, D))
+    g0 = Gaussian(rng.standard_normal(D), np.eye(D) * 1.5)
+    g1 = Gaussian(rng.standard_normal(D), A @ A.T / D + 0.2 * np.eye(D))
+    e0, e1 = g0.get_energy_function(), g1.get_energy_function()
+    x = torch.as_tensor(rng.standard_normal((64, D)))
+    for beta in (0.0, 0.3, 1.0):
+        m = _mixed_gaussian(e0, e1, beta)
+        mine = U.O.GaussianEnergy(m.mu[0], m.S[0], torch.float64)
+        ref = U.O.MixedEnergy(U.O.GaussianEnergy(e0.mu[0], e0.S[0], torch.float64), U.O.GaussianEnergy(e1.mu[0], e1.S[0], torch.float64), beta)
+        d_mine = mine.energy(x) - mine.energy(x[:1])
+        d_ref = ref.energy(x) - ref.energy(x[:1])
+        assert float((d_mine - d_ref).abs().max()) < 1e-5 * max(1.0, float(d_ref.abs().max()))
+        assert float((mine.grad(x) - ref.grad(x)).abs().max()) < 1e-5 * max(1.0, float(ref.grad(x).abs().max()))
