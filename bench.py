@@ -146,7 +146,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--kernel", default="auto")
-    ap.add_argument("--cpu-chains", type=int, default=1 << 12)
+    ap.add_argument("--cpu-chains", type=int, default=1 << 14,
+                    help="chains of the CPU arm's bounded sample (its throughput still grows a little with the sample)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
@@ -340,7 +341,7 @@ def main():
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        r = cpu_reference_run(steps=3, warmup=1, sample_chains=args.cpu_chains)
+        r = cpu_reference_run(steps=5, warmup=1, sample_chains=args.cpu_chains)
         cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
