@@ -648,3 +648,58 @@ def ais_estimate(e0: Energy, e1: Energy, anneal_steps: int, initial_x, *, step_s
     parts = torch.chunk(w, num_splits, dim=0)
     est = sum(lme(p) for p in parts)
     return est, torch.stack(alphas).mean(), x, w
+
+
+# --------------------------------------------------------------------------------------
+# Training objective (utils/losses.py:36-59, SCGExperiment.ipynb:159-181) -- oracle groundwork for SURVEY
+# section 8(f)3: the losses as the reference writes them, differentiated by torch autograd through this
+# restatement of the dynamics (the reference back-propagates through the unrolled tf.while_loop, including the
+# tf.gradients of the energy, i.e. second-order terms; grad() of every Energy here is a differentiable expression).
+# --------------------------------------------------------------------------------------
+def loss_vec(x, X, p):
+    """loss_vec (utils/losses.py:36-37): expected squared jump distance per chain, + 1e-4."""
+    return ((X - x) ** 2).sum(1) * p + 1e-4
+
+
+def loss_logsumexp(x, X, p):
+    v = loss_vec(x, X, p)
+    return torch.logsumexp(-v, 0) - math.log(v.shape[0])
+
+
+def loss_inverse(x, X, p):
+    v = loss_vec(x, X, p)
+    return -1.0 / (1.0 / (v + 1e-4)).mean()
+
+
+def loss_std(x, X, p):
+    return -loss_vec(x, X, p).mean(0)
+
+
+def loss_mixed(x, Lx, px, scale=1.0):
+    """loss_mixed (utils/losses.py:53-59)."""
+    v1 = loss_vec(x, Lx, px) / scale
+    return (1.0 / v1).mean() - v1.mean()
+
+
+def notebook_loss(x, z, dyn: OracleDynamics, rx: dict, rz: dict, scale=0.1):
+    """The SCG notebook's objective (SCGExperiment.ipynb:159-181): proposals from data samples x and from noise z,
+    loss = scale (E[1/v1] + E[1/v2]) - (E[v1] + E[v2]) / scale with v = |x - Lx|^2 p + 1e-4.
+    rx / rz: injected randomness of the two propose calls {'direction', 'v_f', 'v_b'}."""
+    x = x.to(dyn.dtype)
+    z = z.to(dyn.dtype)
+    Lx, _, px, _ = propose(x, dyn, direction=rx["direction"], v_f=rx["v_f"].to(dyn.dtype), v_b=rx["v_b"].to(dyn.dtype))
+    Lz, _, pz, _ = propose(z, dyn, direction=rz["direction"], v_f=rz["v_f"].to(dyn.dtype), v_b=rz["v_b"].to(dyn.dtype))
+    v1 = ((x - Lx) ** 2).sum(1) * px + 1e-4
+    v2 = ((z - Lz) ** 2).sum(1) * pz + 1e-4
+    return scale * ((1.0 / v1).mean() + (1.0 / v2).mean()) + (-v1.mean() - v2.mean()) / scale
+
+
+def trainable_parameters(dyn: OracleDynamics):
+    """The tensors the reference trains: both nets' weights / biases / scales (utils/layers.py:31-34,83-84); alpha =
+    log(eps) is trainable in the reference too (utils/dynamics.py:50-54) but is a constant of this restatement."""
+    ps = []
+    for net in (dyn.xnet, dyn.vnet):
+        for k in sorted(net):
+            net[k].requires_grad_(True)
+            ps.append(net[k])
+    return ps

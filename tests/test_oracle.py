@@ -283,3 +283,66 @@ def test_ais_oracle_recovers_the_normaliser_ratio():
     assert 0.5 < float(alpha) <= 1.0
     # the final particles target N(mu1, cov1) (weights aside: close already, the annealing is slow)
     assert np.abs(x.numpy().mean(0) - mu1).max() < 0.15
+
+
+def _train_setup(n=64, seed=5):
+    P = U.Problem(regime="stress", **U.CONFIGS["c1_scg2"])
+    dyn = P.oracle(torch.float64)
+    rng = np.random.default_rng(seed)
+
+    def draw():
+        return {"direction": torch.as_tensor(rng.integers(0, 2, n).astype(np.float64)),
+                "v_f": torch.as_tensor(rng.standard_normal((n, P.D))), "v_b": torch.as_tensor(rng.standard_normal((n, P.D)))}
+    x = torch.as_tensor(P.x0(n, rng)).double()
+    z = torch.as_tensor(rng.standard_normal((n, P.D)))
+    return P, dyn, x, z, draw
+
+
+def test_training_losses_and_gradient_through_the_dynamics():
+    """utils/losses.py and the notebook objective on the oracle: autograd through the unrolled leapfrog (second-order in
+    the energy) agrees with central finite differences of the same loss."""
+    P, dyn, x, z, draw = _train_setup()
+    rx, rz = draw(), draw()
+    params = U.O.trainable_parameters(dyn)
+    loss = U.O.notebook_loss(x, z, dyn, rx, rz)
+    assert torch.isfinite(loss)
+    grads = torch.autograd.grad(loss, params, allow_unused=True)
+    assert any(g is not None and float(g.abs().max()) > 0 for g in grads)
+    # finite differences on a few entries of the largest-gradient tensor
+    idx = max(range(len(params)), key=lambda i: 0.0 if grads[i] is None else float(grads[i].abs().max()))
+    w, g = params[idx], grads[idx]
+    flat = g.reshape(-1)
+    for j in torch.topk(flat.abs(), 3).indices.tolist():
+        h = 1e-6
+        with torch.no_grad():
+            w.reshape(-1)[j] += h
+            lp = float(U.O.notebook_loss(x, z, dyn, rx, rz))
+            w.reshape(-1)[j] -= 2 * h
+            lm = float(U.O.notebook_loss(x, z, dyn, rx, rz))
+            w.reshape(-1)[j] += h
+        fd = (lp - lm) / (2 * h)
+        assert abs(fd - float(flat[j])) <= 1e-5 * max(1.0, abs(fd)), (fd, float(flat[j]))
+    # the library of losses on the same proposal
+    with torch.no_grad():
+        Lx, _, px, _ = U.O.propose(x, dyn, direction=rx["direction"], v_f=rx["v_f"], v_b=rx["v_b"])
+        v = U.O.loss_vec(x, Lx, px)
+    assert float(U.O.loss_std(x, Lx, px)) == pytest.approx(-float(v.mean()))
+    assert float(U.O.loss_mixed(x, Lx, px, 0.1)) == pytest.approx(float((0.1 / v).mean() - (v / 0.1).mean()))
+    assert float(U.O.loss_inverse(x, Lx, px)) < 0 and torch.isfinite(U.O.loss_logsumexp(x, Lx, px))
+
+
+def test_a_few_adam_steps_lower_the_notebook_loss():
+    """The notebook's training loop (SCGExperiment.ipynb:254-270) in miniature on the oracle: Adam on both nets with fixed
+    randomness lowers the objective."""
+    P, dyn, x, z, draw = _train_setup(n=128)
+    rx, rz = draw(), draw()
+    params = U.O.trainable_parameters(dyn)
+    opt = torch.optim.Adam(params, lr=1e-3)
+    first = None
+    for it in range(12):
+        opt.zero_grad()
+        loss = U.O.notebook_loss(x, z, dyn, rx, rz)
+        loss.backward()
+        opt.step()
+        first = float(loss) if first is None else first
+    assert float(U.O.notebook_loss(x, z, dyn, rx, rz)) < first
