@@ -344,5 +344,47 @@ def test_a_few_adam_steps_lower_the_notebook_loss():
         loss = U.O.notebook_loss(x, z, dyn, rx, rz)
         loss.backward()
         opt.step()
-        first = float(loss) if first is None else first
+        first = float(loss.detach()) if first is None else first
     assert float(U.O.notebook_loss(x, z, dyn, rx, rz)) < first
+
+
+@pytest.mark.parametrize("name,temperature", [("c1_scg2", 1.0), ("c3_mog2", 1.0), ("c4_rw32", 1.0), ("funnel3", 1.0),
+                                              ("c1_scg2", 1.7)])
+def test_hand_written_reverse_pass_equals_autograd(name, temperature):
+    """oracle/l2hmc_reverse.py (the reverse sweep a CUDA backward kernel would follow: per sub-update vector-Jacobian
+    products, Hessian-vector products of the energy, no autograd) gives the gradient torch.autograd gets through the
+    restated dynamics -- every parameter tensor of both nets and d/d(eps) -- for mixed directions."""
+    import l2hmc_reverse as R
+    kw = dict(U.CONFIGS[name])
+    kw["T"] = min(kw["T"], 4)
+    kw["H"] = min(kw["H"], 12)
+    P = U.Problem(regime="stress", **kw)
+    dyn = P.oracle(torch.float64)
+    dyn.temperature = temperature
+    n = 24
+    rng = np.random.default_rng(11)
+
+    def draw():
+        return {"direction": torch.as_tensor(rng.integers(0, 2, n).astype(np.float64)),
+                "v_f": torch.as_tensor(rng.standard_normal((n, P.D))), "v_b": torch.as_tensor(rng.standard_normal((n, P.D)))}
+    x = torch.as_tensor(P.x0(n, rng)).double()
+    z = torch.as_tensor(rng.standard_normal((n, P.D)))
+    rx, rz = draw(), draw()
+
+    loss_h, g_h = R.notebook_loss_and_grads(x, z, dyn, rx, rz)
+    assert not any(t.requires_grad for t in dyn.xnet.values())
+
+    params = U.O.trainable_parameters(dyn)
+    dyn._eps = dyn._eps.clone().requires_grad_(True)
+    loss_a = U.O.notebook_loss(x, z, dyn, rx, rz)
+    grads = torch.autograd.grad(loss_a, params + [dyn._eps])
+    assert float(loss_h) == pytest.approx(float(loss_a.detach()), rel=1e-12)
+    keys = sorted(dyn.xnet)
+    flat_h = [g_h["xnet"][k] for k in keys] + [g_h["vnet"][k] for k in keys] + [g_h["eps"]]
+    worst = 0.0
+    for gh, ga in zip(flat_h, grads):
+        assert gh.shape == ga.shape
+        worst = max(worst, float((gh - ga).abs().max()) / max(1e-12, float(ga.abs().max())))
+    assert worst < 1e-9, worst
+    assert float(grads[-1].abs()) > 0 and all(float(g.abs().max()) > 0 for g in grads)
+    assert float(g_h["alpha"]) == pytest.approx(float((grads[-1] * dyn._eps).detach()), rel=1e-9)
