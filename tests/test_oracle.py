@@ -345,7 +345,7 @@ def test_a_few_adam_steps_lower_the_notebook_loss():
         loss.backward()
         opt.step()
         first = float(loss.detach()) if first is None else first
-    assert float(U.O.notebook_loss(x, z, dyn, rx, rz)) < first
+    assert float(U.O.notebook_loss(x, z, dyn, rx, rz).detach()) < first
 
 
 @pytest.mark.parametrize("name,temperature", [("c1_scg2", 1.0), ("c3_mog2", 1.0), ("c4_rw32", 1.0), ("funnel3", 1.0),
