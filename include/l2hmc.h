@@ -198,6 +198,37 @@ int l2hmc_acl_spectrum(l2hmc_ctx *ctx, int64_t n_steps, int64_t n, const float *
                        double *out, void *stream);
 
 /* ---- introspection ------------------------------------------------------------------------- */
+/* ---- training path (first-correct version) -------------------------------------------------
+ * Replaces, for one `propose` batch, what the reference obtains from TF1 autodiff: `tf.gradients(loss, params)` behind
+ * `AdamOptimizer.minimize(loss)` (SCGExperiment.ipynb:183-188) with
+ *   v = sum((x - Lx)^2) * px + 1e-4 ; loss = scale * mean(1 / v) - mean(v) / scale       (SCGExperiment.ipynb:171-181,
+ *   utils/losses.py:36-59),
+ * back-propagated through propose's selected direction (utils/sampler.py:34-44), p_accept (utils/dynamics.py:302-309),
+ * the unrolled leapfrog (:246-300) and tf.gradients(energy, x) inside it (:217-218).
+ * Gradient tensors have the shapes of l2hmc_net_params; every output is ACCUMULATED (+=) so that the caller zeroes once
+ * and adds the `x` batch and the `z` batch of the notebook objective.  Device pointers throughout; the call synchronises
+ * the stream.  Covers the Gaussian (one component) and RoughWell energies without aux; other targets: L2HMC_EUNSUPPORTED. */
+typedef struct {
+  float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4, *Ws, *bs, *Wt, *bt, *Wq, *bq, *scale_s, *scale_q;
+} l2hmc_net_grads;
+
+typedef struct {
+  int64_t n;              /* chains of this batch                                                */
+  const float *x;         /* [n,D] start points                                                  */
+  const float *v;         /* [n,D] the fresh momentum of each chain's direction (utils/sampler.py:35-36) */
+  const uint8_t *dir;     /* [n] 1 = forward (the `mask` of utils/sampler.py:34)                 */
+  float scale;            /* the notebook's `scale` (0.1)                                        */
+  float inv_count;        /* 1 / (number of chains the means run over)                           */
+  float *loss;            /* [1]  +=                                                             */
+  float *d_eps;           /* [1]  += d loss / d eps (the reference trains alpha = log eps: times eps) */
+  l2hmc_net_grads grad_xnet, grad_vnet; /* += */
+  float *x_out;           /* Lx [n,D] or NULL                                                    */
+  float *px_out;          /* [n] or NULL                                                         */
+  void *stream;
+} l2hmc_loss_grad_args;
+
+int l2hmc_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a);
+
 const char *l2hmc_kernel_name(const l2hmc_ctx *ctx); /* kernel the next l2hmc_transition will launch */
 int64_t l2hmc_launch_count(const l2hmc_ctx *ctx);    /* kernels launched by this context so far      */
 /* CUDA-event timing of the hot kernel on the launching stream: average ms over launches since reset. */

@@ -88,6 +88,17 @@ class NetParams(C.Structure):
                                    "Wq", "bq", "scale_s", "scale_q")]
 
 
+class NetGrads(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "Ws", "bs", "Wt", "bt",
+                                          "Wq", "bq", "scale_s", "scale_q")]
+
+
+class LossGradArgs(C.Structure):
+    _fields_ = [("n", C.c_int64), ("x", C.c_void_p), ("v", C.c_void_p), ("dir", C.c_void_p), ("scale", C.c_float),
+                ("inv_count", C.c_float), ("loss", C.c_void_p), ("d_eps", C.c_void_p), ("grad_xnet", NetGrads),
+                ("grad_vnet", NetGrads), ("x_out", C.c_void_p), ("px_out", C.c_void_p), ("stream", C.c_void_p)]
+
+
 class TransitionArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("chain_offset", C.c_int64),
                 ("x", C.c_void_p), ("v", C.c_void_p), ("dir", C.c_void_p), ("u", C.c_void_p),
@@ -129,6 +140,7 @@ EXPORTS = [
     ("l2hmc_accept", C.c_int, [_vp, _i64, _i64, _vp, _vp, _vp, _vp, _u64, _u64, _vp, _vp, _vp]),
     ("l2hmc_philox_fill", C.c_int, [_vp, _i64, _i64, _u64, _u64, _vp, _vp, _vp, _vp]),
     ("l2hmc_acl_spectrum", C.c_int, [_vp, _i64, _i64, _vp, C.c_double, _i64, _vp, _vp]),
+    ("l2hmc_loss_grad", C.c_int, [_vp, C.POINTER(LossGradArgs)]),
     ("l2hmc_kernel_name", C.c_char_p, [_vp]),
     ("l2hmc_launch_count", _i64, [_vp]),
     ("l2hmc_timing_enable", C.c_int, [_vp, C.c_int]),

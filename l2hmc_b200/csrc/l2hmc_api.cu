@@ -1595,3 +1595,27 @@ extern "C" int l2hmc_timing_read(l2hmc_ctx *ctx, double *avg_ms, int64_t *launch
   ctx->ev_used = 0;
   return L2HMC_OK;
 }
+
+// ---- training path (train.cuh / train_host.cuh) ------------------------------------------------------------------
+#include "train_host.cuh"
+
+extern "C" int l2hmc_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
+  int rc = check_ready(ctx, "l2hmc_loss_grad");
+  if (rc) return rc;
+  if (!a) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: null args");
+  if (ctx->sh.hmc) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: an HMC-mode context has no parameters to train");
+  if (!ctx->mask_set) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: masks not set (l2hmc_set_masks)");
+  if (!(ctx->net_set[0] && ctx->net_set[1])) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: XNet/VNet not set (l2hmc_set_net)");
+  const bool covered = (ctx->en.kind == L2HMC_ENERGY_GAUSSIAN && ctx->en.ncomp == 1) || ctx->en.kind == L2HMC_ENERGY_ROUGHWELL;
+  if (!covered || ctx->lay.enc.n_layers > 0)
+    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_loss_grad: covers the Gaussian and RoughWell energies without aux (kind %d given)",
+                ctx->en.kind);
+  if (a->n < 0) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: n < 0");
+  if (a->n == 0) return L2HMC_OK;
+  if (!a->x || !a->v || !a->dir || !a->loss || !a->d_eps || !tr_grads_complete(a->grad_xnet) || !tr_grads_complete(a->grad_vnet))
+    return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: x, v, dir, loss, d_eps and all 2 x 16 gradient tensors are required");
+  if (!(a->scale > 0.f) || !isfinite(a->scale) || !isfinite(a->inv_count))
+    return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: scale must be finite and > 0, inv_count finite");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  return tr_loss_grad(ctx, a);
+}

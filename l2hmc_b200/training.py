@@ -1,0 +1,162 @@
+"""Training path: the SCG notebook's objective, its gradient and its optimiser loop on the GPU.
+
+FIRST-CORRECT version: the gradient the reference gets from TF1 autodiff --
+``optimizer.minimize(loss)`` (SCGExperiment.ipynb:183-188) through ``propose`` (utils/sampler.py:28-51), ``p_accept``
+(utils/dynamics.py:302-309), the unrolled leapfrog (:246-300) and ``tf.gradients(energy, x)`` inside it (:217-218) -- is
+computed by ``l2hmc_loss_grad`` (csrc/train.cuh: a recorded forward sweep and a hand-written reverse sweep, plain fp32
+FMA GEMMs).  Gaussian (one component) and RoughWell targets, no aux.  No CPU fallback.
+
+    loss, grads, Lx, px = loss_and_grads(dynamics, x)                  # one propose batch
+    state = train_step(dynamics, opt, samples)                         # one iteration of SCGExperiment.ipynb:254-270
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .dynamics import TORCH_FLOAT
+from .layers import load_stq_net
+from .sampler import tf_accept
+
+NAMES = ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "Ws", "bs", "Wt", "bt", "Wq", "bq", "ls", "lq")
+_ABI = {"ls": "scale_s", "lq": "scale_q"}
+
+
+def _draw(dynamics, n, device, want_u=False):
+    """Direction bits, momenta (and accept uniforms) from the in-kernel Philox stream (l2hmc_philox_fill)."""
+    v = torch.empty((n, dynamics.x_dim), dtype=TORCH_FLOAT, device=device)
+    d = torch.empty((n,), dtype=torch.uint8, device=device)
+    u = torch.empty((n,), dtype=TORCH_FLOAT, device=device) if want_u else None
+    dynamics._chk(dynamics._lib.l2hmc_philox_fill(dynamics._ctx, n, 0, dynamics.seed, dynamics.next_counter(), v.data_ptr(),
+                                                  d.data_ptr(), u.data_ptr() if want_u else None, dynamics._stream()))
+    return d, v, u
+
+
+def zero_grads(dynamics, device) -> Dict[str, object]:
+    """Gradient accumulators shaped like the parameters: {'XNet': {...}, 'VNet': {...}, 'eps': [1], 'loss': [1]}."""
+    def like(p):
+        return {k: torch.zeros(tuple(np.shape(p[k])), dtype=TORCH_FLOAT, device=device) for k in NAMES}
+    return {"XNet": like(dynamics._net_params[0]), "VNet": like(dynamics._net_params[1]),
+            "eps": torch.zeros(1, dtype=TORCH_FLOAT, device=device), "loss": torch.zeros(1, dtype=TORCH_FLOAT, device=device)}
+
+
+def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale: float = 0.1, count: Optional[int] = None):
+    """Add one propose batch to ``acc`` (from zero_grads): loss += scale mean(1/v) - mean(v)/scale with
+    v = |x - Lx|^2 px + 1e-4 (SCGExperiment.ipynb:171-181; utils/losses.py:36-59), gradients likewise.
+    rng: optional {'direction' uint8 [N], 'v' [N, D]}; drawn from the Philox stream otherwise.  ``count``: the number of
+    chains the means run over (default N).  Returns (Lx, px)."""
+    if dynamics.hmc:
+        raise ValueError("an HMC-mode Dynamics has no parameters to train")
+    dynamics._ensure_ctx()
+    dynamics._sync_temperature()
+    x = dynamics._prep(x, "x", dynamics.x_dim)
+    n, dev = x.shape[0], x.device
+    rng = rng or {}
+    if "direction" in rng and "v" in rng:
+        d = rng["direction"].detach().to(device=dev, dtype=torch.uint8).contiguous()
+        v = dynamics._prep(rng["v"], "v", dynamics.x_dim)
+    else:
+        d, v, _ = _draw(dynamics, n, dev)
+        d = rng["direction"].detach().to(device=dev, dtype=torch.uint8).contiguous() if "direction" in rng else d
+        v = dynamics._prep(rng["v"], "v", dynamics.x_dim) if "v" in rng else v
+    if d.numel() != n or v.shape[0] != n:
+        raise ValueError("direction and v must have N rows")
+    Lx = torch.empty((n, dynamics.x_dim), dtype=TORCH_FLOAT, device=dev)
+    px = torch.empty((n,), dtype=TORCH_FLOAT, device=dev)
+    a = _lib.LossGradArgs()
+    a.n, a.x, a.v, a.dir = n, x.data_ptr(), v.data_ptr(), d.data_ptr()
+    a.scale, a.inv_count = float(scale), 1.0 / float(count if count is not None else n)
+    a.loss, a.d_eps = acc["loss"].data_ptr(), acc["eps"].data_ptr()
+    for field, key in (("grad_xnet", "XNet"), ("grad_vnet", "VNet")):
+        g = getattr(a, field)
+        for k in NAMES:
+            t = acc[key][k]
+            if not (t.is_cuda and t.dtype == TORCH_FLOAT and t.is_contiguous()):
+                raise TypeError("gradient accumulators must be contiguous fp32 CUDA tensors")
+            setattr(g, _ABI.get(k, k), t.data_ptr())
+    a.x_out, a.px_out, a.stream = Lx.data_ptr(), px.data_ptr(), dynamics._stream()
+    dynamics._chk(dynamics._lib.l2hmc_loss_grad(dynamics._ctx, C.byref(a)))
+    return Lx, px
+
+
+def loss_and_grads(dynamics, x, *, rng=None, scale=0.1):
+    """Value and gradient of one propose batch.  Returns (loss [1], grads, Lx, px); grads['alpha'] is the gradient for
+    the reference's trainable ``alpha = log(eps)`` (utils/dynamics.py:50-58)."""
+    acc = zero_grads(dynamics, x.device)
+    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng, scale=scale)
+    acc["alpha"] = acc["eps"] * dynamics.eps
+    return acc["loss"], acc, Lx, px
+
+
+def notebook_loss_and_grads(dynamics, x, z, *, rng_x=None, rng_z=None, scale=0.1):
+    """The notebook objective (SCGExperiment.ipynb:159-181): proposals from the samples x and from noise z.
+    Returns (loss [1], grads, Lx, px) with Lx, px those of the x batch (what the training loop feeds back)."""
+    acc = zero_grads(dynamics, x.device)
+    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng_x, scale=scale)
+    accumulate_loss_grads(dynamics, z, acc, rng=rng_z, scale=scale)
+    acc["alpha"] = acc["eps"] * dynamics.eps
+    return acc["loss"], acc, Lx, px
+
+
+class Adam(object):
+    """tf.train.AdamOptimizer(learning_rate) with the notebook's schedule
+    tf.train.exponential_decay(1e-3, global_step, 1000, 0.96, staircase=True) (SCGExperiment.ipynb:183-186);
+    moments live on the GPU, the parameters in the Dynamics' layer objects."""
+
+    def __init__(self, dynamics, learning_rate=1e-3, decay_steps=1000, decay_rate=0.96, beta1=0.9, beta2=0.999, epsilon=1e-8,
+                 eps_trainable=True):
+        self.lr0, self.decay_steps, self.decay_rate = float(learning_rate), int(decay_steps), float(decay_rate)
+        self.b1, self.b2, self.epsilon = float(beta1), float(beta2), float(epsilon)
+        self.global_step = 0
+        self.eps_trainable = bool(eps_trainable)
+        self._m, self._v = {}, {}
+
+    @property
+    def learning_rate(self):
+        return self.lr0 * self.decay_rate ** (self.global_step // self.decay_steps)
+
+    def _update(self, name, p, g):
+        m = self._m.get(name)
+        if m is None:
+            m = self._m[name] = torch.zeros_like(g)
+            self._v[name] = torch.zeros_like(g)
+        v = self._v[name]
+        m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
+        v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+        t = self.global_step + 1
+        lr_t = self.learning_rate * np.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)   # TF's formulation
+        return p - lr_t * m / (v.sqrt() + self.epsilon)
+
+    def apply(self, dynamics, grads):
+        dev = grads["loss"].device
+        for i, key in enumerate(("XNet", "VNet")):
+            new = {}
+            for k in NAMES:
+                p = torch.as_tensor(np.asarray(dynamics._net_params[i][k], np.float32), device=dev)
+                new[k] = self._update(key + "/" + k, p, grads[key][k].reshape(p.shape)).cpu().numpy()
+            load_stq_net(dynamics.XNet if i == 0 else dynamics.VNet, new)
+        dynamics.refresh()
+        if self.eps_trainable:
+            alpha = torch.as_tensor(np.float32(dynamics.alpha), device=dev).reshape(1)
+            g_alpha = grads["eps"] * dynamics.eps
+            dynamics.eps = float(torch.exp(self._update("alpha", alpha, g_alpha))[0])
+        self.global_step += 1
+
+
+def train_step(dynamics, opt, samples, *, scale=0.1, rng_x=None, rng_z=None, z=None, u=None):
+    """One iteration of the notebook's loop (SCGExperiment.ipynb:254-270): loss on the current samples and on fresh noise,
+    Adam update, and the Metropolis-Hastings output ``tf_accept(x, Lx, px)`` as the next samples (:159-160).
+    Returns dict(loss, px, samples, learning_rate)."""
+    x = dynamics._prep(samples, "samples", dynamics.x_dim)
+    if z is None:
+        dynamics._ensure_ctx()
+        _, z, _ = _draw(dynamics, x.shape[0], x.device)   # tf.random_normal(tf.shape(x)) (:161)
+    lr = opt.learning_rate
+    loss, grads, Lx, px = notebook_loss_and_grads(dynamics, x, z, rng_x=rng_x, rng_z=rng_z, scale=scale)
+    nxt = tf_accept(x, Lx, px, u=u, seed=dynamics.seed, counter=dynamics.next_counter())
+    opt.apply(dynamics, grads)
+    return {"loss": float(loss[0]), "px": px, "samples": nxt, "learning_rate": lr}

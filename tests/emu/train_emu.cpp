@@ -1,0 +1,261 @@
+// TEST INFRASTRUCTURE (CPU suite only; never part of libl2hmc.so).
+// Runs the SOURCE of the training-path kernels (l2hmc_b200/csrc/train.cuh) and of their host driver (train_host.cuh) on
+// host threads, so that `pytest -m "not gpu"` can check index arithmetic, strides, the GEMM tiling, the sweep order and
+// the vector-Jacobian products against oracle/l2hmc_reverse.py without a GPU.  One pool thread per CUDA thread of a
+// block; blocks run one after another; __syncthreads / warp shuffles are barriers over the block / the warp; atomicAdd
+// takes a lock.  The component kernels the driver borrows from l2hmc_api.cu (k_grad, k_hamiltonian: already checked on
+// the GPU) are restated here for the two energies the training path covers.
+//
+// Build (tests/test_train_emu.py does this):  g++ -std=c++20 -O1 -pthread -shared -fPIC -DL2HMC_TRAIN_EMU ...
+#include <math.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <barrier>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/l2hmc.h"
+
+// ---- CUDA vocabulary --------------------------------------------------------------------------------------------
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __restrict__
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct uint3_ {
+  unsigned x, y, z;
+};
+static thread_local uint3_ threadIdx, blockIdx;
+static thread_local dim3 blockDim, gridDim;
+
+typedef int cudaError_t;
+typedef void *cudaStream_t;
+enum { cudaSuccess = 0, cudaMemcpyDeviceToDevice = 3 };
+static inline cudaError_t cudaMalloc(void **p, size_t bytes) { return (*p = malloc(bytes)) ? 0 : 2; }
+static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
+static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
+static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return 0; }
+static inline cudaError_t cudaGetLastError() { return 0; }
+static inline cudaError_t cudaSetDevice(int) { return 0; }
+static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+
+static thread_local bool emu_in_worker = false;
+namespace emu {
+constexpr int MAX_THREADS = 256;
+static std::mutex atomic_lock;
+static std::unique_ptr<std::barrier<>> block_bar;
+static std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+static float warp_buf[MAX_THREADS];
+
+// kernels that synchronise (block barrier or warp shuffles) need their threads alive together; the others run their
+// threads one after another on the calling thread
+static bool cooperative(const char *name) {
+  for (const char *k : {"k_gemm", "k_update", "k_update_vjp", "k_loss"})
+    if (strstr(name, k) && strlen(strstr(name, k)) == strlen(k)) return true;
+  return false;
+}
+
+template <class F>
+void launch(const char *name, dim3 grid, dim3 block, F &&body) {
+  const int nt = (int)block.x;
+  if (nt > MAX_THREADS || block.y != 1 || block.z != 1 || nt % 32 != 0) abort();
+  if (!cooperative(name)) {
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+      for (unsigned by = 0; by < grid.y; ++by)
+        for (unsigned bx = 0; bx < grid.x; ++bx)
+          for (int t = 0; t < nt; ++t) {
+            threadIdx = {(unsigned)t, 0, 0};
+            blockIdx = {bx, by, bz};
+            blockDim = block;
+            gridDim = grid;
+            body();
+          }
+    return;
+  }
+  block_bar.reset(new std::barrier<>(nt));
+  warp_bar.clear();
+  for (int w = 0; w < nt / 32; ++w) warp_bar.emplace_back(new std::barrier<>(32));
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        std::vector<std::thread> th;
+        th.reserve(nt);
+        for (int t = 0; t < nt; ++t)
+          th.emplace_back([&, t] {
+            emu_in_worker = true;
+            threadIdx = {(unsigned)t, 0, 0};
+            blockIdx = {bx, by, bz};
+            blockDim = block;
+            gridDim = grid;
+            body();
+            // a thread that left early must not leave the others waiting: drop out of both barriers
+            block_bar->arrive_and_drop();
+            warp_bar[t / 32]->arrive_and_drop();
+          });
+        for (auto &x : th) x.join();
+        // barriers lost their participants: rebuild for the next block
+        block_bar.reset(new std::barrier<>(nt));
+        for (int w = 0; w < nt / 32; ++w) warp_bar[w].reset(new std::barrier<>(32));
+      }
+}
+}  // namespace emu
+
+static inline void __syncthreads() {
+  if (!emu_in_worker) abort();  // a kernel that synchronises was launched as non-cooperative
+  emu::block_bar->arrive_and_wait();
+}
+static inline float __shfl_xor_sync(unsigned, float v, int o) {
+  if (!emu_in_worker) abort();
+  const int t = (int)threadIdx.x;
+  emu::warp_buf[t] = v;
+  emu::warp_bar[t / 32]->arrive_and_wait();
+  const float r = emu::warp_buf[t ^ o];
+  emu::warp_bar[t / 32]->arrive_and_wait();
+  return r;
+}
+static inline float atomicAdd(float *p, float v) {
+  std::lock_guard<std::mutex> g(emu::atomic_lock);
+  const float old = *p;
+  *p = old + v;
+  return old;
+}
+
+// ---- the few types of common.cuh / l2hmc_api.cu the training path touches -------------------------------------------
+namespace l2hmc {
+struct NetRaw {
+  const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4, *Ws, *bs, *Wt, *bt, *Wq, *bq, *ls, *lq;
+};
+struct EnergyDev {
+  int kind, ncomp;
+  const float *mu, *Ssym, *logc;
+  float s0, s1, temperature;
+};
+struct Shape {
+  int D, DP, H, HP, T, LDE, LDH, LDS, hmc;
+  float eps;
+};
+}  // namespace l2hmc
+using l2hmc::EnergyDev;
+using l2hmc::NetRaw;
+using l2hmc::Shape;
+
+struct DevBufEmu {
+  float *p = nullptr;
+};
+struct l2hmc_ctx {
+  Shape sh;
+  EnergyDev en;
+  DevBufEmu mask;
+  NetRaw net_rawv[2];
+  long long launches = 0;
+  std::string err;
+};
+
+static int fail(l2hmc_ctx *ctx, int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  return code;
+}
+#define CUDA_TRY(ctx, expr)                                        \
+  do {                                                             \
+    if ((expr) != cudaSuccess) return fail(ctx, L2HMC_ECUDA, #expr); \
+  } while (0)
+#define GRID(n) (unsigned)(((n) + 127) / 128), 128
+
+// grad U / T_emp and U / T_emp for the Gaussian and RoughWell energies (restated; the real kernels live in l2hmc_api.cu)
+static float emu_energy(const EnergyDev &en, const Shape &sh, const float *x) {
+  float U = 0.f;
+  if (en.kind == 0) {
+    for (int j = 0; j < sh.D; ++j) {
+      float r = 0.f;
+      for (int i = 0; i < sh.D; ++i) r = fmaf(x[i] - en.mu[i], en.Ssym[i * sh.LDS + j], r);
+      U = fmaf(r, x[j] - en.mu[j], U);
+    }
+    U *= 0.5f;
+  } else {
+    float n = 0.f, cs = 0.f;
+    for (int i = 0; i < sh.D; ++i) {
+      n = fmaf(x[i], x[i], n);
+      cs += cosf(x[i] / en.s1);
+    }
+    U = 0.5f * n + en.s0 * cs;
+  }
+  return U / en.temperature;
+}
+static void k_grad(EnergyDev en, Shape sh, long long n, const float *x, float *out) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const float *xr = x + g * sh.D;
+  for (int j = 0; j < sh.D; ++j) {
+    float r;
+    if (en.kind == 0) {
+      r = 0.f;
+      for (int i = 0; i < sh.D; ++i) r = fmaf(xr[i] - en.mu[i], en.Ssym[i * sh.LDS + j], r);
+    } else {
+      r = xr[j] - en.s0 * sinf(xr[j] / en.s1) / en.s1;
+    }
+    out[g * sh.D + j] = r / en.temperature;
+  }
+}
+static void k_hamiltonian(EnergyDev en, Shape sh, long long n, const float *x, const float *v, float *out) {
+  const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  float s = 0.f;
+  for (int d = 0; d < sh.D; ++d) s = fmaf(v[g * sh.D + d], v[g * sh.D + d], s);
+  out[g] = emu_energy(en, sh, x + g * sh.D) + 0.5f * s;
+}
+
+#include "../../l2hmc_b200/csrc/train_host.cuh"
+
+// ---- entry point for tests/test_train_emu.py -----------------------------------------------------------------------
+// Parameters in the reference layout (l2hmc_net_params order, host pointers); energy: kind 0 (mu [D], S [D, D]) or 2
+// (scalars eps, denominator).  Gradients are written to gx / gv (16 tensors each, caller-zeroed).
+extern "C" int emu_loss_grad(int D, int H, int T, float eps, float temperature, int kind, const float *mu, const float *S,
+                             float s0, float s1, const float *mask, const l2hmc_net_params *xnet, const l2hmc_net_params *vnet,
+                             const l2hmc_loss_grad_args *a, char *err, int err_len) {
+  l2hmc_ctx ctx;
+  Shape &sh = ctx.sh;
+  sh.D = D; sh.DP = (D + 3) / 4 * 4; sh.H = H; sh.HP = (H + 3) / 4 * 4; sh.T = T; sh.LDE = 128; sh.LDH = 192;
+  sh.LDS = (sh.DP + 127) / 128 * 128; sh.hmc = 0; sh.eps = eps;
+  std::vector<float> mu_p(sh.DP, 0.f), S_p((size_t)sh.DP * sh.LDS, 0.f), mask_p((size_t)T * sh.DP, 0.f);
+  if (kind == 0)
+    for (int i = 0; i < D; ++i) {
+      mu_p[i] = mu[i];
+      for (int j = 0; j < D; ++j) S_p[(size_t)i * sh.LDS + j] = 0.5f * (S[i * D + j] + S[j * D + i]);
+    }
+  for (int t = 0; t < T; ++t)
+    for (int d = 0; d < D; ++d) mask_p[(size_t)t * sh.DP + d] = mask[t * D + d];
+  ctx.en = EnergyDev{kind, 1, mu_p.data(), S_p.data(), nullptr, s0, s1, temperature};
+  ctx.mask.p = mask_p.data();
+  const l2hmc_net_params *ps[2] = {xnet, vnet};
+  for (int i = 0; i < 2; ++i) {
+    const l2hmc_net_params *p = ps[i];
+    ctx.net_rawv[i] = NetRaw{p->W1, p->b1, p->W2, p->b2, p->W3, p->b3, p->W4, p->b4, p->Ws, p->bs,
+                             p->Wt, p->bt, p->Wq, p->bq, p->scale_s, p->scale_q};
+  }
+  if (!tr_grads_complete(a->grad_xnet) || !tr_grads_complete(a->grad_vnet)) return L2HMC_EINVAL;
+  const int rc = tr_loss_grad(&ctx, a);
+  if (err && err_len > 0) snprintf(err, err_len, "%s", ctx.err.c_str());
+  return rc;
+}

@@ -165,3 +165,40 @@ def test_ais_mixed_gaussian_is_the_annealed_energy_up_to_a_constant():
         d_ref = ref.energy(x) - ref.energy(x[:1])
         assert float((d_mine - d_ref).abs().max()) < 1e-5 * max(1.0, float(d_ref.abs().max()))
         assert float((mine.grad(x) - ref.grad(x)).abs().max()) < 1e-5 * max(1.0, float(ref.grad(x).abs().max()))
+
+
+def test_training_adam_is_tensorflow_adam_with_the_notebook_schedule():
+    """training.Adam (tf.train.AdamOptimizer + exponential_decay(1e-3, step, 1000, 0.96, staircase),
+    SCGExperiment.ipynb:183-186) against torch.optim.Adam on the same gradients; parameters flow back into the layer
+    objects and alpha = log(eps) is trained with them (utils/dynamics.py:50-58).  Host logic only: no GPU involved."""
+    from l2hmc_b200 import training
+    P = U.Problem(regime="stress", **U.CONFIGS["c1_scg2"])
+    dyn = P.product()
+    opt = training.Adam(dyn)
+    assert opt.learning_rate == pytest.approx(1e-3)
+    opt.global_step = 2500
+    assert opt.learning_rate == pytest.approx(1e-3 * 0.96 ** 2)
+    opt.global_step = 0
+    rng = np.random.default_rng(0)
+    ref_p = {(i, k): torch.tensor(np.asarray(dyn._net_params[i][k], np.float32)).clone().requires_grad_(True)
+             for i in range(2) for k in training.NAMES}
+    ref_alpha = torch.tensor([float(dyn.alpha)], requires_grad=True)
+    topt = torch.optim.Adam(list(ref_p.values()) + [ref_alpha], lr=1e-3, eps=1e-8)
+    for step in range(3):
+        grads = {"loss": torch.zeros(1), "eps": torch.tensor([float(rng.standard_normal())], dtype=torch.float32)}
+        for i, key in enumerate(("XNet", "VNet")):
+            grads[key] = {k: torch.tensor(rng.standard_normal(np.shape(dyn._net_params[i][k])).astype(np.float32))
+                          for k in training.NAMES}
+        eps_now = dyn.eps
+        for (i, k), p in ref_p.items():
+            p.grad = grads[("XNet", "VNet")[i]][k].reshape(p.shape).clone()
+        ref_alpha.grad = grads["eps"] * eps_now
+        topt.step()
+        opt.apply(dyn, grads)
+    assert opt.global_step == 3
+    for (i, k), p in ref_p.items():
+        got = np.asarray(dyn._net_params[i][k], np.float32).reshape(p.shape)
+        assert np.allclose(got, p.detach().numpy(), rtol=0, atol=2e-6), (i, k)
+    assert np.log(dyn.eps) == pytest.approx(float(ref_alpha.detach()[0]), abs=2e-6)
+    # the layer objects hold the new weights (what a checkpoint of the nets would save)
+    assert np.allclose(np.asarray(dyn.XNet.layers[3].W), np.asarray(dyn._net_params[0]["W4"]))

@@ -1,0 +1,153 @@
+"""CPU check of the training-path kernels' SOURCE (l2hmc_b200/csrc/train.cuh + train_host.cuh).
+
+tests/emu/train_emu.cpp compiles those two files with g++ and runs every CUDA thread on a host thread, so index
+arithmetic, operand strides, the GEMM tiling, the order of the two sweeps and every vector-Jacobian product are checked
+here against oracle/l2hmc_reverse.py (which equals torch.autograd through the restated dynamics, see test_oracle.py)
+without a GPU.  The GPU run of the same source is tests/test_zz_gpu_training.py.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import util as U
+import l2hmc_reverse as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "emu", "train_emu.cpp")
+OUT = os.path.join(HERE, "emu", "_build", "libtrain_emu.so")
+F = C.POINTER(C.c_float)
+NAMES = ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "Ws", "bs", "Wt", "bt", "Wq", "bq", "scale_s", "scale_q")
+ORACLE_KEY = dict(zip(NAMES, ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "Ws", "bs", "Wt", "bt", "Wq", "bq", "ls", "lq")))
+
+
+class NetParams(C.Structure):   # l2hmc_net_params (include/l2hmc.h)
+    _fields_ = [(k, F) for k in NAMES]
+
+
+# l2hmc_net_grads / l2hmc_loss_grad_args: the product's own ctypes mirrors, so that their layout is checked against the
+# header as g++ compiles it
+from l2hmc_b200._lib import NetGrads, LossGradArgs  # noqa: E402
+
+
+def vptr(a):
+    return a.ctypes.data
+
+
+@pytest.fixture(scope="module")
+def emu():
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    deps = [SRC] + [os.path.join(HERE, "..", "l2hmc_b200", "csrc", f) for f in ("train.cuh", "train_host.cuh")] + \
+           [os.path.join(HERE, "..", "include", "l2hmc.h")]
+    if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-DL2HMC_TRAIN_EMU", "-x", "c++",
+                        "-Wno-unknown-pragmas", SRC, "-o", OUT], check=True)
+    lib = C.CDLL(OUT)
+    lib.emu_loss_grad.restype = C.c_int
+    return lib
+
+
+def fptr(a):
+    return a.ctypes.data_as(F)
+
+
+def pack(net, cls=NetParams):
+    keep = {k: np.ascontiguousarray(np.asarray(net[ORACLE_KEY[k]], dtype=np.float32)) for k in NAMES}
+    return cls(**{k: fptr(v) for k, v in keep.items()}), keep
+
+
+def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
+    n = x.shape[0]
+    xp, keep_x = pack(P.xnet)
+    vp, keep_v = pack(P.vnet)
+    gx = {k: np.zeros_like(a) for k, a in keep_x.items()}
+    gv = {k: np.zeros_like(a) for k, a in keep_v.items()}
+    loss = np.zeros(1, np.float32)
+    d_eps = np.zeros(1, np.float32)
+    Lx = np.zeros((n, P.D), np.float32)
+    px = np.zeros(n, np.float32)
+    x = np.ascontiguousarray(x, np.float32)
+    v = np.ascontiguousarray(v, np.float32)
+    d8 = np.ascontiguousarray(direction, np.uint8)
+    a = LossGradArgs(n=n, x=vptr(x), v=vptr(v), dir=vptr(d8), scale=scale, inv_count=inv_count,
+                     loss=vptr(loss), d_eps=vptr(d_eps), grad_xnet=NetGrads(**{k: vptr(g) for k, g in gx.items()}),
+                     grad_vnet=NetGrads(**{k: vptr(g) for k, g in gv.items()}), x_out=vptr(Lx), px_out=vptr(px), stream=None)
+    mask = np.ascontiguousarray(P.mask, np.float32)
+    if P.kind == "gaussian":
+        kind, mu = 0, np.ascontiguousarray(P.energy.mu.numpy(), np.float32)
+        S = np.ascontiguousarray(P.energy.S.numpy(), np.float32)
+        s0 = s1 = 0.0
+    else:
+        kind, mu, S = 2, np.zeros(P.D, np.float32), np.zeros((P.D, P.D), np.float32)
+        e, den = P.energy._scale(torch.zeros(1))
+        s0, s1 = float(e), float(den)
+    err = C.create_string_buffer(512)
+    rc = lib.emu_loss_grad(C.c_int(P.D), C.c_int(P.H), C.c_int(P.T), C.c_float(P.eps), C.c_float(temperature), C.c_int(kind),
+                           fptr(mu), fptr(S), C.c_float(s0), C.c_float(s1), fptr(mask), C.byref(xp), C.byref(vp), C.byref(a),
+                           err, C.c_int(512))
+    assert rc == 0, err.value
+    return float(loss[0]), float(d_eps[0]), gx, gv, Lx, px
+
+
+@pytest.mark.parametrize("kind,D,H,T,n,temperature", [
+    ("gaussian", 3, 5, 2, 9, 1.0),       # nothing a multiple of anything
+    ("gaussian", 2, 10, 3, 40, 1.7),     # the notebook's shape, T_emp != 1, more than one warp-block of chains
+    ("roughwell", 5, 7, 2, 12, 1.0),
+    ("gaussian", 9, 70, 1, 70, 1.0),     # width and chain count beyond one 64-wide GEMM tile
+])
+def test_training_kernels_under_emulation_match_the_hand_written_reverse_pass(emu, kind, D, H, T, n, temperature):
+    kw = dict(kind=kind, D=D, H=H, T=T, eps=0.1)
+    if kind == "roughwell":
+        kw["easy"] = True
+    P = U.Problem(regime="stress", **kw)
+    rng = np.random.default_rng(4)
+    x = P.x0(n, rng)
+    r = {"direction": torch.as_tensor(rng.integers(0, 2, n).astype(np.float64)),
+         "v_f": torch.as_tensor(rng.standard_normal((n, D)).astype(np.float32)).double(),
+         "v_b": torch.as_tensor(rng.standard_normal((n, D)).astype(np.float32)).double()}
+    d = r["direction"].numpy().astype(np.uint8)
+    v = np.where(d[:, None] == 1, r["v_f"].numpy(), r["v_b"].numpy()).astype(np.float32)
+    scale = 0.1
+
+    dyn = P.oracle(torch.float64, temperature=temperature)
+    with torch.no_grad():
+        acc = R._Acc(dyn)
+        loss_o = R.loss_and_grads(torch.as_tensor(x).double(), dyn, r, scale, acc)
+        Lx_o, _, px_o = U.O.propose_selected(torch.as_tensor(x).double(), dyn, direction=r["direction"],
+                                             v=torch.as_tensor(v).double())
+    loss, d_eps, gx, gv, Lx, px = run_emu(emu, P, x, v, d, scale, 1.0 / n, temperature)
+
+    assert np.abs(Lx - Lx_o.numpy()).max() <= 2e-5 * max(1.0, float(Lx_o.abs().max()))
+    assert np.abs(px - px_o.numpy()).max() <= 2e-5
+    assert loss == pytest.approx(float(loss_o), rel=2e-4)
+    assert d_eps == pytest.approx(float(acc.eps), rel=2e-3, abs=1e-3 * abs(float(loss_o)))
+    worst = 0.0
+    for got, ref in ((gx, acc.x), (gv, acc.v)):
+        for k in NAMES:
+            a, b = got[k].astype(np.float64), ref[ORACLE_KEY[k]].numpy().reshape(got[k].shape)
+            assert np.isfinite(a).all()
+            worst = max(worst, float(np.abs(a - b).max() / max(1e-12, np.abs(b).max())))
+    # fp32 sweep against the fp64 statement: the fp32 noise floor of this gradient is about 1e-5
+    assert worst < 2e-4, worst   # measured 1e-6 .. 1.3e-5
+
+
+def test_emulated_gradients_accumulate_over_two_batches(emu):
+    """Outputs are += : the x batch and the z batch of the notebook objective add up (SCGExperiment.ipynb:159-181)."""
+    P = U.Problem(regime="stress", kind="gaussian", D=2, H=6, T=2, eps=0.1)
+    rng = np.random.default_rng(9)
+    n = 8
+    x, z = P.x0(n, rng), rng.standard_normal((n, 2)).astype(np.float32)
+    d1, d2 = rng.integers(0, 2, n).astype(np.uint8), rng.integers(0, 2, n).astype(np.uint8)
+    v1, v2 = rng.standard_normal((n, 2)).astype(np.float32), rng.standard_normal((n, 2)).astype(np.float32)
+    la, ea, gxa, gva, _, _ = run_emu(emu, P, x, v1, d1, 0.1, 1.0 / n)
+    lb, eb, gxb, gvb, _, _ = run_emu(emu, P, z, v2, d2, 0.1, 1.0 / n)
+    lab, eab, gxab, gvab, _, _ = run_emu(emu, P, np.concatenate([x, z]), np.concatenate([v1, v2]), np.concatenate([d1, d2]),
+                                         0.1, 1.0 / n)
+    assert lab == pytest.approx(la + lb, rel=1e-5)
+    assert eab == pytest.approx(ea + eb, rel=1e-4, abs=1e-4)
+    for k in NAMES:
+        assert np.allclose(gxab[k], gxa[k] + gxb[k], rtol=1e-4, atol=1e-5 * max(1e-6, np.abs(gxab[k]).max()))
+        assert np.allclose(gvab[k], gva[k] + gvb[k], rtol=1e-4, atol=1e-5 * max(1e-6, np.abs(gvab[k]).max()))

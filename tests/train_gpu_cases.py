@@ -1,0 +1,130 @@
+"""GPU cases of the training path (l2hmc_loss_grad; l2hmc_b200/training.py).  Not collected by the main run: executed in a
+subprocess by tests/test_zz_gpu_training.py, so that a fault in this first-correct path cannot disturb the other GPU tests."""
+import numpy as np
+import pytest
+import torch
+
+import util as U
+import l2hmc_reverse as R
+from l2hmc_b200 import propose, training
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+ORACLE_NETS = (("XNet", "x"), ("VNet", "v"))
+
+
+def _setup(name, n, seed=4, **over):
+    kw = dict(U.CONFIGS[name])
+    kw.update(over)
+    P = U.Problem(regime="stress", **kw)
+    rng = np.random.default_rng(seed)
+    x = P.x0(n, rng)
+    d = rng.integers(0, 2, n).astype(np.uint8)
+    v = rng.standard_normal((n, P.D)).astype(np.float32)
+    return P, x, d, v
+
+
+def _oracle(P, x, d, v, scale, temperature=1.0):
+    dyn = P.oracle(torch.float64, temperature=temperature)
+    r = {"direction": torch.as_tensor(d.astype(np.float64)), "v_f": torch.as_tensor(v).double(), "v_b": torch.as_tensor(v).double()}
+    with torch.no_grad():
+        acc = R._Acc(dyn)
+        loss = R.loss_and_grads(torch.as_tensor(x).double(), dyn, r, scale, acc)
+    return float(loss), acc
+
+
+def _worst(grads, acc):
+    worst = 0.0
+    for key, attr in ORACLE_NETS:
+        ref = getattr(acc, attr)
+        for k in training.NAMES:
+            a = grads[key][k].double().cpu().numpy()
+            b = ref[k].numpy().reshape(a.shape)
+            assert np.isfinite(a).all(), (key, k)
+            worst = max(worst, float(np.abs(a - b).max() / max(1e-12, np.abs(b).max())))
+    return worst
+
+
+@pytest.mark.parametrize("name,n,tol", [("c1_scg2", 200, 5e-4), ("c2_scg50", 256, 1e-3), ("c4_rw32", 128, 1e-2)])
+def test_loss_grad_matches_the_hand_written_reverse_pass(name, n, tol):
+    P, x, d, v = _setup(name, n)
+    dyn = P.product()
+    rng = {"direction": torch.as_tensor(d, device=DEV), "v": torch.as_tensor(v, device=DEV)}
+    loss, grads, Lx, px = training.loss_and_grads(dyn, torch.as_tensor(x, device=DEV), rng=rng, scale=0.1)
+    loss_o, acc = _oracle(P, x, d, v, 0.1)
+    assert float(loss[0]) == pytest.approx(loss_o, rel=1e-3)
+    assert _worst(grads, acc) < tol
+    assert float(grads["eps"][0]) == pytest.approx(float(acc.eps), rel=5e-3, abs=1e-3 * abs(loss_o))
+    assert float(grads["alpha"][0]) == pytest.approx(float(acc.eps) * P.eps, rel=5e-3, abs=1e-4 * abs(loss_o))
+    # the forward sweep is the sampling transition: same Lx / px as propose with the same direction and momentum
+    Lx2, _, px2, _ = propose(torch.as_tensor(x, device=DEV), dyn, rng=rng)
+    assert U.max_rel(Lx.cpu().numpy(), Lx2.cpu().numpy()) < 2e-5
+    assert float((px - px2).abs().max()) < 5e-5
+
+
+def test_temperature_enters_the_gradient():
+    P, x, d, v = _setup("c1_scg2", 64)
+    dyn = P.product(use_temperature=True)
+    dyn.temperature = 1.7
+    rng = {"direction": torch.as_tensor(d, device=DEV), "v": torch.as_tensor(v, device=DEV)}
+    loss, grads, _, _ = training.loss_and_grads(dyn, torch.as_tensor(x, device=DEV), rng=rng)
+    loss_o, acc = _oracle(P, x, d, v, 0.1, temperature=1.7)
+    assert float(loss[0]) == pytest.approx(loss_o, rel=1e-3)
+    assert _worst(grads, acc) < 5e-4
+
+
+def test_the_two_batches_of_the_notebook_objective_add_up():
+    P, x, d, v = _setup("c1_scg2", 96)
+    rng2 = np.random.default_rng(8)
+    z = rng2.standard_normal((96, P.D)).astype(np.float32)
+    d2, v2 = rng2.integers(0, 2, 96).astype(np.uint8), rng2.standard_normal((96, P.D)).astype(np.float32)
+    dyn = P.product()
+    t = lambda a: torch.as_tensor(a, device=DEV)  # noqa: E731
+    loss, grads, _, _ = training.notebook_loss_and_grads(dyn, t(x), t(z), rng_x={"direction": t(d), "v": t(v)},
+                                                         rng_z={"direction": t(d2), "v": t(v2)})
+    odyn = P.oracle(torch.float64)
+    rx = {"direction": torch.as_tensor(d.astype(np.float64)), "v_f": torch.as_tensor(v).double(), "v_b": torch.as_tensor(v).double()}
+    rz = {"direction": torch.as_tensor(d2.astype(np.float64)), "v_f": torch.as_tensor(v2).double(), "v_b": torch.as_tensor(v2).double()}
+    loss_o, g = R.notebook_loss_and_grads(torch.as_tensor(x), torch.as_tensor(z), odyn, rx, rz)
+    assert float(loss[0]) == pytest.approx(float(loss_o), rel=1e-3)
+
+    class A:  # the oracle returns plain dicts
+        x, v, eps = g["xnet"], g["vnet"], g["eps"]
+    assert _worst(grads, A) < 5e-4
+
+
+def test_unsupported_targets_and_modes_raise():
+    from l2hmc_b200 import _lib
+    P = U.Problem(regime="stress", **U.CONFIGS["c3_mog2"])
+    dyn = P.product()
+    x = torch.as_tensor(P.x0(8, np.random.default_rng(0)), device=DEV)
+    with pytest.raises(_lib.L2HMCError):
+        training.loss_and_grads(dyn, x)
+    H = U.Problem(hmc=True, **U.CONFIGS["c1_scg2"]).product()
+    with pytest.raises(ValueError):
+        training.loss_and_grads(H, x)
+
+
+def test_training_loop_lowers_the_loss_and_moves_every_parameter():
+    """SCGExperiment.ipynb:254-270 in miniature: Adam with the notebook's schedule on both nets and alpha."""
+    P, x, d, v = _setup("c1_scg2", 200)
+    dyn = P.product()
+    before = [{k: np.array(p[k]) for k in training.NAMES} for p in dyn._net_params]
+    eps0 = dyn.eps
+    t = lambda a: torch.as_tensor(a, device=DEV)  # noqa: E731
+    fixed = dict(rng_x={"direction": t(d), "v": t(v)}, rng_z={"direction": t(d), "v": t(v)})
+    z = t(np.random.default_rng(3).standard_normal((200, P.D)).astype(np.float32))
+    first, _, _, _ = training.notebook_loss_and_grads(dyn, t(x), z, **fixed)
+    opt = training.Adam(dyn)
+    samples = t(x)
+    for it in range(15):
+        out = training.train_step(dyn, opt, samples)
+        samples = out["samples"]
+        assert np.isfinite(out["loss"]) and samples.shape == (200, P.D)
+    assert opt.global_step == 15 and out["learning_rate"] == pytest.approx(1e-3)
+    last, _, _, _ = training.notebook_loss_and_grads(dyn, t(x), z, **fixed)
+    assert float(last[0]) < float(first[0])
+    assert dyn.eps != eps0
+    for p0, p1 in zip(before, dyn._net_params):
+        for k in training.NAMES:
+            assert not np.array_equal(p0[k], np.asarray(p1[k])), k
