@@ -75,8 +75,8 @@ def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale
         g = getattr(a, field)
         for k in NAMES:
             t = acc[key][k]
-            if not (t.is_cuda and t.dtype == TORCH_FLOAT and t.is_contiguous()):
-                raise TypeError("gradient accumulators must be contiguous fp32 CUDA tensors")
+            if not (t.device == dev and t.dtype == TORCH_FLOAT and t.is_contiguous()):
+                raise TypeError("gradient accumulators must be contiguous fp32 tensors on the device of x")
             setattr(g, _ABI.get(k, k), t.data_ptr())
     a.x_out, a.px_out, a.stream = Lx.data_ptr(), px.data_ptr(), dynamics._stream()
     dynamics._chk(dynamics._lib.l2hmc_loss_grad(dynamics._ctx, C.byref(a)))

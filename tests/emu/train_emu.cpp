@@ -64,6 +64,34 @@ static std::unique_ptr<std::barrier<>> block_bar;
 static std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
 static float warp_buf[MAX_THREADS];
 
+struct Pool {
+  std::vector<std::thread> th;
+  std::barrier<> start{MAX_THREADS + 1}, done{MAX_THREADS + 1};
+  std::function<void()> job;
+  int nt = 0;
+  dim3 block, grid;
+  uint3_ bidx{0, 0, 0};
+  Pool() {
+    for (int w = 0; w < MAX_THREADS / 32; ++w) warp_bar.emplace_back(new std::barrier<>(32));
+    for (int t = 0; t < MAX_THREADS; ++t)
+      th.emplace_back([this, t] {
+        emu_in_worker = true;
+        for (;;) {
+          start.arrive_and_wait();
+          if (t < nt) {
+            threadIdx = {(unsigned)t, 0, 0};
+            blockIdx = bidx;
+            blockDim = block;
+            gridDim = grid;
+            job();
+          }
+          done.arrive_and_wait();
+        }
+      });
+    for (auto &x : th) x.detach();
+  }
+};
+
 // kernels that synchronise (block barrier or warp shuffles) need their threads alive together; the others run their
 // threads one after another on the calling thread
 static bool cooperative(const char *name) {
@@ -89,31 +117,22 @@ void launch(const char *name, dim3 grid, dim3 block, F &&body) {
           }
     return;
   }
+  // cooperative kernels: a pool of MAX_THREADS workers, created once (and left to the process exit), runs one block at a
+  // time; every thread of these kernels either reaches each barrier or leaves with its whole warp before any
+  static Pool *pool = new Pool();
   block_bar.reset(new std::barrier<>(nt));
-  warp_bar.clear();
-  for (int w = 0; w < nt / 32; ++w) warp_bar.emplace_back(new std::barrier<>(32));
+  pool->nt = nt;
+  pool->block = block;
+  pool->grid = grid;
+  pool->job = body;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        std::vector<std::thread> th;
-        th.reserve(nt);
-        for (int t = 0; t < nt; ++t)
-          th.emplace_back([&, t] {
-            emu_in_worker = true;
-            threadIdx = {(unsigned)t, 0, 0};
-            blockIdx = {bx, by, bz};
-            blockDim = block;
-            gridDim = grid;
-            body();
-            // a thread that left early must not leave the others waiting: drop out of both barriers
-            block_bar->arrive_and_drop();
-            warp_bar[t / 32]->arrive_and_drop();
-          });
-        for (auto &x : th) x.join();
-        // barriers lost their participants: rebuild for the next block
-        block_bar.reset(new std::barrier<>(nt));
-        for (int w = 0; w < nt / 32; ++w) warp_bar[w].reset(new std::barrier<>(32));
+        pool->bidx = {bx, by, bz};
+        pool->start.arrive_and_wait();
+        pool->done.arrive_and_wait();
       }
+  pool->job = nullptr;
 }
 }  // namespace emu
 

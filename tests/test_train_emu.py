@@ -151,3 +151,89 @@ def test_emulated_gradients_accumulate_over_two_batches(emu):
     for k in NAMES:
         assert np.allclose(gxab[k], gxa[k] + gxb[k], rtol=1e-4, atol=1e-5 * max(1e-6, np.abs(gxab[k]).max()))
         assert np.allclose(gvab[k], gva[k] + gvb[k], rtol=1e-4, atol=1e-5 * max(1e-6, np.abs(gvab[k]).max()))
+
+
+class _EmuLib:
+    """Stands in for libl2hmc.so under a Dynamics whose tensors live on the CPU: l2hmc_loss_grad goes to the emulated
+    kernels, so the marshalling in l2hmc_b200/training.py (struct filling, accumulation, alpha, Adam write-back) runs here."""
+
+    def __init__(self, lib, P):
+        self.lib, self.P = lib, P
+        self.calls = 0
+
+    def l2hmc_loss_grad(self, ctx, a_ref):
+        P = self.P
+        a = a_ref._obj
+        xp, self._kx = pack(self.dyn._net_params[0])
+        vp, self._kv = pack(self.dyn._net_params[1])
+        mask = np.ascontiguousarray(self.dyn.mask, np.float32)
+        mu = np.ascontiguousarray(P.energy.mu.numpy(), np.float32)
+        S = np.ascontiguousarray(P.energy.S.numpy(), np.float32)
+        err = C.create_string_buffer(512)
+        self.calls += 1
+        return self.lib.emu_loss_grad(C.c_int(P.D), C.c_int(P.H), C.c_int(P.T), C.c_float(self.dyn.eps), C.c_float(1.0), C.c_int(0),
+                                      fptr(mu), fptr(S), C.c_float(0), C.c_float(0), fptr(mask), C.byref(xp), C.byref(vp),
+                                      C.byref(a), err, C.c_int(512))
+
+    def l2hmc_last_error(self, ctx):
+        return b"emulated"
+
+    def l2hmc_set_eps(self, ctx, eps):   # the emulated call reads dyn.eps directly
+        return 0
+
+
+def test_training_module_marshalling_and_loop_over_the_emulated_kernels(emu, monkeypatch):
+    from l2hmc_b200 import training
+    P = U.Problem(regime="stress", kind="gaussian", D=2, H=6, T=2, eps=0.1)
+    dyn = P.product()                      # no GPU here: the object has no library context
+    shim = _EmuLib(emu, P)
+    shim.dyn = dyn
+    dyn._lib, dyn._ctx = shim, C.c_void_p(1)
+    monkeypatch.setattr(type(dyn), "_prep", lambda self, t, name, cols=None: t.detach().to(torch.float32).contiguous())
+    monkeypatch.setattr(type(dyn), "_stream", lambda self: None)
+    monkeypatch.setattr(type(dyn), "_sync_temperature", lambda self: None)
+    monkeypatch.setattr(type(dyn), "_ensure_ctx", lambda self: None)
+    monkeypatch.setattr(type(dyn), "_push_nets", lambda self: None)
+    monkeypatch.setattr(type(dyn), "_chk", lambda self, rc: (_ for _ in ()).throw(RuntimeError(rc)) if rc else None)
+    rng = np.random.default_rng(2)
+    n = 16
+
+    def draw(dynamics, n_, device, want_u=False):
+        return (torch.as_tensor(rng.integers(0, 2, n_).astype(np.uint8)), torch.as_tensor(rng.standard_normal((n_, P.D)).astype(np.float32)),
+                None)
+    monkeypatch.setattr(training, "_draw", draw)
+    monkeypatch.setattr(training, "tf_accept", lambda x, Lx, px, u=None, seed=0, counter=0: torch.where((px >= 0.5)[:, None], Lx, x))
+
+    x = torch.as_tensor(P.x0(n, rng))
+    d = torch.as_tensor(rng.integers(0, 2, n).astype(np.uint8))
+    v = torch.as_tensor(rng.standard_normal((n, P.D)).astype(np.float32))
+    loss, grads, Lx, px = training.loss_and_grads(dyn, x, rng={"direction": d, "v": v})
+    odyn = P.oracle(torch.float64)
+    r = {"direction": d.double(), "v_f": v.double(), "v_b": v.double()}
+    with torch.no_grad():
+        acc = R._Acc(odyn)
+        loss_o = R.loss_and_grads(x.double(), odyn, r, 0.1, acc)
+    assert float(loss[0]) == pytest.approx(float(loss_o), rel=2e-4)
+    for key, ref in (("XNet", acc.x), ("VNet", acc.v)):
+        for k in training.NAMES:
+            a, b = grads[key][k].double().numpy(), ref[k].numpy().reshape(grads[key][k].shape)
+            assert np.abs(a - b).max() <= 2e-4 * max(1e-12, np.abs(b).max()), (key, k)
+    assert float(grads["alpha"][0]) == pytest.approx(float(acc.eps) * 0.1, rel=2e-3)
+    assert px.shape == (n,) and Lx.shape == (n, P.D) and float(px.min()) >= 0.0 and float(px.max()) <= 1.0
+
+    # the loop: fixed-randomness loss before / after a few Adam steps, parameters and eps move, weights reach the layers
+    z = torch.as_tensor(rng.standard_normal((n, P.D)).astype(np.float32))
+    fixed = dict(rng_x={"direction": d, "v": v}, rng_z={"direction": d, "v": v})
+    first, _, _, _ = training.notebook_loss_and_grads(dyn, x, z, **fixed)
+    opt = training.Adam(dyn)
+    W4_before, eps_before = np.array(dyn._net_params[0]["W4"]), dyn.eps
+    samples = x
+    for _ in range(6):
+        out = training.train_step(dyn, opt, samples)
+        samples = out["samples"]
+        assert np.isfinite(out["loss"])
+    last, _, _, _ = training.notebook_loss_and_grads(dyn, x, z, **fixed)
+    assert float(last[0]) < float(first[0])
+    assert opt.global_step == 6 and dyn.eps != eps_before
+    assert not np.array_equal(W4_before, np.asarray(dyn._net_params[0]["W4"]))
+    assert shim.calls == 1 + 2 + 6 * 2 + 2
