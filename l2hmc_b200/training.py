@@ -38,6 +38,9 @@ def _draw(dynamics, n, device, want_u=False):
 
 def zero_grads(dynamics, device) -> Dict[str, object]:
     """Gradient accumulators shaped like the parameters: {'XNet': {...}, 'VNet': {...}, 'eps': [1], 'loss': [1]}."""
+    if dynamics.hmc:
+        raise ValueError("an HMC-mode Dynamics has no parameters to train")
+
     def like(p):
         return {k: torch.zeros(tuple(np.shape(p[k])), dtype=TORCH_FLOAT, device=device) for k in NAMES}
     return {"XNet": like(dynamics._net_params[0]), "VNet": like(dynamics._net_params[1]),
