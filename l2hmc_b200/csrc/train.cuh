@@ -12,10 +12,17 @@
 // Layout: chain-major unpadded fp32 rows ([n, D] states, [n, 2D] net input, [n, H] activations, [n, 3D] heads) against
 // the reference-layout weights the context already holds (NetRaw).  GEMMs are a plain shared-memory fp32 FMA kernel with
 // strided operands: this version is about the gradient being right, not about speed (DESIGN.md section 7.1 has the plan
-// for the fused one).  Gaussian and RoughWell targets (closed-form Hessians), no aux.
+// for the fused one).  Gaussian, mixture-of-Gaussians and RoughWell targets (closed-form Hessians), no aux.
 #pragma once
 #ifndef L2HMC_TRAIN_EMU  // tests/emu/train_emu.cpp supplies the few types it needs and runs these kernels on host threads
 #include "common.cuh"
+#endif
+
+#ifndef L2HMC_TR_KCHUNK
+#define L2HMC_TR_KCHUNK 4096  // chains per CTA of a weight-gradient product (split K); the CPU emulation shrinks both
+#endif
+#ifndef L2HMC_TR_SLAB
+#define L2HMC_TR_SLAB 1024    // rows per CTA of a column sum
 #endif
 
 namespace l2hmc {
@@ -95,8 +102,8 @@ __global__ void __launch_bounds__(256) k_gemm(const Gemm g) {
 __global__ void k_colsum(const float *A, long long lda, long long n_rows, int n_cols, const float *w, float *out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cols) return;
-  const long long r0 = (long long)blockIdx.y * 1024;
-  const long long r1 = (r0 + 1024 < n_rows) ? r0 + 1024 : n_rows;
+  const long long r0 = (long long)blockIdx.y * L2HMC_TR_SLAB;
+  const long long r1 = (r0 + L2HMC_TR_SLAB < n_rows) ? r0 + L2HMC_TR_SLAB : n_rows;
   float s = 0.f;
   for (long long r = r0; r < r1; ++r) s = fmaf(w ? w[r] : 1.f, A[r * lda + c], s);
   atomicAdd(out + c, s);
@@ -316,6 +323,50 @@ __global__ void k_hvp(EnergyDev en, Shape sh, long long n, const float *x, const
       float r = 0.f;
       for (int i = 0; i < D; ++i) r = fmaf(wr[i], en.Ssym[i * sh.LDS + j], r);
       o[j] += r / en.temperature;
+    }
+  } else if (en.kind == 1) {
+    // Mixture (utils/distributions.py:125-134): U = -logsumexp_c a_c, a_c = -q_c + log c_c, grad U = sum_c r_c g_c with
+    // r = softmax(a), g_c = A_c (x - mu_c), A_c = (S_c + S_c^T) / 2.  Hessian = sum_c r_c A_c - sum_c r_c g_c g_c^T + gb gb^T,
+    // gb = grad U.  Two passes so that no [components, D] array is held: (1) a_c and s_c = g_c . w, (2) the rows.
+    float r[MAX_COMP], sc[MAX_COMP];
+    float mx = -INFINITY;
+    for (int c = 0; c < en.ncomp; ++c) {
+      const float *mu = en.mu + c * sh.DP;
+      const float *S = en.Ssym + (size_t)c * sh.DP * sh.LDS;
+      float q = 0.f, s = 0.f;
+      for (int j = 0; j < D; ++j) {
+        float g = 0.f;
+        for (int i = 0; i < D; ++i) g = fmaf(xr[i] - mu[i], S[i * sh.LDS + j], g);
+        q = fmaf(g, xr[j] - mu[j], q);
+        s = fmaf(g, wr[j], s);
+      }
+      r[c] = -0.5f * q + en.logc[c];
+      sc[c] = s;
+      mx = fmaxf(mx, r[c]);
+    }
+    float z = 0.f, gbw = 0.f;
+    for (int c = 0; c < en.ncomp; ++c) {
+      r[c] = expf(r[c] - mx);
+      z += r[c];
+    }
+    for (int c = 0; c < en.ncomp; ++c) {
+      r[c] /= z;
+      gbw = fmaf(r[c], sc[c], gbw);  // grad U . w
+    }
+    for (int j = 0; j < D; ++j) {
+      float acc = 0.f, gb = 0.f;
+      for (int c = 0; c < en.ncomp; ++c) {
+        const float *mu = en.mu + c * sh.DP;
+        const float *S = en.Ssym + (size_t)c * sh.DP * sh.LDS;
+        float g = 0.f, wa = 0.f;
+        for (int i = 0; i < D; ++i) {
+          g = fmaf(xr[i] - mu[i], S[i * sh.LDS + j], g);
+          wa = fmaf(wr[i], S[i * sh.LDS + j], wa);
+        }
+        acc = fmaf(r[c], wa - g * sc[c], acc);
+        gb = fmaf(r[c], g, gb);
+      }
+      o[j] += (acc + gb * gbw) / en.temperature;
     }
   } else {  // RoughWell: grad = x - e sin(x / den) / den, diagonal Hessian 1 - e cos(x / den) / den^2   :90-97
     const float e = en.s0, den = en.s1;

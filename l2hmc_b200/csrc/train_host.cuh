@@ -52,7 +52,7 @@ int tr_gemm(l2hmc_ctx *ctx, cudaStream_t s, tr::Gemm g) {
   const long long gy = (g.M + 63) / 64;
   long long gz = 1;
   if (g.mode == 2) {
-    g.kchunk = 4096;
+    g.kchunk = L2HMC_TR_KCHUNK;
     gz = (g.K + g.kchunk - 1) / g.kchunk;
   } else {
     g.kchunk = g.K;
@@ -72,7 +72,7 @@ tr::Gemm tr_g(const float *A, long long sam, long long sak, const float *B, long
 }
 
 int tr_colsum(l2hmc_ctx *ctx, cudaStream_t s, const float *A, long long lda, long long n, int cols, const float *w, float *out) {
-#define TR_COLSUM_GRID tr_gb(dim3((unsigned)((cols + 127) / 128), (unsigned)((n + 1023) / 1024)), 128)
+#define TR_COLSUM_GRID tr_gb(dim3((unsigned)((cols + 127) / 128), (unsigned)((n + L2HMC_TR_SLAB - 1) / L2HMC_TR_SLAB)), 128)
   TR_LAUNCH(ctx, tr::k_colsum, TR_COLSUM_GRID, s, A, lda, n, cols, w, out);
   return L2HMC_OK;
 }

@@ -4,7 +4,7 @@ FIRST-CORRECT version: the gradien
 ``optimizer.minimize(loss)`` (SCGExperiment.ipynb:183-188) through ``propose`` (utils/sampler.py:28-51), ``p_accept``
 (utils/dynamics.py:302-309), the unrolled leapfrog (:246-300) and ``tf.gradients(energy, x)`` inside it (:217-218) -- is
 computed by ``l2hmc_loss_grad`` (csrc/train.cuh: a recorded forward sweep and a hand-written reverse sweep, plain fp32
-FMA GEMMs).  Gaussian (one component) and RoughWell targets, no aux.  No CPU fallback.
+FMA GEMMs).  Gaussian, GMM and RoughWell targets, no aux.  No CPU fallback.
 
     loss, grads, Lx, px = loss_and_grads(dynamics, x)                  # one propose batch
     state = train_step(dynamics, opt, samples)                         # one iteration of SCGExperiment.ipynb:254-270

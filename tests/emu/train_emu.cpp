@@ -158,6 +158,7 @@ static inline float atomicAdd(float *p, float v) {
 
 // ---- the few types of common.cuh / l2hmc_api.cu the training path touches -------------------------------------------
 namespace l2hmc {
+constexpr int MAX_COMP = 8;
 struct NetRaw {
   const float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4, *Ws, *bs, *Wt, *bt, *Wq, *bq, *ls, *lq;
 };
@@ -202,16 +203,29 @@ static int fail(l2hmc_ctx *ctx, int code, const char *fmt, ...) {
   } while (0)
 #define GRID(n) (unsigned)(((n) + 127) / 128), 128
 
-// grad U / T_emp and U / T_emp for the Gaussian and RoughWell energies (restated; the real kernels live in l2hmc_api.cu)
+// grad U / T_emp and U / T_emp for the energies the training path covers (restated; the real kernels live in l2hmc_api.cu)
+static float emu_quad(const float *mu, const float *S, const Shape &sh, const float *x, float *g) {
+  float q = 0.f;
+  for (int j = 0; j < sh.D; ++j) {
+    float r = 0.f;
+    for (int i = 0; i < sh.D; ++i) r = fmaf(x[i] - mu[i], S[i * sh.LDS + j], r);
+    if (g) g[j] = r;
+    q = fmaf(r, x[j] - mu[j], q);
+  }
+  return q;
+}
 static float emu_energy(const EnergyDev &en, const Shape &sh, const float *x) {
   float U = 0.f;
   if (en.kind == 0) {
-    for (int j = 0; j < sh.D; ++j) {
-      float r = 0.f;
-      for (int i = 0; i < sh.D; ++i) r = fmaf(x[i] - en.mu[i], en.Ssym[i * sh.LDS + j], r);
-      U = fmaf(r, x[j] - en.mu[j], U);
+    U = 0.5f * emu_quad(en.mu, en.Ssym, sh, x, nullptr);
+  } else if (en.kind == 1) {
+    float V[l2hmc::MAX_COMP], mx = -INFINITY, s = 0.f;
+    for (int c = 0; c < en.ncomp; ++c) {
+      V[c] = -0.5f * emu_quad(en.mu + c * sh.DP, en.Ssym + (size_t)c * sh.DP * sh.LDS, sh, x, nullptr) + en.logc[c];
+      mx = fmaxf(mx, V[c]);
     }
-    U *= 0.5f;
+    for (int c = 0; c < en.ncomp; ++c) s += expf(V[c] - mx);
+    U = -(logf(s) + mx);
   } else {
     float n = 0.f, cs = 0.f;
     for (int i = 0; i < sh.D; ++i) {
@@ -226,16 +240,25 @@ static void k_grad(EnergyDev en, Shape sh, long long n, const float *x, float *o
   const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (g >= n) return;
   const float *xr = x + g * sh.D;
-  for (int j = 0; j < sh.D; ++j) {
-    float r;
-    if (en.kind == 0) {
-      r = 0.f;
-      for (int i = 0; i < sh.D; ++i) r = fmaf(xr[i] - en.mu[i], en.Ssym[i * sh.LDS + j], r);
-    } else {
-      r = xr[j] - en.s0 * sinf(xr[j] / en.s1) / en.s1;
+  float *o = out + g * sh.D;
+  if (en.kind == 0) {
+    emu_quad(en.mu, en.Ssym, sh, xr, o);
+  } else if (en.kind == 1) {
+    float V[l2hmc::MAX_COMP], gc[l2hmc::MAX_COMP][64], mx = -INFINITY, s = 0.f;
+    for (int c = 0; c < en.ncomp; ++c) {
+      V[c] = -0.5f * emu_quad(en.mu + c * sh.DP, en.Ssym + (size_t)c * sh.DP * sh.LDS, sh, xr, gc[c]) + en.logc[c];
+      mx = fmaxf(mx, V[c]);
     }
-    out[g * sh.D + j] = r / en.temperature;
+    for (int c = 0; c < en.ncomp; ++c) s += (V[c] = expf(V[c] - mx));
+    for (int j = 0; j < sh.D; ++j) {
+      float a = 0.f;
+      for (int c = 0; c < en.ncomp; ++c) a = fmaf(V[c] / s, gc[c][j], a);
+      o[j] = a;
+    }
+  } else {
+    for (int j = 0; j < sh.D; ++j) o[j] = xr[j] - en.s0 * sinf(xr[j] / en.s1) / en.s1;
   }
+  for (int j = 0; j < sh.D; ++j) o[j] /= en.temperature;
 }
 static void k_hamiltonian(EnergyDev en, Shape sh, long long n, const float *x, const float *v, float *out) {
   const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -248,24 +271,27 @@ static void k_hamiltonian(EnergyDev en, Shape sh, long long n, const float *x, c
 #include "../../l2hmc_b200/csrc/train_host.cuh"
 
 // ---- entry point for tests/test_train_emu.py -----------------------------------------------------------------------
-// Parameters in the reference layout (l2hmc_net_params order, host pointers); energy: kind 0 (mu [D], S [D, D]) or 2
-// (scalars eps, denominator).  Gradients are written to gx / gv (16 tensors each, caller-zeroed).
-extern "C" int emu_loss_grad(int D, int H, int T, float eps, float temperature, int kind, const float *mu, const float *S,
-                             float s0, float s1, const float *mask, const l2hmc_net_params *xnet, const l2hmc_net_params *vnet,
+// Parameters in the reference layout (l2hmc_net_params order, host pointers); energy: kind 0 / 1 (mu [ncomp, D],
+// S [ncomp, D, D], logc [ncomp]) or 2 (scalars eps, denominator).  Gradients are written to gx / gv (16 tensors each, caller-zeroed).
+extern "C" int emu_loss_grad(int D, int H, int T, float eps, float temperature, int kind, int ncomp, const float *mu,
+                             const float *S, const float *logc, float s0, float s1, const float *mask, const l2hmc_net_params *xnet, const l2hmc_net_params *vnet,
                              const l2hmc_loss_grad_args *a, char *err, int err_len) {
   l2hmc_ctx ctx;
   Shape &sh = ctx.sh;
   sh.D = D; sh.DP = (D + 3) / 4 * 4; sh.H = H; sh.HP = (H + 3) / 4 * 4; sh.T = T; sh.LDE = 128; sh.LDH = 192;
   sh.LDS = (sh.DP + 127) / 128 * 128; sh.hmc = 0; sh.eps = eps;
-  std::vector<float> mu_p(sh.DP, 0.f), S_p((size_t)sh.DP * sh.LDS, 0.f), mask_p((size_t)T * sh.DP, 0.f);
-  if (kind == 0)
-    for (int i = 0; i < D; ++i) {
-      mu_p[i] = mu[i];
-      for (int j = 0; j < D; ++j) S_p[(size_t)i * sh.LDS + j] = 0.5f * (S[i * D + j] + S[j * D + i]);
-    }
+  if (D > 64 || ncomp > l2hmc::MAX_COMP) return L2HMC_EUNSUPPORTED;
+  std::vector<float> mu_p((size_t)ncomp * sh.DP, 0.f), S_p((size_t)ncomp * sh.DP * sh.LDS, 0.f), mask_p((size_t)T * sh.DP, 0.f);
+  if (kind == 0 || kind == 1)
+    for (int c = 0; c < ncomp; ++c)
+      for (int i = 0; i < D; ++i) {
+        mu_p[(size_t)c * sh.DP + i] = mu[c * D + i];
+        for (int j = 0; j < D; ++j)
+          S_p[((size_t)c * sh.DP + i) * sh.LDS + j] = 0.5f * (S[(c * D + i) * D + j] + S[(c * D + j) * D + i]);
+      }
   for (int t = 0; t < T; ++t)
     for (int d = 0; d < D; ++d) mask_p[(size_t)t * sh.DP + d] = mask[t * D + d];
-  ctx.en = EnergyDev{kind, 1, mu_p.data(), S_p.data(), nullptr, s0, s1, temperature};
+  ctx.en = EnergyDev{kind, ncomp, mu_p.data(), S_p.data(), logc, s0, s1, temperature};
   ctx.mask.p = mask_p.data();
   const l2hmc_net_params *ps[2] = {xnet, vnet};
   for (int i = 0; i < 2; ++i) {

@@ -43,7 +43,7 @@ def emu():
     deps = [SRC] + [os.path.join(HERE, "..", "l2hmc_b200", "csrc", f) for f in ("train.cuh", "train_host.cuh")] + \
            [os.path.join(HERE, "..", "include", "l2hmc.h")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
-        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-DL2HMC_TRAIN_EMU", "-x", "c++",
+        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-DL2HMC_TRAIN_EMU", "-DL2HMC_TR_KCHUNK=16", "-DL2HMC_TR_SLAB=16", "-x", "c++",
                         "-Wno-unknown-pragmas", SRC, "-o", OUT], check=True)
     lib = C.CDLL(OUT)
     lib.emu_loss_grad.restype = C.c_int
@@ -76,18 +76,23 @@ def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
                      loss=vptr(loss), d_eps=vptr(d_eps), grad_xnet=NetGrads(**{k: vptr(g) for k, g in gx.items()}),
                      grad_vnet=NetGrads(**{k: vptr(g) for k, g in gv.items()}), x_out=vptr(Lx), px_out=vptr(px), stream=None)
     mask = np.ascontiguousarray(P.mask, np.float32)
+    ncomp, logc, s0, s1 = 1, np.zeros(1, np.float32), 0.0, 0.0
     if P.kind == "gaussian":
         kind, mu = 0, np.ascontiguousarray(P.energy.mu.numpy(), np.float32)
         S = np.ascontiguousarray(P.energy.S.numpy(), np.float32)
-        s0 = s1 = 0.0
+    elif P.kind == "gmm":
+        kind, ncomp = 1, len(P.energy.mus)
+        mu = np.ascontiguousarray(np.stack([m.numpy() for m in P.energy.mus]), np.float32)
+        S = np.ascontiguousarray(np.stack([m.numpy() for m in P.energy.Ss]), np.float32)
+        logc = np.log(np.array([float(c) for c in P.energy.cs], np.float64)).astype(np.float32)
     else:
         kind, mu, S = 2, np.zeros(P.D, np.float32), np.zeros((P.D, P.D), np.float32)
         e, den = P.energy._scale(torch.zeros(1))
         s0, s1 = float(e), float(den)
     err = C.create_string_buffer(512)
     rc = lib.emu_loss_grad(C.c_int(P.D), C.c_int(P.H), C.c_int(P.T), C.c_float(P.eps), C.c_float(temperature), C.c_int(kind),
-                           fptr(mu), fptr(S), C.c_float(s0), C.c_float(s1), fptr(mask), C.byref(xp), C.byref(vp), C.byref(a),
-                           err, C.c_int(512))
+                           C.c_int(ncomp), fptr(mu), fptr(S), fptr(logc), C.c_float(s0), C.c_float(s1), fptr(mask), C.byref(xp),
+                           C.byref(vp), C.byref(a), err, C.c_int(512))
     assert rc == 0, err.value
     return float(loss[0]), float(d_eps[0]), gx, gv, Lx, px
 
@@ -96,6 +101,8 @@ def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
     ("gaussian", 3, 5, 2, 9, 1.0),       # nothing a multiple of anything
     ("gaussian", 2, 10, 3, 40, 1.7),     # the notebook's shape, T_emp != 1, more than one warp-block of chains
     ("roughwell", 5, 7, 2, 12, 1.0),
+    ("gmm", 2, 10, 3, 24, 1.0),          # config 3's target: the mixture's Hessian-vector product
+    ("gmm", 3, 6, 2, 10, 1.3),
     ("gaussian", 9, 70, 1, 70, 1.0),     # width and chain count beyond one 64-wide GEMM tile
 ])
 def test_training_kernels_under_emulation_match_the_hand_written_reverse_pass(emu, kind, D, H, T, n, temperature):
@@ -172,8 +179,8 @@ class _EmuLib:
         err = C.create_string_buffer(512)
         self.calls += 1
         return self.lib.emu_loss_grad(C.c_int(P.D), C.c_int(P.H), C.c_int(P.T), C.c_float(self.dyn.eps), C.c_float(1.0), C.c_int(0),
-                                      fptr(mu), fptr(S), C.c_float(0), C.c_float(0), fptr(mask), C.byref(xp), C.byref(vp),
-                                      C.byref(a), err, C.c_int(512))
+                                      C.c_int(1), fptr(mu), fptr(S), fptr(np.zeros(1, np.float32)), C.c_float(0), C.c_float(0),
+                                      fptr(mask), C.byref(xp), C.byref(vp), C.byref(a), err, C.c_int(512))
 
     def l2hmc_last_error(self, ctx):
         return b"emulated"

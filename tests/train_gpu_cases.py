@@ -45,7 +45,10 @@ def _worst(grads, acc):
     return worst
 
 
-@pytest.mark.parametrize("name,n,tol", [("c1_scg2", 200, 5e-4), ("c2_scg50", 256, 1e-3), ("c4_rw32", 128, 1e-2)])
+# tolerances: the fp32 noise floor of this gradient at exactly these settings is 0.4 .. 2.1e-5 (fp32 vs fp64 run of the
+# oracle sweep)
+@pytest.mark.parametrize("name,n,tol", [("c1_scg2", 200, 5e-4), ("c2_scg50", 256, 1e-3), ("c3_mog2", 200, 1e-3),
+                                        ("c4_rw32", 128, 1e-3)])
 def test_loss_grad_matches_the_hand_written_reverse_pass(name, n, tol):
     P, x, d, v = _setup(name, n)
     dyn = P.product()
@@ -95,14 +98,14 @@ def test_the_two_batches_of_the_notebook_objective_add_up():
 
 def test_unsupported_targets_and_modes_raise():
     from l2hmc_b200 import _lib
-    P = U.Problem(regime="stress", **U.CONFIGS["c3_mog2"])
+    P = U.Problem(regime="stress", **U.CONFIGS["funnel3"])   # the funnel's Hessian is not restated yet
     dyn = P.product()
     x = torch.as_tensor(P.x0(8, np.random.default_rng(0)), device=DEV)
     with pytest.raises(_lib.L2HMCError):
         training.loss_and_grads(dyn, x)
     H = U.Problem(hmc=True, **U.CONFIGS["c1_scg2"]).product()
     with pytest.raises(ValueError):
-        training.loss_and_grads(H, x)
+        training.loss_and_grads(H, x[:, :2].contiguous())
 
 
 def test_training_loop_lowers_the_loss_and_moves_every_parameter():
