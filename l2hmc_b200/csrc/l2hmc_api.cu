@@ -1606,9 +1606,10 @@ extern "C" int l2hmc_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   if (ctx->sh.hmc) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: an HMC-mode context has no parameters to train");
   if (!ctx->mask_set) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: masks not set (l2hmc_set_masks)");
   if (!(ctx->net_set[0] && ctx->net_set[1])) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: XNet/VNet not set (l2hmc_set_net)");
-  const bool covered = ctx->en.kind == L2HMC_ENERGY_GAUSSIAN || ctx->en.kind == L2HMC_ENERGY_GMM || ctx->en.kind == L2HMC_ENERGY_ROUGHWELL;
+  const bool covered = ctx->en.kind == L2HMC_ENERGY_GAUSSIAN || ctx->en.kind == L2HMC_ENERGY_GMM ||
+                       ctx->en.kind == L2HMC_ENERGY_ROUGHWELL || ctx->en.kind == L2HMC_ENERGY_FUNNEL;
   if (!covered || ctx->lay.enc.n_layers > 0)
-    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_loss_grad: covers the Gaussian, GMM and RoughWell energies without aux (kind %d given)",
+    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_loss_grad: covers the closed-form energies without aux (kind %d given)",
                 ctx->en.kind);
   if (a->n < 0) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: n < 0");
   if (a->n == 0) return L2HMC_OK;

@@ -12,7 +12,7 @@
 // Layout: chain-major unpadded fp32 rows ([n, D] states, [n, 2D] net input, [n, H] activations, [n, 3D] heads) against
 // the reference-layout weights the context already holds (NetRaw).  GEMMs are a plain shared-memory fp32 FMA kernel with
 // strided operands: this version is about the gradient being right, not about speed (DESIGN.md section 7.1 has the plan
-// for the fused one).  Gaussian, mixture-of-Gaussians and RoughWell targets (closed-form Hessians), no aux.
+// for the fused one).  Gaussian, mixture-of-Gaussians, RoughWell and funnel targets (closed-form Hessians), no aux.
 #pragma once
 #ifndef L2HMC_TRAIN_EMU  // tests/emu/train_emu.cpp supplies the few types it needs and runs these kernels on host threads
 #include "common.cuh"
@@ -368,9 +368,24 @@ __global__ void k_hvp(EnergyDev en, Shape sh, long long n, const float *x, const
       }
       o[j] += (acc + gb * gbw) / en.temperature;
     }
-  } else {  // RoughWell: grad = x - e sin(x / den) / den, diagonal Hessian 1 - e cos(x / den) / den^2   :90-97
+  } else if (en.kind == 2) {  // RoughWell: grad = x - e sin(x / den) / den, diagonal Hessian 1 - e cos(x / den) / den^2   :90-97
     const float e = en.s0, den = en.s1;
     for (int j = 0; j < D; ++j) o[j] += wr[j] * (1.f - e * cosf(xr[j] / den) / (den * den)) / en.temperature;
+  } else {
+    // GaussianFunnel (utils/distributions.py:161-180), v = x_0, s = e^v: grad = (v / sigma^2 + (n - |x_1:|^2 / s) / 2, x_1: / s)
+    // inside the clip; outside it s is a constant and the v-coupling drops out (the tf.where branches)
+    const float sigma = en.s0, clip = en.s1;
+    const float v = xr[0];
+    const bool out = (v > clip) || (-clip > v);
+    const float s = out ? expf(v > clip ? clip : -clip) : expf(v);
+    float ss = 0.f, wx = 0.f;
+    for (int i = 1; i < D; ++i) {
+      ss = fmaf(xr[i], xr[i], ss);
+      wx = fmaf(wr[i], xr[i], wx);
+    }
+    const float h00 = 1.f / (sigma * sigma) + (out ? 0.f : 0.5f * ss / s);
+    o[0] += (wr[0] * h00 - (out ? 0.f : wx / s)) / en.temperature;
+    for (int j = 1; j < D; ++j) o[j] += ((wr[j] - (out ? 0.f : wr[0] * xr[j])) / s) / en.temperature;
   }
 }
 

@@ -4,7 +4,7 @@ FIRST-CORRECT version: the gradien
 ``optimizer.minimize(loss)`` (SCGExperiment.ipynb:183-188) through ``propose`` (utils/sampler.py:28-51), ``p_accept``
 (utils/dynamics.py:302-309), the unrolled leapfrog (:246-300) and ``tf.gradients(energy, x)`` inside it (:217-218) -- is
 computed by ``l2hmc_loss_grad`` (csrc/train.cuh: a recorded forward sweep and a hand-written reverse sweep, plain fp32
-FMA GEMMs).  Gaussian, GMM and RoughWell targets, no aux.  No CPU fallback.
+FMA GEMMs).  Gaussian, GMM, RoughWell and funnel targets, no aux.  No CPU fallback.
 
     loss, grads, Lx, px = loss_and_grads(dynamics, x)                  # one propose batch
     state = train_step(dynamics, opt, samples)                         # one iteration of SCGExperiment.ipynb:254-270
@@ -111,11 +111,12 @@ class Adam(object):
     moments live on the GPU, the parameters in the Dynamics' layer objects."""
 
     def __init__(self, dynamics, learning_rate=1e-3, decay_steps=1000, decay_rate=0.96, beta1=0.9, beta2=0.999, epsilon=1e-8,
-                 eps_trainable=True):
+                 eps_trainable=None):
         self.lr0, self.decay_steps, self.decay_rate = float(learning_rate), int(decay_steps), float(decay_rate)
         self.b1, self.b2, self.epsilon = float(beta1), float(beta2), float(epsilon)
         self.global_step = 0
-        self.eps_trainable = bool(eps_trainable)
+        # Dynamics(eps_trainable=...) decides whether alpha is a variable (utils/dynamics.py:49-56)
+        self.eps_trainable = bool(dynamics.eps_trainable if eps_trainable is None else eps_trainable)
         self._m, self._v = {}, {}
 
     @property

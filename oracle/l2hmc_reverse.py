@@ -100,8 +100,20 @@ def energy_hvp(e: O.Energy, x, w):
             out = out + ri * (0.5 * (w @ S) + 0.5 * (w @ S.T)) - ri * gi * (gi * w).sum(1, keepdim=True)
             gbar = gbar + ri * gi
         return out + gbar * (gbar * w).sum(1, keepdim=True)
-    # remaining kinds (funnel, decoder): not needed by the configurations with a training loop in the reference's
-    # notebook; differentiate the closed-form gradient expression instead of restating their Hessians
+    if isinstance(e, O.FunnelEnergy):
+        # grad = (v / sigma^2 + (n - |y|^2 / s) / 2, y / s), v = x_0, y = x_1:, s = e^v inside the clip; outside it s is a
+        # constant and the coupling to v drops out (utils/distributions.py:161-180)
+        v, y = x[:, 0], x[:, 1:]
+        out = (v > e.clip) | (-e.clip > v)
+        inside = (~out).to(x.dtype)
+        s = torch.where(out, torch.exp(torch.where(v > e.clip, torch.full_like(v, e.clip), torch.full_like(v, -e.clip))),
+                        torch.exp(v))
+        ss, wy = (y * y).sum(1), (w[:, 1:] * y).sum(1)
+        h = torch.empty_like(x)
+        h[:, 0] = w[:, 0] * (1.0 / e.sigma ** 2 + inside * 0.5 * ss / s) - inside * wy / s
+        h[:, 1:] = (w[:, 1:] - (inside * w[:, 0])[:, None] * y) / s[:, None]
+        return h
+    # the decoder energy: differentiate its closed-form gradient expression instead of restating the Hessian
     with torch.enable_grad():
         xr = x.detach().clone().requires_grad_(True)
         (h,) = torch.autograd.grad((e.grad(xr) * w).sum(), xr)

@@ -226,13 +226,21 @@ static float emu_energy(const EnergyDev &en, const Shape &sh, const float *x) {
     }
     for (int c = 0; c < en.ncomp; ++c) s += expf(V[c] - mx);
     U = -(logf(s) + mx);
-  } else {
+  } else if (en.kind == 2) {
     float n = 0.f, cs = 0.f;
     for (int i = 0; i < sh.D; ++i) {
       n = fmaf(x[i], x[i], n);
       cs += cosf(x[i] / en.s1);
     }
     U = 0.5f * n + en.s0 * cs;
+  } else {
+    const float sigma = en.s0, clip = en.s1, v = x[0];
+    float ss = 0.f;
+    for (int i = 1; i < sh.D; ++i) ss = fmaf(x[i], x[i], ss);
+    float s = expf(v);
+    if (v > clip) s = expf(clip);
+    if (-clip > v) s = expf(-clip);
+    U = 0.5f * ((v / sigma) * (v / sigma) + ss / s + (float)(sh.D - 1) * logf(6.2831855f * s));
   }
   return U / en.temperature;
 }
@@ -255,8 +263,16 @@ static void k_grad(EnergyDev en, Shape sh, long long n, const float *x, float *o
       for (int c = 0; c < en.ncomp; ++c) a = fmaf(V[c] / s, gc[c][j], a);
       o[j] = a;
     }
-  } else {
+  } else if (en.kind == 2) {
     for (int j = 0; j < sh.D; ++j) o[j] = xr[j] - en.s0 * sinf(xr[j] / en.s1) / en.s1;
+  } else {
+    const float sigma = en.s0, clip = en.s1, v = xr[0];
+    float ss = 0.f;
+    for (int i = 1; i < sh.D; ++i) ss = fmaf(xr[i], xr[i], ss);
+    const bool out_of_clip = v > clip || -clip > v;
+    const float s = out_of_clip ? expf(v > clip ? clip : -clip) : expf(v);
+    o[0] = v / (sigma * sigma) + (out_of_clip ? 0.f : 0.5f * (-ss / s + (float)(sh.D - 1)));
+    for (int j = 1; j < sh.D; ++j) o[j] = xr[j] / s;
   }
   for (int j = 0; j < sh.D; ++j) o[j] /= en.temperature;
 }
@@ -270,28 +286,42 @@ static void k_hamiltonian(EnergyDev en, Shape sh, long long n, const float *x, c
 
 #include "../../l2hmc_b200/csrc/train_host.cuh"
 
-// ---- entry point for tests/test_train_emu.py -----------------------------------------------------------------------
-// Parameters in the reference layout (l2hmc_net_params order, host pointers); energy: kind 0 / 1 (mu [ncomp, D],
-// S [ncomp, D, D], logc [ncomp]) or 2 (scalars eps, denominator).  Gradients are written to gx / gv (16 tensors each, caller-zeroed).
-extern "C" int emu_loss_grad(int D, int H, int T, float eps, float temperature, int kind, int ncomp, const float *mu,
-                             const float *S, const float *logc, float s0, float s1, const float *mask, const l2hmc_net_params *xnet, const l2hmc_net_params *vnet,
-                             const l2hmc_loss_grad_args *a, char *err, int err_len) {
-  l2hmc_ctx ctx;
+struct EmuEnergy {  // padded copies in the layout of the context (mu [ncomp][DP], Ssym [ncomp][DP][LDS])
+  std::vector<float> mu_p, S_p;
+};
+static void emu_setup(l2hmc_ctx &ctx, EmuEnergy &E, int D, int H, int T, float eps, float temperature, int kind, int ncomp,
+                      const float *mu, const float *S, const float *logc, float s0, float s1) {
   Shape &sh = ctx.sh;
   sh.D = D; sh.DP = (D + 3) / 4 * 4; sh.H = H; sh.HP = (H + 3) / 4 * 4; sh.T = T; sh.LDE = 128; sh.LDH = 192;
   sh.LDS = (sh.DP + 127) / 128 * 128; sh.hmc = 0; sh.eps = eps;
-  if (D > 64 || ncomp > l2hmc::MAX_COMP) return L2HMC_EUNSUPPORTED;
-  std::vector<float> mu_p((size_t)ncomp * sh.DP, 0.f), S_p((size_t)ncomp * sh.DP * sh.LDS, 0.f), mask_p((size_t)T * sh.DP, 0.f);
+  E.mu_p.assign((size_t)ncomp * sh.DP, 0.f);
+  E.S_p.assign((size_t)ncomp * sh.DP * sh.LDS, 0.f);
   if (kind == 0 || kind == 1)
     for (int c = 0; c < ncomp; ++c)
       for (int i = 0; i < D; ++i) {
-        mu_p[(size_t)c * sh.DP + i] = mu[c * D + i];
+        E.mu_p[(size_t)c * sh.DP + i] = mu[c * D + i];
         for (int j = 0; j < D; ++j)
-          S_p[((size_t)c * sh.DP + i) * sh.LDS + j] = 0.5f * (S[(c * D + i) * D + j] + S[(c * D + j) * D + i]);
+          E.S_p[((size_t)c * sh.DP + i) * sh.LDS + j] = 0.5f * (S[(c * D + i) * D + j] + S[(c * D + j) * D + i]);
       }
+  ctx.en = EnergyDev{kind, ncomp, E.mu_p.data(), E.S_p.data(), logc, s0, s1, temperature};
+}
+
+// ---- entry points for tests/test_train_emu.py -----------------------------------------------------------------------
+// Parameters in the reference layout (l2hmc_net_params order, host pointers); energy: kind 0 / 1 (mu [ncomp, D],
+// S [ncomp, D, D], logc [ncomp]), 2 (scalars eps, denominator) or 3 (scalars sigma, clip).  Gradients are written to
+// gx / gv (16 tensors each, caller-zeroed).
+extern "C" int emu_loss_grad(int D, int H, int T, float eps, float temperature, int kind, int ncomp, const float *mu,
+                             const float *S, const float *logc, float s0, float s1, const float *mask,
+                             const l2hmc_net_params *xnet, const l2hmc_net_params *vnet, const l2hmc_loss_grad_args *a,
+                             char *err, int err_len) {
+  if (D > 64 || ncomp > l2hmc::MAX_COMP) return L2HMC_EUNSUPPORTED;
+  l2hmc_ctx ctx;
+  EmuEnergy E;
+  emu_setup(ctx, E, D, H, T, eps, temperature, kind, ncomp, mu, S, logc, s0, s1);
+  const Shape &sh = ctx.sh;
+  std::vector<float> mask_p((size_t)T * sh.DP, 0.f);
   for (int t = 0; t < T; ++t)
     for (int d = 0; d < D; ++d) mask_p[(size_t)t * sh.DP + d] = mask[t * D + d];
-  ctx.en = EnergyDev{kind, ncomp, mu_p.data(), S_p.data(), logc, s0, s1, temperature};
   ctx.mask.p = mask_p.data();
   const l2hmc_net_params *ps[2] = {xnet, vnet};
   for (int i = 0; i < 2; ++i) {
@@ -303,4 +333,17 @@ extern "C" int emu_loss_grad(int D, int H, int T, float eps, float temperature, 
   const int rc = tr_loss_grad(&ctx, a);
   if (err && err_len > 0) snprintf(err, err_len, "%s", ctx.err.c_str());
   return rc;
+}
+
+// k_hvp alone: out [n, D] += w . d(grad U / T_emp)/dx at x
+extern "C" int emu_hvp(int D, float temperature, int kind, int ncomp, const float *mu, const float *S, const float *logc,
+                       float s0, float s1, long long n, const float *x, const float *w, float *out) {
+  if (D > 64 || ncomp > l2hmc::MAX_COMP) return L2HMC_EUNSUPPORTED;
+  l2hmc_ctx ctx;
+  EmuEnergy E;
+  emu_setup(ctx, E, D, 1, 1, 0.1f, temperature, kind, ncomp, mu, S, logc, s0, s1);
+  const Shape &sh = ctx.sh;
+  const EnergyDev &en = ctx.en;
+  emu::launch("k_hvp", dim3((unsigned)((n + 127) / 128)), dim3(128), [&] { tr::k_hvp(en, sh, n, x, w, out); });
+  return 0;
 }

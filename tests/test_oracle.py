@@ -388,3 +388,21 @@ def test_hand_written_reverse_pass_equals_autograd(name, temperature):
     assert worst < 1e-9, worst
     assert float(grads[-1].abs()) > 0 and all(float(g.abs().max()) > 0 for g in grads)
     assert float(g_h["alpha"]) == pytest.approx(float((grads[-1] * dyn._eps).detach()), rel=1e-9)
+
+
+@pytest.mark.parametrize("name", ["c1_scg2", "c3_mog2", "c4_rw32", "c4_rw32_hard", "funnel3"])
+def test_closed_form_hessian_vector_products_equal_autograd(name):
+    """l2hmc_reverse.energy_hvp (the forms the training kernels use) against autograd of the gradient expression,
+    including funnel rows beyond the clip where the coupling to x_0 drops out (utils/distributions.py:161-180)."""
+    import l2hmc_reverse as R
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    en = P.energy.to(torch.float64)
+    rng = np.random.default_rng(2)
+    x = torch.as_tensor(P.x0(12, rng)).double()
+    if name == "funnel3":
+        x[0, 0], x[1, 0] = 9.5, -8.5
+    w = torch.as_tensor(rng.standard_normal(x.shape))
+    xr = x.clone().requires_grad_(True)
+    (ref,) = torch.autograd.grad((en.grad(xr) * w).sum(), xr)
+    got = R.energy_hvp(en, x, w)
+    assert float((got - ref).abs().max()) <= 1e-10 * max(1.0, float(ref.abs().max()))

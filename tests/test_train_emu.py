@@ -59,6 +59,27 @@ def pack(net, cls=NetParams):
     return cls(**{k: fptr(v) for k, v in keep.items()}), keep
 
 
+def energy_args(P):
+    """(kind, ncomp, mu, S, logc, s0, s1) of a util.Problem for the emulated context."""
+    ncomp, logc, s0, s1 = 1, np.zeros(1, np.float32), 0.0, 0.0
+    mu, S = np.zeros(P.D, np.float32), np.zeros((P.D, P.D), np.float32)
+    if P.kind == "gaussian":
+        kind, mu = 0, np.ascontiguousarray(P.energy.mu.numpy(), np.float32)
+        S = np.ascontiguousarray(P.energy.S.numpy(), np.float32)
+    elif P.kind == "gmm":
+        kind, ncomp = 1, len(P.energy.mus)
+        mu = np.ascontiguousarray(np.stack([m.numpy() for m in P.energy.mus]), np.float32)
+        S = np.ascontiguousarray(np.stack([m.numpy() for m in P.energy.Ss]), np.float32)
+        logc = np.log(np.array([float(c) for c in P.energy.cs], np.float64)).astype(np.float32)
+    elif P.kind == "roughwell":
+        kind = 2
+        e, den = P.energy._scale(torch.zeros(1))
+        s0, s1 = float(e), float(den)
+    else:
+        kind, s0, s1 = 3, P.energy.sigma, P.energy.clip
+    return kind, ncomp, mu, S, logc, s0, s1
+
+
 def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
     n = x.shape[0]
     xp, keep_x = pack(P.xnet)
@@ -76,19 +97,7 @@ def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
                      loss=vptr(loss), d_eps=vptr(d_eps), grad_xnet=NetGrads(**{k: vptr(g) for k, g in gx.items()}),
                      grad_vnet=NetGrads(**{k: vptr(g) for k, g in gv.items()}), x_out=vptr(Lx), px_out=vptr(px), stream=None)
     mask = np.ascontiguousarray(P.mask, np.float32)
-    ncomp, logc, s0, s1 = 1, np.zeros(1, np.float32), 0.0, 0.0
-    if P.kind == "gaussian":
-        kind, mu = 0, np.ascontiguousarray(P.energy.mu.numpy(), np.float32)
-        S = np.ascontiguousarray(P.energy.S.numpy(), np.float32)
-    elif P.kind == "gmm":
-        kind, ncomp = 1, len(P.energy.mus)
-        mu = np.ascontiguousarray(np.stack([m.numpy() for m in P.energy.mus]), np.float32)
-        S = np.ascontiguousarray(np.stack([m.numpy() for m in P.energy.Ss]), np.float32)
-        logc = np.log(np.array([float(c) for c in P.energy.cs], np.float64)).astype(np.float32)
-    else:
-        kind, mu, S = 2, np.zeros(P.D, np.float32), np.zeros((P.D, P.D), np.float32)
-        e, den = P.energy._scale(torch.zeros(1))
-        s0, s1 = float(e), float(den)
+    kind, ncomp, mu, S, logc, s0, s1 = energy_args(P)
     err = C.create_string_buffer(512)
     rc = lib.emu_loss_grad(C.c_int(P.D), C.c_int(P.H), C.c_int(P.T), C.c_float(P.eps), C.c_float(temperature), C.c_int(kind),
                            C.c_int(ncomp), fptr(mu), fptr(S), fptr(logc), C.c_float(s0), C.c_float(s1), fptr(mask), C.byref(xp),
@@ -103,6 +112,7 @@ def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
     ("roughwell", 5, 7, 2, 12, 1.0),
     ("gmm", 2, 10, 3, 24, 1.0),          # config 3's target: the mixture's Hessian-vector product
     ("gmm", 3, 6, 2, 10, 1.3),
+    ("funnel", 3, 10, 3, 20, 1.0),
     ("gaussian", 9, 70, 1, 70, 1.0),     # width and chain count beyond one 64-wide GEMM tile
 ])
 def test_training_kernels_under_emulation_match_the_hand_written_reverse_pass(emu, kind, D, H, T, n, temperature):
@@ -244,3 +254,25 @@ def test_training_module_marshalling_and_loop_over_the_emulated_kernels(emu, mon
     assert opt.global_step == 6 and dyn.eps != eps_before
     assert not np.array_equal(W4_before, np.asarray(dyn._net_params[0]["W4"]))
     assert shim.calls == 1 + 2 + 6 * 2 + 2
+
+
+@pytest.mark.parametrize("name,temperature", [("c1_scg2", 1.0), ("c3_mog2", 1.3), ("c4_rw32", 1.0), ("c4_rw32_hard", 1.0),
+                                              ("funnel3", 2.0)])
+def test_hessian_vector_product_kernel_under_emulation(emu, name, temperature):
+    """k_hvp alone against the oracle's closed forms, funnel rows beyond the clip included."""
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    rng = np.random.default_rng(6)
+    n = 150                                    # more than one block of 128 threads
+    x = P.x0(n, rng)
+    if name == "funnel3":
+        x[0, 0], x[1, 0] = 9.5, -8.5
+    w = rng.standard_normal(x.shape).astype(np.float32)
+    base = rng.standard_normal(x.shape).astype(np.float32)
+    out = base.copy()
+    kind, ncomp, mu, S, logc, s0, s1 = energy_args(P)
+    emu.emu_hvp.restype = C.c_int
+    rc = emu.emu_hvp(C.c_int(P.D), C.c_float(temperature), C.c_int(kind), C.c_int(ncomp), fptr(mu), fptr(S), fptr(logc),
+                     C.c_float(s0), C.c_float(s1), C.c_longlong(n), fptr(np.ascontiguousarray(x)), fptr(w), fptr(out))
+    assert rc == 0
+    ref = R.energy_hvp(P.energy.to(torch.float64), torch.as_tensor(x).double(), torch.as_tensor(w).double()).numpy() / temperature
+    assert np.abs((out - base) - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())

@@ -48,7 +48,7 @@ def _worst(grads, acc):
 # tolerances: the fp32 noise floor of this gradient at exactly these settings is 0.4 .. 2.1e-5 (fp32 vs fp64 run of the
 # oracle sweep)
 @pytest.mark.parametrize("name,n,tol", [("c1_scg2", 200, 5e-4), ("c2_scg50", 256, 1e-3), ("c3_mog2", 200, 1e-3),
-                                        ("c4_rw32", 128, 1e-3)])
+                                        ("c4_rw32", 128, 1e-3), ("funnel3", 128, 1e-3)])
 def test_loss_grad_matches_the_hand_written_reverse_pass(name, n, tol):
     P, x, d, v = _setup(name, n)
     dyn = P.product()
@@ -98,14 +98,15 @@ def test_the_two_batches_of_the_notebook_objective_add_up():
 
 def test_unsupported_targets_and_modes_raise():
     from l2hmc_b200 import _lib
-    P = U.Problem(regime="stress", **U.CONFIGS["funnel3"])   # the funnel's Hessian is not restated yet
-    dyn = P.product()
-    x = torch.as_tensor(P.x0(8, np.random.default_rng(0)), device=DEV)
-    with pytest.raises(_lib.L2HMCError):
-        training.loss_and_grads(dyn, x)
     H = U.Problem(hmc=True, **U.CONFIGS["c1_scg2"]).product()
+    x = torch.as_tensor(np.random.default_rng(0).standard_normal((8, 2)).astype(np.float32), device=DEV)
     with pytest.raises(ValueError):
-        training.loss_and_grads(H, x[:, :2].contiguous())
+        training.loss_and_grads(H, x)
+    V = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])          # decoder energy / aux-conditioned nets: not covered yet
+    d = V.draws(8)
+    dyn = V.product()
+    with pytest.raises(_lib.L2HMCError):
+        training.loss_and_grads(dyn, torch.as_tensor(d["x"], device=DEV))
 
 
 def test_training_loop_lowers_the_loss_and_moves_every_parameter():
