@@ -213,6 +213,13 @@ typedef struct {
   float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4, *Ws, *bs, *Wt, *bt, *Wq, *bq, *scale_s, *scale_q;
 } l2hmc_net_grads;
 
+typedef enum {                 /* get_loss(name), utils/losses.py:26-34, on v = loss_vec(x, Lx, px) (:36-37)        */
+  L2HMC_LOSS_MIXED = 0,        /* loss_mixed     scale * mean(1 / v) - mean(v) / scale   utils/losses.py:53-59      */
+  L2HMC_LOSS_STANDARD = 1,     /* loss_std       -mean(v)                                utils/losses.py:49-51      */
+  L2HMC_LOSS_INVERSE = 2,      /* loss_inverse   -1 / mean(1 / (v + 1e-4))               utils/losses.py:44-47      */
+  L2HMC_LOSS_LOGSUMEXP = 3     /* loss_logsumexp logsumexp(-v) - log N                   utils/losses.py:39-42      */
+} l2hmc_loss_kind;             /* kinds 2 and 3 are not additive over calls: one call = one batch mean             */
+
 typedef struct {
   int64_t n;              /* chains of this batch                                                */
   const float *x;         /* [n,D] start points                                                  */
@@ -226,6 +233,7 @@ typedef struct {
   float *x_out;           /* Lx [n,D] or NULL                                                    */
   float *px_out;          /* [n] or NULL                                                         */
   void *stream;
+  int32_t loss_kind;      /* l2hmc_loss_kind; 0 = the notebook's objective                        */
 } l2hmc_loss_grad_args;
 
 int l2hmc_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a);

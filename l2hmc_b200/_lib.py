@@ -96,7 +96,8 @@ class NetGrads(C.Structure):
 class LossGradArgs(C.Structure):
     _fields_ = [("n", C.c_int64), ("x", C.c_void_p), ("v", C.c_void_p), ("dir", C.c_void_p), ("scale", C.c_float),
                 ("inv_count", C.c_float), ("loss", C.c_void_p), ("d_eps", C.c_void_p), ("grad_xnet", NetGrads),
-                ("grad_vnet", NetGrads), ("x_out", C.c_void_p), ("px_out", C.c_void_p), ("stream", C.c_void_p)]
+                ("grad_vnet", NetGrads), ("x_out", C.c_void_p), ("px_out", C.c_void_p), ("stream", C.c_void_p),
+                ("loss_kind", C.c_int32)]
 
 
 class TransitionArgs(C.Structure):

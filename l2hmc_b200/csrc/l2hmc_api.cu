@@ -1615,8 +1615,9 @@ extern "C" int l2hmc_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   if (a->n == 0) return L2HMC_OK;
   if (!a->x || !a->v || !a->dir || !a->loss || !a->d_eps || !tr_grads_complete(a->grad_xnet) || !tr_grads_complete(a->grad_vnet))
     return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: x, v, dir, loss, d_eps and all 2 x 16 gradient tensors are required");
-  if (!(a->scale > 0.f) || !isfinite(a->scale) || !isfinite(a->inv_count))
-    return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: scale must be finite and > 0, inv_count finite");
+  if (a->loss_kind < 0 || a->loss_kind > 3) return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: loss_kind %d unknown", a->loss_kind);
+  if (!(a->scale > 0.f) || !isfinite(a->scale) || !(a->inv_count > 0.f) || !isfinite(a->inv_count))
+    return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: scale and inv_count must be finite and > 0");
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   return tr_loss_grad(ctx, a);
 }

@@ -389,16 +389,11 @@ __global__ void k_hvp(EnergyDev en, Shape sh, long long n, const float *x, const
   }
 }
 
-// Objective of the batch and the cotangents that start the reverse sweep.
-//   p = exp(min(H0 - H1 + logJ, 0)), non-finite -> 0 (utils/dynamics.py:302-309); vv = |x0 - X|^2 p + 1e-4;
-//   loss_n = (scale / vv - vv / scale) * inv_count            (SCGExperiment.ipynb:171-181)
-// in: gU1 = grad U(X) / T_emp.  out: lossv[n], px[n], glj[n], gx = d/dX, gv = d/dV.
-__global__ void k_loss(long long n, int D, const float *x0, const float *X, const float *V, const float *H0, const float *H1,
-                       const float *logj, const float *gU1, float scale, float inv_count, float *lossv, float *px,
-                       float *glj, float *gx, float *gv) {
-  const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (g >= n) return;
+// ---- objective (utils/losses.py:36-59) ---------------------------------------------------------------------------
+// p = exp(min(H0 - H1 + logJ, 0)), non-finite -> 0 (utils/dynamics.py:302-309); vv = |x0 - X|^2 p + 1e-4 (loss_vec).
+// One warp per chain; returns sq = |x0 - X|^2 to every lane.
+__device__ __forceinline__ float loss_vec_chain(long long g, int lane, int D, const float *x0, const float *X, const float *H0,
+                                               const float *H1, const float *logj, float &p, bool &differentiable) {
   float sq = 0.f;
   for (int d = lane; d < D; d += 32) {
     const float dx = x0[g * D + d] - X[g * D + d];
@@ -406,19 +401,106 @@ __global__ void k_loss(long long n, int D, const float *x0, const float *X, cons
   }
   sq = warp_sum(sq);
   const float arg = H0[g] - H1[g] + logj[g];
-  float p = expf(fminf(arg, 0.f));
+  p = expf(fminf(arg, 0.f));
   const bool ok = isfinite(p);
   if (!ok) p = 0.f;
+  differentiable = ok && arg < 0.f;   // the min() clamp and the non-finite guard pass no gradient
+  return sq;
+}
+
+// vv[n] alone, for the losses whose d loss / d v needs a statistic of the whole batch first
+__global__ void k_loss_v(long long n, int D, const float *x0, const float *X, const float *H0, const float *H1,
+                         const float *logj, float *vv) {
+  const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  float p;
+  bool diff;
+  const float sq = loss_vec_chain(g, lane, D, x0, X, H0, H1, logj, p, diff);
+  if (lane == 0) vv[g] = sq * p + 1e-4f;
+}
+
+// stats[0] = sum 1 / (v + 1e-4) (loss_inverse); stats[1] = max(-v), stats[2] = sum exp(-v - max) (loss_logsumexp).
+// One block of 256 threads.
+__global__ void __launch_bounds__(256) k_loss_stats(long long n, const float *vv, float *stats) {
+  __shared__ float red[256];
+  const int t = threadIdx.x;
+  float a = 0.f, mx = -INFINITY;
+  for (long long i = t; i < n; i += 256) {
+    a += 1.f / (vv[i] + 1e-4f);
+    mx = fmaxf(mx, -vv[i]);
+  }
+  red[t] = mx;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) red[t] = fmaxf(red[t], red[t + o]);
+    __syncthreads();
+  }
+  mx = red[0];
+  __syncthreads();
+  float e = 0.f;
+  for (long long i = t; i < n; i += 256) e += expf(-vv[i] - mx);
+  red[t] = a;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  a = red[0];
+  __syncthreads();
+  red[t] = e;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (t < o) red[t] += red[t + o];
+    __syncthreads();
+  }
+  if (t == 0) {
+    stats[0] = a;
+    stats[1] = mx;
+    stats[2] = red[0];
+  }
+}
+
+// Loss terms of the batch and the cotangents that start the reverse sweep.  kind (get_loss names, utils/losses.py:26-34):
+//   0 'mixed'     scale mean(1/v) - mean(v)/scale   (:53-59; the notebook's objective, SCGExperiment.ipynb:171-181)
+//   1 'standard'  -mean(v)                          (:49-51)
+//   2 'inverse'   -1 / mean(1 / (v + 1e-4))         (:44-47)      needs stats[0]
+//   3 'logsumexp' logsumexp(-v) - log N             (:39-42)      needs stats[1], stats[2]
+// means run over 1 / inv_count chains.  in: gU1 = grad U(X) / T_emp.  out: lossv[n] (terms that sum to the loss), px[n],
+// glj[n], gx = d/dX, gv = d/dV.
+__global__ void k_loss(int kind, long long n, int D, const float *x0, const float *X, const float *V, const float *H0,
+                       const float *H1, const float *logj, const float *gU1, const float *stats, float scale, float inv_count,
+                       float *lossv, float *px, float *glj, float *gx, float *gv) {
+  const long long g = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (g >= n) return;
+  float p;
+  bool diff;
+  const float sq = loss_vec_chain(g, lane, D, x0, X, H0, H1, logj, p, diff);
   const float vv = sq * p + 1e-4f;
-  const float g_v = (-scale / (vv * vv) - 1.f / scale) * inv_count;
-  const float g_arg = (ok && arg < 0.f) ? g_v * sq * p : 0.f;
+  float g_v, term;
+  if (kind == 0) {
+    g_v = (-scale / (vv * vv) - 1.f / scale) * inv_count;
+    term = (scale / vv - vv / scale) * inv_count;
+  } else if (kind == 1) {
+    g_v = -inv_count;
+    term = -vv * inv_count;
+  } else if (kind == 2) {
+    const float m = stats[0] * inv_count, q = vv + 1e-4f;
+    g_v = -inv_count / (m * m * q * q);
+    term = g == 0 ? -1.f / m : 0.f;
+  } else {
+    g_v = -expf(-vv - stats[1]) / stats[2];
+    term = g == 0 ? stats[1] + logf(stats[2]) + logf(inv_count) : 0.f;
+  }
+  const float g_arg = diff ? g_v * sq * p : 0.f;
   for (int d = lane; d < D; d += 32) {
     const long long i = g * D + d;
     gx[i] = g_v * p * 2.f * (X[i] - x0[i]) - g_arg * gU1[i];
     gv[i] = -g_arg * V[i];
   }
   if (lane == 0) {
-    lossv[g] = (scale / vv - vv / scale) * inv_count;
+    lossv[g] = term;
     px[g] = p;
     glj[g] = g_arg;
   }

@@ -147,7 +147,7 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   struct { float **p; size_t n; } req[] = {
       {&tape_x, nD * 4 * T}, {&tape_v, nD * 4 * T}, {&x, nD}, {&v, nD}, {&gU, nD}, {&ab, 2 * nD}, {&h1, nH}, {&h2, nH},
       {&gh1, nH}, {&gh2, nH}, {&hd, 3 * nD}, {&ghd, 3 * nD}, {&sc, 2 * nD}, {&gab, 2 * nD}, {&gx, nD}, {&gv, nD}, {&gg, nD},
-      {&vec, (size_t)n * 9}};
+      {&vec, (size_t)n * 10 + 4}};
   for (auto &r : req)
     if (ws.get(r.p, r.n) != cudaSuccess) {
       cudaGetLastError();
@@ -155,10 +155,10 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
                   4 * T, (size_t)8 * D * 4 * T);
     }
   float *logj = vec, *H0 = vec + n, *H1 = vec + 2 * n, *lossv = vec + 3 * n, *px = vec + 4 * n, *glj = vec + 5 * n,
-        *geps = vec + 6 * n, *ct = vec + 7 * n, *st = vec + 8 * n;
+        *geps = vec + 6 * n, *ct = vec + 7 * n, *st = vec + 8 * n, *vv = vec + 9 * n, *stats = vec + 10 * n;
   CUDA_TRY(ctx, cudaMemcpyAsync(x, a->x, nD * sizeof(float), cudaMemcpyDeviceToDevice, s));
   CUDA_TRY(ctx, cudaMemcpyAsync(v, a->v, nD * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  CUDA_TRY(ctx, cudaMemsetAsync(vec, 0, (size_t)n * 9 * sizeof(float), s));
+  CUDA_TRY(ctx, cudaMemsetAsync(vec, 0, ((size_t)n * 10 + 4) * sizeof(float), s));
   const tr::Heads heads[2] = {{ctx->net_rawv[0].bs, ctx->net_rawv[0].bt, ctx->net_rawv[0].bq, ctx->net_rawv[0].ls, ctx->net_rawv[0].lq},
                               {ctx->net_rawv[1].bs, ctx->net_rawv[1].bt, ctx->net_rawv[1].bq, ctx->net_rawv[1].ls, ctx->net_rawv[1].lq}};
   const TrNetBufs nb = {ab, ct, st, h1, h2, hd};
@@ -185,8 +185,12 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   TR_LAUNCH(ctx, k_hamiltonian, tr_gb(GRID(n)), s, ctx->en, sh, n, tape_x, tape_v, H0);
   TR_LAUNCH(ctx, k_hamiltonian, tr_gb(GRID(n)), s, ctx->en, sh, n, x, v, H1);
   TR_LAUNCH(ctx, k_grad, tr_gb(GRID(n)), s, ctx->en, sh, n, x, gU);
-  TR_LAUNCH(ctx, tr::k_loss, TR_WGRID(n), s, n, D, tape_x, x, v, H0, H1, logj, gU, a->scale, a->inv_count, lossv, px, glj,
-                                                     gx, gv);
+  if (a->loss_kind >= 2) {  // the inverse / logsumexp losses weigh each chain by a statistic of the whole batch
+    TR_LAUNCH(ctx, tr::k_loss_v, TR_WGRID(n), s, n, D, tape_x, x, H0, H1, logj, vv);
+    TR_LAUNCH(ctx, tr::k_loss_stats, tr_gb(1, 256), s, n, vv, stats);
+  }
+  TR_LAUNCH(ctx, tr::k_loss, TR_WGRID(n), s, a->loss_kind, n, D, tape_x, x, v, H0, H1, logj, gU, stats, a->scale, a->inv_count,
+            lossv, px, glj, gx, gv);
   if ((rc = tr_colsum(ctx, s, lossv, 1, n, 1, nullptr, a->loss))) return rc;
   if (a->x_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->x_out, x, nD * sizeof(float), cudaMemcpyDeviceToDevice, s));
   if (a->px_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->px_out, px, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -22,6 +22,7 @@ from .dynamics import TORCH_FLOAT
 from .layers import load_stq_net
 from .sampler import tf_accept
 
+LOSSES = {"mixed": 0, "standard": 1, "inverse": 2, "logsumexp": 3}   # get_loss names, utils/losses.py:26-34
 NAMES = ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "Ws", "bs", "Wt", "bt", "Wq", "bq", "ls", "lq")
 _ABI = {"ls": "scale_s", "lq": "scale_q"}
 
@@ -47,11 +48,16 @@ def zero_grads(dynamics, device) -> Dict[str, object]:
             "eps": torch.zeros(1, dtype=TORCH_FLOAT, device=device), "loss": torch.zeros(1, dtype=TORCH_FLOAT, device=device)}
 
 
-def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale: float = 0.1, count: Optional[int] = None):
+def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale: float = 0.1, count: Optional[int] = None,
+                          loss: str = "mixed"):
     """Add one propose batch to ``acc`` (from zero_grads): loss += scale mean(1/v) - mean(v)/scale with
     v = |x - Lx|^2 px + 1e-4 (SCGExperiment.ipynb:171-181; utils/losses.py:36-59), gradients likewise.
     rng: optional {'direction' uint8 [N], 'v' [N, D]}; drawn from the Philox stream otherwise.  ``count``: the number of
-    chains the means run over (default N).  Returns (Lx, px)."""
+    chains the means run over (default N).  ``loss``: 'mixed' (the notebook's; ``scale`` applies), 'standard', 'inverse'
+    or 'logsumexp' -- ``get_loss(name)`` of utils/losses.py:26-59; the last two are means of one batch and do not add
+    over calls.  Returns (Lx, px)."""
+    if loss not in LOSSES:
+        raise ValueError("loss must be one of %s" % (sorted(LOSSES),))
     if dynamics.hmc:
         raise ValueError("an HMC-mode Dynamics has no parameters to train")
     dynamics._ensure_ctx()
@@ -82,15 +88,16 @@ def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale
                 raise TypeError("gradient accumulators must be contiguous fp32 tensors on the device of x")
             setattr(g, _ABI.get(k, k), t.data_ptr())
     a.x_out, a.px_out, a.stream = Lx.data_ptr(), px.data_ptr(), dynamics._stream()
+    a.loss_kind = LOSSES[loss]
     dynamics._chk(dynamics._lib.l2hmc_loss_grad(dynamics._ctx, C.byref(a)))
     return Lx, px
 
 
-def loss_and_grads(dynamics, x, *, rng=None, scale=0.1):
+def loss_and_grads(dynamics, x, *, rng=None, scale=0.1, loss="mixed"):
     """Value and gradient of one propose batch.  Returns (loss [1], grads, Lx, px); grads['alpha'] is the gradient for
     the reference's trainable ``alpha = log(eps)`` (utils/dynamics.py:50-58)."""
     acc = zero_grads(dynamics, x.device)
-    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng, scale=scale)
+    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng, scale=scale, loss=loss)
     acc["alpha"] = acc["eps"] * dynamics.eps
     return acc["loss"], acc, Lx, px
 

@@ -23,6 +23,7 @@ nets' parameter gradients and d/d(eps).
 """
 from __future__ import annotations
 
+import math
 from typing import Dict, List, Tuple
 
 import numpy as np
@@ -278,24 +279,50 @@ def accept_prob_vjp(dyn, x0, v0, X, V, lj, gp):
     return p, gX, gV, g_arg
 
 
-def loss_and_grads(x, dyn: O.OracleDynamics, r: dict, scale: float, acc: _Acc):
-    """One ``propose`` batch of the notebook objective: v = |x - Lx|^2 p + 1e-4, loss = scale E[1/v] - E[v]/scale
-    (SCGExperiment.ipynb:171-181 == utils/losses.py:53-59 up to where the scale sits).  Each chain back-propagates
-    through its selected direction only: the other one is multiplied by a zero mask (utils/sampler.py:38,44)."""
+LOSS_KINDS = ("mixed", "standard", "inverse", "logsumexp")   # get_loss names, utils/losses.py:26-34
+
+
+def loss_value_and_dv(v, kind: str, scale: float, count: float):
+    """Loss of utils/losses.py:36-59 as a function of v = loss_vec(x, Lx, px) [n], and d loss / d v, by hand.
+    ``count``: the number of chains the means run over (the batch, unless the caller splits one)."""
+    if kind == "mixed":      # scale mean(1/v) - mean(v)/scale   (:53-59; SCGExperiment.ipynb:171-181)
+        return (scale / v).sum() / count - v.sum() / (count * scale), (-scale / (v * v) - 1.0 / scale) / count
+    if kind == "standard":   # -mean(v)   (:49-51)
+        return -v.sum() / count, torch.full_like(v, -1.0 / count)
+    if kind == "inverse":    # -1 / mean(1 / (v + 1e-4))   (:44-47)
+        m = (1.0 / (v + 1e-4)).sum() / count
+        return -1.0 / m, -1.0 / (m * m * (v + 1e-4) ** 2 * count)
+    if kind == "logsumexp":  # logsumexp(-v) - log n   (:39-42)
+        mx = (-v).max()
+        z = torch.exp(-v - mx).sum()
+        return mx + torch.log(z) - math.log(count), -torch.exp(-v - mx) / z
+    raise ValueError(kind)
+
+
+def loss_and_grads(x, dyn: O.OracleDynamics, r: dict, scale: float, acc: _Acc, kind: str = "mixed", count=None):
+    """One ``propose`` batch of a utils/losses.py objective on v = |x - Lx|^2 p + 1e-4 (kind 'mixed' with the scale is the
+    notebook's, SCGExperiment.ipynb:171-181).  Each chain back-propagates through its selected direction only: the other
+    one is multiplied by a zero mask (utils/sampler.py:38,44)."""
     x = x.to(dyn.dtype)
     n = x.shape[0]
+    count = float(n if count is None else count)
     d = r["direction"].to(torch.bool)
-    total = torch.zeros((), dtype=dyn.dtype)
+    groups = []
+    v_all = torch.zeros(n, dtype=dyn.dtype)
+    zero = None
     for sel, fwd, vkey in ((d, True, "v_f"), (~d, False, "v_b")):
         if not sel.any():
             continue
         xs, vs = x[sel], r[vkey].to(dyn.dtype)[sel]
         X, V, lj, tape = transition(dyn, xs, vs, fwd)
-        p, _, _, _ = accept_prob_vjp(dyn, xs, vs, X, V, lj, torch.zeros(xs.shape[0], dtype=dyn.dtype))
+        zero = torch.zeros(xs.shape[0], dtype=dyn.dtype)
+        p, _, _, _ = accept_prob_vjp(dyn, xs, vs, X, V, lj, zero)
         sq = ((xs - X) ** 2).sum(1)
-        v = sq * p + 1e-4
-        total = total + (scale / v).sum() / n - v.sum() / (n * scale)
-        g_v = (-scale / (v * v) - 1.0 / scale) / n
+        v_all[sel] = sq * p + 1e-4
+        groups.append((sel, fwd, xs, vs, X, V, lj, tape, p, sq))
+    total, g_v_all = loss_value_and_dv(v_all, kind, scale, count)
+    for sel, fwd, xs, vs, X, V, lj, tape, p, sq in groups:
+        g_v = g_v_all[sel]
         gX = (g_v * p)[:, None] * 2.0 * (X - xs)
         _, gX2, gV, glj = accept_prob_vjp(dyn, xs, vs, X, V, lj, g_v * sq)
         transition_vjp(dyn, fwd, tape, gX + gX2, gV, glj, acc)

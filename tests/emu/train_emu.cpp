@@ -95,7 +95,7 @@ struct Pool {
 // kernels that synchronise (block barrier or warp shuffles) need their threads alive together; the others run their
 // threads one after another on the calling thread
 static bool cooperative(const char *name) {
-  for (const char *k : {"k_gemm", "k_update", "k_update_vjp", "k_loss"})
+  for (const char *k : {"k_gemm", "k_update", "k_update_vjp", "k_loss", "k_loss_v", "k_loss_stats"})
     if (strstr(name, k) && strlen(strstr(name, k)) == strlen(k)) return true;
   return false;
 }

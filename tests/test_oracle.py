@@ -406,3 +406,30 @@ def test_closed_form_hessian_vector_products_equal_autograd(name):
     (ref,) = torch.autograd.grad((en.grad(xr) * w).sum(), xr)
     got = R.energy_hvp(en, x, w)
     assert float((got - ref).abs().max()) <= 1e-10 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("kind", ["mixed", "standard", "inverse", "logsumexp"])
+def test_hand_written_reverse_pass_for_every_loss_of_the_library(kind):
+    """get_loss(name) of utils/losses.py:26-59: the hand-written d loss / d v and sweep against autograd of the oracle's
+    loss_mixed / loss_std / loss_inverse / loss_logsumexp through the dynamics."""
+    import l2hmc_reverse as R
+    P = U.Problem(regime="stress", kind="gaussian", D=2, H=8, T=3, eps=0.1)
+    dyn = P.oracle(torch.float64)
+    rng = np.random.default_rng(3)
+    n = 20
+    x = torch.as_tensor(P.x0(n, rng)).double()
+    r = {"direction": torch.as_tensor(rng.integers(0, 2, n).astype(np.float64)),
+         "v_f": torch.as_tensor(rng.standard_normal((n, P.D))), "v_b": torch.as_tensor(rng.standard_normal((n, P.D)))}
+    with torch.no_grad():
+        acc = R._Acc(dyn)
+        loss_h = R.loss_and_grads(x, dyn, r, 0.1, acc, kind=kind)
+    params = U.O.trainable_parameters(dyn)
+    Lx, _, px, _ = U.O.propose(x, dyn, direction=r["direction"], v_f=r["v_f"], v_b=r["v_b"])
+    fn = {"mixed": lambda: U.O.loss_mixed(x, Lx, px, 0.1), "standard": lambda: U.O.loss_std(x, Lx, px),
+          "inverse": lambda: U.O.loss_inverse(x, Lx, px), "logsumexp": lambda: U.O.loss_logsumexp(x, Lx, px)}[kind]
+    loss_a = fn()
+    grads = torch.autograd.grad(loss_a, params)
+    assert float(loss_h) == pytest.approx(float(loss_a.detach()), rel=1e-12)
+    keys = sorted(dyn.xnet)
+    for gh, ga in zip([acc.x[k] for k in keys] + [acc.v[k] for k in keys], grads):
+        assert float((gh - ga).abs().max()) <= 1e-9 * max(1e-12, float(ga.abs().max()))

@@ -80,7 +80,7 @@ def energy_args(P):
     return kind, ncomp, mu, S, logc, s0, s1
 
 
-def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
+def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0, loss_kind=0):
     n = x.shape[0]
     xp, keep_x = pack(P.xnet)
     vp, keep_v = pack(P.vnet)
@@ -95,7 +95,8 @@ def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0):
     d8 = np.ascontiguousarray(direction, np.uint8)
     a = LossGradArgs(n=n, x=vptr(x), v=vptr(v), dir=vptr(d8), scale=scale, inv_count=inv_count,
                      loss=vptr(loss), d_eps=vptr(d_eps), grad_xnet=NetGrads(**{k: vptr(g) for k, g in gx.items()}),
-                     grad_vnet=NetGrads(**{k: vptr(g) for k, g in gv.items()}), x_out=vptr(Lx), px_out=vptr(px), stream=None)
+                     grad_vnet=NetGrads(**{k: vptr(g) for k, g in gv.items()}), x_out=vptr(Lx), px_out=vptr(px), stream=None,
+                     loss_kind=loss_kind)
     mask = np.ascontiguousarray(P.mask, np.float32)
     kind, ncomp, mu, S, logc, s0, s1 = energy_args(P)
     err = C.create_string_buffer(512)
@@ -276,3 +277,28 @@ def test_hessian_vector_product_kernel_under_emulation(emu, name, temperature):
     assert rc == 0
     ref = R.energy_hvp(P.energy.to(torch.float64), torch.as_tensor(x).double(), torch.as_tensor(w).double()).numpy() / temperature
     assert np.abs((out - base) - ref).max() <= 2e-5 * max(1.0, np.abs(ref).max())
+
+
+@pytest.mark.parametrize("kind", ["standard", "inverse", "logsumexp"])
+def test_library_losses_under_emulation(emu, kind):
+    """get_loss(name) of utils/losses.py:26-59 through the emulated kernels (the batch statistics of 'inverse' and
+    'logsumexp' come from a one-block reduction), against the hand-written reverse pass."""
+    from l2hmc_b200.training import LOSSES
+    P = U.Problem(regime="stress", kind="gaussian", D=3, H=6, T=2, eps=0.1)
+    rng = np.random.default_rng(12)
+    n = 300                                   # more rows than the reduction block has threads
+    x = P.x0(n, rng)
+    d = rng.integers(0, 2, n).astype(np.uint8)
+    v = rng.standard_normal((n, P.D)).astype(np.float32)
+    r = {"direction": torch.as_tensor(d.astype(np.float64)), "v_f": torch.as_tensor(v).double(), "v_b": torch.as_tensor(v).double()}
+    dyn = P.oracle(torch.float64)
+    with torch.no_grad():
+        acc = R._Acc(dyn)
+        loss_o = R.loss_and_grads(torch.as_tensor(x).double(), dyn, r, 0.1, acc, kind=kind)
+    loss, d_eps, gx, gv, _, _ = run_emu(emu, P, x, v, d, 0.1, 1.0 / n, loss_kind=LOSSES[kind])
+    assert loss == pytest.approx(float(loss_o), rel=2e-4)
+    assert d_eps == pytest.approx(float(acc.eps), rel=2e-3, abs=1e-3 * abs(float(loss_o)))
+    for got, ref in ((gx, acc.x), (gv, acc.v)):
+        for k in NAMES:
+            a, b = got[k].astype(np.float64), ref[ORACLE_KEY[k]].numpy().reshape(got[k].shape)
+            assert np.abs(a - b).max() <= 2e-4 * max(1e-12, np.abs(b).max()), (kind, k)

@@ -132,3 +132,19 @@ def test_training_loop_lowers_the_loss_and_moves_every_parameter():
     for p0, p1 in zip(before, dyn._net_params):
         for k in training.NAMES:
             assert not np.array_equal(p0[k], np.asarray(p1[k])), k
+
+
+@pytest.mark.parametrize("kind", ["standard", "inverse", "logsumexp"])
+def test_library_losses_match_the_hand_written_reverse_pass(kind):
+    """get_loss(name) of utils/losses.py:26-59."""
+    P, x, d, v = _setup("c1_scg2", 600)
+    dyn = P.product()
+    rng = {"direction": torch.as_tensor(d, device=DEV), "v": torch.as_tensor(v, device=DEV)}
+    loss, grads, _, _ = training.loss_and_grads(dyn, torch.as_tensor(x, device=DEV), rng=rng, loss=kind)
+    odyn = P.oracle(torch.float64)
+    r = {"direction": torch.as_tensor(d.astype(np.float64)), "v_f": torch.as_tensor(v).double(), "v_b": torch.as_tensor(v).double()}
+    with torch.no_grad():
+        acc = R._Acc(odyn)
+        loss_o = R.loss_and_grads(torch.as_tensor(x).double(), odyn, r, 0.1, acc, kind=kind)
+    assert float(loss[0]) == pytest.approx(float(loss_o), rel=1e-3)
+    assert _worst(grads, acc) < 1e-3
