@@ -206,8 +206,8 @@ int l2hmc_acl_spectrum(l2hmc_ctx *ctx, int64_t n_steps, int64_t n, const float *
  * back-propagated through propose's selected direction (utils/sampler.py:34-44), p_accept (utils/dynamics.py:302-309),
  * the unrolled leapfrog (:246-300) and tf.gradients(energy, x) inside it (:217-218).
  * Gradient tensors have the shapes of l2hmc_net_params; every output is ACCUMULATED (+=) so that the caller zeroes once
- * and adds the `x` batch and the `z` batch of the notebook objective.  Device pointers throughout; the call synchronises
- * the stream.  Covers the closed-form energies (Gaussian, GMM, RoughWell, funnel) without aux; the decoder target and
+ * and adds the `x` batch and the `z` batch of the notebook objective.  Device pointers throughout; asynchronous on the
+ * stream (scratch, 4*T*2*x_dim floats per chain for the record plus activations, is held by the context).  Covers the closed-form energies (Gaussian, GMM, RoughWell, funnel) without aux; the decoder target and
  * aux-conditioned nets: L2HMC_EUNSUPPORTED. */
 typedef struct {
   float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4, *Ws, *bs, *Wt, *bt, *Wq, *bq, *scale_s, *scale_q;

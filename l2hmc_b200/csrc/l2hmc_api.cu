@@ -80,6 +80,7 @@ struct l2hmc_ctx {
   // host copies of the raw nets (eps / T changes do not need them, kept for re-packing)
   std::vector<float> net_host[2];
   DevBuf mask;
+  DevBuf train_ws;       // scratch of l2hmc_loss_grad (train_host.cuh), grown on demand, kept until destroy
   bool mask_set = false;
   DevBuf energy_buf;
   EnergyDev en;
@@ -665,7 +666,7 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   DevBuf *bufs[] = {&ctx->net_packed[0], &ctx->net_packed[1], &ctx->net_raw[0], &ctx->net_raw[1], &ctx->mask,
                     &ctx->energy_buf, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn,
-                    &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf, &ctx->tc_hc[0], &ctx->tc_hc[1]};
+                    &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf, &ctx->tc_hc[0], &ctx->tc_hc[1], &ctx->train_ws};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   {

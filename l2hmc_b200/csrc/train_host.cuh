@@ -7,19 +7,25 @@ namespace {
 
 namespace tr = l2hmc::train;
 
-struct TrScratch {  // device scratch of one call, released on every exit path
-  std::vector<void *> ptrs;
-  ~TrScratch() {
-    for (void *p : ptrs) cudaFree(p);
-  }
-  cudaError_t get(float **out, size_t n_floats) {
+// Device scratch of l2hmc_loss_grad: one allocation held by the context, grown on demand (no allocation and no
+// synchronisation in the steady state); sub-buffers are carved out at 256-byte boundaries.
+int tr_workspace(l2hmc_ctx *ctx, size_t n_floats, float **out) {
+  if (ctx->train_ws.n < n_floats) {
+    if (ctx->train_ws.p) cudaFree(ctx->train_ws.p);  // waits for work that still uses it
+    ctx->train_ws.p = nullptr;
+    ctx->train_ws.n = 0;
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, (n_floats ? n_floats : 1) * sizeof(float));
-    if (e == cudaSuccess) ptrs.push_back(p);
-    *out = static_cast<float *>(p);
-    return e;
+    if (cudaMalloc(&p, n_floats * sizeof(float)) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(ctx, L2HMC_ENOMEM, "l2hmc_loss_grad: out of device memory (%zu bytes of scratch; the record of the sub-updates takes %d x 2 x x_dim floats per chain)",
+                  n_floats * sizeof(float), 4 * ctx->sh.T);
+    }
+    ctx->train_ws.p = static_cast<float *>(p);
+    ctx->train_ws.n = n_floats;
   }
-};
+  *out = ctx->train_ws.p;
+  return L2HMC_OK;
+}
 
 struct TrNetBufs {
   const float *ab;          // [n, 2D] net input
@@ -141,19 +147,22 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   const long long n = a->n;
   const float eps = sh.eps;
   cudaStream_t s = (cudaStream_t)a->stream;
-  TrScratch ws;
   const size_t nD = (size_t)n * D, nH = (size_t)n * H;
   float *tape_x, *tape_v, *x, *v, *gU, *ab, *h1, *h2, *gh1, *gh2, *hd, *ghd, *sc, *gab, *gx, *gv, *gg, *vec;
   struct { float **p; size_t n; } req[] = {
       {&tape_x, nD * 4 * T}, {&tape_v, nD * 4 * T}, {&x, nD}, {&v, nD}, {&gU, nD}, {&ab, 2 * nD}, {&h1, nH}, {&h2, nH},
       {&gh1, nH}, {&gh2, nH}, {&hd, 3 * nD}, {&ghd, 3 * nD}, {&sc, 2 * nD}, {&gab, 2 * nD}, {&gx, nD}, {&gv, nD}, {&gg, nD},
       {&vec, (size_t)n * 10 + 4}};
-  for (auto &r : req)
-    if (ws.get(r.p, r.n) != cudaSuccess) {
-      cudaGetLastError();
-      return fail(ctx, L2HMC_ENOMEM, "l2hmc_loss_grad: out of device memory (the record of %d sub-updates takes %zu bytes per chain)",
-                  4 * T, (size_t)8 * D * 4 * T);
-    }
+  auto pad = [](size_t k) { return (k + 63) / 64 * 64; };
+  size_t total = 0;
+  for (auto &r : req) total += pad(r.n);
+  float *base = nullptr;
+  int rc = tr_workspace(ctx, total, &base);
+  if (rc) return rc;
+  for (auto &r : req) {
+    *r.p = base;
+    base += pad(r.n);
+  }
   float *logj = vec, *H0 = vec + n, *H1 = vec + 2 * n, *lossv = vec + 3 * n, *px = vec + 4 * n, *glj = vec + 5 * n,
         *geps = vec + 6 * n, *ct = vec + 7 * n, *st = vec + 8 * n, *vv = vec + 9 * n, *stats = vec + 10 * n;
   CUDA_TRY(ctx, cudaMemcpyAsync(x, a->x, nD * sizeof(float), cudaMemcpyDeviceToDevice, s));
@@ -162,7 +171,6 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   const tr::Heads heads[2] = {{ctx->net_rawv[0].bs, ctx->net_rawv[0].bt, ctx->net_rawv[0].bq, ctx->net_rawv[0].ls, ctx->net_rawv[0].lq},
                               {ctx->net_rawv[1].bs, ctx->net_rawv[1].bt, ctx->net_rawv[1].bq, ctx->net_rawv[1].ls, ctx->net_rawv[1].lq}};
   const TrNetBufs nb = {ab, ct, st, h1, h2, hd};
-  int rc;
   // sub-update j of a leapfrog step: 0 and 3 are V (momentum) updates, 1 and 2 the two masked X (position) updates
   auto which_of = [](int j) { return (j == 0 || j == 3) ? 0 : j; };
 
@@ -215,8 +223,7 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
     }
   }
   if ((rc = tr_colsum(ctx, s, geps, 1, n, 1, nullptr, a->d_eps))) return rc;
-  CUDA_TRY(ctx, cudaStreamSynchronize(s));  // the scratch is released on return
-  return L2HMC_OK;
+  return L2HMC_OK;  // asynchronous on the stream, like l2hmc_transition
 }
 
 }  // namespace

@@ -178,14 +178,17 @@ using l2hmc::Shape;
 
 struct DevBufEmu {
   float *p = nullptr;
+  size_t n = 0;
 };
 struct l2hmc_ctx {
   Shape sh;
   EnergyDev en;
   DevBufEmu mask;
   NetRaw net_rawv[2];
+  DevBufEmu train_ws;
   long long launches = 0;
   std::string err;
+  ~l2hmc_ctx() { free(train_ws.p); }
 };
 
 static int fail(l2hmc_ctx *ctx, int code, const char *fmt, ...) {
