@@ -1,12 +1,11 @@
 // TEST INFRASTRUCTURE (CPU suite only; never part of libl2hmc.so).
 // Runs the SOURCE of the training-path kernels (l2hmc_b200/csrc/train.cuh) and of their host driver (train_host.cuh) on
-// host threads, so that `pytest -m "not gpu"` can check index arithmetic, strides, the GEMM tiling, the sweep order and
-// the vector-Jacobian products against oracle/l2hmc_reverse.py without a GPU.  One pool thread per CUDA thread of a
-// block; blocks run one after another; __syncthreads / warp shuffles are barriers over the block / the warp; atomicAdd
-// takes a lock.  The component kernels the driver borrows from l2hmc_api.cu (k_grad, k_hamiltonian: already checked on
+// the host, so that `pytest -m "not gpu"` can check index arithmetic, strides, the GEMM tiling, the sweep order and
+// the vector-Jacobian products against oracle/l2hmc_reverse.py without a GPU.  One fiber per CUDA thread of a block;
+// blocks run one after another; __syncthreads / warp shuffles are scheduler barriers over the block / the warp.  The component kernels the driver borrows from l2hmc_api.cu (k_grad, k_hamiltonian: already checked on
 // the GPU) are restated here for the two energies the training path covers.
 //
-// Build (tests/test_train_emu.py does this):  g++ -std=c++20 -O1 -pthread -shared -fPIC -DL2HMC_TRAIN_EMU ...
+// Build (tests/test_train_emu.py does this):  g++ -std=c++17 -O1 -shared -fPIC -DL2HMC_TRAIN_EMU ...
 #include <math.h>
 #include <stdarg.h>
 #include <stdint.h>
@@ -14,12 +13,11 @@
 #include <stdlib.h>
 #include <string.h>
 
-#include <barrier>
+#include <ucontext.h>
+
 #include <functional>
 #include <memory>
-#include <mutex>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/l2hmc.h"
@@ -41,8 +39,8 @@ struct dim3 {
 struct uint3_ {
   unsigned x, y, z;
 };
-static thread_local uint3_ threadIdx, blockIdx;
-static thread_local dim3 blockDim, gridDim;
+static uint3_ threadIdx, blockIdx;
+static dim3 blockDim, gridDim;
 
 typedef int cudaError_t;
 typedef void *cudaStream_t;
@@ -56,47 +54,99 @@ static inline cudaError_t cudaGetLastError() { return 0; }
 static inline cudaError_t cudaSetDevice(int) { return 0; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 
-static thread_local bool emu_in_worker = false;
+// Every CUDA thread of a block is a fiber (ucontext) on the calling OS thread; a barrier is a yield to a scheduler that
+// releases a warp (shuffles) or the block (__syncthreads) once all of its live threads wait there.  Blocks run one after
+// another.  Deterministic, and no OS threads are involved.
 namespace emu {
 constexpr int MAX_THREADS = 256;
-static std::mutex atomic_lock;
-static std::unique_ptr<std::barrier<>> block_bar;
-static std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
-static float warp_buf[MAX_THREADS];
-
-struct Pool {
-  std::vector<std::thread> th;
-  std::barrier<> start{MAX_THREADS + 1}, done{MAX_THREADS + 1};
-  std::function<void()> job;
-  int nt = 0;
-  dim3 block, grid;
-  uint3_ bidx{0, 0, 0};
-  Pool() {
-    for (int w = 0; w < MAX_THREADS / 32; ++w) warp_bar.emplace_back(new std::barrier<>(32));
-    for (int t = 0; t < MAX_THREADS; ++t)
-      th.emplace_back([this, t] {
-        emu_in_worker = true;
-        for (;;) {
-          start.arrive_and_wait();
-          if (t < nt) {
-            threadIdx = {(unsigned)t, 0, 0};
-            blockIdx = bidx;
-            blockDim = block;
-            gridDim = grid;
-            job();
-          }
-          done.arrive_and_wait();
-        }
-      });
-    for (auto &x : th) x.detach();
-  }
+constexpr size_t STACK_BYTES = 128 * 1024;
+enum { RUN = 0, WAIT_WARP = 1, WAIT_BLOCK = 2 };
+struct Fiber {
+  ucontext_t ctx;
+  bool done = true;
+  int wait = RUN;
 };
+static Fiber fibers[MAX_THREADS];
+static char *stacks = nullptr;
+static ucontext_t sched_ctx;
+static int cur = -1;                        // fiber that is running, -1: the scheduler / a plain call
+static std::function<void()> job;
+static float warp_buf[MAX_THREADS];
+static dim3 cur_block, cur_grid;
+static uint3_ cur_bidx;
 
-// kernels that synchronise (block barrier or warp shuffles) need their threads alive together; the others run their
-// threads one after another on the calling thread
+static void set_ids(int t) {
+  threadIdx = {(unsigned)t, 0, 0};
+  blockIdx = cur_bidx;
+  blockDim = cur_block;
+  gridDim = cur_grid;
+}
+static void fiber_main() {
+  job();
+  fibers[cur].done = true;
+  swapcontext(&fibers[cur].ctx, &sched_ctx);
+}
+static void yield(int kind) {
+  if (cur < 0) abort();  // a kernel that synchronises was launched as one that does not
+  fibers[cur].wait = kind;
+  swapcontext(&fibers[cur].ctx, &sched_ctx);
+}
+
+static void run_block(int nt) {
+  if (!stacks) stacks = static_cast<char *>(malloc(STACK_BYTES * MAX_THREADS));
+  for (int t = 0; t < nt; ++t) {
+    Fiber &f = fibers[t];
+    getcontext(&f.ctx);
+    f.ctx.uc_stack.ss_sp = stacks + STACK_BYTES * t;
+    f.ctx.uc_stack.ss_size = STACK_BYTES;
+    f.ctx.uc_link = nullptr;
+    makecontext(&f.ctx, fiber_main, 0);
+    f.done = false;
+    f.wait = RUN;
+  }
+  for (;;) {
+    bool progressed = false, alive = false;
+    for (int t = 0; t < nt; ++t) {
+      Fiber &f = fibers[t];
+      if (f.done || f.wait != RUN) continue;
+      cur = t;
+      set_ids(t);
+      swapcontext(&sched_ctx, &f.ctx);
+      cur = -1;
+      progressed = true;
+    }
+    for (int w = 0; w < nt / 32; ++w) {  // a warp whose live threads all wait on a shuffle moves on
+      int live = 0, waiting = 0;
+      for (int t = 32 * w; t < 32 * w + 32; ++t) {
+        live += !fibers[t].done;
+        waiting += !fibers[t].done && fibers[t].wait == WAIT_WARP;
+      }
+      if (live && waiting == live) {
+        for (int t = 32 * w; t < 32 * w + 32; ++t) fibers[t].wait = RUN;
+        progressed = true;
+      }
+    }
+    int live = 0, waiting = 0;
+    for (int t = 0; t < nt; ++t) {
+      live += !fibers[t].done;
+      waiting += !fibers[t].done && fibers[t].wait == WAIT_BLOCK;
+    }
+    alive = live > 0;
+    if (live && waiting == live) {
+      for (int t = 0; t < nt; ++t) fibers[t].wait = RUN;
+      progressed = true;
+    }
+    if (!alive) return;
+    if (!progressed) abort();  // deadlock: threads of one warp / block wait at different barriers
+  }
+}
+
+// kernels that synchronise run as fibers; the others run their threads one after another as plain calls
 static bool cooperative(const char *name) {
-  for (const char *k : {"k_gemm", "k_update", "k_update_vjp", "k_loss", "k_loss_v", "k_loss_stats"})
-    if (strstr(name, k) && strlen(strstr(name, k)) == strlen(k)) return true;
+  for (const char *k : {"k_gemm", "k_update", "k_update_vjp", "k_loss", "k_loss_v", "k_loss_stats"}) {
+    const char *p = strstr(name, k);
+    if (p && strlen(p) == strlen(k) && (p == name || p[-1] == ':')) return true;
+  }
   return false;
 }
 
@@ -104,53 +154,38 @@ template <class F>
 void launch(const char *name, dim3 grid, dim3 block, F &&body) {
   const int nt = (int)block.x;
   if (nt > MAX_THREADS || block.y != 1 || block.z != 1 || nt % 32 != 0) abort();
-  if (!cooperative(name)) {
-    for (unsigned bz = 0; bz < grid.z; ++bz)
-      for (unsigned by = 0; by < grid.y; ++by)
-        for (unsigned bx = 0; bx < grid.x; ++bx)
-          for (int t = 0; t < nt; ++t) {
-            threadIdx = {(unsigned)t, 0, 0};
-            blockIdx = {bx, by, bz};
-            blockDim = block;
-            gridDim = grid;
-            body();
-          }
-    return;
-  }
-  // cooperative kernels: a pool of MAX_THREADS workers, created once (and left to the process exit), runs one block at a
-  // time; every thread of these kernels either reaches each barrier or leaves with its whole warp before any
-  static Pool *pool = new Pool();
-  block_bar.reset(new std::barrier<>(nt));
-  pool->nt = nt;
-  pool->block = block;
-  pool->grid = grid;
-  pool->job = body;
+  const bool coop = cooperative(name);
+  cur_block = block;
+  cur_grid = grid;
+  if (coop) job = body;
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {
-        pool->bidx = {bx, by, bz};
-        pool->start.arrive_and_wait();
-        pool->done.arrive_and_wait();
+        cur_bidx = {bx, by, bz};
+        if (coop) {
+          run_block(nt);
+        } else {
+          for (int t = 0; t < nt; ++t) {
+            set_ids(t);
+            body();
+          }
+        }
       }
-  pool->job = nullptr;
+  job = nullptr;
 }
 }  // namespace emu
 
-static inline void __syncthreads() {
-  if (!emu_in_worker) abort();  // a kernel that synchronises was launched as non-cooperative
-  emu::block_bar->arrive_and_wait();
-}
+static inline void __syncthreads() { emu::yield(emu::WAIT_BLOCK); }
 static inline float __shfl_xor_sync(unsigned, float v, int o) {
-  if (!emu_in_worker) abort();
-  const int t = (int)threadIdx.x;
+  const int t = emu::cur;
+  if (t < 0) abort();
   emu::warp_buf[t] = v;
-  emu::warp_bar[t / 32]->arrive_and_wait();
+  emu::yield(emu::WAIT_WARP);
   const float r = emu::warp_buf[t ^ o];
-  emu::warp_bar[t / 32]->arrive_and_wait();
+  emu::yield(emu::WAIT_WARP);
   return r;
 }
 static inline float atomicAdd(float *p, float v) {
-  std::lock_guard<std::mutex> g(emu::atomic_lock);
   const float old = *p;
   *p = old + v;
   return old;

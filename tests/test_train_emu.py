@@ -43,7 +43,7 @@ def emu():
     deps = [SRC] + [os.path.join(HERE, "..", "l2hmc_b200", "csrc", f) for f in ("train.cuh", "train_host.cuh")] + \
            [os.path.join(HERE, "..", "include", "l2hmc.h")]
     if not os.path.exists(OUT) or any(os.path.getmtime(d) > os.path.getmtime(OUT) for d in deps):
-        subprocess.run(["g++", "-std=c++20", "-O1", "-pthread", "-shared", "-fPIC", "-DL2HMC_TRAIN_EMU", "-DL2HMC_TR_KCHUNK=16", "-DL2HMC_TR_SLAB=16", "-x", "c++",
+        subprocess.run(["g++", "-std=c++17", "-O1", "-shared", "-fPIC", "-DL2HMC_TRAIN_EMU", "-DL2HMC_TR_KCHUNK=16", "-DL2HMC_TR_SLAB=16", "-x", "c++",
                         "-Wno-unknown-pragmas", SRC, "-o", OUT], check=True)
     lib = C.CDLL(OUT)
     lib.emu_loss_grad.restype = C.c_int
@@ -115,6 +115,9 @@ def run_emu(lib, P, x, v, direction, scale, inv_count, temperature=1.0, loss_kin
     ("gmm", 3, 6, 2, 10, 1.3),
     ("funnel", 3, 10, 3, 20, 1.0),
     ("gaussian", 9, 70, 1, 70, 1.0),     # width and chain count beyond one 64-wide GEMM tile
+    ("gaussian", 2, 1, 1, 1, 1.0),       # one chain, one hidden unit, one leapfrog step
+    ("gaussian", 50, 100, 2, 130, 1.0),  # BASELINE config 2's shape (fewer steps and chains)
+    ("roughwell", 32, 100, 2, 66, 1.0),  # config 4's shape
 ])
 def test_training_kernels_under_emulation_match_the_hand_written_reverse_pass(emu, kind, D, H, T, n, temperature):
     kw = dict(kind=kind, D=D, H=H, T=T, eps=0.1)
@@ -139,7 +142,7 @@ def test_training_kernels_under_emulation_match_the_hand_written_reverse_pass(em
     loss, d_eps, gx, gv, Lx, px = run_emu(emu, P, x, v, d, scale, 1.0 / n, temperature)
 
     assert np.abs(Lx - Lx_o.numpy()).max() <= 2e-5 * max(1.0, float(Lx_o.abs().max()))
-    assert np.abs(px - px_o.numpy()).max() <= 2e-5
+    assert np.abs(px - px_o.numpy()).max() <= 1e-4   # H is O(100) at 50 dimensions: fp32 cancellation in H0 - H1 + log|J|
     assert loss == pytest.approx(float(loss_o), rel=2e-4)
     assert d_eps == pytest.approx(float(acc.eps), rel=2e-3, abs=1e-3 * abs(float(loss_o)))
     worst = 0.0
@@ -302,3 +305,25 @@ def test_library_losses_under_emulation(emu, kind):
         for k in NAMES:
             a, b = got[k].astype(np.float64), ref[ORACLE_KEY[k]].numpy().reshape(got[k].shape)
             assert np.abs(a - b).max() <= 2e-4 * max(1e-12, np.abs(b).max()), (kind, k)
+
+
+@pytest.mark.parametrize("all_forward", [True, False])
+def test_single_direction_batches_under_emulation(emu, all_forward):
+    """Dynamics.forward only / Dynamics.backward only (utils/dynamics.py:246-300): every chain in one direction."""
+    P = U.Problem(regime="stress", kind="gaussian", D=4, H=6, T=3, eps=0.1)
+    rng = np.random.default_rng(21)
+    n = 11
+    x = P.x0(n, rng)
+    d = np.full(n, 1 if all_forward else 0, np.uint8)
+    v = rng.standard_normal((n, P.D)).astype(np.float32)
+    r = {"direction": torch.as_tensor(d.astype(np.float64)), "v_f": torch.as_tensor(v).double(), "v_b": torch.as_tensor(v).double()}
+    dyn = P.oracle(torch.float64)
+    with torch.no_grad():
+        acc = R._Acc(dyn)
+        loss_o = R.loss_and_grads(torch.as_tensor(x).double(), dyn, r, 0.1, acc)
+    loss, d_eps, gx, gv, _, _ = run_emu(emu, P, x, v, d, 0.1, 1.0 / n)
+    assert loss == pytest.approx(float(loss_o), rel=2e-4)
+    for got, ref in ((gx, acc.x), (gv, acc.v)):
+        for k in NAMES:
+            a, b = got[k].astype(np.float64), ref[ORACLE_KEY[k]].numpy().reshape(got[k].shape)
+            assert np.abs(a - b).max() <= 2e-4 * max(1e-12, np.abs(b).max()), k

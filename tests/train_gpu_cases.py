@@ -62,7 +62,7 @@ def test_loss_grad_matches_the_hand_written_reverse_pass(name, n, tol):
     # the forward sweep is the sampling transition: same Lx / px as propose with the same direction and momentum
     Lx2, _, px2, _ = propose(torch.as_tensor(x, device=DEV), dyn, rng=rng)
     assert U.max_rel(Lx.cpu().numpy(), Lx2.cpu().numpy()) < 2e-5
-    assert float((px - px2).abs().max()) < 5e-5
+    assert float((px - px2).abs().max()) < 2e-4   # two fp32 evaluations of H0 - H1 + log|J| (O(100) at 50 dimensions)
 
 
 def test_temperature_enters_the_gradient():
