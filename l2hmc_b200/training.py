@@ -112,6 +112,24 @@ def notebook_loss_and_grads(dynamics, x, z, *, rng_x=None, rng_z=None, scale=0.1
     return acc["loss"], acc, Lx, px
 
 
+def allreduce_grads(grads, group=None):
+    """Data-parallel training (SURVEY section 8e applied to the training path): chains are sharded over the ranks, every
+    rank accumulates its shard with ``count`` = the GLOBAL number of chains, and this sums loss and gradients over the
+    ranks in ONE all-reduce of the flattened vector (NCCL over NVLink / NVSwitch on GPUs; about 72 k floats for config 2,
+    so latency- not bandwidth-bound).  The exchange the reference never had to make: it trains on one device."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return grads
+    tensors = [grads["loss"], grads["eps"]] + [grads[key][k] for key in ("XNet", "VNet") for k in NAMES]
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    o = 0
+    for t in tensors:
+        t.copy_(flat[o:o + t.numel()].reshape(t.shape))
+        o += t.numel()
+    return grads   # derive grads["alpha"] = grads["eps"] * eps after the reduction
+
+
 class Adam(object):
     """tf.train.AdamOptimizer(learning_rate) with the notebook's schedule
     tf.train.exponential_decay(1e-3, global_step, 1000, 0.96, staircase=True) (SCGExperiment.ipynb:183-186);

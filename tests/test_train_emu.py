@@ -37,8 +37,8 @@ def vptr(a):
     return a.ctypes.data
 
 
-@pytest.fixture(scope="module")
-def emu():
+def build_emu():
+    """Compile (if stale) and load the host build of the training kernels; also used by tests/test_distributed_cpu.py."""
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
     deps = [SRC] + [os.path.join(HERE, "..", "l2hmc_b200", "csrc", f) for f in ("train.cuh", "train_host.cuh")] + \
            [os.path.join(HERE, "..", "include", "l2hmc.h")]
@@ -48,6 +48,11 @@ def emu():
     lib = C.CDLL(OUT)
     lib.emu_loss_grad.restype = C.c_int
     return lib
+
+
+@pytest.fixture(scope="module")
+def emu():
+    return build_emu()
 
 
 def fptr(a):
