@@ -202,3 +202,18 @@ def test_training_adam_is_tensorflow_adam_with_the_notebook_schedule():
     assert np.log(dyn.eps) == pytest.approx(float(ref_alpha.detach()[0]), abs=2e-6)
     # the layer objects hold the new weights (what a checkpoint of the nets would save)
     assert np.allclose(np.asarray(dyn.XNet.layers[3].W), np.asarray(dyn._net_params[0]["W4"]))
+
+
+def test_losses_module_is_utils_losses():
+    """l2hmc_b200.losses (utils/losses.py:26-59, values) against the oracle's restatement, and get_loss's table."""
+    from l2hmc_b200 import losses
+    rng = np.random.default_rng(1)
+    x, X = torch.as_tensor(rng.standard_normal((9, 3))), torch.as_tensor(rng.standard_normal((9, 3)))
+    p = torch.as_tensor(rng.random(9))
+    assert torch.equal(losses.loss_vec(x, X, p), U.O.loss_vec(x, X, p))
+    for name, ref in (("mixed", lambda: U.O.loss_mixed(x, X, p, 1.0)), ("standard", lambda: U.O.loss_std(x, X, p)),
+                      ("inverse", lambda: U.O.loss_inverse(x, X, p)), ("logsumexp", lambda: U.O.loss_logsumexp(x, X, p))):
+        assert float(losses.get_loss(name)(x, X, p)) == pytest.approx(float(ref()), rel=1e-12)
+    assert float(losses.loss_mixed(x, X, p, scale=0.1)) == pytest.approx(float(U.O.loss_mixed(x, X, p, 0.1)), rel=1e-12)
+    with pytest.raises(KeyError):
+        losses.get_loss("nope")

@@ -151,3 +151,16 @@ def test_library_losses_match_the_hand_written_reverse_pass(kind):
         loss_o = R.loss_and_grads(torch.as_tensor(x).double(), odyn, r, 0.1, acc, kind=kind)
     assert float(loss[0]) == pytest.approx(float(loss_o), rel=1e-3)
     assert _worst(grads, acc) < 1e-3
+
+
+def test_loss_value_agrees_with_the_losses_module():
+    """The value l2hmc_loss_grad returns is utils/losses.py's on the proposals it returns."""
+    from l2hmc_b200 import losses
+    P, x, d, v = _setup("c1_scg2", 300)
+    dyn = P.product()
+    xt = torch.as_tensor(x, device=DEV)
+    rng = {"direction": torch.as_tensor(d, device=DEV), "v": torch.as_tensor(v, device=DEV)}
+    for name in ("mixed", "standard", "inverse", "logsumexp"):
+        loss, _, Lx, px = training.loss_and_grads(dyn, xt, rng=rng, scale=0.1, loss=name)
+        ref = losses.loss_mixed(xt, Lx, px, scale=0.1) if name == "mixed" else losses.get_loss(name)(xt, Lx, px)
+        assert float(loss[0]) == pytest.approx(float(ref), rel=1e-4), name
