@@ -45,7 +45,13 @@ static dim3 blockDim, gridDim;
 typedef int cudaError_t;
 typedef void *cudaStream_t;
 enum { cudaSuccess = 0, cudaMemcpyDeviceToDevice = 3 };
-static inline cudaError_t cudaMalloc(void **p, size_t bytes) { return (*p = malloc(bytes)) ? 0 : 2; }
+// fresh device memory is filled with NaNs here, so a kernel that reads scratch it has not written shows up in the results
+static inline cudaError_t cudaMalloc(void **p, size_t bytes) {
+  *p = malloc(bytes);
+  if (!*p) return 2;
+  memset(*p, 0xFF, bytes);
+  return 0;
+}
 static inline cudaError_t cudaFree(void *p) { free(p); return 0; }
 static inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, int, cudaStream_t) { memcpy(d, s, n); return 0; }
 static inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t) { memset(d, v, n); return 0; }
