@@ -153,7 +153,11 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
       {&tape_x, nD * 4 * T}, {&tape_v, nD * 4 * T}, {&x, nD}, {&v, nD}, {&gU, nD}, {&ab, 2 * nD}, {&h1, nH}, {&h2, nH},
       {&gh1, nH}, {&gh2, nH}, {&hd, 3 * nD}, {&ghd, 3 * nD}, {&sc, 2 * nD}, {&gab, 2 * nD}, {&gx, nD}, {&gv, nD}, {&gg, nD},
       {&vec, (size_t)n * 10 + 4}};
+#ifndef L2HMC_TRAIN_EMU
   auto pad = [](size_t k) { return (k + 63) / 64 * 64; };
+#else  // host emulation: a 64-float guard zone (NaN-filled by the emulated cudaMalloc) after each sub-buffer, checked at the end
+  auto pad = [](size_t k) { return (k + 63) / 64 * 64 + 64; };
+#endif
   size_t total = 0;
   for (auto &r : req) total += pad(r.n);
   float *base = nullptr;
@@ -223,6 +227,13 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
     }
   }
   if ((rc = tr_colsum(ctx, s, geps, 1, n, 1, nullptr, a->d_eps))) return rc;
+#ifdef L2HMC_TRAIN_EMU
+  for (auto &r : req) {
+    const uint32_t *guard = reinterpret_cast<const uint32_t *>(*r.p + (r.n + 63) / 64 * 64);
+    for (int i = 0; i < 64; ++i)
+      if (guard[i] != 0xFFFFFFFFu) return fail(ctx, L2HMC_ECUDA, "emulation: a kernel wrote past the end of a scratch buffer");
+  }
+#endif
   return L2HMC_OK;  // asynchronous on the stream, like l2hmc_transition
 }
 
