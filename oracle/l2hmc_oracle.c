@@ -4,9 +4,10 @@
  * oracle/l2hmc_oracle.py).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load it; the product (l2hmc_b200/) never does.
  *
- * PARITY UNPINNED: the reference (TF1 / Python 2, /root/reference) cannot run in this environment and
- * holds no golden vectors, tests or seeds.  This file and the torch oracle are
- * checked against each other and against the algebraic properties the reference's code implies.
+ * PARITY PINNED (round 2): tests/test_reference_pin.py checks this file (and the torch oracle) against vectors the
+ * UNMODIFIED reference sources produced when run on the eager TensorFlow stand-in oracle/tf_shim
+ * (tests/golden/make_ref_golden.py -> tests/golden/ref_*.npz).  The reference itself holds no golden vectors, tests or
+ * seeds.
  *
  * Follows: utils/dynamics.py:95-108,115-218,246-309; utils/sampler.py:28-55; utils/layers.py:29-37,81-95;
  * net wiring SCGExperiment.ipynb:51-77; energies utils/distributions.py:31-32,50-57,90-97,125-134,161-180.

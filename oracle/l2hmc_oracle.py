@@ -6,14 +6,17 @@ reference's hot path.  It is the checker: only ``tests/``,
 reference`` legs may import it.  Nothing under ``l2hmc_b200/`` imports it and the
 product path never falls back to it.
 
-PARITY UNPINNED: the reference (TF1 / Python 2, /root/reference) cannot run in
-this environment (no TensorFlow, no Python 2), holds no tests / golden vectors /
-fixtures and seeds none of its RNGs.  The oracle is
-therefore pinned only by (a) reading the reference line by line (citations
-below), (b) the algebraic properties the reference's code implies (exact
-inverse, log-det vs autograd Jacobian, HMC limit; tests/test_oracle.py) and (c)
-a second, independently written plain-C restatement (oracle/l2hmc_oracle.c)
-that must agree with it.
+PARITY PINNED TO THE REFERENCE'S OWN CODE (round 2): real TensorFlow 1.x / Python 2 are absent here, but the
+reference's hot-path files run UNMODIFIED on an eager torch-backed TensorFlow stand-in (oracle/tf_shim,
+oracle/ref_loader.py, oracle/ref_runner.py).  tests/golden/make_ref_golden.py runs them (float64 and float32) on
+injected parameters and randomness and commits the outputs (tests/golden/ref_*.npz, tests/golden/ref/*.npz);
+tests/test_reference_pin.py asserts this oracle reproduces every one of them -- propose on all BASELINE targets,
+each Dynamics method, chain_operator, the notebook's training objective with tf.gradients w.r.t. every variable,
+utils/losses.py, the numpy diagnostics, utils/ais.py, and mnist_vae.py's own decoder / energy / sampler-net text --
+to 1e-9 in fp64 (fp32 twin: bit-equal samples on most cases).  The reference itself holds no tests, golden vectors
+or seeds; further anchors: the algebraic properties its code implies (exact inverse, log-det
+vs autograd Jacobian, HMC limit; tests/test_oracle.py) and a second, independently written plain-C restatement
+(oracle/l2hmc_oracle.c).
 
 All randomness is injected (the reference draws v, direction bits and accept
 uniforms from unseeded TF RNGs: utils/dynamics.py:248,276, utils/sampler.py:34,54).
@@ -29,7 +32,9 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import numpy as np
 import torch
 
-TWO_PI = 2 * np.pi  # utils/dynamics.py:101 -- python float, cast to the tensor dtype on use
+# utils/dynamics.py:101 -- a python float meeting an fp32 tensor: TF1 makes it an fp32 constant.  The fp64 twin is the
+# fp32 graph in wider arithmetic, so it keeps the fp32-rounded value (as the reference run on oracle/tf_shim does).
+TWO_PI = float(np.float32(2 * np.pi))
 
 
 # --------------------------------------------------------------------------------------
@@ -198,7 +203,7 @@ class FunnelEnergy(Energy):
         s = torch.exp(v)
         sum_sq = (x[:, 1:] ** 2).sum(1)
         n = torch.tensor(float(x.shape[1] - 1), dtype=dt)
-        two_pi = torch.tensor(2.0 * np.pi, dtype=dt)
+        two_pi = torch.tensor(TWO_PI, dtype=dt)  # 2.0 * np.pi * s (utils/distributions.py:167): fp32 constant
         E = 0.5 * (log_p_v + sum_sq / s + n * torch.log(two_pi * s))
         s_min = torch.exp(torch.tensor(-self.clip, dtype=dt))
         s_max = torch.exp(torch.tensor(self.clip, dtype=dt))
@@ -656,9 +661,18 @@ def ais_estimate(e0: Energy, e1: Energy, anneal_steps: int, initial_x, *, step_s
 # restatement of the dynamics (the reference back-propagates through the unrolled tf.while_loop, including the
 # tf.gradients of the energy, i.e. second-order terms; grad() of every Energy here is a differentiable expression).
 # --------------------------------------------------------------------------------------
+def c32(value):
+    """A python float meeting an fp32 tensor becomes an fp32 constant in the reference's graph; the fp64 twin keeps that
+    rounded value (the fp32 graph in wider arithmetic -- what the reference run on oracle/tf_shim computes)."""
+    return float(np.float32(value))
+
+
+EPS_V = c32(1e-4)
+
+
 def loss_vec(x, X, p):
     """loss_vec (utils/losses.py:36-37): expected squared jump distance per chain, + 1e-4."""
-    return ((X - x) ** 2).sum(1) * p + 1e-4
+    return ((X - x) ** 2).sum(1) * p + EPS_V
 
 
 def loss_logsumexp(x, X, p):
@@ -668,7 +682,7 @@ def loss_logsumexp(x, X, p):
 
 def loss_inverse(x, X, p):
     v = loss_vec(x, X, p)
-    return -1.0 / (1.0 / (v + 1e-4)).mean()
+    return -1.0 / (1.0 / (v + EPS_V)).mean()
 
 
 def loss_std(x, X, p):
@@ -677,7 +691,7 @@ def loss_std(x, X, p):
 
 def loss_mixed(x, Lx, px, scale=1.0):
     """loss_mixed (utils/losses.py:53-59)."""
-    v1 = loss_vec(x, Lx, px) / scale
+    v1 = loss_vec(x, Lx, px) / c32(scale)
     return (1.0 / v1).mean() - v1.mean()
 
 
@@ -689,8 +703,9 @@ def notebook_loss(x, z, dyn: OracleDynamics, rx: dict, rz: dict, scale=0.1):
     z = z.to(dyn.dtype)
     Lx, _, px, _ = propose(x, dyn, direction=rx["direction"], v_f=rx["v_f"].to(dyn.dtype), v_b=rx["v_b"].to(dyn.dtype))
     Lz, _, pz, _ = propose(z, dyn, direction=rz["direction"], v_f=rz["v_f"].to(dyn.dtype), v_b=rz["v_b"].to(dyn.dtype))
-    v1 = ((x - Lx) ** 2).sum(1) * px + 1e-4
-    v2 = ((z - Lz) ** 2).sum(1) * pz + 1e-4
+    scale = c32(scale)
+    v1 = ((x - Lx) ** 2).sum(1) * px + EPS_V
+    v2 = ((z - Lz) ** 2).sum(1) * pz + EPS_V
     return scale * ((1.0 / v1).mean() + (1.0 / v2).mean()) + (-v1.mean() - v2.mean()) / scale
 
 

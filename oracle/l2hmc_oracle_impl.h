@@ -1,7 +1,7 @@
 /* Plain-C restatement of the L2HMC sampling path.  TEST INFRASTRUCTURE ONLY (see l2hmc_oracle.c).
  * Included twice by l2hmc_oracle.c: REAL = float (suffix _f32) and REAL = double (suffix _f64).
  * Scalar loops in natural index order; every function cites the reference lines it follows
- * (/root/reference).  PARITY UNPINNED: the reference has no golden vectors and cannot run here. */
+ * (/root/reference).  Pinned to vectors produced by the reference's own sources (tests/test_reference_pin.py). */
 
 #define CAT_(a, b) a##b
 #define CAT(a, b) CAT_(a, b)

@@ -1,7 +1,7 @@
 """Hand-derived reverse mode through the L2HMC transition and the notebook training objective.
 
-TEST INFRASTRUCTURE, like everything under oracle/: imported only by tests/ (parity unpinned -- the reference ships
-no tests, see l2hmc_oracle.py).  This file is the algorithm statement for SURVEY section 8(f)3, the training path:
+TEST INFRASTRUCTURE, like everything under oracle/: imported only by tests/ (pinned: tests/test_reference_pin.py checks it against
+tf.gradients of the reference's own loss cell run on oracle/tf_shim).  This file is the algorithm statement for SURVEY section 8(f)3, the training path:
 the reference obtains its parameter gradients from TF1 autodiff through the unrolled ``tf.while_loop`` of
 ``Dynamics.forward / backward`` (utils/dynamics.py:246-300), through ``tf.gradients`` of the energy inside it (:217-218,
 i.e. Hessian-vector products on the way back), ``p_accept`` (:302-309), ``propose`` (utils/sampler.py:28-51) and the
@@ -285,13 +285,14 @@ LOSS_KINDS = ("mixed", "standard", "inverse", "logsumexp")   # get_loss names, u
 def loss_value_and_dv(v, kind: str, scale: float, count: float):
     """Loss of utils/losses.py:36-59 as a function of v = loss_vec(x, Lx, px) [n], and d loss / d v, by hand.
     ``count``: the number of chains the means run over (the batch, unless the caller splits one)."""
+    scale = O.c32(scale)
     if kind == "mixed":      # scale mean(1/v) - mean(v)/scale   (:53-59; SCGExperiment.ipynb:171-181)
         return (scale / v).sum() / count - v.sum() / (count * scale), (-scale / (v * v) - 1.0 / scale) / count
     if kind == "standard":   # -mean(v)   (:49-51)
         return -v.sum() / count, torch.full_like(v, -1.0 / count)
-    if kind == "inverse":    # -1 / mean(1 / (v + 1e-4))   (:44-47)
-        m = (1.0 / (v + 1e-4)).sum() / count
-        return -1.0 / m, -1.0 / (m * m * (v + 1e-4) ** 2 * count)
+    if kind == "inverse":    # -1 / mean(1 / (v + O.EPS_V))   (:44-47)
+        m = (1.0 / (v + O.EPS_V)).sum() / count
+        return -1.0 / m, -1.0 / (m * m * (v + O.EPS_V) ** 2 * count)
     if kind == "logsumexp":  # logsumexp(-v) - log n   (:39-42)
         mx = (-v).max()
         z = torch.exp(-v - mx).sum()
@@ -318,7 +319,7 @@ def loss_and_grads(x, dyn: O.OracleDynamics, r: dict, scale: float, acc: _Acc, k
         zero = torch.zeros(xs.shape[0], dtype=dyn.dtype)
         p, _, _, _ = accept_prob_vjp(dyn, xs, vs, X, V, lj, zero)
         sq = ((xs - X) ** 2).sum(1)
-        v_all[sel] = sq * p + 1e-4
+        v_all[sel] = sq * p + O.EPS_V
         groups.append((sel, fwd, xs, vs, X, V, lj, tape, p, sq))
     total, g_v_all = loss_value_and_dv(v_all, kind, scale, count)
     for sel, fwd, xs, vs, X, V, lj, tape, p, sq in groups:

@@ -288,7 +288,8 @@ def test_golden_fixtures():
     """Committed fp64-oracle vectors (tests/golden/make_golden.py) reproduced by the CUDA path."""
     import glob
     import os
-    files = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+    files = sorted(f for f in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                   if not os.path.basename(f).startswith("ref_"))  # ref_*: test_reference_pin.py / test_gpu_reference_pin.py
     assert files, "no golden fixtures committed"
     import golden_io
     for f in files:

@@ -221,6 +221,18 @@ class VaeProblem:
         }
 
 
+def vae_weight_checksum(P):
+    """The reference-pinned VAE fixture at mnist_vae.py's layer sizes (tests/golden/ref/c5_vae_full_n32.npz) does not
+    store its 2.9 M weights: VaeProblem regenerates them from its seed; this checksum proves the regenerated weights
+    are the ones the fixture was made with."""
+    tot = 0.0
+    for a in list(P.dec_W) + list(P.dec_b) + (list(P.enc_W) + list(P.enc_b) if P.use_encoder else []) + \
+            [P.xnet[k] for k in sorted(P.xnet)] + [P.vnet[k] for k in sorted(P.vnet)]:
+        a = np.asarray(a, dtype=np.float64)
+        tot += float(np.abs(a).sum()) + 3.0 * float(a.reshape(-1)[:: max(1, a.size // 7)].sum())
+    return tot
+
+
 VAE_CONFIGS = {
     "c5_vae_mini": dict(D=8, H=24, T=4, dec=(64, 64), aux_dim=40, enc=(32, 32)),
     "c5_vae_ragged": dict(D=7, H=21, T=3, dec=(33,), aux_dim=19, enc=(10,)),   # nothing a multiple of 8
