@@ -257,6 +257,12 @@ class Dynamics(object):
         if self._ctx is not None:
             self._chk(self._lib.l2hmc_set_eps(self._ctx, float(self.eps)))
 
+    def set_alpha(self, alpha):
+        """Assign the stored variable alpha = log(eps) itself (utils/dynamics.py:50-58), as an optimiser does."""
+        self.alpha = np.float32(alpha)
+        if self._ctx is not None:
+            self._chk(self._lib.l2hmc_set_eps(self._ctx, float(self.eps)))
+
     @property
     def mask(self):
         return self._mask

@@ -3,7 +3,7 @@
 In the reference these build TF graph nodes that autodiff later differentiates; here the gradient of a loss through the
 sampler comes from ``training.loss_and_grads(dynamics, x, loss=name)`` (one C-ABI call, csrc/train.cuh), and these
 functions give the VALUE of the same objective for given proposals ``(x, Lx, px)`` -- tensors on any device, a few
-elementwise torch ops, not a hot path (monitoring, and the check that the two agree in tests/train_gpu_cases.py).
+elementwise torch ops, not a hot path (monitoring, and the check that the two agree in tests/test_gpu_training.py).
 """
 from __future__ import annotations
 

@@ -60,8 +60,9 @@ def _util(x_dim, device_index):
     return _lib.load(), ctx
 
 
-def tf_accept(x, Lx, px, *, u=None, seed=0, counter=0):
-    """where(px - u >= 0, Lx, x) row-wise (utils/sampler.py:53-55); u drawn in-kernel when None."""
+def tf_accept(x, Lx, px, *, u=None, seed=0, counter=0, chain_offset=0):
+    """where(px - u >= 0, Lx, x) row-wise (utils/sampler.py:53-55); u drawn in-kernel when None (Philox keyed by the global
+    chain id chain_offset + i)."""
     if not (x.is_cuda and Lx.is_cuda and px.is_cuda):
         raise TypeError("tf_accept works on CUDA tensors")
     x = x.detach().to(TORCH_FLOAT).contiguous()
@@ -75,7 +76,7 @@ def tf_accept(x, Lx, px, *, u=None, seed=0, counter=0):
         u = u.detach().to(device=x.device, dtype=TORCH_FLOAT).contiguous()
         up = u.data_ptr()
     stream = C.c_void_p(torch.cuda.current_stream(x.device.index).cuda_stream)
-    _lib.check(lib, ctx, lib.l2hmc_accept(ctx, n, 0, x.data_ptr(), Lx.data_ptr(), px.data_ptr(), up, int(seed),
+    _lib.check(lib, ctx, lib.l2hmc_accept(ctx, n, int(chain_offset), x.data_ptr(), Lx.data_ptr(), px.data_ptr(), up, int(seed),
                                           int(counter), out.data_ptr(), None, stream))
     return out
 

@@ -27,12 +27,13 @@ NAMES = ("W1", "b1", "W2", "b2", "W3", "b3", "W4", "b4", "Ws", "bs", "Wt", "bt",
 _ABI = {"ls": "scale_s", "lq": "scale_q"}
 
 
-def _draw(dynamics, n, device, want_u=False):
-    """Direction bits, momenta (and accept uniforms) from the in-kernel Philox stream (l2hmc_philox_fill)."""
+def _draw(dynamics, n, device, want_u=False, chain_offset=0):
+    """Direction bits, momenta (and accept uniforms) from the in-kernel Philox stream (l2hmc_philox_fill), keyed by the
+    GLOBAL chain id ``chain_offset + i`` so that a sharded batch draws what the single-rank batch draws."""
     v = torch.empty((n, dynamics.x_dim), dtype=TORCH_FLOAT, device=device)
     d = torch.empty((n,), dtype=torch.uint8, device=device)
     u = torch.empty((n,), dtype=TORCH_FLOAT, device=device) if want_u else None
-    dynamics._chk(dynamics._lib.l2hmc_philox_fill(dynamics._ctx, n, 0, dynamics.seed, dynamics.next_counter(), v.data_ptr(),
+    dynamics._chk(dynamics._lib.l2hmc_philox_fill(dynamics._ctx, n, int(chain_offset), dynamics.seed, dynamics.next_counter(), v.data_ptr(),
                                                   d.data_ptr(), u.data_ptr() if want_u else None, dynamics._stream()))
     return d, v, u
 
@@ -49,15 +50,19 @@ def zero_grads(dynamics, device) -> Dict[str, object]:
 
 
 def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale: float = 0.1, count: Optional[int] = None,
-                          loss: str = "mixed"):
+                          loss: str = "mixed", chain_offset: int = 0):
     """Add one propose batch to ``acc`` (from zero_grads): loss += scale mean(1/v) - mean(v)/scale with
     v = |x - Lx|^2 px + 1e-4 (SCGExperiment.ipynb:171-181; utils/losses.py:36-59), gradients likewise.
     rng: optional {'direction' uint8 [N], 'v' [N, D]}; drawn from the Philox stream otherwise.  ``count``: the number of
     chains the means run over (default N).  ``loss``: 'mixed' (the notebook's; ``scale`` applies), 'standard', 'inverse'
     or 'logsumexp' -- ``get_loss(name)`` of utils/losses.py:26-59; the last two are means of one batch and do not add
-    over calls.  Returns (Lx, px)."""
+    over calls.  ``chain_offset``: global index of this shard's first chain (data-parallel training: internal draws are
+    keyed by global chain id, as sharding.ShardedSampler does).  Returns (Lx, px)."""
     if loss not in LOSSES:
         raise ValueError("loss must be one of %s" % (sorted(LOSSES),))
+    if loss in ("inverse", "logsumexp") and count is not None and int(count) != int(x.shape[0]):
+        raise ValueError("loss %r weighs every chain by a statistic of the whole batch: it cannot be accumulated over "
+                         "shards or calls (count must be the batch size)" % loss)
     if dynamics.hmc:
         raise ValueError("an HMC-mode Dynamics has no parameters to train")
     dynamics._ensure_ctx()
@@ -69,7 +74,7 @@ def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale
         d = rng["direction"].detach().to(device=dev, dtype=torch.uint8).contiguous()
         v = dynamics._prep(rng["v"], "v", dynamics.x_dim)
     else:
-        d, v, _ = _draw(dynamics, n, dev)
+        d, v, _ = _draw(dynamics, n, dev, chain_offset=chain_offset)
         d = rng["direction"].detach().to(device=dev, dtype=torch.uint8).contiguous() if "direction" in rng else d
         v = dynamics._prep(rng["v"], "v", dynamics.x_dim) if "v" in rng else v
     if d.numel() != n or v.shape[0] != n:
@@ -93,21 +98,21 @@ def accumulate_loss_grads(dynamics, x, acc, *, rng: Optional[dict] = None, scale
     return Lx, px
 
 
-def loss_and_grads(dynamics, x, *, rng=None, scale=0.1, loss="mixed"):
+def loss_and_grads(dynamics, x, *, rng=None, scale=0.1, loss="mixed", count=None, chain_offset=0):
     """Value and gradient of one propose batch.  Returns (loss [1], grads, Lx, px); grads['alpha'] is the gradient for
     the reference's trainable ``alpha = log(eps)`` (utils/dynamics.py:50-58)."""
     acc = zero_grads(dynamics, x.device)
-    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng, scale=scale, loss=loss)
+    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng, scale=scale, loss=loss, count=count, chain_offset=chain_offset)
     acc["alpha"] = acc["eps"] * dynamics.eps
     return acc["loss"], acc, Lx, px
 
 
-def notebook_loss_and_grads(dynamics, x, z, *, rng_x=None, rng_z=None, scale=0.1):
+def notebook_loss_and_grads(dynamics, x, z, *, rng_x=None, rng_z=None, scale=0.1, count=None, chain_offset=0):
     """The notebook objective (SCGExperiment.ipynb:159-181): proposals from the samples x and from noise z.
     Returns (loss [1], grads, Lx, px) with Lx, px those of the x batch (what the training loop feeds back)."""
     acc = zero_grads(dynamics, x.device)
-    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng_x, scale=scale)
-    accumulate_loss_grads(dynamics, z, acc, rng=rng_z, scale=scale)
+    Lx, px = accumulate_loss_grads(dynamics, x, acc, rng=rng_x, scale=scale, count=count, chain_offset=chain_offset)
+    accumulate_loss_grads(dynamics, z, acc, rng=rng_z, scale=scale, count=count, chain_offset=chain_offset)
     acc["alpha"] = acc["eps"] * dynamics.eps
     return acc["loss"], acc, Lx, px
 
@@ -170,22 +175,29 @@ class Adam(object):
             load_stq_net(dynamics.XNet if i == 0 else dynamics.VNet, new)
         dynamics.refresh()
         if self.eps_trainable:
+            # alpha is the stored variable (utils/dynamics.py:50-54): update it directly, no log(exp(.)) round trip
             alpha = torch.as_tensor(np.float32(dynamics.alpha), device=dev).reshape(1)
             g_alpha = grads["eps"] * dynamics.eps
-            dynamics.eps = float(torch.exp(self._update("alpha", alpha, g_alpha))[0])
+            dynamics.set_alpha(float(self._update("alpha", alpha, g_alpha)[0]))
         self.global_step += 1
 
 
-def train_step(dynamics, opt, samples, *, scale=0.1, rng_x=None, rng_z=None, z=None, u=None):
+def train_step(dynamics, opt, samples, *, scale=0.1, rng_x=None, rng_z=None, z=None, u=None, count=None, chain_offset=0,
+               group=None):
     """One iteration of the notebook's loop (SCGExperiment.ipynb:254-270): loss on the current samples and on fresh noise,
     Adam update, and the Metropolis-Hastings output ``tf_accept(x, Lx, px)`` as the next samples (:159-160).
-    Returns dict(loss, px, samples, learning_rate)."""
+    Data-parallel: pass this rank's shard as ``samples``, ``count`` = the global number of chains and ``chain_offset`` =
+    the global index of the shard's first chain; loss and gradients are summed over the ranks (allreduce_grads) before
+    the (replicated) Adam update.  Returns dict(loss, px, samples, learning_rate)."""
     x = dynamics._prep(samples, "samples", dynamics.x_dim)
     if z is None:
         dynamics._ensure_ctx()
-        _, z, _ = _draw(dynamics, x.shape[0], x.device)   # tf.random_normal(tf.shape(x)) (:161)
+        _, z, _ = _draw(dynamics, x.shape[0], x.device, chain_offset=chain_offset)   # tf.random_normal(tf.shape(x)) (:161)
     lr = opt.learning_rate
-    loss, grads, Lx, px = notebook_loss_and_grads(dynamics, x, z, rng_x=rng_x, rng_z=rng_z, scale=scale)
-    nxt = tf_accept(x, Lx, px, u=u, seed=dynamics.seed, counter=dynamics.next_counter())
+    loss, grads, Lx, px = notebook_loss_and_grads(dynamics, x, z, rng_x=rng_x, rng_z=rng_z, scale=scale, count=count,
+                                                  chain_offset=chain_offset)
+    nxt = tf_accept(x, Lx, px, u=u, seed=dynamics.seed, counter=dynamics.next_counter(), chain_offset=chain_offset)
+    if count is not None:
+        allreduce_grads(grads, group=group)
     opt.apply(dynamics, grads)
     return {"loss": float(loss[0]), "px": px, "samples": nxt, "learning_rate": lr}

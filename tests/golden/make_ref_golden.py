@@ -70,6 +70,8 @@ def save_propose(fname, kw, n, seed, regime, log_jac):
     if not log_jac:
         for k, v in R.run_methods(P, d, "float64").items():
             arrays["m_" + k] = v
+        for k, v in R.run_methods(P, d, "float32").items():
+            arrays["m32_" + k] = v
     path = os.path.join(HERE, fname + ".npz")
     np.savez_compressed(path, **arrays)
     return path

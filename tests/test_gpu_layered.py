@@ -4,10 +4,9 @@ Covers BASELINE config 5 (the MNIST-VAE posterior target: decoder energy + aux-c
 mnist_vae.py:104-178) at the reference's layer sizes and in miniature / ragged shapes, and the same engine on the
 closed-form targets (where it must agree with the fused kernels' oracle too).
 
-Tolerances: as tests/test_gpu_parity.py -- samples within 2e-5 relative (or 4x the fp32 oracle's own error),
-accept probabilities within 5e-5 per chain (or 4x the fp32 oracle's own error: at the full layer sizes the energy is
-a sum over 784 pixels of O(500), so fp32 Hamiltonian differences carry ~1e-4 of noise in either implementation),
-their mean within 1e-5 (or 2x the fp32 oracle's).
+Tolerances: as tests/test_gpu_parity.py -- samples within O32 + 1e-5, per-chain accept probability within 4 * O32 + 1e-5 (O32: the fp32 oracle twin's own error on the
+same inputs; at the full layer sizes the energy is a sum over 784 pixels of O(500), so fp32 Hamiltonian differences
+carry ~1e-4 of noise in either implementation), the mean accept probability within 1e-5 (or the fp32 twin's own).
 """
 import numpy as np
 import pytest
@@ -20,13 +19,23 @@ pytestmark = pytest.mark.gpu
 SAMPLE_TOL = 2e-5
 P_TOL = 5e-5
 P_MEAN_TOL = 1e-5
+NORTH_STAR_TOL = 1e-5
 
 
 def _check(rep):
-    assert rep["Lx_kernel"] <= max(SAMPLE_TOL, 4 * rep["Lx_o32"]), rep
-    assert rep["Lv_kernel"] <= max(SAMPLE_TOL, 4 * rep["Lv_o32"]), rep
-    assert rep["px_kernel"] <= max(P_TOL, 4 * rep["px_o32"]), rep
-    assert rep["px_mean_kernel"] <= max(P_MEAN_TOL, 2 * rep["px_mean_o32"]), rep
+    """north_star: within 1e-5 of the reference on identical seeds.  O32 = the error of the fp32 twin of the
+    (reference-pinned) oracle against its fp64 twin on the same inputs, i.e. the rounding noise the fp32 path carries
+    whatever the implementation:
+      * samples: within O32 + 1e-5;
+      * mean accept probability: within 1e-5, flat (or O32's own mean error where that is larger: chaotic targets);
+      * per-chain accept probability: within 4 * O32 + 1e-5.  It is the MAXIMUM over a few hundred chains of a
+        cancellation error (Hamiltonians of O(100) subtracted in fp32); two evaluation orders of the same arithmetic
+        (Eigen, torch, the kernels) differ by up to ~4x in that maximum while agreeing to 1e-6 in the mean
+        (profiles/r02_parity_noise.txt lists kernel vs O32 for every configuration and engine)."""
+    assert rep["Lx_kernel"] <= rep["Lx_o32"] + NORTH_STAR_TOL, rep
+    assert rep["Lv_kernel"] <= rep["Lv_o32"] + NORTH_STAR_TOL, rep
+    assert rep["px_kernel"] <= 4 * rep["px_o32"] + NORTH_STAR_TOL, rep
+    assert rep["px_mean_kernel"] <= max(NORTH_STAR_TOL, rep["px_mean_o32"]), rep
     assert rep["accept_flips_outside_noise"] == 0, rep
 
 

@@ -1,12 +1,14 @@
 """GPU parity: the CUDA path (through the Python mirror -> ctypes -> C ABI) against the CPU oracle.
 
-Tolerances (written here, per the task statement):
-  * samples Lx, Lv: max|kernel - fp64 oracle| / max(1, max|ref|) <= 2e-5, or 4x the error the fp32
-    oracle itself makes against the fp64 oracle on the same inputs, whichever is larger (the reference's
-    own fp32 path is only defined up to summation order; SURVEY.md section 4 measured 2e-7..2e-5);
-  * accept probability: mean over chains within 1e-5 of the fp64 oracle (BASELINE.json "accept-prob
-    delta"); per chain within max(5e-5, 4x the fp32 oracle's own error);
+Tolerances (written here, per the task statement; north_star: "within 1e-5 relative fp32 tolerance"):
+  * per chain -- samples Lx, Lv as max|kernel - fp64 oracle| / max(1, max|ref|), accept probability absolute:
+    samples within O32 + 1e-5, accept probability within 4 * O32 + 1e-5 (see _check), O32 being the error the fp32
+    twin of the reference-pinned oracle makes against its fp64 twin on the same inputs (the fp32 path is only defined
+    up to summation order);
+  * mean accept probability over chains within 1e-5 of the fp64 oracle (BASELINE.json "accept-prob delta");
   * Metropolis decisions identical except where |p - u| is inside that noise (<= 1e-4).
+Tests of derived properties (round trips, sub-sampled full-size runs, fused multi-transition chains) state their own,
+wider figures next to the assertion.
 """
 import numpy as np
 import pytest
@@ -19,13 +21,23 @@ pytestmark = pytest.mark.gpu
 SAMPLE_TOL = 2e-5
 P_TOL = 5e-5
 P_MEAN_TOL = 1e-5
+NORTH_STAR_TOL = 1e-5
 
 
 def _check(rep):
-    assert rep["Lx_kernel"] <= max(SAMPLE_TOL, 4 * rep["Lx_o32"]), rep
-    assert rep["Lv_kernel"] <= max(SAMPLE_TOL, 4 * rep["Lv_o32"]), rep
-    assert rep["px_kernel"] <= max(P_TOL, 4 * rep["px_o32"]), rep
-    assert rep["px_mean_kernel"] <= max(P_MEAN_TOL, 2 * rep["px_mean_o32"]), rep
+    """north_star: within 1e-5 of the reference on identical seeds.  O32 = the error of the fp32 twin of the
+    (reference-pinned) oracle against its fp64 twin on the same inputs, i.e. the rounding noise the fp32 path carries
+    whatever the implementation:
+      * samples: within O32 + 1e-5;
+      * mean accept probability: within 1e-5, flat (or O32's own mean error where that is larger: chaotic targets);
+      * per-chain accept probability: within 4 * O32 + 1e-5.  It is the MAXIMUM over a few hundred chains of a
+        cancellation error (Hamiltonians of O(100) subtracted in fp32); two evaluation orders of the same arithmetic
+        (Eigen, torch, the kernels) differ by up to ~4x in that maximum while agreeing to 1e-6 in the mean
+        (profiles/r02_parity_noise.txt lists kernel vs O32 for every configuration and engine)."""
+    assert rep["Lx_kernel"] <= rep["Lx_o32"] + NORTH_STAR_TOL, rep
+    assert rep["Lv_kernel"] <= rep["Lv_o32"] + NORTH_STAR_TOL, rep
+    assert rep["px_kernel"] <= 4 * rep["px_o32"] + NORTH_STAR_TOL, rep
+    assert rep["px_mean_kernel"] <= max(NORTH_STAR_TOL, rep["px_mean_o32"]), rep
     assert rep["accept_flips_outside_noise"] == 0, rep
 
 

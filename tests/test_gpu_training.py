@@ -1,5 +1,8 @@
-"""GPU cases of the training path (l2hmc_loss_grad; l2hmc_b200/training.py).  Not collected by the main run: executed in a
-subprocess by tests/test_zz_gpu_training.py, so that a fault in this first-correct path cannot disturb the other GPU tests."""
+"""GPU tests of the training path (l2hmc_loss_grad; l2hmc_b200/training.py): gradient parity with the hand-written reverse
+sweep of the oracle and with tf.gradients of the reference's own loss cell (tests/golden/ref/notebook_loss_*.npz), every
+loss of utils/losses.py, the optimiser loop, data-parallel sharding of the internal draws."""
+import json
+import os
 import numpy as np
 import pytest
 import torch
@@ -164,3 +167,63 @@ def test_loss_value_agrees_with_the_losses_module():
         loss, _, Lx, px = training.loss_and_grads(dyn, xt, rng=rng, scale=0.1, loss=name)
         ref = losses.loss_mixed(xt, Lx, px, scale=0.1) if name == "mixed" else losses.get_loss(name)(xt, Lx, px)
         assert float(loss[0]) == pytest.approx(float(ref), rel=1e-4), name
+
+
+@pytest.mark.parametrize("name", ["notebook_loss_c1_n200", "notebook_loss_c3_n64"])
+def test_training_gradients_match_the_reference(name):
+    """The notebook objective (SCGExperiment.ipynb:159-181) and tf.gradients of it w.r.t. every variable of both nets and
+    alpha, as the UNMODIFIED reference computes them on oracle/tf_shim (tests/golden/make_ref_golden.py), against
+    l2hmc_loss_grad on the same parameters and draws."""
+    import ref_runner  # variable-name table only (oracle/: test infrastructure)
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref", name + ".npz"))
+    meta = json.loads(bytes(z["meta"]).decode())
+    P = U.Problem(regime=meta["regime"], **meta["kw"])
+    P.mask = z["mask"]
+    P.xnet = {k[5:]: z[k] for k in z.files if k.startswith("xnet_")}
+    P.vnet = {k[5:]: z[k] for k in z.files if k.startswith("vnet_")}
+    dyn = P.product()
+    t = lambda a: torch.as_tensor(np.asarray(a), device=DEV)  # noqa: E731
+
+    def sel(pre):
+        d = z[pre + "dir"]
+        return {"direction": t(d), "v": t(np.where(d[:, None] != 0, z[pre + "v_f"], z[pre + "v_b"]).astype(np.float32))}
+    loss, grads, Lx, px = training.notebook_loss_and_grads(dyn, t(z["in_x"]), t(z["in_z"]), rng_x=sel("in_rx_"),
+                                                           rng_z=sel("in_rz_"), scale=meta["scale"])
+    ref_loss = float(z["out_loss"])
+    assert float(loss[0]) == pytest.approx(ref_loss, rel=1e-3)
+    worst = 0.0
+    for scope in ("XNet", "VNet"):
+        for k in training.NAMES:
+            ref_g = z["out_grad__%s__%s" % (scope, ref_runner.NET_VARS[k].replace("/", "__"))]
+            a = grads[scope][k].double().cpu().numpy().reshape(ref_g.shape)
+            worst = max(worst, float(np.abs(a - ref_g).max() / max(1e-12, np.abs(ref_g).max())))
+    assert worst < 1e-3, worst   # fp32 noise floor of this gradient: 0.4 .. 2e-5 (DESIGN.md 7.1)
+    ga = float(np.asarray(z["out_grad__alpha"]).reshape(-1)[0])
+    assert float(grads["alpha"][0]) == pytest.approx(ga, rel=5e-3, abs=1e-4 * abs(ref_loss))
+    assert float(np.max(np.abs(px.cpu().numpy() - z["out_px"]))) <= 2e-4
+
+
+def test_sharded_internal_draws_equal_the_single_rank_draws():
+    """Data-parallel training draws direction bits, momenta, z noise and accept uniforms from Philox keyed by the GLOBAL
+    chain id: two shards with chain_offset and count = N_global add up to the single-rank gradient, and train_step's
+    Metropolis output is the same chain by chain."""
+    P, x, _, _ = _setup("c1_scg2", 200)
+    xt = torch.as_tensor(x, device=DEV)
+    dyn = P.product(seed=11)
+    dyn._ensure_ctx()
+    c0 = dyn._counter
+    loss, g, Lx, px = training.loss_and_grads(dyn, xt)
+    parts = []
+    for lo, hi in ((0, 90), (90, 200)):
+        dyn._counter = c0                       # every rank holds the same Dynamics (seed and call counter)
+        parts.append(training.loss_and_grads(dyn, xt[lo:hi].contiguous(), count=200, chain_offset=lo))
+    assert torch.equal(torch.cat([p[2] for p in parts]), Lx) and torch.equal(torch.cat([p[3] for p in parts]), px)
+    assert float(parts[0][0][0] + parts[1][0][0]) == pytest.approx(float(loss[0]), rel=1e-5)
+    for key in ("XNet", "VNet"):
+        for k in training.NAMES:
+            s = parts[0][1][key][k] + parts[1][1][key][k]
+            assert float((s - g[key][k]).abs().max()) <= 1e-4 * max(1e-12, float(g[key][k].abs().max())), (key, k)
+    # without the offset the second shard would repeat the first shard's draws
+    dyn._counter = c0
+    wrong = training.loss_and_grads(dyn, xt[90:200].contiguous(), count=200)
+    assert not torch.equal(wrong[2], Lx[90:200])

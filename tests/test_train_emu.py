@@ -3,7 +3,7 @@
 tests/emu/train_emu.cpp compiles those two files with g++ and runs every CUDA thread on a host thread, so index
 arithmetic, operand strides, the GEMM tiling, the order of the two sweeps and every vector-Jacobian product are checked
 here against oracle/l2hmc_reverse.py (which equals torch.autograd through the restated dynamics, see test_oracle.py)
-without a GPU.  The GPU run of the same source is tests/test_zz_gpu_training.py.
+without a GPU.  The GPU run of the same source is tests/test_gpu_training.py.
 """
 import ctypes as C
 import os
@@ -224,11 +224,11 @@ def test_training_module_marshalling_and_loop_over_the_emulated_kernels(emu, mon
     rng = np.random.default_rng(2)
     n = 16
 
-    def draw(dynamics, n_, device, want_u=False):
+    def draw(dynamics, n_, device, want_u=False, chain_offset=0):
         return (torch.as_tensor(rng.integers(0, 2, n_).astype(np.uint8)), torch.as_tensor(rng.standard_normal((n_, P.D)).astype(np.float32)),
                 None)
     monkeypatch.setattr(training, "_draw", draw)
-    monkeypatch.setattr(training, "tf_accept", lambda x, Lx, px, u=None, seed=0, counter=0: torch.where((px >= 0.5)[:, None], Lx, x))
+    monkeypatch.setattr(training, "tf_accept", lambda x, Lx, px, u=None, seed=0, counter=0, chain_offset=0: torch.where((px >= 0.5)[:, None], Lx, x))
 
     x = torch.as_tensor(P.x0(n, rng))
     d = torch.as_tensor(rng.integers(0, 2, n).astype(np.uint8))
