@@ -124,6 +124,13 @@ typedef struct {
   void *stream;           /* cudaStream_t                                                        */
   const float *aux;       /* [n,aux_dim] conditioning rows (propose(..., aux=) utils/sampler.py:28; the
                              image batch `inp` of mnist_vae.py:196,204), or NULL when the target takes none */
+  double *stats;          /* [2] or NULL, ACCUMULATED (+=): stats[0] += sum of px_out values, stats[1] += number of
+                             accepted proposals, over every chain and every fused transition of the call -- the
+                             acceptance statistics the notebook prints from np.mean(px_) (SCGExperiment.ipynb:268),
+                             reduced inside the kernel (warp shuffle + one atomic pair per warp).  DEVICE pointer for
+                             l2hmc_transition, HOST pointer for l2hmc_transition_host.                            */
+  float *trace;           /* [n_transitions,n,D] or NULL: the Metropolis output after EVERY fused transition (the
+                             notebook's final_samples list, SCGExperiment.ipynb:291-298); needs do_mh; device only */
 } l2hmc_transition_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -198,6 +205,13 @@ int l2hmc_acl_spectrum(l2hmc_ctx *ctx, int64_t n_steps, int64_t n, const float *
                        double *out, void *stream);
 
 /* ---- introspection ------------------------------------------------------------------------- */
+/* Sticky status bits of the context, raised by its kernels in pinned host-mapped memory and read here WITHOUT a device
+ * synchronisation.  L2HMC_STATUS_F16_RANGE: a launch of the tensor-core kernel met an activation outside the fp16 range
+ * while using the fp16 operand split; the chains of that launch that were affected carry non-finite proposals (accept
+ * probability 0: rejected, x kept -- utils/dynamics.py:309), every later launch of the context uses the tf32 split, and
+ * l2hmc_transition_host repeats its call itself.  clear != 0 resets the word (and allows the fp16 split again). */
+#define L2HMC_STATUS_F16_RANGE 1u
+int l2hmc_status_flags(l2hmc_ctx *ctx, uint32_t *flags, int clear);
 /* ---- training path (first-correct version) -------------------------------------------------
  * Replaces, for one `propose` batch, what the reference obtains from TF1 autodiff: `tf.gradients(loss, params)` behind
  * `AdamOptimizer.minimize(loss)` (SCGExperiment.ipynb:183-188) with

@@ -106,7 +106,8 @@ class TransitionArgs(C.Structure):
                 ("dir_mode", C.c_int32), ("log_jac", C.c_int32), ("do_mh", C.c_int32), ("n_transitions", C.c_int32),
                 ("seed", C.c_uint64), ("counter", C.c_uint64),
                 ("x_out", C.c_void_p), ("v_out", C.c_void_p), ("px_out", C.c_void_p), ("x_next", C.c_void_p),
-                ("accepted", C.c_void_p), ("stream", C.c_void_p), ("aux", C.c_void_p)]
+                ("accepted", C.c_void_p), ("stream", C.c_void_p), ("aux", C.c_void_p),
+                ("stats", C.c_void_p), ("trace", C.c_void_p)]
 
 
 ENERGY_GAUSSIAN, ENERGY_GMM, ENERGY_ROUGHWELL, ENERGY_FUNNEL, ENERGY_DECODER = 0, 1, 2, 3, 4
@@ -147,7 +148,9 @@ EXPORTS = [
     ("l2hmc_timing_enable", C.c_int, [_vp, C.c_int]),
     ("l2hmc_timing_read", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(_i64)]),
     ("l2hmc_debug_counters", C.c_int, [_vp, C.POINTER(_i64), C.c_int]),
+    ("l2hmc_status_flags", C.c_int, [_vp, C.POINTER(C.c_uint32), C.c_int]),
 ]
+STATUS_F16_RANGE = 1
 
 _lib: Optional[C.CDLL] = None
 

@@ -2,6 +2,8 @@
 // Reference citations are into /root/reference (brain-research/l2hmc).
 #pragma once
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
+#include <cooperative_groups/reduce.h>
 #include <stdint.h>
 
 namespace l2hmc {
@@ -57,7 +59,13 @@ struct TransitionIO {
   unsigned long long seed, counter;
   float *x_out, *v_out, *px_out, *x_next;
   uint8_t *accepted;
+  double *stats;          // [2] or null: += sum of px, += number accepted, over every chain and transition of the launch
+  float *trace;           // [n_transitions][n][D] or null: the Metropolis output x_next after every fused transition
+  unsigned int *status;   // the context's status word (pinned, host-mapped): bit 0 = fp16 operand range exceeded
 };
+
+// status bits (l2hmc_status_flags)
+constexpr unsigned int STATUS_F16_RANGE = 1u;
 
 struct KernelArgs {
   Shape sh;
@@ -145,6 +153,20 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// Accept statistics (utils/sampler.py:53-55 aggregated over the launch): called by the threads that hold one valid chain's
+// (px, accepted) each; the calling lanes of a warp are reduced with shuffles and ONE lane issues the two atomics.
+__device__ __forceinline__ void stats_add(double *stats, float px, int acc) {
+  if (stats == nullptr) return;
+  namespace cg = cooperative_groups;
+  const cg::coalesced_group g = cg::coalesced_threads();
+  const float s = cg::reduce(g, px, cg::plus<float>());
+  const int a = cg::reduce(g, acc, cg::plus<int>());
+  if (g.thread_rank() == 0) {
+    atomicAdd(stats, (double)s);
+    atomicAdd(stats + 1, (double)a);
+  }
 }
 
 // p_accept tail (utils/dynamics.py:306-309): exp(min(v, 0)), non-finite -> 0

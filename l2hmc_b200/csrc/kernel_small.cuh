@@ -251,6 +251,12 @@ __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_const
     const float px = io.log_jac ? lj : p;
     const bool acc = io.do_mh && (px - pu >= 0.f);
     const bool last = tr == io.n_transitions - 1;
+    stats_add(io.stats, px, acc ? 1 : 0);
+    if (io.trace) {
+#pragma unroll
+      for (int d = 0; d < DM; ++d)
+        if (d < D) io.trace[((long long)tr * io.n + g) * D + d] = acc ? x[d] : x0[d];
+    }
     if (last) {
       io.px_out[g] = px;
       if (io.accepted) io.accepted[g] = acc ? 1 : 0;

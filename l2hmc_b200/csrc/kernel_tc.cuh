@@ -628,6 +628,7 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
         int acc = 0;
         if (io.do_mh) acc = (px - smem[L.su + c] >= 0.f) ? 1 : 0;
         sacc[c] = acc;
+        if (gch < io.n) stats_add(io.stats, px, acc);
         if (gch < io.n && last) {
           io.px_out[gch] = px;
           if (io.accepted) io.accepted[gch] = (uint8_t)acc;
@@ -643,7 +644,11 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
             io.x_out[g * D + d] = lx;
             if (io.v_out) io.v_out[g * D + d] = vs[d * MT + ch];
             // the state this transition started from: the caller's x, or the x_next written one transition ago
-            if (io.do_mh) io.x_next[g * D + d] = sacc[ch] ? lx : (tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d]);
+            if (io.do_mh) {
+              const float nx = sacc[ch] ? lx : (tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d]);
+              io.x_next[g * D + d] = nx;
+              if (io.trace) io.trace[((long long)tr * io.n + g) * D + d] = nx;
+            }
           }
         }
       } else {
@@ -655,6 +660,7 @@ __global__ void __launch_bounds__(MT * NQ + 64, 1) tc_transition_kernel(const __
             const float prev = tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d];
             const float nx = sacc[ch] ? xs[d * MT + ch] : prev;
             io.x_next[g * D + d] = nx;
+            if (io.trace) io.trace[((long long)tr * io.n + g) * D + d] = nx;
             xs[d * MT + ch] = nx;
           }
         }

@@ -871,6 +871,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         int acc = 0;
         if (io.do_mh) acc = (px - smem[L.su + c] >= 0.f) ? 1 : 0;
         sacc[c] = acc;
+        if (gch < io.n) stats_add(io.stats, px, acc);
         if (gch < io.n && last) {
           io.px_out[gch] = px;
           if (io.accepted) io.accepted[gch] = (uint8_t)acc;
@@ -886,7 +887,11 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             io.x_out[g * D + d] = lx;
             if (io.v_out) io.v_out[g * D + d] = smem[L.vs + ch * RS + d];
             // the state this transition started from: the caller's x, or the x_next written one transition ago
-            if (io.do_mh) io.x_next[g * D + d] = sacc[ch] ? lx : (tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d]);
+            if (io.do_mh) {
+              const float nx = sacc[ch] ? lx : (tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d]);
+              io.x_next[g * D + d] = nx;
+              if (io.trace) io.trace[((long long)tr * io.n + g) * D + d] = nx;
+            }
           }
         }
       } else {
@@ -898,6 +903,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             const float prev = tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d];
             const float nx = sacc[ch] ? smem[L.xs + ch * RS + d] : prev;
             io.x_next[g * D + d] = nx;
+            if (io.trace) io.trace[((long long)tr * io.n + g) * D + d] = nx;
             smem[L.xs + ch * RS + d] = nx;
           }
         }
@@ -910,7 +916,11 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       g_tc_dbg[4] = clock64() - t_begin;
     }
 #endif
-    if (F16 && !(amax < 60000.f)) g_tc_dbg[23] = 1;  // sticky: an A operand left the fp16 range (or was not finite)
+    // an A operand left the fp16 range (or was not finite): raise the CONTEXT's sticky status bit (pinned host-mapped word
+    // the host polls without a device synchronisation; the library then stays on the tf32 split)
+    if (F16 && !(amax < 60000.f)) {
+      if (io.status) atomicOr_system(io.status, STATUS_F16_RANGE);
+    }
     (void)Tm;
   }
   tcgen05_fence_before();

@@ -483,12 +483,20 @@ __device__ __noinline__ void phase_end(const KernelArgs &A, int tr) {
     int acc = 0;
     if (io.do_mh) acc = (px - smem[L.su + ch] >= 0.f) ? 1 : 0;  // tf_accept, utils/sampler.py:53-55
     sacc[ch] = acc;
+    if (g < io.n) stats_add(io.stats, px, acc);
     if (g < io.n && last) {
       io.px_out[g] = px;
       if (io.accepted) io.accepted[g] = (uint8_t)acc;
     }
   }
   __syncthreads();
+  if (io.trace) {
+    for (int i = tid; i < M * D; i += NT) {
+      const int ch = i / D, d = i - ch * D;
+      const long long g = base + ch;
+      if (g < io.n) io.trace[((long long)tr * io.n + g) * D + d] = sacc[ch] ? smem[L.xg + d * M + ch] : smem[L.x0 + d * M + ch];
+    }
+  }
   if (last) {
     for (int i = tid; i < M * D; i += NT) {
       const int ch = i / D, d = i - ch * D;

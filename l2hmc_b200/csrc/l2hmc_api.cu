@@ -107,6 +107,13 @@ struct l2hmc_ctx {
   cudaStream_t hstreams[3] = {nullptr, nullptr, nullptr};  // chunk pipeline of l2hmc_transition_host
   LayeredCtx lay;
   DevBuf haux, diag;
+  double host_stats0[2] = {0.0, 0.0};  // l2hmc_transition_host: the caller's stats before the call (for the tf32 repeat)
+  DevBuf hstats;                        // device twin of the host stats accumulators (2 doubles in a float buffer of 4)
+  // status word of this context: pinned host memory mapped into the device; kernels raise sticky bits with
+  // atomicOr_system, the host reads it WITHOUT synchronising (l2hmc_status_flags, and before every tensor-core launch)
+  unsigned int *status_h = nullptr, *status_d = nullptr;
+  // cudaFuncAttributeMaxDynamicSharedMemorySize already granted on this context's device: [0] tc_s, [1] tc, [2] tile
+  size_t smem_cfg[3] = {0, 0, 0};
 };
 
 static thread_local std::string g_err;
@@ -657,6 +664,14 @@ extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
     delete ctx;
     return fail(nullptr, L2HMC_ECUDA, "l2hmc_create: cudaSetDevice(%d) failed", cfg->device);
   }
+  if (cudaHostAlloc((void **)&ctx->status_h, sizeof(unsigned int), cudaHostAllocMapped) != cudaSuccess ||
+      cudaHostGetDevicePointer((void **)&ctx->status_d, ctx->status_h, 0) != cudaSuccess) {
+    cudaGetLastError();
+    if (ctx->status_h) cudaFreeHost(ctx->status_h);
+    delete ctx;
+    return fail(nullptr, L2HMC_ECUDA, "l2hmc_create: cannot allocate the mapped status word");
+  }
+  *ctx->status_h = 0u;
   *out = ctx;
   return L2HMC_OK;
 }
@@ -666,7 +681,7 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   cudaSetDevice(ctx->cfg.device);
   DevBuf *bufs[] = {&ctx->net_packed[0], &ctx->net_packed[1], &ctx->net_raw[0], &ctx->net_raw[1], &ctx->mask,
                     &ctx->energy_buf, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn,
-                    &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf, &ctx->tc_hc[0], &ctx->tc_hc[1], &ctx->train_ws};
+                    &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf, &ctx->tc_hc[0], &ctx->tc_hc[1], &ctx->train_ws, &ctx->hstats};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
   {
@@ -685,6 +700,7 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   }
   if (ctx->hdir) cudaFree(ctx->hdir);
   if (ctx->hacc) cudaFree(ctx->hacc);
+  if (ctx->status_h) cudaFreeHost(ctx->status_h);
   for (cudaEvent_t e : ctx->ev) cudaEventDestroy(e);
   if (ctx->hstream) cudaStreamDestroy(ctx->hstream);
   for (cudaStream_t hs : ctx->hstreams)
@@ -817,9 +833,21 @@ extern "C" int l2hmc_set_masks(l2hmc_ctx *ctx, const float *mask) {
   return L2HMC_OK;
 }
 
+extern "C" int l2hmc_status_flags(l2hmc_ctx *ctx, uint32_t *flags, int clear) {
+  if (!ctx || !flags) return fail(ctx, L2HMC_EINVAL, "l2hmc_status_flags: null argument");
+  *flags = *(volatile unsigned int *)ctx->status_h;  // pinned host memory the kernels write with system-scope atomics
+  if (clear) {
+    *(volatile unsigned int *)ctx->status_h = 0u;
+    const char *fe = getenv("L2HMC_TC_F16");
+    ctx->td.f16 = (fe && fe[0] == '0') ? 0 : 1;  // the tensor-core kernel may try the fp16 operand split again
+  }
+  return L2HMC_OK;
+}
+
 extern "C" int l2hmc_set_eps(l2hmc_ctx *ctx, float eps) {
   if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_eps: null context");
   if (!(eps > 0.f) || !isfinite(eps)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_eps: eps must be finite and > 0");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));  // tc_pack_hc copies to this context's device
   ctx->sh.eps = eps;
   for (int net_id = 0; net_id < 2; ++net_id) {
     int rc = tc_pack_hc(ctx, net_id);
@@ -989,6 +1017,8 @@ static int validate_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, b
   if (a->dir_mode == L2HMC_DIR_PER_CHAIN && !a->dir && a->n > 0) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: dir_mode PER_CHAIN needs dir");
   if (a->do_mh && !a->x_next && a->n > 0 && !host) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: do_mh needs x_next");
   if (a->n_transitions > 1 && !a->do_mh) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: n_transitions > 1 needs do_mh");
+  if (a->trace && !a->do_mh) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: trace records the Metropolis output and needs do_mh");
+  if (a->trace && host) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition_host: trace is a device-resident output (use l2hmc_transition)");
   if (a->counter + (uint64_t)a->n_transitions >= (1ull << 30)) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: counter must stay below 2^30");
   return L2HMC_OK;
 }
@@ -1007,6 +1037,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
   io.dir_mode = a->dir_mode; io.log_jac = a->log_jac; io.do_mh = a->do_mh; io.n_transitions = a->n_transitions;
   io.seed = a->seed; io.counter = a->counter;
   io.x_out = a->x_out; io.v_out = a->v_out; io.px_out = a->px_out; io.x_next = a->x_next; io.accepted = a->accepted;
+  io.stats = a->stats; io.trace = a->trace; io.status = ctx->status_d;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->timing) {
@@ -1057,7 +1088,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       TA.td.nslot = ns > tc::MAX_SLOT ? tc::MAX_SLOT : (int)ns;
       if (TA.td.nslot < 4) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: shared-memory ring too small for this shape");
       const size_t smem = tc::tc_s_smem_bytes(ctx->sh.DP, ctx->sh.T, TA.td.nslot, TA.td.slot_floats);
-      static thread_local size_t tc_s_configured = 0;
+      size_t &tc_s_configured = ctx->smem_cfg[0];  // the attribute is per device: remembered per context, not per thread
       if (smem > tc_s_configured) {
 #define L2HMC_TC_S_ATTR(Q, HH, F, B, X) \
   CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel_s<Q, HH, F, B, X>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))
@@ -1075,6 +1106,9 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       // fp16 split only when everything packed (weights, biases, time-embedding rows, precision matrix) is well inside
       // the fp16 range; activations are checked by the kernel (sticky flag, l2hmc_debug_counters[23])
       const float wmax = fmaxf(fmaxf(ctx->tc_wmax[0], ctx->tc_wmax[1]), ctx->en.kind == L2HMC_ENERGY_GAUSSIAN ? ctx->tc_wmax[2] : 0.f);
+      // ... and an earlier launch of THIS context that met an out-of-range activation (sticky status bit, read from pinned
+      // host memory without synchronising) puts the context on the tf32 split for good
+      if (*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE) ctx->td.f16 = 0;
       const bool h16 = ctx->td.f16 != 0 && wmax < 3.0e4f;
       TA.td.f16 = h16 ? 1 : 0;
       ctx->tc_used_f16 = h16;
@@ -1096,7 +1130,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     } else {
     ctx->tc_used_f16 = false;
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
-    static thread_local size_t tc_configured = 0;
+    size_t &tc_configured = ctx->smem_cfg[1];
     if (smem > tc_configured) {
       CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       CUDA_TRY(ctx, cudaFuncSetAttribute(tc::tc_transition_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1136,7 +1170,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     }
   } else if (kernel == L2HMC_KERNEL_TILE) {
     const size_t smem = tile::smem_bytes(ctx->sh.DP, ctx->sh.HP, ctx->sh.T);
-    static thread_local size_t configured = 0;
+    size_t &configured = ctx->smem_cfg[2];
     if (smem > configured) {
       CUDA_TRY(ctx, cudaFuncSetAttribute(tile::transition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       configured = smem;
@@ -1213,12 +1247,21 @@ static int transition_host_chunked(l2hmc_ctx *ctx, const l2hmc_transition_args *
     bounds.push_back(n);
   }
   const int NCH = (int)bounds.size() - 1;
+  double *dstats = nullptr;  // accept statistics: one device accumulator pair per stream, summed on the host at the end
+  if (a->stats) {
+    if ((rc = ensure(ctx, ctx->hstats, 12))) return rc;
+    dstats = reinterpret_cast<double *>(ctx->hstats.p);
+    ctx->host_stats0[0] = a->stats[0];
+    ctx->host_stats0[1] = a->stats[1];
+  }
   for (int c = 0; c < NCH; ++c) {
     const size_t lo = bounds[c];
     const size_t m = bounds[c + 1] - lo;
     cudaStream_t s = ctx->hstreams[c % 3];
     l2hmc_transition_args d = *a;
     d.stream = s;
+    d.stats = dstats ? dstats + 2 * (c % 3) : nullptr;
+    if (dstats && c < 3) CUDA_TRY(ctx, cudaMemsetAsync(d.stats, 0, 2 * sizeof(double), s));
     d.n = (int64_t)m;
     d.chain_offset = a->chain_offset + (int64_t)lo;
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->hx.p + lo * D, a->x + lo * D, m * D * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -1248,23 +1291,35 @@ static int transition_host_chunked(l2hmc_ctx *ctx, const l2hmc_transition_args *
     if (a->accepted) CUDA_TRY(ctx, cudaMemcpyAsync(a->accepted + lo, d.accepted, m, cudaMemcpyDeviceToHost, s));
   }
   for (int i = 0; i < 3; ++i) CUDA_TRY(ctx, cudaStreamSynchronize(ctx->hstreams[i]));
+  if (dstats) {
+    double h[6];
+    const int used = NCH < 3 ? NCH : 3;
+    CUDA_TRY(ctx, cudaMemcpy(h, dstats, (size_t)used * 2 * sizeof(double), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < used; ++i) {
+      a->stats[0] += h[2 * i];
+      a->stats[1] += h[2 * i + 1];
+    }
+  }
   return L2HMC_OK;
 }
 
 static int transition_host_once(l2hmc_ctx *ctx, const l2hmc_transition_args *a);
 
-// The host-buffer entry point is synchronous, so it can afford to look at the fp16 range flag of the tensor-core
-// kernel: if an operand left the fp16 range the call is repeated with the tf32 split (fp32 range) and the context
-// stays on tf32.  Device-resident callers (l2hmc_transition) check l2hmc_debug_counters[23] themselves.
+// The host-buffer entry point is synchronous: when its launch raised the fp16 range bit of the context's status word
+// the call is repeated at once with the tf32 split (fp32 range).  Device-resident callers (l2hmc_transition) are
+// asynchronous: the affected chains of THAT call carry non-finite proposals, which p_accept maps to probability 0
+// (utils/dynamics.py:309), i.e. they are rejected and keep x; every later launch of the context sees the sticky bit
+// (polled from pinned host memory, no synchronisation) and runs the tf32 split.  l2hmc_status_flags reports it.
 extern "C" int l2hmc_transition_host(l2hmc_ctx *ctx, const l2hmc_transition_args *a) {
+  const bool was_set = ctx && ctx->status_h && (*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE);
   int rc = transition_host_once(ctx, a);
-  if (rc != L2HMC_OK || !ctx || ctx->kernel != L2HMC_KERNEL_TC || !ctx->tc_used_f16) return rc;
-  long long flag = 0;
-  CUDA_TRY(ctx, cudaMemcpyFromSymbol(&flag, tc::g_tc_dbg, sizeof(flag), 23 * sizeof(long long)));
-  if (!flag) return L2HMC_OK;
-  flag = 0;
-  CUDA_TRY(ctx, cudaMemcpyToSymbol(tc::g_tc_dbg, &flag, sizeof(flag), 23 * sizeof(long long)));
+  if (rc != L2HMC_OK || !ctx || ctx->kernel != L2HMC_KERNEL_TC || !ctx->tc_used_f16 || was_set) return rc;
+  if (!(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE)) return L2HMC_OK;
   ctx->td.f16 = 0;
+  if (a->stats) {  // the repeated call must not count twice: the caller's accumulators are host memory here
+    a->stats[0] = ctx->host_stats0[0];
+    a->stats[1] = ctx->host_stats0[1];
+  }
   return transition_host_once(ctx, a);
 }
 
@@ -1327,6 +1382,13 @@ static int transition_host_once(l2hmc_ctx *ctx, const l2hmc_transition_args *a) 
     if ((rc = ensure_u8(ctx, ctx->hacc, ctx->hacc_n, n))) return rc;
     d.accepted = ctx->hacc;
   }
+  if (a->stats) {
+    if ((rc = ensure(ctx, ctx->hstats, 12))) return rc;
+    d.stats = reinterpret_cast<double *>(ctx->hstats.p);
+    ctx->host_stats0[0] = a->stats[0];
+    ctx->host_stats0[1] = a->stats[1];
+    CUDA_TRY(ctx, cudaMemsetAsync(d.stats, 0, 2 * sizeof(double), s));
+  }
   if ((rc = launch_transition(ctx, &d, s))) return rc;
   if (a->x_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->x_out, d.x_out, n * D * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (a->px_out) CUDA_TRY(ctx, cudaMemcpyAsync(a->px_out, d.px_out, n * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1334,6 +1396,12 @@ static int transition_host_once(l2hmc_ctx *ctx, const l2hmc_transition_args *a) 
   if (a->x_next) CUDA_TRY(ctx, cudaMemcpyAsync(a->x_next, d.x_next, n * D * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (a->accepted) CUDA_TRY(ctx, cudaMemcpyAsync(a->accepted, d.accepted, n, cudaMemcpyDeviceToHost, s));
   CUDA_TRY(ctx, cudaStreamSynchronize(s));
+  if (a->stats) {
+    double h[2];
+    CUDA_TRY(ctx, cudaMemcpy(h, d.stats, sizeof(h), cudaMemcpyDeviceToHost));
+    a->stats[0] += h[0];
+    a->stats[1] += h[1];
+  }
   return L2HMC_OK;
 }
 

@@ -358,6 +358,12 @@ __global__ void k_lay_end(LayDims dm, LayState st, TransitionIO io, int tr) {
   const float p = accept_prob(st.h0[n], st.U[n] + 0.5f * kin, logj);
   const float px = io.log_jac ? logj : p;
   const int acc = io.do_mh ? ((px - st.u[n] >= 0.f) ? 1 : 0) : 0;
+  if (lane == 0 && io.stats) {  // one warp per chain here: its lane 0 adds the chain (a launch of n atomics per transition)
+    atomicAdd(io.stats, (double)px);
+    atomicAdd(io.stats + 1, (double)acc);
+  }
+  if (io.trace)
+    for (int d = lane; d < D; d += 32) io.trace[((long long)tr * io.n + n) * D + d] = acc ? st.x[n * dm.Dp + d] : st.x0[n * dm.Dp + d];
   if (last) {
     if (lane == 0) {
       io.px_out[n] = px;

@@ -16,20 +16,20 @@ from . import _lib
 from .sampler import _util
 
 
-def sample_trace(x, dynamics, n_steps, aux=None):
+def sample_trace(x, dynamics, n_steps, aux=None, stats=None):
     """Run ``n_steps`` transitions (propose + MH) and return the device-resident trace [n_steps, N, x_dim] of the
-    chain states after each one -- the loop of SCGExperiment.ipynb:291-298 without leaving the GPU."""
+    chain states after each one -- the loop of SCGExperiment.ipynb:291-298 without leaving the GPU: ONE launch of the
+    fused kernel iterates the chain on-chip and writes every transition's Metropolis output into the trace
+    (``l2hmc_transition_args.trace``).  ``stats``: optional CUDA float64 [2] accumulator of (sum of accept
+    probabilities, number accepted) over the whole trace."""
     n, d = x.shape
-    trace = torch.empty((int(n_steps), n, d), dtype=torch.float32, device=x.device)
-    scratch = {"Lx": torch.empty((n, d), dtype=torch.float32, device=x.device), "Lv": None,
-               "px": torch.empty((n,), dtype=torch.float32, device=x.device),
-               "accepted": torch.empty((n,), dtype=torch.uint8, device=x.device)}
-    cur = x
-    for t in range(int(n_steps)):
-        out = dict(scratch, x_next=trace[t])
-        dir_mode = _lib.DIR_FORWARD if dynamics.hmc else _lib.DIR_RANDOM
-        dynamics._transition(cur, dir_mode=dir_mode, do_mh=True, want_v=False, out=out, aux=aux)
-        cur = trace[t]
+    n_steps = int(n_steps)
+    trace = torch.empty((n_steps, n, d), dtype=torch.float32, device=x.device)
+    if n_steps == 0:
+        return trace
+    dir_mode = _lib.DIR_FORWARD if dynamics.hmc else _lib.DIR_RANDOM
+    dynamics._transition(x, dir_mode=dir_mode, do_mh=True, want_v=False, n_transitions=n_steps, aux=aux, trace=trace,
+                         stats=stats)
     return trace
 
 

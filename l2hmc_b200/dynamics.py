@@ -212,14 +212,23 @@ class Dynamics(object):
             n, w, Wp, bp = self._mlp_args(*self._aux_encoder)
             self._chk(self._lib.l2hmc_set_aux_encoder(self._ctx, n, w, Wp, bp))
 
-    def fp16_range_exceeded(self):
-        """True when the tensor-core kernel's fp16 operand split met a value outside the fp16 range (|a| >= 6e4 or not
-        finite) since the library was loaded: results of the affected chains are not valid -- rerun with
-        L2HMC_TC_F16=0 (tf32 split, fp32 range).  Synchronises the device."""
+    def status_flags(self, clear=False):
+        """Sticky status bits of the context (l2hmc_status_flags): read from pinned host memory, no device synchronisation
+        (a launch still in flight may raise a bit later)."""
         self._ensure_ctx()
-        buf = (C.c_int64 * 24)()
-        self._chk(self._lib.l2hmc_debug_counters(self._ctx, buf, 24))
-        return bool(buf[23])
+        f = C.c_uint32(0)
+        self._chk(self._lib.l2hmc_status_flags(self._ctx, C.byref(f), int(bool(clear))))
+        return int(f.value)
+
+    def fp16_range_exceeded(self, synchronize=True):
+        """True when a launch of THIS Dynamics' tensor-core kernel met an activation outside the fp16 range while using
+        the fp16 operand split.  The affected chains of that launch carry non-finite proposals (accept probability 0:
+        rejected, like any non-finite p in the reference, utils/dynamics.py:309); every later launch runs the tf32 split
+        (fp32 range) on its own.  ``synchronize``: wait for launches in flight first, so that the answer covers them."""
+        self._ensure_ctx()
+        if synchronize:
+            torch.cuda.synchronize(self.device_index)
+        return bool(self.status_flags() & _lib.STATUS_F16_RANGE)
 
     def set_likelihood_scale(self, beta):
         """Decoder energy only: U = beta * sum BCE + 0.5 |z|^2, the annealed energy between the prior and the posterior
@@ -334,9 +343,11 @@ class Dynamics(object):
 
     def _transition(self, x, *, v=None, dir_mode=_lib.DIR_FORWARD, direction=None, u=None, log_jac=False,
                     do_mh=False, n_transitions=1, want_v=True, counter=None, chain_offset=0, seed=None, out=None,
-                    aux=None):
+                    aux=None, stats=None, trace=None):
         """One l2hmc_transition call. Returns dict(Lx, Lv, px, x_next, accepted).  `out` may hold preallocated
-        tensors of the right shapes under the same keys (steady-state loops then allocate nothing)."""
+        tensors of the right shapes under the same keys (steady-state loops then allocate nothing).
+        stats: optional CUDA float64 [2] accumulator (+= sum of px, += number accepted, reduced in the kernel);
+        trace: optional CUDA fp32 [n_transitions, N, x_dim] receiving the Metropolis output of every fused transition."""
         self._ensure_ctx()
         self._sync_temperature()
         x = self._prep(x, "x", self.x_dim)
@@ -384,13 +395,23 @@ class Dynamics(object):
         a.px_out = out["px"].data_ptr()
         a.x_next = out["x_next"].data_ptr() if do_mh else None
         a.accepted = out["accepted"].data_ptr() if do_mh else None
+        if stats is not None:
+            if not (stats.is_cuda and stats.dtype == torch.float64 and stats.numel() == 2 and stats.is_contiguous()):
+                raise TypeError("stats must be a contiguous CUDA float64 tensor of 2 elements")
+            a.stats = stats.data_ptr()
+        if trace is not None:
+            if not (trace.is_cuda and trace.dtype == TORCH_FLOAT and trace.is_contiguous() and
+                    tuple(trace.shape) == (int(n_transitions), n, self.x_dim)):
+                raise TypeError("trace must be a contiguous CUDA fp32 tensor [n_transitions, N, x_dim]")
+            a.trace = trace.data_ptr()
         a.stream = self._stream()
         self._chk(self._lib.l2hmc_transition(self._ctx, C.byref(a)))
         return out
 
     def transition_host(self, x, *, v=None, direction=None, u=None, dir_mode=_lib.DIR_RANDOM, log_jac=False,
-                        do_mh=True, n_transitions=1, counter=None, chain_offset=0, seed=None, out=None, aux=None):
-        """The same transition through l2hmc_transition_host: numpy in, numpy out, H2D/D2H inside."""
+                        do_mh=True, n_transitions=1, counter=None, chain_offset=0, seed=None, out=None, aux=None, stats=None):
+        """The same transition through l2hmc_transition_host: numpy in, numpy out, H2D/D2H inside.
+        stats: optional numpy float64 [2] accumulator (+= sum of px, += number accepted)."""
         self._ensure_ctx()
         self._sync_temperature()
         x = np.ascontiguousarray(x, dtype=NP_FLOAT)
@@ -434,6 +455,10 @@ class Dynamics(object):
         a.px_out = ptr("px")
         a.x_next = ptr("x_next") if do_mh else None
         a.accepted = out["accepted"].ctypes.data if (do_mh and out.get("accepted") is not None) else None
+        if stats is not None:
+            if not (isinstance(stats, np.ndarray) and stats.dtype == np.float64 and stats.size == 2 and stats.flags.c_contiguous):
+                raise TypeError("stats must be a contiguous numpy float64 array of 2 elements")
+            a.stats = stats.ctypes.data
         self._chk(self._lib.l2hmc_transition_host(self._ctx, C.byref(a)))
         return out
 

@@ -18,23 +18,26 @@ from . import _lib
 from .dynamics import Dynamics, TORCH_FLOAT
 
 
-def propose(x, dynamics, init_v=None, aux=None, do_mh_step=False, log_jac=False, *, rng=None, n_transitions=1):
+def propose(x, dynamics, init_v=None, aux=None, do_mh_step=False, log_jac=False, *, rng=None, n_transitions=1, stats=None):
     """One L2HMC (or HMC) proposal; returns ``(Lx, Lv, px, outputs)`` like the reference.
 
     rng: optional dict with explicit randomness -- 'direction' uint8 [N] (1 = forward), 'v' [N, D]
     momentum for the selected direction, 'u' [N] accept uniforms.  Missing entries are drawn in-kernel
     (Philox keyed by dynamics.seed and its call counter).
     n_transitions > 1 iterates the MH chain on-chip (requires do_mh_step); outputs are the last ones.
+    stats: optional CUDA float64 [2] accumulator: += sum of px, += number of accepted proposals, reduced in the kernel
+    (what the notebook prints as np.mean(px_), SCGExperiment.ipynb:268, without a second pass over px).
     """
     rng = rng or {}
     if dynamics.hmc:
         # utils/sampler.py:29-31 -- forward only, init_v forwarded, MH output always appended
         v = init_v if init_v is not None else rng.get("v")
         o = dynamics._transition(x, v=v, dir_mode=_lib.DIR_FORWARD, u=rng.get("u"), do_mh=True,
-                                 n_transitions=n_transitions, aux=aux)
+                                 n_transitions=n_transitions, aux=aux, stats=stats)
         return o["Lx"], o["Lv"], o["px"], [o["x_next"]]
     o = dynamics._transition(x, v=rng.get("v"), dir_mode=_lib.DIR_RANDOM, direction=rng.get("direction"),
-                             u=rng.get("u"), log_jac=log_jac, do_mh=do_mh_step, n_transitions=n_transitions, aux=aux)
+                             u=rng.get("u"), log_jac=log_jac, do_mh=do_mh_step, n_transitions=n_transitions, aux=aux,
+                             stats=stats)
     Lv = o["Lv"] if init_v is not None else None  # utils/sampler.py:40-42
     outputs = []
     if do_mh_step:

@@ -289,16 +289,7 @@ class DecoderBernoulliEnergy(Energy):
         return d + z
 
 
-def make_softplus_mlp(rng, widths, last_factor=1.0):
-    """Weights of a Linear/softplus stack with the reference initialiser (utils/layers.py:29-37,
-    factor 1.0; the decoder's last layer uses factor 0.01, mnist_vae.py:110); small biases so the
-    synthetic problem exercises them."""
-    Ws, bs = [], []
-    for i in range(len(widths) - 1):
-        f = last_factor if i == len(widths) - 2 else 1.0
-        Ws.append(trunc_normal(rng, (widths[i], widths[i + 1]), math.sqrt(1.3 * 2.0 * f / widths[i])))
-        bs.append((0.05 * rng.standard_normal(widths[i + 1])).astype(np.float32))
-    return Ws, bs
+from l2hmc_b200.synthetic import make_softplus_mlp  # noqa: E402,F401
 
 
 # --------------------------------------------------------------------------------------
@@ -538,43 +529,9 @@ def chain_operator(init_x, dyn: OracleDynamics, nb_steps: int, *, init_v, direct
 # --------------------------------------------------------------------------------------
 # Synthetic problem builders shared by tests / bench
 # --------------------------------------------------------------------------------------
-def trunc_normal(rng: np.random.Generator, shape, std):
-    """variance_scaling_initializer(uniform=False) draws a truncated normal (+-2 sigma), utils/layers.py:32."""
-    out = rng.standard_normal(shape)
-    bad = np.abs(out) > 2.0
-    while bad.any():
-        out[bad] = rng.standard_normal(int(bad.sum()))
-        bad = np.abs(out) > 2.0
-    return (out * std).astype(np.float32)
-
-
-def make_net(rng, D, H, factor, regime="init"):
-    """Weights of one S/T/Q net.  regime 'init' follows SCGExperiment.ipynb:55-71 (embed factors 1/3,
-    factor/3, 1/3; hidden 1.0; heads 0.001; biases 0; log-scales 0).  'stress' (trained-like) uses head
-    factor 0.003, N(0, 0.05^2) biases and log-scales ~ U(-0.5, 0.5): S, Q are O(0.1), log|J| is O(1) and
-    accept probabilities spread over (0, 1) instead of sitting near the untrained value."""
-    def lin(i, o, f):
-        return trunc_normal(rng, (i, o), math.sqrt(1.3 * 2.0 * f / i))
-    hf = 0.001 if regime == "init" else 0.003
-    p = {
-        "W1": lin(D, H, 1.0 / 3), "W2": lin(D, H, factor / 3.0), "W3": lin(2, H, 1.0 / 3),
-        "W4": lin(H, H, 1.0), "Ws": lin(H, D, hf), "Wt": lin(H, D, hf), "Wq": lin(H, D, hf),
-    }
-    for k, n in (("b1", H), ("b2", H), ("b3", H), ("b4", H), ("bs", D), ("bt", D), ("bq", D)):
-        p[k] = (np.zeros(n, np.float32) if regime == "init"
-                else (0.05 * rng.standard_normal(n)).astype(np.float32))
-    for k in ("ls", "lq"):
-        p[k] = (np.zeros(D, np.float32) if regime == "init"
-                else rng.uniform(-0.5, 0.5, D).astype(np.float32))
-    return p
-
-
-def make_masks(rng, T, D):
-    """_init_mask (utils/dynamics.py:84-93): floor(D/2) ones at a random permutation's head, per step."""
-    m = np.zeros((T, D), np.float32)
-    for t in range(T):
-        m[t, rng.permutation(D)[: int(D / 2)]] = 1.0
-    return m
+# (defined with the product's synthetic workloads so that bench.py's product arm needs no test infrastructure; the
+# oracle sees the same arrays)
+from l2hmc_b200.synthetic import trunc_normal, make_net, make_masks  # noqa: E402,F401
 
 
 # --------------------------------------------------------------------------------------

@@ -463,105 +463,126 @@ def test_tc_fp16_and_tf32_splits_agree_and_range_flag(monkeypatch):
     assert U.max_rel(a["Lx"].cpu().numpy(), b["Lx"].cpu().numpy()) <= SAMPLE_TOL
     assert U.max_rel(a["Lv"].cpu().numpy(), b["Lv"].cpu().numpy()) <= SAMPLE_TOL
     assert float((a["px"] - b["px"]).abs().max()) <= 2 * P_TOL
-    dyn = P.product(kernel="tc")
-    assert not dyn.fp16_range_exceeded()
+    # the synchronous host-buffer entry point notices an out-of-range activation, repeats the call with the tf32 split
+    # and stays on it
     big = x.clone()
     big[0, 0] = 1.0e5                              # outside the fp16 range
-    dyn._transition(big, **kw)
-    assert dyn.fp16_range_exceeded()
-    # the synchronous host-buffer entry point notices, repeats the call with the tf32 split and stays on it
     ref = P.product(kernel="tc")
     monkeypatch.setenv("L2HMC_TC_F16", "0")
     ref32 = P.product(kernel="tc")
     r32 = ref32._transition(big, **kw)
     monkeypatch.delenv("L2HMC_TC_F16", raising=False)
-    host = ref.transition_host(big.cpu().numpy(), v=v.cpu().numpy(), direction=dr.cpu().numpy(), u=u.cpu().numpy(), do_mh=True)
-    assert ref.kernel_name == "tc_3xtf32"
+    st = np.zeros(2, np.float64)
+    host = ref.transition_host(big.cpu().numpy(), v=v.cpu().numpy(), direction=dr.cpu().numpy(), u=u.cpu().numpy(), do_mh=True,
+                               stats=st)
+    assert ref.kernel_name == "tc_3xtf32" and ref.fp16_range_exceeded()
     assert np.array_equal(host["x_next"], r32["x_next"].cpu().numpy())
+    assert st[1] == float(host["accepted"].sum())   # the repeated call is not counted twice
+
+def test_fp16_range_status_is_per_context_and_later_launches_fall_back_to_tf32():
+    """The range flag lives in the CONTEXT (pinned status word), not in a process-wide device symbol: a context that met
+    an out-of-range activation reports it and runs the tf32 split from its next launch on, without any caller action;
+    other contexts are untouched.  The chains of the tripping launch that were affected are rejected (p = 0), never
+    accepted with garbage."""
+    P = U.Problem(regime="stress", **U.CONFIGS["c2_scg50"])
+    x, v, dr, u = _fixed_inputs(P, 600)
+    kw = dict(v=v, direction=dr, u=u, do_mh=True)
+    a, b = P.product(kernel="tc"), P.product(kernel="tc")
+    big = x.clone()
+    big[5, 3] = 2.0e5
+    o = a._transition(big, **kw)
+    assert a.fp16_range_exceeded() and not b.fp16_range_exceeded()
+    assert a.status_flags() & 1 and not (b.status_flags() & 1)
+    bad = ~torch.isfinite(o["Lx"]).all(dim=1)
+    assert bool(bad[5]) and bool((o["px"][bad] == 0).all()) and bool((o["accepted"][bad] == 0).all())
+    assert torch.equal(o["x_next"][bad], big[bad])
+    # next launch of the same context: tf32 split, finite results for the same out-of-range input
+    o2 = a._transition(big, **kw)
+    assert a.kernel_name == "tc_3xtf32" and bool(torch.isfinite(o2["Lx"]).all())
+    b._transition(x, **kw)
+    assert b.kernel_name == "tc_3xf16"
+    # clearing the word re-arms the fp16 split
+    assert a.status_flags(clear=True) & 1 and a.status_flags() == 0
+    a._transition(x, **kw)
+    assert a.kernel_name == "tc_3xf16" and not a.fp16_range_exceeded()
 
 
-# ---- kernel selection: every kernel that covers a configuration must pass on it -------------------------
-@pytest.mark.parametrize("name,n,kernel", [
-    ("c1_scg2", 200, "small"), ("c1_scg2", 200, "tile"),
-    ("c3_mog2", 300, "small"), ("c3_mog2", 300, "tile"),
-    ("funnel3", 200, "small"), ("funnel3", 200, "tile"),
-])
-def test_small_and_tile_kernels_on_small_nets(name, n, kernel):
+@pytest.mark.parametrize("wscale,xscale", [(1e-4, 1.0), (1.0, 1e-5), (1e-3, 1e-3)])
+def test_tc_fp16_split_with_small_operands(wscale, xscale, monkeypatch):
+    """Underflow side of the fp16 operand split.  hi / lo fp16 parts bottom out at the fp16 subnormal spacing, so every
+    operand element carries an ABSOLUTE error of up to 2^-25 = 3e-8 (fp32-accurate relative to O(1) values -- the metric
+    of every parity test: error / max(1, |ref|)).  Measured here with head weights of 1e-4 x their usual size (hi / lo
+    in the subnormal range) and with states / momenta of 1e-5 and 1e-3 x their usual size:
+      * in the parity metric the kernel stays at the fp32 oracle's own level in all three cases;
+      * relative to the results' OWN magnitude the floor shows once states are ~1e-3 (6e-5 measured): bounded here by
+        1e-4, and the tf32 split (L2HMC_TC_F16=0: fp32 exponent range) is at the oracle's level there too."""
+    P = U.Problem(regime="stress", **U.CONFIGS["c2_scg50"])
+    for net in (P.xnet, P.vnet):
+        for k in ("Ws", "Wt", "Wq", "bs", "bt", "bq"):
+            net[k] = (net[k] * wscale).astype(np.float32)
+    d = P.draws(256, 5)
+    for k in ("x", "v_f", "v_b"):
+        d[k] = (d[k] * xscale).astype(np.float32)
+    r64 = U.run_oracle_propose(P, d, torch.float64)
+    r32 = U.run_oracle_propose(P, d, torch.float32)
+    monkeypatch.delenv("L2HMC_TC_F16", raising=False)
+    dyn = P.product(kernel="tc")
+    rk = U.run_kernel_propose(P, d, dyn=dyn)
+    assert dyn.kernel_name == "tc_3xf16" and not dyn.fp16_range_exceeded()
+    monkeypatch.setenv("L2HMC_TC_F16", "0")
+    dyn32 = P.product(kernel="tc")
+    rt = U.run_kernel_propose(P, d, dyn=dyn32)
+    monkeypatch.delenv("L2HMC_TC_F16", raising=False)
+    assert dyn32.kernel_name == "tc_3xtf32"
+    for k in ("Lx", "Lv"):
+        assert U.max_rel(rk[k], r64[k]) <= U.max_rel(r32[k], r64[k]) + NORTH_STAR_TOL, k
+        own = max(float(np.abs(r64[k]).max()), 1e-30)
+        err_k, err_t, err_o = (float(np.abs(r[k] - r64[k]).max()) / own for r in (rk, rt, r32))
+        assert err_k <= 1e-4, (k, err_k, err_o)
+        assert err_t <= err_o + NORTH_STAR_TOL, (k, err_t, err_o)
+    o32 = float(np.abs(r32["px"] - r64["px"]).max())
+    assert float(np.abs(rk["px"] - r64["px"]).max()) <= 4 * o32 + NORTH_STAR_TOL
+    assert float(np.abs(rt["px"] - r64["px"]).max()) <= 4 * o32 + NORTH_STAR_TOL
+
+
+@pytest.mark.parametrize("name,n,kernel", [("c1_scg2", 333, "small"), ("c3_mog2", 200, "tile"), ("c2_scg50", 300, "tc"),
+                                           ("c2_scg50", 200, "tile"), ("c4_rw32", 200, "layered")])
+def test_accept_statistics_and_trace_come_from_the_kernel(name, n, kernel):
+    """l2hmc_transition_args.stats / .trace: (sum of px, number accepted) reduced in the kernel over every chain and every
+    fused transition, and the Metropolis output of every fused transition -- against separate single-transition calls."""
     P = U.Problem(regime="stress", **U.CONFIGS[name])
-    dyn = P.product(kernel=kernel)
-    rep, _ = U.parity_report(P, n, dyn=dyn)
-    assert dyn.kernel_name == {"small": "small_fma", "tile": "tile_fma"}[kernel]
-    _check(rep)
+    dyn = P.product(kernel=kernel, seed=9)
+    x = torch.as_tensor(P.x0(n, np.random.default_rng(2))).cuda()
+    K = 3
+    c0 = 40
+    stats = torch.zeros(2, dtype=torch.float64, device="cuda")
+    trace = torch.empty((K, n, P.D), dtype=torch.float32, device="cuda")
+    l0 = dyn.launch_count
+    o = dyn._transition(x, dir_mode=3, do_mh=True, n_transitions=K, counter=c0, stats=stats, trace=trace)
+    fused_launches = dyn.launch_count - l0
+    cur, sum_p, n_acc = x, 0.0, 0
+    for t in range(K):
+        s = dyn._transition(cur, dir_mode=3, do_mh=True, counter=c0 + t)
+        assert torch.equal(trace[t], s["x_next"]), t
+        sum_p += float(s["px"].double().sum())
+        n_acc += int(s["accepted"].sum())
+        cur = s["x_next"]
+    assert torch.equal(o["x_next"], cur)
+    assert float(stats[1]) == n_acc
+    assert abs(float(stats[0]) - sum_p) <= 1e-4 * max(1.0, sum_p)
+    if kernel != "layered":
+        assert fused_launches == 1
+    # the accumulators add over calls
+    dyn._transition(x, dir_mode=3, do_mh=True, counter=c0, stats=stats)
+    assert float(stats[1]) >= n_acc
 
 
-@pytest.mark.parametrize("name,n", [("c2_scg50", 200), ("c2_scg50", 65), ("c4_rw32", 200), ("c4_rw32_hard", 130)])
-def test_tile_kernel_on_large_nets(name, n):
-    """AUTO picks the tensor-core kernel for these shapes; the generic FMA kernel must stay correct on them."""
-    P = U.Problem(regime="stress", **U.CONFIGS[name])
-    dyn = P.product(kernel="tile")
-    rep, _ = U.parity_report(P, n, dyn=dyn)
-    assert dyn.kernel_name == "tile_fma"
-    _check(rep)
-
-
-def test_auto_kernel_choice():
-    assert U.Problem(**U.CONFIGS["c1_scg2"]).product().kernel_name == "small_fma"
-    assert U.Problem(**U.CONFIGS["c2_scg50"]).product().kernel_name.startswith("tc_3x")
-    assert U.Problem(**U.CONFIGS["c4_rw32"]).product().kernel_name.startswith("tc_3x")
-    assert U.Problem(**U.CONFIGS["c3_mog2"]).product().kernel_name == "small_fma"
-    assert U.Problem(kind="gmm", D=8, H=32, T=5, eps=0.1).product().kernel_name == "tile_fma"  # GMM: not on the TC path
-    assert U.Problem(kind="gaussian", D=2, T=5, eps=0.1, hmc=True).product().kernel_name == "small_fma"
-    assert U.Problem(kind="gaussian", D=50, T=5, eps=0.1, hmc=True).product().kernel_name == "tile_fma"
-
-
-def test_small_kernel_multi_transition_and_generic_size():
-    """Fused transitions on the thread-per-chain kernel; and the padded <4,16> instantiation (D=3, H=12)."""
-    P = U.Problem(regime="stress", **U.CONFIGS["c1_scg2"])
-    dyn = P.product(seed=5)
-    x0 = torch.as_tensor(P.draws(333)["x"]).cuda()
-    a = dyn._transition(x0, dir_mode=3, do_mh=True, n_transitions=4, counter=10)
-    x = x0
-    for t in range(4):
-        b = dyn._transition(x, dir_mode=3, do_mh=True, counter=10 + t)
-        x = b["x_next"]
-    assert torch.equal(a["x_next"], b["x_next"]) and torch.equal(a["px"], b["px"])
-    P2 = U.Problem(kind="gaussian", D=3, H=12, T=7, eps=0.1, regime="stress")
-    d2 = P2.product()
-    assert d2.kernel_name == "small_fma"
-    rep, _ = U.parity_report(P2, 150, dyn=d2)
-    _check(rep)
-
-
-# ---- annealed importance sampling (utils/ais.py) on the HMC-mode kernels --------------------------------
-@pytest.mark.parametrize("D,refresh", [(3, False), (6, True)])
-def test_ais_estimate_matches_oracle(D, refresh):
-    """ais_estimate (Gaussian -> Gaussian) against the fp64 restatement with the same injected randomness: weights,
-    final particles, estimate and mean accept probability; D=3 runs the chain-per-thread kernel, D=6 the tile kernel."""
-    from l2hmc_b200.ais import ais_estimate
-    from l2hmc_b200.distributions import Gaussian
-    n, steps, L, eps = 384, 12, 5, 0.25
-    rng = np.random.default_rng(3)
-    A = rng.standard_normal((D, D))
-    cov1 = A @ A.T / D + 0.3 * np.eye(D)
-    mu1 = rng.standard_normal(D) * 0.5
-    g0, g1 = Gaussian(np.zeros(D), np.eye(D)), Gaussian(mu1, cov1)
-    e0 = U.O.GaussianEnergy(np.zeros(D), g0.i_sigma)
-    e1 = U.O.GaussianEnergy(mu1, g1.i_sigma)
-    r = {"v0": rng.standard_normal((n, D)).astype(np.float32), "v": rng.standard_normal((steps, n, D)).astype(np.float32),
-         "u": rng.random((steps, n)).astype(np.float32)}
-    x0 = rng.standard_normal((n, D)).astype(np.float32)
-    est_o, alpha_o, x_o, w_o = U.O.ais_estimate(e0, e1, steps, x0, step_size=eps, leapfrogs=L, v0=r["v0"], v_refresh=r["v"],
-                                                u=r["u"], refresh=refresh, num_splits=4)
-    est, alpha, x, w = ais_estimate(g0.get_energy_function(), g1.get_energy_function(), steps, torch.as_tensor(x0).cuda(),
-                                    step_size=eps, leapfrogs=L, x_dim=D, num_splits=4, refresh=refresh, rng=r, return_state=True)
-    # a Metropolis decision may flip where |p - u| is inside fp32 noise: compare the chains that agree on every decision
-    same = np.abs(x.cpu().numpy() - x_o.numpy()).max(1) < 1e-3
-    assert same.mean() > 0.99
-    assert U.max_rel(x.cpu().numpy()[same], x_o.numpy()[same]) <= 5e-5
-    assert float(np.abs(w.cpu().numpy()[same] - w_o.numpy()[same]).max()) <= 2e-4
-    assert abs(alpha - float(alpha_o)) <= 1e-4
-    if same.all():
-        assert abs(est - float(est_o)) <= 1e-3
-    with pytest.raises(NotImplementedError):
-        from l2hmc_b200.distributions import RoughWell
-        ais_estimate(g0.get_energy_function(), RoughWell(D, 0.1).get_energy_function(), 2, torch.as_tensor(x0).cuda(), x_dim=D)
+def test_host_entry_point_returns_accept_statistics():
+    P = U.Problem(regime="stress", **U.CONFIGS["c2_scg50"])
+    dyn = P.product(seed=4)
+    for n in (5000, 40000):   # single launch / chunk pipeline over three streams
+        x = P.x0(n, np.random.default_rng(3))
+        st = np.zeros(2, np.float64)
+        out = dyn.transition_host(x, counter=7, stats=st)
+        assert st[1] == float(out["accepted"].sum())
+        assert abs(st[0] - float(out["px"].astype(np.float64).sum())) <= 1e-4 * max(1.0, st[0])

@@ -16,139 +16,47 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 import l2hmc_oracle as O  # noqa: E402  (test infrastructure)
 
 
-# ---- targets -------------------------------------------------------------------------------------
-def scg2_cov():
-    return np.array([[50.05, -49.95], [-49.95, 50.05]])  # SCGExperiment.ipynb:105
+from l2hmc_b200 import synthetic as S  # noqa: E402  (product-side problem definitions)
+from l2hmc_b200.synthetic import scg2_cov, scg_cov  # noqa: E402,F401
 
 
-def scg_cov(D, seed=0):
-    """Builder-defined D-dim strongly correlated Gaussian: spectrum logspace(2,-1), random rotation."""
-    from scipy.stats import ortho_group
-    if D == 2:
-        return scg2_cov()
-    R = ortho_group.rvs(D, random_state=seed)
-    return R.T @ np.diag(np.logspace(2, -1, D)) @ R
+def oracle_energy(P):
+    """The oracle's Energy for a synthetic problem: built from the SAME numbers the product's distribution holds."""
+    g = P.dist
+    if P.kind == "gaussian":
+        return O.GaussianEnergy(np.asarray(g.mu, dtype=np.float32), g.i_sigma.astype(np.float32))
+    if P.kind == "gmm":
+        return O.GMMEnergy(g.mus, g.i_sigmas, g.constants)
+    if P.kind == "roughwell":
+        return O.RoughWellEnergy(g.eps, g.easy)
+    if P.kind == "funnel":
+        return O.FunnelEnergy(g.sigma, g.clip)
+    raise ValueError(P.kind)
 
 
 def target(kind, D, **kw):
     """Returns (product distribution object, oracle Energy, x0 sampler(n, rng))."""
-    from l2hmc_b200 import distributions as dist
-    if kind == "gaussian":
-        cov = scg_cov(D, kw.get("seed", 0))
-        mu = np.asarray(kw.get("mu", np.zeros(D)), dtype=np.float64)
-        g = dist.Gaussian(mu, cov)
-        en = O.GaussianEnergy(mu.astype(np.float32), g.i_sigma.astype(np.float32))
-        L = np.linalg.cholesky(cov)
-        return g, en, (lambda n, rng: (rng.standard_normal((n, D)) @ L.T + mu).astype(np.float32))
-    if kind == "gmm":
-        var = kw.get("var", 0.1)
-        mus = [np.array([-2.0, 0.0] + [0.0] * (D - 2)), np.array([2.0, 0.0] + [0.0] * (D - 2))]
-        sig = [var * np.eye(D), var * np.eye(D)]
-        g = dist.GMM(mus, sig, [0.5, 0.5])
-        en = O.GMMEnergy(mus, g.i_sigmas, g.constants)
-
-        def x0(n, rng):
-            c = rng.integers(0, 2, n)
-            return (np.stack(mus)[c] + np.sqrt(var) * rng.standard_normal((n, D))).astype(np.float32)
-        return g, en, x0
-    if kind == "roughwell":
-        g = dist.RoughWell(D, kw.get("eps", 0.1), easy=kw.get("easy", False))
-        en = O.RoughWellEnergy(g.eps, g.easy)
-        return g, en, (lambda n, rng: rng.standard_normal((n, D)).astype(np.float32))
-    if kind == "funnel":
-        g = dist.GaussianFunnel(dim=D)
-        en = O.FunnelEnergy(g.sigma, g.clip)
-
-        def x0(n, rng):
-            x = rng.standard_normal((n, D)).astype(np.float32)
-            x[:, 0] *= 2.0
-            return x
-        return g, en, x0
-    raise ValueError(kind)
+    g, x0 = S.target(kind, D, **kw)
+    P = type("T", (), {"kind": kind, "dist": g})
+    return g, oracle_energy(P), x0
 
 
 # ---- problems ---------------------------------------------------------------------------------------
-class Problem:
-    """One synthetic configuration: weights, masks, target; builds the oracle and the product object."""
+class Problem(S.SyntheticProblem):
+    """One synthetic configuration (l2hmc_b200/synthetic.py: weights, masks, target, product object) plus the oracle's
+    view of the same arrays."""
 
-    def __init__(self, kind="gaussian", D=2, H=10, T=10, eps=0.1, regime="init", hmc=False, seed=0, **kw):
-        self.kind, self.D, self.H, self.T, self.eps, self.hmc = kind, D, H, T, eps, hmc
-        rng = np.random.default_rng(seed)
-        self.dist, self.energy, self.x0 = target(kind, D, **kw)
-        self.mask = O.make_masks(rng, T, D)
-        self.xnet = None if hmc else O.make_net(rng, D, H, 2.0, regime)
-        self.vnet = None if hmc else O.make_net(rng, D, H, 1.0, regime)
-        self.rng = rng
+    def __init__(self, *a, **kw):
+        super().__init__(*a, **kw)
+        self.energy = oracle_energy(self)
 
     def oracle(self, dtype=torch.float64, temperature=1.0):
         return O.OracleDynamics(self.D, self.T, self.eps, self.energy, self.mask, self.xnet, self.vnet,
                                 hmc=self.hmc, temperature=temperature, dtype=dtype)
 
-    def net_factory(self):
-        from l2hmc_b200.layers import Linear, Sequential, Zip, Parallel, ScaleTanh, relu, load_stq_net
-        H = self.H
-        params = {"XNet": self.xnet, "VNet": self.vnet}
 
-        def network(x_dim, scope, factor):  # SCGExperiment.ipynb:51-77 with width H
-            net = Sequential([
-                Zip([
-                    Linear(x_dim, H, scope='embed_1', factor=1.0 / 3),
-                    Linear(x_dim, H, scope='embed_2', factor=factor * 1.0 / 3),
-                    Linear(2, H, scope='embed_3', factor=1.0 / 3),
-                    lambda _: 0.,
-                ]),
-                sum,
-                relu,
-                Linear(H, H, scope='linear_1'),
-                relu,
-                Parallel([
-                    Sequential([Linear(H, x_dim, scope='linear_s', factor=0.001), ScaleTanh(x_dim, scope='scale_s')]),
-                    Linear(H, x_dim, scope='linear_t', factor=0.001),
-                    Sequential([Linear(H, x_dim, scope='linear_f', factor=0.001), ScaleTanh(x_dim, scope='scale_f')]),
-                ])
-            ])
-            load_stq_net(net, params[scope])
-            return net
-        return network
-
-    def product(self, **kw):
-        from l2hmc_b200 import Dynamics
-        d = Dynamics(self.D, self.dist.get_energy_function(), T=self.T, eps=self.eps, hmc=self.hmc,
-                     net_factory=None if self.hmc else self.net_factory(), **kw)
-        d.mask = self.mask
-        return d
-
-    def draws(self, n, seed=1):
-        rng = np.random.default_rng(seed)
-        return {
-            "x": self.x0(n, rng),
-            "v_f": rng.standard_normal((n, self.D)).astype(np.float32),
-            "v_b": rng.standard_normal((n, self.D)).astype(np.float32),
-            "dir": rng.integers(0, 2, n).astype(np.uint8),
-            "u": rng.random(n).astype(np.float32),
-        }
-
-
-class VaeProblem:
-    """BASELINE config 5 in miniature or at full layer sizes: the decoder-Bernoulli posterior target of
-    mnist_vae.py:104-126 with S/T/Q nets that add a shared softplus-MLP encoding of aux to their first stage
-    (mnist_vae.py:134-167).  Random weights, Bernoulli(0.5) aux rows (no dataset here)."""
-    hmc = False
-
-    def __init__(self, D=8, H=24, T=4, eps=0.1, dec=(64, 64), aux_dim=40, enc=(32, 32), regime="stress", seed=0,
-                 use_encoder=True):
-        self.kind, self.D, self.H, self.T, self.eps = "decoder", D, H, T, eps
-        rng = np.random.default_rng(seed)
-        self.aux_dim = aux_dim
-        self.dec_w = [D] + list(dec) + [aux_dim]
-        self.dec_W, self.dec_b = O.make_softplus_mlp(rng, self.dec_w, last_factor=0.01)
-        self.use_encoder = use_encoder
-        if use_encoder:
-            self.enc_w = [aux_dim] + list(enc) + [H]
-            self.enc_W, self.enc_b = O.make_softplus_mlp(rng, self.enc_w)
-        self.mask = O.make_masks(rng, T, D)
-        self.xnet = O.make_net(rng, D, H, 2.0, regime)
-        self.vnet = O.make_net(rng, D, H, 1.0, regime)
+class VaeProblem(S.SyntheticVaeProblem):
+    """BASELINE config 5 (l2hmc_b200/synthetic.py) plus the oracle's view of the same arrays."""
 
     def oracle_for(self, d, dtype=torch.float64, temperature=1.0):
         en = O.DecoderBernoulliEnergy(self.dec_W, self.dec_b, d["aux"], dtype)
@@ -159,66 +67,6 @@ class VaeProblem:
             tt = lambda a: torch.as_tensor(np.asarray(a)).to(dtype)  # noqa: E731
             ae = O.softplus_mlp([tt(W) for W in self.enc_W], [tt(b) for b in self.enc_b], tt(d["aux"]))
         return dyn, ae
-
-    @staticmethod
-    def _mlp(widths, Ws, bs, scope):
-        from l2hmc_b200.layers import Linear, Sequential, softplus
-        layers = []
-        for i in range(len(Ws)):
-            l = Linear(widths[i], widths[i + 1], scope="%s_%d" % (scope, i + 1))
-            l.W = torch.as_tensor(Ws[i]).clone()
-            l.b = torch.as_tensor(bs[i]).clone()
-            layers.append(l)
-            if i + 1 < len(Ws):
-                layers.append(softplus)
-        return Sequential(layers)
-
-    def net_factory(self):
-        from l2hmc_b200.layers import Linear, Sequential, Zip, Parallel, ScaleTanh, relu, load_stq_net
-        H = self.H
-        params = {"XNet": self.xnet, "VNet": self.vnet}
-        encoder_sampler = self._mlp(self.enc_w, self.enc_W, self.enc_b, "encoder") if self.use_encoder else (lambda _: 0.)
-
-        def net_factory(x_dim, scope, factor):  # mnist_vae.py:142-167
-            net = Sequential([
-                Zip([
-                    Linear(x_dim, H, scope='embed_1', factor=0.33),
-                    Linear(x_dim, H, scope='embed_2', factor=factor * 0.33),
-                    Linear(2, H, scope='embed_3', factor=0.33),
-                    encoder_sampler,
-                ]),
-                sum,
-                relu,
-                Linear(H, H, scope='linear_1'),
-                relu,
-                Parallel([
-                    Sequential([Linear(H, x_dim, scope='linear_s', factor=0.01), ScaleTanh(x_dim, scope='scale_s')]),
-                    Linear(H, x_dim, scope='linear_t', factor=0.01),
-                    Sequential([Linear(H, x_dim, scope='linear_f', factor=0.01), ScaleTanh(x_dim, scope='scale_f')]),
-                ])
-            ])
-            load_stq_net(net, params[scope])
-            return net
-        return net_factory
-
-    def product(self, **kw):
-        from l2hmc_b200 import Dynamics
-        from l2hmc_b200.vae import DecoderEnergy
-        energy = DecoderEnergy(self._mlp(self.dec_w, self.dec_W, self.dec_b, "decoder"))
-        d = Dynamics(self.D, energy, T=self.T, eps=self.eps, net_factory=self.net_factory(), **kw)
-        d.mask = self.mask
-        return d
-
-    def draws(self, n, seed=1):
-        rng = np.random.default_rng(seed)
-        return {
-            "x": rng.standard_normal((n, self.D)).astype(np.float32),  # latent prior, like init_x = latent_q
-            "aux": (rng.random((n, self.aux_dim)) < 0.5).astype(np.float32),
-            "v_f": rng.standard_normal((n, self.D)).astype(np.float32),
-            "v_b": rng.standard_normal((n, self.D)).astype(np.float32),
-            "dir": rng.integers(0, 2, n).astype(np.uint8),
-            "u": rng.random(n).astype(np.float32),
-        }
 
 
 def vae_weight_checksum(P):
@@ -233,13 +81,7 @@ def vae_weight_checksum(P):
     return tot
 
 
-VAE_CONFIGS = {
-    "c5_vae_mini": dict(D=8, H=24, T=4, dec=(64, 64), aux_dim=40, enc=(32, 32)),
-    "c5_vae_ragged": dict(D=7, H=21, T=3, dec=(33,), aux_dim=19, enc=(10,)),   # nothing a multiple of 8
-    "c5_vae_noenc": dict(D=8, H=24, T=4, dec=(64, 64), aux_dim=40, use_encoder=False),
-    # the layer sizes of mnist_vae.py: latent 50, decoder 1024-1024-784, encoder 512-512-200, nets 200 wide, Lf=15
-    "c5_vae_full": dict(D=50, H=200, T=15, dec=(1024, 1024), aux_dim=784, enc=(512, 512)),
-}
+VAE_CONFIGS = S.VAE_CONFIGS
 
 
 def t64(a):
@@ -253,18 +95,7 @@ def max_rel(a, b):
     return float(np.max(np.abs(a - b)) / max(1.0, float(np.max(np.abs(b)))))
 
 
-CONFIGS = {
-    # name: Problem kwargs  (BASELINE.json configs, reduced where noted by the tests)
-    "c1_scg2": dict(kind="gaussian", D=2, H=10, T=10, eps=0.1),
-    "c2_scg50": dict(kind="gaussian", D=50, H=100, T=10, eps=0.1),
-    "c3_mog2": dict(kind="gmm", D=2, H=10, T=25, eps=0.1),
-    "c4_rw32": dict(kind="roughwell", D=32, H=100, T=10, eps=0.1, easy=True),
-    # easy=False has curvature 1/eps_rw^3 = 1000: leapfrog is only stable below ~0.06, and at step 0.1
-    # trajectories are chaotic (fp32 and fp64 oracles differ by O(1), accept prob 0), so the hard
-    # variant is exercised at step 0.01 where parity is meaningful.
-    "c4_rw32_hard": dict(kind="roughwell", D=32, H=100, T=10, eps=0.01, easy=False),
-    "funnel3": dict(kind="funnel", D=3, H=10, T=10, eps=0.1),
-}
+CONFIGS = S.CONFIGS  # BASELINE.json configs, reduced where noted by the tests
 
 
 # ---- parity measurement (GPU) ------------------------------------------------------------------------
