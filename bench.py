@@ -347,7 +347,16 @@ def other_config(runner, name, peaks, quick):
     if vae:
         P.x0 = lambda n, rng: rng.standard_normal((n, P.D)).astype(np.float32)   # latent prior, like init_x = latent_q
         aux = torch.as_tensor((np.random.default_rng(7 + rank).random((n_local, P.aux_dim)) < 0.5).astype(np.float32)).to(dev)
-    r = runner.run(P, n_local, lo, steps, 3, aux=aux, gather_total=n_total if sharded else None)
+    # long enough a timed region for the 50 ms clock sampler to see it (>= ~0.4 s): calibrate on a few steps first
+    cal = runner.run(P, n_local, lo, 2, 3, aux=aux, gather_total=None)
+    per = max(cal["ms"] / 2.0, 1e-3)
+    steps = int(min(20000, max(steps, np.ceil((150.0 if quick else 400.0) / per))))
+    if world > 1:  # every rank must time the same number of steps
+        import torch.distributed as dist
+        t = torch.tensor([steps], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        steps = int(t[0])
+    r = runner.run(P, n_local, lo, steps, 3, aux=aux, gather_total=n_total if sharded else None, dyn=cal["dyn"])
     value = n_total * P.T * steps / (r["ms"] * 1e-3)
     flops = n_local * P.T * flop_step(P.D, P.H, G)
     kernel = r["kernel"]
