@@ -110,6 +110,10 @@ __device__ __forceinline__ void compute_bar_n() { asm volatile("bar.sync 1, %0;"
 #ifndef L2HMC_TC_SLEEP_NS
 #define L2HMC_TC_SLEEP_NS 64
 #endif
+#ifndef L2HMC_TC_PRODUCER_SLEEP_NS
+#define L2HMC_TC_PRODUCER_SLEEP_NS 64
+#endif
+template <int NS = L2HMC_TC_SLEEP_NS>
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
   uint32_t done = 0;
   const uint32_t bar_u32 = smem_u32(bar);
@@ -124,9 +128,7 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) 
         : "r"(bar_u32), "r"(parity)
         : "memory");
     if (done) break;
-#if L2HMC_TC_SLEEP_NS > 0
-    __nanosleep(L2HMC_TC_SLEEP_NS);
-#endif
+    if (NS > 0) __nanosleep(NS);
   }
 }
 

@@ -49,6 +49,12 @@ constexpr uint32_t S_AHI = 0, S_ALO = 104, S_R1 = 208, S_R2 = 320, S_R3 = 432;
 // (profiles/r01_tc_probe.txt: 14 / 28 / 56 B/cycle for 8 / 16 / 32 KB), so the B stream (33 B/cycle per SM once every
 // GEMM overlaps an epilogue) wants few large copies; the A operand is still handed over per slot of 16 k.
 constexpr int KSLOT_S = L2HMC_TC_KSLOT_S;
+#ifndef L2HMC_TC_F32X2
+#define L2HMC_TC_F32X2 1  // packed fp32 arithmetic (FFMA2 / FMUL2 / FADD2) in the epilogues
+#endif
+#ifndef L2HMC_TC_SETMAXNREG
+#define L2HMC_TC_SETMAXNREG (L2HMC_TC_S_NQ > 2)  // the last warpgroup (MMA issuer, TMA producer, two idle warps) hands registers to the compute warpgroups
+#endif
 static_assert(KSLOT_S % 2 == 0, "ring slot = whole A hand-over slots");
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
@@ -73,8 +79,8 @@ __host__ __device__ inline TcLayS make_tclay_s(int RS, int DP, int T) {
   l.su = l.h0 + MT;
   l.sdir = l.su + MT;
   l.sacc = l.sdir + MT;
-  l.part = l.sacc + MT;                      // [2][MT]: partial Hamiltonian, then partial log|J| (one after the other)
-  l.hcs = l.part + 2 * MT;                    // [2 nets][DP/4][HCS_PER_CHUNK]
+  l.part = l.sacc + MT;                      // [4][MT]: partial Hamiltonian, then partial log|J| (one after the other), per thread group
+  l.hcs = l.part + 4 * MT;                    // [2 nets][DP/4][HCS_PER_CHUNK]
   l.ring = (l.hcs + 2 * (DP / 4) * HCS_PER_CHUNK + 31) & ~31;  // 128-byte aligned
   return l;
 }
@@ -127,9 +133,17 @@ __device__ __forceinline__ void put_a(uint32_t lane_base, int k0, const float (&
   static_assert(N == 4 || N == 8, "4 or 8 values");
   float hi[N], lo[N];
 #pragma unroll
-  for (int j = 0; j < N; ++j) {
+  for (int j = 0; j < N; j += 2) {
     hi[j] = __uint_as_float(__float_as_uint(a[j]) & 0xFFFFE000u);
+    hi[j + 1] = __uint_as_float(__float_as_uint(a[j + 1]) & 0xFFFFE000u);
+#if L2HMC_TC_F32X2
+    const float2 l2 = __fadd2_rn(make_float2(a[j], a[j + 1]), make_float2(-hi[j], -hi[j + 1]));  // exact: one FADD2 for two residuals
+    lo[j] = l2.x;
+    lo[j + 1] = l2.y;
+#else
     lo[j] = a[j] - hi[j];
+    lo[j + 1] = a[j + 1] - hi[j + 1];
+#endif
   }
   if (F16) {
     uint32_t h2[N / 2], l2[N / 2];
@@ -226,7 +240,7 @@ __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, 
 #pragma unroll 1
     for (int ks = 0; ks < g.nsteps; ks += KSLOT_S) {
       const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT_S, g.nsteps - ks);
-      mbar_wait_sleep(&S.empty[s], ph);
+      mbar_wait_sleep<L2HMC_TC_PRODUCER_SLEEP_NS>(&S.empty[s], ph);  // the producer waits 97 % of the time and shares a scheduler with two compute warps
       if (elect_one()) {
         mbar_arrive_expect_tx(&S.full[s], bytes);
         const int nk = min(KSLOT_S, g.nsteps - ks);
@@ -290,9 +304,11 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
           // tf32 (K step = 8 k): slot = 2 K steps, grad 1.  fp16 (K step = 16 k): slot = 1 K step, grad: 2 slots.
           bool need;
           int sub;
+          int sub0 = -1;  // fp16 grad: a K step (16 k) is FOUR x - mu chunks = two K slots, owned by different thread groups
           if (F16) {
             need = true;
             sub = grad ? min(2 * (ks + kk) + 1, nsub - 1) : ks + kk;
+            if (grad) sub0 = min(2 * (ks + kk), nsub - 1);
           } else {
             need = grad || (kk & 1) == 0;
             sub = grad ? ks + kk : (ks + kk) >> 1;
@@ -301,6 +317,7 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
             t0 = clock64();
 #endif
+            if (sub0 >= 0) mbar_wait(&a_sub[sub0], par);
             mbar_wait(&a_sub[sub], par);
             tcgen05_fence_after();
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
@@ -360,9 +377,34 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 // what the heads epilogue prepares for the GEMM that follows it
 enum { NEXT_NONE = 0, NEXT_X1 = 1, NEXT_X2 = 2, NEXT_G = 3, NEXT_V = 4 };
 
+// Register budget per warp role (setmaxnreg): the CTA is launched with 12 warps = 3 warpgroups at the compile-time count
+// (<= 168: three warps share one scheduler's 16 K registers); warpgroup 2 (MMA issuer, TMA producer, two idle warps) gives
+// registers back and the two compute warpgroups take them: per scheduler 2 x 232 + 40 <= 512 registers per lane.
+#ifndef L2HMC_TC_REGS_COMPUTE
+#define L2HMC_TC_REGS_COMPUTE (L2HMC_TC_S_NQ == 3 ? 152 : 232)  // per scheduler: NQ x compute + 40 <= 512 registers per lane
+#endif
+#ifndef L2HMC_TC_REGS_AUX
+#define L2HMC_TC_REGS_AUX 40
+#endif
+// compute threads per chain: the chunks of a chain's epilogue are dealt round-robin to NQ_S threads (warp w, lane l: chain
+// 32 (w % 4) + l, chunks q = w / 4, w / 4 + NQ_S, ...).  The epilogues sit on the critical path (GEMM k+1 follows epilogue k
+// slot by slot).  3 threads per chain (12 compute warps, registers rebalanced with setmaxnreg) were expected to shorten each
+// epilogue by ~30 %; measured, the kernel got 2 % SLOWER: the epilogues are bound by what the SM can issue to its fp32 / alu
+// pipes in total, not by per-thread latency -- so the lever is fewer instructions (packed FFMA2 / FMUL2 / FADD2, no dead adds).
+#ifndef L2HMC_TC_S_NQ
+#define L2HMC_TC_S_NQ 2   // measured on config 2 (profiles/r02_tc_s_experiments.txt): 2 -> 2.95 ms, 3 (with setmaxnreg) -> 3.02 ms
+#endif
+constexpr int NQ_S = L2HMC_TC_S_NQ;
+constexpr int TC_S_THREADS = L2HMC_TC_SETMAXNREG ? MT * NQ_S + 128 : MT * NQ_S + 64;
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+
 template <int NQC, int NHC, bool FAST, bool BIASG, bool F16>
-__global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const __grid_constant__ TcArgs A) {
-  constexpr int NCT = MT * 2;  // compute threads: 2 per chain
+__global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const __grid_constant__ TcArgs A) {
+  constexpr int NQ = NQ_S;
+  constexpr int NCT = MT * NQ;  // compute threads: NQ per chain
   constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
   constexpr int DP = SDims<NQC>::DP, RS = SDims<NQC>::RS;
   constexpr int NSUB = ((NQC > NHC ? NQC : NHC) + 1) / 2;  // K slots (2 K steps) of the deepest GEMM = sub-barriers
@@ -394,7 +436,8 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       mbar_init(&S.empty[s], 1);
     }
     mbar_init(S.a_ready, 1);  // unused here (a_sub instead)
-    for (int p = 0; p < NSUB_MAX; ++p) mbar_init(&a_sub[p], NCT / 32);  // one arrival per compute warp
+    // K slot p = the chunks 2p and 2p + 1 (16 k of the operand): one arrival per warp of their two owner groups
+    for (int p = 0; p < NSUB_MAX; ++p) mbar_init(&a_sub[p], 8);
     mbar_init(S.acc_ready, 1);  // unused here (acc_rdy instead)
     mbar_init(&acc_rdy[0], 1);
     mbar_init(&acc_rdy[1], 1);
@@ -407,19 +450,20 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
   const uint32_t tmem = tmem_slot;
   if (tmem != 0u) __trap();  // this CTA owns all 512 columns: column / lane 0 is a constant in the issuer and below
 
-  if (warp == W_TMA) {
-    producer_loop_s<NQC, F16>(A, S, ring, NSLOT, SLOT_FLOATS);
-  } else if (warp == W_MMA) {
-    issuer_loop_s<NQC, F16>(A, S, a_sub, acc_rdy, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
+  if (warp >= W_MMA) {
+    if (L2HMC_TC_SETMAXNREG) reg_dec<L2HMC_TC_REGS_AUX>();  // the whole third warpgroup (two of its warps have nothing else to do)
+    if (warp == W_TMA) producer_loop_s<NQC, F16>(A, S, ring, NSLOT, SLOT_FLOATS);
+    else if (warp == W_MMA) issuer_loop_s<NQC, F16>(A, S, a_sub, acc_rdy, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
   } else {
     // ===================== compute warps =====================
+    if (L2HMC_TC_SETMAXNREG) reg_inc<L2HMC_TC_REGS_COMPUTE>();
     using I0 = std::integral_constant<int, 0>;
     using I1 = std::integral_constant<int, 1>;
     const int c = 32 * (warp & 3) + lane;  // chain within the tile == TMEM lane
-    const int qd = warp >> 2;              // 0 / 1: this thread owns the chunks q = qd, qd + 2, ... (warp-uniform)
+    const int qd = warp >> 2;              // 0 .. NQ-1: this thread owns the chunks q = qd, qd + NQ, ... (warp-uniform)
     const uint32_t lb = ((uint32_t)(32 * (warp & 3))) << 16;
-    const int qn = (NQC - qd + 1) / 2;     // its 4-dim chunks: q = qd + 2 i, i < qn
-    const int hn = (NHC - qd + 1) / 2;     // its 8-column hidden chunks: q = qd + 2 i, i < hn
+    const int qn = (NQC - qd + NQ - 1) / NQ;  // its 4-dim chunks: q = qd + NQ i, i < qn
+    const int hn = (NHC - qd + NQ - 1) / NQ;  // its 8-column hidden chunks: q = qd + NQ i, i < hn
     const long long gch = base + c;
     const bool gauss = A.en.kind == 0;
     float *xr = smem + L.xs + c * RS, *vr = smem + L.vs + c * RS, *gr = smem + L.gs + c * RS;
@@ -440,21 +484,24 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       ++gi;
       tcgen05_fence_after();
     };
-    // K slot p of the next A operand is complete for this warp's chains: every thread's tcgen05.st has landed, one
-    // arrival per warp
-    auto slot_done = [&](int p) {
+    // chunk q of the next A operand is complete for this warp's chains: every thread's tcgen05.st has landed, one
+    // arrival per warp on the chunk's K slot
+    auto slot_done = [&](int q) {
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&a_sub[p]);
+      if (lane == 0) mbar_arrive(&a_sub[q >> 1]);
     };
-    // ... and every K slot from `from` on (chunks this warp does not own, or an operand that is handed over whole)
+    // ... and the arrivals this warp owes for chunks it would own but that do not exist / are handed over whole: every
+    // chunk index c >= from with c % NQ == qd, up to the last K slot (each slot is armed for two arrivals per lane quarter)
     auto a_done = [&](int from) {
       tmem_wait_st();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0)
-        for (int p = from; p < NSUB; ++p) mbar_arrive(&a_sub[p]);
+      if (lane == 0) {
+        int c = from + ((qd - from) % NQ + NQ) % NQ;  // first index >= from owned by this thread group
+        for (; c < 2 * NSUB; c += NQ) mbar_arrive(&a_sub[c >> 1]);
+      }
     };
     const float eps = sh.eps, Tm = A.en.temperature, rTm = 1.f / A.en.temperature;
     float amax = 0.f;  // F16: largest |value| this thread put into an A operand
@@ -462,7 +509,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       // TMEM is not cleared by the allocation: K tails of the A operand that no epilogue writes (k >= 8 NHC of the
       // embed / hidden operands, the grad GEMM's tail before the first net call) must not hold NaN / Inf patterns
       const uint32_t z4[4] = {0u, 0u, 0u, 0u};
-      for (int cq = qd; cq < 14; cq += 2) {
+      for (int cq = qd; cq < 14; cq += NQ) {
         tmem_st4u(S_AHI + lb + 4 * cq, z4);
         tmem_st4u(S_ALO + lb + 4 * cq, z4);
       }
@@ -497,7 +544,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       } else {
 #pragma unroll 1
         for (int i = 0; i < qn; ++i) {
-          const int q = qd + 2 * i;
+          const int q = qd + NQ * i;
           float z[4];
           philox_normals4(io.seed, ctr, io.chain_offset + gch, q, z);
 #pragma unroll
@@ -541,7 +588,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         put_a<F16, 4>(lb, 4 * q, a, amax);
       };
       auto zero_gtail = [&]() {  // KG = DP rounded to 8: one more 4-column chunk of zeros when NQC is odd
-        if (!F16 && (NQC & 1) && qd == 1) {  // fp16: the K tail holds finite values of earlier operands, its B rows are 0
+        if (!F16 && (NQC & 1) && qd == NQC % NQ) {  // fp16: the K tail holds finite values of earlier operands, its B rows are 0
           const float z[4] = {0.f, 0.f, 0.f, 0.f};
           put_a<F16, 4>(lb, DP, z, amax);
         }
@@ -573,7 +620,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         float U = 0.f, K = 0.f;
 #pragma unroll 1
         for (int i = 0; i < qn; ++i) {
-          const int q = qd + 2 * i;
+          const int q = qd + NQ * i;
           float g4[4];
           tmem_ld4(lb + acc + 4 * q, g4);
           const float4 xv = lds4(xr + 4 * q);
@@ -588,9 +635,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             ham_chunk(x4, v4, g4, q, U, K);
           }
           put_ab(q, x4, g4);
-          slot_done(i);
+          slot_done(q);
         }
-        a_done(qn);
+        a_done(NQC);
         Hpart = (gauss ? 0.5f * U : U) + 0.5f * K;
       };
       // start of a transition: grad U(x), H(x, v) partial, first V-net input
@@ -598,20 +645,20 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         if (gauss) {
 #pragma unroll 1
           for (int i = 0; i < qn; ++i) {
-            const int q = qd + 2 * i;
+            const int q = qd + NQ * i;
             const float4 xv = lds4(xr + 4 * q);
             const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
             put_xmu(q, x4);
-            slot_done(i);
+            slot_done(q);
           }
           zero_gtail();
-          a_done(qn);
+          a_done(NQC);
           grad_epilogue(S_R2, true, Hpart);
         } else {
           float U = 0.f, K = 0.f;
 #pragma unroll 1
           for (int i = 0; i < qn; ++i) {
-            const int q = qd + 2 * i;
+            const int q = qd + NQ * i;
             const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q);
             const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
             float g4[4];
@@ -619,9 +666,9 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
             sts4(gr + 4 * q, g4);
             ham_chunk(x4, v4, g4, q, U, K);
             put_ab(q, x4, g4);
-            slot_done(i);
+            slot_done(q);
           }
-          a_done(qn);
+          a_done(NQC);
           Hpart = U + 0.5f * K;
         }
       };
@@ -630,7 +677,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         float U = 0.f, K = 0.f;
 #pragma unroll 1
         for (int i = 0; i < qn; ++i) {
-          const int q = qd + 2 * i;
+          const int q = qd + NQ * i;
           const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), gv = lds4(gr + 4 * q);
           const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w}, g4[4] = {gv.x, gv.y, gv.z, gv.w};
           ham_chunk(x4, v4, g4, q, U, K);
@@ -644,22 +691,28 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       auto hidden_epilogue = [&](uint32_t acc, const float *__restrict__ bias, bool handover) {
         wait_acc();
         float h[2][8];
-        tmem_ld8(lb + acc + 8 * qd, h[0]);
+        if (hn > 0) tmem_ld8(lb + acc + 8 * qd, h[0]);
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
-          const int q = qd + 2 * i;
+          const int q = qd + NQ * i;
           float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
           if (!BIASG) {  // BIASG: the bias is a weight row that meets a constant-1 column of the A operand
             b0 = ldg4(bias + 8 * q);
             b1 = ldg4(bias + 8 * q + 4);
           }
           tmem_wait_ld();
-          if (i + 1 < hn) tmem_ld8(lb + acc + 8 * (q + 2), h[B ^ 1]);
+          if (i + 1 < hn) tmem_ld8(lb + acc + 8 * (q + NQ), h[B ^ 1]);
           const float(&hh)[8] = h[B];
-          const float a[8] = {fmaxf(hh[0] + b0.x, 0.f), fmaxf(hh[1] + b0.y, 0.f), fmaxf(hh[2] + b0.z, 0.f), fmaxf(hh[3] + b0.w, 0.f),
-                              fmaxf(hh[4] + b1.x, 0.f), fmaxf(hh[5] + b1.y, 0.f), fmaxf(hh[6] + b1.z, 0.f), fmaxf(hh[7] + b1.w, 0.f)};
+          float a[8];
+          if (BIASG) {  // no `+ 0.f`: the compiler must keep that add (it turns -0 into +0)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaxf(hh[j], 0.f);
+          } else {
+            a[0] = fmaxf(hh[0] + b0.x, 0.f); a[1] = fmaxf(hh[1] + b0.y, 0.f); a[2] = fmaxf(hh[2] + b0.z, 0.f); a[3] = fmaxf(hh[3] + b0.w, 0.f);
+            a[4] = fmaxf(hh[4] + b1.x, 0.f); a[5] = fmaxf(hh[5] + b1.y, 0.f); a[6] = fmaxf(hh[6] + b1.z, 0.f); a[7] = fmaxf(hh[7] + b1.w, 0.f);
+          }
           put_a<F16, 8>(lb, 8 * q, a, amax);
-          if (handover) slot_done(i);
+          if (handover) slot_done(q);
         };
         // two chunks per iteration (the register double buffer needs static names); rolled: the fully unrolled
         // version of this kernel had a 178 KB loop body and spent 40 % of the epilogue time on instruction fetch
@@ -668,7 +721,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
           chunk(i, I0{});
           if (i + 1 < hn) chunk(i + 1, I1{});
         }
-        a_done(handover ? hn : 0);
+        a_done(handover ? NHC : 0);
       };
 
       // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) + next A operand --------------
@@ -690,7 +743,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
               b[j] = nx1 ? (fwd ? m4[j] : 1.f - m4[j]) * x4[j] : g4[j];
             }
             put_ab(q, a, b);
-            slot_done(i);
+            slot_done(q);
           }
         } else {
           if (next == NEXT_X2) {  // X net, second half: its k is this half's 1 - k
@@ -699,16 +752,16 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
 #pragma unroll
             for (int j = 0; j < 4; ++j) b[j] = (flip ? m4[j] : 1.f - m4[j]) * x4[j];
             put_ab(q, v4, b);
-            slot_done(i);
+            slot_done(q);
           } else if (gauss) {  // NEXT_G: grad U at the new x (K step i of the grad GEMM = the chunks i of both threads)
             put_xmu(q, x4);
-            slot_done(i);
+            slot_done(q);
           } else {
             float g[4];
             roughwell_grad(q, x4, g);
             sts4(gr + 4 * q, g);
             put_ab(q, x4, g);
-            slot_done(i);
+            slot_done(q);
           }
         }
       };
@@ -723,89 +776,162 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         const float hc = MODE == 0 ? 0.5f * eps : eps;
         const float *hcs_net = smem + L.hcs + (MODE == 0 ? NQC * HCS_PER_CHUNK : 0);  // V net (MODE 0) second
         const bool flip = (fwd != (xh == 0));  // MODE 1: k = m, or 1 - m when flipped
-        const int na = (CA - qd + 1) / 2;      // this thread's chunks in part 0: i < na
+        const int na = qd < CA ? (CA - qd + NQ - 1) / NQ : 0;  // this thread's chunks in part 0 (q < CA): i < na
         const int ib = PART == 0 ? 0 : na, ie = PART == 0 ? na : qn;
         wait_acc();
-        float s4[2][4], t4[2][4], q4[2][4];
+        float s4[2][1][4], t4[2][1][4], q4[2][1][4];  // [register buffer][.][dimension]
         if (ib < ie) {
-          const int q = qd + 2 * ib;
-          tmem_ld4(lb + cS + 4 * q, s4[0]);
-          tmem_ld4(lb + cT + 4 * q, t4[0]);
-          tmem_ld4(lb + cQ + 4 * q, q4[0]);
+          const int q = qd + NQ * ib;
+          tmem_ld4(lb + cS + 4 * q, s4[0][0]);
+          tmem_ld4(lb + cT + 4 * q, t4[0][0]);
+          tmem_ld4(lb + cQ + 4 * q, q4[0][0]);
         }
         if (PART == 1 && next != NEXT_NONE) {
 #pragma unroll 1
           for (int i = 0; i < na; ++i) {  // deferred A operand of the part-0 chunks
-            const int q = qd + 2 * i;
+            const int q = qd + NQ * i;
             const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), mv = lds4(mrow + 4 * q), gv = lds4(gr + 4 * q);
             const float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
             const float m4[4] = {mv.x, mv.y, mv.z, mv.w}, g4[4] = {gv.x, gv.y, gv.z, gv.w};
             prep(mode_c, xh, next, q, i, x4, v4, g4, m4);
           }
         }
-        auto chunk = [&](int i, auto buf_c) {
-          constexpr int B = decltype(buf_c)::value;
-          const int q = qd + 2 * i;
+        // inputs of one chunk: head constants, state, mask row, (grad U)
+        struct ChunkIn {
+          float bs2[4], bq2[4], cSc[4], cQc[4], bth[4], x4[4], v4[4], m4[4], g4[4];
+        };
+        auto load_in = [&](int q, ChunkIn &c) {
           const float *hcq = hcs_net + HCS_PER_CHUNK * q;
           const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
           const float4 c_bs = BIASG ? z4 : lds4(hcq), c_bq = BIASG ? z4 : lds4(hcq + 4), c_cs = lds4(hcq + 8), c_cq = lds4(hcq + 12);
           const float4 c_bt = BIASG ? z4 : lds4(hcq + 16);
-          const float bs2[4] = {c_bs.x, c_bs.y, c_bs.z, c_bs.w}, bq2[4] = {c_bq.x, c_bq.y, c_bq.z, c_bq.w};
-          const float cSc[4] = {c_cs.x, c_cs.y, c_cs.z, c_cs.w}, cQc[4] = {c_cq.x, c_cq.y, c_cq.z, c_cq.w};
-          const float bth[4] = {c_bt.x, c_bt.y, c_bt.z, c_bt.w};
+          c.bs2[0] = c_bs.x; c.bs2[1] = c_bs.y; c.bs2[2] = c_bs.z; c.bs2[3] = c_bs.w;
+          c.bq2[0] = c_bq.x; c.bq2[1] = c_bq.y; c.bq2[2] = c_bq.z; c.bq2[3] = c_bq.w;
+          c.cSc[0] = c_cs.x; c.cSc[1] = c_cs.y; c.cSc[2] = c_cs.z; c.cSc[3] = c_cs.w;
+          c.cQc[0] = c_cq.x; c.cQc[1] = c_cq.y; c.cQc[2] = c_cq.z; c.cQc[3] = c_cq.w;
+          c.bth[0] = c_bt.x; c.bth[1] = c_bt.y; c.bth[2] = c_bt.z; c.bth[3] = c_bt.w;
           const float4 xv = lds4(xr + 4 * q), vv = lds4(vr + 4 * q), mv = lds4(mrow + 4 * q);
-          float x4[4] = {xv.x, xv.y, xv.z, xv.w}, v4[4] = {vv.x, vv.y, vv.z, vv.w};
-          const float m4[4] = {mv.x, mv.y, mv.z, mv.w};
-          float g4[4] = {0.f, 0.f, 0.f, 0.f};
+          c.x4[0] = xv.x; c.x4[1] = xv.y; c.x4[2] = xv.z; c.x4[3] = xv.w;
+          c.v4[0] = vv.x; c.v4[1] = vv.y; c.v4[2] = vv.z; c.v4[3] = vv.w;
+          c.m4[0] = mv.x; c.m4[1] = mv.y; c.m4[2] = mv.z; c.m4[3] = mv.w;
+          c.g4[0] = c.g4[1] = c.g4[2] = c.g4[3] = 0.f;
           if (MODE == 0) {
             const float4 gv = lds4(gr + 4 * q);
-            g4[0] = gv.x; g4[1] = gv.y; g4[2] = gv.z; g4[3] = gv.w;
+            c.g4[0] = gv.x; c.g4[1] = gv.y; c.g4[2] = gv.z; c.g4[3] = gv.w;
           }
-          tmem_wait_ld();
-          if (i + 1 < ie) {  // next chunk's accumulators travel while this chunk is processed
-            tmem_ld4(lb + cS + 4 * (q + 2), s4[B ^ 1]);
-            tmem_ld4(lb + cT + 4 * (q + 2), t4[B ^ 1]);
-            tmem_ld4(lb + cQ + 4 * (q + 2), q4[B ^ 1]);
+        };
+        // the update of one chunk (utils/dynamics.py:121-155 / :166-199) from its accumulators sa / ta / qa
+        auto update = [&](ChunkIn &c, const float (&sa)[4], const float (&ta)[4], const float (&qa)[4], float &lj) {
+#if L2HMC_TC_F32X2
+          if (FAST) {
+            // Packed fp32 (FFMA2 / FMUL2 / FADD2, sm_100): the three-register scalar FFMA / FMUL / FADD issue at half rate on
+            // this architecture, and this epilogue is bound by the fp32 pipe (~30 scalar fp32 instructions per dimension,
+            // 66-75 % pipe occupancy measured).  The 4 dimensions of a chunk are independent: two per instruction.  Same
+            // IEEE operations in the same order as the scalar form below (bit-identical per dimension); the selects
+            // w = fwd ? 1 : -e and k = flip ? 1 - m : m become exact FMAs with per-thread constants.
+            const float2 c2l = make_float2(2.f * L2E, 2.f * L2E), one2 = make_float2(1.f, 1.f), m2two = make_float2(-2.f, -2.f);
+            const float2 hc2 = make_float2(hc, hc), sg2 = make_float2(sg, sg);
+            const float2 wa2 = fwd ? make_float2(0.f, 0.f) : make_float2(-1.f, -1.f), wb2 = fwd ? one2 : make_float2(0.f, 0.f);
+            const float2 ka2 = flip ? make_float2(-1.f, -1.f) : one2, kb2 = flip ? one2 : make_float2(0.f, 0.f);
+            float2 lj2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 4; j += 2) {
+              const float2 aS = __ffma2_rn(make_float2(sa[j], sa[j + 1]), c2l, make_float2(c.bs2[j], c.bs2[j + 1]));
+              const float2 aQ = __ffma2_rn(make_float2(qa[j], qa[j + 1]), c2l, make_float2(c.bq2[j], c.bq2[j + 1]));
+              // tanh(z) = 1 - 2 / (e^{2z} + 1); one reciprocal serves both heads (arguments clamped so that the
+              // product of the two denominators stays finite: tanh(19.7) == 1 in fp32)
+              const float2 eS = make_float2(ex2_approx(fminf(aS.x, 57.f)), ex2_approx(fminf(aS.y, 57.f)));
+              const float2 eQ = make_float2(ex2_approx(fminf(aQ.x, 57.f)), ex2_approx(fminf(aQ.y, 57.f)));
+              const float2 dS = __fadd2_rn(eS, one2), dQ = __fadd2_rn(eQ, one2);
+              const float2 den = __fmul2_rn(dS, dQ);
+              const float2 r = make_float2(rcp_approx(den.x), rcp_approx(den.y));
+              const float2 svl = __fmul2_rn(make_float2(c.cSc[j], c.cSc[j + 1]), __ffma2_rn(__fmul2_rn(r, dQ), m2two, one2));  // cS * tanh
+              const float2 fql = __fmul2_rn(make_float2(c.cQc[j], c.cQc[j + 1]), __ffma2_rn(__fmul2_rn(r, dS), m2two, one2));
+              const float2 Tt = __ffma2_rn(make_float2(ta[j], ta[j + 1]), hc2, make_float2(c.bth[j], c.bth[j + 1]));  // h * (t + bt)
+              const float2 eQx = make_float2(ex2_approx(fql.x), ex2_approx(fql.y));
+              const float2 svs = __fmul2_rn(svl, sg2);  // +- (scale * S) * log2(e)
+              const float2 e = make_float2(ex2_approx(svs.x), ex2_approx(svs.y));
+              const float2 w = __ffma2_rn(e, wa2, wb2);  // fwd ? 1 : -e
+              if (MODE == 0) {
+                // fwd: v e + h (T - e^{fq} g) ; bwd: (v - h (T - e^{fq} g)) e
+                const float2 hg = __fmul2_rn(hc2, make_float2(c.g4[j], c.g4[j + 1]));
+                const float2 tmp = __ffma2_rn(make_float2(-eQx.x, -eQx.y), hg, Tt);
+                const float2 v2 = __ffma2_rn(make_float2(c.v4[j], c.v4[j + 1]), e, __fmul2_rn(tmp, w));
+                c.v4[j] = v2.x;
+                c.v4[j + 1] = v2.y;
+                lj2 = __fadd2_rn(lj2, svs);
+              } else {
+                const float2 k = __ffma2_rn(make_float2(c.m4[j], c.m4[j + 1]), ka2, kb2);  // flip ? 1 - m : m
+                const float2 uu = __ffma2_rn(k, make_float2(-1.f, -1.f), one2);           // 1 - k
+                // fwd: x e + h (e^{fq} v + T) ; bwd: e (x - h (e^{fq} v + T))
+                const float2 x2 = make_float2(c.x4[j], c.x4[j + 1]);
+                const float2 inner = __ffma2_rn(eQx, __fmul2_rn(hc2, make_float2(c.v4[j], c.v4[j + 1])), Tt);
+                const float2 nx = __ffma2_rn(x2, e, __fmul2_rn(inner, w));
+                const float2 xo = __ffma2_rn(uu, nx, __fmul2_rn(k, x2));
+                c.x4[j] = xo.x;
+                c.x4[j + 1] = xo.y;
+                lj2 = __ffma2_rn(uu, svs, lj2);
+              }
+            }
+            lj += lj2.x + lj2.y;
+            return;
           }
+#endif
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             float svl, fql;
             if (FAST) {
               // tanh(z) = 1 - 2 / (e^{2z} + 1); one reciprocal serves both heads (arguments clamped so that the
               // product of the two denominators stays finite: tanh(19.7) == 1 in fp32)
-              const float eS = ex2_approx(fminf(fmaf(s4[B][j], 2.f * L2E, bs2[j]), 57.f));
-              const float eQ = ex2_approx(fminf(fmaf(q4[B][j], 2.f * L2E, bq2[j]), 57.f));
+              const float eS = ex2_approx(fminf(fmaf(sa[j], 2.f * L2E, c.bs2[j]), 57.f));
+              const float eQ = ex2_approx(fminf(fmaf(qa[j], 2.f * L2E, c.bq2[j]), 57.f));
               const float dS = eS + 1.f, dQ = eQ + 1.f;
               const float r = rcp_approx(dS * dQ);
-              svl = cSc[j] * fmaf(r * dQ, -2.f, 1.f);  // cS * tanh
-              fql = cQc[j] * fmaf(r * dS, -2.f, 1.f);
+              svl = c.cSc[j] * fmaf(r * dQ, -2.f, 1.f);  // cS * tanh
+              fql = c.cQc[j] * fmaf(r * dS, -2.f, 1.f);
             } else {
-              svl = cSc[j] * tanhf((s4[B][j] * (2.f * L2E) + bs2[j]) * (0.5f * LN2));
-              fql = cQc[j] * tanhf((q4[B][j] * (2.f * L2E) + bq2[j]) * (0.5f * LN2));
+              svl = c.cSc[j] * tanhf((sa[j] * (2.f * L2E) + c.bs2[j]) * (0.5f * LN2));
+              fql = c.cQc[j] * tanhf((qa[j] * (2.f * L2E) + c.bq2[j]) * (0.5f * LN2));
             }
-            const float Tt = fmaf(t4[B][j], hc, bth[j]);  // h * (t + bt)
+            const float Tt = fmaf(ta[j], hc, c.bth[j]);  // h * (t + bt)
             const float eQx = FAST ? ex2_approx(fql) : exp2f(fql);
             const float svs = svl * sg;                     // +- (scale * S) * log2(e)
             const float e = FAST ? ex2_approx(svs) : exp2f(svs);
             const float w = fwd ? 1.f : -e;
             if (MODE == 0) {
               // fwd: v e + h (T - e^{fq} g) ; bwd: (v - h (T - e^{fq} g)) e
-              const float tmp = fmaf(-eQx, hc * g4[j], Tt);
-              v4[j] = fmaf(v4[j], e, tmp * w);
-              ljl += svs;
+              const float tmp = fmaf(-eQx, hc * c.g4[j], Tt);
+              c.v4[j] = fmaf(c.v4[j], e, tmp * w);
+              lj += svs;
             } else {
-              const float k = flip ? 1.f - m4[j] : m4[j];
+              const float k = flip ? 1.f - c.m4[j] : c.m4[j];
               const float uu = 1.f - k;
               // fwd: x e + h (e^{fq} v + T) ; bwd: e (x - h (e^{fq} v + T))
-              const float inner = fmaf(eQx, hc * v4[j], Tt);
-              const float nx = fmaf(x4[j], e, inner * w);
-              x4[j] = k * x4[j] + uu * nx;
-              ljl = fmaf(uu, svs, ljl);
+              const float inner = fmaf(eQx, hc * c.v4[j], Tt);
+              const float nx = fmaf(c.x4[j], e, inner * w);
+              c.x4[j] = k * c.x4[j] + uu * nx;
+              lj = fmaf(uu, svs, lj);
             }
           }
-          if (MODE == 0) sts4(vr + 4 * q, v4);
-          else sts4(xr + 4 * q, x4);
-          if (PART == 1) prep(mode_c, xh, next, q, i, x4, v4, g4, m4);
+        };
+        auto finish = [&](int q, int i, ChunkIn &c) {
+          if (MODE == 0) sts4(vr + 4 * q, c.v4);
+          else sts4(xr + 4 * q, c.x4);
+          if (PART == 1) prep(mode_c, xh, next, q, i, c.x4, c.v4, c.g4, c.m4);
+        };
+        auto chunk = [&](int i, auto buf_c) {
+          constexpr int B = decltype(buf_c)::value;
+          const int q = qd + NQ * i;
+          ChunkIn c;
+          load_in(q, c);
+          tmem_wait_ld();
+          if (i + 1 < ie) {  // next chunk's accumulators travel while this chunk is processed
+            tmem_ld4(lb + cS + 4 * (q + NQ), s4[B ^ 1][0]);
+            tmem_ld4(lb + cT + 4 * (q + NQ), t4[B ^ 1][0]);
+            tmem_ld4(lb + cQ + 4 * (q + NQ), q4[B ^ 1][0]);
+          }
+          update(c, s4[B][0], t4[B][0], q4[B][0], ljl);
+          finish(q, i, c);
         };
 #pragma unroll 1
         for (int i = ib; i < ie; i += 2) {
@@ -814,7 +940,7 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
         }
         if (PART == 1) {
           if (MODE == 1 && next == NEXT_G && gauss) zero_gtail();  // before this warp's arrival on the last K step
-          if (next != NEXT_NONE) a_done(qn);
+          if (next != NEXT_NONE) a_done(NQC);
           else tcgen05_fence_before();
         } else {
           tcgen05_fence_before();
@@ -825,7 +951,12 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       first_grad(hpart0);
       smem[L.part + qd * MT + c] = hpart0;
       compute_bar();
-      if (qd == 0) smem[L.h0 + c] = smem[L.part + c] + smem[L.part + MT + c];
+      if (qd == 0) {
+        float h0s = 0.f;
+#pragma unroll
+        for (int r = 0; r < NQ; ++r) h0s += smem[L.part + r * MT + c];
+        smem[L.h0 + c] = h0s;
+      }
 
 #pragma unroll 1
       for (int it = 0; it < sh.T; ++it) {
@@ -859,13 +990,17 @@ __global__ void __launch_bounds__(MT * 2 + 64, 1) tc_transition_kernel_s(const _
       compute_bar();  // h0 readers are done with `part`
       smem[L.part + qd * MT + c] = final_ham();
       compute_bar();
-      const float h1 = smem[L.part + c] + smem[L.part + MT + c];
+      float h1 = 0.f;
+#pragma unroll
+      for (int r = 0; r < NQ; ++r) h1 += smem[L.part + r * MT + c];
       compute_bar();
       smem[L.part + qd * MT + c] = ljl * LN2;
       compute_bar();
       const bool last = (tr == io.n_transitions - 1);
       if (qd == 0) {
-        const float logj = smem[L.part + c] + smem[L.part + MT + c];
+        float logj = 0.f;
+#pragma unroll
+        for (int r = 0; r < NQ; ++r) logj += smem[L.part + r * MT + c];
         const float p = accept_prob(smem[L.h0 + c], h1, logj);
         const float px = io.log_jac ? logj : p;
         int acc = 0;

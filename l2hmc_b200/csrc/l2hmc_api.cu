@@ -43,14 +43,16 @@ struct LayMlp {  // Linear / softplus stack (decoder of the energy, aux encoder 
   DevBuf buf;
   std::vector<const float *> W, Wt, b;
 };
-struct LayTcWeight {  // one weight matrix pre-split / pre-tiled for tc_gemm_kernel
-  tcg::TcGemmB d;
-  DevBuf buf;
+struct LayTcWeight {  // one weight matrix pre-split / pre-tiled for tc_gemm_kernel: tf32 image, and fp16 image when allowed
+  tcg::TcGemmB d, d16;
+  DevBuf buf, buf16;
+  bool has16 = false;
 };
 struct LayeredCtx {
   layered::LayDims dm;
   bool gemm_tc = true;                             // tcgen05 split GEMMs (false: fp32 FMA sgemm_kernel)
-  bool gemm_f16 = false;                           // fp16 x3 operand split instead of tf32 x3 (L2HMC_LAYERED_GEMM=f16)
+  bool gemm_f16 = true;                            // fp16 x3 operand split (default; L2HMC_LAYERED_GEMM=tf32 keeps tf32 x3)
+  bool used_f16 = false;                           // what the last GEMM launch used
   std::map<const float *, LayTcWeight> tcw;        // keyed by the device pointer of the row-major weight
   int sms = 0;
   DevBuf net_buf[2];
@@ -650,8 +652,8 @@ extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
   lay_setup_dims(ctx);
   {
     const char *gm = getenv("L2HMC_LAYERED_GEMM");  // "fma" forces the fp32 FMA GEMMs
-    if (gm && gm[0] == 'f' && gm[1] == '1') ctx->lay.gemm_f16 = true;  // "f16"
-    else if (gm && gm[0] == 'f') ctx->lay.gemm_tc = false;             // "fma"
+    if (gm && gm[0] == 't') ctx->lay.gemm_f16 = false;                 // "tf32": the tf32 x3 split only
+    else if (gm && gm[0] == 'f' && gm[1] == 'm') ctx->lay.gemm_tc = false;  // "fma"
     cudaDeviceGetAttribute(&ctx->lay.sms, cudaDevAttrMultiProcessorCount, cfg->device);
   }
   int rc = pick_kernel(ctx);
@@ -695,7 +697,10 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
     for (DevBuf &b : L.eact)
       if (b.p) cudaFree(b.p);
     for (auto &kv : L.tcw)
+    {
       if (kv.second.buf.p) cudaFree(kv.second.buf.p);
+      if (kv.second.buf16.p) cudaFree(kv.second.buf16.p);
+    }
     if (L.ws_event) cudaEventDestroy(L.ws_event);
   }
   if (ctx->hdir) cudaFree(ctx->hdir);
@@ -1101,7 +1106,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
 #undef L2HMC_TC_S_ATTR
         tc_s_configured = smem;
       }
-      const unsigned nthreads = (unsigned)(tc::MT * 2 + 64);
+      const unsigned nthreads = (unsigned)tc::TC_S_THREADS;  // 8 compute warps + MMA issuer + TMA producer + 2 idle (whole warpgroups: setmaxnreg)
       const bool fm = ctx->td.fast_math != 0, bg = ctx->td.biasg != 0;
       // fp16 split only when everything packed (weights, biases, time-embedding rows, precision matrix) is well inside
       // the fp16 range; activations are checked by the kernel (sticky flag, l2hmc_debug_counters[23])
@@ -1625,7 +1630,7 @@ extern "C" const char *l2hmc_kernel_name(const l2hmc_ctx *ctx) {
     case L2HMC_KERNEL_TILE: return "tile_fma";
     case L2HMC_KERNEL_SMALL: return "small_fma";
     case L2HMC_KERNEL_TC: return ctx->tc_used_f16 ? "tc_3xf16" : "tc_3xtf32";  // operand split of the last launch
-    case L2HMC_KERNEL_LAYERED: return ctx->lay.gemm_tc ? (ctx->lay.gemm_f16 ? "layered_tc3xf16" : "layered_tc3xtf32") : "layered_fma";
+    case L2HMC_KERNEL_LAYERED: return ctx->lay.gemm_tc ? ((ctx->lay.gemm_f16 && !(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE)) ? "layered_tc3xf16" : "layered_tc3xtf32") : "layered_fma";
     default: return "none";
   }
 }

@@ -27,13 +27,33 @@ inline void lay_setup_dims(l2hmc_ctx *ctx) {
 // Pre-split (tf32 hi / lo) and pre-tile a row-major weight [K][ldb] for tc_gemm_kernel; keyed by its device pointer.
 int lay_tc_register(l2hmc_ctx *ctx, const float *dev_B, const float *host_B, int ldb, int K, int N) {
   LayeredCtx &L = ctx->lay;
-  std::vector<float> pk;
   LayTcWeight &w = L.tcw[dev_B];
-  l2hmc::tcg::pack_b(host_B, ldb, K, N, pk, &w.d, L.gemm_f16);
-  int rc = ensure(ctx, w.buf, pk.size());
-  if (rc) return rc;
-  CUDA_TRY(ctx, cudaMemcpy(w.buf.p, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
-  w.d.pk = w.buf.p;
+  // the tf32 image always (fp32 exponent range); the fp16 image beside it when the fp16 split is enabled and every entry
+  // of this weight is well inside the fp16 range -- lay_gemm picks per launch (status word of the context)
+  {
+    std::vector<float> pk;
+    l2hmc::tcg::pack_b(host_B, ldb, K, N, pk, &w.d, false);
+    int rc = ensure(ctx, w.buf, pk.size());
+    if (rc) return rc;
+    CUDA_TRY(ctx, cudaMemcpy(w.buf.p, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
+    w.d.pk = w.buf.p;
+  }
+  w.has16 = false;
+  if (L.gemm_f16) {
+    float wmax = 0.f;
+    for (int k = 0; k < K; ++k)
+      for (int n = 0; n < N; ++n) wmax = fmaxf(wmax, fabsf(host_B[(size_t)k * ldb + n]));
+    if (wmax < 3.0e4f) {
+      std::vector<float> pk;
+      l2hmc::tcg::pack_b(host_B, ldb, K, N, pk, &w.d16, true);
+      int rc = ensure(ctx, w.buf16, pk.size());
+      if (rc) return rc;
+      CUDA_TRY(ctx, cudaMemcpy(w.buf16.p, pk.data(), pk.size() * sizeof(float), cudaMemcpyHostToDevice));
+      w.d16.pk = w.buf16.p;
+      w.d16.status = ctx->status_d;
+      w.has16 = true;
+    }
+  }
   return L2HMC_OK;
 }
 
@@ -214,7 +234,11 @@ int lay_gemm(l2hmc_ctx *ctx, cudaStream_t s, GemmArgs g) {
     const bool aligned = (reinterpret_cast<uintptr_t>(g.bias) % 16) == 0 && (reinterpret_cast<uintptr_t>(g.bias_b) % 16) == 0 &&
                          (reinterpret_cast<uintptr_t>(g.A) % 16) == 0 && (g.lda % 4) == 0;
     if (it != ctx->lay.tcw.end() && aligned) {
-      CUDA_TRY(ctx, l2hmc::tcg::launch_tc_gemm(g, it->second.d, ctx->lay.sms, s));
+      // fp16 operand split unless this context has met an activation outside the fp16 range (sticky status bit, polled
+      // from pinned host memory without synchronising) or the weight itself is out of range
+      const bool f16 = ctx->lay.gemm_f16 && it->second.has16 && !(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE);
+      ctx->lay.used_f16 = f16;
+      CUDA_TRY(ctx, l2hmc::tcg::launch_tc_gemm(g, f16 ? it->second.d16 : it->second.d, ctx->lay.sms, s));
       ctx->launches++;
       return L2HMC_OK;
     }

@@ -47,6 +47,7 @@ struct TcGemmB {
   int nblk;  // n-blocks
   int nkb;   // k-blocks (K padded to a multiple of the k-block with zero rows)
   int f16;   // image holds fp16 hi / lo, k-block = 32 (else tf32, k-block = 16)
+  unsigned int *status;  // the context's status word (host-mapped): the fp16 A path raises STATUS_F16_RANGE on an out-of-range activation
 };
 
 __host__ __device__ inline size_t b_block_floats(int BN) { return (size_t)2 * GBK * BN; }
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
     }
     const long long total = my_tiles * nkb;
     const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    float amax = 0.f;  // F16: largest |activation| this thread converted (fp16 overflows at 65504)
     constexpr int NV = F16 ? 2 : 1;  // float4 per 16-byte piece of the operand image (8 halfs or 4 tf32)
     auto load_blk = [&](long long flat, float4(&dst)[4 * NV]) {
       if (flat >= total) return;
@@ -192,6 +194,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float h0 = trunc_tf32(a[2 * j]), h1 = trunc_tf32(a[2 * j + 1]);
+            amax = fmaxf(amax, fmaxf(fabsf(a[2 * j]), fabsf(a[2 * j + 1])));
             hp[j] = pack_h2g(h0, h1);
             lp[j] = pack_h2g(a[2 * j] - h0, a[2 * j + 1] - h1);
           }
@@ -241,6 +244,9 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
         }
       }
     }
+    // an activation left the fp16 range (or was not finite): sticky bit in the context's status word; the host then uses
+    // the tf32 images of the weights (kept beside the fp16 ones) for every later GEMM of the context
+    if (F16 && !(amax < 60000.f) && tb.status) atomicOr_system(tb.status, l2hmc::STATUS_F16_RANGE);
   } else if (warp < 16) {
     // ---------------- epilogue warps: thread = output row of accumulator (e / 4), TMEM lane group (e % 4) ----------
     const int e = warp - 8;
@@ -388,7 +394,10 @@ inline cudaError_t launch_tc_gemm(const layered::GemmArgs &g, const TcGemmB &tb,
   cudaError_t e = cudaSuccess;
 #define L2HMC_TCG_LAUNCH(E)                                                                                              \
   case E: {                                                                                                              \
-    static thread_local size_t configured = 0;                                                                           \
+    static size_t configured_dev[64] = {0};                                                                              \
+    int dev_ = 0;                                                                                                        \
+    cudaGetDevice(&dev_);                                                                                                \
+    size_t &configured = configured_dev[dev_ & 63];                                                                      \
     if (smem > configured) {                                                                                             \
       e = cudaFuncSetAttribute(tc_gemm_kernel<E, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);        \
       if (e != cudaSuccess) return e;                                                                                    \
@@ -473,6 +482,7 @@ inline size_t pack_b(const float *B, int ldb, int K, int N, std::vector<float> &
             }
     }
   desc->pk = nullptr;  // caller sets the device pointer
+  desc->status = nullptr;
   desc->BN = BN;
   desc->nblk = nblk;
   desc->nkb = nkb;

@@ -63,9 +63,32 @@ def test_vae_target_on_fma_gemms(name, n):
     _check(rep)
 
 
-def test_default_layered_gemms_are_tensor_core():
+def test_default_layered_gemms_are_tensor_core_fp16_split_with_a_range_guard(monkeypatch):
+    """The layered engine's GEMMs default to the fp16 x3 operand split (half the tensor time and half the shared-memory
+    operand bytes of the tf32 x3 split).  Its A path tracks |activation|: an out-of-range value raises the context's
+    sticky status bit, and from the next call on the context uses the tf32 images kept beside the fp16 ones."""
+    monkeypatch.delenv("L2HMC_LAYERED_GEMM", raising=False)
     P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
-    assert P.product().kernel_name in ("layered_tc3xtf32", "layered_tc3xf16")
+    dyn = P.product()
+    assert dyn.kernel_name == "layered_tc3xf16"
+    d = P.draws(160)
+    ok = U.run_kernel_propose(P, d, dyn=dyn)
+    assert np.isfinite(ok["Lx"]).all() and not dyn.fp16_range_exceeded()
+    monkeypatch.setenv("L2HMC_LAYERED_GEMM", "tf32")
+    ref32 = P.product()
+    assert ref32.kernel_name == "layered_tc3xtf32"
+    monkeypatch.delenv("L2HMC_LAYERED_GEMM", raising=False)
+    r32 = U.run_kernel_propose(P, d, dyn=ref32)
+    assert U.max_rel(ok["Lx"], r32["Lx"]) <= SAMPLE_TOL and float(np.abs(ok["px"] - r32["px"]).max()) <= 2 * P_TOL
+    big = dict(d)
+    big["x"] = d["x"].copy()
+    big["x"][7, 1] = 3.0e5                       # outside the fp16 range
+    U.run_kernel_propose(P, big, dyn=dyn)
+    assert dyn.fp16_range_exceeded() and dyn.kernel_name == "layered_tc3xtf32"
+    again = U.run_kernel_propose(P, big, dyn=dyn)  # now on the tf32 images: equal to a tf32-only context
+    want = U.run_kernel_propose(P, big, dyn=ref32)
+    assert np.array_equal(again["x_next"], want["x_next"]) and np.array_equal(again["px"], want["px"])
+    assert not ref32.fp16_range_exceeded()
 
 
 def test_vae_log_jac_mode():
