@@ -382,6 +382,39 @@ def other_config(runner, name, peaks, quick):
     return out
 
 
+def training_config(runner, name, n, steps, quick):
+    """One iteration of the notebook's training loop (SCGExperiment.ipynb:254-270: the objective on the current samples
+    and on fresh noise, its gradient through the unrolled leapfrog, Adam, Metropolis output fed back) per step, through
+    l2hmc_b200.training (l2hmc_loss_grad).  Rank 0 only: the path is measured on one GPU."""
+    from l2hmc_b200 import synthetic as S, training
+    dev = runner.dev
+    P = S.SyntheticProblem(regime="init", **S.CONFIGS[name])   # training starts from the notebook's initialisation
+    dyn = P.product(device=dev.index, seed=3)
+    opt = training.Adam(dyn)
+    samples = torch.as_tensor(P.x0(n, np.random.default_rng(5))).to(dev)
+    for _ in range(3):
+        samples = training.train_step(dyn, opt, samples)["samples"]
+    torch.cuda.synchronize(dev)
+    steps = max(3, steps // 3) if quick else steps
+    launches0 = dyn.launch_count
+    t_wall0 = time.time()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        out = training.train_step(dyn, opt, samples)
+        samples = out["samples"]
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    t_wall1 = time.time()
+    clocks = runner.sampler.summary(t_wall0, t_wall1) if runner.sampler else None
+    return {"name": "train_" + name, "workload": "notebook training loop (loss on samples + noise batch, reverse sweep, Adam), %d chains, "
+            "x_dim %d, width %d, Lf=%d" % (n, P.D, P.H, P.T), "chains": n, "steps": steps,
+            "training_steps_per_s": steps / dt, "ms_per_step": 1e3 * dt / steps,
+            # both batches (x and z) run forward and reverse sweeps of Lf leapfrog steps per chain
+            "leapfrog_steps_per_s_forward_equivalent": 2 * n * P.T * steps / dt,
+            "loss": out["loss"], "mean_accept_prob": float(out["px"].mean()), "clocks": clocks,
+            "timing": "host wall clock around train_step (includes the host-side Adam write-back), device synchronised"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -491,6 +524,13 @@ def main():
             except Exception as e:  # noqa: BLE001 -- a failing side configuration must not lose the headline line
                 others.append({"name": name, "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
             torch.cuda.empty_cache()
+    train = []
+    if not args.no_other_configs and rank == 0:
+        for name, nn, st in (("c1_scg2", 200, 60), ("c2_scg50", 4096, 12)):
+            try:
+                train.append(training_config(runner, name, nn, st, args.quick))
+            except Exception as e:  # noqa: BLE001
+                train.append({"name": "train_" + name, "error": "%s: %s" % (type(e).__name__, str(e)[:300])})
 
     if sampler:
         sampler.stop()
@@ -564,7 +604,8 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "parity": rep,
-            "other_configs": others}
+            "other_configs": others,
+            "training": train}
     print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -131,6 +131,16 @@ typedef struct {
                              l2hmc_transition, HOST pointer for l2hmc_transition_host.                            */
   float *trace;           /* [n_transitions,n,D] or NULL: the Metropolis output after EVERY fused transition (the
                              notebook's final_samples list, SCGExperiment.ipynb:291-298); needs do_mh; device only */
+  int32_t chain;          /* 1: chain_operator (utils/sampler.py:57-85) in ONE launch.  n_transitions is then nb_steps: that
+                             many SUB-PROPOSALS are composed -- each with a fresh direction bit and fresh momentum
+                             (dir [n_transitions,n], v [n_transitions,n,D] when given, else Philox at counter + s), log|J|
+                             accumulated, no Metropolis step in between -- and the call closes with
+                             px_out = p_accept(x, v0, x_K, v_K, sum log|J|)  (or the summed log|J| when log_jac), ONE set
+                             of uniforms u [n] and x_next = tf_accept(x, x_K, px).  The reference's quirk is kept: the
+                             sub-proposals ignore the carried momentum, the final Hamiltonians pair x with v0 = init_v
+                             and x_K with the LAST sub-proposal's momentum.  Fused kernels only (small, tile, the
+                             shape-specialised tensor-core kernel); others: L2HMC_EUNSUPPORTED.                       */
+  const float *v0;        /* chain mode: init_v [n,D] (utils/sampler.py:58-59), or NULL: drawn (Philox at counter + n_transitions) */
 } l2hmc_transition_args;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -222,7 +232,13 @@ int l2hmc_status_flags(l2hmc_ctx *ctx, uint32_t *flags, int clear);
  * Gradient tensors have the shapes of l2hmc_net_params; every output is ACCUMULATED (+=) so that the caller zeroes once
  * and adds the `x` batch and the `z` batch of the notebook objective.  Device pointers throughout; asynchronous on the
  * stream (scratch, 4*T*2*x_dim floats per chain for the record plus activations, is held by the context).  Covers the closed-form energies (Gaussian, GMM, RoughWell, funnel) without aux; the decoder target and
- * aux-conditioned nets: L2HMC_EUNSUPPORTED. */
+ * aux-conditioned nets: L2HMC_EUNSUPPORTED.
+ * Determinism: the weight gradients are sums over chains accumulated with fp32 atomicAdd (split-K GEMMs, per-warp
+ *   reductions), so two calls on the same inputs agree to fp32 rounding of a different summation order (~1e-6 relative),
+ *   not bit for bit; loss, Lx and px_out are deterministic.  (TF1's reductions on the reference's GPU path are not
+ *   run-to-run deterministic either.)
+ * Streams: the scratch belongs to the context -- calls on ONE context must be issued on one stream (or ordered by the
+ *   caller); use one context per stream for concurrent batches. */
 typedef struct {
   float *W1, *b1, *W2, *b2, *W3, *b3, *W4, *b4, *Ws, *bs, *Wt, *bt, *Wq, *bq, *scale_s, *scale_q;
 } l2hmc_net_grads;

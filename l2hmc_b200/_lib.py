@@ -107,7 +107,7 @@ class TransitionArgs(C.Structure):
                 ("seed", C.c_uint64), ("counter", C.c_uint64),
                 ("x_out", C.c_void_p), ("v_out", C.c_void_p), ("px_out", C.c_void_p), ("x_next", C.c_void_p),
                 ("accepted", C.c_void_p), ("stream", C.c_void_p), ("aux", C.c_void_p),
-                ("stats", C.c_void_p), ("trace", C.c_void_p)]
+                ("stats", C.c_void_p), ("trace", C.c_void_p), ("chain", C.c_int32), ("v0", C.c_void_p)]
 
 
 ENERGY_GAUSSIAN, ENERGY_GMM, ENERGY_ROUGHWELL, ENERGY_FUNNEL, ENERGY_DECODER = 0, 1, 2, 3, 4

@@ -62,7 +62,18 @@ struct TransitionIO {
   double *stats;          // [2] or null: += sum of px, += number accepted, over every chain and transition of the launch
   float *trace;           // [n_transitions][n][D] or null: the Metropolis output x_next after every fused transition
   unsigned int *status;   // the context's status word (pinned, host-mapped): bit 0 = fp16 operand range exceeded
+  // chain_operator (utils/sampler.py:57-85) in one launch: the n_transitions loop composes n_transitions SUB-PROPOSALS
+  // (fresh direction and momentum each, log|J| accumulated, no Metropolis step in between) and closes with ONE accept
+  // probability p_accept(x_in, v0, x_K, v_K, sum log|J|) and one Metropolis step against x_in.
+  int chain;
+  const float *v0;        // chain mode: init_v [n][D] paired with x_in in the first Hamiltonian (null: drawn, Philox)
 };
+
+// chain mode: the momentum of the first Hamiltonian when the caller gave none (tf.random_normal, utils/sampler.py:58-59):
+// the normals stream at the call counter one past the last sub-proposal's
+__device__ __forceinline__ unsigned long long chain_v0_counter(const TransitionIO &io) {
+  return io.counter + (unsigned long long)io.n_transitions;
+}
 
 // status bits (l2hmc_status_flags)
 constexpr unsigned int STATUS_F16_RANGE = 1u;

@@ -144,11 +144,15 @@ __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_const
 #pragma unroll
   for (int d = 0; d < DM; ++d) x[d] = d < D ? io.x[g * D + d] : 0.f;
 
+  float x0[DM], h_old = 0.f, lj = 0.f;
   for (int tr = 0; tr < io.n_transitions; ++tr) {
     const unsigned long long ctr = io.counter + (unsigned long long)tr;
-    float x0[DM];
+    const bool first = !io.chain || tr == 0;              // chain mode: one Hamiltonian / log|J| / start point for all sub-proposals
+    const bool closing = !io.chain || tr == io.n_transitions - 1;
+    if (first) {
 #pragma unroll
-    for (int d = 0; d < DM; ++d) x0[d] = x[d];
+      for (int d = 0; d < DM; ++d) x0[d] = x[d];
+    }
     if (io.v != nullptr) {
 #pragma unroll
       for (int d = 0; d < DM; ++d) v[d] = d < D ? io.v[((long long)tr * io.n + g) * D + d] : 0.f;
@@ -165,17 +169,29 @@ __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_const
     if (io.dir_mode == 1) fwd = false;
     else if (io.dir_mode == 2) fwd = io.dir[(long long)tr * io.n + g] != 0;
     else if (io.dir_mode == 3) fwd = pd != 0;
-    if (io.do_mh && io.u != nullptr) pu = io.u[(long long)tr * io.n + g];
+    if (io.do_mh && io.u != nullptr) pu = io.u[(io.chain ? 0ll : (long long)tr * io.n) + g];  // chain mode: one set of uniforms
 
     grad_small<DM>(A.en, sh, x, gr);
     float kin = 0.f;
+    if (first) {
+      if (io.chain) {  // H(x_in, init_v): the sub-proposals draw their own momenta (utils/sampler.py:35-36, 79)
+        float z[4] = {0.f, 0.f, 0.f, 0.f};
+        if (io.v0 == nullptr) philox_normals4(io.seed, chain_v0_counter(io), io.chain_offset + g, 0, z);
 #pragma unroll
-    for (int d = 0; d < DM; ++d) kin = fmaf(v[d], v[d], kin);
-    float xs0[DM];
+        for (int d = 0; d < DM; ++d) {
+          const float v0d = d < D ? (io.v0 ? io.v0[g * D + d] : z[d]) : 0.f;
+          kin = fmaf(v0d, v0d, kin);
+        }
+      } else {
 #pragma unroll
-    for (int d = 0; d < DM; ++d) xs0[d] = x[d];
-    const float h_old = energy_chain(A.en, sh, xs0, 1) + 0.5f * kin;
-    float lj = 0.f;
+        for (int d = 0; d < DM; ++d) kin = fmaf(v[d], v[d], kin);
+      }
+      float xs0[DM];
+#pragma unroll
+      for (int d = 0; d < DM; ++d) xs0[d] = x[d];
+      h_old = energy_chain(A.en, sh, xs0, 1) + 0.5f * kin;
+      lj = 0.f;
+    }
 
     for (int it = 0; it < T; ++it) {
       const int t = fwd ? it : T - 1 - it;
@@ -240,6 +256,7 @@ __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_const
       }
     }
     if (sh.hmc) lj = 0.f;
+    if (!closing) continue;  // chain mode: the next sub-proposal starts from this proposal, no Metropolis step in between
     kin = 0.f;
 #pragma unroll
     for (int d = 0; d < DM; ++d) kin = fmaf(v[d], v[d], kin);

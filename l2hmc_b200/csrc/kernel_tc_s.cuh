@@ -532,6 +532,7 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
     }
     compute_bar();
 
+    float ljl = 0.f;
     for (int tr = 0; tr < io.n_transitions; ++tr) {
       const unsigned long long ctr = io.counter + (unsigned long long)tr;
       // ---- setup: momentum, direction, uniform -------------------------------------------------------
@@ -561,13 +562,16 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
         else if (io.dir_mode == 2) dbit = (gch < io.n) ? (io.dir[(long long)tr * io.n + gch] != 0) : 1;
         else if (io.dir_mode == 3) dbit = pd;
         sdir[c] = dbit;
-        if (io.do_mh && io.u != nullptr) pu = (gch < io.n) ? io.u[(long long)tr * io.n + gch] : 0.f;
+        if (io.do_mh && io.u != nullptr) pu = (gch < io.n) ? io.u[(io.chain ? 0ll : (long long)tr * io.n) + gch] : 0.f;
         smem[L.su + c] = pu;
       }
       compute_bar();
       const bool fwd = sdir[c] != 0;
       const float sg = fwd ? 1.f : -1.f;
-      float ljl = 0.f;  // log|J| of this thread's dimensions, in log2 units
+      // chain mode (chain_operator in one launch): the sub-proposals share one start point, one first Hamiltonian (paired
+      // with init_v, not with their own momenta) and one log|J| accumulator; one Metropolis step after the last
+      const bool chain_first = !io.chain || tr == 0, chain_last = !io.chain || tr == io.n_transitions - 1;
+      if (chain_first) ljl = 0.f;  // log|J| of this thread's dimensions, in log2 units
 
       // ---- A operands ------------------------------------------------------------------------------------
       // net input of one 4-dim chunk: [a0..3 | b0..3] = K step q of the embed GEMM (weight rows permuted to match)
@@ -949,9 +953,27 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
 
       float hpart0 = 0.f;
       first_grad(hpart0);
-      smem[L.part + qd * MT + c] = hpart0;
+      if (io.chain) {
+        // H(x_in, init_v): replace the kinetic part of this thread's dimensions by init_v's (utils/sampler.py:58-59, 79)
+        float Kv = 0.f, K0 = 0.f;
+#pragma unroll 1
+        for (int i = 0; i < qn; ++i) {
+          const int q = qd + NQ * i;
+          const float4 vv = lds4(vr + 4 * q);
+          Kv = fmaf(vv.x, vv.x, fmaf(vv.y, vv.y, fmaf(vv.z, vv.z, fmaf(vv.w, vv.w, Kv))));
+          float z[4] = {0.f, 0.f, 0.f, 0.f};
+          if (io.v0 == nullptr) philox_normals4(io.seed, chain_v0_counter(io), io.chain_offset + gch, q, z);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float v0 = (gch < io.n && 4 * q + j < D) ? (io.v0 ? io.v0[gch * D + 4 * q + j] : z[j]) : 0.f;
+            K0 = fmaf(v0, v0, K0);
+          }
+        }
+        hpart0 += 0.5f * (K0 - Kv);
+      }
+      if (chain_first) smem[L.part + qd * MT + c] = hpart0;
       compute_bar();
-      if (qd == 0) {
+      if (qd == 0 && chain_first) {
         float h0s = 0.f;
 #pragma unroll
         for (int r = 0; r < NQ; ++r) h0s += smem[L.part + r * MT + c];
@@ -988,6 +1010,7 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
 
       // ---- log|J|, Hamiltonian, accept ---------------------------------------------------------------
       compute_bar();  // h0 readers are done with `part`
+      if (!chain_last) continue;  // chain mode: the next sub-proposal starts from this proposal, no Metropolis step in between
       smem[L.part + qd * MT + c] = final_ham();
       compute_bar();
       float h1 = 0.f;
@@ -1023,7 +1046,7 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
             if (io.v_out) io.v_out[g * D + d] = smem[L.vs + ch * RS + d];
             // the state this transition started from: the caller's x, or the x_next written one transition ago
             if (io.do_mh) {
-              const float nx = sacc[ch] ? lx : (tr == 0 ? io.x[g * D + d] : io.x_next[g * D + d]);
+              const float nx = sacc[ch] ? lx : ((tr == 0 || io.chain) ? io.x[g * D + d] : io.x_next[g * D + d]);
               io.x_next[g * D + d] = nx;
               if (io.trace) io.trace[((long long)tr * io.n + g) * D + d] = nx;
             }

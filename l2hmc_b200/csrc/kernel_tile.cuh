@@ -400,7 +400,7 @@ __device__ __noinline__ void phase_grad(const KernelArgs &A) {
 
 // U(x) + 0.5|v|^2 for chain `ch` from the tile state; for the Gaussian kind it reuses d = x - mu
 // (vx rows DP..) and g = d Ssym / T (xg rows DP..) left by the last phase_grad on the same x.
-__device__ __noinline__ float hamiltonian_chain(const KernelArgs &A, int ch) {
+__device__ __noinline__ float hamiltonian_chain(const KernelArgs &A, int ch, bool v0_chain = false) {
   const Shape &sh = A.sh;
   const EnergyDev &en = A.en;
   const Lay L = make_lay(sh.DP, sh.HP, sh.T);
@@ -413,9 +413,24 @@ __device__ __noinline__ float hamiltonian_chain(const KernelArgs &A, int ch) {
     U = energy_chain(en, sh, smem + L.xg + ch, M);
   }
   float kin = 0.f;
-  for (int d = 0; d < sh.D; ++d) {
-    const float v = smem[L.vx + d * M + ch];
-    kin = fmaf(v, v, kin);
+  if (v0_chain) {
+    // chain mode, first Hamiltonian: H(x_in, init_v) -- the sub-proposals draw their own momenta (utils/sampler.py:35-36, 79)
+    const TransitionIO &io = A.io;
+    const long long g = (long long)blockIdx.x * M + ch;
+    for (int b = 0; b < sh.DP / 4; ++b) {
+      float z[4] = {0.f, 0.f, 0.f, 0.f};
+      if (io.v0 == nullptr) philox_normals4(io.seed, chain_v0_counter(io), io.chain_offset + g, b, z);
+      for (int q = 0; q < 4; ++q) {
+        const int d = 4 * b + q;
+        const float v = (g < io.n && d < sh.D) ? (io.v0 ? io.v0[g * sh.D + d] : z[q]) : 0.f;
+        kin = fmaf(v, v, kin);
+      }
+    }
+  } else {
+    for (int d = 0; d < sh.D; ++d) {
+      const float v = smem[L.vx + d * M + ch];
+      kin = fmaf(v, v, kin);
+    }
   }
   return U + 0.5f * kin;
 }
@@ -428,8 +443,10 @@ __device__ __noinline__ void phase_begin(const KernelArgs &A, int tr) {
   const int tid = threadIdx.x, D = sh.D, DP = sh.DP;
   const long long base = (long long)blockIdx.x * M;
   const unsigned long long ctr = io.counter + (unsigned long long)tr;
-  for (int i = tid; i < DP * M; i += NT) smem[L.x0 + i] = smem[L.xg + i];
-  for (int i = tid; i < (DP / 2) * M; i += NT) smem[L.ljs + i] = 0.f;
+  if (!io.chain || tr == 0) {  // chain mode: one start point and one log|J| accumulator for all sub-proposals
+    for (int i = tid; i < DP * M; i += NT) smem[L.x0 + i] = smem[L.xg + i];
+    for (int i = tid; i < (DP / 2) * M; i += NT) smem[L.ljs + i] = 0.f;
+  }
   if (io.v != nullptr) {
     for (int i = tid; i < M * DP; i += NT) {
       const int ch = i / DP, d = i - ch * DP;
@@ -456,7 +473,7 @@ __device__ __noinline__ void phase_begin(const KernelArgs &A, int tr) {
     else if (io.dir_mode == 2) dbit = (g < io.n) ? (io.dir[(long long)tr * io.n + g] != 0) : 1;
     else if (io.dir_mode == 3) dbit = pd;
     reinterpret_cast<int *>(smem + L.sdir)[tid] = dbit;
-    if (io.do_mh && io.u != nullptr) pu = (g < io.n) ? io.u[(long long)tr * io.n + g] : 0.f;
+    if (io.do_mh && io.u != nullptr) pu = (g < io.n) ? io.u[(io.chain ? 0ll : (long long)tr * io.n) + g] : 0.f;
     smem[L.su + tid] = pu;
   }
   __syncthreads();
@@ -470,6 +487,7 @@ __device__ __noinline__ void phase_end(const KernelArgs &A, int tr) {
   const int tid = threadIdx.x, D = sh.D, DP = sh.DP;
   const long long base = (long long)blockIdx.x * M;
   const bool last = (tr == io.n_transitions - 1);
+  if (io.chain && !last) return;  // chain mode: the next sub-proposal starts from this proposal, no Metropolis step in between
   int *sacc = reinterpret_cast<int *>(smem + L.sacc);
   if (tid < M) {
     const int ch = tid;
@@ -535,7 +553,7 @@ __global__ void __launch_bounds__(NT, 2) transition_kernel(const __grid_constant
   for (int tr = 0; tr < io.n_transitions; ++tr) {
     phase_begin(A, tr);
     phase_grad(A);
-    if (tid < M) smem[L.h0 + tid] = hamiltonian_chain(A, tid);
+    if (tid < M && (!io.chain || tr == 0)) smem[L.h0 + tid] = hamiltonian_chain(A, tid, io.chain != 0);
     __syncthreads();
 
     for (int it = 0; it < sh.T; ++it) {

@@ -1021,7 +1021,9 @@ static int validate_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, b
   if (a->dir_mode < 0 || a->dir_mode > 3) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: bad dir_mode %d", a->dir_mode);
   if (a->dir_mode == L2HMC_DIR_PER_CHAIN && !a->dir && a->n > 0) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: dir_mode PER_CHAIN needs dir");
   if (a->do_mh && !a->x_next && a->n > 0 && !host) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: do_mh needs x_next");
-  if (a->n_transitions > 1 && !a->do_mh) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: n_transitions > 1 needs do_mh");
+  if (a->n_transitions > 1 && !a->do_mh && !a->chain) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: n_transitions > 1 needs do_mh");
+  if (a->chain && a->trace) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: chain mode has one Metropolis step: no per-transition trace");
+  if (a->chain && host) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition_host: chain mode is a device-resident call (use l2hmc_transition)");
   if (a->trace && !a->do_mh) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: trace records the Metropolis output and needs do_mh");
   if (a->trace && host) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition_host: trace is a device-resident output (use l2hmc_transition)");
   if (a->counter + (uint64_t)a->n_transitions >= (1ull << 30)) return fail(ctx, L2HMC_EINVAL, "l2hmc_transition: counter must stay below 2^30");
@@ -1043,6 +1045,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
   io.seed = a->seed; io.counter = a->counter;
   io.x_out = a->x_out; io.v_out = a->v_out; io.px_out = a->px_out; io.x_next = a->x_next; io.accepted = a->accepted;
   io.stats = a->stats; io.trace = a->trace; io.status = ctx->status_d;
+  io.chain = a->chain ? 1 : 0; io.v0 = a->v0;
 
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->timing) {
@@ -1133,6 +1136,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       }
 #undef L2HMC_TC_S_LAUNCH
     } else {
+    if (a->chain) return fail(ctx, L2HMC_EUNSUPPORTED, "chain mode: not in the generic tensor-core kernel (compose l2hmc_transition calls with log_jac = 1)");
     ctx->tc_used_f16 = false;
     const size_t smem = tc::tc_smem_bytes(ctx->sh.DP, ctx->sh.T, ctx->td.nslot, ctx->td.slot_floats);
     size_t &tc_configured = ctx->smem_cfg[1];
@@ -1183,6 +1187,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     const long long blocks = (a->n + tile::M - 1) / tile::M;
     tile::transition_kernel<<<(unsigned)blocks, tile::NT, smem, stream>>>(K);
   } else if (kernel == L2HMC_KERNEL_LAYERED) {
+    if (a->chain) return fail(ctx, L2HMC_EUNSUPPORTED, "chain mode: not in the layered engine (compose l2hmc_transition calls with log_jac = 1)");
     int rc = launch_layered(ctx, a, K.io, stream);  // counts its own launches
     if (rc) return rc;
     ctx->launches -= 1;

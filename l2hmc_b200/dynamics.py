@@ -343,7 +343,7 @@ class Dynamics(object):
 
     def _transition(self, x, *, v=None, dir_mode=_lib.DIR_FORWARD, direction=None, u=None, log_jac=False,
                     do_mh=False, n_transitions=1, want_v=True, counter=None, chain_offset=0, seed=None, out=None,
-                    aux=None, stats=None, trace=None):
+                    aux=None, stats=None, trace=None, chain=False, v0=None):
         """One l2hmc_transition call. Returns dict(Lx, Lv, px, x_next, accepted).  `out` may hold preallocated
         tensors of the right shapes under the same keys (steady-state loops then allocate nothing).
         stats: optional CUDA float64 [2] accumulator (+= sum of px, += number accepted, reduced in the kernel);
@@ -376,7 +376,7 @@ class Dynamics(object):
             dir_mode = _lib.DIR_PER_CHAIN
         if u is not None:
             u = self._prep(u, "u")
-            if u.numel() != n_transitions * n:
+            if u.numel() != (1 if chain else n_transitions) * n:
                 raise ValueError("u must have N entries")
             keep.append(u)
             a.u = u.data_ptr()
@@ -399,6 +399,14 @@ class Dynamics(object):
             if not (stats.is_cuda and stats.dtype == torch.float64 and stats.numel() == 2 and stats.is_contiguous()):
                 raise TypeError("stats must be a contiguous CUDA float64 tensor of 2 elements")
             a.stats = stats.data_ptr()
+        if chain:
+            a.chain = 1
+            if v0 is not None:
+                v0 = self._prep(v0, "init_v", self.x_dim)
+                if v0.shape[0] != n:
+                    raise ValueError("init_v must be [N, x_dim]")
+                keep.append(v0)
+                a.v0 = v0.data_ptr()
         if trace is not None:
             if not (trace.is_cuda and trace.dtype == TORCH_FLOAT and trace.is_contiguous() and
                     tuple(trace.shape) == (int(n_transitions), n, self.x_dim)):

@@ -101,18 +101,58 @@ def chain_operator(init_x, dynamics, nb_steps, aux=None, init_v=None, do_mh_step
     Hamiltonian and makes ``propose`` return Lv); the final p_accept pairs init_v with the last Lv.
     rng: optional list (one dict per sub-proposal, see ``propose``) plus rng_final={'u': ...} as the
     last element for the closing MH step.
+
+    ONE kernel launch where the fused kernels cover the problem (``l2hmc_transition_args.chain``: the sub-proposals, the
+    accumulated log|J|, p_accept and the Metropolis step all stay on chip); on the layered engine (VAE target, wide nets)
+    and the generic tensor-core kernel the same composition runs as a loop of launches.
     """
+    nb_steps = int(nb_steps)
+    fused = _chain_in_one_launch(init_x, dynamics, nb_steps, aux, init_v, do_mh_step, rng)
+    if fused is not None:
+        return fused
     if init_v is None:
         init_v = randn_like(init_x, seed=dynamics.seed ^ 0x5EED, counter=dynamics.next_counter())
     x, v = init_x, init_v
     log_jac = torch.zeros((init_x.shape[0],), dtype=TORCH_FLOAT, device=init_x.device)
-    for t in range(int(nb_steps)):
+    for t in range(nb_steps):
         r = rng[t] if rng is not None else None
         x, v, px, _ = propose(x, dynamics, init_v=v, aux=aux, log_jac=True, do_mh_step=False, rng=r)
         log_jac = log_jac + px
     p_accept = dynamics.p_accept(init_x, init_v, x, v, log_jac, aux=aux)
     outputs = []
     if do_mh_step:
-        u = rng[int(nb_steps)].get("u") if rng is not None and len(rng) > int(nb_steps) else None
+        u = rng[nb_steps].get("u") if rng is not None and len(rng) > nb_steps else None
         outputs.append(tf_accept(init_x, x, p_accept, u=u, seed=dynamics.seed, counter=dynamics.next_counter()))
     return x, v, p_accept, outputs
+
+
+def _chain_in_one_launch(init_x, dynamics, nb_steps, aux, init_v, do_mh_step, rng):
+    """chain_operator through l2hmc_transition_args.chain, or None when this Dynamics runs on an engine without it."""
+    if dynamics.hmc or aux is not None or nb_steps < 1 or dynamics.aux_dim:
+        return None
+    dynamics._ensure_ctx()
+    if not dynamics.kernel_name.startswith(("small", "tile", "tc_")):
+        return None
+    v = d = u = None
+    if rng is not None:
+        steps = list(rng[:nb_steps])
+        if len(steps) != nb_steps:
+            raise ValueError("rng needs one dict per sub-proposal")
+        have_v = [("v" in r) for r in steps]
+        have_d = [("direction" in r) for r in steps]
+        if any(have_v) != all(have_v) or any(have_d) != all(have_d):
+            return None   # partially injected randomness: the loop of launches handles it
+        if all(have_v):
+            v = torch.stack([dynamics._prep(r["v"], "v", dynamics.x_dim) for r in steps])
+        if all(have_d):
+            d = torch.stack([r["direction"].detach().to(device=init_x.device, dtype=torch.uint8) for r in steps])
+        if len(rng) > nb_steps:
+            u = rng[nb_steps].get("u")
+    try:
+        o = dynamics._transition(init_x, v=v, dir_mode=_lib.DIR_RANDOM, direction=d, u=u, do_mh=True, n_transitions=nb_steps,
+                                 chain=True, v0=init_v)
+    except _lib.L2HMCError as e:
+        if e.code == 3:   # L2HMC_EUNSUPPORTED: this shape runs on the generic tensor-core kernel
+            return None
+        raise
+    return o["Lx"], o["Lv"], o["px"], ([o["x_next"]] if do_mh_step else [])

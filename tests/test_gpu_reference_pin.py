@@ -125,9 +125,12 @@ def test_dynamics_methods_match_the_reference(path):
             close(val, key)
 
 
-@pytest.mark.parametrize("name", ["chain_operator_c1_n64", "chain_operator_c2_n32"])
-def test_chain_operator_matches_the_reference(name):
-    """utils/sampler.py:57-85 as the reference runs it."""
+@pytest.mark.parametrize("name,kernel,launches", [("chain_operator_c1_n64", "auto", 1), ("chain_operator_c1_n64", "tile", 1),
+                                                  ("chain_operator_c2_n32", "auto", 1), ("chain_operator_c2_n32", "tile", 1),
+                                                  ("chain_operator_c2_n32", "layered", None)])
+def test_chain_operator_matches_the_reference(name, kernel, launches):
+    """utils/sampler.py:57-85 as the reference runs it -- in ONE kernel launch on the fused kernels (small, tile, the
+    shape-specialised tensor-core kernel: l2hmc_transition_args.chain), as a loop of launches on the layered engine."""
     from l2hmc_b200 import chain_operator
     z = np.load(os.path.join(GOLD, "ref", name + ".npz"))
     meta = _meta(z)
@@ -142,7 +145,12 @@ def test_chain_operator_matches_the_reference(name):
         sel = np.where(z["in_dirs"][s][:, None] != 0, z["in_v_fs"][s], z["in_v_bs"][s]).astype(np.float32)
         rngs.append({"direction": g(z["in_dirs"][s]), "v": g(sel)})
     rngs.append({"u": g(z["in_u"])})
-    fx, fv, p, outs = chain_operator(g(z["in_x"]), P.product(), steps, init_v=g(z["in_init_v"]), do_mh_step=True, rng=rngs)
+    dyn = P.product(kernel=kernel)
+    dyn._ensure_ctx()
+    l0 = dyn.launch_count
+    fx, fv, p, outs = chain_operator(g(z["in_x"]), dyn, steps, init_v=g(z["in_init_v"]), do_mh_step=True, rng=rngs)
+    if launches is not None:
+        assert dyn.launch_count - l0 == launches, (dyn.kernel_name, dyn.launch_count - l0)
     assert U.max_rel(fx.cpu().numpy(), z["out_final_x"]) <= 3e-5
     assert U.max_rel(fv.cpu().numpy(), z["out_final_v"]) <= 3e-5
     assert float(np.max(np.abs(p.cpu().numpy() - z["out_p_accept"]))) <= 2e-4
@@ -150,6 +158,36 @@ def test_chain_operator_matches_the_reference(name):
     acc_k = np.all(outs[0].cpu().numpy() == fx.cpu().numpy(), axis=1)
     margin = np.abs(z["out_p_accept"] - z["in_u"])
     assert int(((acc_ref != acc_k) & (margin > 1e-3)).sum()) == 0
+    # rejected chains keep init_x
+    xn = outs[0].cpu().numpy()
+    assert np.array_equal(xn[~acc_k], z["in_x"][~acc_k])
+
+
+def test_chain_operator_with_in_kernel_randomness_is_one_launch_and_self_consistent():
+    """No injected randomness: directions, momenta, init_v and the closing uniforms come from the Philox stream inside the
+    one launch; re-injecting exactly those draws (l2hmc_philox_fill at the same counters) reproduces the result."""
+    from l2hmc_b200 import chain_operator
+    P = U.Problem(regime="stress", **U.CONFIGS["c2_scg50"])
+    dyn = P.product(seed=21)
+    n, K = 300, 3
+    x = torch.as_tensor(P.x0(n, np.random.default_rng(4))).cuda()
+    dyn._ensure_ctx()
+    c0, l0 = dyn._counter, dyn.launch_count
+    fx, fv, p, outs = chain_operator(x, dyn, K, do_mh_step=True)
+    assert dyn.launch_count - l0 == 1 and dyn._counter == c0 + K
+    import ctypes as C
+    vs, ds = [], []
+    for s in range(K + 1):   # counters c0 .. c0+K-1: the sub-proposals; c0+K: init_v
+        v = torch.empty((n, P.D), device="cuda")
+        d = torch.empty((n,), dtype=torch.uint8, device="cuda")
+        u = torch.empty((n,), device="cuda")
+        dyn._chk(dyn._lib.l2hmc_philox_fill(dyn._ctx, n, 0, dyn.seed, c0 + s, v.data_ptr(), d.data_ptr(), u.data_ptr(), dyn._stream()))
+        vs.append(v); ds.append(d)
+        if s == K - 1:
+            u_last = u
+    rngs = [{"direction": ds[s], "v": vs[s]} for s in range(K)] + [{"u": u_last}]
+    fx2, fv2, p2, outs2 = chain_operator(x, dyn, K, init_v=vs[K], do_mh_step=True, rng=rngs)
+    assert torch.equal(fx, fx2) and torch.equal(fv, fv2) and torch.equal(p, p2) and torch.equal(outs[0], outs2[0])
 
 
 def _load_vae(name):
