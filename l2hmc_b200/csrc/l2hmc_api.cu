@@ -1675,8 +1675,41 @@ extern "C" int l2hmc_timing_read(l2hmc_ctx *ctx, double *avg_ms, int64_t *launch
   return L2HMC_OK;
 }
 
-// ---- training path (train.cuh / train_host.cuh) ------------------------------------------------------------------
+// ---- training path (train.cuh / train_host.cuh; train_small.cuh: the fused kernel for small nets) ----------------
 #include "train_host.cuh"
+#include "train_small.cuh"
+
+static NetRaw grads_as_raw(const l2hmc_net_grads &g) {
+  NetRaw r;
+  r.W1 = g.W1; r.b1 = g.b1; r.W2 = g.W2; r.b2 = g.b2; r.W3 = g.W3; r.b3 = g.b3; r.W4 = g.W4; r.b4 = g.b4;
+  r.Ws = g.Ws; r.bs = g.bs; r.Wt = g.Wt; r.bt = g.bt; r.Wq = g.Wq; r.bq = g.bq; r.ls = g.scale_s; r.lq = g.scale_q;
+  return r;
+}
+
+static int launch_small_train(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
+  small::SmallTrainArgs A;
+  A.base.sh = ctx->sh;
+  A.base.xnet = ctx->net_rawv[0];
+  A.base.vnet = ctx->net_rawv[1];
+  A.base.tbx = ctx->net_dev[0].tb;
+  A.base.tbv = ctx->net_dev[1].tb;
+  A.base.en = ctx->en;
+  A.base.mask = ctx->mask.p;
+  memset(&A.base.io, 0, sizeof(A.base.io));
+  small::TrainIO &t = A.tio;
+  t.n = a->n; t.x = a->x; t.v = a->v; t.dir = a->dir; t.scale = a->scale; t.inv_count = a->inv_count; t.loss_kind = a->loss_kind;
+  t.loss = a->loss; t.d_eps = a->d_eps; t.gx = grads_as_raw(a->grad_xnet); t.gv = grads_as_raw(a->grad_vnet);
+  t.x_out = a->x_out; t.px_out = a->px_out;
+  cudaStream_t s = (cudaStream_t)a->stream;
+  const unsigned blocks = (unsigned)((a->n + small::NT - 1) / small::NT);
+  if (ctx->sh.D <= 2 && ctx->sh.H <= 10)
+    small::small_train_kernel<2, 10, 32><<<blocks, small::NT, small::small_train_smem_bytes<2, 10>(ctx->sh.T), s>>>(A);
+  else
+    small::small_train_kernel<4, 16, 32><<<blocks, small::NT, small::small_train_smem_bytes<4, 16>(ctx->sh.T), s>>>(A);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return L2HMC_OK;
+}
 
 extern "C" int l2hmc_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   int rc = check_ready(ctx, "l2hmc_loss_grad");
@@ -1698,5 +1731,12 @@ extern "C" int l2hmc_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   if (!(a->scale > 0.f) || !isfinite(a->scale) || !(a->inv_count > 0.f) || !isfinite(a->inv_count))
     return fail(ctx, L2HMC_EINVAL, "l2hmc_loss_grad: scale and inv_count must be finite and > 0");
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  // small nets (the notebook's: x_dim <= 4, width <= 16) with a separable loss: the whole batch in ONE launch, one chain
+  // per thread (train_small.cuh); L2HMC_TRAIN_FUSED=0 keeps the launch sequence (the two are compared in the tests)
+  {
+    const char *fe = getenv("L2HMC_TRAIN_FUSED");
+    const bool fused_ok = !(fe && fe[0] == '0') && ctx->sh.D <= 4 && ctx->sh.H <= 16 && ctx->sh.T <= 32 && a->loss_kind <= 1;
+    if (fused_ok) return launch_small_train(ctx, a);
+  }
   return tr_loss_grad(ctx, a);
 }

@@ -1,10 +1,12 @@
 """Training path: the SCG notebook's objective, its gradient and its optimiser loop on the GPU.
 
-FIRST-CORRECT version: the gradient the reference gets from TF1 autodiff --
+SURVEY section 8(f)3; DESIGN.md section 7.1: the gradient the reference gets from TF1 autodiff --
 ``optimizer.minimize(loss)`` (SCGExperiment.ipynb:183-188) through ``propose`` (utils/sampler.py:28-51), ``p_accept``
 (utils/dynamics.py:302-309), the unrolled leapfrog (:246-300) and ``tf.gradients(energy, x)`` inside it (:217-218) -- is
-computed by ``l2hmc_loss_grad`` (csrc/train.cuh: a recorded forward sweep and a hand-written reverse sweep, plain fp32
-FMA GEMMs).  Gaussian, GMM, RoughWell and funnel targets, no aux.  No CPU fallback.
+computed by ``l2hmc_loss_grad``: for the notebook's small nets (x_dim <= 4, width <= 16) ONE launch of a fused kernel
+(csrc/train_small.cuh: one chain per thread, recorded forward sweep and hand-written reverse sweep on chip); for larger
+nets a launch sequence (csrc/train.cuh: plain fp32 FMA GEMMs -- correct, not fast).  Gaussian, GMM, RoughWell and funnel
+targets, no aux.  No CPU fallback.
 
     loss, grads, Lx, px = loss_and_grads(dynamics, x)                  # one propose batch
     state = train_step(dynamics, opt, samples)                         # one iteration of SCGExperiment.ipynb:254-270
@@ -137,8 +139,11 @@ def allreduce_grads(grads, group=None):
 
 class Adam(object):
     """tf.train.AdamOptimizer(learning_rate) with the notebook's schedule
-    tf.train.exponential_decay(1e-3, global_step, 1000, 0.96, staircase=True) (SCGExperiment.ipynb:183-186);
-    moments live on the GPU, the parameters in the Dynamics' layer objects."""
+    tf.train.exponential_decay(1e-3, global_step, 1000, 0.96, staircase=True) (SCGExperiment.ipynb:183-186).
+
+    The S/T/Q nets are small (541 parameters in the notebook, 71.7 k at width 100): the update itself is host arithmetic
+    in float32 (TF's formulation), fed by ONE device-to-host read of the flattened gradients per step; the master
+    parameters live in the Dynamics' layer objects, one ``refresh()`` pushes them back to the library."""
 
     def __init__(self, dynamics, learning_rate=1e-3, decay_steps=1000, decay_rate=0.96, beta1=0.9, beta2=0.999, epsilon=1e-8,
                  eps_trainable=None):
@@ -154,30 +159,39 @@ class Adam(object):
         return self.lr0 * self.decay_rate ** (self.global_step // self.decay_steps)
 
     def _update(self, name, p, g):
+        """p, g: float32 numpy arrays of one variable; returns the new value (float32)."""
+        f32 = np.float32
         m = self._m.get(name)
         if m is None:
-            m = self._m[name] = torch.zeros_like(g)
-            self._v[name] = torch.zeros_like(g)
+            m = self._m[name] = np.zeros_like(g, dtype=f32)
+            self._v[name] = np.zeros_like(g, dtype=f32)
         v = self._v[name]
-        m.mul_(self.b1).add_(g, alpha=1.0 - self.b1)
-        v.mul_(self.b2).addcmul_(g, g, value=1.0 - self.b2)
+        m *= f32(self.b1)
+        m += f32(1.0 - self.b1) * g
+        v *= f32(self.b2)
+        v += f32(1.0 - self.b2) * (g * g)
         t = self.global_step + 1
-        lr_t = self.learning_rate * np.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t)   # TF's formulation
-        return p - lr_t * m / (v.sqrt() + self.epsilon)
+        lr_t = f32(self.learning_rate * np.sqrt(1.0 - self.b2 ** t) / (1.0 - self.b1 ** t))   # TF's formulation
+        return (p - lr_t * m / (np.sqrt(v) + f32(self.epsilon))).astype(f32)
 
     def apply(self, dynamics, grads):
-        dev = grads["loss"].device
+        tensors = [grads["eps"].reshape(-1)] + [grads[key][k].reshape(-1) for key in ("XNet", "VNet") for k in NAMES]
+        flat = torch.cat(tensors).detach().to(torch.float32).cpu().numpy()   # the one device -> host read of the step
+        g_eps = flat[0]
+        o = 1
         for i, key in enumerate(("XNet", "VNet")):
             new = {}
             for k in NAMES:
-                p = torch.as_tensor(np.asarray(dynamics._net_params[i][k], np.float32), device=dev)
-                new[k] = self._update(key + "/" + k, p, grads[key][k].reshape(p.shape)).cpu().numpy()
+                p = np.asarray(dynamics._net_params[i][k], np.float32)
+                g = flat[o:o + p.size].reshape(p.shape)
+                o += p.size
+                new[k] = self._update(key + "/" + k, p, g)
             load_stq_net(dynamics.XNet if i == 0 else dynamics.VNet, new)
         dynamics.refresh()
         if self.eps_trainable:
             # alpha is the stored variable (utils/dynamics.py:50-54): update it directly, no log(exp(.)) round trip
-            alpha = torch.as_tensor(np.float32(dynamics.alpha), device=dev).reshape(1)
-            g_alpha = grads["eps"] * dynamics.eps
+            alpha = np.asarray([dynamics.alpha], np.float32)
+            g_alpha = np.asarray([g_eps * np.float32(dynamics.eps)], np.float32)
             dynamics.set_alpha(float(self._update("alpha", alpha, g_alpha)[0]))
         self.global_step += 1
 

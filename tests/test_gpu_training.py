@@ -227,3 +227,43 @@ def test_sharded_internal_draws_equal_the_single_rank_draws():
     dyn._counter = c0
     wrong = training.loss_and_grads(dyn, xt[90:200].contiguous(), count=200)
     assert not torch.equal(wrong[2], Lx[90:200])
+
+
+@pytest.mark.parametrize("name,n", [("c1_scg2", 200), ("c3_mog2", 333), ("funnel3", 130)])
+def test_fused_small_net_training_kernel_is_one_launch_and_equals_the_launch_sequence(name, n, monkeypatch):
+    """x_dim <= 4 / width <= 16 (the notebook's nets): l2hmc_loss_grad is ONE launch of small_train_kernel (one chain per
+    thread, tape in local memory, gradients reduced once per block); it must agree with the launch-sequence path
+    (L2HMC_TRAIN_FUSED=0: ~200 launches per leapfrog step) and with the oracle's hand-written reverse sweep."""
+    P, x, d, v = _setup(name, n)
+    rng = {"direction": torch.as_tensor(d, device=DEV), "v": torch.as_tensor(v, device=DEV)}
+    xt = torch.as_tensor(x, device=DEV)
+    monkeypatch.delenv("L2HMC_TRAIN_FUSED", raising=False)
+    dyn = P.product()
+    dyn._ensure_ctx()
+    l0 = dyn.launch_count
+    loss, grads, Lx, px = training.loss_and_grads(dyn, xt, rng=rng, scale=0.1)
+    assert dyn.launch_count - l0 == 1
+    monkeypatch.setenv("L2HMC_TRAIN_FUSED", "0")
+    dyn2 = P.product()
+    dyn2._ensure_ctx()
+    l0 = dyn2.launch_count
+    loss2, grads2, Lx2, px2 = training.loss_and_grads(dyn2, xt, rng=rng, scale=0.1)
+    assert dyn2.launch_count - l0 > 100
+    monkeypatch.delenv("L2HMC_TRAIN_FUSED", raising=False)
+    assert float(loss[0]) == pytest.approx(float(loss2[0]), rel=2e-4)
+    assert U.max_rel(Lx.cpu().numpy(), Lx2.cpu().numpy()) < 2e-5 and float((px - px2).abs().max()) < 2e-4
+    loss_o, acc = _oracle(P, x, d, v, 0.1)
+    assert float(loss[0]) == pytest.approx(loss_o, rel=1e-3)
+    assert _worst(grads, acc) < 1e-3
+    assert float(grads["eps"][0]) == pytest.approx(float(acc.eps), rel=5e-3, abs=1e-3 * abs(loss_o))
+    for key in ("XNet", "VNet"):
+        for k in training.NAMES:
+            a, b = grads[key][k], grads2[key][k]
+            assert float((a - b).abs().max()) <= 2e-3 * max(1e-12, float(b.abs().max())), (key, k)
+    # 'standard' is separable too; 'inverse' needs a batch statistic and stays on the launch sequence
+    l0 = dyn.launch_count
+    training.loss_and_grads(dyn, xt, rng=rng, loss="standard")
+    assert dyn.launch_count - l0 == 1
+    l0 = dyn.launch_count
+    training.loss_and_grads(dyn, xt, rng=rng, loss="inverse")
+    assert dyn.launch_count - l0 > 100
