@@ -59,11 +59,6 @@ static_assert(KSLOT_S % 2 == 0, "ring slot = whole A hand-over slots");
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
 
-template <int NQC>
-struct SDims {
-  static constexpr int DP = 4 * NQC;
-  static constexpr int RS = (NQC & 1) ? DP : DP + 4;  // row stride with RS/4 odd: 8 lanes x 16 B hit 32 distinct banks
-};
 
 constexpr int HCS_PER_CHUNK = 20;  // shared-memory copy of the head constants: bs2, bq2, cS, cQ, bth (4 floats each)
 struct TcLayS {
@@ -85,6 +80,12 @@ __host__ __device__ inline TcLayS make_tclay_s(int RS, int DP, int T) {
   return l;
 }
 __host__ __device__ inline int tc_s_row_stride(int DP) { return ((DP / 4) & 1) ? DP : DP + 4; }
+// shapes the TMEM map of this kernel holds (A_hi / A_lo 104 columns each, accumulators 112 + 112 + 80)
+__host__ __device__ inline bool tc_s_shape_fits(int nqc, int nhc) {
+  const int ca = (nqc + 1) / 2, cb = nqc - ca;
+  return nqc >= 2 && nhc >= 2 && 8 * nqc <= 104 && 8 * nhc <= 104 && 12 * ca <= 112 && 12 * cb <= 80 && (8 * nhc + 15) / 16 * 16 <= 112 &&
+         ((nqc > nhc ? nqc : nhc) + 1) / 2 <= NSUB_MAX;
+}
 __host__ __device__ inline size_t tc_s_smem_bytes(int DP, int T, int nslot, int slot_floats) {
   return sizeof(float) * ((size_t)make_tclay_s(tc_s_row_stride(DP), DP, T).ring + (size_t)nslot * slot_floats);
 }
@@ -205,10 +206,10 @@ __device__ __forceinline__ void walk_schedule_s(const TcArgs &A, F &&f) {
 }
 // chunk stream of a GEMM in the specialised image [embed (interleaved rows) | hidden | heads_a | heads_b]; one chunk =
 // one MMA K step (8 k in tf32, 16 k in fp16) = {hi slab, lo slab} = 16 * n 32-bit words either way
-template <int NQC, bool F16>
-__device__ __forceinline__ GemmDesc gemm_desc_s(const TcArgs &A, int kind, int net) {
-  constexpr int CA = (NQC + 1) / 2, CB = NQC - CA;
-  constexpr int N3A = (12 * CA + 15) / 16 * 16, N3B = (12 * CB + 15) / 16 * 16;
+template <bool F16>
+__device__ __forceinline__ GemmDesc gemm_desc_s(const TcArgs &A, const int NQC, int kind, int net) {
+  const int CA = (NQC + 1) / 2, CB = NQC - CA;
+  const int N3A = (12 * CA + 15) / 16 * 16, N3B = (12 * CB + 15) / 16 * 16;
   constexpr int KS = F16 ? 16 : 8;
   const TcDims &td = A.td;
   const TcNet &N = net ? A.vnet : A.xnet;
@@ -232,11 +233,11 @@ __device__ __forceinline__ GemmDesc gemm_desc_s(const TcArgs &A, int kind, int n
 }
 
 // ===================== TMA producer of this schedule (one warp) =====================
-template <int NQC, bool F16>
-__device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, float *ring, uint32_t NSLOT, uint32_t SLOT_FLOATS) {
+template <bool F16>
+__device__ __forceinline__ void producer_loop_s(const TcArgs &A, const int NQC, const Sync &S, float *ring, uint32_t NSLOT, uint32_t SLOT_FLOATS) {
   uint32_t s = 0, ph = 1;
   walk_schedule_s(A, [&](int kind, int net, int it) {
-    const GemmDesc g = gemm_desc_s<NQC, F16>(A, kind, net);
+    const GemmDesc g = gemm_desc_s<F16>(A, NQC, kind, net);
 #pragma unroll 1
     for (int ks = 0; ks < g.nsteps; ks += KSLOT_S) {
       const uint32_t bytes = (uint32_t)g.chunk_floats * 4u * (uint32_t)min(KSLOT_S, g.nsteps - ks);
@@ -266,8 +267,8 @@ __device__ __forceinline__ void producer_loop_s(const TcArgs &A, const Sync &S, 
 // As issuer_loop (uniform datapath, elect.sync), plus: the accumulator region per GEMM, the A operand awaited per K slot
 // (a_sub[K step / 2]; grad: a_sub[K step], its A operand has 4 columns per chunk; heads_b: not at all), and two
 // accumulator-ready barriers used alternately (heads_a and heads_b complete without an epilogue in between).
-template <int NQC, bool F16>
-__device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, uint64_t *a_sub, uint64_t *acc_rdy, int nsub, float *ring,
+template <bool F16>
+__device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const int NQC, const Sync &S, uint64_t *a_sub, uint64_t *acc_rdy, int nsub, float *ring,
                                               uint32_t NSLOT, uint32_t SLOT_FLOATS, int lane) {
   uint32_t s = 0, ph = 0, gi = 0, ai = 0;  // ring slot / phase, GEMM counter, A-operand generation counter
   const uint32_t ring_u32 = smem_u32(ring);
@@ -280,7 +281,7 @@ __device__ __forceinline__ void issuer_loop_s(const TcArgs &A, const Sync &S, ui
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
     const long long w_a0 = w_a, w_f0 = w_f;
 #endif
-    const GemmDesc g = gemm_desc_s<NQC, F16>(A, kind, net);
+    const GemmDesc g = gemm_desc_s<F16>(A, NQC, kind, net);
     const uint32_t acc = s_region(kind);
     const uint32_t idesc = F16 ? make_idesc_f16(128, g.n) : make_idesc_tf32(128, g.n);
     const uint64_t desc0 = make_smem_desc(0u, (uint32_t)(g.n / 8) * 128u, 128u);
@@ -401,16 +402,23 @@ __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.al
 template <int N>
 __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 
-template <int NQC, int NHC, bool FAST, bool BIASG, bool F16>
+// NQC_T / NHC_T > 0: chunk counts fixed at compile time (the benchmark shapes: 13 x 13 = config 2, 8 x 13 = config 4);
+// 0 x 0: read from the launch arguments -- one instantiation for every other (x_dim, width) inside the TMEM map
+// (x_dim <= 52, width <= 104), so that those shapes do not fall to the 2.2x slower generic kernel of kernel_tc.cuh.
+template <int NQC_T, int NHC_T, bool FAST, bool BIASG, bool F16>
 __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const __grid_constant__ TcArgs A) {
+  const int NQC = NQC_T > 0 ? NQC_T : A.sh.DP / 4;
+  const int NHC = NHC_T > 0 ? NHC_T : A.td.HK / 8;
   constexpr int NQ = NQ_S;
   constexpr int NCT = MT * NQ;  // compute threads: NQ per chain
   constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
-  constexpr int DP = SDims<NQC>::DP, RS = SDims<NQC>::RS;
-  constexpr int NSUB = ((NQC > NHC ? NQC : NHC) + 1) / 2;  // K slots (2 K steps) of the deepest GEMM = sub-barriers
-  static_assert(NSUB <= NSUB_MAX, "too many K slots");
-  constexpr int CA = (NQC + 1) / 2, CB = NQC - CA;  // dimension chunks of heads_a / heads_b
-  static_assert(8 * NQC <= 104 && 8 * NHC <= 104 && 12 * CA <= 112 && 12 * CB <= 80 && (8 * NHC + 15) / 16 * 16 <= 112, "TMEM map of kernel_tc_s.cuh");
+  const int DP = 4 * NQC, RS = (NQC & 1) ? DP : DP + 4;  // row stride with RS/4 odd: 8 lanes x 16 B hit 32 distinct banks
+  const int NSUB = ((NQC > NHC ? NQC : NHC) + 1) / 2;  // K slots (2 K steps) of the deepest GEMM = sub-barriers
+  const int CA = (NQC + 1) / 2, CB = NQC - CA;  // dimension chunks of heads_a / heads_b
+  // TMEM map of this kernel (the host checks the same for run-time shapes, tc_s_shape_fits)
+  static_assert(NQC_T == 0 || (8 * NQC_T <= 104 && 12 * ((NQC_T + 1) / 2) <= 112 && 12 * (NQC_T / 2) <= 80), "TMEM map of kernel_tc_s.cuh");
+  static_assert(NHC_T == 0 || (8 * NHC_T <= 104 && (8 * NHC_T + 15) / 16 * 16 <= 112), "TMEM map of kernel_tc_s.cuh");
+  static_assert((NQC_T == 0) == (NHC_T == 0), "chunk counts: both fixed or both run-time");
   constexpr float L2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
   auto compute_bar = []() { compute_bar_n<NCT>(); };
   extern __shared__ __align__(128) float smem[];
@@ -452,8 +460,8 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
 
   if (warp >= W_MMA) {
     if (L2HMC_TC_SETMAXNREG) reg_dec<L2HMC_TC_REGS_AUX>();  // the whole third warpgroup (two of its warps have nothing else to do)
-    if (warp == W_TMA) producer_loop_s<NQC, F16>(A, S, ring, NSLOT, SLOT_FLOATS);
-    else if (warp == W_MMA) issuer_loop_s<NQC, F16>(A, S, a_sub, acc_rdy, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
+    if (warp == W_TMA) producer_loop_s<F16>(A, NQC, S, ring, NSLOT, SLOT_FLOATS);
+    else if (warp == W_MMA) issuer_loop_s<F16>(A, NQC, S, a_sub, acc_rdy, NSUB, ring, NSLOT, SLOT_FLOATS, lane);
   } else {
     // ===================== compute warps =====================
     if (L2HMC_TC_SETMAXNREG) reg_inc<L2HMC_TC_REGS_COMPUTE>();
@@ -774,9 +782,9 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
       // written while heads_b still reads it, and the tensor pipe works on heads_b during part 0.
       auto heads_epilogue = [&](auto mode_c, auto part_c, const int xh, const int next, const TcNet &N, const float *mrow) {
         constexpr int MODE = decltype(mode_c)::value, PART = decltype(part_c)::value;
-        constexpr int CP = PART == 0 ? CA : CB;                                   // chunks of this part
-        constexpr uint32_t cS = PART == 0 ? S_R1 : S_R3 - 4 * CA;                 // S column of chunk q: cS + 4 q
-        constexpr uint32_t cT = cS + 4 * CP, cQ = cS + 8 * CP;
+        const int CP = PART == 0 ? CA : CB;                                   // chunks of this part
+        const uint32_t cS = PART == 0 ? S_R1 : S_R3 - 4 * CA;                 // S column of chunk q: cS + 4 q
+        const uint32_t cT = cS + 4 * CP, cQ = cS + 8 * CP;
         const float hc = MODE == 0 ? 0.5f * eps : eps;
         const float *hcs_net = smem + L.hcs + (MODE == 0 ? NQC * HCS_PER_CHUNK : 0);  // V net (MODE 0) second
         const bool flip = (fwd != (xh == 0));  // MODE 1: k = m, or 1 - m when flipped

@@ -1081,8 +1081,11 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     // shape-specialised compute path (kernel_tc_s.cuh) where an instantiation exists; L2HMC_TC_GENERIC=1 forces the generic one
     const int nqc = ctx->sh.DP / 4, nhc = ctx->td.HK / 8;
     const char *ge = getenv("L2HMC_TC_GENERIC");
+    // fixed-shape instantiations for the benchmark shapes, the run-time-shape instantiation for everything else the
+    // kernel's TMEM map holds (x_dim <= 52, width <= 104)
+    const bool fixed_shape = (nqc == 13 && nhc == 13) || (nqc == 8 && nhc == 13);
     const bool spec = !(ge && ge[0] == '1') && ctx->td.nq == 2 && ctx->tc_net[0].hc && ctx->tc_net[1].hc &&
-                      ((nqc == 13 && nhc == 13) || (nqc == 8 && nhc == 13));
+                      (fixed_shape || tc::tc_s_shape_fits(nqc, nhc));
     const unsigned blocks = (unsigned)((a->n + tc::MT - 1) / tc::MT);
     if (spec) {
       const long long state_bytes = (long long)tc::make_tclay_s(tc::tc_s_row_stride(ctx->sh.DP), ctx->sh.DP, ctx->sh.T).ring * 4;
@@ -1106,6 +1109,8 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
         L2HMC_TC_S_ATTR(13, 13, false, false, true); L2HMC_TC_S_ATTR(13, 13, false, false, false);
         L2HMC_TC_S_ATTR(8, 13, true, false, true); L2HMC_TC_S_ATTR(8, 13, true, false, false);
         L2HMC_TC_S_ATTR(8, 13, false, false, true); L2HMC_TC_S_ATTR(8, 13, false, false, false);
+        L2HMC_TC_S_ATTR(0, 0, true, false, true); L2HMC_TC_S_ATTR(0, 0, true, false, false);
+        L2HMC_TC_S_ATTR(0, 0, false, false, true); L2HMC_TC_S_ATTR(0, 0, false, false, false);
 #undef L2HMC_TC_S_ATTR
         tc_s_configured = smem;
       }
@@ -1121,7 +1126,7 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
       TA.td.f16 = h16 ? 1 : 0;
       ctx->tc_used_f16 = h16;
 #define L2HMC_TC_S_LAUNCH(Q, HH, F, B, X) tc::tc_transition_kernel_s<Q, HH, F, B, X><<<blocks, nthreads, smem, stream>>>(TA)
-      if (nqc == 13) {
+      if (nqc == 13 && nhc == 13) {
         if (bg) {
           if (fm) { if (h16) L2HMC_TC_S_LAUNCH(13, 13, true, true, true); else L2HMC_TC_S_LAUNCH(13, 13, true, true, false); }
           else { if (h16) L2HMC_TC_S_LAUNCH(13, 13, false, true, true); else L2HMC_TC_S_LAUNCH(13, 13, false, true, false); }
@@ -1129,10 +1134,14 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
           if (fm) { if (h16) L2HMC_TC_S_LAUNCH(13, 13, true, false, true); else L2HMC_TC_S_LAUNCH(13, 13, true, false, false); }
           else { if (h16) L2HMC_TC_S_LAUNCH(13, 13, false, false, true); else L2HMC_TC_S_LAUNCH(13, 13, false, false, false); }
         }
-      } else {
+      } else if (nqc == 8 && nhc == 13) {
         if (bg) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: no bias-in-GEMM instantiation for this shape");
         if (fm) { if (h16) L2HMC_TC_S_LAUNCH(8, 13, true, false, true); else L2HMC_TC_S_LAUNCH(8, 13, true, false, false); }
         else { if (h16) L2HMC_TC_S_LAUNCH(8, 13, false, false, true); else L2HMC_TC_S_LAUNCH(8, 13, false, false, false); }
+      } else {  // chunk counts read from the arguments
+        if (bg) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: no bias-in-GEMM instantiation for this shape");
+        if (fm) { if (h16) L2HMC_TC_S_LAUNCH(0, 0, true, false, true); else L2HMC_TC_S_LAUNCH(0, 0, true, false, false); }
+        else { if (h16) L2HMC_TC_S_LAUNCH(0, 0, false, false, true); else L2HMC_TC_S_LAUNCH(0, 0, false, false, false); }
       }
 #undef L2HMC_TC_S_LAUNCH
     } else {

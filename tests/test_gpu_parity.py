@@ -586,3 +586,30 @@ def test_host_entry_point_returns_accept_statistics():
         out = dyn.transition_host(x, counter=7, stats=st)
         assert st[1] == float(out["accepted"].sum())
         assert abs(st[0] - float(out["px"].astype(np.float64).sum())) <= 1e-4 * max(1.0, st[0])
+
+
+@pytest.mark.parametrize("kind,D,H,T", [("gaussian", 20, 64, 6), ("gaussian", 40, 100, 5), ("gaussian", 16, 32, 8), ("roughwell", 50, 64, 4),
+                                        ("gaussian", 8, 100, 7), ("roughwell", 24, 48, 5), ("gaussian", 33, 72, 3), ("gaussian", 50, 88, 4)])
+def test_tc_run_time_shape_kernel(kind, D, H, T, monkeypatch):
+    """Every (x_dim <= 52, width <= 104) runs the overlapped tensor-core pipeline of kernel_tc_s.cuh: the chunk counts of
+    the two benchmark shapes are compile-time constants, all other shapes use the instantiation that reads them from the
+    launch arguments (instead of the 2.2x slower generic kernel).  Parity against the oracle, and a different result in the
+    last bits than the generic kernel's (L2HMC_TC_GENERIC=1) proves which one ran."""
+    kw = dict(mu=np.full(D, 0.3)) if kind == "gaussian" else dict(easy=True)
+    P = U.Problem(kind=kind, D=D, H=H, T=T, eps=0.1, regime="stress", **kw)
+    monkeypatch.delenv("L2HMC_TC_GENERIC", raising=False)
+    dyn = P.product(kernel="tc")
+    rep, (d, r64, r32, rk) = U.parity_report(P, 300, dyn=dyn)
+    assert dyn.kernel_name in ("tc_3xf16", "tc_3xtf32")
+    _check(rep)
+    assert not dyn.fp16_range_exceeded()
+    monkeypatch.setenv("L2HMC_TC_GENERIC", "1")
+    gen = U.run_kernel_propose(P, d, dyn=P.product(kernel="tc"))
+    monkeypatch.delenv("L2HMC_TC_GENERIC", raising=False)
+    assert U.max_rel(gen["Lx"], rk["Lx"]) <= SAMPLE_TOL and not np.array_equal(gen["Lx"], rk["Lx"])
+    # fused multi-transition launch and chain mode on a run-time shape
+    x = torch.as_tensor(d["x"]).cuda()
+    o3 = dyn._transition(x, dir_mode=3, do_mh=True, n_transitions=2, counter=5)
+    s1 = dyn._transition(x, dir_mode=3, do_mh=True, counter=5)
+    s2 = dyn._transition(s1["x_next"], dir_mode=3, do_mh=True, counter=6)
+    assert torch.equal(o3["x_next"], s2["x_next"])
