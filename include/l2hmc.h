@@ -51,7 +51,8 @@ typedef enum {
   L2HMC_ENERGY_GMM = 1,       /* GMM.get_energy_function            utils/distributions.py:125-134 */
   L2HMC_ENERGY_ROUGHWELL = 2, /* RoughWell.get_energy_function      utils/distributions.py:90-97   */
   L2HMC_ENERGY_FUNNEL = 3,    /* GaussianFunnel.get_energy_function utils/distributions.py:161-180 */
-  L2HMC_ENERGY_DECODER = 4    /* energy(z, aux) of the VAE posterior target   mnist_vae.py:104-126 (l2hmc_set_energy_decoder) */
+  L2HMC_ENERGY_DECODER = 4,   /* energy(z, aux) of the VAE posterior target   mnist_vae.py:104-126 (l2hmc_set_energy_decoder) */
+  L2HMC_ENERGY_MIXED = 5      /* (1 - beta) U_a + beta U_b of two closed-form kinds: curr_energy of utils/ais.py:44-45 (l2hmc_set_energy_mixed) */
 } l2hmc_energy_kind;
 
 typedef enum { L2HMC_XNET = 0, L2HMC_VNET = 1 } l2hmc_net_id; /* utils/dynamics.py:78-79 */
@@ -165,6 +166,19 @@ int l2hmc_set_likelihood_scale(l2hmc_ctx *ctx, float beta);
  *  FUNNEL   : scalars[0] = sigma (2.0), scalars[1] = clip (8.0) */
 int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const float *mu, const float *S,
                      const float *logc, const float *scalars, int n_scalars);
+
+/* The annealed energy of annealed importance sampling, utils/ais.py:44-45:
+ *   curr_energy(z) = (1 - beta) * init_energy(z) + beta * final_energy(z)
+ * for two closed-form energies (kinds GAUSSIAN / GMM / ROUGHWELL / FUNNEL, each described like the arguments of
+ * l2hmc_set_energy).  Evaluated per chain inside the fused kernels (small / tile; HMC-mode Dynamics as utils/ais.py:58
+ * builds them); l2hmc_set_mix_beta moves beta between annealing steps without re-sending the parameters. */
+typedef struct {
+  int32_t kind, n_comp;
+  const float *mu, *S, *logc, *scalars;
+  int32_t n_scalars;
+} l2hmc_energy_desc;
+int l2hmc_set_energy_mixed(l2hmc_ctx *ctx, const l2hmc_energy_desc *a, const l2hmc_energy_desc *b, float beta);
+int l2hmc_set_mix_beta(l2hmc_ctx *ctx, float beta);
 
 /* energy(z, aux) = sum_pix sigmoid_cross_entropy_with_logits(labels=aux, logits=decoder(z)) + 0.5 |z|^2
  * (mnist_vae.py:122-126) with decoder = Linear, softplus, ..., Linear (mnist_vae.py:104-111).

@@ -110,7 +110,12 @@ class TransitionArgs(C.Structure):
                 ("stats", C.c_void_p), ("trace", C.c_void_p), ("chain", C.c_int32), ("v0", C.c_void_p)]
 
 
-ENERGY_GAUSSIAN, ENERGY_GMM, ENERGY_ROUGHWELL, ENERGY_FUNNEL, ENERGY_DECODER = 0, 1, 2, 3, 4
+ENERGY_GAUSSIAN, ENERGY_GMM, ENERGY_ROUGHWELL, ENERGY_FUNNEL, ENERGY_DECODER, ENERGY_MIXED = 0, 1, 2, 3, 4, 5
+
+
+class EnergyDesc(C.Structure):   # l2hmc_energy_desc
+    _fields_ = [("kind", C.c_int32), ("n_comp", C.c_int32), ("mu", C.POINTER(C.c_float)), ("S", C.POINTER(C.c_float)),
+                ("logc", C.POINTER(C.c_float)), ("scalars", C.POINTER(C.c_float)), ("n_scalars", C.c_int32)]
 XNET, VNET = 0, 1
 DIR_FORWARD, DIR_BACKWARD, DIR_PER_CHAIN, DIR_RANDOM = 0, 1, 2, 3
 KERNEL_AUTO, KERNEL_TILE, KERNEL_SMALL, KERNEL_TC, KERNEL_LAYERED, KERNEL_LAYERED_FMA = 0, 1, 2, 3, 4, 5
@@ -128,6 +133,8 @@ EXPORTS = [
     ("l2hmc_set_temperature", C.c_int, [_vp, _f32]),
     ("l2hmc_set_likelihood_scale", C.c_int, [_vp, _f32]),
     ("l2hmc_set_energy", C.c_int, [_vp, C.c_int, C.c_int, _fp, _fp, _fp, _fp, C.c_int]),
+    ("l2hmc_set_energy_mixed", C.c_int, [_vp, C.POINTER(EnergyDesc), C.POINTER(EnergyDesc), C.c_float]),
+    ("l2hmc_set_mix_beta", C.c_int, [_vp, C.c_float]),
     ("l2hmc_set_energy_decoder", C.c_int, [_vp, C.c_int, C.POINTER(_i32), C.POINTER(_fp), C.POINTER(_fp)]),
     ("l2hmc_set_aux_encoder", C.c_int, [_vp, C.c_int, C.POINTER(_i32), C.POINTER(_fp), C.POINTER(_fp)]),
     ("l2hmc_bind_aux", C.c_int, [_vp, _i64, _vp]),

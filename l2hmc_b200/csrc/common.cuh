@@ -37,7 +37,14 @@ struct EnergyDev {
   const float *logc;  // [ncomp]
   float s0, s1;       // ROUGHWELL: eps, denominator (eps or eps*eps) ; FUNNEL: sigma, clip
   float temperature;  // Dynamics.energy divides by it (utils/dynamics.py:203-212)
+  // kind 5 (MIXED): U = (1 - beta) U_a + beta U_b, the annealed energy of utils/ais.py:44-45.  U_a: kind_a with the fields
+  // above; U_b: kind_b with the fields below.
+  int kind_a, kind_b, ncomp_b;
+  const float *mu_b, *Ssym_b, *logc_b;
+  float s0_b, s1_b, beta;
 };
+constexpr int ENERGY_KIND_MIXED = 5;
+constexpr int MIX_MAXD = 64;  // the fused kernels that evaluate energies per chain cover x_dim <= 64
 
 struct Shape {
   int D, DP;    // x_dim and x_dim rounded up to a multiple of 4
@@ -193,39 +200,45 @@ __device__ __forceinline__ float accept_prob(float e_old, float e_new, float log
 // Per-chain (scalar) energies and gradients, x given as a strided column: x[d*stride].
 // Used by the component kernels and by the tile kernel for the non-GEMM energy kinds.
 // ---------------------------------------------------------------------------------------------
-__device__ __noinline__ float energy_chain(const EnergyDev &en, const Shape &sh, const float *x, int stride) {
+// One closed-form kind; `part` selects which parameter set of the descriptor it reads (0: the primary fields, 1: the _b fields
+// of a mixed energy).  No division by the temperature here.
+__device__ __noinline__ float energy_one(const EnergyDev &en, int part, const Shape &sh, const float *x, int stride) {
   const int D = sh.D;
   float U = 0.f;
-  switch (en.kind) {
+  const int kind = part ? en.kind_b : (en.kind == ENERGY_KIND_MIXED ? en.kind_a : en.kind);
+  const int ncomp = part ? en.ncomp_b : en.ncomp;
+  const float *en_mu = part ? en.mu_b : en.mu, *en_S = part ? en.Ssym_b : en.Ssym, *en_logc = part ? en.logc_b : en.logc;
+  const float s0 = part ? en.s0_b : en.s0, s1 = part ? en.s1_b : en.s1;
+  switch (kind) {
     case 0: {  // Gaussian: 0.5 * d S d^T (utils/distributions.py:31-32)
       for (int j = 0; j < D; ++j) {
         float r = 0.f;
-        for (int i = 0; i < D; ++i) r = fmaf(x[i * stride] - en.mu[i], en.Ssym[i * sh.LDS + j], r);
-        U = fmaf(r, x[j * stride] - en.mu[j], U);
+        for (int i = 0; i < D; ++i) r = fmaf(x[i * stride] - en_mu[i], en_S[i * sh.LDS + j], r);
+        U = fmaf(r, x[j * stride] - en_mu[j], U);
       }
       U *= 0.5f;
     } break;
     case 1: {  // GMM: -logsumexp_i(-q_i + log c_i) (utils/distributions.py:125-134)
       float V[MAX_COMP];
       float mx = -INFINITY;
-      for (int c = 0; c < en.ncomp; ++c) {
-        const float *mu = en.mu + c * sh.DP;
-        const float *S = en.Ssym + (size_t)c * sh.DP * sh.LDS;
+      for (int c = 0; c < ncomp; ++c) {
+        const float *mu = en_mu + c * sh.DP;
+        const float *S = en_S + (size_t)c * sh.DP * sh.LDS;
         float q = 0.f;
         for (int j = 0; j < D; ++j) {
           float r = 0.f;
           for (int i = 0; i < D; ++i) r = fmaf(x[i * stride] - mu[i], S[i * sh.LDS + j], r);
           q = fmaf(r, x[j * stride] - mu[j], q);
         }
-        V[c] = -0.5f * q + en.logc[c];
+        V[c] = -0.5f * q + en_logc[c];
         mx = fmaxf(mx, V[c]);
       }
       float s = 0.f;
-      for (int c = 0; c < en.ncomp; ++c) s += expf(V[c] - mx);
+      for (int c = 0; c < ncomp; ++c) s += expf(V[c] - mx);
       U = -(logf(s) + mx);
     } break;
     case 2: {  // RoughWell (utils/distributions.py:90-97)
-      const float e = en.s0, den = en.s1;
+      const float e = s0, den = s1;
       float n = 0.f, cs = 0.f;
       for (int i = 0; i < D; ++i) {
         float xi = x[i * stride];
@@ -235,7 +248,7 @@ __device__ __noinline__ float energy_chain(const EnergyDev &en, const Shape &sh,
       U = 0.5f * n + e * cs;
     } break;
     case 3: {  // GaussianFunnel (utils/distributions.py:161-180)
-      const float sigma = en.s0, clip = en.s1;
+      const float sigma = s0, clip = s1;
       const float v = x[0];
       const float vs = v / sigma;
       const float lpv = vs * vs;
@@ -250,63 +263,81 @@ __device__ __noinline__ float energy_chain(const EnergyDev &en, const Shape &sh,
     } break;
     default: break;
   }
-  return U / en.temperature;
+  return U;
+}
+
+// U(x) / temperature for the configured energy; kind 5 mixes two closed-form kinds (utils/ais.py:44-45), no recursion (the
+// per-thread stack stays statically sized).
+__device__ __forceinline__ float energy_chain(const EnergyDev &en, const Shape &sh, const float *x, int stride) {
+  if (en.kind == ENERGY_KIND_MIXED)
+    return ((1.f - en.beta) * energy_one(en, 0, sh, x, stride) + en.beta * energy_one(en, 1, sh, x, stride)) / en.temperature;
+  return energy_one(en, 0, sh, x, stride) / en.temperature;
 }
 
 // g[d*gstride] = dU/dx_d / temperature
-__device__ __noinline__ void grad_chain(const EnergyDev &en, const Shape &sh, const float *x, int stride,
-                                  float *g, int gstride) {
+// mode 0: g = dU/dx / T (one closed-form kind).  Mixed energy: mode 1 writes g = w * dU_a/dx, mode 2 finishes
+// g = (g + w * dU_b/dx) / T, so no per-thread scratch array is needed.
+__device__ __forceinline__ void grad_emit(float *g, float val, float w, float T, int mode) {
+  *g = mode == 0 ? val / T : (mode == 1 ? w * val : (*g + w * val) / T);
+}
+
+__device__ __noinline__ void grad_one(const EnergyDev &en, int part, const Shape &sh, const float *x, int stride,
+                                      float *g, int gstride, float w, int mode) {
   const int D = sh.D;
   const float T = en.temperature;
-  switch (en.kind) {
+  const int kind = part ? en.kind_b : (en.kind == ENERGY_KIND_MIXED ? en.kind_a : en.kind);
+  const int ncomp = part ? en.ncomp_b : en.ncomp;
+  const float *en_mu = part ? en.mu_b : en.mu, *en_S = part ? en.Ssym_b : en.Ssym, *en_logc = part ? en.logc_b : en.logc;
+  const float s0 = part ? en.s0_b : en.s0, s1 = part ? en.s1_b : en.s1;
+  switch (kind) {
     case 0: {
       for (int j = 0; j < D; ++j) {
         float r = 0.f;
-        for (int i = 0; i < D; ++i) r = fmaf(x[i * stride] - en.mu[i], en.Ssym[i * sh.LDS + j], r);
-        g[j * gstride] = r / T;
+        for (int i = 0; i < D; ++i) r = fmaf(x[i * stride] - en_mu[i], en_S[i * sh.LDS + j], r);
+        grad_emit(g + j * gstride, r, w, T, mode);
       }
     } break;
     case 1: {
       float V[MAX_COMP];
       float mx = -INFINITY;
-      for (int c = 0; c < en.ncomp; ++c) {
-        const float *mu = en.mu + c * sh.DP;
-        const float *S = en.Ssym + (size_t)c * sh.DP * sh.LDS;
+      for (int c = 0; c < ncomp; ++c) {
+        const float *mu = en_mu + c * sh.DP;
+        const float *S = en_S + (size_t)c * sh.DP * sh.LDS;
         float q = 0.f;
         for (int j = 0; j < D; ++j) {
           float r = 0.f;
           for (int i = 0; i < D; ++i) r = fmaf(x[i * stride] - mu[i], S[i * sh.LDS + j], r);
           q = fmaf(r, x[j * stride] - mu[j], q);
         }
-        V[c] = -0.5f * q + en.logc[c];
+        V[c] = -0.5f * q + en_logc[c];
         mx = fmaxf(mx, V[c]);
       }
       float s = 0.f;
-      for (int c = 0; c < en.ncomp; ++c) {
+      for (int c = 0; c < ncomp; ++c) {
         V[c] = expf(V[c] - mx);
         s += V[c];
       }
       for (int j = 0; j < D; ++j) {
         float acc = 0.f;
-        for (int c = 0; c < en.ncomp; ++c) {
-          const float *mu = en.mu + c * sh.DP;
-          const float *S = en.Ssym + (size_t)c * sh.DP * sh.LDS;
+        for (int c = 0; c < ncomp; ++c) {
+          const float *mu = en_mu + c * sh.DP;
+          const float *S = en_S + (size_t)c * sh.DP * sh.LDS;
           float r = 0.f;
           for (int i = 0; i < D; ++i) r = fmaf(x[i * stride] - mu[i], S[i * sh.LDS + j], r);
           acc = fmaf(V[c] / s, r, acc);
         }
-        g[j * gstride] = acc / T;
+        grad_emit(g + j * gstride, acc, w, T, mode);
       }
     } break;
     case 2: {
-      const float e = en.s0, den = en.s1;
+      const float e = s0, den = s1;
       for (int i = 0; i < D; ++i) {
         float xi = x[i * stride];
-        g[i * gstride] = (xi - e * sinf(xi / den) / den) / T;
+        grad_emit(g + i * gstride, xi - e * sinf(xi / den) / den, w, T, mode);
       }
     } break;
     case 3: {
-      const float sigma = en.s0, clip = en.s1;
+      const float sigma = s0, clip = s1;
       const float v = x[0];
       float ss = 0.f;
       for (int i = 1; i < D; ++i) ss = fmaf(x[i * stride], x[i * stride], ss);
@@ -316,10 +347,20 @@ __device__ __noinline__ void grad_chain(const EnergyDev &en, const Shape &sh, co
       float gv = v / (sigma * sigma) + 0.5f * (-ss / s + n);
       if (hi) { s = expf(clip); gv = v / (sigma * sigma); }
       if (lo) { s = expf(-clip); gv = v / (sigma * sigma); }
-      g[0] = gv / T;
-      for (int i = 1; i < D; ++i) g[i * gstride] = (x[i * stride] / s) / T;
+      grad_emit(g, gv, w, T, mode);
+      for (int i = 1; i < D; ++i) grad_emit(g + i * gstride, x[i * stride] / s, w, T, mode);
     } break;
     default: break;
+  }
+}
+
+// g[d*gstride] = dU/dx_d / temperature for the configured energy (kind 5: (1 - beta) dU_a + beta dU_b, utils/ais.py:44-45)
+__device__ __forceinline__ void grad_chain(const EnergyDev &en, const Shape &sh, const float *x, int stride, float *g, int gstride) {
+  if (en.kind == ENERGY_KIND_MIXED) {
+    grad_one(en, 0, sh, x, stride, g, gstride, 1.f - en.beta, 1);
+    grad_one(en, 1, sh, x, stride, g, gstride, en.beta, 2);
+  } else {
+    grad_one(en, 0, sh, x, stride, g, gstride, 1.f, 0);
   }
 }
 

@@ -84,7 +84,7 @@ struct l2hmc_ctx {
   DevBuf mask;
   DevBuf train_ws;       // scratch of l2hmc_loss_grad (train_host.cuh), grown on demand, kept until destroy
   bool mask_set = false;
-  DevBuf energy_buf;
+  DevBuf energy_buf, energy_buf2;  // energy_buf2: the second part of a mixed energy
   EnergyDev en;
   bool energy_set = false;
   int64_t launches = 0;
@@ -594,6 +594,8 @@ static int resolve_kernel(l2hmc_ctx *ctx, int *out) {
   if (k == L2HMC_KERNEL_AUTO)
     k = needs_layered ? L2HMC_KERNEL_LAYERED
                       : (small_ok ? L2HMC_KERNEL_SMALL : (tc_auto ? L2HMC_KERNEL_TC : L2HMC_KERNEL_TILE));
+  if (ctx->energy_set && ctx->en.kind == L2HMC_ENERGY_MIXED && k != L2HMC_KERNEL_SMALL && k != L2HMC_KERNEL_TILE)
+    return fail(ctx, L2HMC_EUNSUPPORTED, "a mixed (annealed) energy is evaluated by the small and tile kernels (x_dim <= 64)");
   if (k != L2HMC_KERNEL_LAYERED && ((ctx->energy_set && ctx->en.kind == L2HMC_ENERGY_DECODER) || ctx->lay.enc.n_layers > 0))
     return fail(ctx, L2HMC_EUNSUPPORTED, "the decoder energy and aux-conditioned nets run on the layered engine only");
   if (k == L2HMC_KERNEL_LAYERED) {
@@ -682,7 +684,7 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
   DevBuf *bufs[] = {&ctx->net_packed[0], &ctx->net_packed[1], &ctx->net_raw[0], &ctx->net_raw[1], &ctx->mask,
-                    &ctx->energy_buf, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn,
+                    &ctx->energy_buf, &ctx->energy_buf2, &ctx->hx, &ctx->hv, &ctx->hu, &ctx->hxo, &ctx->hvo, &ctx->hpx, &ctx->hxn,
                     &ctx->tc_buf[0], &ctx->tc_buf[1], &ctx->tc_gbuf, &ctx->tc_hc[0], &ctx->tc_hc[1], &ctx->train_ws, &ctx->hstats};
   for (DevBuf *b : bufs)
     if (b->p) cudaFree(b->p);
@@ -875,20 +877,23 @@ extern "C" int l2hmc_set_temperature(l2hmc_ctx *ctx, float t) {
   return L2HMC_OK;
 }
 
-extern "C" int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const float *mu, const float *S,
-                                const float *logc, const float *scalars, int n_scalars) {
-  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: null context");
-  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+// one closed-form energy into a device buffer: fills kind-specific fields of `out` (ncomp, mu, Ssym, logc, s0, s1)
+struct EnergyOne {
+  int kind = -1, ncomp = 1;
+  const float *mu = nullptr, *Ssym = nullptr, *logc = nullptr;
+  float s0 = 0.f, s1 = 0.f;
+  size_t nmu = 0;  // offset of Ssym inside the packed host image (for the tensor-core Gaussian image)
+};
+
+static int pack_energy_one(l2hmc_ctx *ctx, const char *who, int kind, int n_comp, const float *mu, const float *S, const float *logc,
+                           const float *scalars, int n_scalars, DevBuf &dbuf, EnergyOne *out, std::vector<float> *host_image) {
   const Shape &sh = ctx->sh;
-  EnergyDev en = ctx->en;
-  en.kind = kind;
-  en.ncomp = 1;
-  en.mu = en.Ssym = en.logc = nullptr;
-  en.s0 = en.s1 = 0.f;
+  EnergyOne e;
+  e.kind = kind;
   if (kind == L2HMC_ENERGY_GAUSSIAN || kind == L2HMC_ENERGY_GMM) {
     if (kind == L2HMC_ENERGY_GAUSSIAN) n_comp = 1;
-    if (n_comp < 1 || n_comp > MAX_COMP) return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_energy: 1 <= n_comp <= %d", MAX_COMP);
-    if (!mu || !S || (kind == L2HMC_ENERGY_GMM && !logc)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: null parameter array");
+    if (n_comp < 1 || n_comp > MAX_COMP) return fail(ctx, L2HMC_EUNSUPPORTED, "%s: 1 <= n_comp <= %d", who, MAX_COMP);
+    if (!mu || !S || (kind == L2HMC_ENERGY_GMM && !logc)) return fail(ctx, L2HMC_EINVAL, "%s: null parameter array", who);
     const size_t nmu = (size_t)n_comp * sh.DP, nS = (size_t)n_comp * sh.DP * sh.LDS, nc = round_up(n_comp, 4);
     std::vector<float> buf(nmu + nS + nc, 0.f);
     for (int c = 0; c < n_comp; ++c) {
@@ -900,32 +905,82 @@ extern "C" int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const floa
       if (logc) buf[nmu + nS + c] = logc[c];
     }
     for (float f : buf)
-      if (!isfinite(f)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: non-finite parameter");
-    int rc = ensure(ctx, ctx->energy_buf, buf.size());
+      if (!isfinite(f)) return fail(ctx, L2HMC_EINVAL, "%s: non-finite parameter", who);
+    int rc = ensure(ctx, dbuf, buf.size());
     if (rc) return rc;
-    CUDA_TRY(ctx, cudaMemcpy(ctx->energy_buf.p, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
-    if (ctx->tc_ok && kind == L2HMC_ENERGY_GAUSSIAN) {
-      rc = tc_pack_gaussian(ctx, buf.data() + nmu);
-      if (rc) return rc;
-    }
-    en.ncomp = n_comp;
-    en.mu = ctx->energy_buf.p;
-    en.Ssym = en.mu + nmu;
-    en.logc = en.Ssym + nS;
+    CUDA_TRY(ctx, cudaMemcpy(dbuf.p, buf.data(), buf.size() * sizeof(float), cudaMemcpyHostToDevice));
+    e.ncomp = n_comp;
+    e.mu = dbuf.p;
+    e.Ssym = e.mu + nmu;
+    e.logc = e.Ssym + nS;
+    e.nmu = nmu;
+    if (host_image) host_image->swap(buf);
   } else if (kind == L2HMC_ENERGY_ROUGHWELL || kind == L2HMC_ENERGY_FUNNEL) {
-    if (!scalars || n_scalars < 2) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: need 2 scalars");
-    en.s0 = scalars[0];
-    en.s1 = scalars[1];
-    if (kind == L2HMC_ENERGY_FUNNEL && sh.D < 2) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: funnel needs x_dim >= 2");
+    if (!scalars || n_scalars < 2) return fail(ctx, L2HMC_EINVAL, "%s: need 2 scalars", who);
+    e.s0 = scalars[0];
+    e.s1 = scalars[1];
+    if (kind == L2HMC_ENERGY_FUNNEL && sh.D < 2) return fail(ctx, L2HMC_EINVAL, "%s: funnel needs x_dim >= 2", who);
   } else {
-    return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_energy: unknown energy kind %d", kind);
+    return fail(ctx, L2HMC_EUNSUPPORTED, "%s: unknown energy kind %d", who, kind);
   }
+  *out = e;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_energy(l2hmc_ctx *ctx, int kind, int n_comp, const float *mu, const float *S,
+                                const float *logc, const float *scalars, int n_scalars) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy: null context");
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  EnergyOne e;
+  std::vector<float> img;
+  int rc = pack_energy_one(ctx, "l2hmc_set_energy", kind, n_comp, mu, S, logc, scalars, n_scalars, ctx->energy_buf, &e, &img);
+  if (rc) return rc;
+  if (ctx->tc_ok && kind == L2HMC_ENERGY_GAUSSIAN) {
+    rc = tc_pack_gaussian(ctx, img.data() + e.nmu);
+    if (rc) return rc;
+  }
+  EnergyDev en = ctx->en;
+  en.kind = e.kind; en.ncomp = e.ncomp; en.mu = e.mu; en.Ssym = e.Ssym; en.logc = e.logc; en.s0 = e.s0; en.s1 = e.s1;
   ctx->en = en;
   ctx->energy_set = true;
   {
     int k = ctx->kernel;
     if (resolve_kernel(ctx, &k) == L2HMC_OK) ctx->kernel = k;  // AUTO may now pick the tensor-core kernel
   }
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_energy_mixed(l2hmc_ctx *ctx, const l2hmc_energy_desc *a, const l2hmc_energy_desc *b, float beta) {
+  if (!ctx || !a || !b) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy_mixed: null argument");
+  if (!(beta >= 0.f && beta <= 1.f)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_energy_mixed: beta must be in [0, 1]");
+  if (ctx->sh.DP > MIX_MAXD) return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_set_energy_mixed: x_dim <= %d", MIX_MAXD);
+  CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
+  EnergyOne ea, eb;
+  int rc = pack_energy_one(ctx, "l2hmc_set_energy_mixed (a)", a->kind, a->n_comp, a->mu, a->S, a->logc, a->scalars, a->n_scalars,
+                           ctx->energy_buf, &ea, nullptr);
+  if (rc) return rc;
+  rc = pack_energy_one(ctx, "l2hmc_set_energy_mixed (b)", b->kind, b->n_comp, b->mu, b->S, b->logc, b->scalars, b->n_scalars,
+                       ctx->energy_buf2, &eb, nullptr);
+  if (rc) return rc;
+  EnergyDev en = ctx->en;
+  en.kind = L2HMC_ENERGY_MIXED;
+  en.kind_a = ea.kind; en.ncomp = ea.ncomp; en.mu = ea.mu; en.Ssym = ea.Ssym; en.logc = ea.logc; en.s0 = ea.s0; en.s1 = ea.s1;
+  en.kind_b = eb.kind; en.ncomp_b = eb.ncomp; en.mu_b = eb.mu; en.Ssym_b = eb.Ssym; en.logc_b = eb.logc; en.s0_b = eb.s0; en.s1_b = eb.s1;
+  en.beta = beta;
+  ctx->en = en;
+  ctx->energy_set = true;
+  int k = ctx->kernel;
+  rc = resolve_kernel(ctx, &k);
+  if (rc) return rc;
+  ctx->kernel = k;
+  return L2HMC_OK;
+}
+
+extern "C" int l2hmc_set_mix_beta(l2hmc_ctx *ctx, float beta) {
+  if (!ctx) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_mix_beta: null context");
+  if (!ctx->energy_set || ctx->en.kind != L2HMC_ENERGY_MIXED) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_mix_beta: the energy is not a mixed one");
+  if (!(beta >= 0.f && beta <= 1.f)) return fail(ctx, L2HMC_EINVAL, "l2hmc_set_mix_beta: beta must be in [0, 1]");
+  ctx->en.beta = beta;
   return L2HMC_OK;
 }
 

@@ -54,6 +54,20 @@ class EnergyFunction(object):
         return self._evaluator(x.device.index).energy(x)
 
 
+class MixedEnergy(EnergyFunction):
+    """``curr_energy`` of utils/ais.py:44-45: (1 - beta) * init_energy(z) + beta * final_energy(z) for two closed-form
+    energies of this module; evaluated per chain inside the fused kernels (l2hmc_set_energy_mixed)."""
+
+    def __init__(self, a: EnergyFunction, b: EnergyFunction, beta: float = 0.0):
+        closed = (_lib.ENERGY_GAUSSIAN, _lib.ENERGY_GMM, _lib.ENERGY_ROUGHWELL, _lib.ENERGY_FUNNEL)
+        if not (isinstance(a, EnergyFunction) and isinstance(b, EnergyFunction) and a.kind in closed and b.kind in closed):
+            raise TypeError("MixedEnergy mixes two closed-form energies of l2hmc_b200.distributions")
+        if a.dim != b.dim:
+            raise ValueError("the two energies live in different dimensions (%d, %d)" % (a.dim, b.dim))
+        EnergyFunction.__init__(self, _lib.ENERGY_MIXED, a.dim)
+        self.a, self.b, self.beta = a, b, float(beta)
+
+
 def random_tilted_gaussian(dim, log_min=-2., log_max=2.):
     mu = np.zeros((dim,))
     R = ortho_group.rvs(dim)

@@ -191,12 +191,25 @@ class Dynamics(object):
             self._chk(self._lib.l2hmc_set_energy_decoder(self._ctx, n, w, Wp, bp))
             return
         null = C.POINTER(C.c_float)()
-        mu = _fptr(e.mu) if e.mu is not None else null
-        S = _fptr(e.S) if e.S is not None else null
-        lc = _fptr(e.logc) if e.logc is not None else null
-        sc = _fptr(e.scalars) if e.scalars is not None else null
-        ns = 0 if e.scalars is None else int(e.scalars.size)
+
+        def parts(e):
+            return (_fptr(e.mu) if e.mu is not None else null, _fptr(e.S) if e.S is not None else null,
+                    _fptr(e.logc) if e.logc is not None else null, _fptr(e.scalars) if e.scalars is not None else null,
+                    0 if e.scalars is None else int(e.scalars.size))
+        if e.kind == _lib.ENERGY_MIXED:   # (1 - beta) U_a + beta U_b, utils/ais.py:44-45
+            da, db = (_lib.EnergyDesc(p.kind, p.n_comp, *parts(p)) for p in (e.a, e.b))
+            self._chk(self._lib.l2hmc_set_energy_mixed(self._ctx, C.byref(da), C.byref(db), float(e.beta)))
+            return
+        mu, S, lc, sc, ns = parts(e)
         self._chk(self._lib.l2hmc_set_energy(self._ctx, e.kind, e.n_comp, mu, S, lc, sc, ns))
+
+    def set_mix_beta(self, beta):
+        """Move the weight of a mixed (annealed) energy, utils/ais.py:44-45, without re-sending its parameters."""
+        if getattr(self._fn, "kind", None) != _lib.ENERGY_MIXED:
+            raise TypeError("set_mix_beta applies to distributions.MixedEnergy")
+        self._fn.beta = float(beta)
+        if self._ctx is not None:
+            self._chk(self._lib.l2hmc_set_mix_beta(self._ctx, float(beta)))
 
     def _push_mask(self):
         m = np.ascontiguousarray(self._mask, dtype=NP_FLOAT)

@@ -146,25 +146,39 @@ def save_ais():
     import contextlib
     import io
     ref = ref_loader.load()
-    rng = np.random.default_rng(32)
-    D, n, steps, lf, step = 3, 64, 12, 5, 0.3
-    A = rng.standard_normal((D, D))
-    cov1 = A @ A.T / D + 0.5 * np.eye(D)
-    mu1 = rng.standard_normal(D)
-    with contextlib.redirect_stdout(io.StringIO()):
-        e0 = ref.distributions.Gaussian(np.zeros(D), np.eye(D))
-        e1 = ref.distributions.Gaussian(mu1, cov1)
-    x0 = rng.standard_normal((n, D)).astype(np.float32)
-    v0 = rng.standard_normal((n, D)).astype(np.float32)
-    v_refresh = rng.standard_normal((steps, n, D)).astype(np.float32)
-    u = rng.random((steps, n)).astype(np.float32)
-    arrays = {"meta": _meta(name="ais_gauss3", D=D, n=n, anneal_steps=steps, leapfrogs=lf, step_size=step),
-              "mu1": mu1, "cov1": cov1, "in_x": x0, "in_v0": v0, "in_v_refresh": v_refresh, "in_u": u}
-    for k, v in R.run_ais(e0, e1, steps, x0, v0, v_refresh, u, step, lf, "float64").items():
-        arrays["out_" + k] = v
-    path = os.path.join(HERE, "ref", "ais_gauss3.npz")
-    np.savez_compressed(path, **arrays)
-    return path
+    out = []
+    for name in ("ais_gauss3", "ais_roughwell4"):
+        rng = np.random.default_rng(32 if name == "ais_gauss3" else 33)
+        if name == "ais_gauss3":       # Gaussian -> Gaussian
+            D, n, steps, lf, step = 3, 64, 12, 5, 0.3
+            A = rng.standard_normal((D, D))
+            cov1 = A @ A.T / D + 0.5 * np.eye(D)
+            mu1 = rng.standard_normal(D)
+            with contextlib.redirect_stdout(io.StringIO()):
+                e0 = ref.distributions.Gaussian(np.zeros(D), np.eye(D))
+                e1 = ref.distributions.Gaussian(mu1, cov1)
+            extra = {"mu1": mu1, "cov1": cov1}
+            meta = dict(D=D, n=n, anneal_steps=steps, leapfrogs=lf, step_size=step)
+        else:                          # Gaussian -> rough well: a pair whose mixture is not a Gaussian (utils/ais.py:44-45)
+            D, n, steps, lf, step = 4, 96, 10, 5, 0.2
+            rw_eps = 0.3
+            with contextlib.redirect_stdout(io.StringIO()):
+                e0 = ref.distributions.Gaussian(np.zeros(D), 1.5 * np.eye(D))
+                e1 = ref.distributions.RoughWell(D, rw_eps, easy=True)
+            extra = {"cov0": 1.5 * np.eye(D)}
+            meta = dict(D=D, n=n, anneal_steps=steps, leapfrogs=lf, step_size=step, rw_eps=rw_eps, easy=True)
+        x0 = rng.standard_normal((n, D)).astype(np.float32)
+        v0 = rng.standard_normal((n, D)).astype(np.float32)
+        v_refresh = rng.standard_normal((steps, n, D)).astype(np.float32)
+        u = rng.random((steps, n)).astype(np.float32)
+        arrays = {"meta": _meta(name=name, **meta), "in_x": x0, "in_v0": v0, "in_v_refresh": v_refresh, "in_u": u}
+        arrays.update(extra)
+        for k, v in R.run_ais(e0, e1, steps, x0, v0, v_refresh, u, step, lf, "float64").items():
+            arrays["out_" + k] = v
+        path = os.path.join(HERE, "ref", name + ".npz")
+        np.savez_compressed(path, **arrays)
+        out.append(path)
+    return out
 
 
 weight_checksum = U.vae_weight_checksum
@@ -205,7 +219,7 @@ if __name__ == "__main__":
     out.append(save_notebook_loss("notebook_loss_c1_n200", "c1_scg2", 200, 43))
     out.append(save_notebook_loss("notebook_loss_c3_n64", "c3_mog2", 64, 44))
     out.append(save_losses_and_diagnostics())
-    out.append(save_ais())
+    out += save_ais()
     out.append(save_vae("c5_vae_mini_n96", "c5_vae_mini", 96, 45, True))
     out.append(save_vae("c5_vae_full_n32", "c5_vae_full", 32, 46, False))  # mnist_vae.py's own text, its layer sizes
     for p in out:

@@ -246,6 +246,64 @@ def test_ais_matches_the_reference():
     assert abs(float(est) - float(z["out_estimate"])) <= 2e-3  # a flipped Metropolis decision moves one of 64 weights
 
 
+def test_ais_between_unlike_energies_matches_the_reference():
+    """utils/ais.py:44-45 for a pair whose mixture is not a closed form (Gaussian -> rough well): the annealed energy
+    (1 - beta) U0 + beta U1 is evaluated per chain inside the fused kernel (l2hmc_set_energy_mixed)."""
+    from l2hmc_b200.ais import ais_estimate
+    from l2hmc_b200.distributions import Gaussian, RoughWell
+    z = np.load(os.path.join(GOLD, "ref", "ais_roughwell4.npz"))
+    meta = _meta(z)
+    D = meta["D"]
+    g0, g1 = Gaussian(np.zeros(D), z["cov0"]), RoughWell(D, meta["rw_eps"], easy=meta["easy"])
+    r = {"v0": z["in_v0"], "v": z["in_v_refresh"], "u": z["in_u"]}
+    est, alpha = ais_estimate(g0.get_energy_function(), g1.get_energy_function(), meta["anneal_steps"],
+                              torch.as_tensor(z["in_x"]).cuda(), step_size=meta["step_size"], leapfrogs=meta["leapfrogs"],
+                              x_dim=D, rng=r)
+    assert abs(float(alpha) - float(z["out_mean_accept"])) <= 1e-4
+    assert abs(float(est) - float(z["out_estimate"])) <= 2e-3
+
+
+@pytest.mark.parametrize("D,final", [(2, "gmm"), (6, "gmm"), (3, "funnel"), (12, "roughwell")])
+def test_mixed_energy_components_match_the_oracle(D, final):
+    """distributions.MixedEnergy on the device (energy, grad U, an HMC-mode transition; small kernel for x_dim <= 4, tile
+    kernel above) against the oracle's MixedEnergy (utils/ais.py:44-45)."""
+    from l2hmc_b200 import Dynamics
+    from l2hmc_b200.distributions import Gaussian, GMM, GaussianFunnel, RoughWell, MixedEnergy
+    rng = np.random.default_rng(D)
+    cov0 = np.eye(D) * 1.3
+    g0 = Gaussian(np.zeros(D), cov0)
+    e0 = U.O.GaussianEnergy(np.zeros(D), np.linalg.inv(cov0).astype(np.float32))
+    if final == "gmm":
+        mus = [rng.standard_normal(D), rng.standard_normal(D)]
+        sig = [0.5 * np.eye(D), 0.8 * np.eye(D)]
+        g1 = GMM(mus, sig, [0.5, 0.5])
+        e1 = U.O.GMMEnergy(mus, g1.i_sigmas, g1.constants)
+    elif final == "funnel":
+        g1 = GaussianFunnel(dim=D)
+        e1 = U.O.FunnelEnergy(g1.sigma, g1.clip)
+    else:
+        g1 = RoughWell(D, 0.4, easy=True)
+        e1 = U.O.RoughWellEnergy(0.4, True)
+    beta = 0.35
+    mixed = MixedEnergy(g0.get_energy_function(), g1.get_energy_function(), beta)
+    om = U.O.MixedEnergy(e0, e1, beta).to(torch.float64)
+    n = 200
+    x = rng.standard_normal((n, D)).astype(np.float32)
+    v = rng.standard_normal((n, D)).astype(np.float32)
+    dyn = Dynamics(D, mixed, T=6, eps=0.15, hmc=True)
+    xt, vt = torch.as_tensor(x).cuda(), torch.as_tensor(v).cuda()
+    assert U.max_rel(dyn.energy(xt).cpu().numpy(), om.energy(U.t64(x)).numpy()) <= 1e-5
+    assert U.max_rel(dyn.grad_energy(xt).cpu().numpy(), om.grad(U.t64(x)).numpy()) <= 1e-5
+    Lx, Lv, px = dyn.forward(xt, init_v=vt)
+    od = U.O.OracleDynamics(D, 6, 0.15, om, np.zeros((6, D), np.float32), hmc=True, dtype=torch.float64)
+    ox, ov, op = od.forward(U.t64(x), U.t64(v))
+    assert U.max_rel(Lx.cpu().numpy(), ox.numpy()) <= 2e-5 and U.max_rel(Lv.cpu().numpy(), ov.numpy()) <= 2e-5
+    assert float(np.max(np.abs(px.cpu().numpy() - op.numpy()))) <= 1e-4
+    dyn.set_mix_beta(0.8)   # beta moves without re-sending the parameters
+    om2 = U.O.MixedEnergy(e0, e1, 0.8).to(torch.float64)
+    assert U.max_rel(dyn.energy(xt).cpu().numpy(), om2.energy(U.t64(x)).numpy()) <= 1e-5
+
+
 def test_diagnostics_match_the_reference():
     """utils/func_utils.py:45-54,114-120 (numpy in the reference) on the device."""
     from l2hmc_b200 import diagnostics as G

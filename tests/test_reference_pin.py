@@ -45,7 +45,7 @@ def test_fixture_inventory():
     for cfg in ("c1_scg2", "c2_scg50", "c3_mog2", "c4_rw32", "funnel3", "hmc_scg2"):
         assert any(cfg in n for n in names), cfg
     for extra in ("chain_operator_c1_n64", "chain_operator_c2_n32", "notebook_loss_c1_n200", "notebook_loss_c3_n64",
-                  "losses_diagnostics", "ais_gauss3", "c5_vae_mini_n96", "c5_vae_full_n32"):
+                  "losses_diagnostics", "ais_gauss3", "ais_roughwell4", "c5_vae_mini_n96", "c5_vae_full_n32"):
         assert os.path.exists(os.path.join(GOLD, "ref", extra + ".npz")), extra
     for f in PROPOSE_FILES:
         assert "unmodified /root/reference" in _meta(np.load(f))["source"]
@@ -205,6 +205,19 @@ def test_oracle_reproduces_reference_ais():
     D = meta["D"]
     e0 = O.GaussianEnergy(np.zeros(D), np.eye(D))
     e1 = O.GaussianEnergy(z["mu1"].astype(np.float32), np.linalg.inv(z["cov1"]).astype(np.float32))
+    est, alpha, _, _ = O.ais_estimate(e0, e1, meta["anneal_steps"], z["in_x"], step_size=meta["step_size"],
+                                      leapfrogs=meta["leapfrogs"], v0=z["in_v0"], v_refresh=z["in_v_refresh"], u=z["in_u"])
+    assert abs(float(est) - float(z["out_estimate"])) <= 1e-6 * max(1.0, abs(float(z["out_estimate"])))
+    assert abs(float(alpha) - float(z["out_mean_accept"])) <= 1e-6
+
+
+def test_oracle_reproduces_reference_ais_between_unlike_energies():
+    """utils/ais.py:44-45 with a pair whose mixture is not one of the closed forms: Gaussian -> rough well."""
+    z = np.load(os.path.join(GOLD, "ref", "ais_roughwell4.npz"))
+    meta = _meta(z)
+    D = meta["D"]
+    e0 = O.GaussianEnergy(np.zeros(D), np.linalg.inv(z["cov0"]).astype(np.float32))
+    e1 = O.RoughWellEnergy(meta["rw_eps"], meta["easy"])
     est, alpha, _, _ = O.ais_estimate(e0, e1, meta["anneal_steps"], z["in_x"], step_size=meta["step_size"],
                                       leapfrogs=meta["leapfrogs"], v0=z["in_v0"], v_refresh=z["in_v_refresh"], u=z["in_u"])
     assert abs(float(est) - float(z["out_estimate"])) <= 1e-6 * max(1.0, abs(float(z["out_estimate"])))
