@@ -60,6 +60,9 @@ struct LayeredCtx {
   LayMlp dec, enc;
   DevBuf x, v, x0, ab, hd, hA, hB, vec, eaux, auxp, tbias;
   std::vector<DevBuf> dact, eact;
+  std::vector<DevBuf> aimg, gimg;                  // operand images of the decoder's activations / gradients (SplitImage)
+  bool presplit = true;                            // L2HMC_LAYERED_PRESPLIT=0: every GEMM converts its own A operand
+  int presplit_mode = 2;                           // 2: tc_gemm_pre_kernel (default); 1: the 256-row kernel with a TMA-fed A
   long long ws_n = 0;
   cudaEvent_t ws_event = nullptr;  // recorded when a call's last workspace user is enqueued
   bool ws_recorded = false;
@@ -656,6 +659,9 @@ extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
     const char *gm = getenv("L2HMC_LAYERED_GEMM");  // "fma" forces the fp32 FMA GEMMs
     if (gm && gm[0] == 't') ctx->lay.gemm_f16 = false;                 // "tf32": the tf32 x3 split only
     else if (gm && gm[0] == 'f' && gm[1] == 'm') ctx->lay.gemm_tc = false;  // "fma"
+    const char *ps = getenv("L2HMC_LAYERED_PRESPLIT");
+    if (ps && ps[0] == '0') ctx->lay.presplit = false;
+    if (ps && ps[0] == '1') ctx->lay.presplit_mode = 1;
     cudaDeviceGetAttribute(&ctx->lay.sms, cudaDevAttrMultiProcessorCount, cfg->device);
   }
   int rc = pick_kernel(ctx);

@@ -15,6 +15,8 @@
 // State lives in HBM between launches ([n, Dp] x, v; [n, K1p] net input; [n, Hp] activations), every buffer
 // row-padded to a multiple of 8 floats with the pad columns held at zero so each GEMM runs without K tails.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace l2hmc {
@@ -36,7 +38,45 @@ struct GemmArgs {
   float scale;
   int epi;
   int vec;                      // 1: C rows 16-byte aligned and N % 4 == 0 -> float4 stores
+  // tensor-core engine only (tc_gemm.cuh), all optional:
+  const uint8_t *a_img = nullptr;  // A as a pre-split fp16 hi / lo operand image (SplitImage layout) instead of fp32 rows
+  uint8_t *c_img = nullptr;        // also write epi(...) as the operand image the NEXT GEMM reads (its K = this N)
+  int img_nmb = 0;                 // 128-row blocks of either image (both have M rows): 2 * ceil(M / 256)
+  int no_c = 0;                    // 1: do not store the fp32 C (only c_img is wanted); DSOFTPLUS still reads C
 };
+
+// Pre-split operand image of an activation matrix X [M][K] for the fp16 x3 tensor-core GEMM: what tc_gemm_kernel's A path
+// would put into shared memory, kept in HBM so that the consumer fetches it with bulk (TMA) copies and nobody converts an
+// element more than once.  Block (mb, kb) = rows [128 mb, 128 mb + 128) x columns [32 kb, 32 kb + 32), 16 KB:
+// [hi | lo] x [kc = 0..3][row group = 0..15][row in group = 0..7][8 halfs], the UMMA K-major no-swizzle core-matrix order;
+// blocks are stored kb-major ((kb * nmb + mb) * 16 KB) so the two row halves of a 256-row tile are one 32 KB copy.
+// Rows >= M and columns >= K of the image stay zero (the buffer is zero-initialised and only valid elements are written).
+struct SplitImage {
+  static constexpr int BLOCK_BYTES = 16384;
+  __host__ __device__ static int nmb(long long M) { return (int)(2 * ((M + 255) / 256)); }
+  __host__ __device__ static int nkb(int K) { return (K + 31) / 32; }
+  __host__ __device__ static size_t bytes(long long M, int K) { return (size_t)nmb(M) * nkb(K) * BLOCK_BYTES; }
+  // byte offset of the 16-byte piece holding columns [8 * (k / 8), +8) of row m in the hi part (lo: + 8192)
+  __host__ __device__ static size_t piece(long long m, int k, int nmb_) {
+    return ((size_t)(k >> 5) * nmb_ + (size_t)(m >> 7)) * BLOCK_BYTES + (size_t)((k & 31) >> 3) * 2048 + (size_t)((m & 127) >> 3) * 128 +
+           (size_t)(m & 7) * 16;
+  }
+};
+
+// fp32 -> (hi, lo) halfs exactly as tc_gemm_kernel's A path does: hi keeps the top 10 mantissa bits, lo = a - hi.
+__device__ __forceinline__ void split8_to_half(const float (&a)[8], uint4 &hi, uint4 &lo, float &amax) {
+  uint32_t hp[4], lp[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float h0 = __uint_as_float(__float_as_uint(a[2 * j]) & 0xFFFFE000u), h1 = __uint_as_float(__float_as_uint(a[2 * j + 1]) & 0xFFFFE000u);
+    amax = fmaxf(amax, fmaxf(fabsf(a[2 * j]), fabsf(a[2 * j + 1])));
+    const __half2 hh = __floats2half2_rn(h0, h1), ll = __floats2half2_rn(a[2 * j] - h0, a[2 * j + 1] - h1);
+    hp[j] = *reinterpret_cast<const uint32_t *>(&hh);
+    lp[j] = *reinterpret_cast<const uint32_t *>(&ll);
+  }
+  hi = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+  lo = make_uint4(lp[0], lp[1], lp[2], lp[3]);
+}
 
 __device__ __forceinline__ float softplus_f(float t) {  // tf.nn.softplus, overflow-free
   return fmaxf(t, 0.f) + log1pf(expf(-fabsf(t)));
@@ -254,19 +294,45 @@ __global__ void k_lay_grad_generic(LayDims dm, LayState st, EnergyDev en, Shape 
 //   U = like * sum_j [max(l,0) - l a + log(1 + exp(-|l|))] + 0.5 |z|^2, all / temperature;  l <- dU/dl = like * (sigmoid(l) - a).
 // like = 1 for the sampler; the annealed energy of utils/ais.py:44-45 between the prior and this posterior is like = beta.
 __global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const float *aux, float inv_temp, float like,
-                          long long n_chains) {
+                          long long n_chains, uint8_t *img, int img_nmb) {
   const long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= n_chains) return;
   float s = 0.f;
   float *l = logits + n * ldl;
   const float *a = aux + n * dm.aux;
-  for (int j = lane; j < dm.aux; j += 32) {
-    const float lj = l[j], aj = a[j];
-    const float e = expf(-fabsf(lj));
-    s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
-    const float r = __fdividef(1.f, 1.f + e);  // 1 + e in [1, 2]
-    l[j] = like * (((lj >= 0.f) ? r : e * r) - aj);
+  if (img != nullptr) {
+    // dU/dl goes out as the operand image of the first reverse GEMM (SplitImage; |dU/dl| <= like <= 1, no range guard):
+    // a lane owns 8 consecutive columns = one 16-byte piece of hi and of lo
+    float unused = 0.f;
+    for (int j0 = 8 * lane; j0 < dm.aux; j0 += 256) {
+      float d8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float dj = 0.f;
+        if (j0 + j < dm.aux) {
+          const float lj = l[j0 + j], aj = a[j0 + j];
+          const float e = expf(-fabsf(lj));
+          s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
+          const float r = __fdividef(1.f, 1.f + e);
+          dj = like * (((lj >= 0.f) ? r : e * r) - aj);
+        }
+        d8[j] = dj;
+      }
+      uint4 hi, lo;
+      split8_to_half(d8, hi, lo, unused);
+      uint8_t *ip = img + SplitImage::piece(n, j0, img_nmb);
+      *reinterpret_cast<uint4 *>(ip) = hi;
+      *reinterpret_cast<uint4 *>(ip + 8192) = lo;
+    }
+  } else {
+    for (int j = lane; j < dm.aux; j += 32) {
+      const float lj = l[j], aj = a[j];
+      const float e = expf(-fabsf(lj));
+      s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
+      const float r = __fdividef(1.f, 1.f + e);  // 1 + e in [1, 2]
+      l[j] = like * (((lj >= 0.f) ? r : e * r) - aj);
+    }
   }
   float q = 0.f;
   for (int d = lane; d < dm.D; d += 32) {

@@ -236,13 +236,18 @@ int lay_gemm(l2hmc_ctx *ctx, cudaStream_t s, GemmArgs g) {
     if (it != ctx->lay.tcw.end() && aligned) {
       // fp16 operand split unless this context has met an activation outside the fp16 range (sticky status bit, polled
       // from pinned host memory without synchronising) or the weight itself is out of range
-      const bool f16 = ctx->lay.gemm_f16 && it->second.has16 && !(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE);
+      const bool imgs = g.a_img != nullptr || g.c_img != nullptr;  // decided by the caller under the same conditions
+      const bool f16 = imgs || (ctx->lay.gemm_f16 && it->second.has16 && !(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE));
       ctx->lay.used_f16 = f16;
-      CUDA_TRY(ctx, l2hmc::tcg::launch_tc_gemm(g, f16 ? it->second.d16 : it->second.d, ctx->lay.sms, s));
+      if (g.a_img != nullptr && ctx->lay.presplit_mode == 2)  // 128-row tiles, two accumulators: the epilogue overlaps the MMAs
+        CUDA_TRY(ctx, l2hmc::tcg::launch_tc_gemm_pre(g, it->second.d16, ctx->lay.sms, s));
+      else
+        CUDA_TRY(ctx, l2hmc::tcg::launch_tc_gemm(g, f16 ? it->second.d16 : it->second.d, ctx->lay.sms, s));
       ctx->launches++;
       return L2HMC_OK;
     }
   }
+  if (g.a_img || g.c_img || g.no_c) return fail(ctx, L2HMC_EINVAL, "layered engine: operand images need the tensor-core GEMM");
   const int bn8 = round_up(g.N, 128), bn4 = round_up(g.N, 64);
   const unsigned my = (unsigned)((g.M + 127) / 128);
   // Measured on B200 (profiles/r01_vae_launches.txt): both tile widths run at 46-50% of the FMA peak per padded
@@ -319,17 +324,42 @@ int lay_energy_grad(l2hmc_ctx *ctx, cudaStream_t s, long long n, const float *au
   const LayMlp &m = L.dec;
   const int nl = m.n_layers;
   int rc;
+  // Operand images (layered::SplitImage): with the fp16 x3 tensor-core GEMMs every activation / gradient that is the A
+  // operand of the next GEMM is written ONCE, already split, by the kernel that produces it (GEMM epilogue or k_lay_bce) and
+  // fetched by TMA; otherwise each of the next GEMM's N / 256 column tiles would convert it again.
+  bool pre = L.gemm_tc && L.gemm_f16 && L.presplit && want_grad && !(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE);
+  for (int i = 0; pre && i < nl; ++i) {
+    auto fw = L.tcw.find(m.W[i]), bw = L.tcw.find(m.Wt[i]);
+    pre = fw != L.tcw.end() && bw != L.tcw.end() && fw->second.has16 && bw->second.has16;
+  }
+  const int nmb = l2hmc::layered::SplitImage::nmb(n);
+  if (pre) {
+    L.aimg.resize(nl + 1);
+    L.gimg.resize(nl + 1);
+    for (int i = 1; i <= nl; ++i) {
+      const size_t fl = l2hmc::layered::SplitImage::bytes(n, m.wp[i]) / sizeof(float);
+      if (i < nl && (rc = ensure_zero(ctx, L.aimg[i], fl))) return rc;
+      if ((rc = ensure_zero(ctx, L.gimg[i], fl))) return rc;
+    }
+  }
+  auto img = [](DevBuf &b) { return reinterpret_cast<uint8_t *>(b.p); };
   const float *A = st.x;
   int lda = dm.Dp;
   for (int i = 0; i < nl; ++i) {
     const bool last = (i + 1 == nl);
     GemmArgs g = gemm_args(A, lda, m.W[i], m.wp[i + 1], L.dact[i + 1].p, m.wp[i + 1], n, m.wp[i + 1], m.wp[i], m.b[i],
                            last ? l2hmc::layered::EPI_BIAS : l2hmc::layered::EPI_SOFTPLUS);
+    if (pre) {
+      g.img_nmb = nmb;
+      if (i >= 1) g.a_img = img(L.aimg[i]);
+      if (!last) g.c_img = img(L.aimg[i + 1]);
+    }
     if ((rc = lay_gemm(ctx, s, g))) return rc;
     A = L.dact[i + 1].p;
     lda = m.wp[i + 1];
   }
-  l2hmc::layered::k_lay_bce<<<WGRID(n), 0, s>>>(dm, st, L.dact[nl].p, m.wp[nl], aux, 1.0f / ctx->en.temperature, L.like_scale, n);
+  l2hmc::layered::k_lay_bce<<<WGRID(n), 0, s>>>(dm, st, L.dact[nl].p, m.wp[nl], aux, 1.0f / ctx->en.temperature, L.like_scale, n,
+                                                pre ? img(L.gimg[nl]) : nullptr, nmb);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
   if (!want_grad) return L2HMC_OK;
@@ -337,10 +367,20 @@ int lay_energy_grad(l2hmc_ctx *ctx, cudaStream_t s, long long n, const float *au
   for (int i = nl - 1; i >= 1; --i) {
     GemmArgs g = gemm_args(L.dact[i + 1].p, m.wp[i + 1], m.Wt[i], m.wp[i], L.dact[i].p, m.wp[i], n, m.wp[i], m.wp[i + 1],
                            nullptr, l2hmc::layered::EPI_DSOFTPLUS);
+    if (pre) {  // gradient images only: the fp32 buffer keeps the activation (read by the softplus' factor)
+      g.img_nmb = nmb;
+      g.a_img = img(L.gimg[i + 1]);
+      g.c_img = img(L.gimg[i]);
+      g.no_c = 1;
+    }
     if ((rc = lay_gemm(ctx, s, g))) return rc;
   }
   GemmArgs g = gemm_args(L.dact[1].p, m.wp[1], m.Wt[0], m.wp[0], st.ab + dm.D, dm.K1p, n, dm.D, m.wp[1], nullptr,
                          l2hmc::layered::EPI_ADD_SCALE);
+  if (pre) {
+    g.img_nmb = nmb;
+    g.a_img = img(L.gimg[1]);
+  }
   g.R = st.x;  // + z: gradient of the standard normal prior (mnist_vae.py:125)
   g.ldr = dm.Dp;
   g.scale = 1.0f / ctx->en.temperature;

@@ -108,8 +108,82 @@ __device__ __forceinline__ float epi_apply(float v, float aux, float scale) {
   return v;
 }
 
-template <int EPI, bool F16>
+// One 16-column chunk of an output row: acc = A B for columns [nbase, nbase + 16) of row m (m < M, nbase < N) -> fused layer
+// tail -> fp32 C and / or the operand image of the next GEMM.  Shared by the GEMM kernels below.
+template <int EPI>
+__device__ __forceinline__ void epi_chunk(const layered::GemmArgs &g, float (&acc)[16], long long m, int nbase, const float *bias,
+                                          float &omax) {
+  float *Cp = g.C + m * (long long)g.ldc + nbase;
+  const bool full = nbase + 15 < g.N;
+  if (full && g.vec) {
+    // fast path: whole 16-column chunk inside N, 16-byte aligned rows
+    float aux[16];
+    if (EPI == layered::EPI_DSOFTPLUS) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = *reinterpret_cast<const float4 *>(Cp + 4 * q);
+        aux[4 * q] = t.x; aux[4 * q + 1] = t.y; aux[4 * q + 2] = t.z; aux[4 * q + 3] = t.w;
+      }
+    } else if (EPI == layered::EPI_ADD_SCALE || (EPI == layered::EPI_RELU && g.R != nullptr)) {
+      const float *Rp = g.R + m * (long long)g.ldr + nbase;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) aux[j] = Rp[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) aux[j] = 0.f;
+    }
+    if (EPI != layered::EPI_DSOFTPLUS && EPI != layered::EPI_ADD_SCALE && bias != nullptr) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + nbase + 4 * q));
+        acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = epi_apply<EPI>(acc[j], aux[j], g.scale);
+    if (!g.no_c) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4 *>(Cp + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int nn = nbase + j;
+      float o = 0.f;
+      if (nn < g.N) {
+        float v = acc[j], a = 0.f;
+        if (EPI == layered::EPI_DSOFTPLUS) a = Cp[j];
+        else if (EPI == layered::EPI_ADD_SCALE || (EPI == layered::EPI_RELU && g.R != nullptr)) a = g.R[m * (long long)g.ldr + nn];
+        if (EPI != layered::EPI_DSOFTPLUS && EPI != layered::EPI_ADD_SCALE && bias != nullptr) v += bias[nn];
+        o = epi_apply<EPI>(v, a, g.scale);
+        if (!g.no_c) Cp[j] = o;
+      }
+      acc[j] = o;  // columns >= N of the operand image are zero
+    }
+  }
+  if (g.c_img != nullptr) {
+    // the same values as the next GEMM's operand image: columns [nbase, nbase + 16) = two 16-byte pieces of hi and of lo;
+    // the 32 lanes of the warp (consecutive rows) write 512 contiguous bytes per piece
+    uint8_t *ip = g.c_img + layered::SplitImage::piece(m, nbase, g.img_nmb);
+#pragma unroll
+    for (int p8 = 0; p8 < 2; ++p8) {
+      float a8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] = acc[8 * p8 + j];
+      uint4 hi, lo;
+      layered::split8_to_half(a8, hi, lo, omax);
+      *reinterpret_cast<uint4 *>(ip + p8 * 2048) = hi;
+      *reinterpret_cast<uint4 *>(ip + 8192 + p8 * 2048) = lo;
+    }
+  }
+}
+
+// APRE (needs F16): A arrives as a pre-split operand image (layered::SplitImage, g.a_img) and is fetched by the TMA warp with
+// one 32 KB bulk copy per k-block; nobody converts, and warps 0-7 join the epilogue (16 epilogue warps, alternate chunks).
+template <int EPI, bool F16, bool APRE = false>
 __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::GemmArgs g, const TcGemmB tb) {
+  static_assert(!APRE || F16, "the operand image holds fp16 pairs");
   constexpr int KB = F16 ? 2 * GBK : GBK;  // K elements per k-block (the stage bytes are the same)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte aligned base (descriptors address in 16-byte units; keep stages well aligned)
@@ -138,7 +212,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
       tc::mbar_init(&empty[s], 1);
     }
     tc::mbar_init(acc_full, 1);
-    tc::mbar_init(acc_empty, 8);
+    tc::mbar_init(acc_empty, APRE ? 16 : 8);
     tc::fence_mbar_init();
   }
   if (warp == W_MMA) tc::tmem_alloc(tmem_slot, 512);  // two 256-column accumulators (row halves of the tile)
@@ -147,7 +221,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
   tc::tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 8) {
+  if (!APRE && warp < 8) {
     // ---------------- A path: LDG (3 k-blocks in flight) -> tf32 hi / lo -> UMMA layout ----------------
     // element i of this thread: idx = i*256 + tid -> r8 = idx & 7, kc = (idx >> 3) & 3, mg = idx >> 5 (0..31)
     int mrow[4], kofs[4];
@@ -249,8 +323,11 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
     if (F16 && !(amax < 60000.f) && tb.status) atomicOr_system(tb.status, l2hmc::STATUS_F16_RANGE);
   } else if (warp < 16) {
     // ---------------- epilogue warps: thread = output row of accumulator (e / 4), TMEM lane group (e % 4) ----------
-    const int e = warp - 8;
+    // (APRE: warps 0-7 take the even 16-column chunks, warps 8-15 the odd ones)
+    const int e = warp & 7;
     const int lg = e & 3, half = e >> 2;
+    const int cpart = APRE ? (warp >> 3) : 0, cstep = APRE ? 32 : 16;
+    float omax = 0.f;  // largest |value| written to the operand image (fp16 range guard of the consumer)
     for (long long ti = 0; ti < my_tiles; ++ti) {
       const long long tile = blockIdx.x + ti * gridDim.x;
       const long long mb = tile / nblk;
@@ -262,61 +339,19 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
       const bool mok = m < g.M;
       const float *bias = (EPI == layered::EPI_RELU && g.dir != nullptr && mok && g.dir[m] == 0) ? g.bias_b : g.bias;
       const uint32_t trow = tmem_base + (uint32_t)(half * 256) + ((uint32_t)(32 * lg) << 16);
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = cpart * 16; c < BN; c += cstep) {
         float acc[16];
         tc::tmem_ld16(trow + (uint32_t)c, acc);
         tc::tmem_wait_ld();
         const int nbase = n0 + c;
         if (!mok || nbase >= g.N) continue;
-        float *Cp = g.C + m * (long long)g.ldc + nbase;
-        const bool full = nbase + 15 < g.N;
-        if (full && g.vec) {
-          // fast path: whole 16-column chunk inside N, 16-byte aligned rows
-          float aux[16];
-          if (EPI == layered::EPI_DSOFTPLUS) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = *reinterpret_cast<const float4 *>(Cp + 4 * q);
-              aux[4 * q] = t.x; aux[4 * q + 1] = t.y; aux[4 * q + 2] = t.z; aux[4 * q + 3] = t.w;
-            }
-          } else if (EPI == layered::EPI_ADD_SCALE || (EPI == layered::EPI_RELU && g.R != nullptr)) {
-            const float *Rp = g.R + m * (long long)g.ldr + nbase;
-#pragma unroll
-            for (int j = 0; j < 16; ++j) aux[j] = Rp[j];
-          } else {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) aux[j] = 0.f;
-          }
-          if (EPI != layered::EPI_DSOFTPLUS && EPI != layered::EPI_ADD_SCALE && bias != nullptr) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float4 t = __ldg(reinterpret_cast<const float4 *>(bias + nbase + 4 * q));
-              acc[4 * q] += t.x; acc[4 * q + 1] += t.y; acc[4 * q + 2] += t.z; acc[4 * q + 3] += t.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 16; ++j) acc[j] = epi_apply<EPI>(acc[j], aux[j], g.scale);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            *reinterpret_cast<float4 *>(Cp + 4 * q) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int nn = nbase + j;
-            if (nn < g.N) {
-              float v = acc[j], a = 0.f;
-              if (EPI == layered::EPI_DSOFTPLUS) a = Cp[j];
-              else if (EPI == layered::EPI_ADD_SCALE || (EPI == layered::EPI_RELU && g.R != nullptr)) a = g.R[m * (long long)g.ldr + nn];
-              if (EPI != layered::EPI_DSOFTPLUS && EPI != layered::EPI_ADD_SCALE && bias != nullptr) v += bias[nn];
-              Cp[j] = epi_apply<EPI>(v, a, g.scale);
-            }
-          }
-        }
+        epi_chunk<EPI>(g, acc, m, nbase, bias, omax);
       }
       tc::tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(acc_empty);
     }
+    if (g.c_img != nullptr && !(omax < 60000.f) && tb.status) atomicOr_system(tb.status, l2hmc::STATUS_F16_RANGE);
   } else if (warp == W_TMA) {
     // ---------------- B path (TMA bulk copies of the packed weight image) ----------------
     if (lane == 0) {
@@ -325,12 +360,16 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
       for (long long ti = 0; ti < my_tiles; ++ti) {
         const long long tile = blockIdx.x + ti * gridDim.x;
         const int nb = (int)(tile % nblk);
+        const long long mb = tile / nblk;
         const float *src = tb.pk + ((size_t)nb * nkb) * b_block_floats(BN);
         for (int kb = 0; kb < nkb; ++kb, ++flat) {
           const int s = (int)(flat % GNS);
           const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
           wait_spin(&empty[s], ph ^ 1u);
-          tc::mbar_arrive_expect_tx(&full_b[s], bytes);
+          tc::mbar_arrive_expect_tx(&full_b[s], bytes + (APRE ? A_ALL : 0u));
+          if (APRE)  // blocks (2 mb, kb) and (2 mb + 1, kb) of the image are adjacent: [A0 hi | A0 lo | A1 hi | A1 lo]
+            tc::bulk_g2s(smem + s * SB, g.a_img + ((size_t)kb * g.img_nmb + (size_t)(2 * mb)) * layered::SplitImage::BLOCK_BYTES, A_ALL,
+                         &full_b[s]);
           tc::bulk_g2s(smem + s * SB + A_ALL, src + (size_t)kb * b_block_floats(BN), bytes, &full_b[s]);
         }
       }
@@ -347,7 +386,7 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
         for (int kb = 0; kb < nkb; ++kb, ++flat) {
           const int s = (int)(flat % GNS);
           const uint32_t ph = (uint32_t)(flat / GNS) & 1u;
-          wait_spin(&full_a[s], ph);
+          if (!APRE) wait_spin(&full_a[s], ph);
           wait_spin(&full_b[s], ph);
           tc::tcgen05_fence_after();
           const uint32_t sa = tc::smem_u32(smem + s * SB), sb = sa + A_ALL;
@@ -386,8 +425,177 @@ __global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_kernel(const layered::Ge
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// tc_gemm_pre_kernel: the GEMM for a pre-split A operand (layered::SplitImage), fp16 x3, with the epilogue off the critical
+// path.  Persistent CTAs walk 128 x BN tiles; TMEM holds TWO accumulators of BN <= 256 columns, so the 16 epilogue warps
+// drain tile i (fused layer tail, fp32 C and / or the next operand image) while the tensor pipe already accumulates tile
+// i + 1 -- in the 256-row kernel above the pipe idles for the whole epilogue (ncu: 50 % tensor-active on the decoder GEMMs).
+//   warps 0-15  epilogue: TMEM lane group warp % 4, 16-column chunks (warp / 4), (warp / 4) + 4, ...
+//   warp 16     TMA: per k-block of 32 one 16 KB copy of the A image block and one of the packed B block
+//   warp 17     MMA issuer (SS form), 6 MMAs (2 K=16 steps x 3 products) per stage
+// 4-stage ring of 16 KB + 2 * BN * 64 B; mbarriers full / empty per stage, acc_full / acc_empty per accumulator.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int P_NS = 4;
+__host__ __device__ inline size_t pre_stage_bytes(int BN) { return (size_t)2 * GM * GBK * 4 + b_block_floats(BN) * 4; }
+__host__ __device__ inline size_t tc_gemm_pre_smem(int BN) { return P_NS * pre_stage_bytes(BN) + 1024 + 256; }
+
+template <int EPI>
+__global__ void __launch_bounds__(G_THREADS, 1) tc_gemm_pre_kernel(const layered::GemmArgs g, const TcGemmB tb) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int BN = tb.BN;
+  const size_t SB = pre_stage_bytes(BN);
+  const uint32_t A_IMG = GM * GBK * 4;  // 8 KB: hi or lo of one 128 x 32 block; stage: [A hi | A lo | B hi | B lo]
+  const uint32_t A_ALL = 2 * A_IMG;
+  const uint32_t B_HALF = (uint32_t)BN * GBK * 4;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem + P_NS * SB);
+  uint64_t *full = bars, *empty = bars + P_NS, *acc_full = bars + 2 * P_NS, *acc_empty = bars + 2 * P_NS + 2;
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * P_NS + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkb = tb.nkb, nblk = tb.nblk;
+  const long long mblocks = (g.M + GM - 1) / GM;
+  const long long tiles = mblocks * nblk;  // n-block fastest: neighbouring CTAs read the same A blocks through L2
+  const long long my_tiles = (tiles > blockIdx.x) ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < P_NS; ++s) {
+      tc::mbar_init(&full[s], 1);
+      tc::mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      tc::mbar_init(&acc_full[b], 1);
+      tc::mbar_init(&acc_empty[b], 16);
+    }
+    tc::fence_mbar_init();
+  }
+  if (warp == W_MMA) tc::tmem_alloc(tmem_slot, 512);
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  tc::tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 16) {
+    const int lg = warp & 3, cpart = warp >> 2;
+    float omax = 0.f;
+    for (long long ti = 0; ti < my_tiles; ++ti) {
+      const long long tile = blockIdx.x + ti * gridDim.x;
+      const long long mb = tile / nblk;
+      const int nb = (int)(tile - mb * nblk);
+      const int n0 = nb * BN;
+      const int buf = (int)(ti & 1);
+      wait_spin(&acc_full[buf], (uint32_t)(ti >> 1) & 1u);
+      tc::tcgen05_fence_after();
+      const long long m = mb * GM + lg * 32 + lane;
+      const bool mok = m < g.M;
+      const float *bias = (EPI == layered::EPI_RELU && g.dir != nullptr && mok && g.dir[m] == 0) ? g.bias_b : g.bias;
+      const uint32_t trow = tmem_base + (uint32_t)(buf * 256) + ((uint32_t)(32 * lg) << 16);
+      for (int c = cpart * 16; c < BN; c += 64) {
+        float acc[16];
+        tc::tmem_ld16(trow + (uint32_t)c, acc);
+        tc::tmem_wait_ld();
+        const int nbase = n0 + c;
+        if (!mok || nbase >= g.N) continue;
+        epi_chunk<EPI>(g, acc, m, nbase, bias, omax);
+      }
+      tc::tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+    }
+    if (g.c_img != nullptr && !(omax < 60000.f) && tb.status) atomicOr_system(tb.status, l2hmc::STATUS_F16_RANGE);
+  } else if (warp == W_TMA) {
+    if (lane == 0) {
+      const uint32_t bytes_b = 2 * B_HALF;
+      long long flat = 0;
+      for (long long ti = 0; ti < my_tiles; ++ti) {
+        const long long tile = blockIdx.x + ti * gridDim.x;
+        const long long mb = tile / nblk;
+        const int nb = (int)(tile - mb * nblk);
+        const float *src = tb.pk + ((size_t)nb * nkb) * b_block_floats(BN);
+        for (int kb = 0; kb < nkb; ++kb, ++flat) {
+          const int s = (int)(flat % P_NS);
+          const uint32_t ph = (uint32_t)(flat / P_NS) & 1u;
+          wait_spin(&empty[s], ph ^ 1u);
+          tc::mbar_arrive_expect_tx(&full[s], bytes_b + A_ALL);
+          tc::bulk_g2s(smem + s * SB, g.a_img + ((size_t)kb * g.img_nmb + (size_t)mb) * layered::SplitImage::BLOCK_BYTES, A_ALL, &full[s]);
+          tc::bulk_g2s(smem + s * SB + A_ALL, src + (size_t)kb * b_block_floats(BN), bytes_b, &full[s]);
+        }
+      }
+    }
+  } else {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16g(GM, BN);
+      const uint32_t lbo_a = (GM / 8) * 128, lbo_b = (uint32_t)(BN / 8) * 128;
+      long long flat = 0;
+      for (long long ti = 0; ti < my_tiles; ++ti) {
+        const int buf = (int)(ti & 1);
+        wait_spin(&acc_empty[buf], ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+        tc::tcgen05_fence_after();
+        const uint32_t dacc = tmem_base + (uint32_t)(buf * 256);
+        for (int kb = 0; kb < nkb; ++kb, ++flat) {
+          const int s = (int)(flat % P_NS);
+          const uint32_t ph = (uint32_t)(flat / P_NS) & 1u;
+          wait_spin(&full[s], ph);
+          tc::tcgen05_fence_after();
+          const uint32_t sa = tc::smem_u32(smem + s * SB), sb = sa + A_ALL;
+#pragma unroll
+          for (int ks = 0; ks < GBK / 8; ++ks) {
+            const uint64_t a_hi = tc::make_smem_desc(sa + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t a_lo = tc::make_smem_desc(sa + A_IMG + ks * 2 * lbo_a, lbo_a, 128);
+            const uint64_t b_hi = tc::make_smem_desc(sb + ks * 2 * lbo_b, lbo_b, 128);
+            const uint64_t b_lo = tc::make_smem_desc(sb + B_HALF + ks * 2 * lbo_b, lbo_b, 128);
+            mma_f16_ss(dacc, a_lo, b_hi, idesc, (kb | ks) != 0);  // small terms first, as in tc_gemm_kernel
+            mma_f16_ss(dacc, a_hi, b_lo, idesc, true);
+            mma_f16_ss(dacc, a_hi, b_hi, idesc, true);
+          }
+          tc::tcgen05_commit(&empty[s]);
+        }
+        tc::tcgen05_commit(&acc_full[buf]);
+      }
+    }
+  }
+  tc::tcgen05_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) {
+    tc::tcgen05_fence_after();
+    tc::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+inline cudaError_t launch_tc_gemm_pre(const layered::GemmArgs &g, const TcGemmB &tb, int sms, cudaStream_t s) {
+  if (!tb.f16 || !g.a_img) return cudaErrorInvalidValue;
+  const size_t smem = tc_gemm_pre_smem(tb.BN);
+  const long long tiles = (long long)tb.nblk * ((g.M + GM - 1) / GM);
+  const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+  cudaError_t e = cudaSuccess;
+#define L2HMC_TCP_LAUNCH(E)                                                                                              \
+  case E: {                                                                                                              \
+    static size_t configured_dev[64] = {0};                                                                              \
+    int dev_ = 0;                                                                                                        \
+    cudaGetDevice(&dev_);                                                                                                \
+    size_t &configured = configured_dev[dev_ & 63];                                                                      \
+    if (smem > configured) {                                                                                             \
+      e = cudaFuncSetAttribute(tc_gemm_pre_kernel<E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);           \
+      if (e != cudaSuccess) return e;                                                                                    \
+      configured = smem;                                                                                                 \
+    }                                                                                                                    \
+    tc_gemm_pre_kernel<E><<<grid, G_THREADS, smem, s>>>(g, tb);                                                          \
+  } break;
+  switch (g.epi) {
+    L2HMC_TCP_LAUNCH(layered::EPI_BIAS)
+    L2HMC_TCP_LAUNCH(layered::EPI_RELU)
+    L2HMC_TCP_LAUNCH(layered::EPI_SOFTPLUS)
+    L2HMC_TCP_LAUNCH(layered::EPI_DSOFTPLUS)
+    L2HMC_TCP_LAUNCH(layered::EPI_ADD_SCALE)
+    default: return cudaErrorInvalidValue;
+  }
+#undef L2HMC_TCP_LAUNCH
+  return cudaGetLastError();
+}
+
 // Launch helper: picks the epilogue instantiation; grid = min(tiles, SMs).
 inline cudaError_t launch_tc_gemm(const layered::GemmArgs &g, const TcGemmB &tb, int sms, cudaStream_t s) {
+  if ((g.a_img || g.c_img) && !tb.f16) return cudaErrorInvalidValue;  // operand images are fp16 pairs
   const size_t smem = tc_gemm_smem(tb.BN);
   const long long tiles = (long long)tb.nblk * ((g.M + GROWS - 1) / GROWS);
   const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
@@ -403,9 +611,12 @@ inline cudaError_t launch_tc_gemm(const layered::GemmArgs &g, const TcGemmB &tb,
       if (e != cudaSuccess) return e;                                                                                    \
       e = cudaFuncSetAttribute(tc_gemm_kernel<E, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
       if (e != cudaSuccess) return e;                                                                                    \
+      e = cudaFuncSetAttribute(tc_gemm_kernel<E, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+      if (e != cudaSuccess) return e;                                                                                    \
       configured = smem;                                                                                                 \
     }                                                                                                                    \
-    if (tb.f16) tc_gemm_kernel<E, true><<<grid, G_THREADS, smem, s>>>(g, tb);                                            \
+    if (tb.f16 && g.a_img) tc_gemm_kernel<E, true, true><<<grid, G_THREADS, smem, s>>>(g, tb);                           \
+    else if (tb.f16) tc_gemm_kernel<E, true><<<grid, G_THREADS, smem, s>>>(g, tb);                                       \
     else tc_gemm_kernel<E, false><<<grid, G_THREADS, smem, s>>>(g, tb);                                                  \
   } break;
   switch (g.epi) {

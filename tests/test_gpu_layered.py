@@ -91,6 +91,39 @@ def test_default_layered_gemms_are_tensor_core_fp16_split_with_a_range_guard(mon
     assert not ref32.fp16_range_exceeded()
 
 
+@pytest.mark.parametrize("name,n", [("c5_vae_mini", 300), ("c5_vae_ragged", 131), ("c5_vae_full", 520)])
+def test_presplit_operand_images_change_nothing(monkeypatch, name, n):
+    """The decoder's activations / gradients travel between its GEMMs as pre-split fp16 hi / lo operand images written by
+    the producing kernel and fetched by TMA (layered::SplitImage); L2HMC_LAYERED_PRESPLIT=0 makes every GEMM convert its
+    own A operand instead.  Same split, same MMA order: bit-identical results (ragged widths, chains not a multiple of the
+    256-row tile, more than one tile per SM column).  The energy VALUE sums its 784 terms in another order in the kernel
+    that also writes the image, so the accept probability agrees to fp32 rounding only."""
+    P = U.VaeProblem(**U.VAE_CONFIGS[name])
+    d = P.draws(n)
+    monkeypatch.delenv("L2HMC_LAYERED_PRESPLIT", raising=False)
+    a = U.run_kernel_propose(P, d, dyn=P.product())
+    monkeypatch.setenv("L2HMC_LAYERED_PRESPLIT", "0")
+    b = U.run_kernel_propose(P, d, dyn=P.product())
+    for k in ("Lx", "Lv"):
+        assert np.array_equal(a[k], b[k]), k
+    # Hamiltonians of O(500) (784 pixels) subtracted in fp32: per-chain maxima of ~1e-4 between two summation orders
+    assert float(np.abs(a["px"] - b["px"]).max()) <= 10 * P_TOL and float(np.abs(a["px"] - b["px"]).mean()) <= 1e-5
+    assert np.isfinite(a["Lx"]).all()
+
+
+def test_presplit_kernel_variants_agree(monkeypatch):
+    """L2HMC_LAYERED_PRESPLIT=1 keeps the 256-row GEMM kernel with a TMA-fed A; the default (2) is tc_gemm_pre_kernel (128-row
+    tiles, two accumulators, epilogue overlapped with the next tile's MMAs).  Same k order, same epilogue: identical."""
+    P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_full"])
+    d = P.draws(300)
+    monkeypatch.setenv("L2HMC_LAYERED_PRESPLIT", "1")
+    a = U.run_kernel_propose(P, d, dyn=P.product())
+    monkeypatch.setenv("L2HMC_LAYERED_PRESPLIT", "2")
+    b = U.run_kernel_propose(P, d, dyn=P.product())
+    for k in ("Lx", "Lv", "px", "x_next"):
+        assert np.array_equal(a[k], b[k]), k
+
+
 def test_vae_log_jac_mode():
     P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
     rep, _ = U.parity_report(P, 192, log_jac=True)
