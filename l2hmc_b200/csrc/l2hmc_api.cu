@@ -61,6 +61,7 @@ struct LayeredCtx {
   DevBuf x, v, x0, ab, hd, hA, hB, vec, eaux, auxp, tbias;
   std::vector<DevBuf> dact, eact;
   std::vector<DevBuf> aimg, gimg;                  // operand images of the decoder's activations / gradients (SplitImage)
+  DevBuf ximg, abimg, hAimg, hBimg;                // ... of x, of the net input [a | b], of the nets' two hidden activations
   bool presplit = true;                            // L2HMC_LAYERED_PRESPLIT=0: every GEMM converts its own A operand
   int presplit_mode = 2;                           // 2: tc_gemm_pre_kernel (default); 1: the 256-row kernel with a TMA-fed A
   long long ws_n = 0;
@@ -697,9 +698,13 @@ extern "C" void l2hmc_destroy(l2hmc_ctx *ctx) {
   {
     LayeredCtx &L = ctx->lay;
     DevBuf *lb[] = {&L.net_buf[0], &L.net_buf[1], &L.dec.buf, &L.enc.buf, &L.x, &L.v, &L.x0, &L.ab, &L.hd, &L.hA, &L.hB,
-                    &L.vec, &L.eaux, &L.auxp, &L.tbias, &ctx->haux, &ctx->diag};
+                    &L.vec, &L.eaux, &L.auxp, &L.tbias, &ctx->haux, &ctx->diag, &L.ximg, &L.abimg, &L.hAimg, &L.hBimg};
     for (DevBuf *b : lb)
       if (b->p) cudaFree(b->p);
+    for (DevBuf &b : L.aimg)
+      if (b.p) cudaFree(b.p);
+    for (DevBuf &b : L.gimg)
+      if (b.p) cudaFree(b.p);
     for (DevBuf &b : L.dact)
       if (b.p) cudaFree(b.p);
     for (DevBuf &b : L.eact)

@@ -305,13 +305,28 @@ __global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const
     // dU/dl goes out as the operand image of the first reverse GEMM (SplitImage; |dU/dl| <= like <= 1, no range guard):
     // a lane owns 8 consecutive columns = one 16-byte piece of hi and of lo
     float unused = 0.f;
+    // 16-byte loads when the rows allow it (row strides multiples of 4 floats, 16-byte aligned bases)
+    const bool vec = ((ldl | dm.aux) & 3) == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(aux)) & 15) == 0;
     for (int j0 = 8 * lane; j0 < dm.aux; j0 += 256) {
-      float d8[8];
+      float l8[8], a8[8], d8[8];
+      if (vec && j0 + 8 <= dm.aux) {
+        const float4 l0 = *reinterpret_cast<const float4 *>(l + j0), l1 = *reinterpret_cast<const float4 *>(l + j0 + 4);
+        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(a + j0)), a1 = __ldg(reinterpret_cast<const float4 *>(a + j0 + 4));
+        l8[0] = l0.x; l8[1] = l0.y; l8[2] = l0.z; l8[3] = l0.w; l8[4] = l1.x; l8[5] = l1.y; l8[6] = l1.z; l8[7] = l1.w;
+        a8[0] = a0.x; a8[1] = a0.y; a8[2] = a0.z; a8[3] = a0.w; a8[4] = a1.x; a8[5] = a1.y; a8[6] = a1.z; a8[7] = a1.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const bool ok = j0 + j < dm.aux;
+          l8[j] = ok ? l[j0 + j] : 0.f;
+          a8[j] = ok ? a[j0 + j] : 0.f;
+        }
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float dj = 0.f;
         if (j0 + j < dm.aux) {
-          const float lj = l[j0 + j], aj = a[j0 + j];
+          const float lj = l8[j], aj = a8[j];
           const float e = expf(-fabsf(lj));
           s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
           const float r = __fdividef(1.f, 1.f + e);
@@ -342,6 +357,26 @@ __global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const
   s = warp_sum(s);
   q = warp_sum(q);
   if (lane == 0) st.U[n] = (like * s + 0.5f * q) * inv_temp;
+}
+
+// fp32 rows [n][ld] (columns [0, K), K % 8 == 0, pad columns zero) -> operand image (SplitImage) for a GEMM whose A they are.
+// Block = 128 rows x 2 column pieces at a time; a warp writes 512 contiguous bytes per piece.
+__global__ void __launch_bounds__(256) k_lay_split(const float *src, int ld, int K, long long n, uint8_t *img, int img_nmb,
+                                                   unsigned int *status) {
+  const long long m = blockIdx.x * 128ll + (threadIdx.x & 127);
+  if (m >= n) return;
+  float amax = 0.f;
+  const float *row = src + m * ld;
+  for (int p = threadIdx.x >> 7; p < (K >> 3); p += 2) {
+    const float4 v0 = *reinterpret_cast<const float4 *>(row + 8 * p), v1 = *reinterpret_cast<const float4 *>(row + 8 * p + 4);
+    const float a8[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    uint4 hi, lo;
+    split8_to_half(a8, hi, lo, amax);
+    uint8_t *ip = img + SplitImage::piece(m, 8 * p, img_nmb);
+    *reinterpret_cast<uint4 *>(ip) = hi;
+    *reinterpret_cast<uint4 *>(ip + 8192) = lo;
+  }
+  if (!(amax < 60000.f) && status) atomicOr_system(status, l2hmc::STATUS_F16_RANGE);
 }
 
 __global__ void k_lay_add_h0(LayState st, long long n_chains) {

@@ -310,6 +310,28 @@ int lay_encode_aux(l2hmc_ctx *ctx, cudaStream_t s, long long n, const float *aux
   return L2HMC_OK;
 }
 
+// The fp16 x3 tensor-core GEMMs with pre-split operand images are usable for this context right now
+bool lay_presplit_ok(l2hmc_ctx *ctx) {
+  const LayeredCtx &L = ctx->lay;
+  return L.gemm_tc && L.gemm_f16 && L.presplit && !(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE);
+}
+bool lay_has16(l2hmc_ctx *ctx, const float *dev_B) {
+  auto it = ctx->lay.tcw.find(dev_B);
+  return it != ctx->lay.tcw.end() && it->second.has16;
+}
+uint8_t *lay_img(DevBuf &b) { return reinterpret_cast<uint8_t *>(b.p); }
+
+// fp32 rows -> operand image (for A operands no GEMM epilogue produces: the state rows x and [a | b])
+int lay_split(l2hmc_ctx *ctx, cudaStream_t s, const float *src, int ld, int K, long long n, DevBuf &img) {
+  int rc = ensure_zero(ctx, img, l2hmc::layered::SplitImage::bytes(n, K) / sizeof(float));
+  if (rc) return rc;
+  l2hmc::layered::k_lay_split<<<(unsigned)((n + 127) / 128), 256, 0, s>>>(src, ld, K, n, lay_img(img), l2hmc::layered::SplitImage::nmb(n),
+                                                                          ctx->status_d);
+  CUDA_TRY(ctx, cudaGetLastError());
+  ctx->launches++;
+  return L2HMC_OK;
+}
+
 // U(x) -> st.U and (want_grad) grad U(x) -> ab[:, D:2D], for the chains' current st.x
 int lay_energy_grad(l2hmc_ctx *ctx, cudaStream_t s, long long n, const float *aux, int want_grad) {
   LayeredCtx &L = ctx->lay;
@@ -327,11 +349,8 @@ int lay_energy_grad(l2hmc_ctx *ctx, cudaStream_t s, long long n, const float *au
   // Operand images (layered::SplitImage): with the fp16 x3 tensor-core GEMMs every activation / gradient that is the A
   // operand of the next GEMM is written ONCE, already split, by the kernel that produces it (GEMM epilogue or k_lay_bce) and
   // fetched by TMA; otherwise each of the next GEMM's N / 256 column tiles would convert it again.
-  bool pre = L.gemm_tc && L.gemm_f16 && L.presplit && want_grad && !(*(volatile unsigned int *)ctx->status_h & STATUS_F16_RANGE);
-  for (int i = 0; pre && i < nl; ++i) {
-    auto fw = L.tcw.find(m.W[i]), bw = L.tcw.find(m.Wt[i]);
-    pre = fw != L.tcw.end() && bw != L.tcw.end() && fw->second.has16 && bw->second.has16;
-  }
+  bool pre = lay_presplit_ok(ctx) && want_grad;
+  for (int i = 0; pre && i < nl; ++i) pre = lay_has16(ctx, m.W[i]) && lay_has16(ctx, m.Wt[i]);
   const int nmb = l2hmc::layered::SplitImage::nmb(n);
   if (pre) {
     L.aimg.resize(nl + 1);
@@ -345,13 +364,14 @@ int lay_energy_grad(l2hmc_ctx *ctx, cudaStream_t s, long long n, const float *au
   auto img = [](DevBuf &b) { return reinterpret_cast<uint8_t *>(b.p); };
   const float *A = st.x;
   int lda = dm.Dp;
+  if (pre && (rc = lay_split(ctx, s, st.x, dm.Dp, dm.Dp, n, L.ximg))) return rc;
   for (int i = 0; i < nl; ++i) {
     const bool last = (i + 1 == nl);
     GemmArgs g = gemm_args(A, lda, m.W[i], m.wp[i + 1], L.dact[i + 1].p, m.wp[i + 1], n, m.wp[i + 1], m.wp[i], m.b[i],
                            last ? l2hmc::layered::EPI_BIAS : l2hmc::layered::EPI_SOFTPLUS);
     if (pre) {
       g.img_nmb = nmb;
-      if (i >= 1) g.a_img = img(L.aimg[i]);
+      g.a_img = i >= 1 ? img(L.aimg[i]) : img(L.ximg);
       if (!last) g.c_img = img(L.aimg[i + 1]);
     }
     if ((rc = lay_gemm(ctx, s, g))) return rc;
@@ -394,6 +414,14 @@ int lay_net_call(l2hmc_ctx *ctx, cudaStream_t s, int net_id, int it, long long n
   const LayNetView &w = L.net[net_id];
   LayState st = lay_state(ctx, L.ws_n);
   int rc;
+  // operand images: [a | b] split once, the two hidden activations leave their GEMMs as images only (no fp32 copy)
+  const bool pre = lay_presplit_ok(ctx) && lay_has16(ctx, w.Wemb) && lay_has16(ctx, w.W4) && lay_has16(ctx, w.Wh);
+  const int nmb = l2hmc::layered::SplitImage::nmb(n);
+  if (pre) {
+    if ((rc = lay_split(ctx, s, st.ab, dm.K1p, dm.K1p, n, L.abimg))) return rc;
+    const size_t fl = l2hmc::layered::SplitImage::bytes(n, dm.Hp) / sizeof(float);
+    if ((rc = ensure_zero(ctx, L.hAimg, fl)) || (rc = ensure_zero(ctx, L.hBimg, fl))) return rc;
+  }
   GemmArgs g = gemm_args(st.ab, dm.K1p, w.Wemb, dm.Hp, L.hA.p, dm.Hp, n, dm.Hp, dm.K1p,
                          tbias ? tbias : w.tb + (size_t)it * dm.Hp, l2hmc::layered::EPI_RELU);
   if (!tbias) g.bias_b = w.tb + (size_t)(dm.T - 1 - it) * dm.Hp;
@@ -402,10 +430,13 @@ int lay_net_call(l2hmc_ctx *ctx, cudaStream_t s, int net_id, int it, long long n
     g.R = L.eaux.p;
     g.ldr = dm.Hp;
   }
+  if (pre) { g.img_nmb = nmb; g.a_img = lay_img(L.abimg); g.c_img = lay_img(L.hAimg); g.no_c = 1; }
   if ((rc = lay_gemm(ctx, s, g))) return rc;
   g = gemm_args(L.hA.p, dm.Hp, w.W4, dm.Hp, L.hB.p, dm.Hp, n, dm.Hp, dm.Hp, w.b4, l2hmc::layered::EPI_RELU);
+  if (pre) { g.img_nmb = nmb; g.a_img = lay_img(L.hAimg); g.c_img = lay_img(L.hBimg); g.no_c = 1; }
   if ((rc = lay_gemm(ctx, s, g))) return rc;
   g = gemm_args(L.hB.p, dm.Hp, w.Wh, dm.N3p, st.hd, dm.N3p, n, dm.N3p, dm.Hp, w.bh, l2hmc::layered::EPI_BIAS);
+  if (pre) { g.img_nmb = nmb; g.a_img = lay_img(L.hBimg); }
   return lay_gemm(ctx, s, g);
 }
 
