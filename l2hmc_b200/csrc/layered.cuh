@@ -294,60 +294,19 @@ __global__ void k_lay_grad_generic(LayDims dm, LayState st, EnergyDev en, Shape 
 //   U = like * sum_j [max(l,0) - l a + log(1 + exp(-|l|))] + 0.5 |z|^2, all / temperature;  l <- dU/dl = like * (sigmoid(l) - a).
 // like = 1 for the sampler; the annealed energy of utils/ais.py:44-45 between the prior and this posterior is like = beta.
 __global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const float *aux, float inv_temp, float like,
-                          long long n_chains, uint8_t *img, int img_nmb) {
+                          long long n_chains) {
   const long long n = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (n >= n_chains) return;
   float s = 0.f;
   float *l = logits + n * ldl;
   const float *a = aux + n * dm.aux;
-  if (img != nullptr) {
-    // dU/dl goes out as the operand image of the first reverse GEMM (SplitImage; |dU/dl| <= like <= 1, no range guard):
-    // a lane owns 8 consecutive columns = one 16-byte piece of hi and of lo
-    float unused = 0.f;
-    // 16-byte loads when the rows allow it (row strides multiples of 4 floats, 16-byte aligned bases)
-    const bool vec = ((ldl | dm.aux) & 3) == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(aux)) & 15) == 0;
-    for (int j0 = 8 * lane; j0 < dm.aux; j0 += 256) {
-      float l8[8], a8[8], d8[8];
-      if (vec && j0 + 8 <= dm.aux) {
-        const float4 l0 = *reinterpret_cast<const float4 *>(l + j0), l1 = *reinterpret_cast<const float4 *>(l + j0 + 4);
-        const float4 a0 = __ldg(reinterpret_cast<const float4 *>(a + j0)), a1 = __ldg(reinterpret_cast<const float4 *>(a + j0 + 4));
-        l8[0] = l0.x; l8[1] = l0.y; l8[2] = l0.z; l8[3] = l0.w; l8[4] = l1.x; l8[5] = l1.y; l8[6] = l1.z; l8[7] = l1.w;
-        a8[0] = a0.x; a8[1] = a0.y; a8[2] = a0.z; a8[3] = a0.w; a8[4] = a1.x; a8[5] = a1.y; a8[6] = a1.z; a8[7] = a1.w;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const bool ok = j0 + j < dm.aux;
-          l8[j] = ok ? l[j0 + j] : 0.f;
-          a8[j] = ok ? a[j0 + j] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float dj = 0.f;
-        if (j0 + j < dm.aux) {
-          const float lj = l8[j], aj = a8[j];
-          const float e = expf(-fabsf(lj));
-          s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
-          const float r = __fdividef(1.f, 1.f + e);
-          dj = like * (((lj >= 0.f) ? r : e * r) - aj);
-        }
-        d8[j] = dj;
-      }
-      uint4 hi, lo;
-      split8_to_half(d8, hi, lo, unused);
-      uint8_t *ip = img + SplitImage::piece(n, j0, img_nmb);
-      *reinterpret_cast<uint4 *>(ip) = hi;
-      *reinterpret_cast<uint4 *>(ip + 8192) = lo;
-    }
-  } else {
-    for (int j = lane; j < dm.aux; j += 32) {
-      const float lj = l[j], aj = a[j];
-      const float e = expf(-fabsf(lj));
-      s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
-      const float r = __fdividef(1.f, 1.f + e);  // 1 + e in [1, 2]
-      l[j] = like * (((lj >= 0.f) ? r : e * r) - aj);
-    }
+  for (int j = lane; j < dm.aux; j += 32) {
+    const float lj = l[j], aj = a[j];
+    const float e = expf(-fabsf(lj));
+    s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
+    const float r = __fdividef(1.f, 1.f + e);  // 1 + e in [1, 2]
+    l[j] = like * (((lj >= 0.f) ? r : e * r) - aj);
   }
   float q = 0.f;
   for (int d = lane; d < dm.D; d += 32) {
@@ -357,6 +316,70 @@ __global__ void k_lay_bce(LayDims dm, LayState st, float *logits, int ldl, const
   s = warp_sum(s);
   q = warp_sum(q);
   if (lane == 0) st.U[n] = (like * s + 0.5f * q) * inv_temp;
+}
+
+// The same, with dU/dl written as the operand image of the first reverse GEMM (SplitImage; |dU/dl| <= like <= 1: no range
+// guard) instead of in place.  A warp owns 8 consecutive chains: lane = (row r8 = lane & 7, column piece kc = lane >> 3), one
+// iteration = a 32-column k-block, so its loads are 128 contiguous bytes per row and its image stores 128 contiguous bytes
+// per piece (full 32-byte sectors -- 16-byte stores scattered over the image cost a sector fill each).
+__global__ void __launch_bounds__(256) k_lay_bce_img(LayDims dm, LayState st, const float *logits, int ldl, const float *aux,
+                                                     float inv_temp, float like, long long n_chains, uint8_t *img, int img_nmb) {
+  const long long w = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, r8 = lane & 7, kc = lane >> 3;
+  const long long n = w * 8 + r8;
+  const bool ok = n < n_chains;
+  const long long nn = ok ? n : 0;
+  const float *l = logits + nn * ldl;
+  const float *a = aux + nn * dm.aux;
+  // 16-byte loads when the rows allow it (row strides multiples of 4 floats, 16-byte aligned bases)
+  const bool vec = ((ldl | dm.aux) & 3) == 0 && ((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(aux)) & 15) == 0;
+  float s = 0.f, unused = 0.f;
+  for (int j0 = 8 * kc; j0 < dm.aux; j0 += 32) {
+    float l8[8], a8[8], d8[8];
+    if (vec && j0 + 8 <= dm.aux) {
+      const float4 l0 = __ldg(reinterpret_cast<const float4 *>(l + j0)), l1 = __ldg(reinterpret_cast<const float4 *>(l + j0 + 4));
+      const float4 a0 = __ldg(reinterpret_cast<const float4 *>(a + j0)), a1 = __ldg(reinterpret_cast<const float4 *>(a + j0 + 4));
+      l8[0] = l0.x; l8[1] = l0.y; l8[2] = l0.z; l8[3] = l0.w; l8[4] = l1.x; l8[5] = l1.y; l8[6] = l1.z; l8[7] = l1.w;
+      a8[0] = a0.x; a8[1] = a0.y; a8[2] = a0.z; a8[3] = a0.w; a8[4] = a1.x; a8[5] = a1.y; a8[6] = a1.z; a8[7] = a1.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool in = j0 + j < dm.aux;
+        l8[j] = in ? l[j0 + j] : 0.f;
+        a8[j] = in ? a[j0 + j] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float dj = 0.f;
+      if (j0 + j < dm.aux) {
+        const float lj = l8[j], aj = a8[j];
+        const float e = expf(-fabsf(lj));
+        s += fmaxf(lj, 0.f) - lj * aj + log1p_unit(e);
+        const float r = __fdividef(1.f, 1.f + e);  // 1 + e in [1, 2]
+        dj = like * (((lj >= 0.f) ? r : e * r) - aj);
+      }
+      d8[j] = dj;
+    }
+    if (ok) {
+      uint4 hi, lo;
+      split8_to_half(d8, hi, lo, unused);
+      uint8_t *ip = img + SplitImage::piece(n, j0, img_nmb);
+      *reinterpret_cast<uint4 *>(ip) = hi;
+      *reinterpret_cast<uint4 *>(ip + 8192) = lo;
+    }
+  }
+  float q = 0.f;
+  for (int d = kc; d < dm.D; d += 4) {
+    const float z = st.x[nn * dm.Dp + d];
+    q = fmaf(z, z, q);
+  }
+  // the four column pieces of a row sit in lanes r8, r8 + 8, r8 + 16, r8 + 24
+  s += __shfl_xor_sync(0xffffffffu, s, 8);
+  s += __shfl_xor_sync(0xffffffffu, s, 16);
+  q += __shfl_xor_sync(0xffffffffu, q, 8);
+  q += __shfl_xor_sync(0xffffffffu, q, 16);
+  if (ok && kc == 0) st.U[n] = (like * s + 0.5f * q) * inv_temp;
 }
 
 // fp32 rows [n][ld] (columns [0, K), K % 8 == 0, pad columns zero) -> operand image (SplitImage) for a GEMM whose A they are.

@@ -378,8 +378,11 @@ int lay_energy_grad(l2hmc_ctx *ctx, cudaStream_t s, long long n, const float *au
     A = L.dact[i + 1].p;
     lda = m.wp[i + 1];
   }
-  l2hmc::layered::k_lay_bce<<<WGRID(n), 0, s>>>(dm, st, L.dact[nl].p, m.wp[nl], aux, 1.0f / ctx->en.temperature, L.like_scale, n,
-                                                pre ? img(L.gimg[nl]) : nullptr, nmb);
+  if (pre)
+    l2hmc::layered::k_lay_bce_img<<<(unsigned)((n + 63) / 64), 256, 0, s>>>(dm, st, L.dact[nl].p, m.wp[nl], aux, 1.0f / ctx->en.temperature,
+                                                                            L.like_scale, n, img(L.gimg[nl]), nmb);
+  else
+    l2hmc::layered::k_lay_bce<<<WGRID(n), 0, s>>>(dm, st, L.dact[nl].p, m.wp[nl], aux, 1.0f / ctx->en.temperature, L.like_scale, n);
   CUDA_TRY(ctx, cudaGetLastError());
   ctx->launches++;
   if (!want_grad) return L2HMC_OK;
