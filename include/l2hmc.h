@@ -247,10 +247,12 @@ int l2hmc_status_flags(l2hmc_ctx *ctx, uint32_t *flags, int clear);
  * and adds the `x` batch and the `z` batch of the notebook objective.  Device pointers throughout; asynchronous on the
  * stream (scratch, 4*T*2*x_dim floats per chain for the record plus activations, is held by the context).  Covers the closed-form energies (Gaussian, GMM, RoughWell, funnel) without aux; the decoder target and
  * aux-conditioned nets: L2HMC_EUNSUPPORTED.
- * Determinism: the weight gradients are sums over chains accumulated with fp32 atomicAdd (split-K GEMMs, per-warp
- *   reductions), so two calls on the same inputs agree to fp32 rounding of a different summation order (~1e-6 relative),
- *   not bit for bit; loss, Lx and px_out are deterministic.  (TF1's reductions on the reference's GPU path are not
- *   run-to-run deterministic either.)
+ * Determinism: on the launch-sequence path (any shape) the sums over chains -- weight-gradient products, bias column sums,
+ *   loss -- are split over CTAs into per-part slices and added in part order by a second kernel: two calls on the same
+ *   inputs return the same bits.  The fused kernel for the notebook's small nets (x_dim <= 4, width <= 16, T <= 32)
+ *   adds one partial sum per block with fp32 atomicAdd: there two calls agree to fp32 rounding of another summation
+ *   order (~1e-6 relative), not bit for bit (L2HMC_TRAIN_FUSED=0 selects the launch sequence); loss, Lx and px_out are
+ *   deterministic on both.  (TF1's reductions on the reference's GPU path are not run-to-run deterministic either.)
  * Streams: the scratch belongs to the context -- calls on ONE context must be issued on one stream (or ordered by the
  *   caller); use one context per stream for concurrent batches. */
 typedef struct {

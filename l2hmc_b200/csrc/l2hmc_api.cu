@@ -87,6 +87,7 @@ struct l2hmc_ctx {
   std::vector<float> net_host[2];
   DevBuf mask;
   DevBuf train_ws;       // scratch of l2hmc_loss_grad (train_host.cuh), grown on demand, kept until destroy
+  float *train_part = nullptr;  // inside train_ws: the parts of the call's split reductions
   bool mask_set = false;
   DevBuf energy_buf, energy_buf2;  // energy_buf2: the second part of a mixed energy
   EnergyDev en;

@@ -8,7 +8,7 @@
 //   forward sweep : 4 T sub-updates (V, X, X, V per leapfrog step); the state (x, v) in front of each one is recorded
 //   reverse sweep : per sub-update, last to first: recompute its net forward from the record, apply the vector-Jacobian
 //                   product of the update (k_update_vjp), of the S/T/Q net (GEMMs against the transposed weights, weight
-//                   gradients as K = chains products with atomic accumulation) and of grad U (k_hvp).
+//                   gradients as K = chains products, split over CTAs and reduced in a fixed order) and of grad U (k_hvp).
 // Layout: chain-major unpadded fp32 rows ([n, D] states, [n, 2D] net input, [n, H] activations, [n, 3D] heads) against
 // the reference-layout weights the context already holds (NetRaw).  GEMMs are a plain shared-memory fp32 FMA kernel with
 // strided operands: this version is about the gradient being right, not about speed (DESIGN.md section 7.1 has the plan
@@ -18,23 +18,27 @@
 #include "common.cuh"
 #endif
 
+// Reductions over the chains (weight-gradient products, column sums) are split over CTAs and finished in a fixed order by
+// k_reduce_add: deterministic, no atomics.  Smallest split sizes (the host grows them so that at most TR_MAX_PARTS parts
+// exist per reduction); the CPU emulation shrinks both.
 #ifndef L2HMC_TR_KCHUNK
-#define L2HMC_TR_KCHUNK 4096  // chains per CTA of a weight-gradient product (split K); the CPU emulation shrinks both
+#define L2HMC_TR_KCHUNK 128   // chains per CTA of a weight-gradient product (split K)
 #endif
 #ifndef L2HMC_TR_SLAB
-#define L2HMC_TR_SLAB 1024    // rows per CTA of a column sum
+#define L2HMC_TR_SLAB 64      // rows per CTA of a column sum
 #endif
+#define L2HMC_TR_MAX_PARTS 64
 
 namespace l2hmc {
 namespace train {
 
-// C[m][n] (=, +=, atomic +=) sum_k A(m,k) B(k,n);  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
+// C[m][n] (=, +=, or per-part slices) sum_k A(m,k) B(k,n);  A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn]
 struct Gemm {
   const float *A; long long sam, sak;
   const float *B; long long sbk, sbn;
   float *C; long long ldc;
   long long M; int N; long long K;
-  int mode;          // 0 store, 1 add (one writer per element), 2 atomicAdd (split K)
+  int mode;          // 0 store, 1 add (one writer per element), 2 split K: part blockIdx.z stores its [M][N] slice of C (ldc = N)
   long long kchunk;  // K range per blockIdx.z
 };
 
@@ -93,20 +97,30 @@ __global__ void __launch_bounds__(256) k_gemm(const Gemm g) {
       float *c = g.C + m * g.ldc + n;
       if (g.mode == 0) *c = acc[i][j];
       else if (g.mode == 1) *c += acc[i][j];
-      else atomicAdd(c, acc[i][j]);
+      else c[(long long)blockIdx.z * g.M * g.ldc] = acc[i][j];
     }
   }
 }
 
-// out[c] += sum_r w[r] * A[r*lda + c]  (w == null: plain column sums); rows split over blockIdx.y, atomics per slab
-__global__ void k_colsum(const float *A, long long lda, long long n_rows, int n_cols, const float *w, float *out) {
+// part[blockIdx.y][c] = sum over the slab's rows of w[r] * A[r*lda + c]  (w == null: plain column sums)
+__global__ void k_colsum(const float *A, long long lda, long long n_rows, int n_cols, const float *w, float *part, long long slab) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= n_cols) return;
-  const long long r0 = (long long)blockIdx.y * L2HMC_TR_SLAB;
-  const long long r1 = (r0 + L2HMC_TR_SLAB < n_rows) ? r0 + L2HMC_TR_SLAB : n_rows;
+  const long long r0 = (long long)blockIdx.y * slab;
+  const long long r1 = (r0 + slab < n_rows) ? r0 + slab : n_rows;
   float s = 0.f;
   for (long long r = r0; r < r1; ++r) s = fmaf(w ? w[r] : 1.f, A[r * lda + c], s);
-  atomicAdd(out + c, s);
+  part[(long long)blockIdx.y * n_cols + c] = s;
+}
+
+// dst[m*ldc + n] += part[0][m][n] + part[1][m][n] + ... (parts added in index order: the same bits on every run)
+__global__ void k_reduce_add(const float *part, int n_parts, long long M, int N, float *dst, long long ldc) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= M * N) return;
+  float s = 0.f;
+  for (int z = 0; z < n_parts; ++z) s += part[(long long)z * M * N + i];
+  const long long m = i / N;
+  dst[m * ldc + (i - m * N)] += s;
 }
 
 // per chain: the step index it is at and its time features (utils/dynamics.py:99-105; backward chains count down, :285)

@@ -53,19 +53,36 @@ inline TrGB tr_gb(dim3 g, dim3 b) { return TrGB{g, b}; }
     (ctx)->launches++;                                  \
   } while (0)
 
+// Parts of a reduction over K elements with a smallest part size: at most L2HMC_TR_MAX_PARTS of them
+inline long long tr_part_size(long long K, long long smallest) {
+  const long long grown = (K + L2HMC_TR_MAX_PARTS - 1) / L2HMC_TR_MAX_PARTS;
+  return grown > smallest ? grown : smallest;
+}
+// floats of the scratch the split reductions of one call need (largest product: [max(H, D)][H] per part)
+inline size_t tr_part_floats(int D, int H) { return (size_t)L2HMC_TR_MAX_PARTS * (size_t)(H > D ? H : D) * (size_t)(H > D ? H : D); }
+
+#define TR_EGRID(tot) tr_gb((unsigned)(((tot) + 255) / 256), 256)
+#define TR_WGRID(n) tr_gb((unsigned)(((n) * 32 + 255) / 256), 256)
+
+// mode 2 (C += A B with K = the chains): split K over CTAs into ctx's part buffer, then an ordered reduction
 int tr_gemm(l2hmc_ctx *ctx, cudaStream_t s, tr::Gemm g) {
   if (g.M <= 0 || g.N <= 0 || g.K <= 0) return L2HMC_OK;
   const long long gy = (g.M + 63) / 64;
   long long gz = 1;
+  float *dst = g.C;
+  const long long dst_ld = g.ldc;
   if (g.mode == 2) {
-    g.kchunk = L2HMC_TR_KCHUNK;
+    g.kchunk = tr_part_size(g.K, L2HMC_TR_KCHUNK);
     gz = (g.K + g.kchunk - 1) / g.kchunk;
+    g.C = ctx->train_part;
+    g.ldc = g.N;
   } else {
     g.kchunk = g.K;
   }
   if (gy > 65535 || gz > 65535) return fail(ctx, L2HMC_EUNSUPPORTED, "l2hmc_loss_grad: more than 4.1M chains per call");
 #define TR_GEMM_GRID tr_gb(dim3((unsigned)((g.N + 63) / 64), (unsigned)gy, (unsigned)gz), 256)
   TR_LAUNCH(ctx, tr::k_gemm, TR_GEMM_GRID, s, g);
+  if (g.mode == 2) TR_LAUNCH(ctx, tr::k_reduce_add, TR_EGRID(g.M * g.N), s, ctx->train_part, (int)gz, g.M, g.N, dst, dst_ld);
   return L2HMC_OK;
 }
 
@@ -77,14 +94,15 @@ tr::Gemm tr_g(const float *A, long long sam, long long sak, const float *B, long
   return g;
 }
 
+// out[c] += sum_r w[r] A[r][c]: slabs of rows into the part buffer, then the ordered reduction
 int tr_colsum(l2hmc_ctx *ctx, cudaStream_t s, const float *A, long long lda, long long n, int cols, const float *w, float *out) {
-#define TR_COLSUM_GRID tr_gb(dim3((unsigned)((cols + 127) / 128), (unsigned)((n + L2HMC_TR_SLAB - 1) / L2HMC_TR_SLAB)), 128)
-  TR_LAUNCH(ctx, tr::k_colsum, TR_COLSUM_GRID, s, A, lda, n, cols, w, out);
+  const long long slab = tr_part_size(n, L2HMC_TR_SLAB);
+  const long long parts = (n + slab - 1) / slab;
+#define TR_COLSUM_GRID tr_gb(dim3((unsigned)((cols + 127) / 128), (unsigned)parts), 128)
+  TR_LAUNCH(ctx, tr::k_colsum, TR_COLSUM_GRID, s, A, lda, n, cols, w, ctx->train_part, slab);
+  TR_LAUNCH(ctx, tr::k_reduce_add, TR_EGRID(cols), s, ctx->train_part, (int)parts, 1ll, cols, out, (long long)cols);
   return L2HMC_OK;
 }
-
-#define TR_EGRID(tot) tr_gb((unsigned)(((tot) + 255) / 256), 256)
-#define TR_WGRID(n) tr_gb((unsigned)(((n) * 32 + 255) / 256), 256)
 
 // [S | T | Q] pre-activations of net([a, b, t]) for every chain (SCGExperiment.ipynb:51-77), activations kept
 int tr_net_forward(l2hmc_ctx *ctx, cudaStream_t s, const NetRaw &w, long long n, const TrNetBufs &b) {
@@ -148,11 +166,11 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
   const float eps = sh.eps;
   cudaStream_t s = (cudaStream_t)a->stream;
   const size_t nD = (size_t)n * D, nH = (size_t)n * H;
-  float *tape_x, *tape_v, *x, *v, *gU, *ab, *h1, *h2, *gh1, *gh2, *hd, *ghd, *sc, *gab, *gx, *gv, *gg, *vec;
+  float *tape_x, *tape_v, *x, *v, *gU, *ab, *h1, *h2, *gh1, *gh2, *hd, *ghd, *sc, *gab, *gx, *gv, *gg, *vec, *part;
   struct { float **p; size_t n; } req[] = {
       {&tape_x, nD * 4 * T}, {&tape_v, nD * 4 * T}, {&x, nD}, {&v, nD}, {&gU, nD}, {&ab, 2 * nD}, {&h1, nH}, {&h2, nH},
       {&gh1, nH}, {&gh2, nH}, {&hd, 3 * nD}, {&ghd, 3 * nD}, {&sc, 2 * nD}, {&gab, 2 * nD}, {&gx, nD}, {&gv, nD}, {&gg, nD},
-      {&vec, (size_t)n * 10 + 4}};
+      {&vec, (size_t)n * 10 + 4}, {&part, tr_part_floats(D, H)}};
 #ifndef L2HMC_TRAIN_EMU
   auto pad = [](size_t k) { return (k + 63) / 64 * 64; };
 #else  // host emulation: a 64-float guard zone (NaN-filled by the emulated cudaMalloc) after each sub-buffer, checked at the end
@@ -167,6 +185,7 @@ int tr_loss_grad(l2hmc_ctx *ctx, const l2hmc_loss_grad_args *a) {
     *r.p = base;
     base += pad(r.n);
   }
+  ctx->train_part = part;
   float *logj = vec, *H0 = vec + n, *H1 = vec + 2 * n, *lossv = vec + 3 * n, *px = vec + 4 * n, *glj = vec + 5 * n,
         *geps = vec + 6 * n, *ct = vec + 7 * n, *st = vec + 8 * n, *vv = vec + 9 * n, *stats = vec + 10 * n;
   CUDA_TRY(ctx, cudaMemcpyAsync(x, a->x, nD * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -227,6 +227,7 @@ struct l2hmc_ctx {
   DevBufEmu mask;
   NetRaw net_rawv[2];
   DevBufEmu train_ws;
+  float *train_part = nullptr;
   long long launches = 0;
   std::string err;
   ~l2hmc_ctx() { free(train_ws.p); }
