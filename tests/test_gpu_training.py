@@ -229,6 +229,22 @@ def test_sharded_internal_draws_equal_the_single_rank_draws():
     assert not torch.equal(wrong[2], Lx[90:200])
 
 
+def test_launch_sequence_gradients_are_bit_reproducible():
+    """The sums over chains (weight-gradient products, bias column sums, loss) are split over CTAs and added in part order
+    (train.cuh: k_reduce_add), no atomics: the same inputs give the same bits, with more chains than one part holds."""
+    P, x, d, v = _setup("c2_scg50", 1000)
+    rng = {"direction": torch.as_tensor(d, device=DEV), "v": torch.as_tensor(v, device=DEV)}
+    xt = torch.as_tensor(x, device=DEV)
+    dyn = P.product()
+    a = training.loss_and_grads(dyn, xt, rng=rng, scale=0.1)
+    b = training.loss_and_grads(dyn, xt, rng=rng, scale=0.1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3])
+    for key in ("XNet", "VNet"):
+        for k in training.NAMES:
+            assert torch.equal(a[1][key][k], b[1][key][k]), (key, k)
+    assert torch.equal(a[1]["eps"], b[1]["eps"])
+
+
 @pytest.mark.parametrize("name,n", [("c1_scg2", 200), ("c3_mog2", 333), ("funnel3", 130)])
 def test_fused_small_net_training_kernel_is_one_launch_and_equals_the_launch_sequence(name, n, monkeypatch):
     """x_dim <= 4 / width <= 16 (the notebook's nets): l2hmc_loss_grad is ONE launch of small_train_kernel (one chain per
