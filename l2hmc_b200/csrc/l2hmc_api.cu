@@ -19,6 +19,7 @@
 #include "kernel_small.cuh"
 #include "layered.cuh"
 #include "tc_gemm.cuh"
+#include "tc_net.cuh"
 
 #include <map>
 
@@ -64,6 +65,7 @@ struct LayeredCtx {
   DevBuf ximg, abimg, hAimg, hBimg;                // ... of x, of the net input [a | b], of the nets' two hidden activations
   bool presplit = true;                            // L2HMC_LAYERED_PRESPLIT=0: every GEMM converts its own A operand
   int presplit_mode = 2;                           // 2: tc_gemm_pre_kernel (default); 1: the 256-row kernel with a TMA-fed A
+  bool fused_net = true;                           // one kernel per S/T/Q net call (tc_net.cuh); L2HMC_LAYERED_FUSED_NET=0: three GEMMs
   long long ws_n = 0;
   cudaEvent_t ws_event = nullptr;  // recorded when a call's last workspace user is enqueued
   bool ws_recorded = false;
@@ -664,6 +666,8 @@ extern "C" int l2hmc_create(const l2hmc_config *cfg, l2hmc_ctx **out) {
     const char *ps = getenv("L2HMC_LAYERED_PRESPLIT");
     if (ps && ps[0] == '0') ctx->lay.presplit = false;
     if (ps && ps[0] == '1') ctx->lay.presplit_mode = 1;
+    const char *fn = getenv("L2HMC_LAYERED_FUSED_NET");
+    if (fn && fn[0] == '0') ctx->lay.fused_net = false;
     cudaDeviceGetAttribute(&ctx->lay.sms, cudaDevAttrMultiProcessorCount, cfg->device);
   }
   int rc = pick_kernel(ctx);

@@ -425,9 +425,28 @@ int lay_net_call(l2hmc_ctx *ctx, cudaStream_t s, int net_id, int it, long long n
     const size_t fl = l2hmc::layered::SplitImage::bytes(n, dm.Hp) / sizeof(float);
     if ((rc = ensure_zero(ctx, L.hAimg, fl)) || (rc = ensure_zero(ctx, L.hBimg, fl))) return rc;
   }
-  GemmArgs g = gemm_args(st.ab, dm.K1p, w.Wemb, dm.Hp, L.hA.p, dm.Hp, n, dm.Hp, dm.K1p,
-                         tbias ? tbias : w.tb + (size_t)it * dm.Hp, l2hmc::layered::EPI_RELU);
-  if (!tbias) g.bias_b = w.tb + (size_t)(dm.T - 1 - it) * dm.Hp;
+  const float *bias_f = tbias ? tbias : w.tb + (size_t)it * dm.Hp;
+  const float *bias_b = tbias ? tbias : w.tb + (size_t)(dm.T - 1 - it) * dm.Hp;
+  if (pre && L.fused_net) {
+    // the three GEMMs as one kernel (tc_net.cuh): the hidden activations stay on the SM
+    l2hmc::tcg::NetFusedArgs p;
+    p.a_img = lay_img(L.abimg); p.img_nmb = nmb; p.M = n;
+    p.w1 = L.tcw[w.Wemb].d16; p.w2 = L.tcw[w.W4].d16; p.w3 = L.tcw[w.Wh].d16;
+    p.N1 = dm.Hp; p.N3 = dm.N3p;
+    p.bias1 = bias_f; p.bias1_b = bias_b; p.dir = dir;
+    p.R = L.enc.n_layers > 0 ? L.eaux.p : nullptr; p.ldr = dm.Hp;
+    p.bias2 = w.b4; p.bias3 = w.bh; p.hd = st.hd; p.ldc = dm.N3p; p.status = ctx->status_d;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(bias_f) | reinterpret_cast<uintptr_t>(bias_b) | reinterpret_cast<uintptr_t>(w.b4) |
+                           reinterpret_cast<uintptr_t>(w.bh)) % 16) == 0;
+    if (aligned && l2hmc::tcg::tc_net_fits(p, 227 * 1024)) {
+      CUDA_TRY(ctx, l2hmc::tcg::launch_tc_net(p, L.sms, s));
+      ctx->launches++;
+      L.used_f16 = true;
+      return L2HMC_OK;
+    }
+  }
+  GemmArgs g = gemm_args(st.ab, dm.K1p, w.Wemb, dm.Hp, L.hA.p, dm.Hp, n, dm.Hp, dm.K1p, bias_f, l2hmc::layered::EPI_RELU);
+  g.bias_b = bias_b;
   g.dir = dir;
   if (L.enc.n_layers > 0) {
     g.R = L.eaux.p;

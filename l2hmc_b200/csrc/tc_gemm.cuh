@@ -110,9 +110,11 @@ __device__ __forceinline__ float epi_apply(float v, float aux, float scale) {
 
 // One 16-column chunk of an output row: acc = A B for columns [nbase, nbase + 16) of row m (m < M, nbase < N) -> fused layer
 // tail -> fp32 C and / or the operand image of the next GEMM.  Shared by the GEMM kernels below.
+// img_row / img_nmb: the row and 128-row-block count used for the image address (default: the global row of g.c_img; the fused
+// net kernel writes a one-block image in shared memory with the row inside the tile).
 template <int EPI>
 __device__ __forceinline__ void epi_chunk(const layered::GemmArgs &g, float (&acc)[16], long long m, int nbase, const float *bias,
-                                          float &omax) {
+                                          float &omax, long long img_row = -1, int img_nmb = 0) {
   float *Cp = g.C + m * (long long)g.ldc + nbase;
   const bool full = nbase + 15 < g.N;
   if (full && g.vec) {
@@ -165,7 +167,7 @@ __device__ __forceinline__ void epi_chunk(const layered::GemmArgs &g, float (&ac
   if (g.c_img != nullptr) {
     // the same values as the next GEMM's operand image: columns [nbase, nbase + 16) = two 16-byte pieces of hi and of lo;
     // the 32 lanes of the warp (consecutive rows) write 512 contiguous bytes per piece
-    uint8_t *ip = g.c_img + layered::SplitImage::piece(m, nbase, g.img_nmb);
+    uint8_t *ip = g.c_img + (img_row >= 0 ? layered::SplitImage::piece(img_row, nbase, img_nmb) : layered::SplitImage::piece(m, nbase, g.img_nmb));
 #pragma unroll
     for (int p8 = 0; p8 < 2; ++p8) {
       float a8[8];

@@ -124,6 +124,25 @@ def test_presplit_kernel_variants_agree(monkeypatch):
         assert np.array_equal(a[k], b[k]), k
 
 
+@pytest.mark.parametrize("name,n", [("c5_vae_mini", 300), ("c5_vae_ragged", 131), ("c5_vae_noenc", 200), ("c5_vae_full", 700)])
+def test_fused_net_kernel_equals_the_three_gemms(monkeypatch, name, n):
+    """tc_net_kernel (one launch per S/T/Q net call, hidden activations as operand images in shared memory) against the
+    three tc_gemm_pre_kernel launches it replaces (L2HMC_LAYERED_FUSED_NET=0): same split, k order and epilogue code, so
+    the same bits; and fewer launches."""
+    P = U.VaeProblem(**U.VAE_CONFIGS[name])
+    d = P.draws(n)
+    monkeypatch.delenv("L2HMC_LAYERED_FUSED_NET", raising=False)
+    da = P.product()
+    a = U.run_kernel_propose(P, d, dyn=da)
+    la = da.launch_count
+    monkeypatch.setenv("L2HMC_LAYERED_FUSED_NET", "0")
+    db = P.product()
+    b = U.run_kernel_propose(P, d, dyn=db)
+    for k in ("Lx", "Lv", "px", "x_next"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.isfinite(a["Lx"]).all() and la < db.launch_count
+
+
 def test_vae_log_jac_mode():
     P = U.VaeProblem(**U.VAE_CONFIGS["c5_vae_mini"])
     rep, _ = U.parity_report(P, 192, log_jac=True)
