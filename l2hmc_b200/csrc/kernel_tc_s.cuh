@@ -55,6 +55,12 @@ constexpr int KSLOT_S = L2HMC_TC_KSLOT_S;
 #ifndef L2HMC_TC_SETMAXNREG
 #define L2HMC_TC_SETMAXNREG (L2HMC_TC_S_NQ > 2)  // the last warpgroup (MMA issuer, TMA producer, two idle warps) hands registers to the compute warpgroups
 #endif
+#ifndef L2HMC_TC_SPLIT_LAST
+#define L2HMC_TC_SPLIT_LAST 0  // hidden epilogues: an odd last 8-column chunk is shared by the two threads of a chain (4 columns each)
+#endif
+#ifndef L2HMC_TC_P0_PAIR
+#define L2HMC_TC_P0_PAIR 0  // heads epilogue, part 0 (state update only, nothing handed over): two chunks per step for the scheduler
+#endif
 static_assert(KSLOT_S % 2 == 0, "ring slot = whole A hand-over slots");
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
@@ -220,7 +226,7 @@ __device__ __forceinline__ GemmDesc gemm_desc_s(const TcArgs &A, const int NQC, 
   if (kind == 0) {
     g.src = F16 ? A.gimg_h : A.gimg; g.nsteps = ng; g.n = td.NG;
   } else if (kind == 1) {
-    g.src = img; g.nsteps = ne; g.n = td.N1;
+    g.src = img; g.nsteps = ne + (td.biasg == 2 ? 1 : 0); g.n = td.N1;  // biasg 2: one more K step that holds the bias rows only
   } else if (kind == 2) {
     g.src = img + o_hid; g.nsteps = nh; g.n = td.N1;
   } else if (kind == 3) {
@@ -413,7 +419,9 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
   constexpr int NCT = MT * NQ;  // compute threads: NQ per chain
   constexpr int W_MMA = NCT / 32, W_TMA = W_MMA + 1;
   const int DP = 4 * NQC, RS = (NQC & 1) ? DP : DP + 4;  // row stride with RS/4 odd: 8 lanes x 16 B hit 32 distinct banks
-  const int NSUB = ((NQC > NHC ? NQC : NHC) + 1) / 2;  // K slots (2 K steps) of the deepest GEMM = sub-barriers
+  // K slots (16 k) of the deepest GEMM = sub-barriers (biasg 2: the embed has one more, the bias K step)
+  const int NSUB0 = ((NQC > NHC ? NQC : NHC) + 1) / 2;
+  const int NSUB = (BIASG && A.td.biasg == 2 && NQC / 2 + 1 > NSUB0) ? NQC / 2 + 1 : NSUB0;
   const int CA = (NQC + 1) / 2, CB = NQC - CA;  // dimension chunks of heads_a / heads_b
   // TMEM map of this kernel (the host checks the same for run-time shapes, tc_s_shape_fits)
   static_assert(NQC_T == 0 || (8 * NQC_T <= 104 && 12 * ((NQC_T + 1) / 2) <= 112 && 12 * (NQC_T / 2) <= 80), "TMEM map of kernel_tc_s.cuh");
@@ -471,7 +479,7 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
     const int qd = warp >> 2;              // 0 .. NQ-1: this thread owns the chunks q = qd, qd + NQ, ... (warp-uniform)
     const uint32_t lb = ((uint32_t)(32 * (warp & 3))) << 16;
     const int qn = (NQC - qd + NQ - 1) / NQ;  // its 4-dim chunks: q = qd + NQ i, i < qn
-    const int hn = (NHC - qd + NQ - 1) / NQ;  // its 8-column hidden chunks: q = qd + NQ i, i < hn
+    const int hn_all = (NHC - qd + NQ - 1) / NQ;  // its 8-column hidden chunks: q = qd + NQ i, i < hn_all
     const long long gch = base + c;
     const bool gauss = A.en.kind == 0;
     float *xr = smem + L.xs + c * RS, *vr = smem + L.vs + c * RS, *gr = smem + L.gs + c * RS;
@@ -585,11 +593,21 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
       // net input of one 4-dim chunk: [a0..3 | b0..3] = K step q of the embed GEMM (weight rows permuted to match)
       // BIASG: the two pad dimensions of the last chunk's a-part select the time-embedding bias row of this chain's
       // direction in the embed weights ([1, 0] forward, [0, 1] backward), see tc_pack_net
+      // biasg 2 (no pad dimensions: x_dim = 4 NQC, NQC even): the one-hot sits in a K step of its own behind the net input
+      // (k = 8 NQC, 8 NQC + 1); the owner of the last chunk rewrites it with every operand (the hidden activations of the
+      // GEMMs in between use the same columns), before the arrival that releases that K step (a_done(NQC))
       auto put_ab = [&](int q, const float (&a)[4], const float (&b)[4]) {
         float ab[8] = {a[0], a[1], a[2], a[3], b[0], b[1], b[2], b[3]};
         if (BIASG && q == NQC - 1) {
-          ab[2] = fwd ? 1.f : 0.f;
-          ab[3] = fwd ? 0.f : 1.f;
+          if (td.biasg == 2) {
+            // 8 values: a whole tf32 K step (TMEM is not cleared by the allocation); fp16: the rest of the 16-k step holds
+            // finite values of earlier operands (zeroed at the start) that meet zero weight rows
+            const float oh[8] = {fwd ? 1.f : 0.f, fwd ? 0.f : 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            put_a<F16, 8>(lb, 8 * NQC, oh, amax);
+          } else {
+            ab[2] = fwd ? 1.f : 0.f;
+            ab[3] = fwd ? 0.f : 1.f;
+          }
         }
         put_a<F16, 8>(lb, 8 * q, ab, amax);
       };
@@ -703,6 +721,12 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
       auto hidden_epilogue = [&](uint32_t acc, const float *__restrict__ bias, bool handover) {
         wait_acc();
         float h[2][8];
+        // SPLIT_LAST: with an odd chunk count one thread of the chain owns a chunk more than the other and the next GEMM's
+        // last K slot waits for it alone; shared, both finish half a chunk earlier
+        const bool split = L2HMC_TC_SPLIT_LAST && NQ == 2 && (NHC & 1) && handover;
+        const int hn = split ? NHC / 2 : hn_all;
+        float hl[4] = {0.f, 0.f, 0.f, 0.f};
+        if (split) tmem_ld4(lb + acc + 8 * (NHC - 1) + 4 * qd, hl);
         if (hn > 0) tmem_ld8(lb + acc + 8 * qd, h[0]);
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
@@ -733,7 +757,22 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
           chunk(i, I0{});
           if (i + 1 < hn) chunk(i + 1, I1{});
         }
-        a_done(handover ? NHC : 0);
+        if (split) {  // columns 8 (NHC - 1) + 4 qd .. + 3 of the last chunk (loaded first: the waits above covered it)
+          const int q = NHC - 1;
+          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (!BIASG) b = ldg4(bias + 8 * q + 4 * qd);
+          if (hn == 0) tmem_wait_ld();
+          float a[4];
+          if (BIASG) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) a[j] = fmaxf(hl[j], 0.f);
+          } else {
+            a[0] = fmaxf(hl[0] + b.x, 0.f); a[1] = fmaxf(hl[1] + b.y, 0.f); a[2] = fmaxf(hl[2] + b.z, 0.f); a[3] = fmaxf(hl[3] + b.w, 0.f);
+          }
+          put_a<F16, 4>(lb, 8 * q + 4 * qd, a, amax);
+          slot_done(q);
+        }
+        a_done(handover ? (split ? NHC + 1 : NHC) : 0);
       };
 
       // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) + next A operand --------------
@@ -945,10 +984,43 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
           update(c, s4[B][0], t4[B][0], q4[B][0], ljl);
           finish(q, i, c);
         };
+        if (PART == 0 && L2HMC_TC_P0_PAIR) {
+          // part 0 hands nothing over (the A operand of its chunks is written in part 1), so the order and grouping of its
+          // chunks is free: two independent chunks per step give the scheduler twice the work in flight per warp
+          auto ld3 = [&](int q, int b) {
+            tmem_ld4(lb + cS + 4 * q, s4[b][0]);
+            tmem_ld4(lb + cT + 4 * q, t4[b][0]);
+            tmem_ld4(lb + cQ + 4 * q, q4[b][0]);
+          };
+          if (ib + 1 < ie) ld3(qd + NQ * (ib + 1), 1);
+#pragma unroll 1
+          for (int i = ib; i < ie; i += 2) {
+            const int q0 = qd + NQ * i, q1 = q0 + NQ;
+            if (i + 1 < ie) {
+              ChunkIn c0, c1;
+              load_in(q0, c0);
+              load_in(q1, c1);
+              tmem_wait_ld();
+              update(c0, s4[0][0], t4[0][0], q4[0][0], ljl);
+              update(c1, s4[1][0], t4[1][0], q4[1][0], ljl);
+              finish(q0, i, c0);
+              finish(q1, i + 1, c1);
+              if (i + 2 < ie) ld3(q0 + 2 * NQ, 0);
+              if (i + 3 < ie) ld3(q1 + 2 * NQ, 1);
+            } else {
+              ChunkIn c0;
+              load_in(q0, c0);
+              tmem_wait_ld();
+              update(c0, s4[0][0], t4[0][0], q4[0][0], ljl);
+              finish(q0, i, c0);
+            }
+          }
+        } else {
 #pragma unroll 1
         for (int i = ib; i < ie; i += 2) {
           chunk(i, I0{});
           if (i + 1 < ie) chunk(i + 1, I1{});
+        }
         }
         if (PART == 1) {
           if (MODE == 1 && next == NEXT_G && gauss) zero_gtail();  // before this warp's arrival on the last K step

@@ -367,7 +367,15 @@ static void tc_setup_dims(l2hmc_ctx *ctx) {
   td.nq = (nqe && nqe[0] >= '2' && nqe[0] <= '4') ? (nqe[0] - '0') : 2;
   // kernel_tc_s: biases as weight rows (needs two pad dimensions in the last 4-dim chunk and a pad hidden unit)
   const char *bg = getenv("L2HMC_TC_BIASG");
-  td.biasg = (!(bg && bg[0] == '0') && sh.D <= sh.DP - 2 && sh.H <= td.HK - 1 && sh.DP == 52) ? 1 : 0;  // instantiated for DP = 52 only
+  // 1: the direction one-hot sits in the two pad dimensions of the last 4-dim chunk (x_dim <= DP - 2); 2: no pad dimensions
+  // (x_dim = DP) -> a K step of its own behind the net input (needs whole 16-k steps before it: DP / 4 even, and room in the
+  // A operand: DP / 4 <= 12).  L2HMC_TC_BIASG=0: explicit biases everywhere; =1: only the round-1 case (config 2's shape).
+  td.biasg = 0;
+  if (!(bg && bg[0] == '0') && sh.H <= td.HK - 1) {
+    const int nqc = sh.DP / 4;
+    if (sh.D <= sh.DP - 2) td.biasg = (bg && bg[0] == '1' && sh.DP != 52) ? 0 : 1;
+    else if (nqc % 2 == 0 && nqc <= 12 && !(bg && bg[0] == '1')) td.biasg = 2;
+  }
   const char *fe = getenv("L2HMC_TC_F16");
   td.f16 = (fe && fe[0] == '0') ? 0 : 1;  // fp16 split when every packed value is inside the fp16 range (checked at pack time)
   ctx->tc_ok = !sh.hmc && td.K1 <= 128 && td.HK <= 128 && td.N1 <= 192 && td.N3 <= 192 && td.nslot >= 4 && td.K1 % 8 == 0;
@@ -401,7 +409,9 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
   // step, which also carry the time-embedding bias row of the chain's step: tb[it] forward, tb[T-1-it] backward -> one
   // image of that K step per leapfrog step, `emb_last`), the hidden layer passes it on and adds b4, the heads add bs/bt/bq.
   const bool biasg = td.biasg != 0;
-  const int kf = td.K1 - 6, kb = td.K1 - 5;  // K rows of the a-part pad dimensions DP-2, DP-1 in the interleaved order
+  // K rows of the one-hot: the a-part pad dimensions DP-2, DP-1 in the interleaved order (biasg 1), or the first two rows of
+  // a K step of its own behind the net input (biasg 2: that step holds nothing else)
+  const int kf = td.biasg == 2 ? td.K1 : td.K1 - 6, kb = kf + 1;
   auto embed_w = [&](int k, int n) -> float {
     if (n >= H) return 0.f;
     const int d = 4 * (k / 8) + (k & 3);
@@ -439,7 +449,7 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
     for (int t = 0; t < T; ++t) {
       std::vector<float> one;
       append_b_stream(one, 8, td.N1, [&](int kk, int n) -> float {
-        const int k = td.K1 - 8 + kk;
+        const int k = (td.biasg == 2 ? td.K1 : td.K1 - 8) + kk;
         if (k == kf) return n < H ? tb_at(t, n) : (n == H ? 1.f : 0.f);
         if (k == kb) return n < H ? tb_at(T - 1 - t, n) : (n == H ? 1.f : 0.f);
         return embed_w(k, n);
@@ -473,13 +483,13 @@ static int tc_pack_net(l2hmc_ctx *ctx, int net_id, const l2hmc_net_params *p) {
     }
     nstream_h = img_h.size();
     if (biasg) {
-      const int k0 = (td.K1 - 1) / 16 * 16;  // first k of the embed's last K = 16 step
+      const int k0 = td.biasg == 2 ? td.K1 : (td.K1 - 1) / 16 * 16;  // first k of the embed's last K = 16 step
       for (int t = 0; t < T; ++t)
         wmax = fmaxf(wmax, append_b_stream_f16(img_h, 16, td.N1, [&](int kk, int n) -> float {
           const int k = k0 + kk;
-          if (k >= td.K1) return 0.f;
           if (k == kf) return n < H ? tb_at(t, n) : (n == H ? 1.f : 0.f);
           if (k == kb) return n < H ? tb_at(T - 1 - t, n) : (n == H ? 1.f : 0.f);
+          if (k >= td.K1) return 0.f;
           return embed_w(k, n);
         }));
     }
@@ -1180,8 +1190,12 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
         L2HMC_TC_S_ATTR(13, 13, false, false, true); L2HMC_TC_S_ATTR(13, 13, false, false, false);
         L2HMC_TC_S_ATTR(8, 13, true, false, true); L2HMC_TC_S_ATTR(8, 13, true, false, false);
         L2HMC_TC_S_ATTR(8, 13, false, false, true); L2HMC_TC_S_ATTR(8, 13, false, false, false);
+        L2HMC_TC_S_ATTR(8, 13, true, true, true); L2HMC_TC_S_ATTR(8, 13, true, true, false);
+        L2HMC_TC_S_ATTR(8, 13, false, true, true); L2HMC_TC_S_ATTR(8, 13, false, true, false);
         L2HMC_TC_S_ATTR(0, 0, true, false, true); L2HMC_TC_S_ATTR(0, 0, true, false, false);
         L2HMC_TC_S_ATTR(0, 0, false, false, true); L2HMC_TC_S_ATTR(0, 0, false, false, false);
+        L2HMC_TC_S_ATTR(0, 0, true, true, true); L2HMC_TC_S_ATTR(0, 0, true, true, false);
+        L2HMC_TC_S_ATTR(0, 0, false, true, true); L2HMC_TC_S_ATTR(0, 0, false, true, false);
 #undef L2HMC_TC_S_ATTR
         tc_s_configured = smem;
       }
@@ -1206,13 +1220,21 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
           else { if (h16) L2HMC_TC_S_LAUNCH(13, 13, false, false, true); else L2HMC_TC_S_LAUNCH(13, 13, false, false, false); }
         }
       } else if (nqc == 8 && nhc == 13) {
-        if (bg) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: no bias-in-GEMM instantiation for this shape");
-        if (fm) { if (h16) L2HMC_TC_S_LAUNCH(8, 13, true, false, true); else L2HMC_TC_S_LAUNCH(8, 13, true, false, false); }
-        else { if (h16) L2HMC_TC_S_LAUNCH(8, 13, false, false, true); else L2HMC_TC_S_LAUNCH(8, 13, false, false, false); }
+        if (bg) {
+          if (fm) { if (h16) L2HMC_TC_S_LAUNCH(8, 13, true, true, true); else L2HMC_TC_S_LAUNCH(8, 13, true, true, false); }
+          else { if (h16) L2HMC_TC_S_LAUNCH(8, 13, false, true, true); else L2HMC_TC_S_LAUNCH(8, 13, false, true, false); }
+        } else {
+          if (fm) { if (h16) L2HMC_TC_S_LAUNCH(8, 13, true, false, true); else L2HMC_TC_S_LAUNCH(8, 13, true, false, false); }
+          else { if (h16) L2HMC_TC_S_LAUNCH(8, 13, false, false, true); else L2HMC_TC_S_LAUNCH(8, 13, false, false, false); }
+        }
       } else {  // chunk counts read from the arguments
-        if (bg) return fail(ctx, L2HMC_EINVAL, "tensor-core kernel: no bias-in-GEMM instantiation for this shape");
-        if (fm) { if (h16) L2HMC_TC_S_LAUNCH(0, 0, true, false, true); else L2HMC_TC_S_LAUNCH(0, 0, true, false, false); }
-        else { if (h16) L2HMC_TC_S_LAUNCH(0, 0, false, false, true); else L2HMC_TC_S_LAUNCH(0, 0, false, false, false); }
+        if (bg) {
+          if (fm) { if (h16) L2HMC_TC_S_LAUNCH(0, 0, true, true, true); else L2HMC_TC_S_LAUNCH(0, 0, true, true, false); }
+          else { if (h16) L2HMC_TC_S_LAUNCH(0, 0, false, true, true); else L2HMC_TC_S_LAUNCH(0, 0, false, true, false); }
+        } else {
+          if (fm) { if (h16) L2HMC_TC_S_LAUNCH(0, 0, true, false, true); else L2HMC_TC_S_LAUNCH(0, 0, true, false, false); }
+          else { if (h16) L2HMC_TC_S_LAUNCH(0, 0, false, false, true); else L2HMC_TC_S_LAUNCH(0, 0, false, false, false); }
+        }
       }
 #undef L2HMC_TC_S_LAUNCH
     } else {

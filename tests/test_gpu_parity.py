@@ -613,3 +613,30 @@ def test_tc_run_time_shape_kernel(kind, D, H, T, monkeypatch):
     s1 = dyn._transition(x, dir_mode=3, do_mh=True, counter=5)
     s2 = dyn._transition(s1["x_next"], dir_mode=3, do_mh=True, counter=6)
     assert torch.equal(o3["x_next"], s2["x_next"])
+
+
+@pytest.mark.parametrize("f16", ["1", "0"])
+@pytest.mark.parametrize("kind,D,H,T", [("roughwell", 32, 100, 10), ("gaussian", 40, 100, 5), ("gaussian", 8, 100, 4), ("gaussian", 48, 50, 3),
+                                        ("gaussian", 30, 100, 4), ("roughwell", 18, 60, 5)])
+def test_tc_biases_in_the_gemms_on_every_shape_with_a_pad_hidden_unit(kind, D, H, T, f16, monkeypatch):
+    """Biases ride in the GEMMs (kernel_tc_s.cuh, BIASG) wherever the width leaves a pad hidden unit: the direction one-hot
+    that selects the time-embedding bias row sits in the pad dimensions of the last 4-dim chunk when x_dim leaves two
+    (config 2; here 30-d, 18-d), else in a K step of its own behind the net input (config 4's 32-d shape, 40-d, 8-d, 48-d).
+    Parity against the oracle on both operand splits, and agreement with the explicit-bias kernel (L2HMC_TC_BIASG=0) up
+    to the summation order -- the last bits differ, which proves that the other code path ran."""
+    kw = dict(mu=np.full(D, 0.3)) if kind == "gaussian" else dict(easy=True)
+    P = U.Problem(kind=kind, D=D, H=H, T=T, eps=0.1, regime="stress", **kw)
+    monkeypatch.setenv("L2HMC_TC_F16", f16)
+    monkeypatch.delenv("L2HMC_TC_BIASG", raising=False)
+    dyn = P.product(kernel="tc")
+    rep, (d, r64, r32, rk) = U.parity_report(P, 300, dyn=dyn)
+    assert dyn.kernel_name == ("tc_3xf16" if f16 == "1" else "tc_3xtf32")
+    _check(rep)
+    assert not dyn.fp16_range_exceeded()
+    monkeypatch.setenv("L2HMC_TC_BIASG", "0")
+    exp = U.run_kernel_propose(P, d, dyn=P.product(kernel="tc"))
+    monkeypatch.delenv("L2HMC_TC_BIASG", raising=False)
+    assert U.max_rel(exp["Lx"], rk["Lx"]) <= SAMPLE_TOL and U.max_rel(exp["Lv"], rk["Lv"]) <= SAMPLE_TOL
+    assert not np.array_equal(exp["Lx"], rk["Lx"])
+    # both directions in one batch were exercised (forward chains read tb[t], backward chains tb[T-1-t])
+    assert 0 < int(np.asarray(d["dir"]).sum()) < len(d["dir"])
