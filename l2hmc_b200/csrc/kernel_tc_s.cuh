@@ -55,12 +55,6 @@ constexpr int KSLOT_S = L2HMC_TC_KSLOT_S;
 #ifndef L2HMC_TC_SETMAXNREG
 #define L2HMC_TC_SETMAXNREG (L2HMC_TC_S_NQ > 2)  // the last warpgroup (MMA issuer, TMA producer, two idle warps) hands registers to the compute warpgroups
 #endif
-#ifndef L2HMC_TC_SPLIT_LAST
-#define L2HMC_TC_SPLIT_LAST 0  // hidden epilogues: an odd last 8-column chunk is shared by the two threads of a chain (4 columns each)
-#endif
-#ifndef L2HMC_TC_P0_PAIR
-#define L2HMC_TC_P0_PAIR 0  // heads epilogue, part 0 (state update only, nothing handed over): two chunks per step for the scheduler
-#endif
 static_assert(KSLOT_S % 2 == 0, "ring slot = whole A hand-over slots");
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
@@ -479,7 +473,7 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
     const int qd = warp >> 2;              // 0 .. NQ-1: this thread owns the chunks q = qd, qd + NQ, ... (warp-uniform)
     const uint32_t lb = ((uint32_t)(32 * (warp & 3))) << 16;
     const int qn = (NQC - qd + NQ - 1) / NQ;  // its 4-dim chunks: q = qd + NQ i, i < qn
-    const int hn_all = (NHC - qd + NQ - 1) / NQ;  // its 8-column hidden chunks: q = qd + NQ i, i < hn_all
+    const int hn = (NHC - qd + NQ - 1) / NQ;  // its 8-column hidden chunks: q = qd + NQ i, i < hn
     const long long gch = base + c;
     const bool gauss = A.en.kind == 0;
     float *xr = smem + L.xs + c * RS, *vr = smem + L.vs + c * RS, *gr = smem + L.gs + c * RS;
@@ -721,12 +715,6 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
       auto hidden_epilogue = [&](uint32_t acc, const float *__restrict__ bias, bool handover) {
         wait_acc();
         float h[2][8];
-        // SPLIT_LAST: with an odd chunk count one thread of the chain owns a chunk more than the other and the next GEMM's
-        // last K slot waits for it alone; shared, both finish half a chunk earlier
-        const bool split = L2HMC_TC_SPLIT_LAST && NQ == 2 && (NHC & 1) && handover;
-        const int hn = split ? NHC / 2 : hn_all;
-        float hl[4] = {0.f, 0.f, 0.f, 0.f};
-        if (split) tmem_ld4(lb + acc + 8 * (NHC - 1) + 4 * qd, hl);
         if (hn > 0) tmem_ld8(lb + acc + 8 * qd, h[0]);
         auto chunk = [&](int i, auto buf_c) {
           constexpr int B = decltype(buf_c)::value;
@@ -757,22 +745,7 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
           chunk(i, I0{});
           if (i + 1 < hn) chunk(i + 1, I1{});
         }
-        if (split) {  // columns 8 (NHC - 1) + 4 qd .. + 3 of the last chunk (loaded first: the waits above covered it)
-          const int q = NHC - 1;
-          float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (!BIASG) b = ldg4(bias + 8 * q + 4 * qd);
-          if (hn == 0) tmem_wait_ld();
-          float a[4];
-          if (BIASG) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) a[j] = fmaxf(hl[j], 0.f);
-          } else {
-            a[0] = fmaxf(hl[0] + b.x, 0.f); a[1] = fmaxf(hl[1] + b.y, 0.f); a[2] = fmaxf(hl[2] + b.z, 0.f); a[3] = fmaxf(hl[3] + b.w, 0.f);
-          }
-          put_a<F16, 4>(lb, 8 * q + 4 * qd, a, amax);
-          slot_done(q);
-        }
-        a_done(handover ? (split ? NHC + 1 : NHC) : 0);
+        a_done(handover ? NHC : 0);
       };
 
       // ---- heads epilogue + fused state update (utils/dynamics.py:121-155 / :166-199) + next A operand --------------
@@ -984,43 +957,10 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
           update(c, s4[B][0], t4[B][0], q4[B][0], ljl);
           finish(q, i, c);
         };
-        if (PART == 0 && L2HMC_TC_P0_PAIR) {
-          // part 0 hands nothing over (the A operand of its chunks is written in part 1), so the order and grouping of its
-          // chunks is free: two independent chunks per step give the scheduler twice the work in flight per warp
-          auto ld3 = [&](int q, int b) {
-            tmem_ld4(lb + cS + 4 * q, s4[b][0]);
-            tmem_ld4(lb + cT + 4 * q, t4[b][0]);
-            tmem_ld4(lb + cQ + 4 * q, q4[b][0]);
-          };
-          if (ib + 1 < ie) ld3(qd + NQ * (ib + 1), 1);
-#pragma unroll 1
-          for (int i = ib; i < ie; i += 2) {
-            const int q0 = qd + NQ * i, q1 = q0 + NQ;
-            if (i + 1 < ie) {
-              ChunkIn c0, c1;
-              load_in(q0, c0);
-              load_in(q1, c1);
-              tmem_wait_ld();
-              update(c0, s4[0][0], t4[0][0], q4[0][0], ljl);
-              update(c1, s4[1][0], t4[1][0], q4[1][0], ljl);
-              finish(q0, i, c0);
-              finish(q1, i + 1, c1);
-              if (i + 2 < ie) ld3(q0 + 2 * NQ, 0);
-              if (i + 3 < ie) ld3(q1 + 2 * NQ, 1);
-            } else {
-              ChunkIn c0;
-              load_in(q0, c0);
-              tmem_wait_ld();
-              update(c0, s4[0][0], t4[0][0], q4[0][0], ljl);
-              finish(q0, i, c0);
-            }
-          }
-        } else {
 #pragma unroll 1
         for (int i = ib; i < ie; i += 2) {
           chunk(i, I0{});
           if (i + 1 < ie) chunk(i + 1, I1{});
-        }
         }
         if (PART == 1) {
           if (MODE == 1 && next == NEXT_G && gauss) zero_gtail();  // before this warp's arrival on the last K step
