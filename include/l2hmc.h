@@ -291,7 +291,10 @@ int l2hmc_timing_enable(l2hmc_ctx *ctx, int on);
 int l2hmc_timing_read(l2hmc_ctx *ctx, double *avg_ms, int64_t *launches); /* synchronises */
 /* Phase accounting of the tensor-core kernel's CTA 0 in SM clock cycles (synchronises the device):
  * out[0] MMA issuer waiting for A operands, [1] waiting for TMA weight slabs, [2] issuer total,
- * [3] compute thread 0 waiting for accumulators, [4] compute thread 0 total, [5] GEMMs issued. n <= 8. */
+ * [3] compute thread 0 waiting for accumulators, [4] compute thread 0 total, [5] GEMMs issued; [8..22] per GEMM kind;
+ * [24 + 16 g + k] compute thread g in {0: first, 1: second thread of chain 0}: cycles working in epilogue kind k (0 embed,
+ * 1 hidden, 2 / 3 heads part 0 / 1 of the V net, 4 / 5 of the X net, 6 grad), [24 + 16 g + 8 + k] waiting for its accumulator
+ * (development builds with -DL2HMC_TC_PHASE_ACCOUNTING only; zeros otherwise). n <= 56. */
 int l2hmc_debug_counters(l2hmc_ctx *ctx, int64_t *out, int n);
 
 #ifdef __cplusplus

@@ -169,7 +169,7 @@ struct Sync {
 // Phase accounting of CTA 0 (clock64 cycles), read back through l2hmc_debug_counters():
 // [0] issuer: waiting for A operands (tensor pipe idle, compute warps busy)   [1] issuer: waiting for TMA data
 // [2] issuer: total   [3] compute thread 0: waiting for accumulators   [4] compute thread 0: total   [5] GEMMs issued
-__device__ long long g_tc_dbg[24];  // [8..12] wait-for-A per GEMM kind, [13..17] wait-for-TMA per kind, [18..22] GEMMs per kind (kernel_tc_s), [23] fp16 range flag
+__device__ long long g_tc_dbg[56];  // [8..12] wait-for-A per GEMM kind, [13..17] wait-for-TMA per kind, [18..22] GEMMs per kind (kernel_tc_s), [23] fp16 range flag
 
 // ---- the GEMM schedule, walked identically by the producer, the MMA issuer and (structurally) the compute warps
 // kind: 0 = grad (Gaussian), 1 = embed, 2 = hidden, 3 = heads ; net: 0 = X, 1 = V

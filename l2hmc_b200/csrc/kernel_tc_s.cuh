@@ -482,6 +482,15 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
     long long w_acc = 0;
     const long long t_begin = clock64();
+    // per epilogue kind (0 embed, 1 hidden, 2 / 3 heads part 0 / 1 of the V net, 4 / 5 of the X net, 6 grad): cycles spent
+    // working [k] and waiting for the accumulator [8 + k]; written by CTA 0, thread 0 (first thread of a chain) and thread 128
+    long long ph_c[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long ph_t0 = 0, ph_w0 = 0;
+#define L2HMC_PH_BEGIN() do { ph_t0 = clock64(); ph_w0 = w_acc; } while (0)
+#define L2HMC_PH_END(k) do { const long long dw_ = w_acc - ph_w0; ph_c[8 + (k)] += dw_; ph_c[(k)] += clock64() - ph_t0 - dw_; } while (0)
+#else
+#define L2HMC_PH_BEGIN() do {} while (0)
+#define L2HMC_PH_END(k) do {} while (0)
 #endif
     auto wait_acc = [&]() {
 #ifdef L2HMC_TC_PHASE_ACCOUNTING
@@ -1010,19 +1019,33 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
           const bool isv = (ni == 0 || ni == 3);
           const TcNet &N = isv ? A.vnet : A.xnet;
           const float *tb = N.tb + (size_t)trow * td.N1;
+          L2HMC_PH_BEGIN();
           hidden_epilogue(S_R1, tb, true);    // embed accumulator -> A of the hidden GEMM
+          L2HMC_PH_END(0);
+          L2HMC_PH_BEGIN();
           hidden_epilogue(S_R2, N.b4, true);  // hidden accumulator -> A of heads_a / heads_b
+          L2HMC_PH_END(1);
           if (isv) {
             const int next = ni == 0 ? NEXT_X1 : (it + 1 < sh.T ? NEXT_V : NEXT_NONE);
+            L2HMC_PH_BEGIN();
             heads_epilogue(I0{}, I0{}, 0, next, N, mrow);
+            L2HMC_PH_END(2);
+            L2HMC_PH_BEGIN();
             heads_epilogue(I0{}, I1{}, 0, next, N, mrow);
+            L2HMC_PH_END(3);
           } else {
             const int next = ni == 1 ? NEXT_X2 : NEXT_G;
+            L2HMC_PH_BEGIN();
             heads_epilogue(I1{}, I0{}, ni - 1, next, N, mrow);
+            L2HMC_PH_END(4);
+            L2HMC_PH_BEGIN();
             heads_epilogue(I1{}, I1{}, ni - 1, next, N, mrow);
+            L2HMC_PH_END(5);
             if (ni == 2 && gauss) {
               float dummy;
+              L2HMC_PH_BEGIN();
               grad_epilogue(S_R2, false, dummy);
+              L2HMC_PH_END(6);
             }
           }
         }
@@ -1093,7 +1116,11 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
       g_tc_dbg[3] = w_acc;
       g_tc_dbg[4] = clock64() - t_begin;
     }
+    if (blockIdx.x == 0 && (tid == 0 || tid == MT))
+      for (int k = 0; k < 16; ++k) g_tc_dbg[24 + (tid == 0 ? 0 : 16) + k] = ph_c[k];
 #endif
+#undef L2HMC_PH_BEGIN
+#undef L2HMC_PH_END
     // an A operand left the fp16 range (or was not finite): raise the CONTEXT's sticky status bit (pinned host-mapped word
     // the host polls without a device synchronisation; the library then stays on the tf32 split)
     if (F16 && !(amax < 60000.f)) {

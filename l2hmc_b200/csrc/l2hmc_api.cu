@@ -1744,10 +1744,10 @@ extern "C" const char *l2hmc_kernel_name(const l2hmc_ctx *ctx) {
 extern "C" int64_t l2hmc_launch_count(const l2hmc_ctx *ctx) { return ctx ? ctx->launches : 0; }
 
 extern "C" int l2hmc_debug_counters(l2hmc_ctx *ctx, int64_t *out, int n) {
-  if (!ctx || !out || n < 0 || n > 24) return fail(ctx, L2HMC_EINVAL, "l2hmc_debug_counters: bad argument");
+  if (!ctx || !out || n < 0 || n > 56) return fail(ctx, L2HMC_EINVAL, "l2hmc_debug_counters: bad argument");
   CUDA_TRY(ctx, cudaSetDevice(ctx->cfg.device));
   CUDA_TRY(ctx, cudaDeviceSynchronize());
-  long long h[24];
+  long long h[56];
   CUDA_TRY(ctx, cudaMemcpyFromSymbol(h, tc::g_tc_dbg, sizeof(h)));
   for (int i = 0; i < n; ++i) out[i] = (int64_t)h[i];
   return L2HMC_OK;

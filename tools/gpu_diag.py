@@ -74,9 +74,16 @@ def timing(kernel):
                   (name, n, P.T, dyn.kernel_name, ms, n * P.T / (ms * 1e-3), float(o["px"].mean())), flush=True)
             if dyn.kernel_name.startswith("tc"):
                 import ctypes as C
-                buf = (C.c_int64 * 24)()
-                dyn._chk(dyn._lib.l2hmc_debug_counters(dyn._ctx, buf, 24))
+                buf = (C.c_int64 * 56)()
+                dyn._chk(dyn._lib.l2hmc_debug_counters(dyn._ctx, buf, 56))
                 c = list(buf)
+                if sum(c[24:56]) > 0:   # kernel_tc_s.cuh, -DL2HMC_TC_PHASE_ACCOUNTING: compute threads per epilogue kind
+                    kn = ("embed", "hidden", "headsV_p0", "headsV_p1", "headsX_p0", "headsX_p1", "grad")
+                    calls = (4, 4, 2, 2, 2, 2, 1)   # per leapfrog step
+                    for g in (0, 1):
+                        o = 24 + 16 * g
+                        print("TCEPI   %-10s thread %d of a chain, cycles per call (work + wait for the accumulator): " % (name, g) + "  ".join(
+                            "%s %.0f+%.0f" % (kn[k], c[o + k] / (calls[k] * P.T), c[o + 8 + k] / (calls[k] * P.T)) for k in range(7)), flush=True)
                 if c[2] > 0 and c[4] > 0:
                     print("TCPHASE %-10s CTA0 cycles: issuer total=%d wait_A=%.1f%% wait_TMA=%.1f%% issue/MMA=%.1f%% | compute total=%d "
                           "wait_acc=%.1f%% | gemms=%d cycles/gemm=%.0f" %
