@@ -55,6 +55,10 @@ constexpr int KSLOT_S = L2HMC_TC_KSLOT_S;
 #ifndef L2HMC_TC_SETMAXNREG
 #define L2HMC_TC_SETMAXNREG (L2HMC_TC_S_NQ > 2)  // the last warpgroup (MMA issuer, TMA producer, two idle warps) hands registers to the compute warpgroups
 #endif
+#ifndef L2HMC_TC_RELU_PACK
+#define L2HMC_TC_RELU_PACK 1  // fp16 split: the relu of the hidden layers happens in the fp16 conversion (cvt.rn.relu.f16x2.f32), not before it
+
+#endif
 static_assert(KSLOT_S % 2 == 0, "ring slot = whole A hand-over slots");
 constexpr int NSUB_MAX = 8;  // sub-barriers of the A operand (one per K slot of 16 columns)
 constexpr int HC_PER_CHUNK = 28;  // floats per 4-dim chunk of TcNet::hc: bs2, bq2, n2cS, cS, n2cQ, cQ, bth (4 each)
@@ -111,6 +115,12 @@ __device__ __forceinline__ uint32_t pack_h2(float k_even, float k_odd) {  // low
   const __half2 h = __floats2half2_rn(k_even, k_odd);
   return *reinterpret_cast<const uint32_t *>(&h);
 }
+// the same with negative values clamped to +0 by the conversion itself (one F2FP.RELU instead of two FMNMX + F2FP)
+__device__ __forceinline__ uint32_t pack_h2_relu(float k_even, float k_odd) {
+  uint32_t r;
+  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(k_odd), "f"(k_even));
+  return r;
+}
 // tcgen05.mma kind::f16 (fp16 inputs, fp32 accumulate): D[tmem] (+)= A[tmem] * B[smem]^T, one K = 16 slice
 __host__ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);  // A / B format 0 = f16, D format 1 = f32
@@ -129,9 +139,13 @@ __device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uin
 //   tf32: hi = a with the 13 low mantissa bits cleared, lo = a - hi (see put_a4); one 32-bit column per k.
 //   fp16: the same hi (11 significant bits: exactly an fp16 inside its normal range) and lo, rounded to fp16 and packed
 //         two per column (column k / 2); amax tracks |a| for the range check (fp16 overflows at 65504).
-template <bool F16, int N>
+// RELU (fp16 only): the operand is relu(a).  hi = a & mask and lo = a - hi have the sign of a (|hi| <= |a|), so clamping both
+// halves at the conversion gives exactly the split of relu(a) -- no separate max(a, 0); amax then also sees the negative
+// pre-activations, which only makes the range check more conservative.
+template <bool F16, int N, bool RELU = false>
 __device__ __forceinline__ void put_a(uint32_t lane_base, int k0, const float (&a)[N], float &amax) {
   static_assert(N == 4 || N == 8, "4 or 8 values");
+  static_assert(!RELU || F16, "relu in the conversion: fp16 split only");
   float hi[N], lo[N];
 #pragma unroll
   for (int j = 0; j < N; j += 2) {
@@ -150,8 +164,8 @@ __device__ __forceinline__ void put_a(uint32_t lane_base, int k0, const float (&
     uint32_t h2[N / 2], l2[N / 2];
 #pragma unroll
     for (int j = 0; j < N / 2; ++j) {
-      h2[j] = pack_h2(hi[2 * j], hi[2 * j + 1]);
-      l2[j] = pack_h2(lo[2 * j], lo[2 * j + 1]);
+      h2[j] = RELU ? pack_h2_relu(hi[2 * j], hi[2 * j + 1]) : pack_h2(hi[2 * j], hi[2 * j + 1]);
+      l2[j] = RELU ? pack_h2_relu(lo[2 * j], lo[2 * j + 1]) : pack_h2(lo[2 * j], lo[2 * j + 1]);
       amax = fmaxf(amax, fmaxf(fabsf(a[2 * j]), fabsf(a[2 * j + 1])));
     }
     if (N == 8) {
@@ -737,14 +751,18 @@ __global__ void __launch_bounds__(TC_S_THREADS, 1) tc_transition_kernel_s(const 
           if (i + 1 < hn) tmem_ld8(lb + acc + 8 * (q + NQ), h[B ^ 1]);
           const float(&hh)[8] = h[B];
           float a[8];
+          constexpr bool RP = F16 && L2HMC_TC_RELU_PACK;  // relu folded into the fp16 conversion of put_a
           if (BIASG) {  // no `+ 0.f`: the compiler must keep that add (it turns -0 into +0)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = fmaxf(hh[j], 0.f);
+            for (int j = 0; j < 8; ++j) a[j] = RP ? hh[j] : fmaxf(hh[j], 0.f);
+          } else if (RP) {
+            a[0] = hh[0] + b0.x; a[1] = hh[1] + b0.y; a[2] = hh[2] + b0.z; a[3] = hh[3] + b0.w;
+            a[4] = hh[4] + b1.x; a[5] = hh[5] + b1.y; a[6] = hh[6] + b1.z; a[7] = hh[7] + b1.w;
           } else {
             a[0] = fmaxf(hh[0] + b0.x, 0.f); a[1] = fmaxf(hh[1] + b0.y, 0.f); a[2] = fmaxf(hh[2] + b0.z, 0.f); a[3] = fmaxf(hh[3] + b0.w, 0.f);
             a[4] = fmaxf(hh[4] + b1.x, 0.f); a[5] = fmaxf(hh[5] + b1.y, 0.f); a[6] = fmaxf(hh[6] + b1.z, 0.f); a[7] = fmaxf(hh[7] + b1.w, 0.f);
           }
-          put_a<F16, 8>(lb, 8 * q, a, amax);
+          put_a<F16, 8, RP>(lb, 8 * q, a, amax);
           if (handover) slot_done(q);
         };
         // two chunks per iteration (the register double buffer needs static names); rolled: the fully unrolled
