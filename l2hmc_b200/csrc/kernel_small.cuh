@@ -58,8 +58,26 @@ __device__ __forceinline__ void load_net(NetS<DM, HM> &s, const NetRaw &w, int D
   }
 }
 
+// exp / tanh of the updates.  FAST: ex2.approx + rcp.approx as in the tensor-core kernels' epilogues (abs error ~1e-7 for the O(1)
+// arguments here; tanhf / expf cost ~25 / ~8 instructions with branches, 32 calls per leapfrog step of a 2-d chain)
+__device__ __forceinline__ float sm_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <bool FAST>
+__device__ __forceinline__ float sm_exp(float x) {
+  return FAST ? sm_ex2(x * 1.4426950408889634f) : expf(x);
+}
+template <bool FAST>
+__device__ __forceinline__ float sm_tanh(float x) {
+  if (!FAST) return tanhf(x);
+  const float t = sm_ex2(x * 2.8853900817779268f);  // e^{2x}; inf gives 1 - 0, 0 gives 1 - 2
+  return 1.f - __fdividef(2.f, t + 1.f);
+}
+
 // [S, T, Q] = net([a, b, t]) with the time/bias row tb (already selected for this chain's direction)
-template <int DM, int HM>
+template <int DM, int HM, bool FAST>
 __device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb, const float (&a)[DM], const float (&b)[DM],
                                          float (&S)[DM], float (&T)[DM], float (&Q)[DM]) {
   float h1[HM], h2[HM];
@@ -96,8 +114,8 @@ __device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb,
   }
 #pragma unroll
   for (int d = 0; d < DM; ++d) {
-    S[d] = n.es[d] * tanhf(S[d]);
-    Q[d] = n.eq[d] * tanhf(Q[d]);
+    S[d] = n.es[d] * sm_tanh<FAST>(S[d]);
+    Q[d] = n.eq[d] * sm_tanh<FAST>(Q[d]);
   }
 }
 
@@ -111,7 +129,7 @@ __device__ __forceinline__ void grad_small(const EnergyDev &en, const Shape &sh,
   for (int d = 0; d < DM; ++d) g[d] = d < sh.D ? gl[d] : 0.f;
 }
 
-template <int DM, int HM>
+template <int DM, int HM, bool FAST>
 __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_constant__ SmallArgs A) {
   extern __shared__ __align__(16) float smem_small[];
   const Shape &sh = A.sh;
@@ -140,7 +158,7 @@ __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_const
   const long long g = (long long)blockIdx.x * NT + threadIdx.x;
   if (g >= io.n) return;
   const float eps = sh.eps;
-  float x[DM], v[DM], gr[DM], xin[DM];
+  float x[DM], v[DM], gr[DM];
 #pragma unroll
   for (int d = 0; d < DM; ++d) x[d] = d < D ? io.x[g * D + d] : 0.f;
 
@@ -195,64 +213,48 @@ __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_const
 
     for (int it = 0; it < T; ++it) {
       const int t = fwd ? it : T - 1 - it;
-      float S[DM], Tt[DM], Q[DM];
-      // ---- v half step ----
-      if (sh.hmc) {
-#pragma unroll
-        for (int d = 0; d < DM; ++d) S[d] = Tt[d] = Q[d] = 0.f;
-      } else {
-        net_eval(NV, tbv + t * HM, x, gr, S, Tt, Q);
-      }
-#pragma unroll
-      for (int d = 0; d < DM; ++d) {
-        const float sv = fwd ? (0.5f * eps) * S[d] : (-0.5f * eps) * S[d];
-        const float cterm = (0.5f * eps) * (-(expf(eps * Q[d]) * gr[d]) + Tt[d]);
-        const float e = expf(sv);
-        v[d] = fwd ? (v[d] * e + cterm) : ((v[d] - cterm) * e);
-        lj += sv;
-      }
-      // ---- two masked x updates ----
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        float k[DM];
+      // four sub-updates per leapfrog step: v half step, two masked x updates, v half step at the new x
+      // (utils/dynamics.py:115-157 / :159-201).  One rolled loop: a single copy of the net evaluation in the instruction
+      // stream (four inlined copies made a ~100 KB loop body and instruction fetch was 23 % of the stall samples).
+#pragma unroll 1
+      for (int call = 0; call < 4; ++call) {
+        const bool isv = call == 0 || call == 3;
+        if (call == 3) grad_small<DM>(A.en, sh, x, gr);
+        float S[DM], Tt[DM], Q[DM], k[DM], a[DM], b[DM];
 #pragma unroll
         for (int d = 0; d < DM; ++d) {
           const float m = msk[t * DM + d];
-          k[d] = (fwd == (half == 0)) ? m : 1.f - m;
-          xin[d] = k[d] * x[d];
+          k[d] = (fwd == (call == 1)) ? m : 1.f - m;  // used by the x updates only
+          a[d] = isv ? x[d] : v[d];
+          b[d] = isv ? gr[d] : k[d] * x[d];
         }
         if (sh.hmc) {
 #pragma unroll
           for (int d = 0; d < DM; ++d) S[d] = Tt[d] = Q[d] = 0.f;
         } else {
-          net_eval(NX, tbx + t * HM, v, xin, S, Tt, Q);
+          net_eval<DM, HM, FAST>(isv ? NV : NX, (isv ? tbv : tbx) + t * HM, a, b, S, Tt, Q);
         }
+        if (isv) {
 #pragma unroll
-        for (int d = 0; d < DM; ++d) {
-          const float uu = 1.f - k[d];
-          const float sx = fwd ? eps * S[d] : -eps * S[d];
-          const float inner = eps * (expf(eps * Q[d]) * v[d] + Tt[d]);
-          const float e = expf(sx);
-          const float nx = fwd ? (x[d] * e + inner) : (e * (x[d] - inner));
-          x[d] = k[d] * x[d] + uu * nx;
-          lj += uu * sx;
+          for (int d = 0; d < DM; ++d) {
+            const float sv = fwd ? (0.5f * eps) * S[d] : (-0.5f * eps) * S[d];
+            const float cterm = (0.5f * eps) * (-(sm_exp<FAST>(eps * Q[d]) * gr[d]) + Tt[d]);
+            const float e = sm_exp<FAST>(sv);
+            v[d] = fwd ? (v[d] * e + cterm) : ((v[d] - cterm) * e);
+            lj += sv;
+          }
+        } else {
+#pragma unroll
+          for (int d = 0; d < DM; ++d) {
+            const float uu = 1.f - k[d];
+            const float sx = fwd ? eps * S[d] : -eps * S[d];
+            const float inner = eps * (sm_exp<FAST>(eps * Q[d]) * v[d] + Tt[d]);
+            const float e = sm_exp<FAST>(sx);
+            const float nx = fwd ? (x[d] * e + inner) : (e * (x[d] - inner));
+            x[d] = k[d] * x[d] + uu * nx;
+            lj += uu * sx;
+          }
         }
-      }
-      // ---- v half step at the new x ----
-      grad_small<DM>(A.en, sh, x, gr);
-      if (sh.hmc) {
-#pragma unroll
-        for (int d = 0; d < DM; ++d) S[d] = Tt[d] = Q[d] = 0.f;
-      } else {
-        net_eval(NV, tbv + t * HM, x, gr, S, Tt, Q);
-      }
-#pragma unroll
-      for (int d = 0; d < DM; ++d) {
-        const float sv = fwd ? (0.5f * eps) * S[d] : (-0.5f * eps) * S[d];
-        const float cterm = (0.5f * eps) * (-(expf(eps * Q[d]) * gr[d]) + Tt[d]);
-        const float e = expf(sv);
-        v[d] = fwd ? (v[d] * e + cterm) : ((v[d] - cterm) * e);
-        lj += sv;
       }
     }
     if (sh.hmc) lj = 0.f;

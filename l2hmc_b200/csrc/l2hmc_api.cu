@@ -1274,10 +1274,15 @@ static int launch_transition(l2hmc_ctx *ctx, const l2hmc_transition_args *a, cud
     SA.mask = ctx->mask.p;
     SA.io = K.io;
     const unsigned blocks = (unsigned)((a->n + small::NT - 1) / small::NT);
+    // exp / tanh of the updates: ex2.approx / rcp.approx like the tensor-core epilogues (L2HMC_SMALL_FAST_MATH=0: expf / tanhf)
+    const char *sfm = getenv("L2HMC_SMALL_FAST_MATH");
+    const bool sfast = !(sfm && sfm[0] == '0');
     if (ctx->sh.D <= 2 && (ctx->sh.hmc || ctx->sh.H <= 10)) {
-      small::small_transition_kernel<2, 10><<<blocks, small::NT, small::small_smem_bytes<2, 10>(ctx->sh.T), stream>>>(SA);
+      if (sfast) small::small_transition_kernel<2, 10, true><<<blocks, small::NT, small::small_smem_bytes<2, 10>(ctx->sh.T), stream>>>(SA);
+      else small::small_transition_kernel<2, 10, false><<<blocks, small::NT, small::small_smem_bytes<2, 10>(ctx->sh.T), stream>>>(SA);
     } else {
-      small::small_transition_kernel<4, 16><<<blocks, small::NT, small::small_smem_bytes<4, 16>(ctx->sh.T), stream>>>(SA);
+      if (sfast) small::small_transition_kernel<4, 16, true><<<blocks, small::NT, small::small_smem_bytes<4, 16>(ctx->sh.T), stream>>>(SA);
+      else small::small_transition_kernel<4, 16, false><<<blocks, small::NT, small::small_smem_bytes<4, 16>(ctx->sh.T), stream>>>(SA);
     }
   } else if (kernel == L2HMC_KERNEL_TILE) {
     const size_t smem = tile::smem_bytes(ctx->sh.DP, ctx->sh.HP, ctx->sh.T);
