@@ -615,6 +615,21 @@ def test_tc_run_time_shape_kernel(kind, D, H, T, monkeypatch):
     assert torch.equal(o3["x_next"], s2["x_next"])
 
 
+@pytest.mark.parametrize("name,n", [("c1_scg2", 400), ("c3_mog2", 512)])
+def test_small_kernel_fast_and_libm_math_agree(name, n, monkeypatch):
+    """The one-chain-per-thread kernel evaluates exp / tanh of the updates with ex2.approx / rcp.approx (as the tensor-core
+    epilogues do); L2HMC_SMALL_FAST_MATH=0 selects expf / tanhf.  Both meet the parity bar, and they differ in the last
+    bits (which proves that the switch selects another instantiation)."""
+    P = U.Problem(regime="stress", **U.CONFIGS[name])
+    monkeypatch.delenv("L2HMC_SMALL_FAST_MATH", raising=False)
+    rep, (d, r64, r32, rk) = U.parity_report(P, n, dyn=P.product(kernel="small"))
+    _check(rep)
+    monkeypatch.setenv("L2HMC_SMALL_FAST_MATH", "0")
+    rep0, (_, _, _, rk0) = U.parity_report(P, n, dyn=P.product(kernel="small"))
+    _check(rep0)
+    assert U.max_rel(rk0["Lx"], rk["Lx"]) <= SAMPLE_TOL and not np.array_equal(rk0["Lx"], rk["Lx"])
+
+
 @pytest.mark.parametrize("f16", ["1", "0"])
 @pytest.mark.parametrize("kind,D,H,T", [("roughwell", 32, 100, 10), ("gaussian", 40, 100, 5), ("gaussian", 8, 100, 4), ("gaussian", 48, 50, 3),
                                         ("gaussian", 30, 100, 4), ("roughwell", 18, 60, 5)])
