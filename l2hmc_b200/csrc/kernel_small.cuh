@@ -232,7 +232,12 @@ __global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_const
 #pragma unroll
           for (int d = 0; d < DM; ++d) S[d] = Tt[d] = Q[d] = 0.f;
         } else {
-          net_eval<DM, HM, FAST>(isv ? NV : NX, (isv ? tbv : tbx) + t * HM, a, b, S, Tt, Q);
+          // ONE base address for the net of this sub-update, opaque to the compiler: with `isv ? NV : NX` it selected between
+          // the two nets at every weight load (two UIADD3 per LDS: 19 % of the executed instructions of an issue-bound kernel)
+          uint32_t noff = isv ? (uint32_t)sizeof(NetS<DM, HM>) : 0u;
+          asm volatile("" : "+r"(noff));
+          const NetS<DM, HM> &N = *reinterpret_cast<const NetS<DM, HM> *>(reinterpret_cast<const char *>(&NX) + noff);
+          net_eval<DM, HM, FAST>(N, (isv ? tbv : tbx) + t * HM, a, b, S, Tt, Q);
         }
         if (isv) {
 #pragma unroll
