@@ -76,6 +76,21 @@ __device__ __forceinline__ float sm_tanh(float x) {
   return 1.f - __fdividef(2.f, t + 1.f);
 }
 
+#ifndef L2HMC_SMALL_F32X2
+#define L2HMC_SMALL_F32X2 1  // packed fp32 FMAs (FFMA2, sm_100): two of the independent accumulators of a layer per instruction
+#endif
+// (h0, h1) += a * (w0, w1): the same two IEEE FMAs as fmaf, one issue slot (the kernel is bound by issue slots, not by the FMA pipe)
+__device__ __forceinline__ void fma_pair(float a, float w0, float w1, float &h0, float &h1) {
+#if L2HMC_SMALL_F32X2
+  const float2 r = __ffma2_rn(make_float2(a, a), make_float2(w0, w1), make_float2(h0, h1));
+  h0 = r.x;
+  h1 = r.y;
+#else
+  h0 = fmaf(a, w0, h0);
+  h1 = fmaf(a, w1, h1);
+#endif
+}
+
 // [S, T, Q] = net([a, b, t]) with the time/bias row tb (already selected for this chain's direction)
 template <int DM, int HM, bool FAST>
 __device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb, const float (&a)[DM], const float (&b)[DM],
@@ -83,10 +98,14 @@ __device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb,
   float h1[HM], h2[HM];
 #pragma unroll
   for (int j = 0; j < HM; ++j) h1[j] = tb[j];
+  static_assert(HM % 2 == 0 && DM % 2 == 0, "pairs of accumulators");
 #pragma unroll
   for (int d = 0; d < DM; ++d)
 #pragma unroll
-    for (int j = 0; j < HM; ++j) h1[j] = fmaf(b[d], n.W2[d][j], fmaf(a[d], n.W1[d][j], h1[j]));
+    for (int j = 0; j < HM; j += 2) {  // fmaf(b, W2, fmaf(a, W1, h1)) per element, as before
+      fma_pair(a[d], n.W1[d][j], n.W1[d][j + 1], h1[j], h1[j + 1]);
+      fma_pair(b[d], n.W2[d][j], n.W2[d][j + 1], h1[j], h1[j + 1]);
+    }
 #pragma unroll
   for (int j = 0; j < HM; ++j) {
     h1[j] = fmaxf(h1[j], 0.f);
@@ -95,7 +114,7 @@ __device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb,
 #pragma unroll
   for (int i = 0; i < HM; ++i)
 #pragma unroll
-    for (int j = 0; j < HM; ++j) h2[j] = fmaf(h1[i], n.W4[i][j], h2[j]);
+    for (int j = 0; j < HM; j += 2) fma_pair(h1[i], n.W4[i][j], n.W4[i][j + 1], h2[j], h2[j + 1]);
 #pragma unroll
   for (int d = 0; d < DM; ++d) {
     S[d] = n.bs[d];
@@ -106,10 +125,10 @@ __device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb,
   for (int i = 0; i < HM; ++i) {
     const float h = fmaxf(h2[i], 0.f);
 #pragma unroll
-    for (int d = 0; d < DM; ++d) {
-      S[d] = fmaf(h, n.Ws[i][d], S[d]);
-      T[d] = fmaf(h, n.Wt[i][d], T[d]);
-      Q[d] = fmaf(h, n.Wq[i][d], Q[d]);
+    for (int d = 0; d < DM; d += 2) {
+      fma_pair(h, n.Ws[i][d], n.Ws[i][d + 1], S[d], S[d + 1]);
+      fma_pair(h, n.Wt[i][d], n.Wt[i][d + 1], T[d], T[d + 1]);
+      fma_pair(h, n.Wq[i][d], n.Wq[i][d + 1], Q[d], Q[d + 1]);
     }
   }
 #pragma unroll
