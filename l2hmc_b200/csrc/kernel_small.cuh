@@ -140,6 +140,52 @@ __device__ __forceinline__ void net_eval(const NetS<DM, HM> &n, const float *tb,
 
 template <int DM>
 __device__ __forceinline__ void grad_small(const EnergyDev &en, const Shape &sh, const float (&x)[DM], float (&g)[DM]) {
+  // Gaussian and mixture targets inline, unrolled over the (at most DM) dimensions: the same operations in the same order as
+  // grad_one (common.cuh), without the call, the strided local arrays and the run-time dimension loops -- grad U is evaluated
+  // once per leapfrog step and the generic routine was ~10 % of the instructions of a step
+  const int D = sh.D;
+  if (en.kind == 0 || en.kind == 1) {
+    const float T = en.temperature;
+    const int ncomp = en.kind == 0 ? 1 : en.ncomp;
+    float V[MAX_COMP];
+    float mx = -INFINITY, s = 0.f;
+    if (en.kind == 1) {
+      for (int c = 0; c < ncomp; ++c) {
+        const float *mu = en.mu + c * sh.DP;
+        const float *S = en.Ssym + (size_t)c * sh.DP * sh.LDS;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < DM; ++j) {
+          float r = 0.f;
+#pragma unroll
+          for (int i = 0; i < DM; ++i)
+            if (i < D && j < D) r = fmaf(x[i] - mu[i], S[i * sh.LDS + j], r);
+          if (j < D) q = fmaf(r, x[j] - mu[j], q);
+        }
+        V[c] = -0.5f * q + en.logc[c];
+        mx = fmaxf(mx, V[c]);
+      }
+      for (int c = 0; c < ncomp; ++c) {
+        V[c] = expf(V[c] - mx);
+        s += V[c];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < DM; ++j) {
+      float acc = 0.f;
+      for (int c = 0; c < ncomp; ++c) {
+        const float *mu = en.mu + c * sh.DP;
+        const float *S = en.Ssym + (size_t)c * sh.DP * sh.LDS;
+        float r = 0.f;
+#pragma unroll
+        for (int i = 0; i < DM; ++i)
+          if (i < D && j < D) r = fmaf(x[i] - mu[i], S[i * sh.LDS + j], r);
+        acc = en.kind == 0 ? r : fmaf(V[c] / s, r, acc);
+      }
+      g[j] = j < D ? acc / T : 0.f;
+    }
+    return;
+  }
   float xs[DM], gl[DM];
 #pragma unroll
   for (int d = 0; d < DM; ++d) { xs[d] = x[d]; gl[d] = 0.f; }
