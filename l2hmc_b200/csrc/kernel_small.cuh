@@ -194,8 +194,11 @@ __device__ __forceinline__ void grad_small(const EnergyDev &en, const Shape &sh,
   for (int d = 0; d < DM; ++d) g[d] = d < sh.D ? gl[d] : 0.f;
 }
 
+#ifndef L2HMC_SMALL_MINBLOCKS
+#define L2HMC_SMALL_MINBLOCKS 6  // resident CTAs per SM the compiler leaves registers for (measured: 1 -> 0.189 / 0.707 ms, 6 -> 0.171 / 0.565, 8 -> 0.176 / 0.559 on configs 1 / 3)
+#endif
 template <int DM, int HM, bool FAST>
-__global__ void __launch_bounds__(NT) small_transition_kernel(const __grid_constant__ SmallArgs A) {
+__global__ void __launch_bounds__(NT, L2HMC_SMALL_MINBLOCKS) small_transition_kernel(const __grid_constant__ SmallArgs A) {
   extern __shared__ __align__(16) float smem_small[];
   const Shape &sh = A.sh;
   const TransitionIO &io = A.io;
