@@ -45,7 +45,8 @@ struct TcDims {
   int fast_math;    // 1: ex2/rcp based exp and tanh in the epilogue (abs error ~1e-7)
   int nq;           // compute threads per chain (2 or 4) -> which instantiation the host launches
   int f16;          // kernel_tc_s: fp16 split instead of tf32 (all operands inside the fp16 range)
-  int biasg;        // kernel_tc_s: biases ride in the GEMMs (weight rows that meet constant-1 / one-hot A columns)
+  int biasg;        // kernel_tc_s: biases ride in the GEMMs (weight rows that meet constant-1 / one-hot A columns): 0 no,
+                    // 1 one-hot in the two pad dimensions of the last 4-dim chunk, 2 one-hot in a K step of its own (no pad dimensions)
 };
 
 struct TcNet {

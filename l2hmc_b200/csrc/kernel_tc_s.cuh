@@ -16,8 +16,11 @@
 //   * the A operand of the NEXT GEMM (net input [a | b], or x - mu for the Gaussian grad) is produced inside the
 //     heads / grad epilogue from values still in registers: no separate pass over the state;
 //   * one mbarrier arrival per warp (count 8) instead of one per thread (count 256);
-//   * biases ride in the GEMMs where the shape has pad rows (BIASG): a constant-1 hidden unit, and a direction one-hot in
-//     the net input that selects the time-embedding bias row of the chain's leapfrog step;
+//   * biases ride in the GEMMs where the width leaves a pad hidden unit (BIASG): a constant-1 hidden unit, and a direction
+//     one-hot in the net input that selects the time-embedding bias row of the chain's leapfrog step -- in the two pad
+//     dimensions of the last chunk where x_dim leaves them (td.biasg 1), else in a K step of its own (td.biasg 2);
+//   * fp16 split: the relu of the two hidden layers happens inside the fp16 conversion of the operand split
+//     (cvt.rn.relu.f16x2.f32 on hi = a & mask and lo = a - hi, which carry the sign of a): no separate max(a, 0);
 //   * the epilogue of GEMM k and the MMAs of GEMM k+1 overlap: three accumulator regions in TMEM, the A operand
 //     handed over in slots of 16 k (the chunks i of both threads of a chain) through sub-barriers a_sub[0..NSUB),
 //     chunks owned round-robin by the two threads of a chain so that they complete in K order, and the net input
